@@ -1,0 +1,215 @@
+/*
+ * wbx_b200.h -- C ABI of libwbx_b200.so, the B200 (sm_100a) engine behind the
+ * WeatherBench-X statistic + aggregation hot path.
+ *
+ * The reference (/root/reference/weatherbenchX) has no FFI of its own: the
+ * plug-in surface is the Python ABCs Statistic / Aggregator.  Each entry
+ * point below names the reference interface it replaces (file:line relative
+ * to /root/reference/weatherbenchX).  INTEGRATION.md shows the ctypes binding
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns an int status: WBX_OK (0) or a negative
+ *    WBX_ERR_*; wbx_last_error() gives a thread-local message.  Nothing here
+ *    aborts the process.
+ *  - plain pointers and sizes only; no torch / CUDA types in signatures
+ *    (streams are passed as void*).
+ *  - the library never frees or writes caller input memory.  Results are
+ *    written into caller-provided buffers.
+ *  - "space" says whether field pointers are device (HBM) addresses or host
+ *    addresses.  Host-space calls stream the slabs host->device inside the
+ *    call (pinned memory recommended: wbx_host_alloc / wbx_host_register).
+ *  - all field data is float32, masks are uint8 (0 = masked out), weights and
+ *    results are float64.
+ */
+#ifndef WBX_B200_H_
+#define WBX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WBX_ABI_VERSION 1
+
+enum {
+  WBX_OK = 0,
+  WBX_ERR_INVALID = -1,     /* bad argument / inconsistent descriptor        */
+  WBX_ERR_CUDA = -2,        /* a CUDA runtime call failed                    */
+  WBX_ERR_NOMEM = -3,       /* host or device allocation failed              */
+  WBX_ERR_UNSUPPORTED = -4, /* valid request the engine cannot serve         */
+  WBX_ERR_NO_DEVICE = -5    /* no usable CUDA device                         */
+};
+
+enum { WBX_SPACE_DEVICE = 0, WBX_SPACE_HOST = 1 };
+
+/* Aggregator NaN / mask modes (aggregation.py:337-357). */
+enum {
+  WBX_FLAG_SKIPNA = 1, /* Aggregator(skipna=True): NaN statistic == masked   */
+  WBX_FLAG_MASKED = 2, /* Aggregator(masked=True) with a 'mask' coordinate   */
+  WBX_FLAG_FORCE_LDG = 16, /* tuning/debug: bypass the TMA ring              */
+  WBX_FLAG_FORCE_TMA = 32  /* tuning/debug: fail instead of falling back     */
+};
+
+/* Slots of the fused deterministic statistics (unique_name in comments). */
+enum {
+  WBX_STAT_ERROR = 0,        /* 'Error'            deterministic.py:94-100   */
+  WBX_STAT_ABS_ERROR = 1,    /* 'AbsoluteError'    deterministic.py:106-112  */
+  WBX_STAT_SQ_ERROR = 2,     /* 'SquaredError'     deterministic.py:118-123  */
+  WBX_STAT_SQ_PRED_ANOM = 3, /* 'SquaredPredictionAnomaly'  :225-232         */
+  WBX_STAT_SQ_TGT_ANOM = 4,  /* 'SquaredTargetAnomaly'      :238-245         */
+  WBX_STAT_ANOM_COV = 5,     /* 'AnomalyCovariance'         :251-259         */
+  WBX_NUM_DET_STATS = 6
+};
+/* sum_weights classes: statistics that share a NaN pattern share a class.
+ * class 0: Error/AbsoluteError/SquaredError, 1: SqPredAnom, 2: SqTgtAnom,
+ * 3: AnomCov.  Without SKIPNA all four classes hold the same value. */
+#define WBX_NUM_DET_WCLASSES 4
+
+typedef struct wbx_ctx wbx_ctx;
+typedef struct wbx_det_plan wbx_det_plan;
+
+/* ---- library / context ------------------------------------------------- */
+
+int wbx_abi_version(void);
+const char* wbx_last_error(void);
+
+/* One context per (process, device).  Owns a stream, scratch and staging
+ * buffers.  Calls on one context are serialised by the caller. */
+int wbx_ctx_create(int device, wbx_ctx** out);
+int wbx_ctx_destroy(wbx_ctx* ctx);
+/* Run subsequent work on this cudaStream_t (NULL = the context's own). */
+int wbx_ctx_set_stream(wbx_ctx* ctx, void* cuda_stream);
+int wbx_ctx_synchronize(wbx_ctx* ctx);
+/* sm_count, total HBM bytes, number of kernels launched by this context so
+ * far (any pointer may be NULL). */
+int wbx_ctx_info(wbx_ctx* ctx, int* sm_count, uint64_t* hbm_bytes,
+                 uint64_t* kernel_launches);
+/* Staging budget (bytes of HBM) used by host-space calls; default 1 GiB. */
+int wbx_ctx_set_staging_bytes(wbx_ctx* ctx, uint64_t bytes);
+
+/* Pinned host memory helpers. */
+int wbx_host_alloc(size_t bytes, void** out);
+int wbx_host_free(void* ptr);
+int wbx_host_register(void* ptr, size_t bytes);
+int wbx_host_unregister(void* ptr);
+
+/* ---- fused deterministic statistics + weighted aggregation ------------- *
+ *
+ * Replaces, in one pass over predictions/targets[/climatology]:
+ *   PerVariableStatistic.compute           metrics/base.py:184-197
+ *   Error / AbsoluteError / SquaredError   metrics/deterministic.py:94-123
+ *   SquaredPredictionAnomaly / SquaredTargetAnomaly / AnomalyCovariance
+ *                                          metrics/deterministic.py:225-259
+ *   (climatology gather)                   metrics/base.py:375-406
+ *   Aggregator.aggregate_stat_var          aggregation.py:337-366
+ *   Aggregator.aggregation_fn (xr.dot)     aggregation.py:297-335
+ *
+ * Work is described as "jobs": job j is one contiguous slab of ny*nx float32
+ * values of each operand (the trailing dims of the field that are all
+ * reduced, e.g. latitude x longitude), found at pred[j] / target[j] /
+ * clim[j] / mask[j].  All reduced leading dims, broadcasting and the
+ * climatology (dayofyear, hour) gather are expressed by the caller through
+ * these per-job addresses.  Job j contributes to output cell cell[j] with
+ * weight  w_outer[j] * w_y[y] * w_x[x]  (missing factors = 1).  cell[] must
+ * be non-decreasing and cover 0..n_cells-1.
+ *
+ * Results (float64):
+ *   sum_ws[c*6 + s] = sum over jobs in cell c, y, x of  valid * stat_s * w
+ *   sum_w [c*4 + k] = sum over jobs in cell c, y, x of  valid_k * w
+ * where valid follows the Aggregator rules: all ones by default (NaN then
+ * propagates into sum_ws), the mask operand when MASKED, ~isnan(stat) when
+ * SKIPNA.  Statistics 3..5 are only meaningful when clim != NULL.
+ */
+typedef struct {
+  int32_t space;      /* WBX_SPACE_* of pred/target/clim/mask addresses      */
+  int32_t flags;      /* WBX_FLAG_*                                          */
+  int64_t n_jobs;
+  int64_t ny, nx;     /* slab shape; nx is the contiguous axis               */
+  int64_t n_cells;
+  const uint64_t* pred;    /* [n_jobs] slab addresses                        */
+  const uint64_t* target;  /* [n_jobs]                                       */
+  const uint64_t* clim;    /* [n_jobs] or NULL                               */
+  const uint64_t* mask;    /* [n_jobs] uint8 slabs, or NULL (needs MASKED)   */
+  const int32_t* cell;     /* [n_jobs] non-decreasing                        */
+  const double* w_outer;   /* [n_jobs] or NULL                               */
+  const double* w_y;       /* [ny] or NULL                                   */
+  const double* w_x;       /* [nx] or NULL                                   */
+} wbx_det_desc;
+
+/* Upload the job tables once; the plan can then be run many times (the field
+ * buffers it points at may be refilled between runs). */
+int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* desc,
+                        wbx_det_plan** out);
+int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan);
+/* out_space: where sum_ws [n_cells*6] / sum_w [n_cells*4] live.  With
+ * WBX_SPACE_DEVICE the call is asynchronous on the context stream; with
+ * WBX_SPACE_HOST it returns after the results are in the host buffers.
+ * accumulate != 0 adds into the output buffers (AggregationState.__add__,
+ * aggregation.py:84-110) instead of overwriting them (device out only). */
+int wbx_det_plan_run(wbx_ctx* ctx, wbx_det_plan* plan, double* sum_ws,
+                     double* sum_w, int32_t out_space, int32_t accumulate);
+/* One-shot convenience: create + run (host outputs) + destroy. */
+int wbx_det_reduce(wbx_ctx* ctx, const wbx_det_desc* desc, double* sum_ws,
+                   double* sum_w);
+
+/* Per-gridpoint statistic values (what Statistic.compute returns when a
+ * caller really wants the full field, metrics/base.py:135-158).  n float32
+ * elements, device pointers, contiguous; clim may be NULL for stats 0..2.
+ * Bit-identical to NumPy float32 arithmetic. */
+int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
+                        const float* target, const float* clim, int64_t n,
+                        float* out);
+
+/* ---- generic strided statistic + weighted aggregation ------------------ *
+ *
+ * Same contract as the fused path (Aggregator.aggregate_stat_var,
+ * aggregation.py:337-366, including bin masks aggregation.py:320-335) for
+ * everything the slab kernel cannot express: arbitrary dim order / strides,
+ * broadcasting inside the reduced dims, multi-dimensional weights, bin masks,
+ * already materialised statistics.  Correct for any layout; coalescing (and so
+ * speed) depends on the layout.  All pointers are device pointers.
+ *
+ * The iteration space has `ndim` dims of extent size[d]; dims with
+ * reduced[d] != 0 are summed.  Every operand gives an element stride per dim
+ * (0 = broadcast).  value = op < 0 ? a[...] : stat_op(a[...], b[...], c[...]);
+ * valid = (mask ? mask[...] != 0 : 1) && (SKIPNA ? !isnan(value) : 1);
+ * f = prod_k factor_k[...];
+ *   sum_ws[cell] = sum valid ? value * f : 0      sum_w[cell] = sum valid * f
+ * Output cells are the row-major flattening of the non-reduced dims in dim
+ * order.  Bin dims are ordinary non-reduced dims on which a/b/c have stride 0.
+ */
+#define WBX_MAX_DIMS 8
+#define WBX_MAX_FACTORS 6
+enum { WBX_DTYPE_F64 = 0, WBX_DTYPE_F32 = 1, WBX_DTYPE_U8 = 2 };
+
+typedef struct {
+  int32_t ndim;
+  int32_t op;        /* -1: `a` is the statistic itself; else WBX_STAT_*      */
+  int32_t flags;     /* WBX_FLAG_SKIPNA (MASKED is implied by mask != NULL)   */
+  int32_t n_factors;
+  int64_t size[WBX_MAX_DIMS];
+  int32_t reduced[WBX_MAX_DIMS];
+  const float* a;
+  int64_t a_stride[WBX_MAX_DIMS];
+  const float* b;    /* targets (op >= 0)                                     */
+  int64_t b_stride[WBX_MAX_DIMS];
+  const float* c;    /* aligned climatology (op >= 3) or NULL                 */
+  int64_t c_stride[WBX_MAX_DIMS];
+  const uint8_t* mask;
+  int64_t mask_stride[WBX_MAX_DIMS];
+  const void* factor[WBX_MAX_FACTORS];
+  int32_t factor_dtype[WBX_MAX_FACTORS];
+  int64_t factor_stride[WBX_MAX_FACTORS][WBX_MAX_DIMS];
+} wbx_generic_desc;
+
+/* sum_ws / sum_w: float64 [n_cells] each, in out_space (device: async). */
+int wbx_reduce_generic(wbx_ctx* ctx, const wbx_generic_desc* desc,
+                       double* sum_ws, double* sum_w, int32_t out_space);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WBX_B200_H_ */

@@ -1,0 +1,301 @@
+"""ctypes binding of libwbx_b200.so (the C ABI declared in include/wbx_b200.h).
+
+The library is loaded lazily, once per process; contexts are cached per
+(process, device).  Nothing here is stored on Metric / Aggregator instances, so
+those stay picklable (Beam pickles them, beam_pipeline.py:150-159).
+
+There is deliberately no CPU fallback: if the shared library is missing or no
+B200 is visible, the calls raise.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import (POINTER, c_char_p, c_double, c_int, c_int32, c_int64,
+                    c_size_t, c_uint64, c_void_p)
+
+import numpy as np
+
+from weatherbenchx_b200 import _build
+
+WBX_OK = 0
+SPACE_DEVICE, SPACE_HOST = 0, 1
+FLAG_SKIPNA, FLAG_MASKED, FLAG_FORCE_LDG, FLAG_FORCE_TMA = 1, 2, 16, 32
+NUM_DET_STATS = 6
+NUM_DET_WCLASSES = 4
+STAT_SLOT = {
+    'Error': 0,
+    'AbsoluteError': 1,
+    'SquaredError': 2,
+    'SquaredPredictionAnomaly': 3,
+    'SquaredTargetAnomaly': 4,
+    'AnomalyCovariance': 5,
+}
+# sum_weights class of each statistic slot (see wbx_b200.h).
+STAT_WCLASS = {0: 0, 1: 0, 2: 0, 3: 1, 4: 2, 5: 3}
+
+_ERR_NAMES = {
+    -1: 'WBX_ERR_INVALID', -2: 'WBX_ERR_CUDA', -3: 'WBX_ERR_NOMEM',
+    -4: 'WBX_ERR_UNSUPPORTED', -5: 'WBX_ERR_NO_DEVICE',
+}
+
+
+class WbxError(RuntimeError):
+  """A libwbx_b200 call failed."""
+
+  def __init__(self, code: int, message: str):
+    super().__init__(f'{_ERR_NAMES.get(code, code)}: {message}')
+    self.code = code
+
+
+class DetDesc(ctypes.Structure):
+  """Mirror of wbx_det_desc."""
+  _fields_ = [
+      ('space', c_int32), ('flags', c_int32),
+      ('n_jobs', c_int64), ('ny', c_int64), ('nx', c_int64),
+      ('n_cells', c_int64),
+      ('pred', POINTER(c_uint64)), ('target', POINTER(c_uint64)),
+      ('clim', POINTER(c_uint64)), ('mask', POINTER(c_uint64)),
+      ('cell', POINTER(c_int32)),
+      ('w_outer', POINTER(c_double)), ('w_y', POINTER(c_double)),
+      ('w_x', POINTER(c_double)),
+  ]
+
+
+MAX_DIMS = 8
+MAX_FACTORS = 6
+DTYPE_F64, DTYPE_F32, DTYPE_U8 = 0, 1, 2
+
+
+class GenericDesc(ctypes.Structure):
+  """Mirror of wbx_generic_desc."""
+  _fields_ = [
+      ('ndim', c_int32), ('op', c_int32), ('flags', c_int32),
+      ('n_factors', c_int32),
+      ('size', c_int64 * MAX_DIMS), ('reduced', c_int32 * MAX_DIMS),
+      ('a', c_void_p), ('a_stride', c_int64 * MAX_DIMS),
+      ('b', c_void_p), ('b_stride', c_int64 * MAX_DIMS),
+      ('c', c_void_p), ('c_stride', c_int64 * MAX_DIMS),
+      ('mask', c_void_p), ('mask_stride', c_int64 * MAX_DIMS),
+      ('factor', c_void_p * MAX_FACTORS),
+      ('factor_dtype', c_int32 * MAX_FACTORS),
+      ('factor_stride', (c_int64 * MAX_DIMS) * MAX_FACTORS),
+  ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/wbx_b200.h.
+SIGNATURES = {
+    'wbx_abi_version': (c_int, []),
+    'wbx_last_error': (c_char_p, []),
+    'wbx_ctx_create': (c_int, [c_int, POINTER(c_void_p)]),
+    'wbx_ctx_destroy': (c_int, [c_void_p]),
+    'wbx_ctx_set_stream': (c_int, [c_void_p, c_void_p]),
+    'wbx_ctx_synchronize': (c_int, [c_void_p]),
+    'wbx_ctx_info': (c_int, [c_void_p, POINTER(c_int), POINTER(c_uint64),
+                             POINTER(c_uint64)]),
+    'wbx_ctx_set_staging_bytes': (c_int, [c_void_p, c_uint64]),
+    'wbx_host_alloc': (c_int, [c_size_t, POINTER(c_void_p)]),
+    'wbx_host_free': (c_int, [c_void_p]),
+    'wbx_host_register': (c_int, [c_void_p, c_size_t]),
+    'wbx_host_unregister': (c_int, [c_void_p]),
+    'wbx_det_plan_create': (c_int, [c_void_p, POINTER(DetDesc),
+                                    POINTER(c_void_p)]),
+    'wbx_det_plan_destroy': (c_int, [c_void_p, c_void_p]),
+    'wbx_det_plan_run': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int32, c_int32]),
+    'wbx_det_reduce': (c_int, [c_void_p, POINTER(DetDesc), c_void_p,
+                               c_void_p]),
+    'wbx_det_elementwise': (c_int, [c_void_p, c_int32, c_void_p, c_void_p,
+                                    c_void_p, c_int64, c_void_p]),
+    'wbx_reduce_generic': (c_int, [c_void_p, POINTER(GenericDesc), c_void_p,
+                                   c_void_p, c_int32]),
+}
+
+_lock = threading.Lock()
+_lib = None
+_lib_pid = None
+_contexts: dict = {}
+
+
+def library_path() -> str:
+  return os.environ.get('WBX_B200_LIBRARY', str(_build.LIB_PATH))
+
+
+def load_library():
+  """Loads (once per process) and returns the ctypes CDLL."""
+  global _lib, _lib_pid
+  with _lock:
+    if _lib is not None and _lib_pid == os.getpid():
+      return _lib
+    path = library_path()
+    if not os.path.exists(path):
+      raise RuntimeError(
+          f'{path} not found. Build it with `python -c "import '
+          '__graft_entry__ as g; g.build()"` (needs nvcc). There is no CPU '
+          'fallback for the statistic/aggregation kernels.')
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+      fn = getattr(lib, name)  # AttributeError if the symbol is missing
+      fn.restype = restype
+      fn.argtypes = argtypes
+    abi = lib.wbx_abi_version()
+    if abi != 1:
+      raise RuntimeError(f'libwbx_b200 ABI {abi} != 1')
+    _lib, _lib_pid = lib, os.getpid()
+    _contexts.clear()
+    return lib
+
+
+def check(code: int):
+  if code != WBX_OK:
+    msg = load_library().wbx_last_error()
+    raise WbxError(code, msg.decode() if msg else '')
+
+
+class Context:
+  """Owns one wbx_ctx (a device, a stream, scratch + staging buffers)."""
+
+  def __init__(self, device: int = 0):
+    self.lib = load_library()
+    handle = c_void_p()
+    check(self.lib.wbx_ctx_create(device, ctypes.byref(handle)))
+    self.handle = handle
+    self.device = device
+    sm = c_int()
+    hbm = c_uint64()
+    check(self.lib.wbx_ctx_info(self.handle, ctypes.byref(sm),
+                                ctypes.byref(hbm), None))
+    self.sm_count = sm.value
+    self.hbm_bytes = hbm.value
+
+  def close(self):
+    if self.handle:
+      self.lib.wbx_ctx_destroy(self.handle)
+      self.handle = None
+
+  def set_stream(self, cuda_stream: int | None):
+    check(self.lib.wbx_ctx_set_stream(self.handle, c_void_p(cuda_stream or 0)))
+
+  def use_torch_stream(self):
+    import torch  # pylint: disable=g-import-not-at-top
+    self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+  def synchronize(self):
+    check(self.lib.wbx_ctx_synchronize(self.handle))
+
+  def kernel_launches(self) -> int:
+    n = c_uint64()
+    check(self.lib.wbx_ctx_info(self.handle, None, None, ctypes.byref(n)))
+    return n.value
+
+  def set_staging_bytes(self, nbytes: int):
+    check(self.lib.wbx_ctx_set_staging_bytes(self.handle, nbytes))
+
+
+def get_context(device: int | None = None) -> Context:
+  """Per-(process, device) cached context."""
+  if device is None:
+    device = int(os.environ.get('LOCAL_RANK', '0')) if os.environ.get(
+        'WBX_B200_DEVICE_FROM_LOCAL_RANK') else 0
+    try:
+      import torch  # pylint: disable=g-import-not-at-top
+      if torch.cuda.is_available():
+        device = torch.cuda.current_device()
+    except ImportError:
+      pass
+  load_library()
+  key = (os.getpid(), device)
+  with _lock:
+    ctx = _contexts.get(key)
+  if ctx is None:
+    ctx = Context(device)
+    with _lock:
+      _contexts[key] = ctx
+  return ctx
+
+
+def _as_ptr(arr: np.ndarray | None, ctype):
+  if arr is None:
+    return ctypes.cast(None, POINTER(ctype))
+  return arr.ctypes.data_as(POINTER(ctype))
+
+
+class DetPlan:
+  """wbx_det_plan: job tables uploaded once, runnable many times."""
+
+  def __init__(self, ctx: Context, *, space: int, flags: int, ny: int, nx: int,
+               pred: np.ndarray, target: np.ndarray, cell: np.ndarray,
+               n_cells: int, clim: np.ndarray | None = None,
+               mask: np.ndarray | None = None,
+               w_outer: np.ndarray | None = None,
+               w_y: np.ndarray | None = None, w_x: np.ndarray | None = None):
+    self.ctx = ctx
+    self.n_cells = int(n_cells)
+    keep = []
+
+    def prep(a, dtype):
+      if a is None:
+        return None
+      a = np.ascontiguousarray(a, dtype=dtype)
+      keep.append(a)
+      return a
+
+    pred, target = prep(pred, np.uint64), prep(target, np.uint64)
+    clim, mask = prep(clim, np.uint64), prep(mask, np.uint64)
+    cell = prep(cell, np.int32)
+    w_outer, w_y, w_x = (prep(w_outer, np.float64), prep(w_y, np.float64),
+                         prep(w_x, np.float64))
+    n_jobs = len(pred)
+    for name, arr, n in (('target', target, n_jobs), ('clim', clim, n_jobs),
+                         ('mask', mask, n_jobs), ('cell', cell, n_jobs),
+                         ('w_outer', w_outer, n_jobs), ('w_y', w_y, ny),
+                         ('w_x', w_x, nx)):
+      if arr is not None and len(arr) != n:
+        raise ValueError(f'{name} has {len(arr)} entries, expected {n}')
+    desc = DetDesc(
+        space=space, flags=flags, n_jobs=n_jobs, ny=ny, nx=nx,
+        n_cells=n_cells,
+        pred=_as_ptr(pred, c_uint64), target=_as_ptr(target, c_uint64),
+        clim=_as_ptr(clim, c_uint64), mask=_as_ptr(mask, c_uint64),
+        cell=_as_ptr(cell, c_int32), w_outer=_as_ptr(w_outer, c_double),
+        w_y=_as_ptr(w_y, c_double), w_x=_as_ptr(w_x, c_double))
+    handle = c_void_p()
+    check(ctx.lib.wbx_det_plan_create(ctx.handle, ctypes.byref(desc),
+                                      ctypes.byref(handle)))
+    self.handle = handle
+    del keep
+
+  def run_to_host(self):
+    """Runs the plan; returns (sum_ws [n_cells, 6], sum_w [n_cells, 4])."""
+    ws = np.empty((self.n_cells, NUM_DET_STATS), np.float64)
+    w = np.empty((self.n_cells, NUM_DET_WCLASSES), np.float64)
+    check(self.ctx.lib.wbx_det_plan_run(
+        self.ctx.handle, self.handle, ws.ctypes.data, w.ctypes.data,
+        SPACE_HOST, 0))
+    return ws, w
+
+  def run_to_device(self, ws_ptr: int, w_ptr: int, accumulate: bool = False):
+    """Asynchronous run into device buffers (f64 [n_cells*6], [n_cells*4])."""
+    check(self.ctx.lib.wbx_det_plan_run(
+        self.ctx.handle, self.handle, c_void_p(ws_ptr), c_void_p(w_ptr),
+        SPACE_DEVICE, 1 if accumulate else 0))
+
+  def close(self):
+    if self.handle:
+      self.ctx.lib.wbx_det_plan_destroy(self.ctx.handle, self.handle)
+      self.handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
+def det_elementwise(ctx: Context, stat: int, pred_ptr: int, target_ptr: int,
+                    clim_ptr: int | None, n: int, out_ptr: int):
+  check(ctx.lib.wbx_det_elementwise(
+      ctx.handle, stat, c_void_p(pred_ptr), c_void_p(target_ptr),
+      c_void_p(clim_ptr or 0), n, c_void_p(out_ptr)))

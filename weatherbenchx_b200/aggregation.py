@@ -1,0 +1,308 @@
+"""Aggregation of statistics into (sum of weighted statistics, sum of weights).
+
+Mirrors /root/reference/weatherbenchX/aggregation.py: combining_sum :27-60,
+AggregationState :63-265, Aggregator :268-408 and
+compute_metric_values_for_single_chunk :411-435 -- same class names, dataclass
+fields, method names, None-for-not-applicable convention and NaN semantics.
+
+What is different underneath: when the statistics handed to the Aggregator are
+``LazyStatistic`` handles, all statistics that share their operands are reduced
+by one fused CUDA launch (statistic + mask + weights + reduction, see
+engine.aggregate_fused) instead of ``ones_like`` + two ``xr.dot`` calls per
+statistic.  The AggregationState itself (a few numbers per output cell) lives on
+the host in float64, as in the reference, and is what gets all-reduced across
+GPUs (distributed.py).
+"""
+
+from __future__ import annotations
+
+import collections
+import dataclasses
+from typing import Any, Callable, Collection, Hashable, Iterable, Mapping, Sequence
+
+from weatherbenchx_b200 import engine
+from weatherbenchx_b200 import xarray_lite as xl
+from weatherbenchx_b200 import xarray_tree
+from weatherbenchx_b200.lazy import LazyStatistic
+from weatherbenchx_b200.metrics import base as metrics_base
+
+
+def combining_sum(data_arrays: Sequence[xl.DataArray]) -> xl.DataArray:
+  """Sum with a zero-filled outer join on non-aligned coordinates."""
+  if not data_arrays:
+    return sum([])  # type: ignore
+  total = data_arrays[0]
+  for da in data_arrays[1:]:
+    a, b = xl.align(total, da, join='outer', fill_value=0)
+    total = a + b
+  return total
+
+
+@dataclasses.dataclass
+class AggregationState:
+  """Sum of weighted statistics and sum of weights, summable across chunks."""
+
+  sum_weighted_statistics: Any
+  sum_weights: Any
+
+  @classmethod
+  def zero(cls) -> 'AggregationState':
+    return cls(sum_weighted_statistics=None, sum_weights=None)
+
+  def __add__(self, other: 'AggregationState') -> 'AggregationState':
+    return self.sum([self, other])
+
+  @classmethod
+  def sum(cls, aggregation_states: Iterable['AggregationState']
+          ) -> 'AggregationState':
+    pairs = [(s.sum_weighted_statistics, s.sum_weights)
+             for s in aggregation_states
+             if s.sum_weighted_statistics is not None]
+    if not pairs:
+      return cls.zero()
+    sws, sw = xarray_tree.map_structure(
+        lambda *leaves: combining_sum(leaves), *pairs)
+    return cls(sws, sw)
+
+  def mean_statistics(self) -> Any:
+    return xarray_tree.map_structure(
+        lambda num, den: num / den,
+        self.sum_weighted_statistics, self.sum_weights)
+
+  def metric_values(self, metrics: Mapping[str, metrics_base.Metric]
+                    ) -> xl.Dataset:
+    """Dataset of '<metric>.<variable>' values from the normalised sums."""
+    values = metrics_base.compute_metrics_from_statistics(
+        metrics, self.mean_statistics())
+    out = xl.Dataset()
+    for metric_name, per_var in values.items():
+      for var_name, da in per_var.items():
+        out[f'{metric_name}.{var_name}'] = da
+    return out
+
+  def sum_along_dims(self, dims: Collection[str]) -> 'AggregationState':
+    if self.sum_weighted_statistics is None:
+      return self
+    return self.map(lambda x: x.sum(dims, skipna=False))
+
+  def dot(self, *arrays: xl.DataArray, dim) -> 'AggregationState':
+    return self.map(lambda x: xl.dot(x, *arrays, dim=dim))
+
+  @classmethod
+  def map_multi(cls, func: Callable[..., xl.DataArray],
+                *agg_states: 'AggregationState') -> 'AggregationState':
+    if any(a.sum_weighted_statistics is None for a in agg_states):
+      raise ValueError('Cannot map a zero AggregationState.')
+    return cls(
+        xarray_tree.map_structure(
+            func, *[a.sum_weighted_statistics for a in agg_states]),
+        xarray_tree.map_structure(func, *[a.sum_weights for a in agg_states]))
+
+  def map(self, func: Callable[[xl.DataArray], xl.DataArray]
+          ) -> 'AggregationState':
+    return self.map_multi(func, self)
+
+  # -- serialisation ---------------------------------------------------------
+  # The reference offers DataTree and '#'-separated Dataset forms
+  # (aggregation.py:203-265).  Without xarray the Dataset form is the
+  # checkpoint format here: a flat {path#leaf: DataArray} mapping.
+
+  def to_dataset(self, separator: str = '#') -> xl.Dataset:
+    out = xl.Dataset()
+
+    def walk(prefix, sws, sw):
+      if isinstance(sws, Mapping):
+        for k in sws:
+          walk(prefix + [str(k)], sws[k], sw[k])
+      else:
+        path = separator.join(prefix)
+        out[f'{path}{separator}sum_weighted_statistics'] = sws
+        out[f'{path}{separator}sum_weights'] = sw
+
+    walk([], self.sum_weighted_statistics, self.sum_weights)
+    return out
+
+  @classmethod
+  def from_dataset(cls, dataset: Mapping[str, xl.DataArray],
+                   separator: str = '#') -> 'AggregationState':
+    def tree():
+      return collections.defaultdict(tree)
+
+    sws, sw = tree(), tree()
+    for path, da in dataset.items():
+      *parts, leaf = str(path).split(separator)
+      target = sws if leaf == 'sum_weighted_statistics' else sw
+      node = target
+      for p in parts[:-1]:
+        node = node[p]
+      node[parts[-1]] = da.rename(parts[-1])
+
+    def freeze(node):
+      if isinstance(node, collections.defaultdict):
+        return {k: freeze(v) for k, v in node.items()}
+      return node
+
+    return cls(freeze(sws), freeze(sw))
+
+
+@dataclasses.dataclass
+class Aggregator:
+  """Weighted / binned / masked sum over ``reduce_dims``.
+
+  NaN policy (identical to the reference): by default NaNs propagate into the
+  aggregated statistic; ``masked=True`` zero-fills and un-weights positions
+  whose 'mask' coordinate is False; ``skipna=True`` treats NaN statistic values
+  as masked.
+
+  Attributes:
+    reduce_dims: dims to average over; variables lacking one are dropped.
+    bin_by: Binning instances; all bin masks are multiplied.
+    weigh_by: Weighting instances; all weights are multiplied.
+    masked: use the statistic's 'mask' coordinate.
+    skipna: omit NaNs (not recommended).
+  """
+
+  reduce_dims: Collection[str]
+  bin_by: Sequence[Any] | None = None
+  weigh_by: Sequence[Any] | None = None
+  masked: bool = False
+  skipna: bool = False
+
+  # -- generic (strided) path ------------------------------------------------
+
+  def _weights_and_bins(self, stat: xl.DataArray):
+    """(factors, bin dim names) or None when a bin mask does not apply."""
+    factors = [w.weights(stat) for w in self.weigh_by or []]
+    names = [b.bin_dim_name for b in self.bin_by or []]
+    if len(set(names)) != len(names):
+      raise ValueError('Bin dimension names must be unique.')
+    for binning in self.bin_by or []:
+      mask = xl.as_data_array(binning.create_bin_mask(stat))
+      if not (set(mask.dims) - {binning.bin_dim_name}).issubset(stat.dims):
+        return None
+      factors.append(mask)
+    return factors, names
+
+  def aggregation_fn(self, stat: xl.DataArray) -> xl.DataArray | None:
+    """Weighted, binned sum of ``stat`` over reduce_dims (no mask logic)."""
+    from weatherbenchx_b200 import generic  # pylint: disable=g-import-not-at-top
+    stat = xl.as_data_array(stat)
+    if not set(self.reduce_dims).issubset(stat.dims):
+      return None
+    prepared = self._weights_and_bins(stat)
+    if prepared is None:
+      return None
+    factors, bin_dims = prepared
+    return generic.aggregate(stat, factors, self.reduce_dims,
+                             extra_dims=bin_dims)[0]
+
+  def _fused_group(self, stats: Sequence[LazyStatistic]):
+    """{kind: AggregationState | None} for lazies sharing operands."""
+    first = stats[0]
+    if not set(self.reduce_dims).issubset(first.dims):
+      return {s.kind: None for s in stats}
+    if self.bin_by:
+      raise engine.FastPathUnavailable('binning')
+    weights = [w.weights(first) for w in self.weigh_by or []]
+    res = engine.aggregate_fused(
+        stats, self.reduce_dims, weights,
+        masked=self.masked and 'mask' in first.coords, skipna=self.skipna)
+    if res is None:
+      return {s.kind: None for s in stats}
+    return {k: AggregationState(v[0], v[1]) for k, v in res.items()}
+
+  def _aggregate_generic(self, stat: xl.DataArray) -> AggregationState | None:
+    from weatherbenchx_b200 import generic  # pylint: disable=g-import-not-at-top
+    if not set(self.reduce_dims).issubset(stat.dims):
+      return None
+    prepared = self._weights_and_bins(stat)
+    if prepared is None:
+      return None
+    factors, bin_dims = prepared
+    mask = stat.coords['mask'] if (self.masked and 'mask' in stat.coords
+                                   ) else None
+    sws, sw = generic.aggregate(stat, factors, self.reduce_dims, mask=mask,
+                                skipna=self.skipna, extra_dims=bin_dims)
+    return AggregationState(sws, sw)
+
+  def aggregate_stat_var(self, stat: xl.DataArray) -> AggregationState | None:
+    """Aggregates one statistic DataArray of one variable."""
+    stat = xl.as_data_array(stat)
+    if isinstance(stat, LazyStatistic) and stat.is_lazy:
+      try:
+        return self._fused_group([stat])[stat.kind]
+      except engine.FastPathUnavailable:
+        pass
+    return self._aggregate_generic(stat)
+
+  def aggregate_stat_vars(self, stats: Mapping[Hashable, xl.DataArray]
+                          ) -> AggregationState:
+    per_var = {v: self.aggregate_stat_var(s)
+               for v, s in stats.items() if s is not None}
+    per_var = {v: s for v, s in per_var.items() if s is not None}
+    return AggregationState(
+        {v: s.sum_weighted_statistics for v, s in per_var.items()},
+        {v: s.sum_weights for v, s in per_var.items()})
+
+  def aggregate_statistics(
+      self, statistics: Mapping[str, Mapping[Hashable, xl.DataArray]],
+  ) -> AggregationState:
+    """Aggregates several statistics, each defined for several variables.
+
+    Lazy statistics of one variable that share their operands (e.g.
+    SquaredError + AbsoluteError + the three ACC statistics) are served by a
+    single fused launch.
+    """
+    results: dict = {name: {} for name in statistics}
+    groups: dict = collections.defaultdict(list)
+    for stat_name, per_var in statistics.items():
+      for var, stat in per_var.items():
+        if stat is None:
+          continue
+        stat = xl.as_data_array(stat)
+        if isinstance(stat, LazyStatistic) and stat.is_lazy:
+          groups[(var,) + stat.group_key()[:2]].append((stat_name, var, stat))
+        else:
+          results[stat_name][var] = self._aggregate_generic(stat)
+    # Statistics of the same (predictions, targets) share one launch; those
+    # that need a climatology define it (one sub-group per climatology).
+    subgroups = []
+    for members in groups.values():
+      by_clim: dict = collections.defaultdict(list)
+      for m in members:
+        by_clim[m[2].group_key()[2]].append(m)
+      plain = by_clim.pop(None, [])
+      if by_clim:
+        keys = list(by_clim)
+        by_clim[keys[0]].extend(plain)
+        subgroups.extend(by_clim.values())
+      else:
+        subgroups.append(plain)
+    for members in subgroups:
+      lazies = [m[2] for m in members]
+      distinct = {}
+      for s in lazies:
+        distinct.setdefault(s.kind, s)
+      try:
+        fused = self._fused_group(list(distinct.values()))
+        for stat_name, var, s in members:
+          results[stat_name][var] = fused[s.kind]
+      except engine.FastPathUnavailable:
+        for stat_name, var, s in members:
+          results[stat_name][var] = self._aggregate_generic(s)
+    sws, sw = {}, {}
+    for stat_name in statistics:
+      ok = {v: s for v, s in results[stat_name].items() if s is not None}
+      sws[stat_name] = {v: s.sum_weighted_statistics for v, s in ok.items()}
+      sw[stat_name] = {v: s.sum_weights for v, s in ok.items()}
+    return AggregationState(sws, sw)
+
+
+def compute_metric_values_for_single_chunk(
+    metrics: Mapping[str, metrics_base.Metric], aggregator: Aggregator,
+    predictions, targets) -> xl.Dataset:
+  """Metric values for one predictions/targets pair (no accumulation)."""
+  statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+      metrics, predictions, targets)
+  return aggregator.aggregate_statistics(statistics).metric_values(metrics)
+

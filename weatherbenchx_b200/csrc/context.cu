@@ -1,0 +1,177 @@
+// Context, error handling and pinned-memory helpers of libwbx_b200.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace wbx {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t err, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) in %s at %s:%d", static_cast<int>(err),
+            cudaGetErrorString(err), what, file, line);
+  if (err == cudaErrorMemoryAllocation) return WBX_ERR_NOMEM;
+  if (err == cudaErrorNoDevice || err == cudaErrorInsufficientDriver)
+    return WBX_ERR_NO_DEVICE;
+  return WBX_ERR_CUDA;
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return WBX_OK;
+  if (ptr) {
+    cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t err = cudaMalloc(&ptr, want);
+  if (err != cudaSuccess) {
+    ptr = nullptr;
+    return cuda_fail(err, "cudaMalloc", __FILE__, __LINE__);
+  }
+  cap = want;
+  return WBX_OK;
+}
+
+void DevBuf::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+
+}  // namespace wbx
+
+extern "C" {
+
+int wbx_abi_version(void) { return WBX_ABI_VERSION; }
+
+const char* wbx_last_error(void) { return wbx::g_error; }
+
+int wbx_ctx_create(int device, wbx_ctx** out) {
+  WBX_REQUIRE(out != nullptr, "wbx_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    wbx::set_error("wbx_ctx_create: no CUDA device available (%s)",
+                   cudaGetErrorString(err));
+    return WBX_ERR_NO_DEVICE;
+  }
+  WBX_REQUIRE(device >= 0 && device < count,
+              "wbx_ctx_create: device %d out of range [0, %d)", device, count);
+  WBX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  WBX_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    wbx::set_error(
+        "wbx_ctx_create: device %d is sm_%d%d; libwbx_b200 is built for "
+        "sm_100a (B200) only",
+        device, prop.major, prop.minor);
+    return WBX_ERR_UNSUPPORTED;
+  }
+  wbx_ctx* ctx = new (std::nothrow) wbx_ctx();
+  if (!ctx) {
+    wbx::set_error("wbx_ctx_create: out of host memory");
+    return WBX_ERR_NOMEM;
+  }
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->hbm_bytes = prop.totalGlobalMem;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  WBX_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  WBX_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    WBX_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+    WBX_CUDA(
+        cudaEventCreateWithFlags(&ctx->ev_compute[i], cudaEventDisableTiming));
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return WBX_OK;
+}
+
+int wbx_ctx_destroy(wbx_ctx* ctx) {
+  if (!ctx) return WBX_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->own_stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  ctx->records.release();
+  ctx->out_ws.release();
+  ctx->out_w.release();
+  for (int i = 0; i < 2; ++i) {
+    ctx->staging[i].release();
+    ctx->stage_tables[i].release();
+    if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    if (ctx->ev_compute[i]) cudaEventDestroy(ctx->ev_compute[i]);
+  }
+  if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
+  cudaStreamDestroy(ctx->own_stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return WBX_OK;
+}
+
+int wbx_ctx_set_stream(wbx_ctx* ctx, void* cuda_stream) {
+  WBX_REQUIRE(ctx != nullptr, "wbx_ctx_set_stream: ctx is NULL");
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream)
+                            : ctx->own_stream;
+  return WBX_OK;
+}
+
+int wbx_ctx_synchronize(wbx_ctx* ctx) {
+  WBX_REQUIRE(ctx != nullptr, "wbx_ctx_synchronize: ctx is NULL");
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return WBX_OK;
+}
+
+int wbx_ctx_info(wbx_ctx* ctx, int* sm_count, uint64_t* hbm_bytes,
+                 uint64_t* kernel_launches) {
+  WBX_REQUIRE(ctx != nullptr, "wbx_ctx_info: ctx is NULL");
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+  if (kernel_launches) *kernel_launches = ctx->launches;
+  return WBX_OK;
+}
+
+int wbx_ctx_set_staging_bytes(wbx_ctx* ctx, uint64_t bytes) {
+  WBX_REQUIRE(ctx != nullptr, "wbx_ctx_set_staging_bytes: ctx is NULL");
+  WBX_REQUIRE(bytes >= (1ull << 20), "staging budget must be >= 1 MiB");
+  ctx->staging_bytes = bytes;
+  return WBX_OK;
+}
+
+int wbx_host_alloc(size_t bytes, void** out) {
+  WBX_REQUIRE(out != nullptr, "wbx_host_alloc: out is NULL");
+  *out = nullptr;
+  WBX_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return WBX_OK;
+}
+
+int wbx_host_free(void* ptr) {
+  if (!ptr) return WBX_OK;
+  WBX_CUDA(cudaFreeHost(ptr));
+  return WBX_OK;
+}
+
+int wbx_host_register(void* ptr, size_t bytes) {
+  WBX_REQUIRE(ptr != nullptr, "wbx_host_register: ptr is NULL");
+  WBX_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return WBX_OK;
+}
+
+int wbx_host_unregister(void* ptr) {
+  WBX_REQUIRE(ptr != nullptr, "wbx_host_unregister: ptr is NULL");
+  WBX_CUDA(cudaHostUnregister(ptr));
+  return WBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,635 @@
+// Host side of the fused deterministic-statistics reduction: plan building,
+// kernel selection, host-space streaming.  C ABI in include/wbx_b200.h.
+#include <algorithm>
+#include <new>
+#include <string.h>
+
+#include "det_reduce.cuh"
+
+namespace wbx {
+
+enum Path { kPathTma = 0, kPathLdg4 = 1, kPathLdg1 = 2 };
+
+static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace wbx
+
+struct wbx_det_plan {
+  int32_t space = 0, flags = 0;
+  int64_t n_jobs = 0, ny = 0, nx = 0, n_cells = 0;
+  bool has_clim = false, has_mask = false, skipna = false, per_elem = false;
+  bool has_wo = false, has_wy = false, has_wx = false;
+  std::vector<uint64_t> pred, target, clim, mask;
+  std::vector<int32_t> cell;
+  std::vector<double> wo, wy, wx;
+  double sum_wy = 1.0, sum_wx = 1.0;
+  int path = 0;
+  int tile = 0, tiles_per_slab = 0, stages = 0, stage_bytes = 0;
+  size_t smem_bytes = 0;
+  int n_stats = 3, n_weights = 0, nacc = 3;
+  // device-space plans: tables uploaded once.
+  wbx::DevBuf tables;
+  wbx::DetParams params{};
+  const int32_t* d_cell_first_job = nullptr;
+  const double* d_cell_w = nullptr;
+  int grid = 0;
+  // weights are shared by device- and host-space plans.
+  wbx::DevBuf weights;
+  const double* d_wy = nullptr;
+  const double* d_wx = nullptr;
+  std::vector<unsigned char> chunk_host[2];
+};
+
+namespace wbx {
+
+template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM>
+static int launch_variant(wbx_ctx* ctx, const wbx_det_plan* plan,
+                          const DetParams& P, int grid) {
+  cudaStream_t st = ctx->stream;
+  if (plan->path == kPathTma) {
+    auto kern = det_reduce_tma_kernel<CLIM, MASK, SKIPNA, PER_ELEM>;
+    WBX_CUDA(cudaFuncSetAttribute(kern,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(plan->smem_bytes)));
+    kern<<<grid, kTmaThreads, plan->smem_bytes, st>>>(P, plan->stages,
+                                                      plan->stage_bytes);
+  } else if (plan->path == kPathLdg4) {
+    det_reduce_ldg_kernel<CLIM, MASK, SKIPNA, PER_ELEM, 4>
+        <<<grid, kLdgThreads, 0, st>>>(P);
+  } else {
+    det_reduce_ldg_kernel<CLIM, MASK, SKIPNA, true, 1>
+        <<<grid, kLdgThreads, 0, st>>>(P);
+  }
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return WBX_OK;
+}
+
+static int launch_main(wbx_ctx* ctx, const wbx_det_plan* plan,
+                       const DetParams& P, int grid) {
+  const int key = (plan->has_clim ? 8 : 0) | (plan->has_mask ? 4 : 0) |
+                  (plan->skipna ? 2 : 0) | (plan->per_elem ? 1 : 0);
+  switch (key) {
+#define WBX_CASE(K, A, B, C, D) \
+  case K:                       \
+    return launch_variant<A, B, C, D>(ctx, plan, P, grid);
+    WBX_CASE(0, false, false, false, false)
+    WBX_CASE(1, false, false, false, true)
+    WBX_CASE(2, false, false, true, false)
+    WBX_CASE(3, false, false, true, true)
+    WBX_CASE(4, false, true, false, false)
+    WBX_CASE(5, false, true, false, true)
+    WBX_CASE(6, false, true, true, false)
+    WBX_CASE(7, false, true, true, true)
+    WBX_CASE(8, true, false, false, false)
+    WBX_CASE(9, true, false, false, true)
+    WBX_CASE(10, true, false, true, false)
+    WBX_CASE(11, true, false, true, true)
+    WBX_CASE(12, true, true, false, false)
+    WBX_CASE(13, true, true, false, true)
+    WBX_CASE(14, true, true, true, false)
+    WBX_CASE(15, true, true, true, true)
+#undef WBX_CASE
+  }
+  set_error("internal: bad variant key %d", key);
+  return WBX_ERR_INVALID;
+}
+
+static int grid_for(const wbx_ctx* ctx, const wbx_det_plan* plan,
+                    long long total_tiles) {
+  long long g = plan->path == kPathTma ? ctx->sm_count : ctx->sm_count * 6ll;
+  return static_cast<int>(std::max(1ll, std::min(g, total_tiles)));
+}
+
+static int warps_for(const wbx_det_plan* plan) {
+  return plan->path == kPathTma ? kConsumerWarps : kLdgWarps;
+}
+
+static int launch_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
+                           const double* records, const int32_t* d_first,
+                           const double* d_cell_w, int n_cells, int grid_main,
+                           long long total_tiles, double* out_ws, double* out_w,
+                           int accumulate) {
+  FinalizeParams F;
+  F.records = records;
+  F.cell_first_job = d_first;
+  F.cell_w = d_cell_w;
+  F.out_ws = out_ws;
+  F.out_w = out_w;
+  F.total_tiles = total_tiles;
+  F.n_cells = n_cells;
+  F.grid_main = grid_main;
+  F.tiles_per_slab = plan->tiles_per_slab;
+  F.warps = warps_for(plan);
+  F.n_stats = plan->n_stats;
+  F.n_weights = plan->n_weights;
+  F.accumulate = accumulate;
+  const int slots = WBX_NUM_DET_STATS + WBX_NUM_DET_WCLASSES;
+  const long long threads = static_cast<long long>(n_cells) * slots;
+  const int block = 128;
+  const int grid = static_cast<int>((threads + block - 1) / block);
+  det_finalize_kernel<<<grid, block, 0, ctx->stream>>>(F);
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return WBX_OK;
+}
+
+static int ensure_pinned_out(wbx_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_out_cap) return WBX_OK;
+  if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
+  ctx->pinned_out = nullptr;
+  ctx->pinned_out_cap = 0;
+  WBX_CUDA(cudaHostAlloc(&ctx->pinned_out, bytes, cudaHostAllocDefault));
+  ctx->pinned_out_cap = bytes;
+  return WBX_OK;
+}
+
+// cell prefix (first job of every cell) and constant sum_weights per cell for
+// the job range [j0, j1).
+static void cell_tables(const wbx_det_plan* plan, int64_t j0, int64_t j1,
+                        std::vector<int32_t>* first, std::vector<double>* cw) {
+  const int c0 = plan->cell[j0];
+  const int c1 = plan->cell[j1 - 1];
+  const int n = c1 - c0 + 1;
+  first->assign(n + 1, 0);
+  cw->assign(n, 0.0);
+  for (int64_t j = j0; j < j1; ++j) {
+    const int c = plan->cell[j] - c0;
+    (*first)[c + 1] = static_cast<int32_t>(j - j0 + 1);
+    const double wo = plan->has_wo ? plan->wo[j] : 1.0;
+    (*cw)[c] += wo * plan->sum_wy * plan->sum_wx;
+  }
+  // cells are dense and non-decreasing, so first[c+1] was set for every c.
+}
+
+}  // namespace wbx
+
+using wbx::round_up;
+
+extern "C" {
+
+int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
+                        wbx_det_plan** out) {
+  WBX_REQUIRE(ctx && d && out, "wbx_det_plan_create: NULL argument");
+  *out = nullptr;
+  WBX_REQUIRE(d->space == WBX_SPACE_DEVICE || d->space == WBX_SPACE_HOST,
+              "det: bad space %d", d->space);
+  WBX_REQUIRE(d->n_jobs >= 1, "det: n_jobs must be >= 1 (got %lld)",
+              (long long)d->n_jobs);
+  WBX_REQUIRE(d->ny >= 1 && d->nx >= 1, "det: ny, nx must be >= 1");
+  WBX_REQUIRE(d->ny * d->nx < (1ll << 30),
+              "det: slab of %lld x %lld elements is too large",
+              (long long)d->ny, (long long)d->nx);
+  WBX_REQUIRE(d->n_jobs < (1ll << 31), "det: too many jobs");
+  WBX_REQUIRE(d->pred && d->target && d->cell,
+              "det: pred, target and cell tables are required");
+  WBX_REQUIRE(d->n_cells >= 1 && d->n_cells <= d->n_jobs,
+              "det: n_cells must be in [1, n_jobs]");
+  const bool masked = (d->flags & WBX_FLAG_MASKED) != 0;
+  WBX_REQUIRE(masked == (d->mask != nullptr),
+              "det: WBX_FLAG_MASKED and a mask table must be given together");
+  WBX_REQUIRE(d->cell[0] == 0, "det: cell[0] must be 0");
+  for (int64_t j = 1; j < d->n_jobs; ++j) {
+    const int step = d->cell[j] - d->cell[j - 1];
+    WBX_REQUIRE(step == 0 || step == 1,
+                "det: cell[] must be non-decreasing and dense (job %lld)",
+                (long long)j);
+  }
+  WBX_REQUIRE(d->cell[d->n_jobs - 1] == d->n_cells - 1,
+              "det: cell[] must end at n_cells - 1");
+  for (int64_t j = 0; j < d->n_jobs; ++j) {
+    WBX_REQUIRE(d->pred[j] && d->target[j], "det: NULL slab address (job %lld)",
+                (long long)j);
+    if (d->clim) WBX_REQUIRE(d->clim[j] != 0, "det: NULL clim slab address");
+    if (d->mask) WBX_REQUIRE(d->mask[j] != 0, "det: NULL mask slab address");
+  }
+
+  wbx_det_plan* p = new (std::nothrow) wbx_det_plan();
+  if (!p) {
+    wbx::set_error("det: out of host memory");
+    return WBX_ERR_NOMEM;
+  }
+  p->space = d->space;
+  p->flags = d->flags;
+  p->n_jobs = d->n_jobs;
+  p->ny = d->ny;
+  p->nx = d->nx;
+  p->n_cells = d->n_cells;
+  p->has_clim = d->clim != nullptr;
+  p->has_mask = d->mask != nullptr;
+  p->skipna = (d->flags & WBX_FLAG_SKIPNA) != 0;
+  p->has_wo = d->w_outer != nullptr;
+  p->has_wy = d->w_y != nullptr;
+  p->has_wx = d->w_x != nullptr;
+  p->pred.assign(d->pred, d->pred + d->n_jobs);
+  p->target.assign(d->target, d->target + d->n_jobs);
+  if (p->has_clim) p->clim.assign(d->clim, d->clim + d->n_jobs);
+  if (p->has_mask) p->mask.assign(d->mask, d->mask + d->n_jobs);
+  p->cell.assign(d->cell, d->cell + d->n_jobs);
+  if (p->has_wo) p->wo.assign(d->w_outer, d->w_outer + d->n_jobs);
+  if (p->has_wy) {
+    p->wy.assign(d->w_y, d->w_y + d->ny);
+    p->sum_wy = 0.0;
+    for (double v : p->wy) p->sum_wy += v;
+  } else {
+    p->sum_wy = static_cast<double>(d->ny);
+  }
+  if (p->has_wx) {
+    p->wx.assign(d->w_x, d->w_x + d->nx);
+    p->sum_wx = 0.0;
+    for (double v : p->wx) p->sum_wx += v;
+  } else {
+    p->sum_wx = static_cast<double>(d->nx);
+  }
+  p->per_elem = p->has_wx || (d->nx % 4) != 0;
+  p->n_stats = p->has_clim ? 6 : 3;
+  p->n_weights = p->skipna ? (p->has_clim ? 4 : 1) : (p->has_mask ? 1 : 0);
+  p->nacc = p->n_stats + p->n_weights;
+
+  const int64_t slab = d->ny * d->nx;
+  bool aligned = (slab % 4) == 0 && (!p->has_mask || (slab % 16) == 0);
+  if (aligned && d->space == WBX_SPACE_DEVICE) {
+    for (int64_t j = 0; j < d->n_jobs && aligned; ++j) {
+      aligned = (d->pred[j] % 16) == 0 && (d->target[j] % 16) == 0 &&
+                (!p->has_clim || (d->clim[j] % 16) == 0) &&
+                (!p->has_mask || (d->mask[j] % 16) == 0);
+    }
+  }
+  // tile: 4096 elements (16 KiB per operand) unless the slab is smaller.
+  int tile = 4096;
+  if (slab < tile) tile = static_cast<int>(round_up(slab, 16));
+  p->tile = tile;
+  p->tiles_per_slab = static_cast<int>((slab + tile - 1) / tile);
+  p->stage_bytes = static_cast<int>(round_up(
+      static_cast<size_t>(tile) * 4 * (p->has_clim ? 3 : 2) +
+          (p->has_mask ? tile : 0),
+      128));
+  const size_t overhead = 2 * wbx::kMaxStages * sizeof(uint64_t) +
+                          wbx::kMaxStages * sizeof(wbx::StageMeta) + 128;
+  const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024) - overhead;
+  int stages = static_cast<int>(budget / p->stage_bytes);
+  stages = std::min(stages, wbx::kMaxStages);
+  // No point in more stages than tiles a CTA will ever see.
+  p->stages = stages;
+  p->smem_bytes = static_cast<size_t>(stages) * p->stage_bytes + overhead;
+  if (d->flags & WBX_FLAG_FORCE_TMA) {
+    if (!aligned || stages < 2) {
+      delete p;
+      wbx::set_error("det: WBX_FLAG_FORCE_TMA but operands are not 16-byte "
+                     "aligned / slab %% 4 != 0");
+      return WBX_ERR_UNSUPPORTED;
+    }
+    p->path = wbx::kPathTma;
+  } else if (aligned && stages >= 2 && !(d->flags & WBX_FLAG_FORCE_LDG)) {
+    p->path = wbx::kPathTma;
+  } else if (aligned) {
+    p->path = wbx::kPathLdg4;
+  } else {
+    p->path = wbx::kPathLdg1;
+    p->per_elem = true;
+  }
+
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  // weights (shared by both spaces)
+  {
+    const size_t bytes = (p->wy.size() + p->wx.size()) * sizeof(double);
+    if (bytes) {
+      int rc = p->weights.reserve(bytes);
+      if (rc != WBX_OK) { delete p; return rc; }
+      double* base = p->weights.as<double>();
+      if (p->has_wy) {
+        WBX_CUDA(cudaMemcpyAsync(base, p->wy.data(),
+                                 p->wy.size() * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        p->d_wy = base;
+      }
+      if (p->has_wx) {
+        WBX_CUDA(cudaMemcpyAsync(base + p->wy.size(), p->wx.data(),
+                                 p->wx.size() * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        p->d_wx = base + p->wy.size();
+      }
+    }
+  }
+
+  if (d->space == WBX_SPACE_DEVICE) {
+    std::vector<int32_t> first;
+    std::vector<double> cw;
+    wbx::cell_tables(p, 0, p->n_jobs, &first, &cw);
+    const size_t nj = static_cast<size_t>(p->n_jobs);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      size_t o = off;
+      off += round_up(bytes, 16);
+      return o;
+    };
+    const size_t o_pred = take(nj * 8), o_tgt = take(nj * 8);
+    const size_t o_clim = p->has_clim ? take(nj * 8) : 0;
+    const size_t o_mask = p->has_mask ? take(nj * 8) : 0;
+    const size_t o_wo = p->has_wo ? take(nj * 8) : 0;
+    const size_t o_cell = take(nj * 4);
+    const size_t o_first = take(first.size() * 4);
+    const size_t o_cw = take(cw.size() * 8);
+    std::vector<unsigned char>& host = p->chunk_host[0];
+    host.assign(off, 0);
+    memcpy(host.data() + o_pred, p->pred.data(), nj * 8);
+    memcpy(host.data() + o_tgt, p->target.data(), nj * 8);
+    if (p->has_clim) memcpy(host.data() + o_clim, p->clim.data(), nj * 8);
+    if (p->has_mask) memcpy(host.data() + o_mask, p->mask.data(), nj * 8);
+    if (p->has_wo) memcpy(host.data() + o_wo, p->wo.data(), nj * 8);
+    memcpy(host.data() + o_cell, p->cell.data(), nj * 4);
+    memcpy(host.data() + o_first, first.data(), first.size() * 4);
+    memcpy(host.data() + o_cw, cw.data(), cw.size() * 8);
+    int rc = p->tables.reserve(off);
+    if (rc != WBX_OK) { delete p; return rc; }
+    unsigned char* base = p->tables.as<unsigned char>();
+    WBX_CUDA(cudaMemcpyAsync(base, host.data(), off, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+    wbx::DetParams& P = p->params;
+    P.pred = reinterpret_cast<const uint64_t*>(base + o_pred);
+    P.target = reinterpret_cast<const uint64_t*>(base + o_tgt);
+    P.clim = p->has_clim ? reinterpret_cast<const uint64_t*>(base + o_clim)
+                         : nullptr;
+    P.mask = p->has_mask ? reinterpret_cast<const uint64_t*>(base + o_mask)
+                         : nullptr;
+    P.w_outer =
+        p->has_wo ? reinterpret_cast<const double*>(base + o_wo) : nullptr;
+    P.cell = reinterpret_cast<const int32_t*>(base + o_cell);
+    P.w_y = p->d_wy;
+    P.w_x = p->d_wx;
+    P.n_jobs = p->n_jobs;
+    P.total_tiles = p->n_jobs * p->tiles_per_slab;
+    P.cell_base = 0;
+    P.ny = static_cast<int>(p->ny);
+    P.nx = static_cast<int>(p->nx);
+    P.slab = static_cast<int>(slab);
+    P.tile = p->tile;
+    P.tiles_per_slab = p->tiles_per_slab;
+    P.records = nullptr;
+    p->d_cell_first_job = reinterpret_cast<const int32_t*>(base + o_first);
+    p->d_cell_w = reinterpret_cast<const double*>(base + o_cw);
+    p->grid = wbx::grid_for(ctx, p, P.total_tiles);
+  } else {
+    WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  *out = p;
+  return WBX_OK;
+}
+
+int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan) {
+  if (!plan) return WBX_OK;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+  }
+  plan->tables.release();
+  plan->weights.release();
+  delete plan;
+  return WBX_OK;
+}
+
+static int run_device_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
+                            double* d_w, int accumulate) {
+  const int warps = wbx::warps_for(plan);
+  const size_t rec_bytes = (static_cast<size_t>(plan->grid) + plan->n_cells) *
+                           warps * plan->nacc * sizeof(double);
+  int rc = ctx->records.reserve(rec_bytes);
+  if (rc != WBX_OK) return rc;
+  wbx::DetParams P = plan->params;
+  P.records = ctx->records.as<double>();
+  rc = wbx::launch_main(ctx, plan, P, plan->grid);
+  if (rc != WBX_OK) return rc;
+  return wbx::launch_finalize(ctx, plan, P.records, plan->d_cell_first_job,
+                              plan->d_cell_w, static_cast<int>(plan->n_cells),
+                              plan->grid, P.total_tiles, d_ws, d_w, accumulate);
+}
+
+// Host-space: stream chunks of jobs through two staging buffers; copies of
+// chunk i+1 overlap the kernel of chunk i.
+static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
+                          double* d_w) {
+  const size_t slab = static_cast<size_t>(plan->ny * plan->nx);
+  const size_t fbytes = slab * 4;
+  const size_t mbytes = round_up(slab, 16);
+  const size_t job_bytes =
+      fbytes * (plan->has_clim ? 3 : 2) + (plan->has_mask ? mbytes : 0);
+  int64_t per_chunk = static_cast<int64_t>((ctx->staging_bytes / 2) / job_bytes);
+  per_chunk = std::max<int64_t>(1, std::min<int64_t>(per_chunk, plan->n_jobs));
+  for (int b = 0; b < 2; ++b) {
+    int rc = ctx->staging[b].reserve(static_cast<size_t>(per_chunk) * job_bytes);
+    if (rc != WBX_OK) return rc;
+  }
+  WBX_CUDA(cudaMemsetAsync(d_ws, 0,
+                           plan->n_cells * WBX_NUM_DET_STATS * sizeof(double),
+                           ctx->stream));
+  WBX_CUDA(cudaMemsetAsync(d_w, 0,
+                           plan->n_cells * WBX_NUM_DET_WCLASSES * sizeof(double),
+                           ctx->stream));
+  const int warps = wbx::warps_for(plan);
+  int buf = 0;
+  for (int64_t j0 = 0; j0 < plan->n_jobs; j0 += per_chunk, buf ^= 1) {
+    const int64_t j1 = std::min<int64_t>(plan->n_jobs, j0 + per_chunk);
+    const size_t nj = static_cast<size_t>(j1 - j0);
+    unsigned char* sbase = ctx->staging[buf].as<unsigned char>();
+    unsigned char* s_pred = sbase;
+    unsigned char* s_tgt = s_pred + nj * fbytes;
+    unsigned char* s_clim = s_tgt + nj * fbytes;
+    unsigned char* s_mask = s_clim + (plan->has_clim ? nj * fbytes : 0);
+    // Before overwriting this staging buffer, wait for the kernel that last
+    // read it.
+    WBX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute[buf], 0));
+    auto copy_operand = [&](const std::vector<uint64_t>& addr,
+                            unsigned char* dst, size_t bytes,
+                            size_t stride) -> int {
+      size_t j = 0;
+      while (j < nj) {
+        // merge runs of slabs that are contiguous in host memory.
+        size_t run = 1;
+        if (stride == bytes) {
+          while (j + run < nj &&
+                 addr[j0 + j + run] == addr[j0 + j + run - 1] + bytes)
+            ++run;
+        }
+        WBX_CUDA(cudaMemcpyAsync(
+            dst + j * stride, reinterpret_cast<const void*>(addr[j0 + j]),
+            run * bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        j += run;
+      }
+      return WBX_OK;
+    };
+    int rc = copy_operand(plan->pred, s_pred, fbytes, fbytes);
+    if (rc != WBX_OK) return rc;
+    rc = copy_operand(plan->target, s_tgt, fbytes, fbytes);
+    if (rc != WBX_OK) return rc;
+    if (plan->has_clim) {
+      rc = copy_operand(plan->clim, s_clim, fbytes, fbytes);
+      if (rc != WBX_OK) return rc;
+    }
+    if (plan->has_mask) {
+      rc = copy_operand(plan->mask, s_mask, slab, mbytes);
+      if (rc != WBX_OK) return rc;
+    }
+    // chunk tables
+    std::vector<int32_t> first;
+    std::vector<double> cw;
+    wbx::cell_tables(plan, j0, j1, &first, &cw);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      size_t o = off;
+      off += round_up(bytes, 16);
+      return o;
+    };
+    const size_t o_pred = take(nj * 8), o_tgt = take(nj * 8);
+    const size_t o_clim = plan->has_clim ? take(nj * 8) : 0;
+    const size_t o_mask = plan->has_mask ? take(nj * 8) : 0;
+    const size_t o_wo = plan->has_wo ? take(nj * 8) : 0;
+    const size_t o_cell = take(nj * 4);
+    const size_t o_first = take(first.size() * 4);
+    const size_t o_cw = take(cw.size() * 8);
+    std::vector<unsigned char>& host = plan->chunk_host[buf];
+    host.assign(off, 0);
+    uint64_t* h_pred = reinterpret_cast<uint64_t*>(host.data() + o_pred);
+    uint64_t* h_tgt = reinterpret_cast<uint64_t*>(host.data() + o_tgt);
+    uint64_t* h_clim = reinterpret_cast<uint64_t*>(host.data() + o_clim);
+    uint64_t* h_mask = reinterpret_cast<uint64_t*>(host.data() + o_mask);
+    for (size_t j = 0; j < nj; ++j) {
+      h_pred[j] = reinterpret_cast<uint64_t>(s_pred + j * fbytes);
+      h_tgt[j] = reinterpret_cast<uint64_t>(s_tgt + j * fbytes);
+      if (plan->has_clim)
+        h_clim[j] = reinterpret_cast<uint64_t>(s_clim + j * fbytes);
+      if (plan->has_mask)
+        h_mask[j] = reinterpret_cast<uint64_t>(s_mask + j * mbytes);
+    }
+    if (plan->has_wo)
+      memcpy(host.data() + o_wo, plan->wo.data() + j0, nj * 8);
+    memcpy(host.data() + o_cell, plan->cell.data() + j0, nj * 4);
+    memcpy(host.data() + o_first, first.data(), first.size() * 4);
+    memcpy(host.data() + o_cw, cw.data(), cw.size() * 8);
+    rc = ctx->stage_tables[buf].reserve(off);
+    if (rc != WBX_OK) return rc;
+    unsigned char* tbase = ctx->stage_tables[buf].as<unsigned char>();
+    WBX_CUDA(cudaMemcpyAsync(tbase, host.data(), off, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    WBX_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+
+    wbx::DetParams P{};
+    P.pred = reinterpret_cast<const uint64_t*>(tbase + o_pred);
+    P.target = reinterpret_cast<const uint64_t*>(tbase + o_tgt);
+    P.clim = plan->has_clim ? reinterpret_cast<const uint64_t*>(tbase + o_clim)
+                            : nullptr;
+    P.mask = plan->has_mask ? reinterpret_cast<const uint64_t*>(tbase + o_mask)
+                            : nullptr;
+    P.w_outer =
+        plan->has_wo ? reinterpret_cast<const double*>(tbase + o_wo) : nullptr;
+    P.cell = reinterpret_cast<const int32_t*>(tbase + o_cell);
+    P.w_y = plan->d_wy;
+    P.w_x = plan->d_wx;
+    P.n_jobs = static_cast<long long>(nj);
+    P.total_tiles = static_cast<long long>(nj) * plan->tiles_per_slab;
+    P.cell_base = plan->cell[j0];
+    P.ny = static_cast<int>(plan->ny);
+    P.nx = static_cast<int>(plan->nx);
+    P.slab = static_cast<int>(slab);
+    P.tile = plan->tile;
+    P.tiles_per_slab = plan->tiles_per_slab;
+    const int grid = wbx::grid_for(ctx, plan, P.total_tiles);
+    const int n_cells = static_cast<int>(cw.size());
+    const size_t rec_bytes = (static_cast<size_t>(grid) + n_cells) * warps *
+                             plan->nacc * sizeof(double);
+    // records are reused by consecutive chunks on the same compute stream, so
+    // stream order already serialises their use.
+    rc = ctx->records.reserve(rec_bytes);
+    if (rc != WBX_OK) return rc;
+    P.records = ctx->records.as<double>();
+    WBX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+    rc = wbx::launch_main(ctx, plan, P, grid);
+    if (rc != WBX_OK) return rc;
+    rc = wbx::launch_finalize(
+        ctx, plan, P.records,
+        reinterpret_cast<const int32_t*>(tbase + o_first),
+        reinterpret_cast<const double*>(tbase + o_cw), n_cells, grid,
+        P.total_tiles, d_ws + static_cast<size_t>(P.cell_base) * WBX_NUM_DET_STATS,
+        d_w + static_cast<size_t>(P.cell_base) * WBX_NUM_DET_WCLASSES, 1);
+    if (rc != WBX_OK) return rc;
+    WBX_CUDA(cudaEventRecord(ctx->ev_compute[buf], ctx->stream));
+  }
+  return WBX_OK;
+}
+
+int wbx_det_plan_run(wbx_ctx* ctx, wbx_det_plan* plan, double* sum_ws,
+                     double* sum_w, int32_t out_space, int32_t accumulate) {
+  WBX_REQUIRE(ctx && plan && sum_ws && sum_w, "wbx_det_plan_run: NULL argument");
+  WBX_REQUIRE(out_space == WBX_SPACE_DEVICE || out_space == WBX_SPACE_HOST,
+              "wbx_det_plan_run: bad out_space");
+  WBX_REQUIRE(!(accumulate && out_space == WBX_SPACE_HOST),
+              "wbx_det_plan_run: accumulate needs device outputs");
+  WBX_REQUIRE(!(accumulate && plan->space == WBX_SPACE_HOST),
+              "wbx_det_plan_run: accumulate is not supported for host-space "
+              "plans");
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  const size_t ws_bytes = plan->n_cells * WBX_NUM_DET_STATS * sizeof(double);
+  const size_t w_bytes = plan->n_cells * WBX_NUM_DET_WCLASSES * sizeof(double);
+  double* d_ws = sum_ws;
+  double* d_w = sum_w;
+  if (out_space == WBX_SPACE_HOST) {
+    int rc = ctx->out_ws.reserve(ws_bytes);
+    if (rc != WBX_OK) return rc;
+    rc = ctx->out_w.reserve(w_bytes);
+    if (rc != WBX_OK) return rc;
+    d_ws = ctx->out_ws.as<double>();
+    d_w = ctx->out_w.as<double>();
+  }
+  int rc = plan->space == WBX_SPACE_DEVICE
+               ? run_device_space(ctx, plan, d_ws, d_w, accumulate)
+               : run_host_space(ctx, plan, d_ws, d_w);
+  if (rc != WBX_OK) return rc;
+  if (out_space == WBX_SPACE_HOST) {
+    rc = wbx::ensure_pinned_out(ctx, ws_bytes + w_bytes);
+    if (rc != WBX_OK) return rc;
+    unsigned char* pin = static_cast<unsigned char*>(ctx->pinned_out);
+    WBX_CUDA(cudaMemcpyAsync(pin, d_ws, ws_bytes, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    WBX_CUDA(cudaMemcpyAsync(pin + ws_bytes, d_w, w_bytes,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(sum_ws, pin, ws_bytes);
+    memcpy(sum_w, pin + ws_bytes, w_bytes);
+  }
+  return WBX_OK;
+}
+
+int wbx_det_reduce(wbx_ctx* ctx, const wbx_det_desc* desc, double* sum_ws,
+                   double* sum_w) {
+  wbx_det_plan* plan = nullptr;
+  int rc = wbx_det_plan_create(ctx, desc, &plan);
+  if (rc != WBX_OK) return rc;
+  rc = wbx_det_plan_run(ctx, plan, sum_ws, sum_w, WBX_SPACE_HOST, 0);
+  wbx_det_plan_destroy(ctx, plan);
+  return rc;
+}
+
+int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
+                        const float* target, const float* clim, int64_t n,
+                        float* out) {
+  WBX_REQUIRE(ctx && pred && target && out, "wbx_det_elementwise: NULL argument");
+  WBX_REQUIRE(stat >= 0 && stat < WBX_NUM_DET_STATS,
+              "wbx_det_elementwise: bad statistic %d", stat);
+  WBX_REQUIRE(stat < WBX_STAT_SQ_PRED_ANOM || clim != nullptr,
+              "wbx_det_elementwise: statistic %d needs a climatology", stat);
+  WBX_REQUIRE(n >= 0, "wbx_det_elementwise: negative n");
+  if (n == 0) return WBX_OK;
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  const int block = 256;
+  const long long want = (n + block - 1) / block;
+  const int grid = static_cast<int>(
+      std::min<long long>(want, static_cast<long long>(ctx->sm_count) * 16));
+  wbx::det_elementwise_kernel<<<grid, block, 0, ctx->stream>>>(
+      stat, pred, target, clim, n, out);
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return WBX_OK;
+}
+
+}  // extern "C"

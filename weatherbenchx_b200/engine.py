@@ -1,0 +1,509 @@
+"""Planner and launcher: turns (lazy statistics, Aggregator settings) into job
+tables for the C ABI (include/wbx_b200.h) and turns the results back into
+labelled arrays.
+
+What the reference does per statistic and variable
+(aggregation.py:337-366): build a mask, zero-fill, ``xr.dot(stat, *weights,
+*bin_masks, dim=reduce_dims)`` twice.  Here every statistic that shares its
+operands is served by ONE fused kernel launch: the trailing run of reduced,
+contiguous dims (typically latitude x longitude) becomes the *slab* the kernel
+streams; every combination of the remaining (outer) dims is a *job* with its own
+operand addresses -- which is how broadcasting, reduced outer dims and the
+climatology (dayofyear, hour) gather are expressed without copying data.
+
+No arithmetic on field data happens in this module.
+"""
+
+from __future__ import annotations
+
+import collections
+import dataclasses
+from typing import Hashable, Mapping, Sequence
+
+import numpy as np
+
+from weatherbenchx_b200 import _cabi
+from weatherbenchx_b200 import xarray_lite as xl
+from weatherbenchx_b200.lazy import AlignedClimatology, LazyStatistic
+
+
+class FastPathUnavailable(Exception):
+  """The fused slab kernel cannot express this aggregation."""
+
+
+# ---------------------------------------------------------------------------
+# Payload helpers (torch is plumbing: device memory + dtype/layout fixes)
+# ---------------------------------------------------------------------------
+
+
+def _torch():
+  import torch  # pylint: disable=g-import-not-at-top
+  return torch
+
+
+def to_device(da: xl.DataArray, device: int | None = None) -> xl.DataArray:
+  """DataArray whose payload is a float32/uint8 CUDA tensor."""
+  torch = _torch()
+  if da.is_device:
+    return da
+  arr = np.ascontiguousarray(da.to_numpy())
+  if arr.dtype.kind == 'f' and arr.dtype != np.float32:
+    arr = arr.astype(np.float32)
+  dev = torch.device('cuda', torch.cuda.current_device()
+                     if device is None else device)
+  tensor = torch.from_numpy(arr).to(dev, non_blocking=False)
+  coords = dict(da.coords)
+  return da._replace(data=tensor, coords=coords)  # pylint: disable=protected-access
+
+
+class _Operand:
+  """Address arithmetic view of one operand (host ndarray or CUDA tensor)."""
+
+  def __init__(self, da: xl.DataArray, itemsize: int):
+    self.da = da
+    self.dims = da.dims
+    payload = da.data
+    self.payload = payload
+    if xl._is_device(payload):  # pylint: disable=protected-access
+      self.is_device = True
+      self.ptr = payload.data_ptr()
+      self.strides = dict(zip(da.dims, payload.stride()))
+    else:
+      self.is_device = False
+      self.ptr = payload.ctypes.data
+      self.strides = dict(
+          zip(da.dims, (s // payload.itemsize for s in payload.strides)))
+    self.itemsize = itemsize
+    self.sizes = da.sizes
+
+
+def _normalise(da: xl.DataArray, kind: str) -> xl.DataArray:
+  """float32 (fields) / uint8 (masks) payload, any memory space."""
+  payload = da.data
+  if kind == 'mask':
+    if xl._is_device(payload):  # pylint: disable=protected-access
+      torch = _torch()
+      if payload.dtype not in (torch.bool, torch.uint8):
+        payload = payload != 0
+      return da._replace(data=payload)  # pylint: disable=protected-access
+    if payload.dtype != np.bool_ and payload.dtype != np.uint8:
+      payload = payload != 0
+    return da._replace(data=payload.view(np.uint8)  # pylint: disable=protected-access
+                       if payload.dtype == np.bool_ else payload)
+  if xl._is_device(payload):  # pylint: disable=protected-access
+    torch = _torch()
+    if payload.dtype != torch.float32:
+      payload = payload.to(torch.float32)
+    return da._replace(data=payload)  # pylint: disable=protected-access
+  if payload.dtype != np.float32:
+    payload = payload.astype(np.float32)
+  return da._replace(data=payload)  # pylint: disable=protected-access
+
+
+def _inner_contiguous(op: _Operand, inner: Sequence[Hashable]) -> bool:
+  """True if ``inner`` are op's trailing dims and form a contiguous block."""
+  n = len(inner)
+  if tuple(op.dims[-n:]) != tuple(inner):
+    return False
+  expect = 1
+  for d in reversed(inner):
+    if op.sizes[d] != 1 and op.strides[d] != expect:
+      return False
+    expect *= op.sizes[d]
+  return True
+
+
+def _make_contiguous(da: xl.DataArray) -> xl.DataArray:
+  payload = da.data
+  if xl._is_device(payload):  # pylint: disable=protected-access
+    return da._replace(data=payload.contiguous())  # pylint: disable=protected-access
+  return da._replace(data=np.ascontiguousarray(payload))  # pylint: disable=protected-access
+
+
+# ---------------------------------------------------------------------------
+# Climatology alignment (index arithmetic only)
+# ---------------------------------------------------------------------------
+
+
+def _dayofyear_hour(valid_time: np.ndarray):
+  vt = np.asarray(valid_time).astype('datetime64[ns]')
+  day = vt.astype('datetime64[D]')
+  year0 = vt.astype('datetime64[Y]').astype('datetime64[D]')
+  doy = (day - year0).astype(np.int64) + 1
+  hour = ((vt - day.astype('datetime64[ns]')) //
+          np.timedelta64(1, 'h')).astype(np.int64)
+  return doy, hour
+
+
+def _label_positions(labels: np.ndarray, wanted: np.ndarray, dim: str):
+  labels = np.asarray(labels)
+  order = np.argsort(labels, kind='stable')
+  pos = np.searchsorted(labels[order], wanted)
+  pos = np.clip(pos, 0, len(labels) - 1)
+  found = order[pos]
+  if not np.array_equal(labels[found], wanted):
+    raise KeyError(f'not all values found in climatology index {dim!r}')
+  return found.astype(np.int64)
+
+
+def align_climatology(predictions: xl.DataArray,
+                      climatology: xl.DataArray) -> AlignedClimatology:
+  """Index form of metrics/base.py:383-403 (valid_time -> dayofyear/hour)."""
+  coords = predictions.coords
+  if 'valid_time' in coords:
+    vt = coords['valid_time']
+    valid, time_dims = vt.to_numpy(), vt.dims
+  elif 'init_time' in coords and 'lead_time' in coords:
+    it, lt = coords['init_time'], coords['lead_time']
+    if it.ndim != 1 or lt.ndim != 1:
+      raise ValueError('init_time / lead_time coordinates must be 1-d')
+    valid = it.to_numpy()[:, None] + lt.to_numpy()[None, :]
+    time_dims = (it.dims[0], lt.dims[0])
+  else:
+    raise ValueError('Predictions should have either valid_time or '
+                     'init/lead_time dimensions.')
+  positions = {}
+  if 'time' in climatology.coords and 'time' in climatology.dims:
+    positions['time'] = _label_positions(
+        climatology.coords['time'].to_numpy(), valid, 'time')
+  else:
+    doy, hour = _dayofyear_hour(valid)
+    positions['dayofyear'] = _label_positions(
+        climatology.coords['dayofyear'].to_numpy(), doy, 'dayofyear')
+    if 'hour' in climatology.dims:
+      positions['hour'] = _label_positions(
+          climatology.coords['hour'].to_numpy(), hour, 'hour')
+  return AlignedClimatology(climatology, tuple(time_dims), positions)
+
+
+# ---------------------------------------------------------------------------
+# Fused aggregation
+# ---------------------------------------------------------------------------
+
+_PLAN_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
+_PLAN_CACHE_SIZE = 32
+
+
+def clear_plan_cache():
+  for plan in _PLAN_CACHE.values():
+    plan.close()
+  _PLAN_CACHE.clear()
+
+
+def _job_offsets(job_dims, job_sizes, strides: Mapping) -> np.ndarray:
+  """Element offset of every job (row-major over job_dims) for one operand."""
+  total = np.zeros([1] * len(job_dims), dtype=np.int64)
+  for axis, d in enumerate(job_dims):
+    if d in strides and strides[d] != 0:
+      shape = [1] * len(job_dims)
+      shape[axis] = job_sizes[axis]
+      total = total + (np.arange(job_sizes[axis], dtype=np.int64) *
+                       strides[d]).reshape(shape)
+  return np.broadcast_to(total, job_sizes).reshape(-1)
+
+
+def _weight_vector(dims, sizes, per_dim: Mapping) -> np.ndarray | None:
+  """Outer product of 1-d weights over ``dims`` flattened row-major."""
+  if not any(d in per_dim for d in dims):
+    return None
+  out = np.ones([sizes[d] for d in dims], dtype=np.float64)
+  for axis, d in enumerate(dims):
+    if d in per_dim:
+      shape = [1] * len(dims)
+      shape[axis] = sizes[d]
+      out = out * per_dim[d].reshape(shape)
+  return out.reshape(-1)
+
+
+@dataclasses.dataclass
+class FusedSpec:
+  """Everything wbx_det_plan_create needs, plus how to label the results."""
+  space: int
+  flags: int
+  ny: int
+  nx: int
+  n_cells: int
+  pred: np.ndarray
+  target: np.ndarray
+  clim: np.ndarray | None
+  mask: np.ndarray | None
+  cell: np.ndarray
+  w_outer: np.ndarray | None
+  w_y: np.ndarray | None
+  w_x: np.ndarray | None
+  scalar: float
+  kept: list
+  kept_shape: list
+  coords: dict
+  keepalive: tuple
+  cache_key: tuple
+
+
+def build_fused_spec(stats: Sequence[LazyStatistic],
+                     reduce_dims: Sequence[Hashable],
+                     weights: Sequence[xl.DataArray] = (),
+                     masked: bool = False, skipna: bool = False,
+                     flags_extra: int = 0,
+                     device: int | None = None) -> FusedSpec | None:
+  """Plans one fused launch for statistics that share operands (no GPU use).
+
+  Returns None when the aggregation does not apply (reduce dims missing,
+  aggregation.py:305-309); raises FastPathUnavailable when the slab kernel
+  cannot express the request.
+  """
+  # The statistic that carries the climatology (if any) defines the launch;
+  # climatology-free statistics of the same operands ride along for free.
+  stats = sorted(stats, key=lambda s: s.climatology is None)
+  first = stats[0]
+  dims = first.dims
+  sizes = first.sizes
+  reduce_set = set(reduce_dims)
+  if not reduce_set.issubset(dims):
+    return None
+  for s in stats:
+    same_ops = s.group_key()[:2] == first.group_key()[:2]
+    same_clim = (s.climatology is None or
+                 s.group_key()[2] == first.group_key()[2])
+    if not (same_ops and same_clim) or s.dims != dims:
+      raise ValueError('statistics in one fused group must share operands')
+    if s.kind not in _cabi.STAT_SLOT:
+      raise FastPathUnavailable(f'{s.kind} is not a fused statistic')
+
+  def canonical(da, kind):
+    # operand dims follow the statistic's dim order (a view; copied later only
+    # if the slab is not contiguous).
+    order = tuple(d for d in dims if d in da.dims)
+    if order != da.dims:
+      da = da.transpose(*order)
+    return _normalise(da, kind)
+
+  pred = canonical(first.predictions, 'field')
+  tgt = canonical(first.targets, 'field')
+  clim = first.climatology
+  clim_da = _normalise(clim.climatology, 'field') if clim is not None else None
+  mask_da = None
+  if masked and 'mask' in first.coords:
+    mask_da = canonical(first.coords['mask'], 'mask')
+
+  # ---- weights: scalars, 1-d vectors; anything else needs the generic path.
+  scalar = 1.0
+  per_dim: dict = {}
+  for w in weights:
+    if w.ndim == 0:
+      scalar *= float(w.to_numpy())
+    elif w.ndim == 1 and w.dims[0] in dims:
+      d = w.dims[0]
+      vec = np.asarray(w.to_numpy(), dtype=np.float64)
+      if len(vec) != sizes[d]:
+        raise ValueError(f'weight along {d!r} has wrong length')
+      per_dim[d] = per_dim[d] * vec if d in per_dim else vec
+    else:
+      raise FastPathUnavailable('multi-dimensional weights')
+
+  # ---- slab = trailing run of reduced dims present in every operand.
+  operands = [pred, tgt] + ([mask_da] if mask_da is not None else [])
+  inner: list = []
+  for d in reversed(dims):
+    if d not in reduce_set:
+      break
+    trial = [d] + inner
+    ok = all(tuple(o.dims[-len(trial):]) == tuple(trial) for o in operands)
+    if clim is not None:
+      ok = ok and tuple(clim_da.dims[-len(trial):]) == tuple(trial)
+    if not ok:
+      break
+    inner = trial
+  while inner and np.prod([sizes[d] for d in inner]) >= (1 << 30):
+    inner = inner[1:]
+  if not inner:
+    raise FastPathUnavailable('no contiguous reduced trailing dims')
+
+  def contiguous_operand(da):
+    op = _Operand(da, 4)
+    if not _inner_contiguous(op, inner):
+      da = _make_contiguous(da)
+    return da
+
+  pred, tgt = contiguous_operand(pred), contiguous_operand(tgt)
+  if clim_da is not None:
+    clim_da = contiguous_operand(clim_da)
+  if mask_da is not None:
+    mask_da = contiguous_operand(mask_da)
+
+  # ---- memory space: all host -> streamed by the library; else all device.
+  fields = [pred, tgt] + [x for x in (clim_da, mask_da) if x is not None]
+  if any(f.is_device for f in fields) and not all(f.is_device for f in fields):
+    pred, tgt = to_device(pred, device), to_device(tgt, device)
+    clim_da = to_device(clim_da, device) if clim_da is not None else None
+    mask_da = to_device(mask_da, device) if mask_da is not None else None
+  space = _cabi.SPACE_DEVICE if pred.is_device else _cabi.SPACE_HOST
+
+  op_p, op_t = _Operand(pred, 4), _Operand(tgt, 4)
+  op_c = _Operand(clim_da, 4) if clim_da is not None else None
+  op_m = _Operand(mask_da, 1) if mask_da is not None else None
+
+  outer = [d for d in dims if d not in inner]
+  kept = [d for d in outer if d not in reduce_set]
+  red_outer = [d for d in outer if d in reduce_set]
+  job_dims = kept + red_outer
+  job_sizes = [sizes[d] for d in job_dims]
+  n_cells = int(np.prod([sizes[d] for d in kept], dtype=np.int64)) if kept else 1
+  per_cell = int(np.prod([sizes[d] for d in red_outer], dtype=np.int64)
+                 ) if red_outer else 1
+  y_dims, x_dim = inner[:-1], inner[-1]
+  ny = int(np.prod([sizes[d] for d in y_dims], dtype=np.int64)) if y_dims else 1
+  nx = sizes[x_dim]
+
+  flags = flags_extra
+  if skipna:
+    flags |= _cabi.FLAG_SKIPNA
+  if op_m is not None:
+    flags |= _cabi.FLAG_MASKED
+
+  cache_key = (
+      space, flags, tuple(dims), tuple(sizes[d] for d in dims), tuple(inner),
+      tuple(sorted(reduce_set, key=str)),
+      op_p.ptr, tuple(op_p.strides.items()), op_t.ptr,
+      tuple(op_t.strides.items()),
+      (op_c.ptr, tuple(op_c.strides.items()),
+       tuple((k, v.tobytes()) for k, v in clim.positions.items()))
+      if op_c is not None else None,
+      (op_m.ptr, tuple(op_m.strides.items())) if op_m is not None else None,
+      tuple((str(d), v.tobytes()) for d, v in sorted(
+          per_dim.items(), key=lambda kv: str(kv[0]))),
+  )
+
+  def addresses(op: _Operand) -> np.ndarray:
+    off = _job_offsets(job_dims, job_sizes, op.strides)
+    return (np.uint64(op.ptr) +
+            (off * op.itemsize).astype(np.uint64)).astype(np.uint64)
+
+  clim_addr = None
+  if op_c is not None:
+    strides = {d: s for d, s in op_c.strides.items()
+               if d not in clim.positions}
+    off = _job_offsets(job_dims, job_sizes, strides).copy()
+    # gather term over the prediction time dims
+    term = np.zeros(next(iter(clim.positions.values())).shape, np.int64)
+    for cd, pos in clim.positions.items():
+      term = term + pos * op_c.strides[cd]
+    shape = [1] * len(job_dims)
+    for td, n in zip(clim.time_dims, term.shape):
+      if td not in job_dims:
+        raise FastPathUnavailable('climatology time dim inside the slab')
+      shape[job_dims.index(td)] = n
+    order = np.argsort([job_dims.index(td) for td in clim.time_dims])
+    term = np.transpose(term, order).reshape(shape)
+    off = (off.reshape(job_sizes) + term).reshape(-1)
+    clim_addr = (np.uint64(op_c.ptr) +
+                 (off * 4).astype(np.uint64)).astype(np.uint64)
+
+  coords = {d: first.coords[d] for d in kept if d in first.coords}
+  for name, cv in first.coords.items():
+    if name not in coords and name != 'mask' and set(cv.dims) <= set(kept):
+      coords[name] = cv
+  return FusedSpec(
+      space=space, flags=flags, ny=ny, nx=nx, n_cells=n_cells,
+      pred=addresses(op_p), target=addresses(op_t), clim=clim_addr,
+      mask=addresses(op_m) if op_m is not None else None,
+      cell=np.repeat(np.arange(n_cells, dtype=np.int32), per_cell),
+      w_outer=_weight_vector(job_dims, sizes, per_dim),
+      w_y=_weight_vector(y_dims, sizes, per_dim), w_x=per_dim.get(x_dim),
+      scalar=scalar, kept=kept, kept_shape=[sizes[d] for d in kept],
+      coords=coords, keepalive=(pred, tgt, clim_da, mask_da),
+      cache_key=cache_key)
+
+
+def aggregate_fused(stats: Sequence[LazyStatistic],
+                    reduce_dims: Sequence[Hashable],
+                    weights: Sequence[xl.DataArray] = (),
+                    masked: bool = False, skipna: bool = False,
+                    flags_extra: int = 0, device: int | None = None):
+  """One fused launch for statistics that share operands.
+
+  Returns {kind: (sum_weighted_statistics, sum_weights)} as host DataArrays,
+  or None when the aggregation does not apply.  Raises FastPathUnavailable
+  when the slab kernel cannot express the request.
+  """
+  spec = build_fused_spec(stats, reduce_dims, weights, masked, skipna,
+                          flags_extra, device)
+  if spec is None:
+    return None
+  ctx = _cabi.get_context(device)
+  plan = _PLAN_CACHE.get(spec.cache_key)
+  if plan is not None and plan.ctx is not ctx:
+    plan = None
+  if plan is None:
+    plan = _cabi.DetPlan(
+        ctx, space=spec.space, flags=spec.flags, ny=spec.ny, nx=spec.nx,
+        pred=spec.pred, target=spec.target, clim=spec.clim, mask=spec.mask,
+        cell=spec.cell, n_cells=spec.n_cells, w_outer=spec.w_outer,
+        w_y=spec.w_y, w_x=spec.w_x)
+    _PLAN_CACHE[spec.cache_key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+      _, old = _PLAN_CACHE.popitem(last=False)
+      old.close()
+  else:
+    _PLAN_CACHE.move_to_end(spec.cache_key)
+  # Keep the operands alive for as long as the plan may be run.
+  plan.keepalive = spec.keepalive
+  if spec.space == _cabi.SPACE_DEVICE:
+    ctx.use_torch_stream()
+  ws, w = plan.run_to_host()
+  out = {}
+  for s in stats:
+    slot = _cabi.STAT_SLOT[s.kind]
+    sum_ws = (ws[:, slot] * spec.scalar).reshape(spec.kept_shape)
+    sum_w = (w[:, _cabi.STAT_WCLASS[slot]] * spec.scalar).reshape(
+        spec.kept_shape)
+    out[s.kind] = (
+        xl.DataArray(sum_ws, spec.kept, coords=spec.coords, name=s.name),
+        xl.DataArray(sum_w, spec.kept, coords=spec.coords, name=s.name),
+    )
+  return out
+
+
+# ---------------------------------------------------------------------------
+# Materialisation of a lazy statistic (elementwise kernel)
+# ---------------------------------------------------------------------------
+
+
+def _broadcast_device(da: xl.DataArray, dims, sizes, device=None):
+  da = to_device(_normalise(da, 'field'), device)
+  t = da.data
+  present = [d for d in dims if d in da.dims]
+  t = t.permute(*[da.dims.index(d) for d in present])
+  view = [sizes[d] if d in present else 1 for d in dims]
+  t = t.reshape(view).expand(*[sizes[d] for d in dims])
+  return t.contiguous() if not t.is_contiguous() else t
+
+
+def materialize(stat: LazyStatistic, device: int | None = None):
+  """Evaluates the statistic per grid point on the GPU; returns a CUDA tensor."""
+  torch = _torch()
+  dims, sizes = stat.dims, stat.sizes
+  p = _broadcast_device(stat.predictions, dims, sizes, device)
+  t = _broadcast_device(stat.targets, dims, sizes, device)
+  c = None
+  if stat.climatology is not None:
+    ac = stat.climatology
+    clim = to_device(_normalise(ac.climatology, 'field'), device)
+    ct = clim.data
+    cdims = list(clim.dims)
+    # move the climatology time dims to the front and gather
+    front = list(ac.clim_time_dims)
+    rest = [d for d in cdims if d not in front]
+    ct = ct.permute(*[cdims.index(d) for d in front + rest])
+    index = tuple(torch.as_tensor(ac.positions[d], device=ct.device)
+                  for d in front)
+    gathered = ct[index]
+    gdims = tuple(ac.time_dims) + tuple(rest)
+    c = _broadcast_device(
+        xl.DataArray(gathered, gdims), dims, sizes, device)
+  out = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+  ctx = _cabi.get_context(p.device.index)
+  ctx.use_torch_stream()
+  _cabi.det_elementwise(ctx, _cabi.STAT_SLOT[stat.kind], p.data_ptr(),
+                        t.data_ptr(), c.data_ptr() if c is not None else None,
+                        out.numel(), out.data_ptr())
+  return out

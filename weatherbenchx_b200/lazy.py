@@ -1,0 +1,140 @@
+"""Deferred per-gridpoint statistics.
+
+``Statistic.compute`` in the reference returns fully materialised DataArrays
+(metrics/base.py:135-158), which the Aggregator then reads again
+(aggregation.py:337-366).  Here ``compute`` returns a ``LazyStatistic`` -- a
+DataArray-shaped handle that records *which* statistic of *which* operands is
+meant.  ``Aggregator`` recognises the handle and runs the fused CUDA kernel
+(statistic + weights + reduction in one pass over HBM); any other consumer that
+touches ``.data`` / ``.values`` gets the materialised field, evaluated on the
+GPU by the elementwise kernel.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from typing import Sequence
+
+import numpy as np
+
+from weatherbenchx_b200 import xarray_lite as xl
+
+
+@dataclasses.dataclass
+class AlignedClimatology:
+  """Climatology + the (dayofyear[, hour]) gather that aligns it.
+
+  Restates metrics/base.py:383-403 as index arrays instead of a materialised
+  ``climatology.sel(...)``: ``time_dims`` are the prediction dims the valid
+  time depends on, ``positions[clim_dim]`` the integer position along
+  ``clim_dim`` for every valid time.
+  """
+  climatology: xl.DataArray          # dims e.g. (dayofyear, hour, level, lat, lon)
+  time_dims: tuple                   # ('init_time', 'lead_time') or ('valid_time',)
+  positions: dict                    # clim time dim -> int64 array over time_dims
+
+  @property
+  def clim_time_dims(self) -> tuple:
+    return tuple(self.positions)
+
+  @property
+  def dims(self) -> tuple:
+    rest = tuple(d for d in self.climatology.dims
+                 if d not in self.positions)
+    return self.time_dims + rest
+
+  @property
+  def sizes(self) -> dict:
+    first = next(iter(self.positions.values()))
+    out = dict(zip(self.time_dims, first.shape))
+    for d, n in self.climatology.sizes.items():
+      if d not in self.positions:
+        out[d] = n
+    return out
+
+
+class LazyStatistic(xl.DataArray):
+  """A per-gridpoint statistic that is evaluated on demand."""
+
+  def __init__(self, kind: str, predictions: xl.DataArray,
+               targets: xl.DataArray,
+               climatology: AlignedClimatology | None = None):
+    xl._check_index_coords(predictions, targets)  # pylint: disable=protected-access
+    dims = predictions.dims + tuple(
+        d for d in targets.dims if d not in predictions.dims)
+    sizes = dict(targets.sizes, **predictions.sizes)
+    if climatology is not None:
+      for d, n in climatology.sizes.items():
+        if d in sizes and sizes[d] != n:
+          raise ValueError(
+              f'climatology size {n} != data size {sizes[d]} along {d!r}')
+        if d not in sizes:
+          dims = dims + (d,)
+          sizes[d] = n
+    self.kind = kind
+    self.predictions = predictions
+    self.targets = targets
+    self.climatology = climatology
+    self.dims = dims
+    self._sizes = {d: sizes[d] for d in dims}
+    self.name = predictions.name
+    self.attrs = {}
+    self._coords = xl._merge_coords(predictions, targets, dims)  # pylint: disable=protected-access
+    self._materialized = None
+
+  # -- metadata without materialising ---------------------------------------
+
+  @property
+  def shape(self):
+    return tuple(self._sizes[d] for d in self.dims)
+
+  @property
+  def sizes(self):
+    return dict(self._sizes)
+
+  @property
+  def dtype(self):
+    return np.dtype(np.float32)
+
+  @property
+  def is_device(self) -> bool:
+    return True
+
+  @property
+  def is_lazy(self) -> bool:
+    return self._materialized is None
+
+  def group_key(self):
+    """Statistics with the same key can share one pass over the operands."""
+    clim = self.climatology
+    return (id(self.predictions), id(self.targets),
+            id(clim.climatology) if clim is not None else None)
+
+  def __repr__(self):
+    return f'<LazyStatistic {self.kind} {self.name!r} {self.sizes}>'
+
+  # -- materialisation --------------------------------------------------------
+
+  @property
+  def _data(self):
+    if self._materialized is None:
+      from weatherbenchx_b200 import engine  # pylint: disable=g-import-not-at-top
+      self._materialized = engine.materialize(self)
+    return self._materialized
+
+  @_data.setter
+  def _data(self, value):
+    self._materialized = value
+
+  def _replace(self, data=None, dims=None, coords=None, name='__keep__'):
+    out = xl.DataArray.__new__(xl.DataArray)
+    out._data = self._data if data is None else xl._as_payload(data)  # pylint: disable=protected-access
+    out.dims = self.dims if dims is None else tuple(dims)
+    out.name = self.name if name == '__keep__' else name
+    out.attrs = dict(self.attrs)
+    out._coords = dict(self._coords if coords is None else coords)
+    return out
+
+
+def statistic_names(stats: Sequence[LazyStatistic]) -> list:
+  return [s.kind for s in stats]
