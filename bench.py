@@ -1,0 +1,452 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the WeatherBench-X statistic + aggregation hot path.
+
+Headline workload (BASELINE.json metric: grid-points/sec for lat-weighted RMSE
+on 0.25 degree fields): one step = one pass of lat-weighted RMSE
+(SquaredError statistic x GridAreaWeighting, reduced over init_time, latitude,
+longitude) over a batch of 5 variables x 20 init_times x 721 x 1440 float32
+prediction/target fields = 103.8 M grid points, 830 MB read (8 algorithmic
+bytes per point).  Inputs are synthetic (Gaussian, ERA5-like magnitudes).
+
+  value  : device-resident inputs, K timed steps, CUDA events, max over ranks.
+  e2e    : the same step through the public class API
+           (aggregation.compute_metric_values_for_single_chunk) with HOST
+           (pinned) numpy inputs; host->device streaming and the device->host
+           read of the result are inside the timed region.
+  --impl reference : the reference's CPU path (NumPy restatement that mirrors
+           it op for op: oracle/wbx_oracle.py::reference_path_rmse) on all host
+           cores, same workload.
+
+N > 1 (torchrun): weak scaling -- every rank owns its own batch of the same
+shape (shards of (variable, init_time)); each step ends with ONE all-reduce of
+the packed float64 AggregationState over NCCL.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+N_VARS, N_INIT, NLAT, NLON = 5, 20, 721, 1440
+VAR_NAMES = ['2m_temperature', '10m_u_component_of_wind',
+             '10m_v_component_of_wind', 'mean_sea_level_pressure',
+             'total_precipitation_6hr']
+POINTS_PER_STEP = N_VARS * N_INIT * NLAT * NLON
+ALG_BYTES_PER_POINT = 8  # read prediction + target once
+METRIC = 'grid-points/sec, lat-weighted RMSE on 0.25deg (721x1440) fields'
+WORKLOAD = (f'lat-weighted RMSE (SquaredError x GridAreaWeighting, reduce '
+            f'init_time/latitude/longitude), {N_VARS} vars x {N_INIT} init x '
+            f'{NLAT}x{NLON} f32')
+
+
+def measured_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as f:
+      return json.load(f).get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json)'
+  return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+  """nvidia-smi clock / throttle sampling during the timed region."""
+
+  QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,'
+           'clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,'
+           'clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, device_index: int):
+    self.device_index = device_index
+    self.proc = None
+    self.lines = []
+    self.thread = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--query-gpu={self.QUERY}',
+           '--format=csv,noheader,nounits', '-lms', '100',
+           '-i', str(self.device_index)],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+      self.proc = None
+      return
+
+    def pump():
+      for line in self.proc.stdout:
+        self.lines.append((time.time(), line.strip()))
+
+    self.thread = threading.Thread(target=pump, daemon=True)
+    self.thread.start()
+
+  def stop(self, windows):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, smax, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    for ts, line in self.lines:
+      if not any(a <= ts <= b for a, b in windows):
+        continue
+      parts = [x.strip() for x in line.split(',')]
+      if len(parts) < 9:
+        continue
+      try:
+        sm.append(float(parts[1]))
+        smax.append(float(parts[2]))
+      except ValueError:
+        continue
+      for name, val in zip(names, parts[5:9]):
+        if val.lower().startswith('active'):
+          reasons.add(name)
+    return {
+        'sm_mhz': float(np.median(sm)) if sm else None,
+        'sm_max_mhz': float(max(smax)) if smax else None,
+        'reasons': sorted(reasons), 'samples': len(sm),
+    }
+
+
+# ---------------------------------------------------------------------------
+# reference arm (CPU)
+# ---------------------------------------------------------------------------
+
+_W = {}
+
+
+def _ref_worker_init(seed, n_init):
+  import wbx_oracle as oracle
+  rng = np.random.default_rng(seed)
+  _W['p'] = rng.standard_normal((n_init, NLAT, NLON), dtype=np.float32)
+  _W['t'] = rng.standard_normal((n_init, NLAT, NLON), dtype=np.float32)
+  _W['w'] = oracle.grid_area_weights(np.linspace(-90, 90, NLAT))
+  _W['oracle'] = oracle
+
+
+def _ref_worker_step(n):
+  return _W['oracle'].reference_path_rmse(_W['p'][:n], _W['t'][:n], _W['w'])
+
+
+def run_reference(args):
+  """The reference's CPU path on all host cores (kind: port, see module doc)."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  import multiprocessing as mp
+  cores = os.cpu_count() or 1
+  total_units = N_VARS * N_INIT          # (variable, init_time) fields per step
+  workers = min(cores, total_units)
+  # every worker owns a contiguous block of (variable, init_time) fields; the
+  # parent sums the per-worker states (the CombinePerKey of the reference).
+  per = [total_units // workers + (1 if i < total_units % workers else 0)
+         for i in range(workers)]
+  ctx = mp.get_context('fork')
+  pools = []
+  for i, n in enumerate(per):
+    pool = ctx.Pool(1, initializer=_ref_worker_init, initargs=(1000 + i, n))
+    pools.append(pool)
+  counts = list(per)
+
+  def step():
+    results = [p.apply_async(_ref_worker_step, (n,))
+               for p, n in zip(pools, counts)]
+    sws = sum(r.get()[0] for r in results)
+    sw = sum(r.get()[1] for r in results)
+    return float(np.sqrt(sws / sw))
+  step()
+  t0 = time.perf_counter()
+  step()
+  t_full = time.perf_counter() - t0
+  # Bound the whole run to ~150 s: if K full passes would take longer, every
+  # step processes a fixed fraction of each worker's fields instead.
+  budget = 150.0
+  frac = min(1.0, budget / max(t_full * (args.steps + args.warmup), 1e-9))
+  counts = [max(1, int(n * frac)) for n in per]
+  points = sum(counts) * NLAT * NLON
+  for _ in range(args.warmup):
+    step()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    step()
+  dt = time.perf_counter() - t0
+  for p in pools:
+    p.terminate()
+  value = points * args.steps / dt
+  line = {
+      'impl': 'reference', 'metric': METRIC, 'value': value,
+      'unit': 'grid-points/s', 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': WORKLOAD, 'points_per_step': POINTS_PER_STEP},
+      'cpu_baseline': {
+          'value': value, 'unit': 'grid-points/s', 'cores': workers,
+          'kind': 'port',
+          'sample': (f'{points} of {POINTS_PER_STEP} grid points per step '
+                     f'({sum(counts)} of {total_units} fields); '
+                     'NumPy restatement mirroring the '
+                     'reference op for op (unfused temporaries, ones_like, '
+                     'two einsums); xarray label overhead not included '
+                     '(xarray not installable)')},
+      'e2e': {'value': value, 'unit': 'grid-points/s',
+              'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+
+
+def cpu_baseline_sample():
+  """Single-process NumPy reference path on a bounded sample (rank 0, N=1)."""
+  import wbx_oracle as oracle
+  n_init = 4
+  rng = np.random.default_rng(0)
+  p = rng.standard_normal((n_init, NLAT, NLON), dtype=np.float32)
+  t = rng.standard_normal((n_init, NLAT, NLON), dtype=np.float32)
+  w = oracle.grid_area_weights(np.linspace(-90, 90, NLAT))
+  oracle.reference_path_rmse(p, t, w)
+  reps, t0 = 0, time.perf_counter()
+  while time.perf_counter() - t0 < 8.0:
+    oracle.reference_path_rmse(p, t, w)
+    reps += 1
+  dt = time.perf_counter() - t0
+  return {
+      'value': reps * n_init * NLAT * NLON / dt, 'unit': 'grid-points/s',
+      'cores': 1, 'kind': 'port',
+      'sample': (f'{reps} passes over {n_init} x {NLAT} x {NLON} f32 fields '
+                 f'({dt:.1f} s), single NumPy process, reference-mirroring '
+                 'path (oracle.reference_path_rmse)'),
+  }
+
+
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  from weatherbenchx_b200 import _cabi, aggregation, weighting
+  from weatherbenchx_b200 import xarray_lite as xl
+  from weatherbenchx_b200.metrics import deterministic
+  import wbx_oracle as oracle
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise RuntimeError('bench.py needs a B200; there is no CPU fallback')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  ctx = _cabi.get_context(local_rank)
+  ctx.use_torch_stream()
+
+  lat = np.linspace(-90, 90, NLAT)
+  lon = np.linspace(0, 360, NLON, endpoint=False)
+  w_lat = oracle.grid_area_weights(lat)  # checker-side weights for the sanity assert
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(1000 + rank)
+  # device-resident batch: [var, init, lat, lon]
+  tgt = torch.empty((N_VARS, N_INIT, NLAT, NLON), device=dev)
+  prd = torch.empty_like(tgt)
+  for v in range(N_VARS):
+    tgt[v].normal_(280.0, 10.0, generator=gen)
+    prd[v].copy_(tgt[v]).add_(torch.empty_like(tgt[v]).normal_(
+        0.0, 2.0, generator=gen))
+  slab_bytes = NLAT * NLON * 4
+  jobs = [(v, i) for v in range(N_VARS) for i in range(N_INIT)]
+  gaw = weighting.GridAreaWeighting().weights(
+      xl.DataArray(np.zeros(NLAT), ('latitude',), coords={'latitude': lat}))
+  plan = _cabi.DetPlan(
+      ctx, space=_cabi.SPACE_DEVICE, flags=0, ny=NLAT, nx=NLON,
+      pred=np.array([prd.data_ptr() + (v * N_INIT + i) * slab_bytes
+                     for v, i in jobs], np.uint64),
+      target=np.array([tgt.data_ptr() + (v * N_INIT + i) * slab_bytes
+                       for v, i in jobs], np.uint64),
+      cell=np.array([v for v, _ in jobs], np.int32), n_cells=N_VARS,
+      w_y=gaw.values)
+  out_ws = torch.zeros((N_VARS, 6), dtype=torch.float64, device=dev)
+  out_w = torch.zeros((N_VARS, 4), dtype=torch.float64, device=dev)
+  packed = torch.zeros((N_VARS, 10), dtype=torch.float64, device=dev)
+
+  def step():
+    plan.run_to_device(out_ws.data_ptr(), out_w.data_ptr())
+    if world > 1:
+      packed[:, :6].copy_(out_ws)
+      packed[:, 6:].copy_(out_w)
+      dist.all_reduce(packed)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(max(args.warmup, 3)):
+    step()
+  barrier()
+  # sanity: the number being timed is the right number (rank-local state).
+  plan.run_to_device(out_ws.data_ptr(), out_w.data_ptr())
+  torch.cuda.synchronize()
+  d = (prd[0].double() - tgt[0].double())
+  ref = float(((d * d) * torch.as_tensor(w_lat, device=dev)[None, :, None]).sum())
+  got = float(out_ws[0, 2])
+  assert abs(got - ref) <= 1e-5 * abs(ref), (got, ref)
+
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+    time.sleep(0.3)
+  barrier()
+  launches0 = ctx.kernel_launches()
+  ctx.profile(True)
+  ctx.kernel_time(reset=True)
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  win0 = time.time()
+  ev0.record()
+  for _ in range(args.steps):
+    step()
+  ev1.record()
+  barrier()
+  win1 = time.time()
+  elapsed_ms = ev0.elapsed_time(ev1)
+  kernel_ms, kernel_n = ctx.kernel_time(reset=True)
+  ctx.profile(False)
+  launches = ctx.kernel_launches() - launches0
+  if world > 1:
+    tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(tmax.item())
+  value = world * POINTS_PER_STEP * args.steps / (elapsed_ms * 1e-3)
+
+  # ---- e2e: public class API, host (pinned) inputs --------------------------
+  e2e_steps = max(1, min(args.steps, args.e2e_steps))
+  host_p = torch.empty((N_VARS, N_INIT, NLAT, NLON), dtype=torch.float32,
+                       pin_memory=True)
+  host_t = torch.empty_like(host_p).pin_memory()
+  host_p.copy_(prd)
+  host_t.copy_(tgt)
+  torch.cuda.synchronize()
+  coords = {'init_time': np.arange(N_INIT), 'latitude': lat, 'longitude': lon}
+  dims = ('init_time', 'latitude', 'longitude')
+  preds = {n: xl.DataArray(host_p[v].numpy(), dims, coords=coords, name=n)
+           for v, n in enumerate(VAR_NAMES)}
+  tgts = {n: xl.DataArray(host_t[v].numpy(), dims, coords=coords, name=n)
+          for v, n in enumerate(VAR_NAMES)}
+  metrics = {'rmse': deterministic.RMSE()}
+  aggregator = aggregation.Aggregator(
+      reduce_dims=['init_time', 'latitude', 'longitude'],
+      weigh_by=[weighting.GridAreaWeighting()])
+
+  def e2e_step():
+    values = aggregation.compute_metric_values_for_single_chunk(
+        metrics, aggregator, preds, tgts)
+    if world > 1:
+      vec = torch.as_tensor(
+          np.array([values[f'rmse.{n}'].item() for n in VAR_NAMES]),
+          device=dev)
+      dist.all_reduce(vec)
+    return values
+
+  for _ in range(2):
+    values = e2e_step()
+  rmse0 = float(np.sqrt(out_ws[0, 2].item() / out_w[0, 0].item()))
+  assert abs(values[f'rmse.{VAR_NAMES[0]}'].item() - rmse0) <= 1e-6 * rmse0
+  barrier()
+  e0 = time.time()
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    e2e_step()
+  torch.cuda.synchronize()
+  e2e_s = time.perf_counter() - t0
+  e1 = time.time()
+  if world > 1:
+    tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    e2e_s = float(tmax.item())
+  e2e_value = world * POINTS_PER_STEP * e2e_steps / e2e_s
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+  clocks = sampler.stop([(win0, win1), (e0, e1)])
+  peak, peak_src = measured_peaks()
+  per_launch_ms = kernel_ms / max(kernel_n, 1)
+  achieved = POINTS_PER_STEP * ALG_BYTES_PER_POINT / (per_launch_ms * 1e-3) / 1e9
+  line = {
+      'metric': METRIC, 'value': value, 'unit': 'grid-points/s',
+      'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+      'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+      'data': 'synthetic',
+      'config': {
+          'workload': WORKLOAD, 'points_per_step_per_gpu': POINTS_PER_STEP,
+          'bytes_per_step_per_gpu': POINTS_PER_STEP * ALG_BYTES_PER_POINT,
+          'l2': 'inputs (830 MB per step) exceed the 126 MB L2; no flush needed',
+          'parallelism': f'dp{world} over (variable, init_time); one f64 '
+                         'state all-reduce per step' if world > 1 else 'single GPU',
+          'e2e_steps': e2e_steps,
+      },
+      'e2e': {
+          'value': e2e_value, 'unit': 'grid-points/s',
+          'ms_per_step': 1e3 * e2e_s / e2e_steps,
+          'h2d_bytes_per_step': POINTS_PER_STEP * ALG_BYTES_PER_POINT,
+          'd2h_bytes_per_step': N_VARS * 10 * 8,
+          'api': 'aggregation.compute_metric_values_for_single_chunk, pinned '
+                 'host numpy inputs, host-space C-ABI plan (H2D inside)'},
+      'gpu_launches': int(launches),
+      'roofline': {
+          'bound': 'hbm', 'kernel': 'det_reduce_tma_kernel<0,0,0,0>',
+          'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+          'frac': achieved / peak, 'traffic': None,
+          'peak_source': peak_src,
+          'kernel_ms_per_launch': per_launch_ms, 'launches_timed': int(kernel_n),
+          'algorithmic_bytes_per_launch': POINTS_PER_STEP * ALG_BYTES_PER_POINT},
+      'clocks': clocks,
+  }
+  if world == 1 and not args.no_cpu_baseline:
+    line['cpu_baseline'] = cpu_baseline_sample()
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=1000)
+  ap.add_argument('--warmup', type=int, default=10)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--e2e-steps', type=int, default=20)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    if args.steps == 1000:
+      args.steps = 20
+    if args.warmup == 10:
+      args.warmup = 3
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -87,6 +87,13 @@ int wbx_ctx_synchronize(wbx_ctx* ctx);
  * far (any pointer may be NULL). */
 int wbx_ctx_info(wbx_ctx* ctx, int* sm_count, uint64_t* hbm_bytes,
                  uint64_t* kernel_launches);
+/* Kernel timing for roofline accounting: when enabled, every main (streaming)
+ * kernel launch is bracketed by CUDA events on its own stream.
+ * wbx_ctx_kernel_time synchronises and returns the accumulated device time of
+ * those kernels (milliseconds) and their count since the last reset. */
+int wbx_ctx_profile(wbx_ctx* ctx, int32_t enable);
+int wbx_ctx_kernel_time(wbx_ctx* ctx, double* total_ms, uint64_t* count,
+                        int32_t reset);
 /* Staging budget (bytes of HBM) used by host-space calls; default 1 GiB. */
 int wbx_ctx_set_staging_bytes(wbx_ctx* ctx, uint64_t bytes);
 

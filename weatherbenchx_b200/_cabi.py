@@ -95,6 +95,9 @@ SIGNATURES = {
     'wbx_ctx_synchronize': (c_int, [c_void_p]),
     'wbx_ctx_info': (c_int, [c_void_p, POINTER(c_int), POINTER(c_uint64),
                              POINTER(c_uint64)]),
+    'wbx_ctx_profile': (c_int, [c_void_p, c_int32]),
+    'wbx_ctx_kernel_time': (c_int, [c_void_p, POINTER(c_double),
+                                    POINTER(c_uint64), c_int32]),
     'wbx_ctx_set_staging_bytes': (c_int, [c_void_p, c_uint64]),
     'wbx_host_alloc': (c_int, [c_size_t, POINTER(c_void_p)]),
     'wbx_host_free': (c_int, [c_void_p]),
@@ -189,6 +192,16 @@ class Context:
     n = c_uint64()
     check(self.lib.wbx_ctx_info(self.handle, None, None, ctypes.byref(n)))
     return n.value
+
+  def profile(self, enable: bool = True):
+    check(self.lib.wbx_ctx_profile(self.handle, 1 if enable else 0))
+
+  def kernel_time(self, reset: bool = True):
+    """(total milliseconds, launches) of the main kernels since last reset."""
+    ms, n = c_double(), c_uint64()
+    check(self.lib.wbx_ctx_kernel_time(self.handle, ctypes.byref(ms),
+                                       ctypes.byref(n), 1 if reset else 0))
+    return ms.value, n.value
 
   def set_staging_bytes(self, nbytes: int):
     check(self.lib.wbx_ctx_set_staging_bytes(self.handle, nbytes))

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/wbx_b200.h"
@@ -62,6 +63,15 @@ struct wbx_ctx {
   wbx::DevBuf stage_tables[2];
   void* pinned_out = nullptr;
   size_t pinned_out_cap = 0;
+  // optional per-kernel timing (wbx_ctx_profile)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_ms = 0.0;
+  uint64_t prof_count = 0;
+  int prof_begin();          // records the start event on `stream`
+  int prof_end();            // records the stop event on `stream`
+  int prof_collect();        // folds finished event pairs into prof_ms
 };
 
 // ---------------------------------------------------------------------------

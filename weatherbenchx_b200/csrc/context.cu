@@ -49,7 +49,70 @@ void DevBuf::release() {
 
 }  // namespace wbx
 
+int wbx_ctx::prof_begin() {
+  if (!profile) return WBX_OK;
+  if (prof_used == prof_events.size()) {
+    if (prof_used >= 4096) {
+      int rc = prof_collect();
+      if (rc != WBX_OK) return rc;
+    }
+    if (prof_used == prof_events.size()) {
+      cudaEvent_t a, b;
+      WBX_CUDA(cudaEventCreate(&a));
+      WBX_CUDA(cudaEventCreate(&b));
+      prof_events.emplace_back(a, b);
+    }
+  }
+  WBX_CUDA(cudaEventRecord(prof_events[prof_used].first, stream));
+  return WBX_OK;
+}
+
+int wbx_ctx::prof_end() {
+  if (!profile) return WBX_OK;
+  WBX_CUDA(cudaEventRecord(prof_events[prof_used].second, stream));
+  ++prof_used;
+  return WBX_OK;
+}
+
+int wbx_ctx::prof_collect() {
+  for (size_t i = 0; i < prof_used; ++i) {
+    WBX_CUDA(cudaEventSynchronize(prof_events[i].second));
+    float ms = 0.f;
+    WBX_CUDA(cudaEventElapsedTime(&ms, prof_events[i].first,
+                                  prof_events[i].second));
+    prof_ms += ms;
+    ++prof_count;
+  }
+  prof_used = 0;
+  return WBX_OK;
+}
+
 extern "C" {
+
+int wbx_ctx_profile(wbx_ctx* ctx, int32_t enable) {
+  WBX_REQUIRE(ctx != nullptr, "wbx_ctx_profile: ctx is NULL");
+  if (!enable && ctx->profile) {
+    int rc = ctx->prof_collect();
+    if (rc != WBX_OK) return rc;
+  }
+  ctx->profile = enable != 0;
+  return WBX_OK;
+}
+
+int wbx_ctx_kernel_time(wbx_ctx* ctx, double* total_ms, uint64_t* count,
+                        int32_t reset) {
+  WBX_REQUIRE(ctx != nullptr, "wbx_ctx_kernel_time: ctx is NULL");
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  int rc = ctx->prof_collect();
+  if (rc != WBX_OK) return rc;
+  if (total_ms) *total_ms = ctx->prof_ms;
+  if (count) *count = ctx->prof_count;
+  if (reset) {
+    ctx->prof_ms = 0.0;
+    ctx->prof_count = 0;
+  }
+  return WBX_OK;
+}
 
 int wbx_abi_version(void) { return WBX_ABI_VERSION; }
 
@@ -111,6 +174,10 @@ int wbx_ctx_destroy(wbx_ctx* ctx) {
     ctx->stage_tables[i].release();
     if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     if (ctx->ev_compute[i]) cudaEventDestroy(ctx->ev_compute[i]);
+  }
+  for (auto& pr : ctx->prof_events) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
   }
   if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
   cudaStreamDestroy(ctx->own_stream);

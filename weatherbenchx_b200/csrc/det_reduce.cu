@@ -46,6 +46,8 @@ template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM>
 static int launch_variant(wbx_ctx* ctx, const wbx_det_plan* plan,
                           const DetParams& P, int grid) {
   cudaStream_t st = ctx->stream;
+  int prc = ctx->prof_begin();
+  if (prc != WBX_OK) return prc;
   if (plan->path == kPathTma) {
     auto kern = det_reduce_tma_kernel<CLIM, MASK, SKIPNA, PER_ELEM>;
     WBX_CUDA(cudaFuncSetAttribute(kern,
@@ -62,7 +64,7 @@ static int launch_variant(wbx_ctx* ctx, const wbx_det_plan* plan,
   }
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
-  return WBX_OK;
+  return ctx->prof_end();
 }
 
 static int launch_main(wbx_ctx* ctx, const wbx_det_plan* plan,
