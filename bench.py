@@ -282,7 +282,7 @@ def run_b200(args):
       target=np.array([tgt.data_ptr() + (v * N_INIT + i) * slab_bytes
                        for v, i in jobs], np.uint64),
       cell=np.array([v for v, _ in jobs], np.int32), n_cells=N_VARS,
-      w_y=gaw.values)
+      w_y=gaw.values, stat_mask=1 << _cabi.STAT_SLOT['SquaredError'])
   out_ws = torch.zeros((N_VARS, 6), dtype=torch.float64, device=dev)
   out_w = torch.zeros((N_VARS, 4), dtype=torch.float64, device=dev)
   packed = torch.zeros((N_VARS, 10), dtype=torch.float64, device=dev)

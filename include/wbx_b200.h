@@ -144,6 +144,9 @@ typedef struct {
   const double* w_outer;   /* [n_jobs] or NULL                               */
   const double* w_y;       /* [ny] or NULL                                   */
   const double* w_x;       /* [nx] or NULL                                   */
+  int32_t stat_mask;       /* bit s => accumulate WBX_STAT_* slot s; 0 = all.
+                              Unselected slots of sum_ws are left as 0.       */
+  int32_t reserved;
 } wbx_det_desc;
 
 /* Upload the job tables once; the plan can then be run many times (the field

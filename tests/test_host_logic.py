@@ -404,7 +404,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header_sizes():
-  assert ctypes.sizeof(_cabi.DetDesc) == 8 + 4 * 8 + 8 * 8
+  assert ctypes.sizeof(_cabi.DetDesc) == 8 + 4 * 8 + 8 * 8 + 8
   assert ctypes.sizeof(_cabi.GenericDesc) == (
       16 + 8 * 8 + 8 * 4 + 4 * (8 + 8 * 8) + 6 * 8 + 6 * 4 + 6 * 8 * 8 + 0
       + (8 - (16 + 64 + 32 + 288 + 48 + 24) % 8) % 8)

@@ -61,6 +61,7 @@ class DetDesc(ctypes.Structure):
       ('cell', POINTER(c_int32)),
       ('w_outer', POINTER(c_double)), ('w_y', POINTER(c_double)),
       ('w_x', POINTER(c_double)),
+      ('stat_mask', c_int32), ('reserved', c_int32),
   ]
 
 
@@ -183,7 +184,10 @@ class Context:
 
   def use_torch_stream(self):
     import torch  # pylint: disable=g-import-not-at-top
-    self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+    # torch's default stream has handle 0, which the C ABI reads as "use the
+    # context's own stream"; cudaStreamLegacy (0x1) names it explicitly.
+    handle = torch.cuda.current_stream(self.device).cuda_stream
+    self.set_stream(handle if handle else 1)
 
   def synchronize(self):
     check(self.lib.wbx_ctx_synchronize(self.handle))
@@ -243,7 +247,8 @@ class DetPlan:
                n_cells: int, clim: np.ndarray | None = None,
                mask: np.ndarray | None = None,
                w_outer: np.ndarray | None = None,
-               w_y: np.ndarray | None = None, w_x: np.ndarray | None = None):
+               w_y: np.ndarray | None = None, w_x: np.ndarray | None = None,
+               stat_mask: int = 0):
     self.ctx = ctx
     self.n_cells = int(n_cells)
     keep = []
@@ -273,7 +278,8 @@ class DetPlan:
         pred=_as_ptr(pred, c_uint64), target=_as_ptr(target, c_uint64),
         clim=_as_ptr(clim, c_uint64), mask=_as_ptr(mask, c_uint64),
         cell=_as_ptr(cell, c_int32), w_outer=_as_ptr(w_outer, c_double),
-        w_y=_as_ptr(w_y, c_double), w_x=_as_ptr(w_x, c_double))
+        w_y=_as_ptr(w_y, c_double), w_x=_as_ptr(w_x, c_double),
+        stat_mask=stat_mask, reserved=0)
     handle = c_void_p()
     check(ctx.lib.wbx_det_plan_create(ctx.handle, ctypes.byref(desc),
                                       ctypes.byref(handle)))

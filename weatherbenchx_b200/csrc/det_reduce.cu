@@ -38,6 +38,7 @@ struct wbx_det_plan {
   const double* d_wy = nullptr;
   const double* d_wx = nullptr;
   std::vector<unsigned char> chunk_host[2];
+  int stat_mask = 0x3f;
 };
 
 namespace wbx {
@@ -97,6 +98,16 @@ static int launch_main(wbx_ctx* ctx, const wbx_det_plan* plan,
   return WBX_ERR_INVALID;
 }
 
+static void fill_steps(const wbx_det_plan* plan, DetParams* P) {
+  const int nx = static_cast<int>(plan->nx);
+  const int group = 4 * kConsumerThreads;
+  P->group_dq = group / nx;
+  P->group_dr = group % nx;
+  P->tile_dq = plan->tile / nx;
+  P->tile_dr = plan->tile % nx;
+  P->stat_mask = plan->stat_mask;
+}
+
 static int grid_for(const wbx_ctx* ctx, const wbx_det_plan* plan,
                     long long total_tiles) {
   long long g = plan->path == kPathTma ? ctx->sm_count : ctx->sm_count * 6ll;
@@ -127,7 +138,7 @@ static int launch_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
   F.n_weights = plan->n_weights;
   F.accumulate = accumulate;
   const int slots = WBX_NUM_DET_STATS + WBX_NUM_DET_WCLASSES;
-  const long long threads = static_cast<long long>(n_cells) * slots;
+  const long long threads = static_cast<long long>(n_cells) * slots * 32;
   const int block = 128;
   const int grid = static_cast<int>((threads + block - 1) / block);
   det_finalize_kernel<<<grid, block, 0, ctx->stream>>>(F);
@@ -244,6 +255,11 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     p->sum_wx = static_cast<double>(d->nx);
   }
   p->per_elem = p->has_wx || (d->nx % 4) != 0;
+  p->stat_mask = d->stat_mask ? (d->stat_mask & 0x3f) : 0x3f;
+  if (!p->has_clim) p->stat_mask &= 0x7;
+  WBX_REQUIRE(p->stat_mask != 0,
+              "det: stat_mask selects only climatology statistics but clim is "
+              "NULL");
   p->n_stats = p->has_clim ? 6 : 3;
   p->n_weights = p->skipna ? (p->has_clim ? 4 : 1) : (p->has_mask ? 1 : 0);
   p->nacc = p->n_stats + p->n_weights;
@@ -369,6 +385,7 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     P.tile = p->tile;
     P.tiles_per_slab = p->tiles_per_slab;
     P.records = nullptr;
+    wbx::fill_steps(p, &P);
     p->d_cell_first_job = reinterpret_cast<const int32_t*>(base + o_first);
     p->d_cell_w = reinterpret_cast<const double*>(base + o_cw);
     p->grid = wbx::grid_for(ctx, p, P.total_tiles);
@@ -536,6 +553,7 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     P.slab = static_cast<int>(slab);
     P.tile = plan->tile;
     P.tiles_per_slab = plan->tiles_per_slab;
+    wbx::fill_steps(plan, &P);
     const int grid = wbx::grid_for(ctx, plan, P.total_tiles);
     const int n_cells = static_cast<int>(cw.size());
     const size_t rec_bytes = (static_cast<size_t>(grid) + n_cells) * warps *

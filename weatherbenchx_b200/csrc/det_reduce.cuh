@@ -15,7 +15,7 @@
 //     cell changes;
 //   * TMA variant: one producer thread streams tiles of every operand into a
 //     shared-memory ring with cp.async.bulk (UBLKCP) + mbarrier transaction
-//     counts; 8 consumer warps read the ring with 128-bit LDS, evaluate the
+//     counts; 16 consumer warps read the ring with 128-bit LDS, evaluate the
 //     statistics in f32 exactly as NumPy does, and accumulate weight * value
 //     in f64 registers;
 //   * LDG variant (unaligned or tiny inputs, and an A/B baseline): same
@@ -29,7 +29,7 @@
 
 namespace wbx {
 
-constexpr int kConsumerWarps = 8;
+constexpr int kConsumerWarps = 16;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kTmaThreads = kConsumerThreads + 32;  // + producer warp
 constexpr int kLdgThreads = 256;
@@ -52,6 +52,12 @@ struct DetParams {
   int slab;            // ny * nx
   int tile;            // elements per tile (multiple of 16)
   int tiles_per_slab;
+  // (quotient, remainder) of the element strides a consumer thread advances
+  // by, divided by nx: between its float4 groups inside a tile and from one
+  // tile to the next.  Lets the kernel track (row, column) without dividing.
+  int group_dq, group_dr;
+  int tile_dq, tile_dr;
+  int stat_mask;       // bit s set => statistic slot s is wanted
   double* records;
 };
 
@@ -126,7 +132,8 @@ struct PointStats {
 template <bool CLIM, bool MASK, bool SKIPNA>
 __device__ __forceinline__ void accum_row4(const float4 p, const float4 t,
                                            const float4 c, const uchar4 m,
-                                           const double w, double* acc) {
+                                           const double w, const int stat_mask,
+                                           double* acc) {
   using L = AccLayout<CLIM, MASK, SKIPNA>;
   PointStats<CLIM, MASK, SKIPNA> q0, q1, q2, q3;
   q0.eval(p.x, t.x, c.x, m.x);
@@ -135,9 +142,11 @@ __device__ __forceinline__ void accum_row4(const float4 p, const float4 t,
   q3.eval(p.w, t.w, c.w, m.w);
 #pragma unroll
   for (int k = 0; k < L::kStats; ++k) {
-    const float s4 = __fadd_rn(__fadd_rn(q0.s[k], q1.s[k]),
-                               __fadd_rn(q2.s[k], q3.s[k]));
-    acc[k] += static_cast<double>(s4) * w;
+    if (stat_mask & (1 << k)) {  // warp-uniform
+      const float s4 = __fadd_rn(__fadd_rn(q0.s[k], q1.s[k]),
+                                 __fadd_rn(q2.s[k], q3.s[k]));
+      acc[k] += static_cast<double>(s4) * w;
+    }
   }
 #pragma unroll
   for (int k = 0; k < L::kWeights; ++k) {
@@ -149,13 +158,13 @@ __device__ __forceinline__ void accum_row4(const float4 p, const float4 t,
 template <bool CLIM, bool MASK, bool SKIPNA>
 __device__ __forceinline__ void accum_point(float p, float t, float c,
                                             unsigned char m, const double w,
-                                            double* acc) {
+                                            const int stat_mask, double* acc) {
   using L = AccLayout<CLIM, MASK, SKIPNA>;
   PointStats<CLIM, MASK, SKIPNA> q;
   q.eval(p, t, c, m);
 #pragma unroll
   for (int k = 0; k < L::kStats; ++k)
-    acc[k] += static_cast<double>(q.s[k]) * w;
+    if (stat_mask & (1 << k)) acc[k] += static_cast<double>(q.s[k]) * w;
 #pragma unroll
   for (int k = 0; k < L::kWeights; ++k)
     acc[L::kStats + k] += static_cast<double>(q.valid[k]) * w;
@@ -179,14 +188,13 @@ struct WeightCursor {
 template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM>
 __device__ __forceinline__ void accum_group4(const float4 p, const float4 t,
                                              const float4 c, const uchar4 m,
-                                             unsigned e, double wo,
+                                             unsigned y, unsigned x, double wo,
                                              const WeightCursor& wc,
+                                             const int stat_mask,
                                              double* acc) {
-  unsigned y = e / static_cast<unsigned>(wc.nx);
   if constexpr (!PER_ELEM) {
-    accum_row4<CLIM, MASK, SKIPNA>(p, t, c, m, wc.row(y, wo), acc);
+    accum_row4<CLIM, MASK, SKIPNA>(p, t, c, m, wc.row(y, wo), stat_mask, acc);
   } else {
-    unsigned x = e - y * static_cast<unsigned>(wc.nx);
     const float pp[4] = {p.x, p.y, p.z, p.w};
     const float tt[4] = {t.x, t.y, t.z, t.w};
     const float cc[4] = {c.x, c.y, c.z, c.w};
@@ -195,7 +203,7 @@ __device__ __forceinline__ void accum_group4(const float4 p, const float4 t,
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       accum_point<CLIM, MASK, SKIPNA>(pp[i], tt[i], cc[i], mm[i],
-                                      wrow * wc.col(x), acc);
+                                      wrow * wc.col(x), stat_mask, acc);
       if (++x == static_cast<unsigned>(wc.nx)) {
         x = 0;
         ++y;
@@ -313,13 +321,35 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   for (int a = 0; a < L::kAcc; ++a) acc[a] = 0.0;
   const WeightCursor wc{P.w_y, P.w_x, P.nx};
   int cur_cell = -1;
-  const int ctid = threadIdx.x;  // 0..255
+  const int ctid = threadIdx.x;  // 0 .. kConsumerThreads-1
+  const unsigned unx = static_cast<unsigned>(P.nx);
+  // (row, column) of this thread's first group in a tile that starts a slab.
+  const unsigned y_first = static_cast<unsigned>(4 * ctid) / unx;
+  const unsigned x_first = static_cast<unsigned>(4 * ctid) - y_first * unx;
+  unsigned ty = 0, tx = 0;  // ... in the current tile
+  int prev_e0 = -1;
   int it = 0;
   for (long long g = t_begin; g < t_end; ++g, ++it) {
     const int s = it % stages;
     const uint32_t ph = (it / stages) & 1;
     mbar_wait(&full[s], ph);
     const StageMeta mt = meta[s];
+    if (mt.e0 == 0) {
+      ty = y_first;
+      tx = x_first;
+    } else if (prev_e0 >= 0 && mt.e0 == prev_e0 + P.tile) {
+      ty += P.tile_dq;
+      tx += P.tile_dr;
+      if (tx >= unx) {
+        tx -= unx;
+        ++ty;
+      }
+    } else {  // first tile of this CTA starts inside a slab
+      const unsigned e = static_cast<unsigned>(mt.e0 + 4 * ctid);
+      ty = e / unx;
+      tx = e - ty * unx;
+    }
+    prev_e0 = mt.e0;
     if (mt.cell != cur_cell) {
       if (cur_cell >= 0) {
         double* rec = P.records +
@@ -335,7 +365,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     const float4* sc = reinterpret_cast<const float4*>(st + off_c);
     const uchar4* sm = reinterpret_cast<const uchar4*>(st + off_m);
     const int nvec = mt.len >> 2;
-#pragma unroll 4
+    unsigned gy = ty, gx = tx;
+#pragma unroll 2
     for (int j = ctid; j < nvec; j += kConsumerThreads) {
       const float4 pv = sp[j];
       const float4 tv = stt[j];
@@ -343,8 +374,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       uchar4 mv = make_uchar4(1, 1, 1, 1);
       if constexpr (CLIM) cv = sc[j];
       if constexpr (MASK) mv = sm[j];
-      accum_group4<CLIM, MASK, SKIPNA, PER_ELEM>(
-          pv, tv, cv, mv, static_cast<unsigned>(mt.e0 + 4 * j), mt.wo, wc, acc);
+      accum_group4<CLIM, MASK, SKIPNA, PER_ELEM>(pv, tv, cv, mv, gy, gx, mt.wo,
+                                                 wc, P.stat_mask, acc);
+      gy += P.group_dq;
+      gx += P.group_dr;
+      if (gx >= unx) {
+        gx -= unx;
+        ++gy;
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
@@ -422,9 +459,11 @@ __global__ void __launch_bounds__(kLdgThreads)
           if (j < nvec) {
             if constexpr (!CLIM) cv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if constexpr (!MASK) mv[u] = make_uchar4(1, 1, 1, 1);
+            const unsigned e = static_cast<unsigned>(e0 + 4 * j);
+            const unsigned y = e / static_cast<unsigned>(P.nx);
             accum_group4<CLIM, MASK, SKIPNA, PER_ELEM>(
-                pv[u], tv[u], cv[u], mv[u],
-                static_cast<unsigned>(e0 + 4 * j), wo, wc, acc);
+                pv[u], tv[u], cv[u], mv[u], y,
+                e - y * static_cast<unsigned>(P.nx), wo, wc, P.stat_mask, acc);
           }
         }
       }
@@ -440,7 +479,8 @@ __global__ void __launch_bounds__(kLdgThreads)
         if constexpr (CLIM) cv = ldg_stream_f1(ca + e);
         if constexpr (MASK) mv = __ldg(ma + e);
         accum_point<CLIM, MASK, SKIPNA>(pv, tv, cv, mv,
-                                        wc.row(y, wo) * wc.col(x), acc);
+                                        wc.row(y, wo) * wc.col(x), P.stat_mask,
+                                        acc);
       }
     }
     if (++k == P.tiles_per_slab) {
@@ -475,12 +515,16 @@ struct FinalizeParams {
   int accumulate;
 };
 
-__global__ void det_finalize_kernel(const FinalizeParams F) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) det_finalize_kernel(
+    const FinalizeParams F) {
+  // One warp per (cell, slot): lanes stride over the records of the cell in a
+  // fixed assignment, then a butterfly sum -- parallel and still bit-stable.
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   const int slots = WBX_NUM_DET_STATS + WBX_NUM_DET_WCLASSES;
-  if (idx >= F.n_cells * slots) return;
-  const int c = idx / slots;
-  const int slot = idx - c * slots;
+  if (warp_global >= F.n_cells * slots) return;
+  const int c = warp_global / slots;
+  const int slot = warp_global - c * slots;
   const int nacc = F.n_stats + F.n_weights;
   int a = -1;
   double value = 0.0;
@@ -506,19 +550,20 @@ __global__ void det_finalize_kernel(const FinalizeParams F) {
     const long long G = F.grid_main;
     const int b_lo = static_cast<int>(((ft + 1) * G - 1) / F.total_tiles);
     const int b_hi = static_cast<int>(((lt + 1) * G - 1) / F.total_tiles);
+    const int n = (b_hi - b_lo + 1) * F.warps;
+    const double* rec =
+        F.records + (static_cast<size_t>(b_lo) + c) * F.warps * nacc + a;
     double sum = 0.0;
-    for (int b = b_lo; b <= b_hi; ++b) {
-      const double* rec =
-          F.records + (static_cast<size_t>(b) + c) * F.warps * nacc + a;
-      for (int w = 0; w < F.warps; ++w) sum += rec[(size_t)w * nacc];
-    }
-    value = sum;
+    for (int i = lane; i < n; i += 32) sum += rec[static_cast<size_t>(i) * nacc];
+    value = warp_sum(sum);
   }
-  double* dst = slot < WBX_NUM_DET_STATS
-                    ? F.out_ws + (size_t)c * WBX_NUM_DET_STATS + slot
-                    : F.out_w + (size_t)c * WBX_NUM_DET_WCLASSES +
-                          (slot - WBX_NUM_DET_STATS);
-  *dst = F.accumulate ? (*dst + value) : value;
+  if (lane == 0) {
+    double* dst = slot < WBX_NUM_DET_STATS
+                      ? F.out_ws + (size_t)c * WBX_NUM_DET_STATS + slot
+                      : F.out_w + (size_t)c * WBX_NUM_DET_WCLASSES +
+                            (slot - WBX_NUM_DET_STATS);
+    *dst = F.accumulate ? (*dst + value) : value;
+  }
 }
 
 // ---------------------------------------------------------------------------

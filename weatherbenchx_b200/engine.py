@@ -232,6 +232,7 @@ class FusedSpec:
   w_y: np.ndarray | None
   w_x: np.ndarray | None
   scalar: float
+  stat_mask: int
   kept: list
   kept_shape: list
   coords: dict
@@ -360,8 +361,11 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
   if op_m is not None:
     flags |= _cabi.FLAG_MASKED
 
+  stat_mask = 0
+  for s in stats:
+    stat_mask |= 1 << _cabi.STAT_SLOT[s.kind]
   cache_key = (
-      space, flags, tuple(dims), tuple(sizes[d] for d in dims), tuple(inner),
+      space, flags, stat_mask, tuple(dims), tuple(sizes[d] for d in dims), tuple(inner),
       tuple(sorted(reduce_set, key=str)),
       op_p.ptr, tuple(op_p.strides.items()), op_t.ptr,
       tuple(op_t.strides.items()),
@@ -409,7 +413,7 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
       cell=np.repeat(np.arange(n_cells, dtype=np.int32), per_cell),
       w_outer=_weight_vector(job_dims, sizes, per_dim),
       w_y=_weight_vector(y_dims, sizes, per_dim), w_x=per_dim.get(x_dim),
-      scalar=scalar, kept=kept, kept_shape=[sizes[d] for d in kept],
+      scalar=scalar, stat_mask=stat_mask, kept=kept, kept_shape=[sizes[d] for d in kept],
       coords=coords, keepalive=(pred, tgt, clim_da, mask_da),
       cache_key=cache_key)
 
@@ -438,7 +442,7 @@ def aggregate_fused(stats: Sequence[LazyStatistic],
         ctx, space=spec.space, flags=spec.flags, ny=spec.ny, nx=spec.nx,
         pred=spec.pred, target=spec.target, clim=spec.clim, mask=spec.mask,
         cell=spec.cell, n_cells=spec.n_cells, w_outer=spec.w_outer,
-        w_y=spec.w_y, w_x=spec.w_x)
+        w_y=spec.w_y, w_x=spec.w_x, stat_mask=spec.stat_mask)
     _PLAN_CACHE[spec.cache_key] = plan
     while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
       _, old = _PLAN_CACHE.popitem(last=False)
