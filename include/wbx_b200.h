@@ -173,6 +173,74 @@ int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
                         const float* target, const float* clim, int64_t n,
                         float* out);
 
+/* ---- ensemble CRPS statistics + weighted aggregation ------------------- *
+ *
+ * Replaces, in one pass over the ensemble and the targets:
+ *   CRPSSkill._compute_per_variable    metrics/probabilistic.py:129-145
+ *   CRPSSpread._compute_per_variable   metrics/probabilistic.py:194-247
+ *     (the O(M^2) member-pair estimator; the sort/PWM branch :214-240 computes
+ *      the same statistic -- same unique_name -- and is served by this kernel)
+ *   Aggregator.aggregate_stat_var      aggregation.py:337-366
+ *
+ * Jobs / cells / weights exactly as for wbx_det_desc.  Per job the targets are
+ * one contiguous slab of ny*nx float32; ensemble member m of grid point g
+ * (g = y*nx + x) is at  ens[j] + 4*(m*member_stride + g*point_stride).
+ * Results: sum_ws[c*2 + s], sum_w[c*2 + s] with s = 0 CRPSSkill, 1 CRPSSpread.
+ * n_members < 2 without WBX_CRPS_SKIPNA_ENSEMBLE is an error
+ * (probabilistic.py:210-212).
+ */
+enum {
+  WBX_CRPS_FAIR = 256,            /* divide by M(M-1) instead of M^2          */
+  WBX_CRPS_SKIPNA_ENSEMBLE = 512  /* NaN members are missing members          */
+};
+
+typedef struct wbx_crps_plan wbx_crps_plan;
+
+typedef struct {
+  int32_t space;       /* WBX_SPACE_* of ens/target/mask addresses            */
+  int32_t flags;       /* WBX_FLAG_SKIPNA | WBX_FLAG_MASKED | WBX_CRPS_*      */
+  int64_t n_jobs;
+  int64_t ny, nx;
+  int64_t n_members;
+  int64_t member_stride;  /* elements between members of one grid point       */
+  int64_t point_stride;   /* elements between grid points of one member       */
+  int64_t n_cells;
+  const uint64_t* ens;     /* [n_jobs]                                        */
+  const uint64_t* target;  /* [n_jobs]                                        */
+  const uint64_t* mask;    /* [n_jobs] uint8 slabs or NULL                    */
+  const int32_t* cell;     /* [n_jobs] non-decreasing                         */
+  const double* w_outer;   /* [n_jobs] or NULL                                */
+  const double* w_y;       /* [ny] or NULL                                    */
+  const double* w_x;       /* [nx] or NULL                                    */
+} wbx_crps_desc;
+
+int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* desc,
+                         wbx_crps_plan** out);
+int wbx_crps_plan_destroy(wbx_ctx* ctx, wbx_crps_plan* plan);
+/* sum_ws / sum_w: float64 [n_cells*2]; semantics as wbx_det_plan_run. */
+int wbx_crps_plan_run(wbx_ctx* ctx, wbx_crps_plan* plan, double* sum_ws,
+                      double* sum_w, int32_t out_space, int32_t accumulate);
+
+/* Per-gridpoint CRPSSkill / CRPSSpread values for arbitrary strided layouts
+ * (device pointers).  Points are the row-major flattening of `ndim` dims; the
+ * target may broadcast (stride 0).  skill / spread: float32 [n_points], either
+ * may be NULL.  flags: WBX_CRPS_*. */
+#define WBX_CRPS_MAX_DIMS 8
+typedef struct {
+  int32_t ndim;
+  int32_t flags;
+  int64_t n_members;
+  int64_t member_stride;
+  int64_t size[WBX_CRPS_MAX_DIMS];
+  int64_t ens_stride[WBX_CRPS_MAX_DIMS];
+  int64_t target_stride[WBX_CRPS_MAX_DIMS];
+  const float* ens;
+  const float* target;
+} wbx_crps_point_desc;
+
+int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* desc,
+                       float* skill, float* spread);
+
 /* ---- generic strided statistic + weighted aggregation ------------------ *
  *
  * Same contract as the fused path (Aggregator.aggregate_stat_var,

@@ -1,0 +1,278 @@
+"""GPU parity tests of the CRPS path (CRPSSkill, CRPSSpread, CRPSEnsemble)."""
+
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+import wbx_oracle as oracle
+import wbx_test_utils as utils
+from weatherbenchx_b200 import _cabi
+from weatherbenchx_b200 import aggregation
+from weatherbenchx_b200 import engine
+from weatherbenchx_b200 import weighting
+from weatherbenchx_b200 import xarray_lite as xl
+from weatherbenchx_b200.lazy import LazyEnsembleStatistic
+from weatherbenchx_b200.metrics import base as metrics_base
+from weatherbenchx_b200.metrics import probabilistic
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'hotpath_golden.npz')
+
+
+def compute_all_metrics(metrics, predictions, targets, reduce_dims, **kw):
+  """metrics/metrics_test_utils.py:86-95."""
+  statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+      metrics, predictions, targets)
+  state = aggregation.Aggregator(reduce_dims=reduce_dims, **kw
+                                 ).aggregate_statistics(statistics)
+  return state.metric_values(metrics)
+
+
+def _mock(ensemble_size=None, seed=None):
+  return utils.to_f32(utils.mock_prediction_data(
+      time_start='2020-01-01T00', time_stop='2020-01-03T00', random=True,
+      ensemble_size=ensemble_size, seed=seed))
+
+
+@pytest.mark.parametrize('ensemble_size,use_sort,fair', list(
+    itertools.product([4, 5], [False, True], [True, False])))
+def test_crps(ensemble_size, use_sort, fair):
+  """metrics/metrics_test.py:603-660: CRPS == brute force (8 cases)."""
+  targets = _mock(seed=10)
+  predictions = _mock(ensemble_size, seed=11)
+  metrics = {'crps': probabilistic.CRPSEnsemble(
+      ensemble_dim='realization', use_sort=use_sort, fair=fair)}
+  results = compute_all_metrics(metrics, predictions, targets,
+                                reduce_dims=['latitude', 'longitude'])
+  for v in ('2m_temperature', 'geopotential'):
+    x, y = predictions[v].values, targets[v].values
+    dims = targets[v].dims
+    axes = tuple(dims.index(d) for d in ('latitude', 'longitude'))
+    spread = oracle.crps_spread_brute_force(x, -1, fair).mean(axes)
+    skill = np.abs(y[..., None].astype(np.float64) - x).mean(-1).mean(axes)
+    expected = skill - 0.5 * spread
+    got = results[f'crps.{v}']
+    kept = tuple(d for d in dims if d not in ('latitude', 'longitude'))
+    np.testing.assert_allclose(got.transpose(*kept).values, expected,
+                               rtol=RTOL)
+
+
+@pytest.mark.parametrize('ensemble_size,fair', list(
+    itertools.product([4, 5], [True, False])))
+def test_crps_with_nans(ensemble_size, fair):
+  """metrics/metrics_test.py:1199-1274."""
+  targets = _mock(seed=20)
+  predictions = _mock(ensemble_size, seed=21)
+  with_nan = dict(predictions)
+  arr = predictions['2m_temperature'].values.copy()
+  arr[..., 0] = np.nan
+  with_nan['2m_temperature'] = predictions['2m_temperature'].copy(data=arr)
+  skipna = {'crps': probabilistic.CRPSEnsemble(
+      ensemble_dim='realization', fair=fair, skipna_ensemble=True)}
+  plain = {'crps': probabilistic.CRPSEnsemble(
+      ensemble_dim='realization', fair=fair)}
+  rd = ['latitude', 'longitude']
+  results = compute_all_metrics(skipna, with_nan, targets, rd)
+  dropped = {k: v.isel(realization=slice(1, None))
+             for k, v in predictions.items()}
+  expected_dropped = compute_all_metrics(plain, dropped, targets, rd)
+  expected_full = compute_all_metrics(plain, predictions, targets, rd)
+  xl.testing.assert_allclose(results['crps.2m_temperature'],
+                             expected_dropped['crps.2m_temperature'])
+  xl.testing.assert_allclose(results['crps.geopotential'],
+                             expected_full['crps.geopotential'])
+  # without skipna_ensemble the NaN member poisons the variable
+  poisoned = compute_all_metrics(plain, with_nan, targets, rd)
+  assert np.isnan(poisoned['crps.2m_temperature'].values).all()
+
+
+def test_crps_errors():
+  """probabilistic.py:210-216."""
+  targets = _mock(seed=1)
+  one = _mock(1, seed=2)
+  with pytest.raises(ValueError, match='Failed to compute statistic'):
+    compute_all_metrics(
+        {'c': probabilistic.CRPSEnsemble(ensemble_dim='realization')},
+        one, targets, ['latitude', 'longitude'])
+  with pytest.raises(ValueError, match='Failed to compute statistic'):
+    compute_all_metrics(
+        {'c': probabilistic.CRPSEnsemble(ensemble_dim='realization',
+                                         use_sort=True, skipna_ensemble=True)},
+        _mock(4, seed=3), targets, ['latitude', 'longitude'])
+  assert (probabilistic.CRPSSpread('realization', fair=False).unique_name ==
+          'CRPSSpread_realization_unfair_predictions')
+  assert probabilistic.CRPSSkill('number').unique_name == 'CRPSSkill_number'
+
+
+@pytest.mark.parametrize('m', [4, 5])
+@pytest.mark.parametrize('fair', [True, False])
+def test_golden_crps_through_cabi(m, fair):
+  g = np.load(GOLDEN)
+  x = np.ascontiguousarray(g[f'crps{m}_x'])     # [init, lat, lon, member]
+  y = np.ascontiguousarray(g[f'crps{m}_y'])
+  n_init, ny, nx = y.shape
+  w = g['w_lat']
+  plan = _cabi.CrpsPlan(
+      _cabi.get_context(), space=_cabi.SPACE_HOST,
+      flags=_cabi.CRPS_FAIR if fair else 0, ny=ny, nx=nx, n_members=m,
+      member_stride=1, point_stride=m,
+      ens=np.array([x.ctypes.data + i * ny * nx * m * 4 for i in range(n_init)],
+                   np.uint64),
+      target=np.array([y.ctypes.data + i * ny * nx * 4 for i in range(n_init)],
+                      np.uint64),
+      cell=np.arange(n_init, dtype=np.int32), n_cells=n_init, w_y=w)
+  ws, wsum = plan.run_to_host()
+  spread = g[f'crps{m}_spread_{"fair" if fair else "unfair"}']
+  np.testing.assert_allclose(
+      ws[:, 0], (g[f'crps{m}_skill'] * w[None, :, None]).sum((1, 2)), rtol=RTOL)
+  np.testing.assert_allclose(
+      ws[:, 1], (spread * w[None, :, None]).sum((1, 2)), rtol=RTOL)
+  np.testing.assert_allclose(wsum, np.full((n_init, 2), w.sum() * nx),
+                             rtol=1e-12)
+
+
+@pytest.mark.parametrize('members', [2, 8, 13, 50])
+@pytest.mark.parametrize('layout', ['member_last', 'member_major'])
+@pytest.mark.parametrize('space', ['host', 'device'])
+def test_fused_crps_matches_oracle(members, layout, space):
+  rng = np.random.default_rng(members)
+  n_init, nlat, nlon = 3, 12, 20
+  coords = {'init_time': np.arange(n_init),
+            'latitude': np.linspace(-82.5, 82.5, nlat),
+            'longitude': np.arange(nlon) * 18.0,
+            'number': np.arange(members)}
+  y = rng.normal(size=(n_init, nlat, nlon)).astype(np.float32)
+  if layout == 'member_last':
+    edims = ('init_time', 'latitude', 'longitude', 'number')
+    x = rng.normal(size=(n_init, nlat, nlon, members)).astype(np.float32)
+    ens_axis = 3
+  else:
+    edims = ('init_time', 'number', 'latitude', 'longitude')
+    x = rng.normal(size=(n_init, members, nlat, nlon)).astype(np.float32)
+    ens_axis = 1
+  X = xl.DataArray(x, edims, coords={d: coords[d] for d in edims}, name='t')
+  Y = xl.DataArray(y, ('init_time', 'latitude', 'longitude'),
+                   coords={d: coords[d] for d in
+                           ('init_time', 'latitude', 'longitude')}, name='t')
+  if space == 'device':
+    X, Y = engine.to_device(X), engine.to_device(Y)
+  metrics = {'crps': probabilistic.CRPSEnsemble()}
+  for rd in (['latitude', 'longitude'], ['init_time', 'latitude', 'longitude']):
+    values = compute_all_metrics(metrics, {'t': X}, {'t': Y}, rd,
+                                 weigh_by=[weighting.GridAreaWeighting()])
+    w = oracle.grid_area_weights(coords['latitude'])
+    skill = oracle.crps_skill(x, y, ens_axis)
+    spread = oracle.crps_spread(x, ens_axis, fair=True)
+    dims = ('init_time', 'latitude', 'longitude')
+    s_ws, s_w, _ = oracle.aggregate(skill, dims, rd,
+                                    weights=[(w, ('latitude',))])
+    p_ws, p_w, _ = oracle.aggregate(spread, dims, rd,
+                                    weights=[(w, ('latitude',))])
+    np.testing.assert_allclose(values['crps.t'].values,
+                               s_ws / s_w - 0.5 * p_ws / p_w, rtol=RTOL)
+
+
+def test_pointwise_fields_match_oracle():
+  rng = np.random.default_rng(0)
+  x = rng.normal(size=(2, 5, 7, 6)).astype(np.float32)
+  x[0, 1, 2, 3] = np.nan
+  y = rng.normal(size=(2, 5, 7)).astype(np.float32)
+  dims = ('t', 'latitude', 'longitude')
+  X = xl.DataArray(x, dims + ('number',), name='v')
+  Y = xl.DataArray(y, dims, name='v')
+  for skipna in (False, True):
+    sk = LazyEnsembleStatistic('CRPSSkill', X, Y, 'number', True, skipna).values
+    sp = LazyEnsembleStatistic('CRPSSpread', X, Y, 'number', True, skipna).values
+    np.testing.assert_allclose(
+        sk, oracle.crps_skill(x, y, -1, skipna_ensemble=skipna), rtol=2e-6,
+        equal_nan=True)
+    np.testing.assert_allclose(
+        sp, oracle.crps_spread(x, -1, fair=True, skipna_ensemble=skipna),
+        rtol=2e-5, atol=1e-6, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE-size properties: 0.25 degree, M = 50, device resident
+# ---------------------------------------------------------------------------
+
+
+@pytest.fixture(scope='module')
+def big():
+  import torch
+  torch.manual_seed(1)
+  n_init, m, ny, nx = 2, 50, 721, 1440
+  y = torch.randn(n_init, ny, nx, device='cuda')
+  x = y[:, None] + torch.randn(n_init, m, ny, nx, device='cuda')
+  coords = {'init_time': np.arange(n_init), 'number': np.arange(m),
+            'latitude': np.linspace(-90, 90, ny),
+            'longitude': np.linspace(0, 360, nx, endpoint=False)}
+  X = xl.DataArray(x, ('init_time', 'number', 'latitude', 'longitude'),
+                   coords=coords, name='t2m')
+  Y = xl.DataArray(y, ('init_time', 'latitude', 'longitude'),
+                   coords={k: coords[k] for k in
+                           ('init_time', 'latitude', 'longitude')}, name='t2m')
+  return X, Y
+
+
+def _crps_sums(X, Y, reduce_dims, weights=True, **kw):
+  stats = [LazyEnsembleStatistic(k, X, Y, 'number', True, False)
+           for k in ('CRPSSkill', 'CRPSSpread')]
+  w = [weighting.GridAreaWeighting().weights(stats[0])] if weights else []
+  return engine.aggregate_crps(stats, list(reduce_dims), w, **kw)
+
+
+def test_big_matches_torch_on_rows_and_is_deterministic(big):
+  import torch
+  X, Y = big
+  res = _crps_sums(X, Y, ['longitude'], weights=False)
+  skill, spread = res['CRPSSkill'][0].values, res['CRPSSpread'][0].values
+  assert skill.shape == (2, 721)
+  rows = [0, 360, 720]
+  x = X.data[:, :, rows, :].double()
+  y = Y.data[:, rows, :].double()
+  ref_skill = (x - y[:, None]).abs().mean(1).sum(-1).cpu().numpy()
+  pair = (x[:, :, None] - x[:, None, :]).abs().sum((1, 2)) / (50 * 49)
+  np.testing.assert_allclose(skill[:, rows], ref_skill, rtol=RTOL)
+  np.testing.assert_allclose(spread[:, rows], pair.sum(-1).cpu().numpy(),
+                             rtol=RTOL)
+  np.testing.assert_array_equal(res['CRPSSkill'][1].values, 1440.0)
+  again = _crps_sums(X, Y, ['longitude'], weights=False)
+  assert again['CRPSSpread'][0].values.tobytes() == spread.tobytes()
+
+
+def test_big_scaling_and_chunk_combine(big):
+  X, Y = big
+  rd = ['init_time', 'latitude', 'longitude']
+  base = _crps_sums(X, Y, rd)
+  X2 = xl.DataArray(X.data * 2, X.dims, coords=X.coords, name='t2m')
+  Y2 = xl.DataArray(Y.data * 2, Y.dims, coords=Y.coords, name='t2m')
+  dbl = _crps_sums(X2, Y2, rd)
+  for k in base:   # |2a - 2b| = 2|a - b| exactly in binary floating point
+    assert dbl[k][0].values == 2 * base[k][0].values
+  parts = [_crps_sums(X.isel(init_time=slice(i, i + 1)),
+                      Y.isel(init_time=slice(i, i + 1)), rd) for i in range(2)]
+  for k in base:
+    np.testing.assert_allclose(sum(p[k][0].values for p in parts),
+                               base[k][0].values, rtol=1e-12)
+    np.testing.assert_allclose(sum(p[k][1].values for p in parts),
+                               base[k][1].values, rtol=1e-12)
+  # CRPS of a calibrated Gaussian ensemble: skill ~ 2/sqrt(pi)*... sanity only
+  crps = (base['CRPSSkill'][0].values / base['CRPSSkill'][1].values - 0.5 *
+          base['CRPSSpread'][0].values / base['CRPSSpread'][1].values)
+  assert 0.2 < crps < 0.3   # sigma / sqrt(pi) * (sqrt(2) - 1) * ... ~ 0.2337
+
+
+def test_identical_members_have_zero_spread():
+  import torch
+  y = torch.randn(1, 64, 128, device='cuda')
+  x = (y + 1.5)[:, None].expand(1, 10, 64, 128).contiguous()
+  X = xl.DataArray(x, ('init_time', 'number', 'latitude', 'longitude'),
+                   name='v')
+  Y = xl.DataArray(y, ('init_time', 'latitude', 'longitude'), name='v')
+  res = _crps_sums(X, Y, ['latitude', 'longitude'], weights=False)
+  assert res['CRPSSpread'][0].values == 0.0
+  np.testing.assert_allclose(res['CRPSSkill'][0].values, 1.5 * 64 * 128,
+                             rtol=1e-5)

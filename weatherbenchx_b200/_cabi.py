@@ -86,6 +86,34 @@ class GenericDesc(ctypes.Structure):
   ]
 
 
+CRPS_FAIR, CRPS_SKIPNA_ENSEMBLE = 256, 512
+
+
+class CrpsDesc(ctypes.Structure):
+  """Mirror of wbx_crps_desc."""
+  _fields_ = [
+      ('space', c_int32), ('flags', c_int32),
+      ('n_jobs', c_int64), ('ny', c_int64), ('nx', c_int64),
+      ('n_members', c_int64), ('member_stride', c_int64),
+      ('point_stride', c_int64), ('n_cells', c_int64),
+      ('ens', POINTER(c_uint64)), ('target', POINTER(c_uint64)),
+      ('mask', POINTER(c_uint64)), ('cell', POINTER(c_int32)),
+      ('w_outer', POINTER(c_double)), ('w_y', POINTER(c_double)),
+      ('w_x', POINTER(c_double)),
+  ]
+
+
+class CrpsPointDesc(ctypes.Structure):
+  """Mirror of wbx_crps_point_desc."""
+  _fields_ = [
+      ('ndim', c_int32), ('flags', c_int32),
+      ('n_members', c_int64), ('member_stride', c_int64),
+      ('size', c_int64 * MAX_DIMS), ('ens_stride', c_int64 * MAX_DIMS),
+      ('target_stride', c_int64 * MAX_DIMS),
+      ('ens', c_void_p), ('target', c_void_p),
+  ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/wbx_b200.h.
 SIGNATURES = {
     'wbx_abi_version': (c_int, []),
@@ -113,6 +141,13 @@ SIGNATURES = {
                                c_void_p]),
     'wbx_det_elementwise': (c_int, [c_void_p, c_int32, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_void_p]),
+    'wbx_crps_plan_create': (c_int, [c_void_p, POINTER(CrpsDesc),
+                                     POINTER(c_void_p)]),
+    'wbx_crps_plan_destroy': (c_int, [c_void_p, c_void_p]),
+    'wbx_crps_plan_run': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int32, c_int32]),
+    'wbx_crps_pointwise': (c_int, [c_void_p, POINTER(CrpsPointDesc), c_void_p,
+                                   c_void_p]),
     'wbx_reduce_generic': (c_int, [c_void_p, POINTER(GenericDesc), c_void_p,
                                    c_void_p, c_int32]),
 }
@@ -318,3 +353,79 @@ def det_elementwise(ctx: Context, stat: int, pred_ptr: int, target_ptr: int,
   check(ctx.lib.wbx_det_elementwise(
       ctx.handle, stat, c_void_p(pred_ptr), c_void_p(target_ptr),
       c_void_p(clim_ptr or 0), n, c_void_p(out_ptr)))
+
+
+class CrpsPlan:
+  """wbx_crps_plan: CRPSSkill + CRPSSpread aggregated in one launch."""
+
+  def __init__(self, ctx: Context, *, space: int, flags: int, ny: int, nx: int,
+               n_members: int, member_stride: int, point_stride: int,
+               ens: np.ndarray, target: np.ndarray, cell: np.ndarray,
+               n_cells: int, mask: np.ndarray | None = None,
+               w_outer: np.ndarray | None = None,
+               w_y: np.ndarray | None = None, w_x: np.ndarray | None = None):
+    self.ctx = ctx
+    self.n_cells = int(n_cells)
+    keep = []
+
+    def prep(a, dtype):
+      if a is None:
+        return None
+      a = np.ascontiguousarray(a, dtype=dtype)
+      keep.append(a)
+      return a
+
+    ens, target, mask = (prep(ens, np.uint64), prep(target, np.uint64),
+                         prep(mask, np.uint64))
+    cell = prep(cell, np.int32)
+    w_outer, w_y, w_x = (prep(w_outer, np.float64), prep(w_y, np.float64),
+                         prep(w_x, np.float64))
+    n_jobs = len(ens)
+    for name, arr, n in (('target', target, n_jobs), ('mask', mask, n_jobs),
+                         ('cell', cell, n_jobs), ('w_outer', w_outer, n_jobs),
+                         ('w_y', w_y, ny), ('w_x', w_x, nx)):
+      if arr is not None and len(arr) != n:
+        raise ValueError(f'{name} has {len(arr)} entries, expected {n}')
+    desc = CrpsDesc(
+        space=space, flags=flags, n_jobs=n_jobs, ny=ny, nx=nx,
+        n_members=n_members, member_stride=member_stride,
+        point_stride=point_stride, n_cells=n_cells,
+        ens=_as_ptr(ens, c_uint64), target=_as_ptr(target, c_uint64),
+        mask=_as_ptr(mask, c_uint64), cell=_as_ptr(cell, c_int32),
+        w_outer=_as_ptr(w_outer, c_double), w_y=_as_ptr(w_y, c_double),
+        w_x=_as_ptr(w_x, c_double))
+    handle = c_void_p()
+    code = ctx.lib.wbx_crps_plan_create(ctx.handle, ctypes.byref(desc),
+                                        ctypes.byref(handle))
+    if code != WBX_OK:
+      msg = (ctx.lib.wbx_last_error() or b'').decode()
+      if 'n_ensemble < 2' in msg:
+        raise ValueError(msg)  # probabilistic.py:210-212
+      raise WbxError(code, msg)
+    self.handle = handle
+    del keep
+
+  def run_to_host(self):
+    """(sum_ws [n_cells, 2], sum_w [n_cells, 2]); column 0 skill, 1 spread."""
+    ws = np.empty((self.n_cells, 2), np.float64)
+    w = np.empty((self.n_cells, 2), np.float64)
+    check(self.ctx.lib.wbx_crps_plan_run(
+        self.ctx.handle, self.handle, ws.ctypes.data, w.ctypes.data,
+        SPACE_HOST, 0))
+    return ws, w
+
+  def run_to_device(self, ws_ptr: int, w_ptr: int, accumulate: bool = False):
+    check(self.ctx.lib.wbx_crps_plan_run(
+        self.ctx.handle, self.handle, c_void_p(ws_ptr), c_void_p(w_ptr),
+        SPACE_DEVICE, 1 if accumulate else 0))
+
+  def close(self):
+    if self.handle:
+      self.ctx.lib.wbx_crps_plan_destroy(self.ctx.handle, self.handle)
+      self.handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass

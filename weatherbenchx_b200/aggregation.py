@@ -204,7 +204,9 @@ class Aggregator:
     if self.bin_by:
       raise engine.FastPathUnavailable('binning')
     weights = [w.weights(first) for w in self.weigh_by or []]
-    res = engine.aggregate_fused(
+    launch = (engine.aggregate_crps if first.kind in engine.CRPS_SLOT
+              else engine.aggregate_fused)
+    res = launch(
         stats, self.reduce_dims, weights,
         masked=self.masked and 'mask' in first.coords, skipna=self.skipna)
     if res is None:
@@ -272,6 +274,25 @@ class Aggregator:
       for m in members:
         by_clim[m[2].group_key()[2]].append(m)
       plain = by_clim.pop(None, [])
+      # ensemble (CRPS) statistics run in their own kernel.
+      crps = [m for m in plain if m[2].kind in engine.CRPS_SLOT]
+      plain = [m for m in plain if m[2].kind not in engine.CRPS_SLOT]
+      by_skip: dict = collections.defaultdict(list)
+      for m in crps:
+        by_skip[(m[2].ensemble_dim, m[2].skipna_ensemble)].append(m)
+      for group in by_skip.values():
+        # one launch evaluates the skill and ONE flavour (fair / unfair) of
+        # the spread; a second flavour gets its own launch.
+        fair_values = sorted({m[2].fair for m in group
+                              if m[2].kind == 'CRPSSpread'}, reverse=True)
+        main = [m for m in group if m[2].kind != 'CRPSSpread' or
+                m[2].fair == fair_values[0]]
+        subgroups.append(main)
+        for fv in fair_values[1:]:
+          subgroups.append([m for m in group if m[2].kind == 'CRPSSpread'
+                            and m[2].fair == fv])
+      if not plain and not by_clim:
+        continue
       if by_clim:
         keys = list(by_clim)
         by_clim[keys[0]].extend(plain)

@@ -1,0 +1,769 @@
+// Ensemble CRPS statistics on the GPU: CRPSSkill and CRPSSpread
+// (metrics/probabilistic.py:116-145, 165-247) fused with the weighted
+// aggregation of Aggregator.aggregate_stat_var (aggregation.py:337-366).
+//
+//   skill(point)  = mean_m |x_m - y|
+//   spread(point) = sum_{i,j} |x_i - x_j| / (M (M - fair))
+//                 = 2 sum_{i<j} |x_i - x_j| / (M (M - fair))
+// with skipna_ensemble: NaN members are dropped per point and M becomes the
+// per-point count (probabilistic.py:206-209); otherwise a NaN member makes the
+// point NaN, exactly as the NumPy reductions of the reference do.
+//
+// The member-pair sum is O(M^2): 2 FP32 instructions per pair, ~2.55 kFLOP and
+// 4 (M + 1) bytes per grid point at M = 50, i.e. at the FP32-issue / HBM ridge
+// (DESIGN.md).  One thread owns one grid point.  A CTA stages a tile of G
+// points x M members in shared memory (member-major, so the per-thread reads
+// are conflict-free whatever the global layout is), then every thread walks
+// the pair triangle in 8 x 8 register tiles: 16 LDS feed 128 FP32 instructions.
+// The weighted reduction reuses the record scheme of the deterministic kernel
+// (per-(CTA, cell, warp) partials, fixed-order second pass).
+#include <algorithm>
+#include <new>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace wbx {
+
+constexpr int kCrpsThreads = 128;          // = grid points per tile
+constexpr int kCrpsWarps = kCrpsThreads / 32;
+constexpr int kCrpsPitch = kCrpsThreads + 1;  // smem row pitch (floats)
+constexpr int kBlk = 8;                    // register tile edge
+
+struct CrpsParams {
+  const uint64_t* ens;      // [n_jobs] address of (member 0, point 0)
+  const uint64_t* target;   // [n_jobs]
+  const uint64_t* mask;     // [n_jobs] or NULL
+  const int32_t* cell;
+  const double* w_outer;
+  const double* w_y;
+  const double* w_x;
+  long long n_jobs;
+  long long total_tiles;
+  long long member_stride;  // elements
+  long long point_stride;   // elements
+  int cell_base;
+  int ny, nx, slab;
+  int n_members;
+  int tiles_per_slab;
+  int fair;
+  int skipna_stat;          // Aggregator(skipna=True)
+  double* records;
+};
+
+// skill / spread of one grid point whose members sit in a shared-memory column
+// xs[m * pitch].  ENS_SKIPNA drops NaN members.
+template <bool ENS_SKIPNA>
+__device__ __forceinline__ void crps_point(const float* __restrict__ xs,
+                                           const int pitch, const int M,
+                                           const float y, const int fair,
+                                           float* skill, float* spread) {
+  float sk = 0.f, sp = 0.f;
+  int n = 0;
+  const int Mb = M & ~(kBlk - 1);
+  auto pair = [&](float a, float b) {
+    const float d = fabsf(a - b);
+    if constexpr (ENS_SKIPNA) {
+      sp += (d == d) ? d : 0.f;
+    } else {
+      sp += d;
+    }
+  };
+  auto single = [&](float a) {
+    const float d = fabsf(a - y);
+    if constexpr (ENS_SKIPNA) {
+      const bool ok = (a == a);
+      // NaN target still poisons the skill (mean over members of NaN == NaN).
+      sk += ok ? d : 0.f;
+      n += ok ? 1 : 0;
+    } else {
+      sk += d;
+    }
+  };
+  for (int ib = 0; ib < Mb; ib += kBlk) {
+    float xi[kBlk];
+#pragma unroll
+    for (int i = 0; i < kBlk; ++i) xi[i] = xs[(ib + i) * pitch];
+#pragma unroll
+    for (int i = 0; i < kBlk; ++i) single(xi[i]);
+#pragma unroll
+    for (int i = 0; i < kBlk; ++i)
+#pragma unroll
+      for (int j = i + 1; j < kBlk; ++j) pair(xi[i], xi[j]);
+    for (int jb = ib + kBlk; jb < Mb; jb += kBlk) {
+      float xj[kBlk];
+#pragma unroll
+      for (int j = 0; j < kBlk; ++j) xj[j] = xs[(jb + j) * pitch];
+#pragma unroll
+      for (int i = 0; i < kBlk; ++i)
+#pragma unroll
+        for (int j = 0; j < kBlk; ++j) pair(xi[i], xj[j]);
+    }
+  }
+  // tail members (M % 8): pair each with every earlier member.
+  for (int t = Mb; t < M; ++t) {
+    const float xt = xs[t * pitch];
+    single(xt);
+    for (int m = 0; m < t; ++m) pair(xt, xs[m * pitch]);
+  }
+  if constexpr (ENS_SKIPNA) {
+    const float fn = static_cast<float>(n);
+    *skill = __fdiv_rn(sk, fn);  // n == 0 -> 0/0 = NaN, as nanmean does
+    *spread = __fdiv_rn(2.f * sp, fn * (fn - static_cast<float>(fair)));
+  } else {
+    *skill = __fdiv_rn(sk, static_cast<float>(M));
+    *spread = __fdiv_rn(2.f * sp, static_cast<float>(M * (M - fair)));
+  }
+}
+
+constexpr int kCrpsAcc = 4;  // skill, spread, weight(skill), weight(spread)
+
+template <bool ENS_SKIPNA, bool MASK>
+__global__ void __launch_bounds__(kCrpsThreads)
+    crps_reduce_kernel(const CrpsParams P) {
+  extern __shared__ float smem[];
+  float* xs = smem;                                  // [M][pitch]
+  float* ys = xs + static_cast<size_t>(P.n_members) * kCrpsPitch;  // [G]
+  unsigned char* ms = reinterpret_cast<unsigned char*>(ys + kCrpsThreads);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = P.n_members;
+  const long long t_begin =
+      (static_cast<long long>(blockIdx.x) * P.total_tiles) / gridDim.x;
+  const long long t_end =
+      (static_cast<long long>(blockIdx.x + 1) * P.total_tiles) / gridDim.x;
+  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0};
+  int cur_cell = -1;
+  long long job = t_begin / P.tiles_per_slab;
+  int k = static_cast<int>(t_begin - job * P.tiles_per_slab);
+  for (long long g = t_begin; g < t_end; ++g) {
+    const float* ea = reinterpret_cast<const float*>(__ldg(P.ens + job));
+    const float* ta = reinterpret_cast<const float*>(__ldg(P.target + job));
+    const unsigned char* ma = nullptr;
+    if constexpr (MASK)
+      ma = reinterpret_cast<const unsigned char*>(__ldg(P.mask + job));
+    const int cell = __ldg(P.cell + job);
+    const double wo = P.w_outer ? __ldg(P.w_outer + job) : 1.0;
+    if (cell != cur_cell) {
+      if (cur_cell >= 0) {
+        double* rec = P.records +
+                      ((static_cast<size_t>(blockIdx.x) + (cur_cell - P.cell_base)) *
+                           kCrpsWarps + warp) * kCrpsAcc;
+#pragma unroll
+        for (int a = 0; a < kCrpsAcc; ++a) {
+          const double v = warp_sum(acc[a]);
+          if (lane == 0) rec[a] = v;
+          acc[a] = 0.0;
+        }
+      }
+      cur_cell = cell;
+    }
+    const int e0 = k * kCrpsThreads;
+    const int len = min(kCrpsThreads, P.slab - e0);
+    __syncthreads();  // everyone is done with the previous tile
+    // ---- stage the tile: coalesce along whichever axis is contiguous ------
+    if (P.point_stride == 1) {
+      for (int m = warp; m < M; m += kCrpsWarps) {
+        const float* src = ea + static_cast<long long>(m) * P.member_stride + e0;
+        for (int q = lane; q < len; q += 32)
+          xs[m * kCrpsPitch + q] = ldg_stream_f1(src + q);
+      }
+    } else {
+      // member axis fastest (member_stride == 1 typically): walk the tile in
+      // memory order and transpose into the member-major layout.
+      const long long total = static_cast<long long>(len) * M;
+      for (long long q = tid; q < total; q += kCrpsThreads) {
+        const int pt = static_cast<int>(q / M);
+        const int m = static_cast<int>(q - static_cast<long long>(pt) * M);
+        xs[m * kCrpsPitch + pt] = ldg_stream_f1(
+            ea + static_cast<long long>(e0 + pt) * P.point_stride +
+            static_cast<long long>(m) * P.member_stride);
+      }
+    }
+    if (tid < len) {
+      ys[tid] = ldg_stream_f1(ta + e0 + tid);
+      if constexpr (MASK) ms[tid] = __ldg(ma + e0 + tid);
+    }
+    __syncthreads();
+    if (tid < len) {
+      float skill, spread;
+      crps_point<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], P.fair, &skill,
+                             &spread);
+      const unsigned e = static_cast<unsigned>(e0 + tid);
+      const unsigned yy = e / static_cast<unsigned>(P.nx);
+      const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
+      double w = wo;
+      if (P.w_y) w *= __ldg(P.w_y + yy);
+      if (P.w_x) w *= __ldg(P.w_x + xx);
+      bool base = true;
+      if constexpr (MASK) base = ms[tid] != 0;
+      const bool ok_sk = base && (!P.skipna_stat || skill == skill);
+      const bool ok_sp = base && (!P.skipna_stat || spread == spread);
+      acc[0] += (ok_sk ? static_cast<double>(skill) : 0.0) * w;
+      acc[1] += (ok_sp ? static_cast<double>(spread) : 0.0) * w;
+      acc[2] += (ok_sk ? 1.0 : 0.0) * w;
+      acc[3] += (ok_sp ? 1.0 : 0.0) * w;
+    }
+    if (++k == P.tiles_per_slab) {
+      k = 0;
+      ++job;
+    }
+  }
+  if (cur_cell >= 0) {
+    double* rec = P.records +
+                  ((static_cast<size_t>(blockIdx.x) + (cur_cell - P.cell_base)) *
+                       kCrpsWarps + warp) * kCrpsAcc;
+#pragma unroll
+    for (int a = 0; a < kCrpsAcc; ++a) {
+      const double v = warp_sum(acc[a]);
+      if (lane == 0) rec[a] = v;
+    }
+  }
+}
+
+// out[c*2 + s] (statistics) and out_w[c*2 + s] (weights), one warp per output.
+struct CrpsFinalizeParams {
+  const double* records;
+  const int32_t* cell_first_job;
+  double* out_ws;
+  double* out_w;
+  long long total_tiles;
+  int n_cells, grid_main, tiles_per_slab, accumulate;
+};
+
+__global__ void __launch_bounds__(128) crps_finalize_kernel(
+    const CrpsFinalizeParams F) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= F.n_cells * kCrpsAcc) return;
+  const int c = warp_global / kCrpsAcc;
+  const int a = warp_global - c * kCrpsAcc;
+  const long long ft =
+      static_cast<long long>(F.cell_first_job[c]) * F.tiles_per_slab;
+  const long long lt =
+      static_cast<long long>(F.cell_first_job[c + 1]) * F.tiles_per_slab - 1;
+  const long long G = F.grid_main;
+  const int b_lo = static_cast<int>(((ft + 1) * G - 1) / F.total_tiles);
+  const int b_hi = static_cast<int>(((lt + 1) * G - 1) / F.total_tiles);
+  const int n = (b_hi - b_lo + 1) * kCrpsWarps;
+  const double* rec =
+      F.records + (static_cast<size_t>(b_lo) + c) * kCrpsWarps * kCrpsAcc + a;
+  double sum = 0.0;
+  for (int i = lane; i < n; i += 32) sum += rec[static_cast<size_t>(i) * kCrpsAcc];
+  sum = warp_sum(sum);
+  if (lane == 0) {
+    double* dst = a < 2 ? F.out_ws + (size_t)c * 2 + a
+                        : F.out_w + (size_t)c * 2 + (a - 2);
+    *dst = F.accumulate ? (*dst + sum) : sum;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-point CRPS statistics for arbitrary layouts (what CRPSSkill / CRPSSpread
+// .compute return when the full field is wanted).
+// ---------------------------------------------------------------------------
+struct CrpsPointParams {
+  const float* ens;
+  const float* target;
+  long long size[WBX_MAX_DIMS];
+  long long e_stride[WBX_MAX_DIMS];
+  long long t_stride[WBX_MAX_DIMS];
+  long long member_stride;
+  long long n_points;
+  int ndim, n_members, fair;
+  float* skill;
+  float* spread;
+};
+
+template <bool ENS_SKIPNA>
+__global__ void __launch_bounds__(kCrpsThreads)
+    crps_pointwise_kernel(const CrpsPointParams P) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const long long pt = blockIdx.x * static_cast<long long>(kCrpsThreads) + tid;
+  if (pt >= P.n_points) return;
+  long long rem = pt, eo = 0, to = 0;
+  for (int d = P.ndim - 1; d >= 0; --d) {
+    const long long i = rem % P.size[d];
+    rem /= P.size[d];
+    eo += i * P.e_stride[d];
+    to += i * P.t_stride[d];
+  }
+  float* col = smem + tid;
+  for (int m = 0; m < P.n_members; ++m)
+    col[m * kCrpsPitch] = P.ens[eo + m * P.member_stride];
+  float skill, spread;
+  crps_point<ENS_SKIPNA>(col, kCrpsPitch, P.n_members, P.target[to], P.fair,
+                         &skill, &spread);
+  if (P.skill) P.skill[pt] = skill;
+  if (P.spread) P.spread[pt] = spread;
+}
+
+}  // namespace wbx
+
+struct wbx_crps_plan {
+  int32_t space = 0, flags = 0;
+  int64_t n_jobs = 0, ny = 0, nx = 0, n_members = 0, n_cells = 0;
+  int64_t member_stride = 0, point_stride = 0;
+  bool has_mask = false, has_wo = false, has_wy = false, has_wx = false;
+  std::vector<uint64_t> ens, target, mask;
+  std::vector<int32_t> cell;
+  std::vector<double> wo, wy, wx;
+  int tiles_per_slab = 0;
+  size_t smem_bytes = 0;
+  wbx::DevBuf tables, weights;
+  wbx::CrpsParams params{};
+  const int32_t* d_cell_first_job = nullptr;
+  const double* d_wy = nullptr;
+  const double* d_wx = nullptr;
+  int grid = 0;
+  std::vector<unsigned char> chunk_host[2];
+};
+
+namespace wbx {
+
+static inline size_t rup(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
+                       const CrpsParams& P, int grid) {
+  const bool ens_skipna = (plan->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
+  int prc = ctx->prof_begin();
+  if (prc != WBX_OK) return prc;
+#define WBX_CRPS_LAUNCH(A, B)                                                  \
+  do {                                                                         \
+    auto kern = crps_reduce_kernel<A, B>;                                      \
+    WBX_CUDA(cudaFuncSetAttribute(kern,                                        \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  static_cast<int>(plan->smem_bytes)));        \
+    kern<<<grid, kCrpsThreads, plan->smem_bytes, ctx->stream>>>(P);            \
+  } while (0)
+  if (ens_skipna && plan->has_mask) WBX_CRPS_LAUNCH(true, true);
+  else if (ens_skipna) WBX_CRPS_LAUNCH(true, false);
+  else if (plan->has_mask) WBX_CRPS_LAUNCH(false, true);
+  else WBX_CRPS_LAUNCH(false, false);
+#undef WBX_CRPS_LAUNCH
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return ctx->prof_end();
+}
+
+static int crps_grid(const wbx_ctx* ctx, const wbx_crps_plan* plan,
+                     long long total_tiles) {
+  // several CTAs per SM so that staging of one overlaps the pair loop of others
+  const size_t per_sm = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+  long long ctas_per_sm = std::max<size_t>(1, per_sm / (plan->smem_bytes + 1024));
+  ctas_per_sm = std::min<long long>(ctas_per_sm, 8);
+  const long long g = ctx->sm_count * ctas_per_sm;
+  return static_cast<int>(std::max(1ll, std::min(g, total_tiles)));
+}
+
+static void crps_cell_first(const wbx_crps_plan* plan, int64_t j0, int64_t j1,
+                            std::vector<int32_t>* first) {
+  const int c0 = plan->cell[j0];
+  const int n = plan->cell[j1 - 1] - c0 + 1;
+  first->assign(n + 1, 0);
+  for (int64_t j = j0; j < j1; ++j)
+    (*first)[plan->cell[j] - c0 + 1] = static_cast<int32_t>(j - j0 + 1);
+}
+
+// Packs the job tables of [j0, j1) (with the given operand addresses) into one
+// host blob, uploads it and fills P.  Returns the device pointer of the
+// cell_first_job table through `d_first`.
+static int crps_upload_tables(wbx_ctx* ctx, const wbx_crps_plan* plan,
+                              int64_t j0, int64_t j1, const uint64_t* ens,
+                              const uint64_t* target, const uint64_t* mask,
+                              std::vector<unsigned char>* host, DevBuf* dev,
+                              cudaStream_t stream, CrpsParams* P,
+                              const int32_t** d_first, int* n_cells) {
+  const size_t nj = static_cast<size_t>(j1 - j0);
+  std::vector<int32_t> first;
+  crps_cell_first(plan, j0, j1, &first);
+  *n_cells = static_cast<int>(first.size()) - 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += rup(bytes, 16);
+    return o;
+  };
+  const size_t o_ens = take(nj * 8), o_tgt = take(nj * 8);
+  const size_t o_mask = plan->has_mask ? take(nj * 8) : 0;
+  const size_t o_wo = plan->has_wo ? take(nj * 8) : 0;
+  const size_t o_cell = take(nj * 4);
+  const size_t o_first = take(first.size() * 4);
+  host->assign(off, 0);
+  memcpy(host->data() + o_ens, ens, nj * 8);
+  memcpy(host->data() + o_tgt, target, nj * 8);
+  if (plan->has_mask) memcpy(host->data() + o_mask, mask, nj * 8);
+  if (plan->has_wo) memcpy(host->data() + o_wo, plan->wo.data() + j0, nj * 8);
+  memcpy(host->data() + o_cell, plan->cell.data() + j0, nj * 4);
+  memcpy(host->data() + o_first, first.data(), first.size() * 4);
+  int rc = dev->reserve(off);
+  if (rc != WBX_OK) return rc;
+  unsigned char* base = dev->as<unsigned char>();
+  WBX_CUDA(cudaMemcpyAsync(base, host->data(), off, cudaMemcpyHostToDevice,
+                           stream));
+  P->ens = reinterpret_cast<const uint64_t*>(base + o_ens);
+  P->target = reinterpret_cast<const uint64_t*>(base + o_tgt);
+  P->mask = plan->has_mask ? reinterpret_cast<const uint64_t*>(base + o_mask)
+                           : nullptr;
+  P->w_outer =
+      plan->has_wo ? reinterpret_cast<const double*>(base + o_wo) : nullptr;
+  P->cell = reinterpret_cast<const int32_t*>(base + o_cell);
+  P->w_y = plan->d_wy;
+  P->w_x = plan->d_wx;
+  P->n_jobs = static_cast<long long>(nj);
+  P->total_tiles = static_cast<long long>(nj) * plan->tiles_per_slab;
+  P->cell_base = plan->cell[j0];
+  P->ny = static_cast<int>(plan->ny);
+  P->nx = static_cast<int>(plan->nx);
+  P->slab = static_cast<int>(plan->ny * plan->nx);
+  P->n_members = static_cast<int>(plan->n_members);
+  P->tiles_per_slab = plan->tiles_per_slab;
+  P->fair = (plan->flags & WBX_CRPS_FAIR) ? 1 : 0;
+  P->skipna_stat = (plan->flags & WBX_FLAG_SKIPNA) ? 1 : 0;
+  *d_first = reinterpret_cast<const int32_t*>(base + o_first);
+  return WBX_OK;
+}
+
+static int crps_finalize(wbx_ctx* ctx, const wbx_crps_plan* plan,
+                         const double* records, const int32_t* d_first,
+                         int n_cells, int grid_main, long long total_tiles,
+                         double* out_ws, double* out_w, int accumulate) {
+  CrpsFinalizeParams F;
+  F.records = records;
+  F.cell_first_job = d_first;
+  F.out_ws = out_ws;
+  F.out_w = out_w;
+  F.total_tiles = total_tiles;
+  F.n_cells = n_cells;
+  F.grid_main = grid_main;
+  F.tiles_per_slab = plan->tiles_per_slab;
+  F.accumulate = accumulate;
+  const long long threads = static_cast<long long>(n_cells) * kCrpsAcc * 32;
+  const int block = 128;
+  crps_finalize_kernel<<<static_cast<int>((threads + block - 1) / block), block,
+                         0, ctx->stream>>>(F);
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return WBX_OK;
+}
+
+}  // namespace wbx
+
+extern "C" {
+
+int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* d,
+                         wbx_crps_plan** out) {
+  WBX_REQUIRE(ctx && d && out, "wbx_crps_plan_create: NULL argument");
+  *out = nullptr;
+  WBX_REQUIRE(d->space == WBX_SPACE_DEVICE || d->space == WBX_SPACE_HOST,
+              "crps: bad space");
+  WBX_REQUIRE(d->n_jobs >= 1 && d->n_jobs < (1ll << 31), "crps: bad n_jobs");
+  WBX_REQUIRE(d->ny >= 1 && d->nx >= 1 && d->ny * d->nx < (1ll << 30),
+              "crps: bad slab shape");
+  const bool ens_skipna = (d->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
+  if (!ens_skipna && d->n_members < 2) {
+    wbx::set_error("Cannot estimate CRPS spread with n_ensemble < 2.");
+    return WBX_ERR_INVALID;  // probabilistic.py:210-212
+  }
+  WBX_REQUIRE(d->n_members >= 1 && d->n_members <= 1024,
+              "crps: n_members %lld out of range [1, 1024]",
+              (long long)d->n_members);
+  WBX_REQUIRE(d->ens && d->target && d->cell, "crps: missing tables");
+  WBX_REQUIRE(d->member_stride >= 1 && d->point_stride >= 1,
+              "crps: strides must be positive");
+  WBX_REQUIRE(d->n_cells >= 1 && d->n_cells <= d->n_jobs, "crps: bad n_cells");
+  const bool masked = (d->flags & WBX_FLAG_MASKED) != 0;
+  WBX_REQUIRE(masked == (d->mask != nullptr),
+              "crps: WBX_FLAG_MASKED and a mask table must be given together");
+  WBX_REQUIRE(d->cell[0] == 0, "crps: cell[0] must be 0");
+  for (int64_t j = 1; j < d->n_jobs; ++j) {
+    const int step = d->cell[j] - d->cell[j - 1];
+    WBX_REQUIRE(step == 0 || step == 1, "crps: cell[] must be non-decreasing");
+  }
+  WBX_REQUIRE(d->cell[d->n_jobs - 1] == d->n_cells - 1,
+              "crps: cell[] must end at n_cells - 1");
+  for (int64_t j = 0; j < d->n_jobs; ++j)
+    WBX_REQUIRE(d->ens[j] && d->target[j] && (!d->mask || d->mask[j]),
+                "crps: NULL slab address (job %lld)", (long long)j);
+  if (d->space == WBX_SPACE_HOST) {
+    const int64_t slab = d->ny * d->nx;
+    const bool a = d->point_stride == 1 && d->member_stride >= slab;
+    const bool b = d->member_stride == 1 && d->point_stride == d->n_members;
+    if (!a && !b) {
+      wbx::set_error("crps: host-space plans need member-major slabs "
+                     "(point_stride 1) or member-last points (member_stride 1)");
+      return WBX_ERR_UNSUPPORTED;
+    }
+  }
+  wbx_crps_plan* p = new (std::nothrow) wbx_crps_plan();
+  if (!p) {
+    wbx::set_error("crps: out of host memory");
+    return WBX_ERR_NOMEM;
+  }
+  p->space = d->space;
+  p->flags = d->flags;
+  p->n_jobs = d->n_jobs;
+  p->ny = d->ny;
+  p->nx = d->nx;
+  p->n_members = d->n_members;
+  p->n_cells = d->n_cells;
+  p->member_stride = d->member_stride;
+  p->point_stride = d->point_stride;
+  p->has_mask = d->mask != nullptr;
+  p->has_wo = d->w_outer != nullptr;
+  p->has_wy = d->w_y != nullptr;
+  p->has_wx = d->w_x != nullptr;
+  p->ens.assign(d->ens, d->ens + d->n_jobs);
+  p->target.assign(d->target, d->target + d->n_jobs);
+  if (p->has_mask) p->mask.assign(d->mask, d->mask + d->n_jobs);
+  p->cell.assign(d->cell, d->cell + d->n_jobs);
+  if (p->has_wo) p->wo.assign(d->w_outer, d->w_outer + d->n_jobs);
+  if (p->has_wy) p->wy.assign(d->w_y, d->w_y + d->ny);
+  if (p->has_wx) p->wx.assign(d->w_x, d->w_x + d->nx);
+  const int64_t slab = d->ny * d->nx;
+  p->tiles_per_slab =
+      static_cast<int>((slab + wbx::kCrpsThreads - 1) / wbx::kCrpsThreads);
+  p->smem_bytes = static_cast<size_t>(d->n_members) * wbx::kCrpsPitch * 4 +
+                  wbx::kCrpsThreads * 4 + wbx::kCrpsThreads + 64;
+  if (p->smem_bytes > std::min<size_t>(ctx->smem_optin, 227 * 1024)) {
+    delete p;
+    wbx::set_error("crps: %lld members need more shared memory than one SM has",
+                   (long long)d->n_members);
+    return WBX_ERR_UNSUPPORTED;
+  }
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  const size_t wbytes = (p->wy.size() + p->wx.size()) * sizeof(double);
+  if (wbytes) {
+    int rc = p->weights.reserve(wbytes);
+    if (rc != WBX_OK) { delete p; return rc; }
+    double* base = p->weights.as<double>();
+    if (p->has_wy) {
+      WBX_CUDA(cudaMemcpyAsync(base, p->wy.data(), p->wy.size() * 8,
+                               cudaMemcpyHostToDevice, ctx->stream));
+      p->d_wy = base;
+    }
+    if (p->has_wx) {
+      WBX_CUDA(cudaMemcpyAsync(base + p->wy.size(), p->wx.data(),
+                               p->wx.size() * 8, cudaMemcpyHostToDevice,
+                               ctx->stream));
+      p->d_wx = base + p->wy.size();
+    }
+  }
+  if (d->space == WBX_SPACE_DEVICE) {
+    int n_cells = 0;
+    int rc = wbx::crps_upload_tables(
+        ctx, p, 0, p->n_jobs, p->ens.data(), p->target.data(),
+        p->has_mask ? p->mask.data() : nullptr, &p->chunk_host[0], &p->tables,
+        ctx->stream, &p->params, &p->d_cell_first_job, &n_cells);
+    if (rc != WBX_OK) { delete p; return rc; }
+    p->params.member_stride = p->member_stride;
+    p->params.point_stride = p->point_stride;
+    p->grid = wbx::crps_grid(ctx, p, p->params.total_tiles);
+  }
+  WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = p;
+  return WBX_OK;
+}
+
+int wbx_crps_plan_destroy(wbx_ctx* ctx, wbx_crps_plan* plan) {
+  if (!plan) return WBX_OK;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+  }
+  plan->tables.release();
+  plan->weights.release();
+  delete plan;
+  return WBX_OK;
+}
+
+static int crps_run_device(wbx_ctx* ctx, wbx_crps_plan* plan, double* d_ws,
+                           double* d_w, int accumulate) {
+  const size_t rec = (static_cast<size_t>(plan->grid) + plan->n_cells) *
+                     wbx::kCrpsWarps * wbx::kCrpsAcc * sizeof(double);
+  int rc = ctx->records.reserve(rec);
+  if (rc != WBX_OK) return rc;
+  wbx::CrpsParams P = plan->params;
+  P.records = ctx->records.as<double>();
+  rc = wbx::crps_launch(ctx, plan, P, plan->grid);
+  if (rc != WBX_OK) return rc;
+  return wbx::crps_finalize(ctx, plan, P.records, plan->d_cell_first_job,
+                            static_cast<int>(plan->n_cells), plan->grid,
+                            P.total_tiles, d_ws, d_w, accumulate);
+}
+
+static int crps_run_host(wbx_ctx* ctx, wbx_crps_plan* plan, double* d_ws,
+                         double* d_w) {
+  const size_t slab = static_cast<size_t>(plan->ny * plan->nx);
+  const size_t M = static_cast<size_t>(plan->n_members);
+  const size_t ebytes = slab * M * 4, tbytes = slab * 4;
+  const size_t mbytes = wbx::rup(slab, 16);
+  const size_t job_bytes = ebytes + tbytes + (plan->has_mask ? mbytes : 0);
+  int64_t per_chunk =
+      static_cast<int64_t>((ctx->staging_bytes / 2) / job_bytes);
+  per_chunk = std::max<int64_t>(1, std::min<int64_t>(per_chunk, plan->n_jobs));
+  for (int b = 0; b < 2; ++b) {
+    int rc = ctx->staging[b].reserve(static_cast<size_t>(per_chunk) * job_bytes);
+    if (rc != WBX_OK) return rc;
+  }
+  WBX_CUDA(cudaMemsetAsync(d_ws, 0, plan->n_cells * 2 * sizeof(double),
+                           ctx->stream));
+  WBX_CUDA(cudaMemsetAsync(d_w, 0, plan->n_cells * 2 * sizeof(double),
+                           ctx->stream));
+  const bool member_major = plan->point_stride == 1;
+  int buf = 0;
+  std::vector<uint64_t> a_ens, a_tgt, a_mask;
+  for (int64_t j0 = 0; j0 < plan->n_jobs; j0 += per_chunk, buf ^= 1) {
+    const int64_t j1 = std::min<int64_t>(plan->n_jobs, j0 + per_chunk);
+    const size_t nj = static_cast<size_t>(j1 - j0);
+    unsigned char* sbase = ctx->staging[buf].as<unsigned char>();
+    unsigned char* s_ens = sbase;
+    unsigned char* s_tgt = s_ens + nj * ebytes;
+    unsigned char* s_mask = s_tgt + nj * tbytes;
+    WBX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute[buf], 0));
+    a_ens.resize(nj);
+    a_tgt.resize(nj);
+    a_mask.resize(nj);
+    for (size_t j = 0; j < nj; ++j) {
+      const void* src = reinterpret_cast<const void*>(plan->ens[j0 + j]);
+      unsigned char* dst = s_ens + j * ebytes;
+      if (member_major && static_cast<size_t>(plan->member_stride) != slab) {
+        WBX_CUDA(cudaMemcpy2DAsync(dst, slab * 4, src, plan->member_stride * 4,
+                                   slab * 4, M, cudaMemcpyHostToDevice,
+                                   ctx->copy_stream));
+      } else {
+        WBX_CUDA(cudaMemcpyAsync(dst, src, ebytes, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+      }
+      WBX_CUDA(cudaMemcpyAsync(
+          s_tgt + j * tbytes, reinterpret_cast<const void*>(plan->target[j0 + j]),
+          tbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      if (plan->has_mask)
+        WBX_CUDA(cudaMemcpyAsync(
+            s_mask + j * mbytes,
+            reinterpret_cast<const void*>(plan->mask[j0 + j]), slab,
+            cudaMemcpyHostToDevice, ctx->copy_stream));
+      a_ens[j] = reinterpret_cast<uint64_t>(dst);
+      a_tgt[j] = reinterpret_cast<uint64_t>(s_tgt + j * tbytes);
+      a_mask[j] = reinterpret_cast<uint64_t>(s_mask + j * mbytes);
+    }
+    wbx::CrpsParams P{};
+    const int32_t* d_first = nullptr;
+    int n_cells = 0;
+    int rc = wbx::crps_upload_tables(
+        ctx, plan, j0, j1, a_ens.data(), a_tgt.data(),
+        plan->has_mask ? a_mask.data() : nullptr, &plan->chunk_host[buf],
+        &ctx->stage_tables[buf], ctx->copy_stream, &P, &d_first, &n_cells);
+    if (rc != WBX_OK) return rc;
+    P.member_stride = member_major ? static_cast<long long>(slab) : 1;
+    P.point_stride = member_major ? 1 : static_cast<long long>(M);
+    WBX_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+    const int grid = wbx::crps_grid(ctx, plan, P.total_tiles);
+    rc = ctx->records.reserve((static_cast<size_t>(grid) + n_cells) *
+                              wbx::kCrpsWarps * wbx::kCrpsAcc * sizeof(double));
+    if (rc != WBX_OK) return rc;
+    P.records = ctx->records.as<double>();
+    WBX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+    rc = wbx::crps_launch(ctx, plan, P, grid);
+    if (rc != WBX_OK) return rc;
+    rc = wbx::crps_finalize(ctx, plan, P.records, d_first, n_cells, grid,
+                            P.total_tiles,
+                            d_ws + static_cast<size_t>(P.cell_base) * 2,
+                            d_w + static_cast<size_t>(P.cell_base) * 2, 1);
+    if (rc != WBX_OK) return rc;
+    WBX_CUDA(cudaEventRecord(ctx->ev_compute[buf], ctx->stream));
+  }
+  return WBX_OK;
+}
+
+int wbx_crps_plan_run(wbx_ctx* ctx, wbx_crps_plan* plan, double* sum_ws,
+                      double* sum_w, int32_t out_space, int32_t accumulate) {
+  WBX_REQUIRE(ctx && plan && sum_ws && sum_w, "wbx_crps_plan_run: NULL argument");
+  WBX_REQUIRE(out_space == WBX_SPACE_DEVICE || out_space == WBX_SPACE_HOST,
+              "wbx_crps_plan_run: bad out_space");
+  WBX_REQUIRE(!(accumulate && (out_space == WBX_SPACE_HOST ||
+                               plan->space == WBX_SPACE_HOST)),
+              "wbx_crps_plan_run: accumulate needs device inputs and outputs");
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = plan->n_cells * 2 * sizeof(double);
+  double* d_ws = sum_ws;
+  double* d_w = sum_w;
+  if (out_space == WBX_SPACE_HOST) {
+    int rc = ctx->out_ws.reserve(bytes);
+    if (rc != WBX_OK) return rc;
+    rc = ctx->out_w.reserve(bytes);
+    if (rc != WBX_OK) return rc;
+    d_ws = ctx->out_ws.as<double>();
+    d_w = ctx->out_w.as<double>();
+  }
+  int rc = plan->space == WBX_SPACE_DEVICE
+               ? crps_run_device(ctx, plan, d_ws, d_w, accumulate)
+               : crps_run_host(ctx, plan, d_ws, d_w);
+  if (rc != WBX_OK) return rc;
+  if (out_space == WBX_SPACE_HOST) {
+    WBX_CUDA(cudaMemcpyAsync(sum_ws, d_ws, bytes, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    WBX_CUDA(cudaMemcpyAsync(sum_w, d_w, bytes, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return WBX_OK;
+}
+
+int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* d,
+                       float* skill, float* spread) {
+  WBX_REQUIRE(ctx && d, "wbx_crps_pointwise: NULL argument");
+  WBX_REQUIRE(d->ndim >= 0 && d->ndim <= WBX_MAX_DIMS, "crps: bad ndim");
+  WBX_REQUIRE(d->ens && d->target, "crps: NULL operand");
+  WBX_REQUIRE(skill || spread, "crps: nothing to compute");
+  const bool ens_skipna = (d->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
+  if (!ens_skipna && d->n_members < 2) {
+    wbx::set_error("Cannot estimate CRPS spread with n_ensemble < 2.");
+    return WBX_ERR_INVALID;
+  }
+  WBX_REQUIRE(d->n_members >= 1 && d->n_members <= 1024,
+              "crps: n_members out of range");
+  wbx::CrpsPointParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_points = 1;
+  for (int i = 0; i < d->ndim; ++i) {
+    WBX_REQUIRE(d->size[i] >= 1, "crps: empty dim");
+    P.size[i] = d->size[i];
+    P.e_stride[i] = d->ens_stride[i];
+    P.t_stride[i] = d->target_stride[i];
+    P.n_points *= d->size[i];
+  }
+  P.ens = d->ens;
+  P.target = d->target;
+  P.member_stride = d->member_stride;
+  P.ndim = d->ndim;
+  P.n_members = static_cast<int>(d->n_members);
+  P.fair = (d->flags & WBX_CRPS_FAIR) ? 1 : 0;
+  P.skill = skill;
+  P.spread = spread;
+  const size_t smem = static_cast<size_t>(d->n_members) * wbx::kCrpsPitch * 4;
+  WBX_REQUIRE(smem <= std::min<size_t>(ctx->smem_optin, 227 * 1024),
+              "crps: too many members for shared memory");
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  const long long blocks = (P.n_points + wbx::kCrpsThreads - 1) / wbx::kCrpsThreads;
+  WBX_REQUIRE(blocks < (1ll << 31), "crps: too many points");
+  if (ens_skipna) {
+    auto kern = wbx::crps_pointwise_kernel<true>;
+    WBX_CUDA(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<static_cast<unsigned>(blocks), wbx::kCrpsThreads, smem,
+           ctx->stream>>>(P);
+  } else {
+    auto kern = wbx::crps_pointwise_kernel<false>;
+    WBX_CUDA(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<static_cast<unsigned>(blocks), wbx::kCrpsThreads, smem,
+           ctx->stream>>>(P);
+  }
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return WBX_OK;
+}
+
+}  // extern "C"

@@ -269,10 +269,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       const unsigned char* ma = nullptr;
       int cell = 0;
       double wo = 1.0;
-      int it = 0;
-      for (long long g = t_begin; g < t_end; ++g, ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long g = t_begin; g < t_end; ++g) {
         if (job != loaded_job) {
           pa = reinterpret_cast<const float*>(__ldg(P.pred + job));
           ta = reinterpret_cast<const float*>(__ldg(P.target + job));
@@ -310,6 +309,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           k = 0;
           ++job;
         }
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
     return;
@@ -328,10 +331,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   const unsigned x_first = static_cast<unsigned>(4 * ctid) - y_first * unx;
   unsigned ty = 0, tx = 0;  // ... in the current tile
   int prev_e0 = -1;
-  int it = 0;
-  for (long long g = t_begin; g < t_end; ++g, ++it) {
-    const int s = it % stages;
-    const uint32_t ph = (it / stages) & 1;
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long g = t_begin; g < t_end; ++g) {
     mbar_wait(&full[s], ph);
     const StageMeta mt = meta[s];
     if (mt.e0 == 0) {
@@ -385,6 +387,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1u;
+    }
   }
   if (cur_cell >= 0) {
     double* rec = P.records +

@@ -484,6 +484,8 @@ def _broadcast_device(da: xl.DataArray, dims, sizes, device=None):
 
 def materialize(stat: LazyStatistic, device: int | None = None):
   """Evaluates the statistic per grid point on the GPU; returns a CUDA tensor."""
+  if stat.kind in CRPS_SLOT:
+    return materialize_crps(stat, device)
   torch = _torch()
   dims, sizes = stat.dims, stat.sizes
   p = _broadcast_device(stat.predictions, dims, sizes, device)
@@ -510,4 +512,256 @@ def materialize(stat: LazyStatistic, device: int | None = None):
   _cabi.det_elementwise(ctx, _cabi.STAT_SLOT[stat.kind], p.data_ptr(),
                         t.data_ptr(), c.data_ptr() if c is not None else None,
                         out.numel(), out.data_ptr())
+  return out
+
+
+# ---------------------------------------------------------------------------
+# CRPS (ensemble) statistics
+# ---------------------------------------------------------------------------
+
+CRPS_SLOT = {'CRPSSkill': 0, 'CRPSSpread': 1}
+
+
+@dataclasses.dataclass
+class CrpsSpec:
+  """Everything wbx_crps_plan_create needs, plus result labelling."""
+  space: int
+  flags: int
+  ny: int
+  nx: int
+  n_members: int
+  member_stride: int
+  point_stride: int
+  n_cells: int
+  ens: np.ndarray
+  target: np.ndarray
+  mask: np.ndarray | None
+  cell: np.ndarray
+  w_outer: np.ndarray | None
+  w_y: np.ndarray | None
+  w_x: np.ndarray | None
+  scalar: float
+  kept: list
+  kept_shape: list
+  coords: dict
+  keepalive: tuple
+  cache_key: tuple
+
+
+def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
+                    device=None) -> CrpsSpec | None:
+  """Plans one CRPSSkill(+CRPSSpread) launch; None if not applicable."""
+  first = stats[0]
+  dims, sizes = first.dims, first.sizes
+  ens_dim = first.ensemble_dim
+  reduce_set = set(reduce_dims)
+  if not reduce_set.issubset(dims):
+    return None
+  fair = None
+  for s in stats:
+    if (s.group_key() != first.group_key() or s.ensemble_dim != ens_dim or
+        s.skipna_ensemble != first.skipna_ensemble):
+      raise ValueError('CRPS statistics in one launch must share operands')
+    if s.kind == 'CRPSSpread':
+      fair = s.fair
+  pred = _normalise(first.predictions, 'field')
+  tgt = first.targets
+  order = tuple(d for d in dims if d in tgt.dims)
+  if order != tgt.dims:
+    tgt = tgt.transpose(*order)
+  tgt = _normalise(tgt, 'field')
+  mask_da = None
+  if masked and 'mask' in first.coords:
+    mask_da = first.coords['mask']
+    order = tuple(d for d in dims if d in mask_da.dims)
+    if order != mask_da.dims:
+      mask_da = mask_da.transpose(*order)
+    mask_da = _normalise(mask_da, 'mask')
+
+  scalar, per_dim = 1.0, {}
+  for w in weights:
+    if w.ndim == 0:
+      scalar *= float(w.to_numpy())
+    elif w.ndim == 1 and w.dims[0] in dims:
+      d = w.dims[0]
+      vec = np.asarray(w.to_numpy(), dtype=np.float64)
+      per_dim[d] = per_dim[d] * vec if d in per_dim else vec
+    else:
+      raise FastPathUnavailable('multi-dimensional weights')
+
+  # slab: trailing reduced statistic dims, contiguous in targets (and mask),
+  # and laid out with a single point stride in the ensemble.
+  flat = [tgt] + ([mask_da] if mask_da is not None else [])
+  inner: list = []
+  for d in reversed(dims):
+    if d not in reduce_set:
+      break
+    trial = [d] + inner
+    if not all(tuple(o.dims[-len(trial):]) == tuple(trial) for o in flat):
+      break
+    if d not in pred.dims:
+      break
+    inner = trial
+  if not inner:
+    raise FastPathUnavailable('no contiguous reduced trailing dims')
+  tgt_op = _Operand(tgt, 4)
+  if not _inner_contiguous(tgt_op, inner):
+    tgt = _make_contiguous(tgt)
+  if mask_da is not None and not _inner_contiguous(_Operand(mask_da, 1), inner):
+    mask_da = _make_contiguous(mask_da)
+  op_e = _Operand(pred, 4)
+  point_stride = op_e.strides[inner[-1]]
+  expect = point_stride
+  for d in reversed(inner):
+    if sizes[d] != 1 and op_e.strides[d] != expect:
+      raise FastPathUnavailable('ensemble slab is not uniformly strided')
+    expect *= sizes[d]
+  member_stride = op_e.strides[ens_dim]
+  if point_stride < 1 or member_stride < 1:
+    raise FastPathUnavailable('broadcast ensemble')
+
+  fields = [pred, tgt] + ([mask_da] if mask_da is not None else [])
+  if any(f.is_device for f in fields) and not all(f.is_device for f in fields):
+    pred, tgt = to_device(pred, device), to_device(tgt, device)
+    mask_da = to_device(mask_da, device) if mask_da is not None else None
+    op_e = _Operand(pred, 4)
+    point_stride = op_e.strides[inner[-1]]
+    member_stride = op_e.strides[ens_dim]
+  space = _cabi.SPACE_DEVICE if pred.is_device else _cabi.SPACE_HOST
+  op_t = _Operand(tgt, 4)
+  op_m = _Operand(mask_da, 1) if mask_da is not None else None
+
+  outer = [d for d in dims if d not in inner]
+  kept = [d for d in outer if d not in reduce_set]
+  red_outer = [d for d in outer if d in reduce_set]
+  job_dims = kept + red_outer
+  job_sizes = [sizes[d] for d in job_dims]
+  n_cells = int(np.prod([sizes[d] for d in kept], dtype=np.int64)) if kept else 1
+  per_cell = int(np.prod([sizes[d] for d in red_outer], dtype=np.int64)
+                 ) if red_outer else 1
+  y_dims, x_dim = inner[:-1], inner[-1]
+  ny = int(np.prod([sizes[d] for d in y_dims], dtype=np.int64)) if y_dims else 1
+  nx = sizes[x_dim]
+  if space == _cabi.SPACE_HOST:
+    slab = ny * nx
+    member_major = point_stride == 1 and member_stride >= slab
+    member_last = member_stride == 1 and point_stride == first.n_members
+    if not (member_major or member_last):
+      raise FastPathUnavailable('host ensemble layout needs staging')
+
+  flags = 0
+  if skipna:
+    flags |= _cabi.FLAG_SKIPNA
+  if op_m is not None:
+    flags |= _cabi.FLAG_MASKED
+  if fair is None or fair:
+    flags |= _cabi.CRPS_FAIR
+  if first.skipna_ensemble:
+    flags |= _cabi.CRPS_SKIPNA_ENSEMBLE
+
+  def addresses(op):
+    off = _job_offsets(job_dims, job_sizes, op.strides)
+    return (np.uint64(op.ptr) +
+            (off * op.itemsize).astype(np.uint64)).astype(np.uint64)
+
+  coords = {d: first.coords[d] for d in kept if d in first.coords}
+  for name, cv in first.coords.items():
+    if name not in coords and name != 'mask' and set(cv.dims) <= set(kept):
+      coords[name] = cv
+  cache_key = (
+      'crps', space, flags, tuple(dims), tuple(sizes[d] for d in dims),
+      tuple(inner), tuple(sorted(reduce_set, key=str)), first.n_members,
+      op_e.ptr, tuple(op_e.strides.items()), op_t.ptr,
+      tuple(op_t.strides.items()),
+      (op_m.ptr, tuple(op_m.strides.items())) if op_m is not None else None,
+      tuple((str(d), v.tobytes()) for d, v in sorted(
+          per_dim.items(), key=lambda kv: str(kv[0]))))
+  return CrpsSpec(
+      space=space, flags=flags, ny=ny, nx=nx, n_members=first.n_members,
+      member_stride=int(member_stride), point_stride=int(point_stride),
+      n_cells=n_cells, ens=addresses(op_e), target=addresses(op_t),
+      mask=addresses(op_m) if op_m is not None else None,
+      cell=np.repeat(np.arange(n_cells, dtype=np.int32), per_cell),
+      w_outer=_weight_vector(job_dims, sizes, per_dim),
+      w_y=_weight_vector(y_dims, sizes, per_dim), w_x=per_dim.get(x_dim),
+      scalar=scalar, kept=kept, kept_shape=[sizes[d] for d in kept],
+      coords=coords, keepalive=(pred, tgt, mask_da), cache_key=cache_key)
+
+
+def aggregate_crps(stats, reduce_dims, weights=(), masked=False, skipna=False,
+                   device=None):
+  """{kind: (sum_weighted_statistics, sum_weights)} for CRPSSkill/CRPSSpread."""
+  spec = build_crps_spec(stats, reduce_dims, weights, masked, skipna, device)
+  if spec is None:
+    return None
+  ctx = _cabi.get_context(device)
+  plan = _PLAN_CACHE.get(spec.cache_key)
+  if plan is not None and plan.ctx is not ctx:
+    plan = None
+  if plan is None:
+    plan = _cabi.CrpsPlan(
+        ctx, space=spec.space, flags=spec.flags, ny=spec.ny, nx=spec.nx,
+        n_members=spec.n_members, member_stride=spec.member_stride,
+        point_stride=spec.point_stride, ens=spec.ens, target=spec.target,
+        mask=spec.mask, cell=spec.cell, n_cells=spec.n_cells,
+        w_outer=spec.w_outer, w_y=spec.w_y, w_x=spec.w_x)
+    _PLAN_CACHE[spec.cache_key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+      _, old = _PLAN_CACHE.popitem(last=False)
+      old.close()
+  else:
+    _PLAN_CACHE.move_to_end(spec.cache_key)
+  plan.keepalive = spec.keepalive
+  if spec.space == _cabi.SPACE_DEVICE:
+    ctx.use_torch_stream()
+  ws, w = plan.run_to_host()
+  out = {}
+  for s in stats:
+    slot = CRPS_SLOT[s.kind]
+    out[s.kind] = (
+        xl.DataArray((ws[:, slot] * spec.scalar).reshape(spec.kept_shape),
+                     spec.kept, coords=spec.coords, name=s.name),
+        xl.DataArray((w[:, slot] * spec.scalar).reshape(spec.kept_shape),
+                     spec.kept, coords=spec.coords, name=s.name))
+  return out
+
+
+def materialize_crps(stat, device=None):
+  """Per-gridpoint CRPSSkill / CRPSSpread field (wbx_crps_pointwise)."""
+  import ctypes  # pylint: disable=g-import-not-at-top
+  torch = _torch()
+  dims, sizes = stat.dims, stat.sizes
+  if len(dims) > _cabi.MAX_DIMS:
+    raise NotImplementedError('too many dims')
+  pred = to_device(_normalise(stat.predictions, 'field'), device)
+  tgt = to_device(_normalise(stat.targets, 'field'), device)
+  pe, te = pred.data, tgt.data
+  ps = dict(zip(pred.dims, pe.stride()))
+  ts = dict(zip(tgt.dims, te.stride()))
+  desc = _cabi.CrpsPointDesc()
+  desc.ndim = len(dims)
+  desc.flags = ((_cabi.CRPS_FAIR if stat.fair else 0) |
+                (_cabi.CRPS_SKIPNA_ENSEMBLE if stat.skipna_ensemble else 0))
+  desc.n_members = stat.n_members
+  desc.member_stride = ps[stat.ensemble_dim]
+  for i, d in enumerate(dims):
+    desc.size[i] = sizes[d]
+    desc.ens_stride[i] = ps.get(d, 0) if sizes[d] != 1 else 0
+    desc.target_stride[i] = ts.get(d, 0) if (
+        d in ts and tgt.sizes[d] != 1) else 0
+  desc.ens, desc.target = pe.data_ptr(), te.data_ptr()
+  out = torch.empty([sizes[d] for d in dims], dtype=torch.float32,
+                    device=pe.device)
+  ctx = _cabi.get_context(pe.device.index)
+  ctx.use_torch_stream()
+  skill = out.data_ptr() if stat.kind == 'CRPSSkill' else None
+  spread = out.data_ptr() if stat.kind == 'CRPSSpread' else None
+  code = ctx.lib.wbx_crps_pointwise(ctx.handle, ctypes.byref(desc),
+                                    ctypes.c_void_p(skill),
+                                    ctypes.c_void_p(spread))
+  if code != _cabi.WBX_OK:
+    msg = (ctx.lib.wbx_last_error() or b'').decode()
+    if 'n_ensemble < 2' in msg:
+      raise ValueError(msg)
+    raise _cabi.WbxError(code, msg)
   return out

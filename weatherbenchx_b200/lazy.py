@@ -136,5 +136,45 @@ class LazyStatistic(xl.DataArray):
     return out
 
 
+class LazyEnsembleStatistic(LazyStatistic):
+  """CRPSSkill / CRPSSpread of an ensemble prediction (deferred).
+
+  ``predictions`` carries ``ensemble_dim``; the statistic does not.
+  """
+
+  def __init__(self, kind: str, predictions: xl.DataArray,
+               targets: xl.DataArray, ensemble_dim: str, fair: bool,
+               skipna_ensemble: bool):
+    if ensemble_dim not in predictions.dims:
+      raise ValueError(
+          f'Dimension {ensemble_dim} not found in {predictions.dims}')
+    if ensemble_dim in targets.dims:
+      raise NotImplementedError(
+          'ensemble targets (CRPSSkill with a pseudo-ensemble of targets, '
+          'probabilistic.py:135-142) are outside the B200 hot path')
+    xl._check_index_coords(predictions, targets)  # pylint: disable=protected-access
+    pdims = tuple(d for d in predictions.dims if d != ensemble_dim)
+    dims = pdims + tuple(d for d in targets.dims if d not in pdims)
+    sizes = dict(targets.sizes, **predictions.sizes)
+    self.kind = kind
+    self.predictions = predictions
+    self.targets = targets
+    self.climatology = None
+    self.ensemble_dim = ensemble_dim
+    self.fair = bool(fair)
+    self.skipna_ensemble = bool(skipna_ensemble)
+    self.dims = dims
+    self._sizes = {d: sizes[d] for d in dims}
+    self.name = predictions.name
+    self.attrs = {}
+    coords = xl._merge_coords(predictions, targets, dims)  # pylint: disable=protected-access
+    self._coords = {k: v for k, v in coords.items() if ensemble_dim not in v.dims}
+    self._materialized = None
+
+  @property
+  def n_members(self) -> int:
+    return self.predictions.sizes[self.ensemble_dim]
+
+
 def statistic_names(stats: Sequence[LazyStatistic]) -> list:
   return [s.kind for s in stats]

@@ -1,0 +1,100 @@
+"""Ensemble CRPS statistics and metric served by the CUDA CRPS kernel.
+
+Mirrors the hot-path subset of
+/root/reference/weatherbenchX/metrics/probabilistic.py: CRPSSkill :116-145,
+CRPSSpread :165-247, CRPSEnsemble :606-688 (same constructor arguments, same
+unique_name strings, same errors).  ``use_sort`` is accepted for API parity: as
+in the reference it does not enter the statistic's unique_name -- both
+estimators compute the same statistic -- and the kernel always evaluates the
+O(M^2) pair sum (which also serves skipna_ensemble, that the reference's sort
+branch rejects).
+"""
+
+from __future__ import annotations
+
+from typing import Mapping
+
+from weatherbenchx_b200.lazy import LazyEnsembleStatistic
+from weatherbenchx_b200.metrics import base
+
+ENSEMBLE_DIM = 'number'
+
+
+class CRPSSkill(base.PerVariableStatistic):
+  """The skill term of CRPS, E|X - Y|."""
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM,
+               skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def unique_name(self) -> str:
+    return f'CRPSSkill_{self._ensemble_dim}'
+
+  def _compute_per_variable(self, predictions, targets):
+    return LazyEnsembleStatistic(
+        'CRPSSkill', predictions, targets, self._ensemble_dim, fair=True,
+        skipna_ensemble=self._skipna_ensemble)
+
+
+class CRPSSpread(base.PerVariableStatistic):
+  """Sample estimate of the spread term of CRPS, E|X - X'|."""
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM, use_sort: bool = False,
+               fair: bool = True, which: str = 'predictions',
+               skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._use_sort = use_sort
+    self._which = which
+    self._fair = fair
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def unique_name(self) -> str:
+    fair_str = 'fair' if self._fair else 'unfair'
+    return f'CRPSSpread_{self._ensemble_dim}_{fair_str}_{self._which}'
+
+  def _compute_per_variable(self, predictions, targets):
+    if self._which != 'predictions':
+      if self._which == 'targets':
+        raise NotImplementedError(
+            "CRPSSpread(which='targets') is outside the B200 hot path")
+      raise ValueError(f'Unhandled {self._which=}')
+    if self._use_sort and self._skipna_ensemble:
+      raise ValueError('skipna_ensemble is not supported with use_sort=True.')
+    if (not self._skipna_ensemble and
+        predictions.sizes.get(self._ensemble_dim, 2) < 2):
+      raise ValueError('Cannot estimate CRPS spread with n_ensemble < 2.')
+    return LazyEnsembleStatistic(
+        'CRPSSpread', predictions, targets, self._ensemble_dim,
+        fair=self._fair, skipna_ensemble=self._skipna_ensemble)
+
+
+class CRPSEnsemble(base.PerVariableMetric):
+  """CRPS = E|X - Y| - 0.5 E|X - X'| for an ensemble prediction.
+
+  ``fair=True`` gives the unbiased (eFAIR) estimate of Zamo & Naveau (2018);
+  ``skipna_ensemble=True`` treats NaN members as missing, with a per-point
+  ensemble size.
+  """
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM, use_sort: bool = False,
+               fair: bool = True, skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._use_sort = use_sort
+    self._fair = fair
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def statistics(self) -> Mapping[str, base.Statistic]:
+    return {
+        'CRPSSkill': CRPSSkill(ensemble_dim=self._ensemble_dim,
+                               skipna_ensemble=self._skipna_ensemble),
+        'CRPSSpread': CRPSSpread(ensemble_dim=self._ensemble_dim,
+                                 use_sort=self._use_sort, fair=self._fair,
+                                 skipna_ensemble=self._skipna_ensemble),
+    }
+
+  def _values_from_mean_statistics_per_variable(self, statistic_values):
+    return statistic_values['CRPSSkill'] - 0.5 * statistic_values['CRPSSpread']
