@@ -601,6 +601,16 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
       break
     if d not in pred.dims:
       break
+    # the ensemble must walk the slab with one uniform point stride
+    pstr = dict(zip(pred.dims, _Operand(pred, 4).strides.values()))
+    expect = pstr[trial[-1]]
+    uniform = True
+    for dd in reversed(trial):
+      if sizes[dd] != 1 and pstr[dd] != expect:
+        uniform = False
+      expect *= sizes[dd]
+    if not uniform:
+      break
     inner = trial
   if not inner:
     raise FastPathUnavailable('no contiguous reduced trailing dims')
