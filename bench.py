@@ -239,6 +239,127 @@ def cpu_baseline_sample():
   }
 
 
+def run_suite(ctx, dev, peak):
+  """Secondary workloads of BASELINE.json (single GPU, device resident):
+  config[1] RMSE+ACC on 1.4 deg pressure-level fields and config[2] CRPS with
+  a 50-member ensemble on 0.25 deg fields.  Reported next to the headline; each
+  entry carries its own roofline fraction (kernel time from CUDA events)."""
+  import torch
+  from weatherbenchx_b200 import aggregation, weighting
+  from weatherbenchx_b200 import xarray_lite as xl
+  from weatherbenchx_b200.metrics import deterministic, probabilistic
+  out = {}
+
+  def timed(fn, steps):
+    fn()
+    fn()
+    torch.cuda.synchronize()
+    ctx.profile(True)
+    ctx.kernel_time(reset=True)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    kms, kn = ctx.kernel_time(reset=True)
+    ctx.profile(False)
+    return e0.elapsed_time(e1) / steps, kms / steps, kn // steps
+
+  # ---- config[1]: RMSE + ACC, 6 vars x [40 init, 10 lead, 13 levels, 128, 256]
+  n_var, n_init, n_lead, n_lev, ny, nx = 6, 40, 10, 13, 128, 256
+  lat = np.linspace(-90, 90, ny)
+  coords = {
+      'init_time': np.datetime64('2020-01-01T00', 'ns') +
+                   np.arange(n_init) * np.timedelta64(12, 'h'),
+      'lead_time': (np.arange(n_lead) * np.timedelta64(6, 'h')
+                    ).astype('timedelta64[ns]'),
+      'level': np.arange(n_lev), 'latitude': lat,
+      'longitude': np.linspace(0, 360, nx, endpoint=False)}
+  dims = ('init_time', 'lead_time', 'level', 'latitude', 'longitude')
+  cdims = ('dayofyear', 'hour', 'level', 'latitude', 'longitude')
+  ccoords = {'dayofyear': np.arange(1, 367), 'hour': np.arange(0, 24, 6),
+             'level': coords['level'], 'latitude': lat,
+             'longitude': coords['longitude']}
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(2000)
+  preds, tgts, clim = {}, {}, {}
+  for v in range(n_var):
+    name = f'var{v}'
+    t = torch.empty((n_init, n_lead, n_lev, ny, nx), device=dev)
+    t.normal_(0.0, 1.0, generator=gen)
+    p = t + 0.3 * torch.empty_like(t).normal_(0.0, 1.0, generator=gen)
+    c = torch.empty((366, 4, n_lev, ny, nx), device=dev)
+    c.normal_(0.0, 0.5, generator=gen)
+    preds[name] = xl.DataArray(p, dims, coords=coords, name=name)
+    tgts[name] = xl.DataArray(t, dims, coords=coords, name=name)
+    clim[name] = xl.DataArray(c, cdims, coords=ccoords, name=name)
+  metrics = {'rmse': deterministic.RMSE(), 'acc': deterministic.ACC(clim)}
+  aggregator = aggregation.Aggregator(
+      reduce_dims=['init_time', 'latitude', 'longitude'],
+      weigh_by=[weighting.GridAreaWeighting()])
+  step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
+      metrics, aggregator, preds, tgts)
+  ms, kms, kn = timed(step, 5)
+  pts = n_var * n_init * n_lead * n_lev * ny * nx
+  out['rmse_acc_c2'] = {
+      'workload': 'RMSE+ACC fused (4 statistics, one pass), 6 vars x '
+                  '[40 init,10 lead,13 level,128,256] f32 + climatology '
+                  '[366,4,13,128,256], class API, device inputs',
+      'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+      'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+      'roofline': {'bound': 'hbm', 'achieved': pts * 12 / (kms * 1e-3) / 1e9,
+                   'peak': peak, 'unit': 'GB/s',
+                   'frac': pts * 12 / (kms * 1e-3) / 1e9 / peak,
+                   'algorithmic_bytes_per_point': 12}}
+  del preds, tgts, clim, metrics, step
+  torch.cuda.empty_cache()
+
+  # ---- config[2]: CRPS, M = 50, 5 vars x 20 init x 721 x 1440
+  n_var, n_init, m = 5, 20, 50
+  lat = np.linspace(-90, 90, NLAT)
+  ecoords = {'init_time': np.arange(n_init), 'number': np.arange(m),
+             'latitude': lat,
+             'longitude': np.linspace(0, 360, NLON, endpoint=False)}
+  preds, tgts = {}, {}
+  for v in range(n_var):
+    name = f'var{v}'
+    y = torch.empty((n_init, NLAT, NLON), device=dev)
+    y.normal_(0.0, 1.0, generator=gen)
+    x = torch.empty((n_init, m, NLAT, NLON), device=dev)
+    x.normal_(0.0, 1.0, generator=gen)
+    x += y[:, None]
+    preds[name] = xl.DataArray(
+        x, ('init_time', 'number', 'latitude', 'longitude'), coords=ecoords,
+        name=name)
+    tgts[name] = xl.DataArray(
+        y, ('init_time', 'latitude', 'longitude'),
+        coords={k: ecoords[k] for k in ('init_time', 'latitude', 'longitude')},
+        name=name)
+  metrics = {'crps': probabilistic.CRPSEnsemble()}
+  step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
+      metrics, aggregator, preds, tgts)
+  ms, kms, kn = timed(step, 3)
+  pts = n_var * n_init * NLAT * NLON
+  bpp = 4 * (m + 1)
+  flops = 2.0 * (m * (m - 1) / 2) * 2 + 2 * m   # sub+abs-add per pair, skill
+  out['crps_c3'] = {
+      'workload': 'CRPSEnsemble fair, pairwise O(M^2), M=50, 5 vars x 20 init '
+                  'x 721x1440 f32, ensemble layout [init, member, lat, lon], '
+                  'class API, device inputs',
+      'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+      'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+      'roofline': {'bound': 'hbm', 'achieved': pts * bpp / (kms * 1e-3) / 1e9,
+                   'peak': peak, 'unit': 'GB/s',
+                   'frac': pts * bpp / (kms * 1e-3) / 1e9 / peak,
+                   'algorithmic_bytes_per_point': bpp,
+                   'fp32_tflops': pts * flops / (kms * 1e-3) / 1e12,
+                   'note': 'at the FP32-issue / HBM ridge: ~2.5 kFLOP per '
+                           '204 B point (SURVEY.md 8d)'}}
+  return out
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -424,6 +545,10 @@ def run_b200(args):
   }
   if world == 1 and not args.no_cpu_baseline:
     line['cpu_baseline'] = cpu_baseline_sample()
+  if world == 1 and not args.no_suite:
+    del tgt, prd, host_p, host_t, preds, tgts, plan
+    torch.cuda.empty_cache()
+    line['suite'] = run_suite(ctx, dev, peak)
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
@@ -437,6 +562,8 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--e2e-steps', type=int, default=20)
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-suite', action='store_true',
+                  help='skip the secondary workloads (RMSE+ACC, CRPS)')
   args = ap.parse_args()
   if args.impl == 'reference':
     if args.steps == 1000:
