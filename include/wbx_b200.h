@@ -241,6 +241,26 @@ typedef struct {
 int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* desc,
                        float* skill, float* spread);
 
+/* ---- zonal energy spectrum (real FFT along longitude) ------------------ *
+ *
+ * north_star row "EnergySpectrum".  NOTE: /root/reference/weatherbenchX has no
+ * implementation, call site or test of it (parity unpinned); the definition is
+ * WeatherBench 2's ZonalEnergySpectrum: F = rfft(f, norm='forward'),
+ * S[0] = C |F_0|^2, S[k>0] = 2 C |F_k|^2, C = row_scale[y] (2 pi R cos(lat)).
+ * Job j is one contiguous float32 slab [ny, nx] at field[j] (device address);
+ * spectrum receives float32 [n_jobs, ny, nx/2 + 1] (device).  nx must be even
+ * with nx/2 = 2^a 3^b 5^c <= 2048.  Synchronous on the context stream.
+ */
+typedef struct {
+  int64_t n_jobs;
+  int64_t ny, nx;
+  const uint64_t* field;     /* [n_jobs] device slab addresses (host table)  */
+  const double* row_scale;   /* [ny] host, or NULL for 1.0                   */
+  float* spectrum;           /* device output                                */
+} wbx_spectrum_desc;
+
+int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* desc);
+
 /* ---- generic strided statistic + weighted aggregation ------------------ *
  *
  * Same contract as the fused path (Aggregator.aggregate_stat_var,

@@ -114,6 +114,15 @@ class CrpsPointDesc(ctypes.Structure):
   ]
 
 
+class SpectrumDesc(ctypes.Structure):
+  """Mirror of wbx_spectrum_desc."""
+  _fields_ = [
+      ('n_jobs', c_int64), ('ny', c_int64), ('nx', c_int64),
+      ('field', POINTER(c_uint64)), ('row_scale', POINTER(c_double)),
+      ('spectrum', c_void_p),
+  ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/wbx_b200.h.
 SIGNATURES = {
     'wbx_abi_version': (c_int, []),
@@ -148,6 +157,7 @@ SIGNATURES = {
                                   c_int32, c_int32]),
     'wbx_crps_pointwise': (c_int, [c_void_p, POINTER(CrpsPointDesc), c_void_p,
                                    c_void_p]),
+    'wbx_zonal_spectrum': (c_int, [c_void_p, POINTER(SpectrumDesc)]),
     'wbx_reduce_generic': (c_int, [c_void_p, POINTER(GenericDesc), c_void_p,
                                    c_void_p, c_int32]),
 }
