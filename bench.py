@@ -357,6 +357,46 @@ def run_suite(ctx, dev, peak):
                    'fp32_tflops': pts * flops / (kms * 1e-3) / 1e12,
                    'note': 'at the FP32-issue / HBM ridge: ~2.5 kFLOP per '
                            '204 B point (SURVEY.md 8d)'}}
+  metrics = {'crps': probabilistic.CRPSEnsemble(use_sort=True)}
+  step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
+      metrics, aggregator, preds, tgts)
+  ms, kms, kn = timed(step, 3)
+  out['crps_c3_sort'] = {
+      'workload': 'CRPSEnsemble fair, use_sort=True (sort/PWM estimator in a '
+                  'register sorting network), same data as crps_c3',
+      'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+      'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+      'roofline': {'bound': 'hbm', 'achieved': pts * bpp / (kms * 1e-3) / 1e9,
+                   'peak': peak, 'unit': 'GB/s',
+                   'frac': pts * bpp / (kms * 1e-3) / 1e9 / peak,
+                   'algorithmic_bytes_per_point': bpp}}
+  del preds, tgts, metrics, step
+  torch.cuda.empty_cache()
+
+  # ---- config[3]: zonal energy spectrum, 13 levels x 6 vars x 721 x 1440
+  from weatherbenchx_b200.metrics import spectral
+  n_fields = 13 * 6
+  f = torch.empty((n_fields, NLAT, NLON), device=dev)
+  f.normal_(0.0, 1.0, generator=gen)
+  field = xl.DataArray(
+      f, ('field', 'latitude', 'longitude'),
+      coords={'latitude': lat,
+              'longitude': np.linspace(0, 360, NLON, endpoint=False)},
+      name='u')
+  step = lambda: spectral.zonal_energy_spectrum(field)  # noqa: E731
+  ms, kms, kn = timed(step, 10)
+  pts = n_fields * NLAT * NLON
+  bpp = 4.0 + 4.0 * (NLON // 2 + 1) / NLON
+  out['spectrum_c4'] = {
+      'workload': 'ZonalEnergySpectrum (rfft N=1440 per latitude row, '
+                  'per-row spectra written), 13 levels x 6 vars x 721x1440 '
+                  'f32; parity unpinned (numpy.fft oracle only)',
+      'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+      'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+      'roofline': {'bound': 'hbm', 'achieved': pts * bpp / (kms * 1e-3) / 1e9,
+                   'peak': peak, 'unit': 'GB/s',
+                   'frac': pts * bpp / (kms * 1e-3) / 1e9 / peak,
+                   'algorithmic_bytes_per_point': bpp}}
   return out
 
 

@@ -191,7 +191,11 @@ int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
  */
 enum {
   WBX_CRPS_FAIR = 256,            /* divide by M(M-1) instead of M^2          */
-  WBX_CRPS_SKIPNA_ENSEMBLE = 512  /* NaN members are missing members          */
+  WBX_CRPS_SKIPNA_ENSEMBLE = 512, /* NaN members are missing members          */
+  WBX_CRPS_USE_SORT = 1024        /* sort/PWM estimator (probabilistic.py:
+                                     214-240) in a register sorting network;
+                                     honoured for n_members <= 64, the pair
+                                     sum is used otherwise                    */
 };
 
 typedef struct wbx_crps_plan wbx_crps_plan;

@@ -134,10 +134,11 @@ def test_golden_crps_through_cabi(m, fair):
                              rtol=1e-12)
 
 
-@pytest.mark.parametrize('members', [2, 8, 13, 50])
+@pytest.mark.parametrize('use_sort', [False, True])
+@pytest.mark.parametrize('members', [2, 8, 13, 50, 64, 70])
 @pytest.mark.parametrize('layout', ['member_last', 'member_major'])
 @pytest.mark.parametrize('space', ['host', 'device'])
-def test_fused_crps_matches_oracle(members, layout, space):
+def test_fused_crps_matches_oracle(members, layout, space, use_sort):
   rng = np.random.default_rng(members)
   n_init, nlat, nlon = 3, 12, 20
   coords = {'init_time': np.arange(n_init),
@@ -159,7 +160,7 @@ def test_fused_crps_matches_oracle(members, layout, space):
                            ('init_time', 'latitude', 'longitude')}, name='t')
   if space == 'device':
     X, Y = engine.to_device(X), engine.to_device(Y)
-  metrics = {'crps': probabilistic.CRPSEnsemble()}
+  metrics = {'crps': probabilistic.CRPSEnsemble(use_sort=use_sort)}
   for rd in (['latitude', 'longitude'], ['init_time', 'latitude', 'longitude']):
     values = compute_all_metrics(metrics, {'t': X}, {'t': Y}, rd,
                                  weigh_by=[weighting.GridAreaWeighting()])
@@ -173,6 +174,43 @@ def test_fused_crps_matches_oracle(members, layout, space):
                                     weights=[(w, ('latitude',))])
     np.testing.assert_allclose(values['crps.t'].values,
                                s_ws / s_w - 0.5 * p_ws / p_w, rtol=RTOL)
+
+
+@pytest.mark.parametrize('members', [5, 12, 50])
+def test_sort_and_pair_kernels_agree_with_nans(members):
+  """C ABI level: the sorting-network estimator == the pair sum, including
+  skipna_ensemble (which the class surface only offers with use_sort=False,
+  probabilistic.py:215-216) and NaN propagation without it."""
+  import torch
+  rng = np.random.default_rng(members)
+  ny, nx = 16, 24
+  x = (rng.normal(280, 3, size=(members, ny, nx))).astype(np.float32)
+  x[rng.random(x.shape) < 0.1] = np.nan
+  y = rng.normal(280, 3, size=(ny, nx)).astype(np.float32)
+  xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+  ctx = _cabi.get_context()
+  out = {}
+  for skipna in (True, False):
+    for use_sort in (False, True):
+      flags = (_cabi.CRPS_FAIR | (_cabi.CRPS_SKIPNA_ENSEMBLE if skipna else 0) |
+               (_cabi.CRPS_USE_SORT if use_sort else 0) | _cabi.FLAG_SKIPNA)
+      plan = _cabi.CrpsPlan(
+          ctx, space=_cabi.SPACE_DEVICE, flags=flags, ny=ny, nx=nx,
+          n_members=members, member_stride=ny * nx, point_stride=1,
+          ens=np.array([xd.data_ptr()], np.uint64),
+          target=np.array([yd.data_ptr()], np.uint64),
+          cell=np.zeros(1, np.int32), n_cells=1)
+      out[skipna, use_sort] = plan.run_to_host()
+  for skipna in (True, False):
+    (ws_a, w_a), (ws_b, w_b) = out[skipna, False], out[skipna, True]
+    np.testing.assert_allclose(ws_b, ws_a, rtol=2e-6)
+    np.testing.assert_array_equal(w_b, w_a)
+  # oracle for the skipna_ensemble case (Aggregator skipna drops NaN points)
+  sk = oracle.crps_skill(np.moveaxis(x, 0, -1), y, -1, skipna_ensemble=True)
+  sp = oracle.crps_spread(np.moveaxis(x, 0, -1), -1, fair=True,
+                          skipna_ensemble=True)
+  np.testing.assert_allclose(out[True, True][0][0],
+                             [np.nansum(sk), np.nansum(sp)], rtol=RTOL)
 
 
 def test_pointwise_fields_match_oracle():
@@ -217,8 +255,9 @@ def big():
   return X, Y
 
 
-def _crps_sums(X, Y, reduce_dims, weights=True, **kw):
-  stats = [LazyEnsembleStatistic(k, X, Y, 'number', True, False)
+def _crps_sums(X, Y, reduce_dims, weights=True, use_sort=False, **kw):
+  stats = [LazyEnsembleStatistic(k, X, Y, 'number', True, False,
+                                 use_sort=use_sort)
            for k in ('CRPSSkill', 'CRPSSpread')]
   w = [weighting.GridAreaWeighting().weights(stats[0])] if weights else []
   return engine.aggregate_crps(stats, list(reduce_dims), w, **kw)
@@ -263,6 +302,22 @@ def test_big_scaling_and_chunk_combine(big):
   crps = (base['CRPSSkill'][0].values / base['CRPSSkill'][1].values - 0.5 *
           base['CRPSSpread'][0].values / base['CRPSSpread'][1].values)
   assert 0.2 < crps < 0.3   # sigma / sqrt(pi) * (sqrt(2) - 1) * ... ~ 0.2337
+
+
+def test_big_sort_estimator_equals_pair_sum(big):
+  X, Y = big
+  rd = ['init_time', 'latitude', 'longitude']
+  pair = _crps_sums(X, Y, rd)
+  srt = _crps_sums(X, Y, rd, use_sort=True)
+  for k in pair:
+    np.testing.assert_allclose(srt[k][0].values, pair[k][0].values, rtol=1e-6)
+    np.testing.assert_array_equal(srt[k][1].values, pair[k][1].values)
+  # a large offset must not hurt the sort estimator (moment taken about the min)
+  X2 = xl.DataArray(X.data + 1000.0, X.dims, coords=X.coords, name='t2m')
+  Y2 = xl.DataArray(Y.data + 1000.0, Y.dims, coords=Y.coords, name='t2m')
+  shifted = _crps_sums(X2, Y2, rd, use_sort=True)
+  np.testing.assert_allclose(shifted['CRPSSpread'][0].values,
+                             pair['CRPSSpread'][0].values, rtol=2e-4)
 
 
 def test_identical_members_have_zero_spread():

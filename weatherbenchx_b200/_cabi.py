@@ -86,7 +86,7 @@ class GenericDesc(ctypes.Structure):
   ]
 
 
-CRPS_FAIR, CRPS_SKIPNA_ENSEMBLE = 256, 512
+CRPS_FAIR, CRPS_SKIPNA_ENSEMBLE, CRPS_USE_SORT = 256, 512, 1024
 
 
 class CrpsDesc(ctypes.Structure):

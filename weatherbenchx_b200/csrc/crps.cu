@@ -220,6 +220,172 @@ __global__ void __launch_bounds__(kCrpsThreads)
   }
 }
 
+// ---------------------------------------------------------------------------
+// Sort / probability-weighted-moment estimator (probabilistic.py:214-240):
+//   sum_{i,j} |x_i - x_j| = 2 sum_k (2k - n - 1) x_(k)      (x_(k) sorted)
+// The n <= MAXM members of a point live in registers and are sorted by a fully
+// unrolled Batcher odd-even merge network (543 compare-exchanges at MAXM = 64
+// against 2450 FADDs of the pair sum at M = 50); padding lanes and, with
+// skipna_ensemble, NaN members hold +inf and sort to the end.  The moment sum
+// is taken about the minimum (the coefficients sum to zero), which removes the
+// cancellation the reference avoids by evaluating this branch in float64.
+// Members are read straight from global memory (coalesced across threads for
+// member-major ensembles, L1-served 4 (M) B runs for member-last ones).
+// ---------------------------------------------------------------------------
+// Batcher's odd-even merge sort as compile-time recursion, so that every
+// compare-exchange has constant register indices (a loop-nest formulation made
+// ptxas spill the array to local memory).
+template <int MAXM>
+__device__ __forceinline__ void cmp_exchange(float (&x)[MAXM], const int a,
+                                             const int b) {
+  const float lo = fminf(x[a], x[b]);
+  const float hi = fmaxf(x[a], x[b]);
+  x[a] = lo;
+  x[b] = hi;
+}
+
+// merges the two sorted halves of x[LO .. LO+N) taken with stride R
+template <int MAXM, int LO, int N, int R>
+struct OddEvenMerge {
+  static __device__ __forceinline__ void run(float (&x)[MAXM]) {
+    constexpr int kStep = R * 2;
+    if constexpr (kStep < N) {
+      OddEvenMerge<MAXM, LO, N, kStep>::run(x);
+      OddEvenMerge<MAXM, LO + R, N, kStep>::run(x);
+#pragma unroll
+      for (int i = LO + R; i + R < LO + N; i += kStep)
+        cmp_exchange<MAXM>(x, i, i + R);
+    } else {
+      cmp_exchange<MAXM>(x, LO, LO + R);
+    }
+  }
+};
+
+template <int MAXM, int LO, int N>
+struct OddEvenSort {
+  static __device__ __forceinline__ void run(float (&x)[MAXM]) {
+    if constexpr (N > 1) {
+      OddEvenSort<MAXM, LO, N / 2>::run(x);
+      OddEvenSort<MAXM, LO + N / 2, N / 2>::run(x);
+      OddEvenMerge<MAXM, LO, N, 1>::run(x);
+    }
+  }
+};
+
+template <int MAXM>
+__device__ __forceinline__ void sort_network(float (&x)[MAXM]) {
+  OddEvenSort<MAXM, 0, MAXM>::run(x);
+}
+
+template <int MAXM, bool ENS_SKIPNA, bool MASK>
+__global__ void __launch_bounds__(kCrpsThreads)
+    crps_sort_kernel(const CrpsParams P) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = P.n_members;
+  const long long t_begin =
+      (static_cast<long long>(blockIdx.x) * P.total_tiles) / gridDim.x;
+  const long long t_end =
+      (static_cast<long long>(blockIdx.x + 1) * P.total_tiles) / gridDim.x;
+  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0};
+  int cur_cell = -1;
+  long long job = t_begin / P.tiles_per_slab;
+  int k = static_cast<int>(t_begin - job * P.tiles_per_slab);
+  const float inf = __int_as_float(0x7f800000);
+  for (long long g = t_begin; g < t_end; ++g) {
+    const float* ea = reinterpret_cast<const float*>(__ldg(P.ens + job));
+    const float* ta = reinterpret_cast<const float*>(__ldg(P.target + job));
+    const int cell = __ldg(P.cell + job);
+    const double wo = P.w_outer ? __ldg(P.w_outer + job) : 1.0;
+    if (cell != cur_cell) {
+      if (cur_cell >= 0) {
+        double* rec = P.records +
+                      ((static_cast<size_t>(blockIdx.x) + (cur_cell - P.cell_base)) *
+                           kCrpsWarps + warp) * kCrpsAcc;
+#pragma unroll
+        for (int a = 0; a < kCrpsAcc; ++a) {
+          const double v = warp_sum(acc[a]);
+          if (lane == 0) rec[a] = v;
+          acc[a] = 0.0;
+        }
+      }
+      cur_cell = cell;
+    }
+    const int e0 = k * kCrpsThreads;
+    const int len = min(kCrpsThreads, P.slab - e0);
+    if (tid < len) {
+      const unsigned e = static_cast<unsigned>(e0 + tid);
+      const float* src = ea + static_cast<long long>(e) * P.point_stride;
+      float x[MAXM];
+#pragma unroll
+      for (int m = 0; m < MAXM; ++m)
+        x[m] = (m < M) ? ldg_stream_f1(src + static_cast<long long>(m) *
+                                                  P.member_stride)
+                       : inf;
+      const float y = ldg_stream_f1(ta + e);
+      // skill + NaN bookkeeping (order-independent sums)
+      float sk = 0.f;
+      int n_nan = 0;
+#pragma unroll
+      for (int m = 0; m < MAXM; ++m) {
+        if (m < M) {
+          const bool isn = !(x[m] == x[m]);
+          n_nan += isn ? 1 : 0;
+          const float d = fabsf(x[m] - y);
+          sk += (ENS_SKIPNA && isn) ? 0.f : d;
+          if (isn) x[m] = inf;
+        }
+      }
+      sort_network<MAXM>(x);
+      const int n = ENS_SKIPNA ? (M - n_nan) : M;
+      const float c = x[0];
+      float sp = 0.f;
+#pragma unroll
+      for (int q = 1; q < MAXM; ++q) {
+        if (q < n) sp += static_cast<float>(2 * q + 1 - n) * (x[q] - c);
+      }
+      const float fn = static_cast<float>(n);
+      float skill = __fdiv_rn(sk, fn);
+      float spread = __fdiv_rn(2.f * sp,
+                               fn * (fn - static_cast<float>(P.fair)));
+      if (!ENS_SKIPNA && n_nan > 0) {
+        skill = __int_as_float(0x7fc00000);
+        spread = skill;
+      }
+      const unsigned yy = e / static_cast<unsigned>(P.nx);
+      const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
+      double w = wo;
+      if (P.w_y) w *= __ldg(P.w_y + yy);
+      if (P.w_x) w *= __ldg(P.w_x + xx);
+      bool base = true;
+      if constexpr (MASK) {
+        const unsigned char* ma =
+            reinterpret_cast<const unsigned char*>(__ldg(P.mask + job));
+        base = __ldg(ma + e) != 0;
+      }
+      const bool ok_sk = base && (!P.skipna_stat || skill == skill);
+      const bool ok_sp = base && (!P.skipna_stat || spread == spread);
+      acc[0] += (ok_sk ? static_cast<double>(skill) : 0.0) * w;
+      acc[1] += (ok_sp ? static_cast<double>(spread) : 0.0) * w;
+      acc[2] += (ok_sk ? 1.0 : 0.0) * w;
+      acc[3] += (ok_sp ? 1.0 : 0.0) * w;
+    }
+    if (++k == P.tiles_per_slab) {
+      k = 0;
+      ++job;
+    }
+  }
+  if (cur_cell >= 0) {
+    double* rec = P.records +
+                  ((static_cast<size_t>(blockIdx.x) + (cur_cell - P.cell_base)) *
+                       kCrpsWarps + warp) * kCrpsAcc;
+#pragma unroll
+    for (int a = 0; a < kCrpsAcc; ++a) {
+      const double v = warp_sum(acc[a]);
+      if (lane == 0) rec[a] = v;
+    }
+  }
+}
+
 // out[c*2 + s] (statistics) and out_w[c*2 + s] (weights), one warp per output.
 struct CrpsFinalizeParams {
   const double* records;
@@ -310,6 +476,7 @@ struct wbx_crps_plan {
   std::vector<double> wo, wy, wx;
   int tiles_per_slab = 0;
   size_t smem_bytes = 0;
+  bool use_sort = false;  // register sorting network (n_members <= 64)
   wbx::DevBuf tables, weights;
   wbx::CrpsParams params{};
   const int32_t* d_cell_first_job = nullptr;
@@ -328,6 +495,31 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
   const bool ens_skipna = (plan->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
+  if (plan->use_sort) {
+#define WBX_SORT_LAUNCH(MAXM)                                                  \
+  do {                                                                         \
+    if (ens_skipna && plan->has_mask)                                          \
+      crps_sort_kernel<MAXM, true, true>                                       \
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+    else if (ens_skipna)                                                       \
+      crps_sort_kernel<MAXM, true, false>                                      \
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+    else if (plan->has_mask)                                                   \
+      crps_sort_kernel<MAXM, false, true>                                      \
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+    else                                                                       \
+      crps_sort_kernel<MAXM, false, false>                                     \
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+  } while (0)
+    if (plan->n_members <= 8) WBX_SORT_LAUNCH(8);
+    else if (plan->n_members <= 16) WBX_SORT_LAUNCH(16);
+    else if (plan->n_members <= 32) WBX_SORT_LAUNCH(32);
+    else WBX_SORT_LAUNCH(64);
+#undef WBX_SORT_LAUNCH
+    WBX_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return ctx->prof_end();
+  }
 #define WBX_CRPS_LAUNCH(A, B)                                                  \
   do {                                                                         \
     auto kern = crps_reduce_kernel<A, B>;                                      \
@@ -352,6 +544,7 @@ static int crps_grid(const wbx_ctx* ctx, const wbx_crps_plan* plan,
   const size_t per_sm = std::min<size_t>(ctx->smem_optin, 227 * 1024);
   long long ctas_per_sm = std::max<size_t>(1, per_sm / (plan->smem_bytes + 1024));
   ctas_per_sm = std::min<long long>(ctas_per_sm, 8);
+  if (plan->use_sort) ctas_per_sm = 8;  // register-limited, no shared memory
   const long long g = ctx->sm_count * ctas_per_sm;
   return static_cast<int>(std::max(1ll, std::min(g, total_tiles)));
 }
@@ -525,7 +718,9 @@ int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* d,
       static_cast<int>((slab + wbx::kCrpsThreads - 1) / wbx::kCrpsThreads);
   p->smem_bytes = static_cast<size_t>(d->n_members) * wbx::kCrpsPitch * 4 +
                   wbx::kCrpsThreads * 4 + wbx::kCrpsThreads + 64;
-  if (p->smem_bytes > std::min<size_t>(ctx->smem_optin, 227 * 1024)) {
+  p->use_sort = (d->flags & WBX_CRPS_USE_SORT) != 0 && d->n_members <= 64;
+  if (!p->use_sort &&
+      p->smem_bytes > std::min<size_t>(ctx->smem_optin, 227 * 1024)) {
     delete p;
     wbx::set_error("crps: %lld members need more shared memory than one SM has",
                    (long long)d->n_members);

@@ -10,12 +10,16 @@
 //
 // Algorithm: a length-N real row is read as H = N/2 complex numbers
 // z[n] = x[2n] + i x[2n+1] (the row bytes ARE that array), transformed by a
-// mixed-radix (2,3,4,5) Stockham autosort FFT ping-ponging between two
-// shared-memory buffers, and split into the N/2+1 real-FFT bins
+// mixed-radix Stockham autosort FFT ping-ponging between two shared-memory
+// buffers, and split into the N/2+1 real-FFT bins
 //   X[k] = (Z[k] + conj Z[H-k])/2 - i w_N^k (Z[k] - conj Z[H-k])/2 .
-// Twiddles come from shared-memory tables computed once per CTA in double
-// precision.  One row-group (64 threads) per row, several row-groups per CTA,
-// persistent grid; HBM traffic is 4 B/point in + 4 (N/2+1)/N B/point out.
+// Radices 2,3,4,5 and the in-register composites 8, 9, 10, 16 keep N = 1440
+// (H = 720 = 10 * 9 * 8) at three passes.  Shared-memory indices are padded by
+// one complex per 16 (e + e/16) so that the strided Stockham scatter of the
+// early passes is bank-conflict free; (j / Ns, j % Ns) use host-computed magic
+// multipliers.  Twiddles come from shared-memory tables computed once per CTA
+// in double precision.  One group of `gsize` threads per row, several rows per
+// CTA, persistent grid; HBM traffic is 4 B/point in + 4 (N/2+1)/N B/point out.
 #include <algorithm>
 #include <string.h>
 
@@ -23,9 +27,6 @@
 
 namespace wbx {
 
-constexpr int kSpecGroup = 64;     // threads per row
-constexpr int kSpecRows = 4;       // rows per CTA in flight
-constexpr int kSpecThreads = kSpecGroup * kSpecRows;
 constexpr int kSpecMaxPasses = 12;
 constexpr int kSpecMaxH = 2048;
 
@@ -35,9 +36,14 @@ struct SpecParams {
   float* out;               // [n_jobs, ny, H + 1]
   long long n_rows;         // n_jobs * ny
   int ny, nx, H;
+  int gsize;                // threads per row (multiple of 32)
+  int rows;                 // rows in flight per CTA
   int n_passes;
   int radix[kSpecMaxPasses];
+  unsigned magic[kSpecMaxPasses];  // ceil(2^32 / Ns) of every pass
 };
+
+__device__ __forceinline__ int pad16(int e) { return e + (e >> 4); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -48,10 +54,54 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
 __device__ __forceinline__ float2 csub(float2 a, float2 b) {
   return make_float2(a.x - b.x, a.y - b.y);
 }
-// multiply by -i  (forward transform rotations)
-__device__ __forceinline__ float2 mul_mi(float2 a) {
+__device__ __forceinline__ float2 mul_mi(float2 a) {  // a * (-i)
   return make_float2(a.y, -a.x);
 }
+
+// exp(-2 pi i m / N) for the in-register composite radices.
+__constant__ float2 kW8[8] = {
+    {1.f, 0.f}, {0.70710678118654752440f, -0.70710678118654752440f},
+    {0.f, -1.f}, {-0.70710678118654752440f, -0.70710678118654752440f},
+    {-1.f, 0.f}, {-0.70710678118654752440f, 0.70710678118654752440f},
+    {0.f, 1.f}, {0.70710678118654752440f, 0.70710678118654752440f}};
+__constant__ float2 kW9[9] = {
+    {1.f, 0.f},
+    {0.76604444311897803520f, -0.64278760968653932632f},
+    {0.17364817766693034885f, -0.98480775301220805937f},
+    {-0.5f, -0.86602540378443864676f},
+    {-0.93969262078590838405f, -0.34202014332566873304f},
+    {-0.93969262078590838405f, 0.34202014332566873304f},
+    {-0.5f, 0.86602540378443864676f},
+    {0.17364817766693034885f, 0.98480775301220805937f},
+    {0.76604444311897803520f, 0.64278760968653932632f}};
+__constant__ float2 kW10[10] = {
+    {1.f, 0.f},
+    {0.80901699437494742410f, -0.58778525229247312917f},
+    {0.30901699437494742410f, -0.95105651629515357212f},
+    {-0.30901699437494742410f, -0.95105651629515357212f},
+    {-0.80901699437494742410f, -0.58778525229247312917f},
+    {-1.f, 0.f},
+    {-0.80901699437494742410f, 0.58778525229247312917f},
+    {-0.30901699437494742410f, 0.95105651629515357212f},
+    {0.30901699437494742410f, 0.95105651629515357212f},
+    {0.80901699437494742410f, 0.58778525229247312917f}};
+__constant__ float2 kW16[16] = {
+    {1.f, 0.f},
+    {0.92387953251128675613f, -0.38268343236508977173f},
+    {0.70710678118654752440f, -0.70710678118654752440f},
+    {0.38268343236508977173f, -0.92387953251128675613f},
+    {0.f, -1.f},
+    {-0.38268343236508977173f, -0.92387953251128675613f},
+    {-0.70710678118654752440f, -0.70710678118654752440f},
+    {-0.92387953251128675613f, -0.38268343236508977173f},
+    {-1.f, 0.f},
+    {-0.92387953251128675613f, 0.38268343236508977173f},
+    {-0.70710678118654752440f, 0.70710678118654752440f},
+    {-0.38268343236508977173f, 0.92387953251128675613f},
+    {0.f, 1.f},
+    {0.38268343236508977173f, 0.92387953251128675613f},
+    {0.70710678118654752440f, 0.70710678118654752440f},
+    {0.92387953251128675613f, 0.38268343236508977173f}};
 
 template <int R>
 __device__ __forceinline__ void dft(float2* v);
@@ -75,7 +125,6 @@ __device__ __forceinline__ void dft<4>(float2* v) {
 
 template <>
 __device__ __forceinline__ void dft<3>(float2* v) {
-  // w = exp(-2 pi i / 3) = -1/2 - i sqrt(3)/2
   const float s = 0.86602540378443864676f;
   const float2 t1 = cadd(v[1], v[2]);
   const float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
@@ -100,7 +149,6 @@ __device__ __forceinline__ void dft<5>(float2* v) {
                                 x0.y + c1 * a1.y + c2 * a2.y);
   const float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x,
                                 x0.y + c2 * a1.y + c1 * a2.y);
-  // -i (s1 b1 + s2 b2) and -i (s2 b1 - s1 b2)
   const float2 q1 = make_float2(s1 * b1.y + s2 * b2.y, -(s1 * b1.x + s2 * b2.x));
   const float2 q2 = make_float2(s2 * b1.y - s1 * b2.y, -(s2 * b1.x - s1 * b2.x));
   v[1] = cadd(p1, q1);
@@ -109,54 +157,105 @@ __device__ __forceinline__ void dft<5>(float2* v) {
   v[3] = csub(p2, q2);
 }
 
-// One Stockham pass of radix R over a length-H sequence held in shared memory.
+// In-register Cooley-Tukey for N = R1 * R2 with compile-time indices:
+//   X[k1 + R1 k2] = sum_n2 W_N^{n2 k1} ( sum_n1 x[R2 n1 + n2] W_R1^{n1 k1} )
+//                   W_R2^{n2 k2}
+template <int R1, int R2>
+__device__ __forceinline__ void dft_composite(float2* v, const float2* wN) {
+  float2 y[R1 * R2];
+#pragma unroll
+  for (int n2 = 0; n2 < R2; ++n2) {
+    float2 t[R1];
+#pragma unroll
+    for (int n1 = 0; n1 < R1; ++n1) t[n1] = v[R2 * n1 + n2];
+    dft<R1>(t);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1)
+      y[k1 * R2 + n2] = (n2 * k1 == 0) ? t[k1] : cmul(t[k1], wN[n2 * k1]);
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < R1; ++k1) {
+    float2 t[R2];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) t[n2] = y[k1 * R2 + n2];
+    dft<R2>(t);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = t[k2];
+  }
+}
+
+template <>
+__device__ __forceinline__ void dft<8>(float2* v) {
+  dft_composite<4, 2>(v, kW8);
+}
+template <>
+__device__ __forceinline__ void dft<9>(float2* v) {
+  dft_composite<3, 3>(v, kW9);
+}
+template <>
+__device__ __forceinline__ void dft<10>(float2* v) {
+  dft_composite<5, 2>(v, kW10);
+}
+template <>
+__device__ __forceinline__ void dft<16>(float2* v) {
+  dft_composite<4, 4>(v, kW16);
+}
+
+// One Stockham pass of radix R over a length-H sequence held in shared memory
+// (padded indexing).  q = j / Ns via the magic multiplier.
 template <int R>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in,
                                               float2* __restrict__ out,
                                               const float2* __restrict__ tw,
                                               const int H, const int Ns,
-                                              const int lane) {
+                                              const unsigned magic,
+                                              const int lane, const int gsize) {
   const int B = H / R;
   const int tstep = H / (Ns * R);  // twiddle table stride for this pass
-  for (int j = lane; j < B; j += kSpecGroup) {
-    const int k = j % Ns;
+  for (int j = lane; j < B; j += gsize) {
+    const int q = (Ns == 1) ? j : static_cast<int>(__umulhi(j, magic));
+    const int k = j - q * Ns;
     float2 v[R];
 #pragma unroll
-    for (int t = 0; t < R; ++t) {
-      v[t] = in[j + t * B];
-      if (t > 0 && Ns > 1) v[t] = cmul(v[t], tw[t * k * tstep]);
+    for (int t = 0; t < R; ++t) v[t] = in[pad16(j + t * B)];
+    if (Ns > 1) {
+      const int kt = k * tstep;
+#pragma unroll
+      for (int t = 1; t < R; ++t) v[t] = cmul(v[t], tw[t * kt]);
     }
     dft<R>(v);
-    const int j0 = (j / Ns) * Ns * R + k;
+    const int j0 = q * Ns * R + k;
 #pragma unroll
-    for (int t = 0; t < R; ++t) out[j0 + t * Ns] = v[t];
+    for (int t = 0; t < R; ++t) out[pad16(j0 + t * Ns)] = v[t];
   }
 }
 
-__global__ void __launch_bounds__(kSpecThreads)
+__global__ void __launch_bounds__(512)
     zonal_spectrum_kernel(const SpecParams P) {
   extern __shared__ __align__(16) unsigned char spec_smem[];
   const int H = P.H;
-  float2* tw = reinterpret_cast<float2*>(spec_smem);        // exp(-2 pi i q / H)
-  float2* twn = tw + H;                                     // exp(-2 pi i k / N), k <= H
-  float2* bufs = twn + (H + 1);                             // [rows][2][H]
-  const int group = threadIdx.x / kSpecGroup;
-  const int lane = threadIdx.x % kSpecGroup;
-  for (int q = threadIdx.x; q < H; q += kSpecThreads) {
+  const int Hp = pad16(H) + 1;  // padded buffer length
+  float2* tw = reinterpret_cast<float2*>(spec_smem);  // exp(-2 pi i q / H)
+  float2* twn = tw + H;                               // exp(-2 pi i k / N), k <= H
+  float2* bufs = twn + (H + 1);                       // [rows][2][Hp]
+  const int group = threadIdx.x / P.gsize;
+  const int lane = threadIdx.x - group * P.gsize;
+  for (int q = threadIdx.x; q < H; q += blockDim.x) {
     double s, c;
     sincospi(2.0 * q / H, &s, &c);
     tw[q] = make_float2(static_cast<float>(c), static_cast<float>(-s));
   }
-  for (int q = threadIdx.x; q <= H; q += kSpecThreads) {
+  for (int q = threadIdx.x; q <= H; q += blockDim.x) {
     double s, c;
     sincospi(2.0 * q / P.nx, &s, &c);
     twn[q] = make_float2(static_cast<float>(c), static_cast<float>(-s));
   }
-  float2* a = bufs + static_cast<size_t>(group) * 2 * H;
-  float2* b = a + H;
-  const float inv_n2 = 1.0f / (static_cast<float>(P.nx) * static_cast<float>(P.nx));
-  const long long rows_per_iter = static_cast<long long>(gridDim.x) * kSpecRows;
-  for (long long base = static_cast<long long>(blockIdx.x) * kSpecRows;
+  float2* a = bufs + static_cast<size_t>(group) * 2 * Hp;
+  float2* b = a + Hp;
+  const float inv_n2 =
+      1.0f / (static_cast<float>(P.nx) * static_cast<float>(P.nx));
+  const long long rows_per_iter = static_cast<long long>(gridDim.x) * P.rows;
+  for (long long base = static_cast<long long>(blockIdx.x) * P.rows;
        base < P.n_rows; base += rows_per_iter) {
     const long long row = base + group;
     const bool active = row < P.n_rows;
@@ -166,10 +265,20 @@ __global__ void __launch_bounds__(kSpecThreads)
     if (active) {
       job = row / P.ny;
       y = static_cast<int>(row - job * P.ny);
-      const float2* src = reinterpret_cast<const float2*>(
+      const float4* src = reinterpret_cast<const float4*>(
           reinterpret_cast<const float*>(__ldg(P.field + job)) +
           static_cast<long long>(y) * P.nx);
-      for (int n = lane; n < H; n += kSpecGroup) a[n] = __ldg(src + n);
+      if ((P.nx & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int n = lane; n < (H >> 1); n += P.gsize) {
+          const float4 v4 = ldg_stream_f4(reinterpret_cast<const float*>(src + n));
+          a[pad16(2 * n)] = make_float2(v4.x, v4.y);
+          a[pad16(2 * n + 1)] = make_float2(v4.z, v4.w);
+        }
+      } else {
+        const float2* s2 = reinterpret_cast<const float2*>(src);
+        for (int n = lane; n < H; n += P.gsize) a[pad16(n)] = __ldg(s2 + n);
+      }
     }
     float2* in = a;
     float2* out = b;
@@ -177,11 +286,16 @@ __global__ void __launch_bounds__(kSpecThreads)
     for (int p = 0; p < P.n_passes; ++p) {
       __syncthreads();
       if (active) {
+        const unsigned mg = P.magic[p];
         switch (P.radix[p]) {
-          case 2: stockham_pass<2>(in, out, tw, H, Ns, lane); break;
-          case 3: stockham_pass<3>(in, out, tw, H, Ns, lane); break;
-          case 4: stockham_pass<4>(in, out, tw, H, Ns, lane); break;
-          default: stockham_pass<5>(in, out, tw, H, Ns, lane); break;
+          case 2: stockham_pass<2>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
+          case 3: stockham_pass<3>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
+          case 4: stockham_pass<4>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
+          case 5: stockham_pass<5>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
+          case 8: stockham_pass<8>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
+          case 9: stockham_pass<9>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
+          case 10: stockham_pass<10>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
+          default: stockham_pass<16>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
         }
       }
       Ns *= P.radix[p];
@@ -191,26 +305,53 @@ __global__ void __launch_bounds__(kSpecThreads)
     }
     __syncthreads();
     if (active) {
-      // `in` now holds Z[0..H-1]; produce |X[k]|^2 for k = 0..H.
+      // `in` now holds Z[0..H-1]; produce S[k] for k = 0..H.
       const float scale =
           (P.row_scale ? static_cast<float>(__ldg(P.row_scale + y)) : 1.0f) *
           inv_n2;
       float* dst = P.out + row * static_cast<long long>(H + 1);
-      for (int k = lane; k <= H; k += kSpecGroup) {
-        const float2 zk = in[k == H ? 0 : k];
-        const float2 zc = in[k == 0 || k == H ? 0 : H - k];
-        const float2 zr = make_float2(zc.x, -zc.y);           // conj Z[H-k]
+      for (int k = lane; k <= H; k += P.gsize) {
+        const float2 zk = in[pad16(k == H ? 0 : k)];
+        const float2 zc = in[pad16((k == 0 || k == H) ? 0 : H - k)];
+        const float2 zr = make_float2(zc.x, -zc.y);  // conj Z[H-k]
         const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y + zr.y));
         const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y - zr.y));
         const float2 wo = cmul(twn[k], o);
-        // X = e - i * wo
-        const float xr = e.x + wo.y;
+        const float xr = e.x + wo.y;  // X = e - i * wo
         const float xi = e.y - wo.x;
         const float factor = (k == 0) ? 1.0f : 2.0f;
         dst[k] = factor * scale * (xr * xr + xi * xi);
       }
     }
   }
+}
+
+// H = 2^a 3^b 5^c -> radix list preferring few, large passes.
+static bool factorise(int H, int* radix, int* n_passes) {
+  int a = 0, b = 0, c = 0, rem = H;
+  while (rem % 2 == 0) { rem /= 2; ++a; }
+  while (rem % 3 == 0) { rem /= 3; ++b; }
+  while (rem % 5 == 0) { rem /= 5; ++c; }
+  if (rem != 1) return false;
+  int n = 0;
+  auto push = [&](int r) {
+    if (n < kSpecMaxPasses) radix[n] = r;
+    ++n;
+  };
+  while (a >= 1 && c >= 1) { push(10); --a; --c; }
+  while (b >= 2) { push(9); b -= 2; }
+  while (a >= 4) { push(16); a -= 4; }
+  if (a == 3) { push(8); a = 0; }
+  if (a == 2) { push(4); a = 0; }
+  if (a == 1) { push(2); a = 0; }
+  while (b >= 1) { push(3); --b; }
+  while (c >= 1) { push(5); --c; }
+  if (n > kSpecMaxPasses) return false;
+  // largest radix first: the first pass (Ns = 1) needs no twiddles, so it is
+  // where a big radix saves the most multiplies.
+  std::sort(radix, radix + n, [](int x, int y) { return x > y; });
+  *n_passes = n;
+  return true;
 }
 
 }  // namespace wbx
@@ -231,31 +372,31 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
   }
   SpecParams P;
   memset(&P, 0, sizeof(P));
-  int rem = H, np = 0;
-  const int order[4] = {4, 5, 3, 2};
-  while (rem > 1) {
-    bool found = false;
-    for (int r : order) {
-      if (rem % r == 0) {
-        if (np == kSpecMaxPasses) break;
-        P.radix[np++] = r;
-        rem /= r;
-        found = true;
-        break;
-      }
-    }
-    if (!found) {
-      set_error("spectrum: nx/2 = %d has a prime factor other than 2, 3, 5", H);
-      return WBX_ERR_UNSUPPORTED;
-    }
+  if (!factorise(H, P.radix, &P.n_passes)) {
+    set_error("spectrum: nx/2 = %d has a prime factor other than 2, 3, 5", H);
+    return WBX_ERR_UNSUPPORTED;
   }
-  if (np == 0) P.radix[np++] = 1;  // H == 1 is excluded by nx >= 4 (H >= 2)
-  P.n_passes = np;
+  int max_b = 1, Ns = 1;
+  for (int p = 0; p < P.n_passes; ++p) {
+    max_b = std::max(max_b, H / P.radix[p]);
+    P.magic[p] = Ns == 1 ? 0u
+                         : static_cast<unsigned>(((1ull << 32) + Ns - 1) / Ns);
+    Ns *= P.radix[p];
+  }
   for (int64_t j = 0; j < d->n_jobs; ++j)
     WBX_REQUIRE(d->field[j] != 0 && d->field[j] % 8 == 0,
                 "spectrum: slab %lld is NULL or not 8-byte aligned",
                 (long long)j);
   WBX_CUDA(cudaSetDevice(ctx->device));
+  // threads per row: one butterfly per thread in the widest pass, 32..256
+  P.gsize = std::min(256, std::max(32, (max_b + 31) / 32 * 32));
+  P.rows = std::max(1, 384 / P.gsize);
+  const int threads = P.gsize * P.rows;
+  const int Hp = H + (H >> 4) + 1;
+  const size_t smem = (static_cast<size_t>(H) + (H + 1) +
+                       static_cast<size_t>(P.rows) * 2 * Hp) * sizeof(float2);
+  WBX_REQUIRE(smem <= std::min<size_t>(ctx->smem_optin, 227 * 1024),
+              "spectrum: shared memory budget exceeded");
   // upload the job table and the row scale
   const size_t tbytes = static_cast<size_t>(d->n_jobs) * 8;
   const size_t sbytes = d->row_scale ? static_cast<size_t>(d->ny) * 8 : 0;
@@ -274,22 +415,18 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
   P.ny = static_cast<int>(d->ny);
   P.nx = static_cast<int>(d->nx);
   P.H = H;
-  const size_t smem = (static_cast<size_t>(H) + (H + 1) +
-                       static_cast<size_t>(kSpecRows) * 2 * H) * sizeof(float2);
-  WBX_REQUIRE(smem <= std::min<size_t>(ctx->smem_optin, 227 * 1024),
-              "spectrum: shared memory budget exceeded");
   WBX_CUDA(cudaFuncSetAttribute(zonal_spectrum_kernel,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const size_t per_sm = std::min<size_t>(ctx->smem_optin, 227 * 1024);
   long long ctas_per_sm = std::max<size_t>(1, per_sm / (smem + 1024));
-  ctas_per_sm = std::min<long long>(ctas_per_sm, 2048 / kSpecThreads);
-  const long long want = (P.n_rows + kSpecRows - 1) / kSpecRows;
+  ctas_per_sm = std::min<long long>(ctas_per_sm, std::max(1, 2048 / threads));
+  const long long want = (P.n_rows + P.rows - 1) / P.rows;
   const int grid = static_cast<int>(
       std::max(1ll, std::min<long long>(want, ctx->sm_count * ctas_per_sm)));
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
-  zonal_spectrum_kernel<<<grid, kSpecThreads, smem, ctx->stream>>>(P);
+  zonal_spectrum_kernel<<<grid, threads, smem, ctx->stream>>>(P);
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   prc = ctx->prof_end();

@@ -558,12 +558,14 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
   if not reduce_set.issubset(dims):
     return None
   fair = None
+  use_sort = False
   for s in stats:
     if (s.group_key() != first.group_key() or s.ensemble_dim != ens_dim or
         s.skipna_ensemble != first.skipna_ensemble):
       raise ValueError('CRPS statistics in one launch must share operands')
     if s.kind == 'CRPSSpread':
       fair = s.fair
+      use_sort = s.use_sort
   pred = _normalise(first.predictions, 'field')
   tgt = first.targets
   order = tuple(d for d in dims if d in tgt.dims)
@@ -668,6 +670,8 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
     flags |= _cabi.CRPS_FAIR
   if first.skipna_ensemble:
     flags |= _cabi.CRPS_SKIPNA_ENSEMBLE
+  if use_sort:
+    flags |= _cabi.CRPS_USE_SORT
 
   def addresses(op):
     off = _job_offsets(job_dims, job_sizes, op.strides)

@@ -144,7 +144,7 @@ class LazyEnsembleStatistic(LazyStatistic):
 
   def __init__(self, kind: str, predictions: xl.DataArray,
                targets: xl.DataArray, ensemble_dim: str, fair: bool,
-               skipna_ensemble: bool):
+               skipna_ensemble: bool, use_sort: bool = False):
     if ensemble_dim not in predictions.dims:
       raise ValueError(
           f'Dimension {ensemble_dim} not found in {predictions.dims}')
@@ -163,6 +163,7 @@ class LazyEnsembleStatistic(LazyStatistic):
     self.ensemble_dim = ensemble_dim
     self.fair = bool(fair)
     self.skipna_ensemble = bool(skipna_ensemble)
+    self.use_sort = bool(use_sort)
     self.dims = dims
     self._sizes = {d: sizes[d] for d in dims}
     self.name = predictions.name

@@ -3,11 +3,12 @@
 Mirrors the hot-path subset of
 /root/reference/weatherbenchX/metrics/probabilistic.py: CRPSSkill :116-145,
 CRPSSpread :165-247, CRPSEnsemble :606-688 (same constructor arguments, same
-unique_name strings, same errors).  ``use_sort`` is accepted for API parity: as
-in the reference it does not enter the statistic's unique_name -- both
-estimators compute the same statistic -- and the kernel always evaluates the
-O(M^2) pair sum (which also serves skipna_ensemble, that the reference's sort
-branch rejects).
+unique_name strings, same errors).  As in the reference ``use_sort`` does not
+enter the statistic's unique_name -- both estimators compute the same statistic.
+``use_sort=False`` (default) runs the tiled O(M^2) member-pair kernel;
+``use_sort=True`` runs the sort / probability-weighted-moment estimator in a
+register sorting network (ensembles of up to 64 members; larger ones fall back
+to the pair sum).
 """
 
 from __future__ import annotations
@@ -68,7 +69,8 @@ class CRPSSpread(base.PerVariableStatistic):
       raise ValueError('Cannot estimate CRPS spread with n_ensemble < 2.')
     return LazyEnsembleStatistic(
         'CRPSSpread', predictions, targets, self._ensemble_dim,
-        fair=self._fair, skipna_ensemble=self._skipna_ensemble)
+        fair=self._fair, skipna_ensemble=self._skipna_ensemble,
+        use_sort=self._use_sort)
 
 
 class CRPSEnsemble(base.PerVariableMetric):
