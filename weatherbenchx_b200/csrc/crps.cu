@@ -277,11 +277,14 @@ __device__ __forceinline__ void sort_network(float (&x)[MAXM]) {
   OddEvenSort<MAXM, 0, MAXM>::run(x);
 }
 
-template <int MAXM, bool ENS_SKIPNA, bool MASK>
+// MFIX > 0 fixes the member count at compile time: the +inf padding lanes
+// become constants, ptxas folds every compare-exchange that touches them and
+// the network shrinks to the size of the real ensemble (M = 50: 64 -> 50 wires).
+template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MASK>
 __global__ void __launch_bounds__(kCrpsThreads)
     crps_sort_kernel(const CrpsParams P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int M = P.n_members;
+  const int M = MFIX > 0 ? MFIX : P.n_members;
   const long long t_begin =
       (static_cast<long long>(blockIdx.x) * P.total_tiles) / gridDim.x;
   const long long t_end =
@@ -496,25 +499,28 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
   if (plan->use_sort) {
-#define WBX_SORT_LAUNCH(MAXM)                                                  \
+#define WBX_SORT_LAUNCH(MAXM, MFIX)                                            \
   do {                                                                         \
     if (ens_skipna && plan->has_mask)                                          \
-      crps_sort_kernel<MAXM, true, true>                                       \
+      crps_sort_kernel<MAXM, MFIX, true, true>                                 \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
     else if (ens_skipna)                                                       \
-      crps_sort_kernel<MAXM, true, false>                                      \
+      crps_sort_kernel<MAXM, MFIX, true, false>                                \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
     else if (plan->has_mask)                                                   \
-      crps_sort_kernel<MAXM, false, true>                                      \
+      crps_sort_kernel<MAXM, MFIX, false, true>                                \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
     else                                                                       \
-      crps_sort_kernel<MAXM, false, false>                                     \
+      crps_sort_kernel<MAXM, MFIX, false, false>                               \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
   } while (0)
-    if (plan->n_members <= 8) WBX_SORT_LAUNCH(8);
-    else if (plan->n_members <= 16) WBX_SORT_LAUNCH(16);
-    else if (plan->n_members <= 32) WBX_SORT_LAUNCH(32);
-    else WBX_SORT_LAUNCH(64);
+    // the common operational ensemble sizes get a pruned network
+    if (plan->n_members == 50) WBX_SORT_LAUNCH(64, 50);
+    else if (plan->n_members == 51) WBX_SORT_LAUNCH(64, 51);
+    else if (plan->n_members <= 8) WBX_SORT_LAUNCH(8, 0);
+    else if (plan->n_members <= 16) WBX_SORT_LAUNCH(16, 0);
+    else if (plan->n_members <= 32) WBX_SORT_LAUNCH(32, 0);
+    else WBX_SORT_LAUNCH(64, 0);
 #undef WBX_SORT_LAUNCH
     WBX_CUDA(cudaGetLastError());
     ctx->launches++;
