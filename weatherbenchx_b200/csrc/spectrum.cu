@@ -37,13 +37,12 @@ struct SpecParams {
   long long n_rows;         // n_jobs * ny
   int ny, nx, H;
   int gsize;                // threads per row (multiple of 32)
+  int pad;                  // 1: one pad element per 16 (power-of-two sizes)
   int rows;                 // rows in flight per CTA
   int n_passes;
   int radix[kSpecMaxPasses];
   unsigned magic[kSpecMaxPasses];  // ceil(2^32 / Ns) of every pass
 };
-
-__device__ __forceinline__ int pad16(int e) { return e + (e >> 4); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -201,14 +200,14 @@ __device__ __forceinline__ void dft<16>(float2* v) {
   dft_composite<4, 4>(v, kW16);
 }
 
-// One Stockham pass of radix R over a length-H sequence held in shared memory
-// (padded indexing).  q = j / Ns via the magic multiplier.
+// One Stockham pass of radix R over a length-H sequence held in shared memory.
+// q = j / Ns via the magic multiplier; `pm` is the padding mask (see kernel).
 template <int R>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in,
                                               float2* __restrict__ out,
                                               const float2* __restrict__ tw,
                                               const int H, const int Ns,
-                                              const unsigned magic,
+                                              const unsigned magic, const int pm,
                                               const int lane, const int gsize) {
   const int B = H / R;
   const int tstep = H / (Ns * R);  // twiddle table stride for this pass
@@ -217,7 +216,10 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in,
     const int k = j - q * Ns;
     float2 v[R];
 #pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = in[pad16(j + t * B)];
+    for (int t = 0; t < R; ++t) {
+      const int e = j + t * B;
+      v[t] = in[e + ((e >> 4) & pm)];
+    }
     if (Ns > 1) {
       const int kt = k * tstep;
 #pragma unroll
@@ -226,7 +228,19 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in,
     dft<R>(v);
     const int j0 = q * Ns * R + k;
 #pragma unroll
-    for (int t = 0; t < R; ++t) out[pad16(j0 + t * Ns)] = v[t];
+    for (int t = 0; t < R; ++t) {
+      const int e = j0 + t * Ns;
+      out[e + ((e >> 4) & pm)] = v[t];
+    }
+  }
+}
+
+// Barrier over the `gsize` threads that share one row (rows are independent).
+__device__ __forceinline__ void group_sync(const int group, const int gsize) {
+  if (gsize == 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(gsize) : "memory");
   }
 }
 
@@ -234,10 +248,11 @@ __global__ void __launch_bounds__(512)
     zonal_spectrum_kernel(const SpecParams P) {
   extern __shared__ __align__(16) unsigned char spec_smem[];
   const int H = P.H;
-  const int Hp = pad16(H) + 1;  // padded buffer length
+  const int pm = P.pad ? -1 : 0;
+  const int Hp = (P.pad ? H + (H >> 4) : H) + 2;  // padded buffer length (even)
   float2* tw = reinterpret_cast<float2*>(spec_smem);  // exp(-2 pi i q / H)
   float2* twn = tw + H;                               // exp(-2 pi i k / N), k <= H
-  float2* bufs = twn + (H + 1);                       // [rows][2][Hp]
+  float2* bufs = twn + (H + 2);                       // [rows][2][Hp]
   const int group = threadIdx.x / P.gsize;
   const int lane = threadIdx.x - group * P.gsize;
   for (int q = threadIdx.x; q < H; q += blockDim.x) {
@@ -250,78 +265,98 @@ __global__ void __launch_bounds__(512)
     sincospi(2.0 * q / P.nx, &s, &c);
     twn[q] = make_float2(static_cast<float>(c), static_cast<float>(-s));
   }
+  __syncthreads();  // tables ready; from here on the row groups run decoupled
   float2* a = bufs + static_cast<size_t>(group) * 2 * Hp;
   float2* b = a + Hp;
   const float inv_n2 =
       1.0f / (static_cast<float>(P.nx) * static_cast<float>(P.nx));
   const long long rows_per_iter = static_cast<long long>(gridDim.x) * P.rows;
-  for (long long base = static_cast<long long>(blockIdx.x) * P.rows;
-       base < P.n_rows; base += rows_per_iter) {
-    const long long row = base + group;
-    const bool active = row < P.n_rows;
-    long long job = 0;
-    int y = 0;
-    __syncthreads();  // previous iteration's readers are done (and tables ready)
-    if (active) {
-      job = row / P.ny;
-      y = static_cast<int>(row - job * P.ny);
-      const float4* src = reinterpret_cast<const float4*>(
-          reinterpret_cast<const float*>(__ldg(P.field + job)) +
-          static_cast<long long>(y) * P.nx);
-      if ((P.nx & 3) == 0 &&
-          (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        for (int n = lane; n < (H >> 1); n += P.gsize) {
-          const float4 v4 = ldg_stream_f4(reinterpret_cast<const float*>(src + n));
-          a[pad16(2 * n)] = make_float2(v4.x, v4.y);
-          a[pad16(2 * n + 1)] = make_float2(v4.z, v4.w);
-        }
-      } else {
-        const float2* s2 = reinterpret_cast<const float2*>(src);
-        for (int n = lane; n < H; n += P.gsize) a[pad16(n)] = __ldg(s2 + n);
+  // Register prefetch of the NEXT row (issued before the FFT passes of the
+  // current one) hides the DRAM latency that a one-row-per-warp schedule would
+  // otherwise expose.
+  constexpr int kPre = 12;
+  const int nvec = H >> 1;
+  const bool vec_ok = !P.pad && (P.nx & 3) == 0 && nvec <= kPre * P.gsize;
+  float4 pre[kPre];
+  bool pre_valid = false;
+  auto row_pointer = [&](long long r, int* y_out) {
+    const long long job = r / P.ny;
+    const int y = static_cast<int>(r - job * P.ny);
+    *y_out = y;
+    return reinterpret_cast<const float*>(__ldg(P.field + job)) +
+           static_cast<long long>(y) * P.nx;
+  };
+  auto prefetch = [&](long long r) {
+    int yy;
+    const float* rp = row_pointer(r, &yy);
+    pre_valid = vec_ok && (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
+    if (pre_valid) {
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        const int n = lane + i * P.gsize;
+        if (n < nvec) pre[i] = ldg_stream_f4(rp + 4 * n);
       }
     }
+  };
+  long long row = static_cast<long long>(blockIdx.x) * P.rows + group;
+  if (row < P.n_rows) prefetch(row);
+  for (; row < P.n_rows; row += rows_per_iter) {
+    int y;
+    const float* rowp = row_pointer(row, &y);
+    group_sync(group, P.gsize);  // the previous row's readers are done
+    if (pre_valid) {
+      float4* a4 = reinterpret_cast<float4*>(a);
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        const int n = lane + i * P.gsize;
+        if (n < nvec) a4[n] = pre[i];
+      }
+    } else {
+      const float2* s2 = reinterpret_cast<const float2*>(rowp);
+      for (int n = lane; n < H; n += P.gsize)
+        a[n + ((n >> 4) & pm)] = __ldg(s2 + n);
+    }
+    if (row + rows_per_iter < P.n_rows) prefetch(row + rows_per_iter);
     float2* in = a;
     float2* out = b;
     int Ns = 1;
     for (int p = 0; p < P.n_passes; ++p) {
-      __syncthreads();
-      if (active) {
-        const unsigned mg = P.magic[p];
-        switch (P.radix[p]) {
-          case 2: stockham_pass<2>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
-          case 3: stockham_pass<3>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
-          case 4: stockham_pass<4>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
-          case 5: stockham_pass<5>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
-          case 8: stockham_pass<8>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
-          case 9: stockham_pass<9>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
-          case 10: stockham_pass<10>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
-          default: stockham_pass<16>(in, out, tw, H, Ns, mg, lane, P.gsize); break;
-        }
+      group_sync(group, P.gsize);
+      const unsigned mg = P.magic[p];
+      switch (P.radix[p]) {
+        case 2: stockham_pass<2>(in, out, tw, H, Ns, mg, pm, lane, P.gsize); break;
+        case 3: stockham_pass<3>(in, out, tw, H, Ns, mg, pm, lane, P.gsize); break;
+        case 4: stockham_pass<4>(in, out, tw, H, Ns, mg, pm, lane, P.gsize); break;
+        case 5: stockham_pass<5>(in, out, tw, H, Ns, mg, pm, lane, P.gsize); break;
+        case 8: stockham_pass<8>(in, out, tw, H, Ns, mg, pm, lane, P.gsize); break;
+        case 9: stockham_pass<9>(in, out, tw, H, Ns, mg, pm, lane, P.gsize); break;
+        case 10: stockham_pass<10>(in, out, tw, H, Ns, mg, pm, lane, P.gsize); break;
+        default: stockham_pass<16>(in, out, tw, H, Ns, mg, pm, lane, P.gsize); break;
       }
       Ns *= P.radix[p];
       float2* tmp = in;
       in = out;
       out = tmp;
     }
-    __syncthreads();
-    if (active) {
-      // `in` now holds Z[0..H-1]; produce S[k] for k = 0..H.
-      const float scale =
-          (P.row_scale ? static_cast<float>(__ldg(P.row_scale + y)) : 1.0f) *
-          inv_n2;
-      float* dst = P.out + row * static_cast<long long>(H + 1);
-      for (int k = lane; k <= H; k += P.gsize) {
-        const float2 zk = in[pad16(k == H ? 0 : k)];
-        const float2 zc = in[pad16((k == 0 || k == H) ? 0 : H - k)];
-        const float2 zr = make_float2(zc.x, -zc.y);  // conj Z[H-k]
-        const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y + zr.y));
-        const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y - zr.y));
-        const float2 wo = cmul(twn[k], o);
-        const float xr = e.x + wo.y;  // X = e - i * wo
-        const float xi = e.y - wo.x;
-        const float factor = (k == 0) ? 1.0f : 2.0f;
-        dst[k] = factor * scale * (xr * xr + xi * xi);
-      }
+    group_sync(group, P.gsize);
+    // `in` now holds Z[0..H-1]; produce S[k] for k = 0..H.
+    const float scale =
+        (P.row_scale ? static_cast<float>(__ldg(P.row_scale + y)) : 1.0f) *
+        inv_n2;
+    float* dst = P.out + row * static_cast<long long>(H + 1);
+    for (int k = lane; k <= H; k += P.gsize) {
+      const int ek = (k == H) ? 0 : k;
+      const int ec = (k == 0 || k == H) ? 0 : H - k;
+      const float2 zk = in[ek + ((ek >> 4) & pm)];
+      const float2 zc = in[ec + ((ec >> 4) & pm)];
+      const float2 zr = make_float2(zc.x, -zc.y);  // conj Z[H-k]
+      const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y + zr.y));
+      const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y - zr.y));
+      const float2 wo = cmul(twn[k], o);
+      const float xr = e.x + wo.y;  // X = e - i * wo
+      const float xi = e.y - wo.x;
+      const float factor = (k == 0) ? 1.0f : 2.0f;
+      dst[k] = factor * scale * (xr * xr + xi * xi);
     }
   }
 }
@@ -347,9 +382,16 @@ static bool factorise(int H, int* radix, int* n_passes) {
   while (b >= 1) { push(3); --b; }
   while (c >= 1) { push(5); --c; }
   if (n > kSpecMaxPasses) return false;
-  // largest radix first: the first pass (Ns = 1) needs no twiddles, so it is
-  // where a big radix saves the most multiplies.
+  // Order: an odd radix first if there is one -- the first pass scatters with
+  // stride R, which is bank-conflict free for odd R (and needs no twiddles);
+  // then descending.
   std::sort(radix, radix + n, [](int x, int y) { return x > y; });
+  for (int i = 0; i < n; ++i) {
+    if (radix[i] % 2 == 1) {
+      std::rotate(radix, radix + i, radix + i + 1);
+      break;
+    }
+  }
   *n_passes = n;
   return true;
 }
@@ -388,12 +430,14 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
                 "spectrum: slab %lld is NULL or not 8-byte aligned",
                 (long long)j);
   WBX_CUDA(cudaSetDevice(ctx->device));
-  // threads per row: one butterfly per thread in the widest pass, 32..256
-  P.gsize = std::min(256, std::max(32, (max_b + 31) / 32 * 32));
-  P.rows = std::max(1, 384 / P.gsize);
+  // One warp per row while a pass has at most 128 butterflies (ILP instead of
+  // block-wide barriers); wider groups only for the longest rows.
+  P.gsize = max_b <= 128 ? 32 : std::min(256, (max_b / 2 + 31) / 32 * 32);
+  P.rows = std::min(15, std::max(1, 256 / P.gsize));
+  P.pad = (P.radix[0] % 2 == 0) ? 1 : 0;
   const int threads = P.gsize * P.rows;
-  const int Hp = H + (H >> 4) + 1;
-  const size_t smem = (static_cast<size_t>(H) + (H + 1) +
+  const int Hp = (P.pad ? H + (H >> 4) : H) + 2;
+  const size_t smem = (static_cast<size_t>(H) + (H + 2) +
                        static_cast<size_t>(P.rows) * 2 * Hp) * sizeof(float2);
   WBX_REQUIRE(smem <= std::min<size_t>(ctx->smem_optin, 227 * 1024),
               "spectrum: shared memory budget exceeded");
