@@ -299,18 +299,40 @@ class Aggregator:
         subgroups.extend(by_clim.values())
       else:
         subgroups.append(plain)
+    planned = []  # (members, spec, distinct statistics) of deterministic groups
     for members in subgroups:
       lazies = [m[2] for m in members]
       distinct = {}
       for s in lazies:
         distinct.setdefault(s.kind, s)
+      stats = list(distinct.values())
+      first = stats[0]
       try:
-        fused = self._fused_group(list(distinct.values()))
-        for stat_name, var, s in members:
-          results[stat_name][var] = fused[s.kind]
+        if first.kind in engine.CRPS_SLOT or self.bin_by:
+          fused = self._fused_group(stats)
+          for stat_name, var, s in members:
+            results[stat_name][var] = fused[s.kind]
+          continue
+        if not set(self.reduce_dims).issubset(first.dims):
+          for stat_name, var, s in members:
+            results[stat_name][var] = None
+          continue
+        with_clim = sorted(stats, key=lambda s: s.climatology is None)[0]
+        weights = [w.weights(with_clim) for w in self.weigh_by or []]
+        spec = engine.build_fused_spec(
+            stats, self.reduce_dims, weights,
+            masked=self.masked and 'mask' in with_clim.coords,
+            skipna=self.skipna)
+        planned.append((members, spec, stats))
       except engine.FastPathUnavailable:
         for stat_name, var, s in members:
           results[stat_name][var] = self._aggregate_generic(s)
+    if planned:
+      # variables that share grid, flags and weights go out as ONE launch
+      outs = engine.run_fused_specs([(spec, stats) for _, spec, stats in planned])
+      for (members, _, _), out in zip(planned, outs):
+        for stat_name, var, s in members:
+          results[stat_name][var] = AggregationState(*out[s.kind])
     sws, sw = {}, {}
     for stat_name in statistics:
       ok = {v: s for v, s in results[stat_name].items() if s is not None}

@@ -54,8 +54,22 @@ static int launch_variant(wbx_ctx* ctx, const wbx_det_plan* plan,
     WBX_CUDA(cudaFuncSetAttribute(kern,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(plan->smem_bytes)));
-    kern<<<grid, kTmaThreads, plan->smem_bytes, st>>>(P, plan->stages,
-                                                      plan->stage_bytes);
+    // Programmatic dependent launch: the kernel may be scheduled while the
+    // previous kernel of the stream (the finalize of the last step) drains; it
+    // waits (griddepcontrol.wait) before it touches the shared record scratch.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTmaThreads);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->profile ? 0 : 1;
+    int stages = plan->stages, stage_bytes = plan->stage_bytes;
+    DetParams Pc = P;
+    WBX_CUDA(cudaLaunchKernelEx(&cfg, kern, Pc, stages, stage_bytes));
   } else if (plan->path == kPathLdg4) {
     det_reduce_ldg_kernel<CLIM, MASK, SKIPNA, PER_ELEM, 4>
         <<<grid, kLdgThreads, 0, st>>>(P);
@@ -141,7 +155,19 @@ static int launch_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
   const long long threads = static_cast<long long>(n_cells) * slots * 32;
   const int block = 128;
   const int grid = static_cast<int>((threads + block - 1) / block);
-  det_finalize_kernel<<<grid, block, 0, ctx->stream>>>(F);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->profile ? 0 : 1;
+    WBX_CUDA(cudaLaunchKernelEx(&cfg, det_finalize_kernel, F));
+  }
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   return WBX_OK;

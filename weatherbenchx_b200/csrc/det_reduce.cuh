@@ -252,6 +252,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     fence_mbar_init();
   }
+  // PDL: let the finalize kernel be scheduled behind us right away, and do not
+  // write records before the previous finalize (their last reader) is done.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
 
   const int off_t = P.tile * 4;
@@ -525,6 +529,9 @@ __global__ void __launch_bounds__(128) det_finalize_kernel(
     const FinalizeParams F) {
   // One warp per (cell, slot): lanes stride over the records of the cell in a
   // fixed assignment, then a butterfly sum -- parallel and still bit-stable.
+  // PDL: scheduled early, starts once the reduction kernel has completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int slots = WBX_NUM_DET_STATS + WBX_NUM_DET_WCLASSES;
@@ -559,9 +566,18 @@ __global__ void __launch_bounds__(128) det_finalize_kernel(
     const int n = (b_hi - b_lo + 1) * F.warps;
     const double* rec =
         F.records + (static_cast<size_t>(b_lo) + c) * F.warps * nacc + a;
-    double sum = 0.0;
-    for (int i = lane; i < n; i += 32) sum += rec[static_cast<size_t>(i) * nacc];
-    value = warp_sum(sum);
+    // four independent partial sums keep several loads in flight; the
+    // combination order is fixed, so the result stays bit-stable.
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = lane;
+    for (; i + 96 < n; i += 128) {
+      s0 += __ldcg(rec + static_cast<size_t>(i) * nacc);
+      s1 += __ldcg(rec + static_cast<size_t>(i + 32) * nacc);
+      s2 += __ldcg(rec + static_cast<size_t>(i + 64) * nacc);
+      s3 += __ldcg(rec + static_cast<size_t>(i + 96) * nacc);
+    }
+    for (; i < n; i += 32) s0 += __ldcg(rec + static_cast<size_t>(i) * nacc);
+    value = warp_sum((s0 + s1) + (s2 + s3));
   }
   if (lane == 0) {
     double* dst = slot < WBX_NUM_DET_STATS

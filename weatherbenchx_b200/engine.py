@@ -418,6 +418,103 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
       cache_key=cache_key)
 
 
+def _merge_key(spec: FusedSpec):
+  """Specs with the same key can share one launch (variables of equal grid)."""
+  return (spec.space, spec.flags, spec.ny, spec.nx, spec.clim is None,
+          spec.mask is None,
+          None if spec.w_y is None else spec.w_y.tobytes(),
+          None if spec.w_x is None else spec.w_x.tobytes())
+
+
+def _cached_plan(ctx, key, factory):
+  plan = _PLAN_CACHE.get(key)
+  if plan is not None and plan.ctx is not ctx:
+    plan = None
+  if plan is None:
+    plan = factory()
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+      _, old = _PLAN_CACHE.popitem(last=False)
+      old.close()
+  else:
+    _PLAN_CACHE.move_to_end(key)
+  return plan
+
+
+def run_fused_specs(items, device: int | None = None):
+  """Runs planned fused aggregations; compatible ones (same grid, flags and
+  weights -- typically the variables of one chunk) are merged into ONE launch
+  whose job table is the concatenation and whose cells are offset.
+
+  ``items``: list of (spec, stats).  Returns a list of
+  {kind: (sum_weighted_statistics, sum_weights)} in the same order.
+  """
+  ctx = _cabi.get_context(device)
+  buckets: dict = collections.OrderedDict()
+  for idx, (spec, _) in enumerate(items):
+    buckets.setdefault(_merge_key(spec), []).append(idx)
+  raw: dict = {}
+  for members in buckets.values():
+    specs = [items[i][0] for i in members]
+    first = specs[0]
+    if len(specs) == 1:
+      key = first.cache_key
+      factory = lambda f=first: _cabi.DetPlan(  # noqa: E731
+          ctx, space=f.space, flags=f.flags, ny=f.ny, nx=f.nx, pred=f.pred,
+          target=f.target, clim=f.clim, mask=f.mask, cell=f.cell,
+          n_cells=f.n_cells, w_outer=f.w_outer, w_y=f.w_y, w_x=f.w_x,
+          stat_mask=f.stat_mask)
+    else:
+      key = ('merged',) + tuple(sp.cache_key for sp in specs)
+      offsets = np.cumsum([0] + [sp.n_cells for sp in specs])
+
+      def factory(specs=specs, offsets=offsets, f=first):
+        cat = lambda name: (  # noqa: E731
+            None if getattr(f, name) is None else
+            np.concatenate([getattr(sp, name) for sp in specs]))
+        w_outer = None
+        if any(sp.w_outer is not None for sp in specs):
+          w_outer = np.concatenate([
+              sp.w_outer if sp.w_outer is not None else np.ones(len(sp.pred))
+              for sp in specs])
+        mask_bits = 0
+        for sp in specs:
+          mask_bits |= sp.stat_mask
+        return _cabi.DetPlan(
+            ctx, space=f.space, flags=f.flags, ny=f.ny, nx=f.nx,
+            pred=cat('pred'), target=cat('target'), clim=cat('clim'),
+            mask=cat('mask'),
+            cell=np.concatenate([sp.cell + off for sp, off in
+                                 zip(specs, offsets)]).astype(np.int32),
+            n_cells=int(offsets[-1]), w_outer=w_outer, w_y=f.w_y, w_x=f.w_x,
+            stat_mask=mask_bits)
+    plan = _cached_plan(ctx, key, factory)
+    # Keep the operands alive for as long as the plan may be run.
+    plan.keepalive = tuple(sp.keepalive for sp in specs)
+    if first.space == _cabi.SPACE_DEVICE:
+      ctx.use_torch_stream()
+    ws, w = plan.run_to_host()
+    lo = 0
+    for i, sp in zip(members, specs):
+      raw[i] = (ws[lo:lo + sp.n_cells], w[lo:lo + sp.n_cells])
+      lo += sp.n_cells
+  results = []
+  for idx, (spec, stats) in enumerate(items):
+    ws, w = raw[idx]
+    out = {}
+    for s in stats:
+      slot = _cabi.STAT_SLOT[s.kind]
+      sum_ws = (ws[:, slot] * spec.scalar).reshape(spec.kept_shape)
+      sum_w = (w[:, _cabi.STAT_WCLASS[slot]] * spec.scalar).reshape(
+          spec.kept_shape)
+      out[s.kind] = (
+          xl.DataArray(sum_ws, spec.kept, coords=spec.coords, name=s.name),
+          xl.DataArray(sum_w, spec.kept, coords=spec.coords, name=s.name),
+      )
+    results.append(out)
+  return results
+
+
 def aggregate_fused(stats: Sequence[LazyStatistic],
                     reduce_dims: Sequence[Hashable],
                     weights: Sequence[xl.DataArray] = (),
@@ -433,38 +530,7 @@ def aggregate_fused(stats: Sequence[LazyStatistic],
                           flags_extra, device)
   if spec is None:
     return None
-  ctx = _cabi.get_context(device)
-  plan = _PLAN_CACHE.get(spec.cache_key)
-  if plan is not None and plan.ctx is not ctx:
-    plan = None
-  if plan is None:
-    plan = _cabi.DetPlan(
-        ctx, space=spec.space, flags=spec.flags, ny=spec.ny, nx=spec.nx,
-        pred=spec.pred, target=spec.target, clim=spec.clim, mask=spec.mask,
-        cell=spec.cell, n_cells=spec.n_cells, w_outer=spec.w_outer,
-        w_y=spec.w_y, w_x=spec.w_x, stat_mask=spec.stat_mask)
-    _PLAN_CACHE[spec.cache_key] = plan
-    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-      _, old = _PLAN_CACHE.popitem(last=False)
-      old.close()
-  else:
-    _PLAN_CACHE.move_to_end(spec.cache_key)
-  # Keep the operands alive for as long as the plan may be run.
-  plan.keepalive = spec.keepalive
-  if spec.space == _cabi.SPACE_DEVICE:
-    ctx.use_torch_stream()
-  ws, w = plan.run_to_host()
-  out = {}
-  for s in stats:
-    slot = _cabi.STAT_SLOT[s.kind]
-    sum_ws = (ws[:, slot] * spec.scalar).reshape(spec.kept_shape)
-    sum_w = (w[:, _cabi.STAT_WCLASS[slot]] * spec.scalar).reshape(
-        spec.kept_shape)
-    out[s.kind] = (
-        xl.DataArray(sum_ws, spec.kept, coords=spec.coords, name=s.name),
-        xl.DataArray(sum_w, spec.kept, coords=spec.coords, name=s.name),
-    )
-  return out
+  return run_fused_specs([(spec, stats)], device)[0]
 
 
 # ---------------------------------------------------------------------------
