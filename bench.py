@@ -477,8 +477,6 @@ def run_b200(args):
     time.sleep(0.3)
   barrier()
   launches0 = ctx.kernel_launches()
-  ctx.profile(True)
-  ctx.kernel_time(reset=True)
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   win0 = time.time()
   ev0.record()
@@ -488,9 +486,18 @@ def run_b200(args):
   barrier()
   win1 = time.time()
   elapsed_ms = ev0.elapsed_time(ev1)
+  launches = ctx.kernel_launches() - launches0
+  # Per-kernel time for the roofline: a second pass over the same steps with
+  # every reduction kernel bracketed by CUDA events on its own stream (the
+  # bracketing adds gaps, so it is kept out of the timed region above).
+  prof_steps = min(args.steps, 200)
+  ctx.profile(True)
+  ctx.kernel_time(reset=True)
+  for _ in range(prof_steps):
+    step()
+  barrier()
   kernel_ms, kernel_n = ctx.kernel_time(reset=True)
   ctx.profile(False)
-  launches = ctx.kernel_launches() - launches0
   if world > 1:
     tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

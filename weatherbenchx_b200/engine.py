@@ -146,9 +146,34 @@ def _label_positions(labels: np.ndarray, wanted: np.ndarray, dim: str):
   return found.astype(np.int64)
 
 
+_ALIGN_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
+
+
 def align_climatology(predictions: xl.DataArray,
                       climatology: xl.DataArray) -> AlignedClimatology:
-  """Index form of metrics/base.py:383-403 (valid_time -> dayofyear/hour)."""
+  """Index form of metrics/base.py:383-403 (valid_time -> dayofyear/hour).
+
+  The three ACC statistics of every variable ask for the same alignment; it is
+  memoised on the identity of the time coordinates and of the climatology.
+  """
+  tkeys = tuple(k for k in ('valid_time', 'init_time', 'lead_time')
+                if k in predictions.coords)
+  key = (tuple(id(predictions.coords[k].data) for k in tkeys),
+         id(climatology), id(climatology.data))
+  hit = _ALIGN_CACHE.get(key)
+  if hit is not None and hit[1] is climatology and all(
+      a is predictions.coords[k].data for a, k in zip(hit[2], tkeys)):
+    return hit[0]
+  out = _align_climatology(predictions, climatology)
+  _ALIGN_CACHE[key] = (out, climatology,
+                       tuple(predictions.coords[k].data for k in tkeys))
+  while len(_ALIGN_CACHE) > 64:
+    _ALIGN_CACHE.popitem(last=False)
+  return out
+
+
+def _align_climatology(predictions: xl.DataArray,
+                       climatology: xl.DataArray) -> AlignedClimatology:
   coords = predictions.coords
   if 'valid_time' in coords:
     vt = coords['valid_time']

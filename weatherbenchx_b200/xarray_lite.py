@@ -516,7 +516,7 @@ def _check_index_coords(a: DataArray, b: DataArray):
             '(xarray_lite only supports exact alignment)')
       if d in a.coords and d in b.coords:
         ia, ib = a.coords[d].to_numpy(), b.coords[d].to_numpy()
-        if not np.array_equal(ia, ib):
+        if ia is not ib and not np.array_equal(ia, ib):
           raise ValueError(
               f'index coordinate {d!r} differs between operands; xarray_lite '
               'only supports exact alignment')
