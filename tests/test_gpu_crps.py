@@ -213,6 +213,45 @@ def test_sort_and_pair_kernels_agree_with_nans(members):
                              [np.nansum(sk), np.nansum(sp)], rtol=RTOL)
 
 
+@pytest.mark.parametrize('masked', [False, True])
+def test_tma_staged_pair_kernel_equals_plain_one(masked):
+  """The TMA double-buffered pair kernel and the cooperative-load one run the
+  same per-point arithmetic over the same partition: bit-identical sums."""
+  import torch
+  rng = np.random.default_rng(11)
+  members, n_init, ny, nx = 50, 3, 48, 64          # slab % 16 == 0
+  x = rng.normal(size=(n_init, members, ny, nx)).astype(np.float32)
+  y = rng.normal(size=(n_init, ny, nx)).astype(np.float32)
+  m = (rng.random((n_init, ny, nx)) > 0.2)
+  xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+  md = torch.from_numpy(m).cuda()
+  w = oracle.grid_area_weights(np.linspace(-90, 90, ny))
+  out = []
+  for extra in (0, _cabi.FLAG_FORCE_LDG):
+    plan = _cabi.CrpsPlan(
+        _cabi.get_context(), space=_cabi.SPACE_DEVICE,
+        flags=_cabi.CRPS_FAIR | extra | (_cabi.FLAG_MASKED if masked else 0),
+        ny=ny, nx=nx, n_members=members, member_stride=ny * nx, point_stride=1,
+        ens=np.array([xd.data_ptr() + i * members * ny * nx * 4
+                      for i in range(n_init)], np.uint64),
+        target=np.array([yd.data_ptr() + i * ny * nx * 4
+                         for i in range(n_init)], np.uint64),
+        mask=(np.array([md.data_ptr() + i * ny * nx for i in range(n_init)],
+                       np.uint64) if masked else None),
+        cell=np.zeros(n_init, np.int32), n_cells=1, w_y=w)
+    out.append(plan.run_to_host())
+  assert out[0][0].tobytes() == out[1][0].tobytes()
+  assert out[0][1].tobytes() == out[1][1].tobytes()
+  skill = oracle.crps_skill(x, y, 1)
+  spread = oracle.crps_spread(x, 1, fair=True)
+  wm = w[None, :, None] * (m if masked else 1.0)
+  np.testing.assert_allclose(out[0][0][0], [(skill * wm).sum(),
+                                            (spread * wm).sum()], rtol=RTOL)
+  np.testing.assert_allclose(out[0][1][0], [wm.sum() if masked else
+                                            w.sum() * nx * n_init] * 2,
+                             rtol=1e-12)
+
+
 def test_pointwise_fields_match_oracle():
   rng = np.random.default_rng(0)
   x = rng.normal(size=(2, 5, 7, 6)).astype(np.float32)

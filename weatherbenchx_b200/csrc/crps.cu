@@ -221,6 +221,163 @@ __global__ void __launch_bounds__(kCrpsThreads)
 }
 
 // ---------------------------------------------------------------------------
+// TMA-staged variant of the pair kernel for member-major ensembles
+// (point_stride == 1, 16-byte aligned rows): a producer warp streams the tile
+// of the NEXT 128 points -- one 512-byte cp.async.bulk per member row, plus the
+// target row -- into the other half of a two-stage shared-memory ring while the
+// four compute warps walk the pair triangle of the current tile.  No LDG/STS or
+// address arithmetic in the compute warps, no block-wide barrier per tile.
+// ---------------------------------------------------------------------------
+constexpr int kCrpsTmaThreads = kCrpsThreads + 32;
+constexpr int kCrpsStages = 2;
+
+struct CrpsStageMeta {
+  int cell;
+  int len;
+  int e0;
+  int pad;
+  double wo;
+};
+
+template <bool ENS_SKIPNA, bool MASK>
+__global__ void __launch_bounds__(kCrpsTmaThreads)
+    crps_reduce_tma_kernel(const CrpsParams P) {
+  extern __shared__ __align__(128) unsigned char crps_smem[];
+  const int M = P.n_members;
+  // stage layout: xs [M][128] f32 | ys [128] f32 | ms [128] u8
+  const size_t stage_bytes =
+      (static_cast<size_t>(M) * kCrpsThreads + kCrpsThreads) * 4 + kCrpsThreads;
+  const size_t stage_stride = (stage_bytes + 127) / 128 * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(crps_smem + kCrpsStages * stage_stride);
+  uint64_t* empty = full + kCrpsStages;
+  CrpsStageMeta* meta = reinterpret_cast<CrpsStageMeta*>(empty + kCrpsStages);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long t_begin =
+      (static_cast<long long>(blockIdx.x) * P.total_tiles) / gridDim.x;
+  const long long t_end =
+      (static_cast<long long>(blockIdx.x + 1) * P.total_tiles) / gridDim.x;
+  if (tid == 0) {
+    for (int s = 0; s < kCrpsStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kCrpsWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kCrpsWarps) {
+    if (lane == 0) {
+      const uint64_t policy = l2_evict_first_policy();
+      long long job = t_begin / P.tiles_per_slab;
+      int k = static_cast<int>(t_begin - job * P.tiles_per_slab);
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long g = t_begin; g < t_end; ++g) {
+        const float* ea = reinterpret_cast<const float*>(__ldg(P.ens + job));
+        const float* ta = reinterpret_cast<const float*>(__ldg(P.target + job));
+        const int e0 = k * kCrpsThreads;
+        const int len = min(kCrpsThreads, P.slab - e0);
+        mbar_wait(&empty[s], ph ^ 1u);
+        CrpsStageMeta mt;
+        mt.cell = __ldg(P.cell + job);
+        mt.len = len;
+        mt.e0 = e0;
+        mt.pad = 0;
+        mt.wo = P.w_outer ? __ldg(P.w_outer + job) : 1.0;
+        meta[s] = mt;
+        unsigned char* st = crps_smem + s * stage_stride;
+        float* xs = reinterpret_cast<float*>(st);
+        const uint32_t row_bytes = static_cast<uint32_t>(len) * 4u;
+        mbar_expect_tx(&full[s], row_bytes * static_cast<uint32_t>(M + 1) +
+                                     (MASK ? static_cast<uint32_t>(len) : 0u));
+        for (int m = 0; m < M; ++m)
+          bulk_g2s(xs + m * kCrpsThreads,
+                   ea + static_cast<long long>(m) * P.member_stride + e0,
+                   row_bytes, &full[s], policy);
+        bulk_g2s(xs + M * kCrpsThreads, ta + e0, row_bytes, &full[s], policy);
+        if constexpr (MASK) {
+          const unsigned char* ma =
+              reinterpret_cast<const unsigned char*>(__ldg(P.mask + job));
+          bulk_g2s(st + (static_cast<size_t>(M) + 1) * kCrpsThreads * 4, ma + e0,
+                   static_cast<uint32_t>(len), &full[s], policy);
+        }
+        if (++k == P.tiles_per_slab) {
+          k = 0;
+          ++job;
+        }
+        if (++s == kCrpsStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0};
+  int cur_cell = -1;
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long g = t_begin; g < t_end; ++g) {
+    mbar_wait(&full[s], ph);
+    const CrpsStageMeta mt = meta[s];
+    if (mt.cell != cur_cell) {
+      if (cur_cell >= 0) {
+        double* rec = P.records +
+                      ((static_cast<size_t>(blockIdx.x) + (cur_cell - P.cell_base)) *
+                           kCrpsWarps + warp) * kCrpsAcc;
+#pragma unroll
+        for (int a = 0; a < kCrpsAcc; ++a) {
+          const double v = warp_sum(acc[a]);
+          if (lane == 0) rec[a] = v;
+          acc[a] = 0.0;
+        }
+      }
+      cur_cell = mt.cell;
+    }
+    const unsigned char* st = crps_smem + s * stage_stride;
+    const float* xs = reinterpret_cast<const float*>(st);
+    if (tid < mt.len) {
+      float skill, spread;
+      crps_point<ENS_SKIPNA>(xs + tid, kCrpsThreads, M,
+                             xs[M * kCrpsThreads + tid], P.fair, &skill,
+                             &spread);
+      const unsigned e = static_cast<unsigned>(mt.e0 + tid);
+      const unsigned yy = e / static_cast<unsigned>(P.nx);
+      const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
+      double w = mt.wo;
+      if (P.w_y) w *= __ldg(P.w_y + yy);
+      if (P.w_x) w *= __ldg(P.w_x + xx);
+      bool base = true;
+      if constexpr (MASK)
+        base = st[(static_cast<size_t>(M) + 1) * kCrpsThreads * 4 + tid] != 0;
+      const bool ok_sk = base && (!P.skipna_stat || skill == skill);
+      const bool ok_sp = base && (!P.skipna_stat || spread == spread);
+      acc[0] += (ok_sk ? static_cast<double>(skill) : 0.0) * w;
+      acc[1] += (ok_sp ? static_cast<double>(spread) : 0.0) * w;
+      acc[2] += (ok_sk ? 1.0 : 0.0) * w;
+      acc[3] += (ok_sp ? 1.0 : 0.0) * w;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == kCrpsStages) {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
+  if (cur_cell >= 0) {
+    double* rec = P.records +
+                  ((static_cast<size_t>(blockIdx.x) + (cur_cell - P.cell_base)) *
+                       kCrpsWarps + warp) * kCrpsAcc;
+#pragma unroll
+    for (int a = 0; a < kCrpsAcc; ++a) {
+      const double v = warp_sum(acc[a]);
+      if (lane == 0) rec[a] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Sort / probability-weighted-moment estimator (probabilistic.py:214-240):
 //   sum_{i,j} |x_i - x_j| = 2 sum_k (2k - n - 1) x_(k)      (x_(k) sorted)
 // The n <= MAXM members of a point live in registers and are sorted by a fully
@@ -480,6 +637,8 @@ struct wbx_crps_plan {
   int tiles_per_slab = 0;
   size_t smem_bytes = 0;
   bool use_sort = false;  // register sorting network (n_members <= 64)
+  bool tma_ok = false;    // TMA-staged pair kernel allowed (alignment, size)
+  size_t smem_plain = 0;  // shared memory of the non-TMA pair kernel
   wbx::DevBuf tables, weights;
   wbx::CrpsParams params{};
   const int32_t* d_cell_first_job = nullptr;
@@ -528,12 +687,24 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
   }
 #define WBX_CRPS_LAUNCH(A, B)                                                  \
   do {                                                                         \
-    auto kern = crps_reduce_kernel<A, B>;                                      \
-    WBX_CUDA(cudaFuncSetAttribute(kern,                                        \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  static_cast<int>(plan->smem_bytes)));        \
-    kern<<<grid, kCrpsThreads, plan->smem_bytes, ctx->stream>>>(P);            \
+    if (use_tma) {                                                             \
+      auto kern = crps_reduce_tma_kernel<A, B>;                                \
+      WBX_CUDA(cudaFuncSetAttribute(                                           \
+          kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
+          static_cast<int>(plan->smem_bytes)));                                \
+      kern<<<grid, kCrpsTmaThreads, plan->smem_bytes, ctx->stream>>>(P);       \
+    } else {                                                                   \
+      auto kern = crps_reduce_kernel<A, B>;                                    \
+      WBX_CUDA(cudaFuncSetAttribute(                                           \
+          kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
+          static_cast<int>(plan->smem_bytes)));                                \
+      kern<<<grid, kCrpsThreads, plan->smem_bytes, ctx->stream>>>(P);          \
+    }                                                                          \
   } while (0)
+  // host-space chunks are staged member-major and aligned, so they take the
+  // TMA path whenever the plan allows it.
+  const bool use_tma = plan->tma_ok && P.point_stride == 1 &&
+                       (P.member_stride % 4) == 0;
   if (ens_skipna && plan->has_mask) WBX_CRPS_LAUNCH(true, true);
   else if (ens_skipna) WBX_CRPS_LAUNCH(true, false);
   else if (plan->has_mask) WBX_CRPS_LAUNCH(false, true);
@@ -724,7 +895,28 @@ int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* d,
       static_cast<int>((slab + wbx::kCrpsThreads - 1) / wbx::kCrpsThreads);
   p->smem_bytes = static_cast<size_t>(d->n_members) * wbx::kCrpsPitch * 4 +
                   wbx::kCrpsThreads * 4 + wbx::kCrpsThreads + 64;
+  p->smem_plain = p->smem_bytes;
   p->use_sort = (d->flags & WBX_CRPS_USE_SORT) != 0 && d->n_members <= 64;
+  {
+    // TMA variant: member-major rows, everything 16-byte aligned.
+    const size_t stage =
+        ((static_cast<size_t>(d->n_members) * wbx::kCrpsThreads +
+          wbx::kCrpsThreads) * 4 + wbx::kCrpsThreads + 127) / 128 * 128;
+    const size_t need = wbx::kCrpsStages * stage + 256;
+    bool ok = !(d->flags & WBX_FLAG_FORCE_LDG) && (slab % 4) == 0 &&
+              (!p->has_mask || (slab % 16) == 0) &&
+              need <= std::min<size_t>(ctx->smem_optin, 227 * 1024);
+    if (d->space == WBX_SPACE_DEVICE) {
+      ok = ok && d->point_stride == 1 && (d->member_stride % 4) == 0;
+      for (int64_t j = 0; j < d->n_jobs && ok; ++j)
+        ok = (d->ens[j] % 16) == 0 && (d->target[j] % 16) == 0 &&
+             (!p->has_mask || (d->mask[j] % 16) == 0);
+    } else {
+      ok = ok && d->point_stride == 1;  // host chunks are re-staged member-major
+    }
+    p->tma_ok = ok && !p->use_sort;
+    if (p->tma_ok) p->smem_bytes = need;
+  }
   if (!p->use_sort &&
       p->smem_bytes > std::min<size_t>(ctx->smem_optin, 227 * 1024)) {
     delete p;
