@@ -146,7 +146,19 @@ typedef struct {
   const double* w_x;       /* [nx] or NULL                                   */
   int32_t stat_mask;       /* bit s => accumulate WBX_STAT_* slot s; 0 = all.
                               Unselected slots of sum_ws are left as 0.       */
-  int32_t reserved;
+  int32_t n_classes;       /* 0, or the number of bin classes (see class_map) */
+  const uint8_t* class_map;/* [ny*nx] host, or NULL.  Bin masks over the slab
+                              dims (binning.py Regions / LandSea ..., consumed
+                              at aggregation.py:320-335) folded into classes:
+                              points with the same set of bins share a class.
+                              Results then hold one row per (cell, class):
+                              sum_ws[(c*n_classes + k)*6 + s], sum_w[(..)*4+..];
+                              the caller maps classes to bins with its 0/1
+                              membership matrix.  Needs nx % 4 == 0, slab % 16
+                              == 0, no w_x, no SKIPNA, aligned operands and
+                              n_classes * (#selected stats [+1 if MASKED]) <=
+                              448, else WBX_ERR_UNSUPPORTED (use
+                              wbx_reduce_generic).                            */
 } wbx_det_desc;
 
 /* Upload the job tables once; the plan can then be run many times (the field

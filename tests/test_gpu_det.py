@@ -538,3 +538,146 @@ def test_errors_are_exceptions_not_aborts():
                   pred=np.array([16, 16], np.uint64),
                   target=np.array([16, 16], np.uint64),
                   cell=np.array([1, 0], np.int32), n_cells=2)
+
+
+# ---------------------------------------------------------------------------
+# binned aggregation through the fused class-map kernel
+# ---------------------------------------------------------------------------
+
+REGIONS = {
+    'global': ((-90, 90), (0, 360)), 'tropics': ((-20, 20), (0, 360)),
+    'nh-extratropics': ((20, 90), (0, 360)),
+    'sh-extratropics': ((-90, -20), (0, 360)),
+    'europe': ((35, 75), (-12.5, 42.5)), 'n-america': ((25, 60), (240, 285)),
+    'east-asia': ((25, 60), (102.5, 150)), 'ausnz': ((-45, -12.5), (120, 175)),
+}
+
+
+def _bin_case(seed, shape=(3, 2, 24, 48), nan=False):
+  rng = np.random.default_rng(seed)
+  dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+  coords = {
+      'init_time': (np.datetime64('2020-03-01T00', 'ns') +
+                    np.arange(shape[0]) * np.timedelta64(12, 'h')),
+      'lead_time': (np.arange(shape[1]) * np.timedelta64(6, 'h')
+                    ).astype('timedelta64[ns]'),
+      'latitude': np.linspace(-90, 90, shape[2]),
+      'longitude': np.linspace(0, 360, shape[3], endpoint=False)}
+  p = rng.normal(280, 10, shape).astype(np.float32)
+  t = (p + rng.normal(0, 2, shape)).astype(np.float32)
+  if nan:
+    t[1, 0, 5, 7] = np.nan
+  c = rng.normal(280, 5, (366, 4) + shape[2:]).astype(np.float32)
+  P = xl.DataArray(p, dims, coords=coords, name='z')
+  T = xl.DataArray(t, dims, coords=coords, name='z')
+  C = xl.DataArray(c, ('dayofyear', 'hour', 'latitude', 'longitude'),
+                   coords={'dayofyear': np.arange(1, 367),
+                           'hour': np.arange(0, 24, 6),
+                           'latitude': coords['latitude'],
+                           'longitude': coords['longitude']}, name='z')
+  land = xl.DataArray(rng.random(shape[2:]) > 0.65, ('latitude', 'longitude'),
+                      coords={'latitude': coords['latitude'],
+                              'longitude': coords['longitude']})
+  return P, T, C, land
+
+
+@pytest.mark.parametrize('space', ['host', 'device'])
+@pytest.mark.parametrize('masked', [False, True])
+def test_fused_bins_match_oracle(space, masked, monkeypatch):
+  P, T, C, land = _bin_case(3)
+  mask_np = np.random.default_rng(9).random(P.shape) > 0.2
+  if masked:
+    T = T.assign_coords(mask=xl.DataArray(mask_np, P.dims))
+  bin_by = [binning.Regions(REGIONS, land_sea_mask=land),
+            binning.LandSea(xl.DataArray(land.values.astype(float), land.dims,
+                                         coords=land.coords),
+                            bin_dim_name='ls')]
+  if space == 'device':
+    P, T, C = engine.to_device(P), engine.to_device(T), engine.to_device(C)
+    if masked:
+      T = T.assign_coords(mask=engine.to_device(xl.DataArray(mask_np, P.dims)))
+  # the fused class-map kernel must serve this request, not the generic one
+  from weatherbenchx_b200 import generic
+  monkeypatch.setattr(generic, 'aggregate', lambda *a, **k: (_ for _ in ()).throw(
+      AssertionError('generic path used')))
+  rd = ['init_time', 'latitude', 'longitude']
+  state = _aggregate(ALL_METRICS(C), {'z': P}, {'z': T}, reduce_dims=rd,
+                     weigh_by=[weighting.GridAreaWeighting()], bin_by=bin_by,
+                     masked=masked)
+  Ph, Th = P.to_host(), T.to_host()
+  m1 = bin_by[0].create_bin_mask(Ph).values
+  m2 = bin_by[1].create_bin_mask(Ph).values
+  w = oracle.grid_area_weights(Ph.coords['latitude'].values)
+  expected = _oracle_states_bins(Ph, Th, C.to_host(), rd, w, m1, m2, mask_np,
+                                 masked)
+  for name, (sws, sw, dims) in expected.items():
+    got_ws = state.sum_weighted_statistics[name]['z']
+    got_w = state.sum_weights[name]['z']
+    assert set(got_ws.dims) == set(dims) == {'lead_time', 'region', 'ls'}
+    np.testing.assert_allclose(got_ws.transpose(*dims).values, sws, rtol=RTOL,
+                               atol=1e-6 * np.abs(sws).max())
+    np.testing.assert_allclose(got_w.transpose(*dims).values, sw, rtol=1e-10)
+  assert (state.sum_weights['SquaredError']['z'].coords['region'].values.tolist()
+          == list(REGIONS) + [f'{r}_land' for r in REGIONS])
+
+
+def _oracle_states_bins(P, T, C, rd, w, m1, m2, mask_np, masked):
+  aligned, adims = oracle.align_climatology(
+      C.values, C.dims, {k: C.coords[k].values for k in ('dayofyear', 'hour')},
+      P.coords['init_time'].values, P.coords['lead_time'].values)
+  aligned = np.transpose(aligned, [adims.index(d) for d in P.dims])
+  vals = {n: f(P.values, T.values)
+          for n, f in oracle.DETERMINISTIC_STATISTICS.items()}
+  vals.update({n: f(P.values, T.values, aligned)
+               for n, f in oracle.CLIMATOLOGY_STATISTICS.items()})
+  return {
+      n: oracle.aggregate(
+          v, P.dims, rd, weights=[(w, ('latitude',))],
+          bin_masks=[(m1, ('region', 'latitude', 'longitude')),
+                     (m2, ('ls', 'latitude', 'longitude'))],
+          mask=mask_np, mask_dims=P.dims, masked=masked)
+      for n, v in vals.items()}
+
+
+def test_fused_bins_nan_poisons_every_bin_like_the_reference():
+  """aggregation.py:272-277: a NaN outside a bin still makes that bin NaN."""
+  P, T, C, land = _bin_case(4, nan=True)
+  state = _aggregate({'mse': deterministic.MSE()}, {'z': P}, {'z': T},
+                     reduce_dims=['init_time', 'latitude', 'longitude'],
+                     bin_by=[binning.Regions(REGIONS)])
+  got = state.sum_weighted_statistics['SquaredError']['z']
+  lead = got.dims.index('lead_time')
+  vals = np.moveaxis(got.values, lead, 0)
+  assert np.isnan(vals[0]).all() and np.isfinite(vals[1]).all()
+
+
+def test_fused_bins_full_size_public_benchmark_regions(quarter_degree):
+  """0.25 degree, 2 x 17-ish regions with a land mask: fused == torch f64."""
+  import torch
+  P, T = quarter_degree
+  rng = np.random.default_rng(5)
+  lat, lon = P.coords['latitude'].values, P.coords['longitude'].values
+  # blocky synthetic continents (coherent along longitude like real coasts)
+  land_np = np.kron(rng.random((103, 96)) > 0.7, np.ones((7, 15), bool))
+  land = xl.DataArray(land_np, ('latitude', 'longitude'),
+                      coords={'latitude': lat, 'longitude': lon})
+  regions = binning.Regions(REGIONS, land_sea_mask=land)
+  agg = aggregation.Aggregator(
+      reduce_dims=['init_time', 'latitude', 'longitude'], bin_by=[regions],
+      weigh_by=[weighting.GridAreaWeighting()])
+  stats = {'SquaredError': {'t2m': engine.LazyStatistic('SquaredError', P, T)}}
+  state = agg.aggregate_statistics(stats)
+  got = state.sum_weighted_statistics['SquaredError']['t2m']
+  got_w = state.sum_weights['SquaredError']['t2m']
+  masks = torch.as_tensor(regions.create_bin_mask(P.isel(init_time=0)).values,
+                          device='cuda')
+  w = torch.as_tensor(oracle.grid_area_weights(lat), device='cuda')
+  d = (P.data - T.data)
+  se = (d * d).double().sum(0) * w[:, None]
+  ref = (masks.double() * se[None]).sum((1, 2)).cpu().numpy()
+  ref_w = (masks.double() * w[None, :, None]).sum((1, 2)).cpu().numpy() * 20
+  np.testing.assert_allclose(got.values, ref, rtol=RTOL)
+  np.testing.assert_allclose(got_w.values, ref_w, rtol=1e-10)
+  again = agg.aggregate_statistics(stats)
+  assert (again.sum_weighted_statistics['SquaredError']['t2m'].values.tobytes()
+          == got.values.tobytes())

@@ -404,7 +404,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header_sizes():
-  assert ctypes.sizeof(_cabi.DetDesc) == 8 + 4 * 8 + 8 * 8 + 8
+  assert ctypes.sizeof(_cabi.DetDesc) == 8 + 4 * 8 + 8 * 8 + 8 + 8
   assert ctypes.sizeof(_cabi.GenericDesc) == (
       16 + 8 * 8 + 8 * 4 + 4 * (8 + 8 * 8) + 6 * 8 + 6 * 4 + 6 * 8 * 8 + 0
       + (8 - (16 + 64 + 32 + 288 + 48 + 24) % 8) % 8)
@@ -416,3 +416,49 @@ def test_no_gpu_means_loud_failure():
     pytest.skip('GPU present')
   with pytest.raises(_cabi.WbxError, match='NO_DEVICE|no CUDA device'):
     _cabi.Context(0)
+
+
+# ---------------------------------------------------------------------------
+# bin masks folded into a class map (fused binned kernel, host side)
+# ---------------------------------------------------------------------------
+
+
+def test_fold_bin_masks_reproduces_every_mask():
+  rng = np.random.default_rng(0)
+  lat = np.linspace(-90, 90, 24)
+  lon = np.arange(40) * 9.0
+  stat = xl.DataArray(np.zeros((24, 40), np.float32), ('latitude', 'longitude'),
+                      coords={'latitude': lat, 'longitude': lon})
+  land = xl.DataArray(rng.random((24, 40)) > 0.6, ('latitude', 'longitude'),
+                      coords={'latitude': lat, 'longitude': lon})
+  regions = {'global': ((-90, 90), (0, 360)), 'tropics': ((-20, 20), (0, 360)),
+             'nh': ((20, 90), (0, 360)), 'europe': ((35, 75), (-12.5, 42.5))}
+  m1 = binning.Regions(regions, land_sea_mask=land).create_bin_mask(stat)
+  m2 = binning.LandSea(xl.DataArray(land.values.astype(float), land.dims,
+                                    coords=land.coords),
+                       include_global_mask=True).create_bin_mask(stat)
+  sizes = {'latitude': 24, 'longitude': 40}
+  cls = engine.fold_bin_masks([m1, m2], ['region', 'land_sea'],
+                              ['latitude', 'longitude'], sizes)
+  assert cls.class_map.dtype == np.uint8 and cls.class_map.shape == (960,)
+  assert cls.n_classes == cls.class_map.max() + 1 <= 256
+  for mask, member in ((m1, cls.membership[0]), (m2, cls.membership[1])):
+    rebuilt = member[:, cls.class_map].reshape(mask.shape)
+    np.testing.assert_array_equal(rebuilt.astype(bool), mask.values)
+  # class sums -> bin sums == direct masked sums
+  field = rng.normal(size=960)
+  per_class = np.bincount(cls.class_map, weights=field,
+                          minlength=cls.n_classes)[None, :]
+  got = cls.to_bins(per_class)[0]
+  exp = np.einsum('s,as,bs->ab', field, m1.values.reshape(8, -1).astype(float),
+                  m2.values.reshape(3, -1).astype(float))
+  np.testing.assert_allclose(got, exp, rtol=1e-12, atol=1e-12)
+  # a latitude-only mask broadcasts over longitude
+  band = xl.DataArray(np.stack([lat > 0, lat <= 0]), ('band', 'latitude'),
+                      coords={'band': np.array(['n', 's'])})
+  cls2 = engine.fold_bin_masks([band], ['band'], ['latitude', 'longitude'], sizes)
+  assert cls2.n_classes == 2
+  # masks that depend on an outer dim cannot be folded
+  outer = xl.DataArray(np.ones((2, 3, 24), bool), ('b', 'lead_time', 'latitude'))
+  with pytest.raises(engine.FastPathUnavailable):
+    engine.fold_bin_masks([outer], ['b'], ['latitude', 'longitude'], sizes)

@@ -61,7 +61,8 @@ class DetDesc(ctypes.Structure):
       ('cell', POINTER(c_int32)),
       ('w_outer', POINTER(c_double)), ('w_y', POINTER(c_double)),
       ('w_x', POINTER(c_double)),
-      ('stat_mask', c_int32), ('reserved', c_int32),
+      ('stat_mask', c_int32), ('n_classes', c_int32),
+      ('class_map', POINTER(ctypes.c_uint8)),
   ]
 
 
@@ -293,9 +294,11 @@ class DetPlan:
                mask: np.ndarray | None = None,
                w_outer: np.ndarray | None = None,
                w_y: np.ndarray | None = None, w_x: np.ndarray | None = None,
-               stat_mask: int = 0):
+               stat_mask: int = 0, class_map: np.ndarray | None = None,
+               n_classes: int = 0):
     self.ctx = ctx
     self.n_cells = int(n_cells)
+    self.n_classes = int(n_classes)
     keep = []
 
     def prep(a, dtype):
@@ -324,7 +327,8 @@ class DetPlan:
         clim=_as_ptr(clim, c_uint64), mask=_as_ptr(mask, c_uint64),
         cell=_as_ptr(cell, c_int32), w_outer=_as_ptr(w_outer, c_double),
         w_y=_as_ptr(w_y, c_double), w_x=_as_ptr(w_x, c_double),
-        stat_mask=stat_mask, reserved=0)
+        stat_mask=stat_mask, n_classes=n_classes,
+        class_map=_as_ptr(prep(class_map, np.uint8), ctypes.c_uint8))
     handle = c_void_p()
     check(ctx.lib.wbx_det_plan_create(ctx.handle, ctypes.byref(desc),
                                       ctypes.byref(handle)))
@@ -333,8 +337,9 @@ class DetPlan:
 
   def run_to_host(self):
     """Runs the plan; returns (sum_ws [n_cells, 6], sum_w [n_cells, 4])."""
-    ws = np.empty((self.n_cells, NUM_DET_STATS), np.float64)
-    w = np.empty((self.n_cells, NUM_DET_WCLASSES), np.float64)
+    rows = self.n_cells * max(self.n_classes, 1)
+    ws = np.empty((rows, NUM_DET_STATS), np.float64)
+    w = np.empty((rows, NUM_DET_WCLASSES), np.float64)
     check(self.ctx.lib.wbx_det_plan_run(
         self.ctx.handle, self.handle, ws.ctypes.data, w.ctypes.data,
         SPACE_HOST, 0))

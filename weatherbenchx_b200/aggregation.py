@@ -183,6 +183,19 @@ class Aggregator:
       factors.append(mask)
     return factors, names
 
+  def _bin_masks(self, stat: xl.DataArray):
+    """(masks, bin dim names), or None when a bin mask does not apply."""
+    names = [b.bin_dim_name for b in self.bin_by or []]
+    if len(set(names)) != len(names):
+      raise ValueError('Bin dimension names must be unique.')
+    masks = []
+    for binning in self.bin_by or []:
+      mask = xl.as_data_array(binning.create_bin_mask(stat))
+      if not (set(mask.dims) - {binning.bin_dim_name}).issubset(stat.dims):
+        return None
+      masks.append(mask)
+    return masks, names
+
   def aggregation_fn(self, stat: xl.DataArray) -> xl.DataArray | None:
     """Weighted, binned sum of ``stat`` over reduce_dims (no mask logic)."""
     from weatherbenchx_b200 import generic  # pylint: disable=g-import-not-at-top
@@ -201,14 +214,21 @@ class Aggregator:
     first = stats[0]
     if not set(self.reduce_dims).issubset(first.dims):
       return {s.kind: None for s in stats}
-    if self.bin_by:
-      raise engine.FastPathUnavailable('binning')
     weights = [w.weights(first) for w in self.weigh_by or []]
-    launch = (engine.aggregate_crps if first.kind in engine.CRPS_SLOT
-              else engine.aggregate_fused)
-    res = launch(
-        stats, self.reduce_dims, weights,
-        masked=self.masked and 'mask' in first.coords, skipna=self.skipna)
+    masked = self.masked and 'mask' in first.coords
+    if first.kind in engine.CRPS_SLOT:
+      if self.bin_by:
+        raise engine.FastPathUnavailable('binned CRPS')
+      res = engine.aggregate_crps(stats, self.reduce_dims, weights,
+                                  masked=masked, skipna=self.skipna)
+    else:
+      bins = self._bin_masks(first)
+      if bins is None:
+        return {s.kind: None for s in stats}
+      spec = engine.build_fused_spec(
+          stats, self.reduce_dims, weights, masked=masked, skipna=self.skipna,
+          bin_masks=bins[0], bin_dim_names=bins[1])
+      res = None if spec is None else engine.run_fused_specs([(spec, stats)])[0]
     if res is None:
       return {s.kind: None for s in stats}
     return {k: AggregationState(v[0], v[1]) for k, v in res.items()}
@@ -308,7 +328,7 @@ class Aggregator:
       stats = list(distinct.values())
       first = stats[0]
       try:
-        if first.kind in engine.CRPS_SLOT or self.bin_by:
+        if first.kind in engine.CRPS_SLOT:
           fused = self._fused_group(stats)
           for stat_name, var, s in members:
             results[stat_name][var] = fused[s.kind]
@@ -319,10 +339,15 @@ class Aggregator:
           continue
         with_clim = sorted(stats, key=lambda s: s.climatology is None)[0]
         weights = [w.weights(with_clim) for w in self.weigh_by or []]
+        bins = self._bin_masks(with_clim)
+        if bins is None:  # a bin mask needs dims the statistic does not have
+          for stat_name, var, s in members:
+            results[stat_name][var] = None
+          continue
         spec = engine.build_fused_spec(
             stats, self.reduce_dims, weights,
             masked=self.masked and 'mask' in with_clim.coords,
-            skipna=self.skipna)
+            skipna=self.skipna, bin_masks=bins[0], bin_dim_names=bins[1])
         planned.append((members, spec, stats))
       except engine.FastPathUnavailable:
         for stat_name, var, s in members:

@@ -39,6 +39,12 @@ struct wbx_det_plan {
   const double* d_wx = nullptr;
   std::vector<unsigned char> chunk_host[2];
   int stat_mask = 0x3f;
+  // binned plans (class map over the slab)
+  int n_classes = 0;
+  wbx::DevBuf class_map;
+  std::vector<double> class_w;   // sum of w_y over the points of every class
+  wbx::BinParams bins{};
+  int cells_mult() const { return n_classes > 0 ? n_classes : 1; }
 };
 
 namespace wbx {
@@ -82,8 +88,32 @@ static int launch_variant(wbx_ctx* ctx, const wbx_det_plan* plan,
   return ctx->prof_end();
 }
 
+static int launch_bins(wbx_ctx* ctx, const wbx_det_plan* plan,
+                       const DetParams& P, int grid) {
+  int prc = ctx->prof_begin();
+  if (prc != WBX_OK) return prc;
+#define WBX_BINS_LAUNCH(A, B)                                                  \
+  do {                                                                         \
+    auto kern = det_reduce_bins_kernel<A, B>;                                  \
+    WBX_CUDA(cudaFuncSetAttribute(kern,                                        \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  static_cast<int>(plan->smem_bytes)));        \
+    kern<<<grid, kTmaThreads, plan->smem_bytes, ctx->stream>>>(                \
+        P, plan->bins, plan->stages, plan->stage_bytes);                       \
+  } while (0)
+  if (plan->has_clim && plan->has_mask) WBX_BINS_LAUNCH(true, true);
+  else if (plan->has_clim) WBX_BINS_LAUNCH(true, false);
+  else if (plan->has_mask) WBX_BINS_LAUNCH(false, true);
+  else WBX_BINS_LAUNCH(false, false);
+#undef WBX_BINS_LAUNCH
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return ctx->prof_end();
+}
+
 static int launch_main(wbx_ctx* ctx, const wbx_det_plan* plan,
                        const DetParams& P, int grid) {
+  if (plan->n_classes > 0) return launch_bins(ctx, plan, P, grid);
   const int key = (plan->has_clim ? 8 : 0) | (plan->has_mask ? 4 : 0) |
                   (plan->skipna ? 2 : 0) | (plan->per_elem ? 1 : 0);
   switch (key) {
@@ -137,6 +167,42 @@ static int launch_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
                            const double* d_cell_w, int n_cells, int grid_main,
                            long long total_tiles, double* out_ws, double* out_w,
                            int accumulate) {
+  if (plan->n_classes > 0) {
+    BinFinalizeParams F;
+    F.records = records;
+    F.cell_first_job = d_first;
+    F.cell_class_w = plan->has_mask ? nullptr : d_cell_w;
+    F.out_ws = out_ws;
+    F.out_w = out_w;
+    F.total_tiles = total_tiles;
+    F.n_cells = n_cells;
+    F.grid_main = grid_main;
+    F.tiles_per_slab = plan->tiles_per_slab;
+    F.n_classes = plan->n_classes;
+    F.n_sel = plan->bins.n_sel;
+    F.accumulate = accumulate;
+    for (int i = 0; i < WBX_NUM_DET_STATS; ++i) F.sel[i] = plan->bins.sel[i];
+    if (!accumulate) {
+      // unselected statistic slots are not written by the kernel
+      WBX_CUDA(cudaMemsetAsync(
+          out_ws, 0,
+          sizeof(double) * n_cells * plan->n_classes * WBX_NUM_DET_STATS,
+          ctx->stream));
+      WBX_CUDA(cudaMemsetAsync(
+          out_w, 0,
+          sizeof(double) * n_cells * plan->n_classes * WBX_NUM_DET_WCLASSES,
+          ctx->stream));
+    }
+    const long long warps =
+        static_cast<long long>(n_cells) * plan->n_classes * (F.n_sel + 1);
+    const int block = 128;
+    const long long blocks = (warps * 32 + block - 1) / block;
+    det_bins_finalize_kernel<<<static_cast<unsigned>(blocks), block, 0,
+                               ctx->stream>>>(F);
+    WBX_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return WBX_OK;
+  }
   FinalizeParams F;
   F.records = records;
   F.cell_first_job = d_first;
@@ -197,6 +263,17 @@ static void cell_tables(const wbx_det_plan* plan, int64_t j0, int64_t j1,
     (*first)[c + 1] = static_cast<int32_t>(j - j0 + 1);
     const double wo = plan->has_wo ? plan->wo[j] : 1.0;
     (*cw)[c] += wo * plan->sum_wy * plan->sum_wx;
+  }
+  if (plan->n_classes > 0) {
+    // constant sum_weights per (cell, class): (sum of w_outer) * class weight
+    std::vector<double> wo_sum(n, 0.0);
+    for (int64_t j = j0; j < j1; ++j)
+      wo_sum[plan->cell[j] - c0] += plan->has_wo ? plan->wo[j] : 1.0;
+    cw->assign(static_cast<size_t>(n) * plan->n_classes, 0.0);
+    for (int c = 0; c < n; ++c)
+      for (int k = 0; k < plan->n_classes; ++k)
+        (*cw)[static_cast<size_t>(c) * plan->n_classes + k] =
+            wo_sum[c] * plan->class_w[k];
   }
   // cells are dense and non-decreasing, so first[c+1] was set for every c.
 }
@@ -289,6 +366,39 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
   p->n_stats = p->has_clim ? 6 : 3;
   p->n_weights = p->skipna ? (p->has_clim ? 4 : 1) : (p->has_mask ? 1 : 0);
   p->nacc = p->n_stats + p->n_weights;
+  if (d->n_classes > 0) {
+    WBX_REQUIRE(d->class_map != nullptr, "det: n_classes > 0 needs a class_map");
+    WBX_REQUIRE(d->n_classes <= 256, "det: at most 256 bin classes");
+    p->n_classes = d->n_classes;
+    int nsel = 0;
+    for (int k = 0; k < WBX_NUM_DET_STATS; ++k) p->bins.sel[k] = -1;
+    for (int k = 0; k < p->n_stats; ++k)
+      if (p->stat_mask & (1 << k)) p->bins.sel[nsel++] = k;
+    if (p->has_mask) p->bins.sel[nsel++] = -1;  // weight accumulator
+    p->bins.n_sel = nsel;
+    p->bins.n_classes = d->n_classes;
+    p->nacc = d->n_classes * nsel;
+    const int64_t slab_ = d->ny * d->nx;
+    const bool ok = !p->skipna && !p->has_wx && (d->nx % 4) == 0 &&
+                    (slab_ % 16) == 0 && p->nacc <= 448;
+    if (!ok) {
+      delete p;
+      wbx::set_error("det: this binned request needs the generic path "
+                     "(skipna, w_x, nx %% 4, slab %% 16 or too many "
+                     "classes x statistics)");
+      return WBX_ERR_UNSUPPORTED;
+    }
+    p->class_w.assign(d->n_classes, 0.0);
+    for (int64_t e = 0; e < slab_; ++e) {
+      const int c = d->class_map[e];
+      if (c >= d->n_classes) {
+        delete p;
+        wbx::set_error("det: class_map value %d >= n_classes", c);
+        return WBX_ERR_INVALID;
+      }
+      p->class_w[c] += p->has_wy ? d->w_y[e / d->nx] : 1.0;
+    }
+  }
 
   const int64_t slab = d->ny * d->nx;
   bool aligned = (slab % 4) == 0 && (!p->has_mask || (slab % 16) == 0);
@@ -306,10 +416,14 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
   p->tiles_per_slab = static_cast<int>((slab + tile - 1) / tile);
   p->stage_bytes = static_cast<int>(round_up(
       static_cast<size_t>(tile) * 4 * (p->has_clim ? 3 : 2) +
-          (p->has_mask ? tile : 0),
+          (p->has_mask ? tile : 0) + (p->n_classes > 0 ? tile : 0),
       128));
-  const size_t overhead = 2 * wbx::kMaxStages * sizeof(uint64_t) +
-                          wbx::kMaxStages * sizeof(wbx::StageMeta) + 128;
+  const size_t overhead =
+      2 * wbx::kMaxStages * sizeof(uint64_t) +
+      wbx::kMaxStages * sizeof(wbx::StageMeta) + 128 +
+      (p->n_classes > 0
+           ? static_cast<size_t>(wbx::kConsumerWarps) * p->nacc * sizeof(double)
+           : 0);
   const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024) - overhead;
   int stages = static_cast<int>(budget / p->stage_bytes);
   stages = std::min(stages, wbx::kMaxStages);
@@ -332,8 +446,22 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     p->path = wbx::kPathLdg1;
     p->per_elem = true;
   }
+  if (p->n_classes > 0 && p->path != wbx::kPathTma) {
+    delete p;
+    wbx::set_error("det: binned plans need 16-byte aligned operands (TMA path)");
+    return WBX_ERR_UNSUPPORTED;
+  }
 
   WBX_CUDA(cudaSetDevice(ctx->device));
+  if (p->n_classes > 0) {
+    const size_t bytes = static_cast<size_t>(d->ny * d->nx);
+    int rc = p->class_map.reserve(bytes);
+    if (rc != WBX_OK) { delete p; return rc; }
+    WBX_CUDA(cudaMemcpyAsync(p->class_map.ptr, d->class_map, bytes,
+                             cudaMemcpyHostToDevice, ctx->stream));
+    WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+    p->bins.class_map = p->class_map.as<unsigned char>();
+  }
   // weights (shared by both spaces)
   {
     const size_t bytes = (p->wy.size() + p->wx.size()) * sizeof(double);
@@ -431,6 +559,7 @@ int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan) {
   }
   plan->tables.release();
   plan->weights.release();
+  plan->class_map.release();
   delete plan;
   return WBX_OK;
 }
@@ -466,12 +595,14 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     int rc = ctx->staging[b].reserve(static_cast<size_t>(per_chunk) * job_bytes);
     if (rc != WBX_OK) return rc;
   }
-  WBX_CUDA(cudaMemsetAsync(d_ws, 0,
-                           plan->n_cells * WBX_NUM_DET_STATS * sizeof(double),
-                           ctx->stream));
-  WBX_CUDA(cudaMemsetAsync(d_w, 0,
-                           plan->n_cells * WBX_NUM_DET_WCLASSES * sizeof(double),
-                           ctx->stream));
+  WBX_CUDA(cudaMemsetAsync(
+      d_ws, 0,
+      plan->n_cells * plan->cells_mult() * WBX_NUM_DET_STATS * sizeof(double),
+      ctx->stream));
+  WBX_CUDA(cudaMemsetAsync(
+      d_w, 0,
+      plan->n_cells * plan->cells_mult() * WBX_NUM_DET_WCLASSES * sizeof(double),
+      ctx->stream));
   const int warps = wbx::warps_for(plan);
   int buf = 0;
   for (int64_t j0 = 0; j0 < plan->n_jobs; j0 += per_chunk, buf ^= 1) {
@@ -596,8 +727,12 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
         ctx, plan, P.records,
         reinterpret_cast<const int32_t*>(tbase + o_first),
         reinterpret_cast<const double*>(tbase + o_cw), n_cells, grid,
-        P.total_tiles, d_ws + static_cast<size_t>(P.cell_base) * WBX_NUM_DET_STATS,
-        d_w + static_cast<size_t>(P.cell_base) * WBX_NUM_DET_WCLASSES, 1);
+        P.total_tiles,
+        d_ws + static_cast<size_t>(P.cell_base) * plan->cells_mult() *
+                   WBX_NUM_DET_STATS,
+        d_w + static_cast<size_t>(P.cell_base) * plan->cells_mult() *
+                  WBX_NUM_DET_WCLASSES,
+        1);
     if (rc != WBX_OK) return rc;
     WBX_CUDA(cudaEventRecord(ctx->ev_compute[buf], ctx->stream));
   }
@@ -615,8 +750,10 @@ int wbx_det_plan_run(wbx_ctx* ctx, wbx_det_plan* plan, double* sum_ws,
               "wbx_det_plan_run: accumulate is not supported for host-space "
               "plans");
   WBX_CUDA(cudaSetDevice(ctx->device));
-  const size_t ws_bytes = plan->n_cells * WBX_NUM_DET_STATS * sizeof(double);
-  const size_t w_bytes = plan->n_cells * WBX_NUM_DET_WCLASSES * sizeof(double);
+  const size_t ws_bytes =
+      plan->n_cells * plan->cells_mult() * WBX_NUM_DET_STATS * sizeof(double);
+  const size_t w_bytes =
+      plan->n_cells * plan->cells_mult() * WBX_NUM_DET_WCLASSES * sizeof(double);
   double* d_ws = sum_ws;
   double* d_w = sum_w;
   if (out_space == WBX_SPACE_HOST) {

@@ -241,6 +241,82 @@ def _weight_vector(dims, sizes, per_dim: Mapping) -> np.ndarray | None:
 
 
 @dataclasses.dataclass
+class BinClasses:
+  """Bin masks over the slab folded into one class map (see wbx_b200.h).
+
+  class_map[y * nx + x] is the class of a grid point; membership[k][b, c] says
+  whether class c belongs to bin b of binning k.
+  """
+  class_map: np.ndarray          # uint8 [ny * nx]
+  n_classes: int
+  bin_dims: list                 # one new output dim per binning
+  bin_coords: dict               # bin dim -> labels
+  membership: list               # per binning: float64 [n_bins, n_classes]
+  digest: str
+
+  def to_bins(self, per_class: np.ndarray) -> np.ndarray:
+    """[n_cells, n_classes] class sums -> [n_cells, bins_1, bins_2, ...].
+
+    NaN class sums poison every bin (0 * NaN), like the reference's einsum over
+    bin masks does for NaNs outside the bin."""
+    letters = 'bdefghij'
+    expr = 'ac,' + ','.join(f'{letters[k]}c' for k in range(len(self.membership)))
+    expr += '->a' + ''.join(letters[k] for k in range(len(self.membership)))
+    return np.einsum(expr, per_class, *self.membership)
+
+
+_CLASS_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
+
+
+def fold_bin_masks(bin_masks: Sequence[xl.DataArray], bin_dim_names,
+                   inner: Sequence[Hashable], sizes) -> BinClasses:
+  """Folds boolean bin masks that live on the slab dims into a class map."""
+  import hashlib  # pylint: disable=g-import-not-at-top
+  if len(bin_masks) > 8:
+    raise FastPathUnavailable('too many binnings')
+  inner = list(inner)
+  shape = [sizes[d] for d in inner]
+  slab = int(np.prod(shape, dtype=np.int64))
+  expanded, labels, digest = [], {}, hashlib.blake2b(digest_size=16)
+  for mask, bdim in zip(bin_masks, bin_dim_names):
+    other = [d for d in mask.dims if d != bdim]
+    if not set(other) <= set(inner):
+      raise FastPathUnavailable('bin mask depends on dims outside the slab')
+    arr = mask.transpose(bdim, *[d for d in inner if d in other]).to_numpy()
+    arr = arr.astype(bool, copy=False)
+    view = [arr.shape[0]] + [sizes[d] if d in other else 1 for d in inner]
+    arr = np.broadcast_to(arr.reshape(view), [arr.shape[0]] + shape)
+    arr = np.ascontiguousarray(arr).reshape(arr.shape[0], slab)
+    expanded.append(arr)
+    digest.update(str(bdim).encode())
+    digest.update(arr.tobytes())
+    labels[bdim] = (mask.coords[bdim].to_numpy() if bdim in mask.coords
+                    else np.arange(arr.shape[0]))
+  key = digest.hexdigest()
+  hit = _CLASS_CACHE.get(key)
+  if hit is not None:
+    _CLASS_CACHE.move_to_end(key)
+    return hit
+  stacked = np.concatenate(expanded, axis=0)              # [n_bins_total, slab]
+  packed = np.ascontiguousarray(np.packbits(stacked, axis=0).T)  # [slab, nbytes]
+  void = packed.view(np.dtype((np.void, packed.shape[1]))).reshape(-1)
+  uniq, first_pos, inverse = np.unique(void, return_index=True,
+                                       return_inverse=True)
+  n_classes = len(uniq)
+  if n_classes > 256:
+    raise FastPathUnavailable(f'{n_classes} bin classes (max 256)')
+  membership = [arr[:, first_pos].astype(np.float64) for arr in expanded]
+  out = BinClasses(
+      class_map=inverse.reshape(-1).astype(np.uint8), n_classes=n_classes,
+      bin_dims=list(bin_dim_names), bin_coords=labels, membership=membership,
+      digest=key)
+  _CLASS_CACHE[key] = out
+  while len(_CLASS_CACHE) > 8:
+    _CLASS_CACHE.popitem(last=False)
+  return out
+
+
+@dataclasses.dataclass
 class FusedSpec:
   """Everything wbx_det_plan_create needs, plus how to label the results."""
   space: int
@@ -258,6 +334,7 @@ class FusedSpec:
   w_x: np.ndarray | None
   scalar: float
   stat_mask: int
+  classes: 'BinClasses | None'
   kept: list
   kept_shape: list
   coords: dict
@@ -270,7 +347,10 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
                      weights: Sequence[xl.DataArray] = (),
                      masked: bool = False, skipna: bool = False,
                      flags_extra: int = 0,
-                     device: int | None = None) -> FusedSpec | None:
+                     device: int | None = None,
+                     bin_masks: Sequence[xl.DataArray] = (),
+                     bin_dim_names: Sequence[Hashable] = ()
+                     ) -> FusedSpec | None:
   """Plans one fused launch for statistics that share operands (no GPU use).
 
   Returns None when the aggregation does not apply (reduce dims missing,
@@ -431,7 +511,17 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
   for name, cv in first.coords.items():
     if name not in coords and name != 'mask' and set(cv.dims) <= set(kept):
       coords[name] = cv
+  classes = None
+  if bin_masks:
+    if skipna or per_dim.get(x_dim) is not None or nx % 4 or (ny * nx) % 16:
+      raise FastPathUnavailable('binned slab kernel: unsupported combination')
+    classes = fold_bin_masks(bin_masks, bin_dim_names, inner, sizes)
+    n_sel = bin(stat_mask).count('1') + (1 if op_m is not None else 0)
+    if classes.n_classes * n_sel > 448:
+      raise FastPathUnavailable('too many classes x statistics')
+    cache_key = cache_key + ('bins', classes.digest)
   return FusedSpec(
+      classes=classes,
       space=space, flags=flags, ny=ny, nx=nx, n_cells=n_cells,
       pred=addresses(op_p), target=addresses(op_t), clim=clim_addr,
       mask=addresses(op_m) if op_m is not None else None,
@@ -447,6 +537,7 @@ def _merge_key(spec: FusedSpec):
   """Specs with the same key can share one launch (variables of equal grid)."""
   return (spec.space, spec.flags, spec.ny, spec.nx, spec.clim is None,
           spec.mask is None,
+          None if spec.classes is None else spec.classes.digest,
           None if spec.w_y is None else spec.w_y.tobytes(),
           None if spec.w_x is None else spec.w_x.tobytes())
 
@@ -488,7 +579,9 @@ def run_fused_specs(items, device: int | None = None):
           ctx, space=f.space, flags=f.flags, ny=f.ny, nx=f.nx, pred=f.pred,
           target=f.target, clim=f.clim, mask=f.mask, cell=f.cell,
           n_cells=f.n_cells, w_outer=f.w_outer, w_y=f.w_y, w_x=f.w_x,
-          stat_mask=f.stat_mask)
+          stat_mask=f.stat_mask,
+          class_map=None if f.classes is None else f.classes.class_map,
+          n_classes=0 if f.classes is None else f.classes.n_classes)
     else:
       key = ('merged',) + tuple(sp.cache_key for sp in specs)
       offsets = np.cumsum([0] + [sp.n_cells for sp in specs])
@@ -512,7 +605,9 @@ def run_fused_specs(items, device: int | None = None):
             cell=np.concatenate([sp.cell + off for sp, off in
                                  zip(specs, offsets)]).astype(np.int32),
             n_cells=int(offsets[-1]), w_outer=w_outer, w_y=f.w_y, w_x=f.w_x,
-            stat_mask=mask_bits)
+            stat_mask=mask_bits,
+            class_map=None if f.classes is None else f.classes.class_map,
+            n_classes=0 if f.classes is None else f.classes.n_classes)
     plan = _cached_plan(ctx, key, factory)
     # Keep the operands alive for as long as the plan may be run.
     plan.keepalive = tuple(sp.keepalive for sp in specs)
@@ -520,21 +615,35 @@ def run_fused_specs(items, device: int | None = None):
       ctx.use_torch_stream()
     ws, w = plan.run_to_host()
     lo = 0
+    mult = 1 if first.classes is None else first.classes.n_classes
     for i, sp in zip(members, specs):
-      raw[i] = (ws[lo:lo + sp.n_cells], w[lo:lo + sp.n_cells])
-      lo += sp.n_cells
+      raw[i] = (ws[lo:lo + sp.n_cells * mult], w[lo:lo + sp.n_cells * mult])
+      lo += sp.n_cells * mult
   results = []
   for idx, (spec, stats) in enumerate(items):
     ws, w = raw[idx]
     out = {}
+    cls = spec.classes
+    out_dims, out_shape, out_coords = spec.kept, spec.kept_shape, spec.coords
+    if cls is not None:
+      out_dims = list(spec.kept) + list(cls.bin_dims)
+      out_shape = list(spec.kept_shape) + [m.shape[0] for m in cls.membership]
+      out_coords = dict(spec.coords)
+      for bdim in cls.bin_dims:
+        out_coords[bdim] = cls.bin_coords[bdim]
     for s in stats:
       slot = _cabi.STAT_SLOT[s.kind]
-      sum_ws = (ws[:, slot] * spec.scalar).reshape(spec.kept_shape)
-      sum_w = (w[:, _cabi.STAT_WCLASS[slot]] * spec.scalar).reshape(
-          spec.kept_shape)
+      col_ws = ws[:, slot] * spec.scalar
+      col_w = w[:, _cabi.STAT_WCLASS[slot]] * spec.scalar
+      if cls is not None:
+        with np.errstate(invalid='ignore'):
+          col_ws = cls.to_bins(col_ws.reshape(spec.n_cells, cls.n_classes))
+          col_w = cls.to_bins(col_w.reshape(spec.n_cells, cls.n_classes))
       out[s.kind] = (
-          xl.DataArray(sum_ws, spec.kept, coords=spec.coords, name=s.name),
-          xl.DataArray(sum_w, spec.kept, coords=spec.coords, name=s.name),
+          xl.DataArray(col_ws.reshape(out_shape), out_dims, coords=out_coords,
+                       name=s.name),
+          xl.DataArray(col_w.reshape(out_shape), out_dims, coords=out_coords,
+                       name=s.name),
       )
     results.append(out)
   return results
