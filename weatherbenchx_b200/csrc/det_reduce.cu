@@ -181,7 +181,7 @@ static int launch_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
     F.n_classes = plan->n_classes;
     F.n_sel = plan->bins.n_sel;
     F.accumulate = accumulate;
-    for (int i = 0; i < WBX_NUM_DET_STATS; ++i) F.sel[i] = plan->bins.sel[i];
+    for (int i = 0; i < WBX_NUM_DET_STATS + 2; ++i) F.sel[i] = plan->bins.sel[i];
     if (!accumulate) {
       // unselected statistic slots are not written by the kernel
       WBX_CUDA(cudaMemsetAsync(
@@ -371,7 +371,7 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     WBX_REQUIRE(d->n_classes <= 256, "det: at most 256 bin classes");
     p->n_classes = d->n_classes;
     int nsel = 0;
-    for (int k = 0; k < WBX_NUM_DET_STATS; ++k) p->bins.sel[k] = -1;
+    for (int k = 0; k < WBX_NUM_DET_STATS + 2; ++k) p->bins.sel[k] = -1;
     for (int k = 0; k < p->n_stats; ++k)
       if (p->stat_mask & (1 << k)) p->bins.sel[nsel++] = k;
     if (p->has_mask) p->bins.sel[nsel++] = -1;  // weight accumulator
@@ -712,7 +712,7 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     P.tiles_per_slab = plan->tiles_per_slab;
     wbx::fill_steps(plan, &P);
     const int grid = wbx::grid_for(ctx, plan, P.total_tiles);
-    const int n_cells = static_cast<int>(cw.size());
+    const int n_cells = static_cast<int>(first.size()) - 1;
     const size_t rec_bytes = (static_cast<size_t>(grid) + n_cells) * warps *
                              plan->nacc * sizeof(double);
     // records are reused by consecutive chunks on the same compute stream, so

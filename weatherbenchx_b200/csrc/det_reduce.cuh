@@ -527,7 +527,7 @@ struct BinParams {
   const unsigned char* class_map;  // [slab] device
   int n_classes;
   int n_sel;                       // selected statistics (+1 weight if masked)
-  int sel[WBX_NUM_DET_STATS];      // statistic slot of every selected index
+  int sel[WBX_NUM_DET_STATS + 2];  // statistic slot of every selected index
 };
 
 __device__ __forceinline__ float warp_sum_f32(float v) {
@@ -757,7 +757,7 @@ struct BinFinalizeParams {
   double* out_w;                // [n_cells * n_classes * 4]
   long long total_tiles;
   int n_cells, grid_main, tiles_per_slab, n_classes, n_sel, accumulate;
-  int sel[WBX_NUM_DET_STATS];
+  int sel[WBX_NUM_DET_STATS + 2];
 };
 
 __global__ void __launch_bounds__(128) det_bins_finalize_kernel(
