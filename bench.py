@@ -318,6 +318,55 @@ def run_suite(ctx, dev, peak):
   del preds, tgts, clim, metrics, step
   torch.cuda.empty_cache()
 
+  # ---- binned RMSE: 8 regions x {all, land} = 16 bins, 0.25 deg
+  from weatherbenchx_b200 import binning
+  lat025 = np.linspace(-90, 90, NLAT)
+  lon025 = np.linspace(0, 360, NLON, endpoint=False)
+  rng = np.random.default_rng(7)
+  land = xl.DataArray(
+      np.kron(rng.random((103, 96)) > 0.7, np.ones((7, 15), bool)),
+      ('latitude', 'longitude'), coords={'latitude': lat025, 'longitude': lon025})
+  regions = {
+      'global': ((-90, 90), (0, 360)), 'tropics': ((-20, 20), (0, 360)),
+      'nh-extratropics': ((20, 90), (0, 360)),
+      'sh-extratropics': ((-90, -20), (0, 360)),
+      'europe': ((35, 75), (-12.5, 42.5)), 'n-america': ((25, 60), (240, 285)),
+      'east-asia': ((25, 60), (102.5, 150)), 'ausnz': ((-45, -12.5), (120, 175))}
+  bcoords = {'init_time': np.arange(20), 'latitude': lat025,
+             'longitude': lon025}
+  bdims = ('init_time', 'latitude', 'longitude')
+  preds, tgts = {}, {}
+  for v in range(5):
+    name = f'var{v}'
+    t = torch.empty((20, NLAT, NLON), device=dev)
+    t.normal_(280.0, 10.0, generator=gen)
+    p = t + torch.empty_like(t).normal_(0.0, 2.0, generator=gen)
+    preds[name] = xl.DataArray(p, bdims, coords=bcoords, name=name)
+    tgts[name] = xl.DataArray(t, bdims, coords=bcoords, name=name)
+  metrics = {'rmse': deterministic.RMSE()}
+  bin_agg = aggregation.Aggregator(
+      reduce_dims=['init_time', 'latitude', 'longitude'],
+      weigh_by=[weighting.GridAreaWeighting()],
+      bin_by=[binning.Regions(regions, land_sea_mask=land)])
+  step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
+      metrics, bin_agg, preds, tgts)
+  ms, kms, kn = timed(step, 10)
+  pts = 5 * 20 * NLAT * NLON
+  out['rmse_bins16'] = {
+      'workload': 'lat-weighted RMSE in 16 bins (8 regions x {all, land}), '
+                  '5 vars x 20 init x 721x1440 f32, fused class-map kernel, '
+                  'class API, device inputs',
+      'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+      'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+      'roofline': {'bound': 'hbm', 'achieved': pts * 9 / (kms * 1e-3) / 1e9,
+                   'peak': peak, 'unit': 'GB/s',
+                   'frac': pts * 9 / (kms * 1e-3) / 1e9 / peak,
+                   'algorithmic_bytes_per_point': 9,
+                   'note': '8 B fields + 1 B class map (the map is shared by '
+                           'all slabs and L2-resident)'}}
+  del preds, tgts, metrics, step
+  torch.cuda.empty_cache()
+
   # ---- config[2]: CRPS, M = 50, 5 vars x 20 init x 721 x 1440
   n_var, n_init, m = 5, 20, 50
   lat = np.linspace(-90, 90, NLAT)

@@ -60,6 +60,21 @@ class Regions(Binning):
   def create_bin_mask(self, statistic: xl.DataArray) -> xl.DataArray:
     lat = statistic.coords['latitude'].to_numpy()
     lon = statistic.coords['longitude'].to_numpy()
+    # The mask only depends on the grid: reuse it while the coordinate arrays
+    # are the same objects (every chunk of an evaluation shares them).
+    cached = getattr(self, '_cache', None)
+    if cached is not None and cached[0] is lat and cached[1] is lon:
+      return cached[2]
+    out = self._create_bin_mask(lat, lon)
+    self._cache = (lat, lon, out)
+    return out
+
+  def __getstate__(self):
+    state = dict(self.__dict__)
+    state.pop('_cache', None)
+    return state
+
+  def _create_bin_mask(self, lat, lon) -> xl.DataArray:
     names = list(self._regions)
     masks = np.stack([
         _lat_mask(lat, lat_lims)[:, None] & _lon_mask(lon, lon_lims)[None, :]

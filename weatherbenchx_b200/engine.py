@@ -275,6 +275,25 @@ def fold_bin_masks(bin_masks: Sequence[xl.DataArray], bin_dim_names,
   if len(bin_masks) > 8:
     raise FastPathUnavailable('too many binnings')
   inner = list(inner)
+  # identity fast path: the same mask objects (Binning classes cache them per
+  # grid) map to the same classes without re-hashing tens of megabytes.
+  ident = (tuple(id(m.data) for m in bin_masks), tuple(bin_dim_names),
+           tuple(inner), tuple(sizes[d] for d in inner))
+  hit = _CLASS_IDENT_CACHE.get(ident)
+  if hit is not None and all(a is m.data for a, m in zip(hit[0], bin_masks)):
+    return hit[1]
+  out = _fold_bin_masks(bin_masks, bin_dim_names, inner, sizes)
+  _CLASS_IDENT_CACHE[ident] = (tuple(m.data for m in bin_masks), out)
+  while len(_CLASS_IDENT_CACHE) > 8:
+    _CLASS_IDENT_CACHE.popitem(last=False)
+  return out
+
+
+_CLASS_IDENT_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
+
+
+def _fold_bin_masks(bin_masks, bin_dim_names, inner, sizes) -> BinClasses:
+  import hashlib  # pylint: disable=g-import-not-at-top
   shape = [sizes[d] for d in inner]
   slab = int(np.prod(shape, dtype=np.int64))
   expanded, labels, digest = [], {}, hashlib.blake2b(digest_size=16)
