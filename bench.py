@@ -324,7 +324,8 @@ def run_suite(ctx, dev, peak):
   lon025 = np.linspace(0, 360, NLON, endpoint=False)
   rng = np.random.default_rng(7)
   land = xl.DataArray(
-      np.kron(rng.random((103, 96)) > 0.7, np.ones((7, 15), bool)),
+      # continent-sized land blocks (8.75 x 15 degrees), like real coastlines
+      np.kron(rng.random((21, 24)) > 0.7, np.ones((35, 60), bool))[:NLAT],
       ('latitude', 'longitude'), coords={'latitude': lat025, 'longitude': lon025})
   regions = {
       'global': ((-90, 90), (0, 360)), 'tropics': ((-20, 20), (0, 360)),

@@ -694,47 +694,44 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         const double lw = __shfl_sync(0xffffffffu, wrow, leader);
         const bool mine = uniform && key == lkey;
         double* slot = wacc + (lkey & 0xff) * B.n_sel;
-        for (int q = 0; q < B.n_sel; ++q) {
-          float v = 0.f;
-          if (mine) {
-            const int sidx = B.sel[q];
-            if (sidx >= 0) {
 #pragma unroll
-              for (int k = 0; k < NS; ++k)
-                if (k == sidx)
-                  v = (val[0][k] + val[1][k]) + (val[2][k] + val[3][k]);
-            } else {
-              v = (ok[0] + ok[1]) + (ok[2] + ok[3]);
-            }
+        for (int k = 0; k < NS; ++k) {
+          if (P.stat_mask & (1 << k)) {  // warp-uniform
+            const float v =
+                mine ? (val[0][k] + val[1][k]) + (val[2][k] + val[3][k]) : 0.f;
+            const float tot = warp_sum_f32(v);
+            if (lane == 0)
+              slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
+                  static_cast<double>(tot) * lw;
           }
+        }
+        if constexpr (MASK) {
+          const float v = mine ? (ok[0] + ok[1]) + (ok[2] + ok[3]) : 0.f;
           const float tot = warp_sum_f32(v);
-          if (lane == 0) slot[q] += static_cast<double>(tot) * lw;
+          if (lane == 0) slot[B.n_sel - 1] += static_cast<double>(tot) * lw;
         }
         um &= ~__ballot_sync(0xffffffffu, mine);
       }
-      // ---- mixed lanes: fold their four points one by one -------------------
+      // ---- mixed lanes (a class boundary inside their four points): each
+      // owner folds its own points, one lane after the other (fixed order).
       unsigned mm_ = __ballot_sync(0xffffffffu, active && !uniform);
+      __syncwarp();
       while (mm_) {
         const int src = __ffs(mm_) - 1;
-        const double lw = __shfl_sync(0xffffffffu, wrow, src);
+        if (lane == src) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = __shfl_sync(0xffffffffu, static_cast<int>(cls[i]), src);
-          double* slot = wacc + c * B.n_sel;
-          for (int q = 0; q < B.n_sel; ++q) {
-            float v = 0.f;
-            const int sidx = B.sel[q];
-            if (sidx >= 0) {
+          for (int i = 0; i < 4; ++i) {
+            double* slot = wacc + cls[i] * B.n_sel;
 #pragma unroll
-              for (int k = 0; k < NS; ++k)
-                if (k == sidx) v = val[i][k];
-            } else {
-              v = ok[i];
-            }
-            v = __shfl_sync(0xffffffffu, v, src);
-            if (lane == 0) slot[q] += static_cast<double>(v) * lw;
+            for (int k = 0; k < NS; ++k)
+              if (P.stat_mask & (1 << k))
+                slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
+                    static_cast<double>(val[i][k]) * wrow;
+            if constexpr (MASK)
+              slot[B.n_sel - 1] += static_cast<double>(ok[i]) * wrow;
           }
         }
+        __syncwarp();
         mm_ &= mm_ - 1;
       }
     }
