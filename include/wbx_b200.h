@@ -197,17 +197,22 @@ int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
  * Jobs / cells / weights exactly as for wbx_det_desc.  Per job the targets are
  * one contiguous slab of ny*nx float32; ensemble member m of grid point g
  * (g = y*nx + x) is at  ens[j] + 4*(m*member_stride + g*point_stride).
- * Results: sum_ws[c*2 + s], sum_w[c*2 + s] with s = 0 CRPSSkill, 1 CRPSSpread.
+ * Results: sum_ws[c*4 + s], sum_w[c*4 + s] with s = 0 CRPSSkill, 1 CRPSSpread,
+ * 2 EnsembleVariance (ddof = 1, probabilistic.py:250-273), 3
+ * UnbiasedEnsembleMeanSquaredError ((mean - y)^2 - variance / n, :276-336).
  * n_members < 2 without WBX_CRPS_SKIPNA_ENSEMBLE is an error
- * (probabilistic.py:210-212).
+ * (probabilistic.py:210-212) unless WBX_CRPS_NO_SPREAD says the caller will
+ * not read the spread slot (variance / unbiased MSE are then NaN, as NumPy's).
  */
 enum {
   WBX_CRPS_FAIR = 256,            /* divide by M(M-1) instead of M^2          */
   WBX_CRPS_SKIPNA_ENSEMBLE = 512, /* NaN members are missing members          */
-  WBX_CRPS_USE_SORT = 1024        /* sort/PWM estimator (probabilistic.py:
+  WBX_CRPS_USE_SORT = 1024,       /* sort/PWM estimator (probabilistic.py:
                                      214-240) in a register sorting network;
                                      honoured for n_members <= 64, the pair
                                      sum is used otherwise                    */
+  WBX_CRPS_NO_SPREAD = 2048       /* slot 1 is not needed: skip the
+                                     n_members >= 2 check                     */
 };
 
 typedef struct wbx_crps_plan wbx_crps_plan;
@@ -233,7 +238,7 @@ typedef struct {
 int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* desc,
                          wbx_crps_plan** out);
 int wbx_crps_plan_destroy(wbx_ctx* ctx, wbx_crps_plan* plan);
-/* sum_ws / sum_w: float64 [n_cells*2]; semantics as wbx_det_plan_run. */
+/* sum_ws / sum_w: float64 [n_cells*4]; semantics as wbx_det_plan_run. */
 int wbx_crps_plan_run(wbx_ctx* ctx, wbx_crps_plan* plan, double* sum_ws,
                       double* sum_w, int32_t out_space, int32_t accumulate);
 
@@ -252,6 +257,8 @@ typedef struct {
   int64_t target_stride[WBX_CRPS_MAX_DIMS];
   const float* ens;
   const float* target;
+  float* variance;       /* optional extra outputs [n_points], may be NULL     */
+  float* unbiased_mse;
 } wbx_crps_point_desc;
 
 int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* desc,

@@ -37,6 +37,7 @@ accumulates everything in float64 and is what parity tests compare against.
 from __future__ import annotations
 
 import itertools
+import warnings
 from typing import Mapping, Sequence
 
 import numpy as np
@@ -387,6 +388,34 @@ def crps_spread(x: np.ndarray, ens_axis: int, fair: bool = True,
   out = out.reshape(xm.shape[:-1])
   with np.errstate(invalid='ignore', divide='ignore'):
     return out / (n * (n - int(fair)))
+
+
+def ensemble_variance(x: np.ndarray, ens_axis: int,
+                      skipna_ensemble: bool = False) -> np.ndarray:
+  """EnsembleVariance._compute_per_variable (probabilistic.py:266-273):
+  predictions.var(dim=ensemble_dim, ddof=1, skipna=skipna_ensemble)."""
+  with np.errstate(all='ignore'), warnings.catch_warnings():
+    warnings.simplefilter('ignore')
+    fn = np.nanvar if skipna_ensemble else np.var
+    return fn(x, axis=ens_axis, ddof=1)
+
+
+def unbiased_ensemble_mean_squared_error(
+    x: np.ndarray, y: np.ndarray, ens_axis: int,
+    skipna_ensemble: bool = False) -> np.ndarray:
+  """UnbiasedEnsembleMeanSquaredError (probabilistic.py:300-336) for targets
+  without an ensemble dim: (mean - y)**2 - var / n, with n the per-point count
+  of non-NaN members when skipna_ensemble."""
+  with np.errstate(all='ignore'), warnings.catch_warnings():
+    warnings.simplefilter('ignore')
+    if skipna_ensemble:
+      mean = np.nanmean(x, axis=ens_axis)
+      n = np.sum(~np.isnan(x), axis=ens_axis)
+    else:
+      mean = np.mean(x, axis=ens_axis)
+      n = x.shape[ens_axis]
+    var = ensemble_variance(x, ens_axis, skipna_ensemble)
+    return (mean - y) ** 2 - var / n
 
 
 def crps_spread_brute_force(x: np.ndarray, ens_axis: int, fair: bool):

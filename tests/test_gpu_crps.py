@@ -130,7 +130,13 @@ def test_golden_crps_through_cabi(m, fair):
       ws[:, 0], (g[f'crps{m}_skill'] * w[None, :, None]).sum((1, 2)), rtol=RTOL)
   np.testing.assert_allclose(
       ws[:, 1], (spread * w[None, :, None]).sum((1, 2)), rtol=RTOL)
-  np.testing.assert_allclose(wsum, np.full((n_init, 2), w.sum() * nx),
+  var = oracle.ensemble_variance(x, -1)
+  umse = oracle.unbiased_ensemble_mean_squared_error(x, y, -1)
+  np.testing.assert_allclose(
+      ws[:, 2], (var * w[None, :, None]).sum((1, 2)), rtol=RTOL)
+  np.testing.assert_allclose(
+      ws[:, 3], (umse * w[None, :, None]).sum((1, 2)), rtol=RTOL)
+  np.testing.assert_allclose(wsum, np.full((n_init, 4), w.sum() * nx),
                              rtol=1e-12)
 
 
@@ -209,8 +215,14 @@ def test_sort_and_pair_kernels_agree_with_nans(members):
   sk = oracle.crps_skill(np.moveaxis(x, 0, -1), y, -1, skipna_ensemble=True)
   sp = oracle.crps_spread(np.moveaxis(x, 0, -1), -1, fair=True,
                           skipna_ensemble=True)
-  np.testing.assert_allclose(out[True, True][0][0],
-                             [np.nansum(sk), np.nansum(sp)], rtol=RTOL)
+  xl_ = np.moveaxis(x, 0, -1)
+  var = oracle.ensemble_variance(xl_, -1, skipna_ensemble=True)
+  umse = oracle.unbiased_ensemble_mean_squared_error(xl_, y, -1,
+                                                     skipna_ensemble=True)
+  np.testing.assert_allclose(
+      out[True, True][0][0],
+      [np.nansum(sk), np.nansum(sp), np.nansum(var), np.nansum(umse)],
+      rtol=RTOL)
 
 
 @pytest.mark.parametrize('masked', [False, True])
@@ -245,10 +257,13 @@ def test_tma_staged_pair_kernel_equals_plain_one(masked):
   skill = oracle.crps_skill(x, y, 1)
   spread = oracle.crps_spread(x, 1, fair=True)
   wm = w[None, :, None] * (m if masked else 1.0)
-  np.testing.assert_allclose(out[0][0][0], [(skill * wm).sum(),
-                                            (spread * wm).sum()], rtol=RTOL)
+  var = oracle.ensemble_variance(x, 1)
+  umse = oracle.unbiased_ensemble_mean_squared_error(x, y, 1)
+  np.testing.assert_allclose(
+      out[0][0][0], [(skill * wm).sum(), (spread * wm).sum(),
+                     (var * wm).sum(), (umse * wm).sum()], rtol=RTOL)
   np.testing.assert_allclose(out[0][1][0], [wm.sum() if masked else
-                                            w.sum() * nx * n_init] * 2,
+                                            w.sum() * nx * n_init] * 4,
                              rtol=1e-12)
 
 
@@ -269,6 +284,87 @@ def test_pointwise_fields_match_oracle():
     np.testing.assert_allclose(
         sp, oracle.crps_spread(x, -1, fair=True, skipna_ensemble=skipna),
         rtol=2e-5, atol=1e-6, equal_nan=True)
+    var = LazyEnsembleStatistic('EnsembleVariance', X, Y, 'number', True,
+                                skipna).values
+    umse = LazyEnsembleStatistic('UnbiasedEnsembleMeanSquaredError', X, Y,
+                                 'number', True, skipna).values
+    np.testing.assert_allclose(
+        var, oracle.ensemble_variance(x, -1, skipna_ensemble=skipna),
+        rtol=2e-6, equal_nan=True)
+    np.testing.assert_allclose(
+        umse, oracle.unbiased_ensemble_mean_squared_error(
+            x, y, -1, skipna_ensemble=skipna),
+        rtol=2e-5, atol=1e-6, equal_nan=True)
+
+
+@pytest.mark.parametrize('skipna_ensemble', [False, True])
+@pytest.mark.parametrize('members', [2, 7, 50])
+@pytest.mark.parametrize('space', ['host', 'device'])
+def test_ensemble_moment_metrics_match_oracle(members, space, skipna_ensemble):
+  """UnbiasedSpreadSkillRatio / UnbiasedEnsembleMeanRMSE /
+  EnsembleRootMeanVariance next to CRPSEnsemble: one launch per variable
+  (probabilistic_test.py's spread-skill cases use the same formulae)."""
+  rng = np.random.default_rng(members)
+  n_init, nlat, nlon = 3, 10, 16
+  coords = {'init_time': np.arange(n_init), 'number': np.arange(members),
+            'latitude': np.linspace(-81, 81, nlat),
+            'longitude': np.arange(nlon) * 22.5}
+  dims = ('init_time', 'latitude', 'longitude')
+  y = rng.normal(280, 2, size=(n_init, nlat, nlon)).astype(np.float32)
+  x = (y[:, None] + rng.normal(0, 2, size=(n_init, members, nlat, nlon))
+       ).astype(np.float32)
+  if skipna_ensemble and members > 2:
+    x[rng.random(x.shape) < 0.05] = np.nan
+  X = xl.DataArray(x, ('init_time', 'number', 'latitude', 'longitude'),
+                   coords=coords, name='t')
+  Y = xl.DataArray(y, dims, coords={d: coords[d] for d in dims}, name='t')
+  if space == 'device':
+    X, Y = engine.to_device(X), engine.to_device(Y)
+  kw = dict(skipna_ensemble=skipna_ensemble)
+  metrics = {
+      'ssr': probabilistic.UnbiasedSpreadSkillRatio(**kw),
+      'rmse': probabilistic.UnbiasedEnsembleMeanRMSE(**kw),
+      'spread': probabilistic.EnsembleRootMeanVariance(**kw),
+      'crps': probabilistic.CRPSEnsemble(**kw),
+  }
+  rd = ['init_time', 'latitude', 'longitude']
+  values = compute_all_metrics(metrics, {'t': X}, {'t': Y}, rd,
+                               weigh_by=[weighting.GridAreaWeighting()],
+                               skipna=skipna_ensemble)
+  w = oracle.grid_area_weights(coords['latitude'])[None, :, None]
+  var = oracle.ensemble_variance(x, 1, skipna_ensemble)
+  umse = oracle.unbiased_ensemble_mean_squared_error(x, y, 1, skipna_ensemble)
+
+  def wmean(f):
+    ok = ~np.isnan(f) if skipna_ensemble else np.ones(f.shape, bool)
+    return np.sum(np.where(ok, f, 0) * w) / np.sum(ok * w)
+
+  np.testing.assert_allclose(values['spread.t'].values, np.sqrt(wmean(var)),
+                             rtol=RTOL)
+  np.testing.assert_allclose(values['rmse.t'].values, np.sqrt(wmean(umse)),
+                             rtol=RTOL)
+  np.testing.assert_allclose(values['ssr.t'].values,
+                             np.sqrt(wmean(var) / wmean(umse)), rtol=RTOL)
+  skill = oracle.crps_skill(x, y, 1, skipna_ensemble=skipna_ensemble)
+  spread = oracle.crps_spread(x, 1, fair=True, skipna_ensemble=skipna_ensemble)
+  np.testing.assert_allclose(values['crps.t'].values,
+                             wmean(skill) - 0.5 * wmean(spread), rtol=RTOL)
+
+
+def test_single_member_variance_is_nan_and_spread_raises():
+  x = np.ones((1, 4, 8), np.float32)
+  y = np.zeros((4, 8), np.float32)
+  X = xl.DataArray(x, ('number', 'latitude', 'longitude'), name='t')
+  Y = xl.DataArray(y, ('latitude', 'longitude'), name='t')
+  values = compute_all_metrics(
+      {'spread': probabilistic.EnsembleRootMeanVariance()}, {'t': X}, {'t': Y},
+      ['latitude', 'longitude'])
+  assert np.isnan(values['spread.t'].values)
+  with pytest.raises(ValueError, match='n_ensemble < 2'):
+    compute_all_metrics({'crps': probabilistic.CRPSEnsemble()}, {'t': X},
+                        {'t': Y}, ['latitude', 'longitude'])
+  with pytest.raises(ValueError, match='UnbiasedSpreadSkillRatio'):
+    probabilistic.SpreadSkillRatio(ensemble_dim='number')
 
 
 # ---------------------------------------------------------------------------

@@ -320,3 +320,47 @@ def test_spectrum_identities():
   # scaling by a -> a^2
   np.testing.assert_allclose(oracle.zonal_energy_spectrum(2 * f, lat), 4 * s,
                              rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# ensemble moments (probabilistic.py:250-336).  The reference's own
+# known-answer test is statistical: metrics_test.py:947-983
+# (test_spread_skill_ratio) draws targets and a 5-member ensemble iid from the
+# same distribution and expects the unbiased spread-skill ratio to be 1 within
+# 4 / sqrt(sample_size * ensemble_size).
+# ---------------------------------------------------------------------------
+
+
+def test_spread_skill_ratio_of_iid_ensemble_is_one():
+  ensemble_size = 5
+  shape = (2, 19, 36)       # time, latitude, longitude of the mock data
+  # test_utils.py:43-46: uniform [0, 1) samples, seeds 0 (targets) and 1
+  y = np.random.default_rng(0).random(size=shape).astype(np.float32)
+  x = np.random.default_rng(1).random(
+      size=(ensemble_size,) + shape).astype(np.float32)
+  var = oracle.ensemble_variance(x, 0)
+  umse = oracle.unbiased_ensemble_mean_squared_error(x, y, 0)
+  ratio = np.sqrt(var.mean() / umse.mean())
+  atol = 4 / np.sqrt(y.size * ensemble_size)
+  assert abs(ratio - 1.0) < atol
+
+
+def test_ensemble_moments_closed_form():
+  # members 1, 2, 3, 6 -> mean 3, unbiased variance 14 / 3
+  x = np.array([1.0, 2.0, 3.0, 6.0], np.float32).reshape(4, 1)
+  y = np.array([1.0], np.float32)
+  np.testing.assert_allclose(oracle.ensemble_variance(x, 0), [14 / 3],
+                             rtol=1e-6)
+  np.testing.assert_allclose(
+      oracle.unbiased_ensemble_mean_squared_error(x, y, 0),
+      [4.0 - 14 / 12], rtol=1e-6)
+  # skipna_ensemble: a NaN member is a missing member (n = 3 -> mean 2, var 1)
+  xn = np.array([1.0, 2.0, 3.0, np.nan], np.float32).reshape(4, 1)
+  np.testing.assert_allclose(
+      oracle.ensemble_variance(xn, 0, skipna_ensemble=True), [1.0], rtol=1e-6)
+  np.testing.assert_allclose(
+      oracle.unbiased_ensemble_mean_squared_error(xn, y, 0, True),
+      [1.0 - 1 / 3], rtol=1e-6)
+  assert np.isnan(oracle.ensemble_variance(xn, 0))
+  # a single member has no unbiased variance
+  assert np.isnan(oracle.ensemble_variance(x[:1], 0))

@@ -88,6 +88,7 @@ class GenericDesc(ctypes.Structure):
 
 
 CRPS_FAIR, CRPS_SKIPNA_ENSEMBLE, CRPS_USE_SORT = 256, 512, 1024
+CRPS_NO_SPREAD = 2048
 
 
 class CrpsDesc(ctypes.Structure):
@@ -112,6 +113,7 @@ class CrpsPointDesc(ctypes.Structure):
       ('size', c_int64 * MAX_DIMS), ('ens_stride', c_int64 * MAX_DIMS),
       ('target_stride', c_int64 * MAX_DIMS),
       ('ens', c_void_p), ('target', c_void_p),
+      ('variance', c_void_p), ('unbiased_mse', c_void_p),
   ]
 
 
@@ -421,9 +423,10 @@ class CrpsPlan:
     del keep
 
   def run_to_host(self):
-    """(sum_ws [n_cells, 2], sum_w [n_cells, 2]); column 0 skill, 1 spread."""
-    ws = np.empty((self.n_cells, 2), np.float64)
-    w = np.empty((self.n_cells, 2), np.float64)
+    """(sum_ws [n_cells, 4], sum_w [n_cells, 4]); columns: CRPSSkill,
+    CRPSSpread, EnsembleVariance, UnbiasedEnsembleMeanSquaredError."""
+    ws = np.empty((self.n_cells, 4), np.float64)
+    w = np.empty((self.n_cells, 4), np.float64)
     check(self.ctx.lib.wbx_crps_plan_run(
         self.ctx.handle, self.handle, ws.ctypes.data, w.ctypes.data,
         SPACE_HOST, 0))

@@ -53,6 +53,39 @@ struct CrpsParams {
 
 // skill / spread of one grid point whose members sit in a shared-memory column
 // xs[m * pitch].  ENS_SKIPNA drops NaN members.
+// Ensemble moments of one grid point (probabilistic.py:250-336):
+//   variance  = sum (x - mean)^2 / (n - 1)             EnsembleVariance
+//   umse      = (mean - y)^2 - variance / n            UnbiasedEnsembleMeanSquaredError
+template <bool ENS_SKIPNA>
+__device__ __forceinline__ void ensemble_moments(const float* __restrict__ xs,
+                                                 const int pitch, const int M,
+                                                 const float y, float* variance,
+                                                 float* umse) {
+  float sum = 0.f;
+  int n = 0;
+  for (int m = 0; m < M; ++m) {
+    const float a = xs[m * pitch];
+    if (!ENS_SKIPNA || a == a) {
+      sum += a;
+      ++n;
+    }
+  }
+  const float fn = static_cast<float>(n);
+  const float mean = __fdiv_rn(sum, fn);
+  float ss = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const float a = xs[m * pitch];
+    if (!ENS_SKIPNA || a == a) {
+      const float d = a - mean;
+      ss = __fadd_rn(ss, __fmul_rn(d, d));  // NumPy order, no FMA contraction
+    }
+  }
+  const float var = __fdiv_rn(ss, fn - 1.f);
+  const float e = mean - y;
+  *variance = var;
+  *umse = __fsub_rn(__fmul_rn(e, e), __fdiv_rn(var, fn));
+}
+
 template <bool ENS_SKIPNA>
 __device__ __forceinline__ void crps_point(const float* __restrict__ xs,
                                            const int pitch, const int M,
@@ -116,7 +149,20 @@ __device__ __forceinline__ void crps_point(const float* __restrict__ xs,
   }
 }
 
-constexpr int kCrpsAcc = 4;  // skill, spread, weight(skill), weight(spread)
+constexpr int kCrpsStats = 4;  // skill, spread, variance, unbiased MSE
+constexpr int kCrpsAcc = 2 * kCrpsStats;  // + one weight sum per statistic
+
+__device__ __forceinline__ void crps_accumulate(const float (&v)[kCrpsStats],
+                                                const bool base,
+                                                const int skipna_stat,
+                                                const double w, double* acc) {
+#pragma unroll
+  for (int k = 0; k < kCrpsStats; ++k) {
+    const bool ok = base && (!skipna_stat || v[k] == v[k]);
+    acc[k] += (ok ? static_cast<double>(v[k]) : 0.0) * w;
+    acc[kCrpsStats + k] += (ok ? 1.0 : 0.0) * w;
+  }
+}
 
 template <bool ENS_SKIPNA, bool MASK>
 __global__ void __launch_bounds__(kCrpsThreads)
@@ -131,7 +177,7 @@ __global__ void __launch_bounds__(kCrpsThreads)
       (static_cast<long long>(blockIdx.x) * P.total_tiles) / gridDim.x;
   const long long t_end =
       (static_cast<long long>(blockIdx.x + 1) * P.total_tiles) / gridDim.x;
-  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0};
+  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   int cur_cell = -1;
   long long job = t_begin / P.tiles_per_slab;
   int k = static_cast<int>(t_begin - job * P.tiles_per_slab);
@@ -185,9 +231,11 @@ __global__ void __launch_bounds__(kCrpsThreads)
     }
     __syncthreads();
     if (tid < len) {
-      float skill, spread;
-      crps_point<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], P.fair, &skill,
-                             &spread);
+      float v[kCrpsStats];
+      crps_point<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], P.fair, &v[0],
+                             &v[1]);
+      ensemble_moments<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], &v[2],
+                                   &v[3]);
       const unsigned e = static_cast<unsigned>(e0 + tid);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
@@ -196,12 +244,7 @@ __global__ void __launch_bounds__(kCrpsThreads)
       if (P.w_x) w *= __ldg(P.w_x + xx);
       bool base = true;
       if constexpr (MASK) base = ms[tid] != 0;
-      const bool ok_sk = base && (!P.skipna_stat || skill == skill);
-      const bool ok_sp = base && (!P.skipna_stat || spread == spread);
-      acc[0] += (ok_sk ? static_cast<double>(skill) : 0.0) * w;
-      acc[1] += (ok_sp ? static_cast<double>(spread) : 0.0) * w;
-      acc[2] += (ok_sk ? 1.0 : 0.0) * w;
-      acc[3] += (ok_sp ? 1.0 : 0.0) * w;
+      crps_accumulate(v, base, P.skipna_stat, w, acc);
     }
     if (++k == P.tiles_per_slab) {
       k = 0;
@@ -314,7 +357,7 @@ __global__ void __launch_bounds__(kCrpsTmaThreads)
     return;
   }
 
-  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0};
+  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   int cur_cell = -1;
   int s = 0;
   uint32_t ph = 0;
@@ -338,10 +381,10 @@ __global__ void __launch_bounds__(kCrpsTmaThreads)
     const unsigned char* st = crps_smem + s * stage_stride;
     const float* xs = reinterpret_cast<const float*>(st);
     if (tid < mt.len) {
-      float skill, spread;
-      crps_point<ENS_SKIPNA>(xs + tid, kCrpsThreads, M,
-                             xs[M * kCrpsThreads + tid], P.fair, &skill,
-                             &spread);
+      float v[kCrpsStats];
+      const float yv = xs[M * kCrpsThreads + tid];
+      crps_point<ENS_SKIPNA>(xs + tid, kCrpsThreads, M, yv, P.fair, &v[0], &v[1]);
+      ensemble_moments<ENS_SKIPNA>(xs + tid, kCrpsThreads, M, yv, &v[2], &v[3]);
       const unsigned e = static_cast<unsigned>(mt.e0 + tid);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
@@ -351,12 +394,7 @@ __global__ void __launch_bounds__(kCrpsTmaThreads)
       bool base = true;
       if constexpr (MASK)
         base = st[(static_cast<size_t>(M) + 1) * kCrpsThreads * 4 + tid] != 0;
-      const bool ok_sk = base && (!P.skipna_stat || skill == skill);
-      const bool ok_sp = base && (!P.skipna_stat || spread == spread);
-      acc[0] += (ok_sk ? static_cast<double>(skill) : 0.0) * w;
-      acc[1] += (ok_sp ? static_cast<double>(spread) : 0.0) * w;
-      acc[2] += (ok_sk ? 1.0 : 0.0) * w;
-      acc[3] += (ok_sp ? 1.0 : 0.0) * w;
+      crps_accumulate(v, base, P.skipna_stat, w, acc);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
@@ -446,7 +484,7 @@ __global__ void __launch_bounds__(kCrpsThreads)
       (static_cast<long long>(blockIdx.x) * P.total_tiles) / gridDim.x;
   const long long t_end =
       (static_cast<long long>(blockIdx.x + 1) * P.total_tiles) / gridDim.x;
-  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0};
+  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   int cur_cell = -1;
   long long job = t_begin / P.tiles_per_slab;
   int k = static_cast<int>(t_begin - job * P.tiles_per_slab);
@@ -482,8 +520,8 @@ __global__ void __launch_bounds__(kCrpsThreads)
                                                   P.member_stride)
                        : inf;
       const float y = ldg_stream_f1(ta + e);
-      // skill + NaN bookkeeping (order-independent sums)
-      float sk = 0.f;
+      // skill, moments + NaN bookkeeping (order-independent sums)
+      float sk = 0.f, msum = 0.f;
       int n_nan = 0;
 #pragma unroll
       for (int m = 0; m < MAXM; ++m) {
@@ -492,9 +530,24 @@ __global__ void __launch_bounds__(kCrpsThreads)
           n_nan += isn ? 1 : 0;
           const float d = fabsf(x[m] - y);
           sk += (ENS_SKIPNA && isn) ? 0.f : d;
+          msum += (ENS_SKIPNA && isn) ? 0.f : x[m];
+        }
+      }
+      const float fnm = static_cast<float>(ENS_SKIPNA ? (M - n_nan) : M);
+      const float mean = __fdiv_rn(msum, fnm);
+      float ss = 0.f;
+#pragma unroll
+      for (int m = 0; m < MAXM; ++m) {
+        if (m < M) {
+          const bool isn = !(x[m] == x[m]);
+          const float d = x[m] - mean;
+          ss = __fadd_rn(ss, (ENS_SKIPNA && isn) ? 0.f : __fmul_rn(d, d));
           if (isn) x[m] = inf;
         }
       }
+      float v[kCrpsStats];
+      v[2] = __fdiv_rn(ss, fnm - 1.f);
+      v[3] = __fsub_rn(__fmul_rn(mean - y, mean - y), __fdiv_rn(v[2], fnm));
       sort_network<MAXM>(x);
       const int n = ENS_SKIPNA ? (M - n_nan) : M;
       const float c = x[0];
@@ -511,6 +564,8 @@ __global__ void __launch_bounds__(kCrpsThreads)
         skill = __int_as_float(0x7fc00000);
         spread = skill;
       }
+      v[0] = skill;
+      v[1] = spread;
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
       double w = wo;
@@ -522,12 +577,7 @@ __global__ void __launch_bounds__(kCrpsThreads)
             reinterpret_cast<const unsigned char*>(__ldg(P.mask + job));
         base = __ldg(ma + e) != 0;
       }
-      const bool ok_sk = base && (!P.skipna_stat || skill == skill);
-      const bool ok_sp = base && (!P.skipna_stat || spread == spread);
-      acc[0] += (ok_sk ? static_cast<double>(skill) : 0.0) * w;
-      acc[1] += (ok_sp ? static_cast<double>(spread) : 0.0) * w;
-      acc[2] += (ok_sk ? 1.0 : 0.0) * w;
-      acc[3] += (ok_sp ? 1.0 : 0.0) * w;
+      crps_accumulate(v, base, P.skipna_stat, w, acc);
     }
     if (++k == P.tiles_per_slab) {
       k = 0;
@@ -577,8 +627,9 @@ __global__ void __launch_bounds__(128) crps_finalize_kernel(
   for (int i = lane; i < n; i += 32) sum += rec[static_cast<size_t>(i) * kCrpsAcc];
   sum = warp_sum(sum);
   if (lane == 0) {
-    double* dst = a < 2 ? F.out_ws + (size_t)c * 2 + a
-                        : F.out_w + (size_t)c * 2 + (a - 2);
+    double* dst = a < kCrpsStats
+                      ? F.out_ws + (size_t)c * kCrpsStats + a
+                      : F.out_w + (size_t)c * kCrpsStats + (a - kCrpsStats);
     *dst = F.accumulate ? (*dst + sum) : sum;
   }
 }
@@ -598,6 +649,8 @@ struct CrpsPointParams {
   int ndim, n_members, fair;
   float* skill;
   float* spread;
+  float* variance;
+  float* umse;
 };
 
 template <bool ENS_SKIPNA>
@@ -617,11 +670,16 @@ __global__ void __launch_bounds__(kCrpsThreads)
   float* col = smem + tid;
   for (int m = 0; m < P.n_members; ++m)
     col[m * kCrpsPitch] = P.ens[eo + m * P.member_stride];
-  float skill, spread;
-  crps_point<ENS_SKIPNA>(col, kCrpsPitch, P.n_members, P.target[to], P.fair,
-                         &skill, &spread);
+  float skill, spread, variance, umse;
+  const float yv = P.target[to];
+  crps_point<ENS_SKIPNA>(col, kCrpsPitch, P.n_members, yv, P.fair, &skill,
+                         &spread);
+  ensemble_moments<ENS_SKIPNA>(col, kCrpsPitch, P.n_members, yv, &variance,
+                               &umse);
   if (P.skill) P.skill[pt] = skill;
   if (P.spread) P.spread[pt] = spread;
+  if (P.variance) P.variance[pt] = variance;
+  if (P.umse) P.umse[pt] = umse;
 }
 
 }  // namespace wbx
@@ -831,7 +889,7 @@ int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* d,
   WBX_REQUIRE(d->ny >= 1 && d->nx >= 1 && d->ny * d->nx < (1ll << 30),
               "crps: bad slab shape");
   const bool ens_skipna = (d->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
-  if (!ens_skipna && d->n_members < 2) {
+  if (!ens_skipna && d->n_members < 2 && !(d->flags & WBX_CRPS_NO_SPREAD)) {
     wbx::set_error("Cannot estimate CRPS spread with n_ensemble < 2.");
     return WBX_ERR_INVALID;  // probabilistic.py:210-212
   }
@@ -1000,9 +1058,9 @@ static int crps_run_host(wbx_ctx* ctx, wbx_crps_plan* plan, double* d_ws,
     int rc = ctx->staging[b].reserve(static_cast<size_t>(per_chunk) * job_bytes);
     if (rc != WBX_OK) return rc;
   }
-  WBX_CUDA(cudaMemsetAsync(d_ws, 0, plan->n_cells * 2 * sizeof(double),
+  WBX_CUDA(cudaMemsetAsync(d_ws, 0, plan->n_cells * wbx::kCrpsStats * sizeof(double),
                            ctx->stream));
-  WBX_CUDA(cudaMemsetAsync(d_w, 0, plan->n_cells * 2 * sizeof(double),
+  WBX_CUDA(cudaMemsetAsync(d_w, 0, plan->n_cells * wbx::kCrpsStats * sizeof(double),
                            ctx->stream));
   const bool member_major = plan->point_stride == 1;
   int buf = 0;
@@ -1062,8 +1120,11 @@ static int crps_run_host(wbx_ctx* ctx, wbx_crps_plan* plan, double* d_ws,
     if (rc != WBX_OK) return rc;
     rc = wbx::crps_finalize(ctx, plan, P.records, d_first, n_cells, grid,
                             P.total_tiles,
-                            d_ws + static_cast<size_t>(P.cell_base) * 2,
-                            d_w + static_cast<size_t>(P.cell_base) * 2, 1);
+                            d_ws + static_cast<size_t>(P.cell_base) *
+                                       wbx::kCrpsStats,
+                            d_w + static_cast<size_t>(P.cell_base) *
+                                      wbx::kCrpsStats,
+                            1);
     if (rc != WBX_OK) return rc;
     WBX_CUDA(cudaEventRecord(ctx->ev_compute[buf], ctx->stream));
   }
@@ -1079,7 +1140,7 @@ int wbx_crps_plan_run(wbx_ctx* ctx, wbx_crps_plan* plan, double* sum_ws,
                                plan->space == WBX_SPACE_HOST)),
               "wbx_crps_plan_run: accumulate needs device inputs and outputs");
   WBX_CUDA(cudaSetDevice(ctx->device));
-  const size_t bytes = plan->n_cells * 2 * sizeof(double);
+  const size_t bytes = plan->n_cells * wbx::kCrpsStats * sizeof(double);
   double* d_ws = sum_ws;
   double* d_w = sum_w;
   if (out_space == WBX_SPACE_HOST) {
@@ -1109,9 +1170,10 @@ int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* d,
   WBX_REQUIRE(ctx && d, "wbx_crps_pointwise: NULL argument");
   WBX_REQUIRE(d->ndim >= 0 && d->ndim <= WBX_MAX_DIMS, "crps: bad ndim");
   WBX_REQUIRE(d->ens && d->target, "crps: NULL operand");
-  WBX_REQUIRE(skill || spread, "crps: nothing to compute");
+  WBX_REQUIRE(skill || spread || d->variance || d->unbiased_mse,
+              "crps: nothing to compute");
   const bool ens_skipna = (d->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
-  if (!ens_skipna && d->n_members < 2) {
+  if (!ens_skipna && d->n_members < 2 && spread) {
     wbx::set_error("Cannot estimate CRPS spread with n_ensemble < 2.");
     return WBX_ERR_INVALID;
   }
@@ -1135,6 +1197,8 @@ int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* d,
   P.fair = (d->flags & WBX_CRPS_FAIR) ? 1 : 0;
   P.skill = skill;
   P.spread = spread;
+  P.variance = d->variance;
+  P.umse = d->unbiased_mse;
   const size_t smem = static_cast<size_t>(d->n_members) * wbx::kCrpsPitch * 4;
   WBX_REQUIRE(smem <= std::min<size_t>(ctx->smem_optin, 227 * 1024),
               "crps: too many members for shared memory");

@@ -738,7 +738,8 @@ def materialize(stat: LazyStatistic, device: int | None = None):
 # CRPS (ensemble) statistics
 # ---------------------------------------------------------------------------
 
-CRPS_SLOT = {'CRPSSkill': 0, 'CRPSSpread': 1}
+CRPS_SLOT = {'CRPSSkill': 0, 'CRPSSpread': 1, 'EnsembleVariance': 2,
+             'UnbiasedEnsembleMeanSquaredError': 3}
 
 
 @dataclasses.dataclass
@@ -891,6 +892,8 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
     flags |= _cabi.CRPS_SKIPNA_ENSEMBLE
   if use_sort:
     flags |= _cabi.CRPS_USE_SORT
+  if fair is None:  # no CRPSSpread in this launch
+    flags |= _cabi.CRPS_NO_SPREAD
 
   def addresses(op):
     off = _job_offsets(job_dims, job_sizes, op.strides)
@@ -989,6 +992,10 @@ def materialize_crps(stat, device=None):
   ctx.use_torch_stream()
   skill = out.data_ptr() if stat.kind == 'CRPSSkill' else None
   spread = out.data_ptr() if stat.kind == 'CRPSSpread' else None
+  if stat.kind == 'EnsembleVariance':
+    desc.variance = out.data_ptr()
+  if stat.kind == 'UnbiasedEnsembleMeanSquaredError':
+    desc.unbiased_mse = out.data_ptr()
   code = ctx.lib.wbx_crps_pointwise(ctx.handle, ctypes.byref(desc),
                                     ctypes.c_void_p(skill),
                                     ctypes.c_void_p(spread))

@@ -2,8 +2,11 @@
 
 Mirrors the hot-path subset of
 /root/reference/weatherbenchX/metrics/probabilistic.py: CRPSSkill :116-145,
-CRPSSpread :165-247, CRPSEnsemble :606-688 (same constructor arguments, same
-unique_name strings, same errors).  As in the reference ``use_sort`` does not
+CRPSSpread :165-247, CRPSEnsemble :606-688, and the ensemble-moment family
+EnsembleVariance :250-273, UnbiasedEnsembleMeanSquaredError :276-336 with their
+metrics :864-1005 (same constructor arguments, same unique_name strings, same
+errors).  All four statistics of one (predictions, targets) pair come out of
+ONE kernel launch that reads the ensemble once.  As in the reference ``use_sort`` does not
 enter the statistic's unique_name -- both estimators compute the same statistic.
 ``use_sort=False`` (default) runs the tiled O(M^2) member-pair kernel;
 ``use_sort=True`` runs the sort / probability-weighted-moment estimator in a
@@ -14,6 +17,8 @@ to the pair sum).
 from __future__ import annotations
 
 from typing import Mapping
+
+import numpy as np
 
 from weatherbenchx_b200.lazy import LazyEnsembleStatistic
 from weatherbenchx_b200.metrics import base
@@ -73,6 +78,53 @@ class CRPSSpread(base.PerVariableStatistic):
         use_sort=self._use_sort)
 
 
+class EnsembleVariance(base.PerVariableStatistic):
+  """Variance over the ensemble dimension, standard unbiased (ddof=1) estimator.
+
+  Reference: probabilistic.py:250-273.  Served by the same launch as the CRPS
+  statistics (slot 2 of wbx_crps_plan_run).
+  """
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM,
+               skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def unique_name(self) -> str:
+    return (f'EnsembleVariance_{self._ensemble_dim}_skipna_ensemble_'
+            f'{self._skipna_ensemble}')
+
+  def _compute_per_variable(self, predictions, targets):
+    return LazyEnsembleStatistic(
+        'EnsembleVariance', predictions, targets, self._ensemble_dim,
+        fair=True, skipna_ensemble=self._skipna_ensemble)
+
+
+class UnbiasedEnsembleMeanSquaredError(base.PerVariableStatistic):
+  """(ensemble mean - target)^2 minus the finite-ensemble bias variance / n.
+
+  Reference: probabilistic.py:276-336 (the usual case of deterministic
+  targets; an ensemble of targets is outside the hot path).  Slot 3 of
+  wbx_crps_plan_run.
+  """
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM,
+               skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def unique_name(self) -> str:
+    return (f'UnbiasedEnsembleMeanSquaredError_{self._ensemble_dim}_'
+            f'skipna_ensemble_{self._skipna_ensemble}')
+
+  def _compute_per_variable(self, predictions, targets):
+    return LazyEnsembleStatistic(
+        'UnbiasedEnsembleMeanSquaredError', predictions, targets,
+        self._ensemble_dim, fair=True, skipna_ensemble=self._skipna_ensemble)
+
+
 class CRPSEnsemble(base.PerVariableMetric):
   """CRPS = E|X - Y| - 0.5 E|X - X'| for an ensemble prediction.
 
@@ -100,3 +152,77 @@ class CRPSEnsemble(base.PerVariableMetric):
 
   def _values_from_mean_statistics_per_variable(self, statistic_values):
     return statistic_values['CRPSSkill'] - 0.5 * statistic_values['CRPSSpread']
+
+
+class UnbiasedEnsembleMeanRMSE(base.PerVariableMetric):
+  """Square root of the unbiased ensemble mean MSE (probabilistic.py:864-894)."""
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM,
+               skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def statistics(self) -> Mapping[str, base.Statistic]:
+    return {
+        'UnbiasedEnsembleMeanSquaredError': UnbiasedEnsembleMeanSquaredError(
+            ensemble_dim=self._ensemble_dim,
+            skipna_ensemble=self._skipna_ensemble),
+    }
+
+  def _values_from_mean_statistics_per_variable(self, statistic_values):
+    return np.sqrt(statistic_values['UnbiasedEnsembleMeanSquaredError'])
+
+
+def SpreadSkillRatio(**unused_kwargs):  # pylint: disable=invalid-name
+  """Refuses like the reference (probabilistic.py:897-902)."""
+  raise ValueError(
+      'SpreadSkillRatio is not supported (the reference withdrew it as '
+      'incorrectly implemented); use UnbiasedSpreadSkillRatio instead.')
+
+
+class UnbiasedSpreadSkillRatio(base.PerVariableMetric):
+  """sqrt(mean ensemble variance / unbiased ensemble mean MSE).
+
+  Reference: probabilistic.py:905-967.
+  """
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM,
+               skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def statistics(self) -> Mapping[str, base.Statistic]:
+    return {
+        'EnsembleVariance': EnsembleVariance(
+            ensemble_dim=self._ensemble_dim,
+            skipna_ensemble=self._skipna_ensemble),
+        'UnbiasedEnsembleMeanSquaredError': UnbiasedEnsembleMeanSquaredError(
+            ensemble_dim=self._ensemble_dim,
+            skipna_ensemble=self._skipna_ensemble),
+    }
+
+  def _values_from_mean_statistics_per_variable(self, statistic_values):
+    return np.sqrt(statistic_values['EnsembleVariance'] /
+                     statistic_values['UnbiasedEnsembleMeanSquaredError'])
+
+
+class EnsembleRootMeanVariance(base.PerVariableMetric):
+  """Square root of the mean ensemble variance (probabilistic.py:970-1005)."""
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM,
+               skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def statistics(self) -> Mapping[str, base.Statistic]:
+    return {
+        'EnsembleVariance': EnsembleVariance(
+            ensemble_dim=self._ensemble_dim,
+            skipna_ensemble=self._skipna_ensemble),
+    }
+
+  def _values_from_mean_statistics_per_variable(self, statistic_values):
+    return np.sqrt(statistic_values['EnsembleVariance'])
