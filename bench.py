@@ -422,6 +422,29 @@ def run_suite(ctx, dev, peak):
                    'peak': peak, 'unit': 'GB/s',
                    'frac': pts * bpp / (kms * 1e-3) / 1e9 / peak,
                    'algorithmic_bytes_per_point': bpp}}
+  for key, metrics, what in (
+      ('ens_moments_c3',
+       {'ssr': probabilistic.UnbiasedSpreadSkillRatio(),
+        'rmse': probabilistic.UnbiasedEnsembleMeanRMSE()},
+       'UnbiasedSpreadSkillRatio + UnbiasedEnsembleMeanRMSE (ensemble '
+       'variance and unbiased ensemble-mean MSE; moments-only launch)'),
+      ('crps_ssr_c3',
+       {'crps': probabilistic.CRPSEnsemble(use_sort=True),
+        'ssr': probabilistic.UnbiasedSpreadSkillRatio()},
+       'CRPSEnsemble(use_sort=True) + UnbiasedSpreadSkillRatio, all four '
+       'ensemble statistics from one read of the ensemble')):
+    step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
+        metrics, aggregator, preds, tgts)
+    ms, kms, kn = timed(step, 3)
+    out[key] = {
+        'workload': what + ', same data as crps_c3',
+        'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+        'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+        'roofline': {'bound': 'hbm',
+                     'achieved': pts * bpp / (kms * 1e-3) / 1e9,
+                     'peak': peak, 'unit': 'GB/s',
+                     'frac': pts * bpp / (kms * 1e-3) / 1e9 / peak,
+                     'algorithmic_bytes_per_point': bpp}}
   del preds, tgts, metrics, step
   torch.cuda.empty_cache()
 

@@ -200,19 +200,20 @@ int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
  * Results: sum_ws[c*4 + s], sum_w[c*4 + s] with s = 0 CRPSSkill, 1 CRPSSpread,
  * 2 EnsembleVariance (ddof = 1, probabilistic.py:250-273), 3
  * UnbiasedEnsembleMeanSquaredError ((mean - y)^2 - variance / n, :276-336).
- * n_members < 2 without WBX_CRPS_SKIPNA_ENSEMBLE is an error
- * (probabilistic.py:210-212) unless WBX_CRPS_NO_SPREAD says the caller will
- * not read the spread slot (variance / unbiased MSE are then NaN, as NumPy's).
+ * stat_mask (bit s = slot s, 0 = all four) says which slots the caller reads:
+ * a launch skips the pair / sort work when only the moments are wanted and the
+ * moment passes when only CRPS is; slots outside the mask are unspecified.
+ * n_members < 2 without WBX_CRPS_SKIPNA_ENSEMBLE is an error when slot 1 is
+ * requested (probabilistic.py:210-212); variance / unbiased MSE of a single
+ * member are NaN, as NumPy's.
  */
 enum {
   WBX_CRPS_FAIR = 256,            /* divide by M(M-1) instead of M^2          */
   WBX_CRPS_SKIPNA_ENSEMBLE = 512, /* NaN members are missing members          */
-  WBX_CRPS_USE_SORT = 1024,       /* sort/PWM estimator (probabilistic.py:
+  WBX_CRPS_USE_SORT = 1024        /* sort/PWM estimator (probabilistic.py:
                                      214-240) in a register sorting network;
                                      honoured for n_members <= 64, the pair
                                      sum is used otherwise                    */
-  WBX_CRPS_NO_SPREAD = 2048       /* slot 1 is not needed: skip the
-                                     n_members >= 2 check                     */
 };
 
 typedef struct wbx_crps_plan wbx_crps_plan;
@@ -233,6 +234,8 @@ typedef struct {
   const double* w_outer;   /* [n_jobs] or NULL                                */
   const double* w_y;       /* [ny] or NULL                                    */
   const double* w_x;       /* [nx] or NULL                                    */
+  int32_t stat_mask;       /* bit s = slot s is wanted; 0 = all               */
+  int32_t reserved;
 } wbx_crps_desc;
 
 int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* desc,

@@ -360,9 +360,18 @@ def test_single_member_variance_is_nan_and_spread_raises():
       {'spread': probabilistic.EnsembleRootMeanVariance()}, {'t': X}, {'t': Y},
       ['latitude', 'longitude'])
   assert np.isnan(values['spread.t'].values)
-  with pytest.raises(ValueError, match='n_ensemble < 2'):
+  with pytest.raises(ValueError, match='Failed to compute') as err:
     compute_all_metrics({'crps': probabilistic.CRPSEnsemble()}, {'t': X},
                         {'t': Y}, ['latitude', 'longitude'])
+  assert 'n_ensemble < 2' in str(err.value.__cause__)
+  # the C ABI refuses the spread slot of a single member as well
+  with pytest.raises(ValueError, match='n_ensemble < 2'):
+    _cabi.CrpsPlan(
+        _cabi.get_context(), space=_cabi.SPACE_HOST, flags=_cabi.CRPS_FAIR,
+        ny=4, nx=8, n_members=1, member_stride=32, point_stride=1,
+        ens=np.array([x.ctypes.data], np.uint64),
+        target=np.array([y.ctypes.data], np.uint64),
+        cell=np.zeros(1, np.int32), n_cells=1, stat_mask=0b0011)
   with pytest.raises(ValueError, match='UnbiasedSpreadSkillRatio'):
     probabilistic.SpreadSkillRatio(ensemble_dim='number')
 

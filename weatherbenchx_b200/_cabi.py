@@ -88,7 +88,6 @@ class GenericDesc(ctypes.Structure):
 
 
 CRPS_FAIR, CRPS_SKIPNA_ENSEMBLE, CRPS_USE_SORT = 256, 512, 1024
-CRPS_NO_SPREAD = 2048
 
 
 class CrpsDesc(ctypes.Structure):
@@ -102,6 +101,7 @@ class CrpsDesc(ctypes.Structure):
       ('mask', POINTER(c_uint64)), ('cell', POINTER(c_int32)),
       ('w_outer', POINTER(c_double)), ('w_y', POINTER(c_double)),
       ('w_x', POINTER(c_double)),
+      ('stat_mask', c_int32), ('reserved', c_int32),
   ]
 
 
@@ -380,7 +380,8 @@ class CrpsPlan:
                ens: np.ndarray, target: np.ndarray, cell: np.ndarray,
                n_cells: int, mask: np.ndarray | None = None,
                w_outer: np.ndarray | None = None,
-               w_y: np.ndarray | None = None, w_x: np.ndarray | None = None):
+               w_y: np.ndarray | None = None, w_x: np.ndarray | None = None,
+               stat_mask: int = 0):
     self.ctx = ctx
     self.n_cells = int(n_cells)
     keep = []
@@ -410,7 +411,7 @@ class CrpsPlan:
         ens=_as_ptr(ens, c_uint64), target=_as_ptr(target, c_uint64),
         mask=_as_ptr(mask, c_uint64), cell=_as_ptr(cell, c_int32),
         w_outer=_as_ptr(w_outer, c_double), w_y=_as_ptr(w_y, c_double),
-        w_x=_as_ptr(w_x, c_double))
+        w_x=_as_ptr(w_x, c_double), stat_mask=stat_mask)
     handle = c_void_p()
     code = ctx.lib.wbx_crps_plan_create(ctx.handle, ctypes.byref(desc),
                                         ctypes.byref(handle))

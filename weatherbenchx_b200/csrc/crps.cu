@@ -150,6 +150,8 @@ __device__ __forceinline__ void crps_point(const float* __restrict__ xs,
 }
 
 constexpr int kCrpsStats = 4;  // skill, spread, variance, unbiased MSE
+// what a launch evaluates (template parameter WHAT): slots 0-1 and / or 2-3.
+constexpr int kWantCrps = 1, kWantMoments = 2;
 constexpr int kCrpsAcc = 2 * kCrpsStats;  // + one weight sum per statistic
 
 __device__ __forceinline__ void crps_accumulate(const float (&v)[kCrpsStats],
@@ -164,7 +166,7 @@ __device__ __forceinline__ void crps_accumulate(const float (&v)[kCrpsStats],
   }
 }
 
-template <bool ENS_SKIPNA, bool MASK>
+template <bool ENS_SKIPNA, bool MASK, int WHAT>
 __global__ void __launch_bounds__(kCrpsThreads)
     crps_reduce_kernel(const CrpsParams P) {
   extern __shared__ float smem[];
@@ -231,11 +233,13 @@ __global__ void __launch_bounds__(kCrpsThreads)
     }
     __syncthreads();
     if (tid < len) {
-      float v[kCrpsStats];
-      crps_point<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], P.fair, &v[0],
-                             &v[1]);
-      ensemble_moments<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], &v[2],
-                                   &v[3]);
+      float v[kCrpsStats] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (WHAT & kWantCrps)
+        crps_point<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], P.fair, &v[0],
+                               &v[1]);
+      if constexpr (WHAT & kWantMoments)
+        ensemble_moments<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], &v[2],
+                                     &v[3]);
       const unsigned e = static_cast<unsigned>(e0 + tid);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
@@ -282,7 +286,7 @@ struct CrpsStageMeta {
   double wo;
 };
 
-template <bool ENS_SKIPNA, bool MASK>
+template <bool ENS_SKIPNA, bool MASK, int WHAT>
 __global__ void __launch_bounds__(kCrpsTmaThreads)
     crps_reduce_tma_kernel(const CrpsParams P) {
   extern __shared__ __align__(128) unsigned char crps_smem[];
@@ -381,10 +385,14 @@ __global__ void __launch_bounds__(kCrpsTmaThreads)
     const unsigned char* st = crps_smem + s * stage_stride;
     const float* xs = reinterpret_cast<const float*>(st);
     if (tid < mt.len) {
-      float v[kCrpsStats];
+      float v[kCrpsStats] = {0.f, 0.f, 0.f, 0.f};
       const float yv = xs[M * kCrpsThreads + tid];
-      crps_point<ENS_SKIPNA>(xs + tid, kCrpsThreads, M, yv, P.fair, &v[0], &v[1]);
-      ensemble_moments<ENS_SKIPNA>(xs + tid, kCrpsThreads, M, yv, &v[2], &v[3]);
+      if constexpr (WHAT & kWantCrps)
+        crps_point<ENS_SKIPNA>(xs + tid, kCrpsThreads, M, yv, P.fair, &v[0],
+                               &v[1]);
+      if constexpr (WHAT & kWantMoments)
+        ensemble_moments<ENS_SKIPNA>(xs + tid, kCrpsThreads, M, yv, &v[2],
+                                     &v[3]);
       const unsigned e = static_cast<unsigned>(mt.e0 + tid);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
@@ -475,7 +483,7 @@ __device__ __forceinline__ void sort_network(float (&x)[MAXM]) {
 // MFIX > 0 fixes the member count at compile time: the +inf padding lanes
 // become constants, ptxas folds every compare-exchange that touches them and
 // the network shrinks to the size of the real ensemble (M = 50: 64 -> 50 wires).
-template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MASK>
+template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MASK, bool MOMENTS>
 __global__ void __launch_bounds__(kCrpsThreads)
     crps_sort_kernel(const CrpsParams P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -530,24 +538,29 @@ __global__ void __launch_bounds__(kCrpsThreads)
           n_nan += isn ? 1 : 0;
           const float d = fabsf(x[m] - y);
           sk += (ENS_SKIPNA && isn) ? 0.f : d;
-          msum += (ENS_SKIPNA && isn) ? 0.f : x[m];
+          if constexpr (MOMENTS) msum += (ENS_SKIPNA && isn) ? 0.f : x[m];
+          if constexpr (!MOMENTS) {
+            if (isn) x[m] = inf;
+          }
         }
       }
-      const float fnm = static_cast<float>(ENS_SKIPNA ? (M - n_nan) : M);
-      const float mean = __fdiv_rn(msum, fnm);
-      float ss = 0.f;
+      float v[kCrpsStats] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (MOMENTS) {
+        const float fnm = static_cast<float>(ENS_SKIPNA ? (M - n_nan) : M);
+        const float mean = __fdiv_rn(msum, fnm);
+        float ss = 0.f;
 #pragma unroll
-      for (int m = 0; m < MAXM; ++m) {
-        if (m < M) {
-          const bool isn = !(x[m] == x[m]);
-          const float d = x[m] - mean;
-          ss = __fadd_rn(ss, (ENS_SKIPNA && isn) ? 0.f : __fmul_rn(d, d));
-          if (isn) x[m] = inf;
+        for (int m = 0; m < MAXM; ++m) {
+          if (m < M) {
+            const bool isn = !(x[m] == x[m]);
+            const float d = x[m] - mean;
+            ss = __fadd_rn(ss, (ENS_SKIPNA && isn) ? 0.f : __fmul_rn(d, d));
+            if (isn) x[m] = inf;
+          }
         }
+        v[2] = __fdiv_rn(ss, fnm - 1.f);
+        v[3] = __fsub_rn(__fmul_rn(mean - y, mean - y), __fdiv_rn(v[2], fnm));
       }
-      float v[kCrpsStats];
-      v[2] = __fdiv_rn(ss, fnm - 1.f);
-      v[3] = __fsub_rn(__fmul_rn(mean - y, mean - y), __fdiv_rn(v[2], fnm));
       sort_network<MAXM>(x);
       const int n = ENS_SKIPNA ? (M - n_nan) : M;
       const float c = x[0];
@@ -695,6 +708,7 @@ struct wbx_crps_plan {
   int tiles_per_slab = 0;
   size_t smem_bytes = 0;
   bool use_sort = false;  // register sorting network (n_members <= 64)
+  int what = 3;           // kWantCrps | kWantMoments
   bool tma_ok = false;    // TMA-staged pair kernel allowed (alignment, size)
   size_t smem_plain = 0;  // shared memory of the non-TMA pair kernel
   wbx::DevBuf tables, weights;
@@ -715,21 +729,27 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
   const bool ens_skipna = (plan->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
+  const int what = plan->what;
   if (plan->use_sort) {
-#define WBX_SORT_LAUNCH(MAXM, MFIX)                                            \
+#define WBX_SORT_LAUNCH2(MAXM, MFIX, MOM)                                      \
   do {                                                                         \
     if (ens_skipna && plan->has_mask)                                          \
-      crps_sort_kernel<MAXM, MFIX, true, true>                                 \
+      crps_sort_kernel<MAXM, MFIX, true, true, MOM>                            \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
     else if (ens_skipna)                                                       \
-      crps_sort_kernel<MAXM, MFIX, true, false>                                \
+      crps_sort_kernel<MAXM, MFIX, true, false, MOM>                           \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
     else if (plan->has_mask)                                                   \
-      crps_sort_kernel<MAXM, MFIX, false, true>                                \
+      crps_sort_kernel<MAXM, MFIX, false, true, MOM>                           \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
     else                                                                       \
-      crps_sort_kernel<MAXM, MFIX, false, false>                               \
+      crps_sort_kernel<MAXM, MFIX, false, false, MOM>                          \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+  } while (0)
+#define WBX_SORT_LAUNCH(MAXM, MFIX)                                            \
+  do {                                                                         \
+    if (what & kWantMoments) WBX_SORT_LAUNCH2(MAXM, MFIX, true);               \
+    else WBX_SORT_LAUNCH2(MAXM, MFIX, false);                                  \
   } while (0)
     // the common operational ensemble sizes get a pruned network
     if (plan->n_members == 50) WBX_SORT_LAUNCH(64, 50);
@@ -739,25 +759,32 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
     else if (plan->n_members <= 32) WBX_SORT_LAUNCH(32, 0);
     else WBX_SORT_LAUNCH(64, 0);
 #undef WBX_SORT_LAUNCH
+#undef WBX_SORT_LAUNCH2
     WBX_CUDA(cudaGetLastError());
     ctx->launches++;
     return ctx->prof_end();
   }
-#define WBX_CRPS_LAUNCH(A, B)                                                  \
+#define WBX_CRPS_LAUNCH3(A, B, W)                                              \
   do {                                                                         \
     if (use_tma) {                                                             \
-      auto kern = crps_reduce_tma_kernel<A, B>;                                \
+      auto kern = crps_reduce_tma_kernel<A, B, W>;                             \
       WBX_CUDA(cudaFuncSetAttribute(                                           \
           kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
           static_cast<int>(plan->smem_bytes)));                                \
       kern<<<grid, kCrpsTmaThreads, plan->smem_bytes, ctx->stream>>>(P);       \
     } else {                                                                   \
-      auto kern = crps_reduce_kernel<A, B>;                                    \
+      auto kern = crps_reduce_kernel<A, B, W>;                                 \
       WBX_CUDA(cudaFuncSetAttribute(                                           \
           kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
           static_cast<int>(plan->smem_bytes)));                                \
       kern<<<grid, kCrpsThreads, plan->smem_bytes, ctx->stream>>>(P);          \
     }                                                                          \
+  } while (0)
+#define WBX_CRPS_LAUNCH(A, B)                                                  \
+  do {                                                                         \
+    if (what == kWantCrps) WBX_CRPS_LAUNCH3(A, B, 1);                          \
+    else if (what == kWantMoments) WBX_CRPS_LAUNCH3(A, B, 2);                  \
+    else WBX_CRPS_LAUNCH3(A, B, 3);                                            \
   } while (0)
   // host-space chunks are staged member-major and aligned, so they take the
   // TMA path whenever the plan allows it.
@@ -768,6 +795,7 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
   else if (plan->has_mask) WBX_CRPS_LAUNCH(false, true);
   else WBX_CRPS_LAUNCH(false, false);
 #undef WBX_CRPS_LAUNCH
+#undef WBX_CRPS_LAUNCH3
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   return ctx->prof_end();
@@ -889,7 +917,9 @@ int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* d,
   WBX_REQUIRE(d->ny >= 1 && d->nx >= 1 && d->ny * d->nx < (1ll << 30),
               "crps: bad slab shape");
   const bool ens_skipna = (d->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
-  if (!ens_skipna && d->n_members < 2 && !(d->flags & WBX_CRPS_NO_SPREAD)) {
+  const int stat_mask = d->stat_mask ? d->stat_mask : 15;
+  WBX_REQUIRE(stat_mask > 0 && stat_mask < 16, "crps: bad stat_mask");
+  if (!ens_skipna && d->n_members < 2 && (stat_mask & 2)) {
     wbx::set_error("Cannot estimate CRPS spread with n_ensemble < 2.");
     return WBX_ERR_INVALID;  // probabilistic.py:210-212
   }
@@ -954,7 +984,12 @@ int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* d,
   p->smem_bytes = static_cast<size_t>(d->n_members) * wbx::kCrpsPitch * 4 +
                   wbx::kCrpsThreads * 4 + wbx::kCrpsThreads + 64;
   p->smem_plain = p->smem_bytes;
-  p->use_sort = (d->flags & WBX_CRPS_USE_SORT) != 0 && d->n_members <= 64;
+  p->what = ((stat_mask & 3) ? wbx::kWantCrps : 0) |
+            ((stat_mask & 12) ? wbx::kWantMoments : 0);
+  // moments alone need no sorted sample: the (then HBM-bound) pair-kernel
+  // skeleton serves them.
+  p->use_sort = (d->flags & WBX_CRPS_USE_SORT) != 0 && d->n_members <= 64 &&
+                (p->what & wbx::kWantCrps);
   {
     // TMA variant: member-major rows, everything 16-byte aligned.
     const size_t stage =

@@ -747,6 +747,7 @@ class CrpsSpec:
   """Everything wbx_crps_plan_create needs, plus result labelling."""
   space: int
   flags: int
+  stat_mask: int
   ny: int
   nx: int
   n_members: int
@@ -892,8 +893,9 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
     flags |= _cabi.CRPS_SKIPNA_ENSEMBLE
   if use_sort:
     flags |= _cabi.CRPS_USE_SORT
-  if fair is None:  # no CRPSSpread in this launch
-    flags |= _cabi.CRPS_NO_SPREAD
+  stat_mask = 0
+  for s in stats:
+    stat_mask |= 1 << CRPS_SLOT[s.kind]
 
   def addresses(op):
     off = _job_offsets(job_dims, job_sizes, op.strides)
@@ -905,7 +907,7 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
     if name not in coords and name != 'mask' and set(cv.dims) <= set(kept):
       coords[name] = cv
   cache_key = (
-      'crps', space, flags, tuple(dims), tuple(sizes[d] for d in dims),
+      'crps', space, flags, stat_mask, tuple(dims), tuple(sizes[d] for d in dims),
       tuple(inner), tuple(sorted(reduce_set, key=str)), first.n_members,
       op_e.ptr, tuple(op_e.strides.items()), op_t.ptr,
       tuple(op_t.strides.items()),
@@ -913,7 +915,8 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
       tuple((str(d), v.tobytes()) for d, v in sorted(
           per_dim.items(), key=lambda kv: str(kv[0]))))
   return CrpsSpec(
-      space=space, flags=flags, ny=ny, nx=nx, n_members=first.n_members,
+      space=space, flags=flags, stat_mask=stat_mask, ny=ny, nx=nx,
+      n_members=first.n_members,
       member_stride=int(member_stride), point_stride=int(point_stride),
       n_cells=n_cells, ens=addresses(op_e), target=addresses(op_t),
       mask=addresses(op_m) if op_m is not None else None,
@@ -940,7 +943,8 @@ def aggregate_crps(stats, reduce_dims, weights=(), masked=False, skipna=False,
         n_members=spec.n_members, member_stride=spec.member_stride,
         point_stride=spec.point_stride, ens=spec.ens, target=spec.target,
         mask=spec.mask, cell=spec.cell, n_cells=spec.n_cells,
-        w_outer=spec.w_outer, w_y=spec.w_y, w_x=spec.w_x)
+        w_outer=spec.w_outer, w_y=spec.w_y, w_x=spec.w_x,
+        stat_mask=spec.stat_mask)
     _PLAN_CACHE[spec.cache_key] = plan
     while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
       _, old = _PLAN_CACHE.popitem(last=False)
