@@ -180,7 +180,19 @@ int wbx_det_reduce(wbx_ctx* ctx, const wbx_det_desc* desc, double* sum_ws,
 /* Per-gridpoint statistic values (what Statistic.compute returns when a
  * caller really wants the full field, metrics/base.py:135-158).  n float32
  * elements, device pointers, contiguous; clim may be NULL for stats 0..2.
- * Bit-identical to NumPy float32 arithmetic. */
+ * Bit-identical to NumPy float32 arithmetic.  `stat` is a WBX_STAT_* slot or
+ * one of the elementwise-only codes below, optionally OR-ed with
+ * WBX_EW_ACCUMULATE (out[i] = out[i] + value: the second term of
+ * WindVectorSquaredError, deterministic.py:206-219). */
+enum {
+  WBX_EW_PASS_PRED = 16,            /* value = pred  (Prediction/Target-
+                                       Passthrough, deterministic.py:126-171;
+                                       pass the targets as `pred` for the
+                                       target flavour)                         */
+  WBX_EW_PASS_PRED_NAN_TARGET = 17, /* value = pred, NaN where target is NaN
+                                       (copy_nans_from_targets=True)           */
+  WBX_EW_ACCUMULATE = 256
+};
 int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
                         const float* target, const float* clim, int64_t n,
                         float* out);
@@ -263,6 +275,15 @@ typedef struct {
   float* variance;       /* optional extra outputs [n_points], may be NULL     */
   float* unbiased_mse;
 } wbx_crps_point_desc;
+
+/* Ensemble mean per grid point (wrappers.EnsembleMean.transform_fn,
+ * metrics/wrappers.py:145-148): out[pt] = mean over members, members summed in
+ * index order in float32 as NumPy does for a non-trailing axis; with
+ * WBX_CRPS_SKIPNA_ENSEMBLE NaN members are skipped (nanmean).  Uses ndim, flags,
+ * n_members, member_stride, size, ens_stride and ens of the descriptor; out is
+ * contiguous float32 [n_points] on the device. */
+int wbx_ensemble_mean(wbx_ctx* ctx, const wbx_crps_point_desc* desc,
+                      float* out);
 
 int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* desc,
                        float* skill, float* spread);

@@ -418,6 +418,30 @@ def unbiased_ensemble_mean_squared_error(
     return (mean - y) ** 2 - var / n
 
 
+def ensemble_mean(x: np.ndarray, ens_axis: int,
+                  skipna: bool = False) -> np.ndarray:
+  """wrappers.EnsembleMean.transform_fn (wrappers.py:145-148):
+  da.mean(ensemble_dim, skipna=skipna)."""
+  with np.errstate(all='ignore'), warnings.catch_warnings():
+    warnings.simplefilter('ignore')
+    return (np.nanmean if skipna else np.mean)(x, axis=ens_axis)
+
+
+def wind_vector_squared_error(pu, tu, pv, tv) -> np.ndarray:
+  """WindVectorSquaredError.compute (deterministic.py:211-218)."""
+  return (pu - tu) ** 2 + (pv - tv) ** 2
+
+
+def passthrough(source: np.ndarray, other: np.ndarray,
+                copy_nans: bool = False) -> np.ndarray:
+  """Prediction/TargetPassthrough (deterministic.py:138-147,162-171):
+  source + zeros_like(other), optionally NaN wherever ``other`` is NaN."""
+  result = source + np.zeros_like(other)
+  if copy_nans:
+    result = np.where(~np.isnan(other), result, np.nan).astype(result.dtype)
+  return result
+
+
 def crps_spread_brute_force(x: np.ndarray, ens_axis: int, fair: bool):
   """metrics/metrics_test.py:603-608 -- the reference's own brute force."""
   m = x.shape[ens_axis]

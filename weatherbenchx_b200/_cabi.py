@@ -88,6 +88,8 @@ class GenericDesc(ctypes.Structure):
 
 
 CRPS_FAIR, CRPS_SKIPNA_ENSEMBLE, CRPS_USE_SORT = 256, 512, 1024
+# elementwise-only statistic codes of wbx_det_elementwise
+EW_PASS_PRED, EW_PASS_PRED_NAN_TARGET, EW_ACCUMULATE = 16, 17, 256
 
 
 class CrpsDesc(ctypes.Structure):
@@ -160,6 +162,7 @@ SIGNATURES = {
                                   c_int32, c_int32]),
     'wbx_crps_pointwise': (c_int, [c_void_p, POINTER(CrpsPointDesc), c_void_p,
                                    c_void_p]),
+    'wbx_ensemble_mean': (c_int, [c_void_p, POINTER(CrpsPointDesc), c_void_p]),
     'wbx_zonal_spectrum': (c_int, [c_void_p, POINTER(SpectrumDesc)]),
     'wbx_reduce_generic': (c_int, [c_void_p, POINTER(GenericDesc), c_void_p,
                                    c_void_p, c_int32]),

@@ -24,6 +24,7 @@ from weatherbenchx_b200 import engine
 from weatherbenchx_b200 import xarray_lite as xl
 from weatherbenchx_b200 import xarray_tree
 from weatherbenchx_b200.lazy import LazyStatistic
+from weatherbenchx_b200.lazy import LazySumStatistic
 from weatherbenchx_b200.metrics import base as metrics_base
 
 
@@ -250,7 +251,11 @@ class Aggregator:
   def aggregate_stat_var(self, stat: xl.DataArray) -> AggregationState | None:
     """Aggregates one statistic DataArray of one variable."""
     stat = xl.as_data_array(stat)
-    if isinstance(stat, LazyStatistic) and stat.is_lazy:
+    if (isinstance(stat, LazySumStatistic) and stat.is_lazy and
+        not self.skipna):
+      return _add_states([self.aggregate_stat_var(p) for p in stat.parts])
+    if (isinstance(stat, LazyStatistic) and stat.is_lazy and
+        not isinstance(stat, LazySumStatistic)):
       try:
         return self._fused_group([stat])[stat.kind]
       except engine.FastPathUnavailable:
@@ -277,12 +282,26 @@ class Aggregator:
     """
     results: dict = {name: {} for name in statistics}
     groups: dict = collections.defaultdict(list)
+    sums = []  # (stat_name, var, n_parts) of LazySumStatistic members
     for stat_name, per_var in statistics.items():
       for var, stat in per_var.items():
         if stat is None:
           continue
         stat = xl.as_data_array(stat)
-        if isinstance(stat, LazyStatistic) and stat.is_lazy:
+        if isinstance(stat, LazySumStatistic) and stat.is_lazy:
+          if self.skipna:
+            # NaN of the SUM decides what is skipped: needs the summed field
+            results[stat_name][var] = self._aggregate_generic(stat)
+            continue
+          # the parts join the launches of their own operands (shared with
+          # e.g. the per-component SquaredError); states are added afterwards
+          for i, part in enumerate(stat.parts):
+            key = ('__part__', stat_name, var, i)
+            results[key] = {}
+            pvar = getattr(part, 'var', var)
+            groups[(pvar,) + part.group_key()[:2]].append((key, var, part))
+          sums.append((stat_name, var, len(stat.parts)))
+        elif isinstance(stat, LazyStatistic) and stat.is_lazy:
           groups[(var,) + stat.group_key()[:2]].append((stat_name, var, stat))
         else:
           results[stat_name][var] = self._aggregate_generic(stat)
@@ -358,12 +377,27 @@ class Aggregator:
       for (members, _, _), out in zip(planned, outs):
         for stat_name, var, s in members:
           results[stat_name][var] = AggregationState(*out[s.kind])
+    for stat_name, var, n_parts in sums:
+      results[stat_name][var] = _add_states(
+          [results[('__part__', stat_name, var, i)].get(var)
+           for i in range(n_parts)])
     sws, sw = {}, {}
     for stat_name in statistics:
       ok = {v: s for v, s in results[stat_name].items() if s is not None}
       sws[stat_name] = {v: s.sum_weighted_statistics for v, s in ok.items()}
       sw[stat_name] = {v: s.sum_weights for v, s in ok.items()}
     return AggregationState(sws, sw)
+
+
+def _add_states(states):
+  """State of a sum of statistics on one grid: the weighted sums add, the
+  weights are those of any part (None if a part is not defined)."""
+  if any(s is None for s in states):
+    return None
+  total = states[0].sum_weighted_statistics
+  for s in states[1:]:
+    total = total + s.sum_weighted_statistics
+  return AggregationState(total, states[0].sum_weights)
 
 
 def compute_metric_values_for_single_chunk(

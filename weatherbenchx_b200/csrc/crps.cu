@@ -683,16 +683,90 @@ __global__ void __launch_bounds__(kCrpsThreads)
   float* col = smem + tid;
   for (int m = 0; m < P.n_members; ++m)
     col[m * kCrpsPitch] = P.ens[eo + m * P.member_stride];
-  float skill, spread, variance, umse;
+  float skill = 0.f, spread = 0.f, variance = 0.f, umse = 0.f;
   const float yv = P.target[to];
-  crps_point<ENS_SKIPNA>(col, kCrpsPitch, P.n_members, yv, P.fair, &skill,
-                         &spread);
-  ensemble_moments<ENS_SKIPNA>(col, kCrpsPitch, P.n_members, yv, &variance,
-                               &umse);
+  if (P.skill || P.spread)
+    crps_point<ENS_SKIPNA>(col, kCrpsPitch, P.n_members, yv, P.fair, &skill,
+                           &spread);
+  if (P.variance || P.umse)
+    ensemble_moments<ENS_SKIPNA>(col, kCrpsPitch, P.n_members, yv, &variance,
+                                 &umse);
   if (P.skill) P.skill[pt] = skill;
   if (P.spread) P.spread[pt] = spread;
   if (P.variance) P.variance[pt] = variance;
   if (P.umse) P.umse[pt] = umse;
+}
+
+// ---------------------------------------------------------------------------
+// Ensemble mean field (wrappers.py:145-148).  One thread per VEC consecutive
+// points of the innermost dim; every member row it touches is a coalesced
+// 4*VEC-byte-per-lane load, 8 members in flight per thread.  HBM-bound:
+// 4*(M+1) B per point.
+// ---------------------------------------------------------------------------
+template <bool ENS_SKIPNA, int VEC>
+__global__ void __launch_bounds__(256)
+    ensemble_mean_kernel(const CrpsPointParams P, float* __restrict__ out) {
+  const long long g = blockIdx.x * 256ll + threadIdx.x;
+  const long long pt = g * VEC;
+  if (pt >= P.n_points) return;
+  long long rem = pt, eo = 0;
+  for (int d = P.ndim - 1; d >= 0; --d) {
+    const long long i = rem % P.size[d];
+    rem /= P.size[d];
+    eo += i * P.e_stride[d];
+  }
+  const float* __restrict__ src = P.ens + eo;
+  float sum[VEC], cnt[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) sum[v] = cnt[v] = 0.f;
+  auto add = [&](const float (&x)[VEC]) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      if (!ENS_SKIPNA || x[v] == x[v]) {
+        sum[v] += x[v];
+        cnt[v] += 1.f;
+      }
+    }
+  };
+  constexpr int kInFlight = 8;
+  const int M = P.n_members;
+  int m = 0;
+  for (; m + kInFlight <= M; m += kInFlight) {
+    float x[kInFlight][VEC];
+#pragma unroll
+    for (int k = 0; k < kInFlight; ++k) {
+      const float* q = src + (m + k) * P.member_stride;
+      if constexpr (VEC == 4) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(q));
+        x[k][0] = t.x; x[k][1] = t.y; x[k][2] = t.z; x[k][3] = t.w;
+      } else {
+        x[k][0] = __ldcs(q);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kInFlight; ++k) add(x[k]);
+  }
+  for (; m < M; ++m) {
+    float x[VEC];
+    const float* q = src + m * P.member_stride;
+    if constexpr (VEC == 4) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(q));
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+      x[0] = __ldcs(q);
+    }
+    add(x);
+  }
+  if constexpr (VEC == 4) {
+    float4 r;
+    r.x = __fdiv_rn(sum[0], cnt[0]);
+    r.y = __fdiv_rn(sum[1], cnt[1]);
+    r.z = __fdiv_rn(sum[2], cnt[2]);
+    r.w = __fdiv_rn(sum[3], cnt[3]);
+    *reinterpret_cast<float4*>(out + pt) = r;
+  } else {
+    out[pt] = __fdiv_rn(sum[0], cnt[0]);
+  }
 }
 
 }  // namespace wbx
@@ -1253,6 +1327,53 @@ int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* d,
     kern<<<static_cast<unsigned>(blocks), wbx::kCrpsThreads, smem,
            ctx->stream>>>(P);
   }
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return WBX_OK;
+}
+
+int wbx_ensemble_mean(wbx_ctx* ctx, const wbx_crps_point_desc* d, float* out) {
+  WBX_REQUIRE(ctx && d && out, "wbx_ensemble_mean: NULL argument");
+  WBX_REQUIRE(d->ndim >= 0 && d->ndim <= WBX_MAX_DIMS,
+              "wbx_ensemble_mean: bad ndim");
+  WBX_REQUIRE(d->ens, "wbx_ensemble_mean: NULL operand");
+  WBX_REQUIRE(d->n_members >= 1 && d->n_members < (1ll << 31),
+              "wbx_ensemble_mean: n_members out of range");
+  wbx::CrpsPointParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_points = 1;
+  for (int i = 0; i < d->ndim; ++i) {
+    WBX_REQUIRE(d->size[i] >= 1, "wbx_ensemble_mean: empty dim");
+    P.size[i] = d->size[i];
+    P.e_stride[i] = d->ens_stride[i];
+    P.n_points *= d->size[i];
+  }
+  P.ens = d->ens;
+  P.member_stride = d->member_stride;
+  P.ndim = d->ndim;
+  P.n_members = static_cast<int>(d->n_members);
+  // 4 points per thread when the innermost dim is dense and every row /
+  // member start stays 16-byte aligned
+  bool vec4 = d->ndim >= 1 && d->ens_stride[d->ndim - 1] == 1 &&
+              d->size[d->ndim - 1] % 4 == 0 && d->member_stride % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(d->ens) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (int i = 0; vec4 && i + 1 < d->ndim; ++i)
+    vec4 = d->ens_stride[i] % 4 == 0;
+  const bool ens_skipna = (d->flags & WBX_CRPS_SKIPNA_ENSEMBLE) != 0;
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  const long long threads = vec4 ? P.n_points / 4 : P.n_points;
+  const long long blocks = (threads + 255) / 256;
+  WBX_REQUIRE(blocks < (1ll << 31), "wbx_ensemble_mean: too many points");
+  const unsigned grid = static_cast<unsigned>(blocks);
+  if (vec4 && ens_skipna)
+    wbx::ensemble_mean_kernel<true, 4><<<grid, 256, 0, ctx->stream>>>(P, out);
+  else if (vec4)
+    wbx::ensemble_mean_kernel<false, 4><<<grid, 256, 0, ctx->stream>>>(P, out);
+  else if (ens_skipna)
+    wbx::ensemble_mean_kernel<true, 1><<<grid, 256, 0, ctx->stream>>>(P, out);
+  else
+    wbx::ensemble_mean_kernel<false, 1><<<grid, 256, 0, ctx->stream>>>(P, out);
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   return WBX_OK;

@@ -797,9 +797,13 @@ int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
                         const float* target, const float* clim, int64_t n,
                         float* out) {
   WBX_REQUIRE(ctx && pred && target && out, "wbx_det_elementwise: NULL argument");
-  WBX_REQUIRE(stat >= 0 && stat < WBX_NUM_DET_STATS,
+  const int code = stat & 0xff;
+  WBX_REQUIRE(stat >= 0 && (stat & ~(0xff | WBX_EW_ACCUMULATE)) == 0 &&
+                  (code < WBX_NUM_DET_STATS || code == WBX_EW_PASS_PRED ||
+                   code == WBX_EW_PASS_PRED_NAN_TARGET),
               "wbx_det_elementwise: bad statistic %d", stat);
-  WBX_REQUIRE(stat < WBX_STAT_SQ_PRED_ANOM || clim != nullptr,
+  WBX_REQUIRE(code < WBX_STAT_SQ_PRED_ANOM || code >= WBX_NUM_DET_STATS ||
+                  clim != nullptr,
               "wbx_det_elementwise: statistic %d needs a climatology", stat);
   WBX_REQUIRE(n >= 0, "wbx_det_elementwise: negative n");
   if (n == 0) return WBX_OK;

@@ -893,18 +893,23 @@ __global__ void __launch_bounds__(128) det_finalize_kernel(
 // ---------------------------------------------------------------------------
 // Per-gridpoint statistic values (materialised Statistic.compute output).
 // ---------------------------------------------------------------------------
-__global__ void det_elementwise_kernel(const int stat,
+__global__ void det_elementwise_kernel(const int stat_and_flags,
                                        const float* __restrict__ p,
                                        const float* __restrict__ t,
                                        const float* __restrict__ c,
-                                       const long long n,
-                                       float* __restrict__ out) {
+                                       const long long n, float* out) {
+  const int stat = stat_and_flags & 0xff;
+  const bool add = (stat_and_flags & WBX_EW_ACCUMULATE) != 0;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
        i < n; i += stride) {
     const float pv = p[i], tv = t[i];
     float r;
     switch (stat) {
+      case WBX_EW_PASS_PRED: r = pv; break;
+      case WBX_EW_PASS_PRED_NAN_TARGET:
+        r = (tv == tv) ? pv : __int_as_float(0x7fc00000);
+        break;
       case WBX_STAT_ERROR: r = __fsub_rn(pv, tv); break;
       case WBX_STAT_ABS_ERROR: r = fabsf(__fsub_rn(pv, tv)); break;
       case WBX_STAT_SQ_ERROR: {
@@ -928,7 +933,7 @@ __global__ void det_elementwise_kernel(const int stat,
         break;
       }
     }
-    out[i] = r;
+    out[i] = add ? __fadd_rn(out[i], r) : r;
   }
 }
 

@@ -705,6 +705,9 @@ def materialize(stat: LazyStatistic, device: int | None = None):
   """Evaluates the statistic per grid point on the GPU; returns a CUDA tensor."""
   if stat.kind in CRPS_SLOT:
     return materialize_crps(stat, device)
+  parts = getattr(stat, 'parts', None)
+  if parts is not None:  # sum of statistics (WindVectorSquaredError)
+    return materialize_sum(stat, device)
   torch = _torch()
   dims, sizes = stat.dims, stat.sizes
   p = _broadcast_device(stat.predictions, dims, sizes, device)
@@ -732,6 +735,125 @@ def materialize(stat: LazyStatistic, device: int | None = None):
                         t.data_ptr(), c.data_ptr() if c is not None else None,
                         out.numel(), out.data_ptr())
   return out
+
+
+def materialize_sum(stat, device: int | None = None):
+  """Field of a LazySumStatistic: the parts are added in order in float32,
+  out = ((part0) + part1) + ..., each term accumulated by the elementwise
+  kernel (deterministic.py:216-218 for the wind vector)."""
+  torch = _torch()
+  dims, sizes = stat.dims, stat.sizes
+  out = None
+  for i, part in enumerate(stat.parts):
+    if part.kind not in _cabi.STAT_SLOT or part.climatology is not None:
+      raise NotImplementedError(f'sum of {part.kind} statistics')
+    p = _broadcast_device(part.predictions, dims, sizes, device)
+    t = _broadcast_device(part.targets, dims, sizes, device)
+    if out is None:
+      out = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+    ctx = _cabi.get_context(p.device.index)
+    ctx.use_torch_stream()
+    _cabi.det_elementwise(
+        ctx, _cabi.STAT_SLOT[part.kind] | (_cabi.EW_ACCUMULATE if i else 0),
+        p.data_ptr(), t.data_ptr(), None, out.numel(), out.data_ptr())
+  return out
+
+
+_ZERO_SLABS: dict = {}
+
+
+def zero_slab(dims, shape, device=None) -> xl.DataArray:
+  """A shared float32 zero array (host ndarray if device is None)."""
+  key = (tuple(dims), tuple(shape), str(device))
+  hit = _ZERO_SLABS.get(key)
+  if hit is None:
+    if device is None:
+      payload = np.zeros(shape, np.float32)
+    else:
+      payload = _torch().zeros(shape, dtype=_torch().float32, device=device)
+    hit = xl.DataArray(payload, tuple(dims))
+    if len(_ZERO_SLABS) > 16:
+      _ZERO_SLABS.clear()
+    _ZERO_SLABS[key] = hit
+  return hit
+
+
+def passthrough(source: xl.DataArray, other: xl.DataArray,
+                copy_nans: bool = True,
+                device: int | None = None) -> xl.DataArray:
+  """``source + zeros_like(other)``, with NaN wherever ``other`` is NaN if
+  ``copy_nans`` (Prediction/TargetPassthrough, deterministic.py:143-147,
+  167-171), evaluated eagerly by the elementwise kernel."""
+  torch = _torch()
+  dims = source.dims + tuple(d for d in other.dims if d not in source.dims)
+  sizes = dict(other.sizes, **source.sizes)
+  a = _broadcast_device(source, dims, sizes, device)
+  b = _broadcast_device(other, dims, sizes, device)
+  out = torch.empty(a.shape, dtype=torch.float32, device=a.device)
+  ctx = _cabi.get_context(a.device.index)
+  ctx.use_torch_stream()
+  _cabi.det_elementwise(
+      ctx, _cabi.EW_PASS_PRED_NAN_TARGET if copy_nans else _cabi.EW_PASS_PRED,
+      a.data_ptr(), b.data_ptr(), None, out.numel(), out.data_ptr())
+  coords = xl._merge_coords(source, other, dims)  # pylint: disable=protected-access
+  return xl.DataArray(out, dims, coords=coords, name=source.name)
+
+
+# ---------------------------------------------------------------------------
+# Ensemble mean field (wrappers.EnsembleMean)
+# ---------------------------------------------------------------------------
+
+_ENS_MEAN_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
+
+
+def ensemble_mean(da: xl.DataArray, ensemble_dim, skipna: bool = False,
+                  device: int | None = None) -> xl.DataArray:
+  """``da.mean(ensemble_dim, skipna=skipna)`` on the GPU (wbx_ensemble_mean).
+
+  Every statistic wrapped with the same EnsembleMean transform asks for the
+  mean of the same array (wrappers.py:988-1003 maps the transform once per
+  wrapped statistic); the result is memoised on the identity of the input so
+  they share one pass over the ensemble AND one operand identity, which lets
+  the Aggregator fuse them into one launch.
+  """
+  import ctypes  # pylint: disable=g-import-not-at-top
+  torch = _torch()
+  da = xl.as_data_array(da)
+  key = (id(da), id(da.data), ensemble_dim, bool(skipna))
+  hit = _ENS_MEAN_CACHE.get(key)
+  if hit is not None and hit[1] is da and hit[2] is da.data:
+    _ENS_MEAN_CACHE.move_to_end(key)
+    return hit[0]
+  if ensemble_dim not in da.dims:
+    raise ValueError(f'Dimension {ensemble_dim!r} not found in {da.dims}')
+  dims = tuple(d for d in da.dims if d != ensemble_dim)
+  if len(dims) > _cabi.MAX_DIMS:
+    raise NotImplementedError('too many dims')
+  src = to_device(_normalise(da, 'field'), device)
+  t = src.data
+  strides = dict(zip(src.dims, t.stride()))
+  desc = _cabi.CrpsPointDesc()
+  desc.ndim = len(dims)
+  desc.flags = _cabi.CRPS_SKIPNA_ENSEMBLE if skipna else 0
+  desc.n_members = da.sizes[ensemble_dim]
+  desc.member_stride = strides[ensemble_dim]
+  for i, d in enumerate(dims):
+    desc.size[i] = da.sizes[d]
+    desc.ens_stride[i] = strides[d]
+  desc.ens = t.data_ptr()
+  out = torch.empty([da.sizes[d] for d in dims], dtype=torch.float32,
+                    device=t.device)
+  ctx = _cabi.get_context(t.device.index)
+  ctx.use_torch_stream()
+  _cabi.check(ctx.lib.wbx_ensemble_mean(ctx.handle, ctypes.byref(desc),
+                                        ctypes.c_void_p(out.data_ptr())))
+  coords = {k: v for k, v in da.coords.items() if ensemble_dim not in v.dims}
+  result = xl.DataArray(out, dims, coords=coords, name=da.name,
+                        attrs=da.attrs)
+  _ENS_MEAN_CACHE[key] = (result, da, da.data)
+  while len(_ENS_MEAN_CACHE) > 16:
+    _ENS_MEAN_CACHE.popitem(last=False)
+  return result
 
 
 # ---------------------------------------------------------------------------

@@ -136,6 +136,59 @@ class LazyStatistic(xl.DataArray):
     return out
 
 
+class LazyPassthrough(LazyStatistic):
+  """``source + zeros_like(other)`` (Prediction/TargetPassthrough,
+  deterministic.py:138-147,162-171) as the fused 'Error' statistic of
+  ``source`` against a shared all-zero slab: ``source - 0`` is exact, NaN
+  propagates, and the kernel reads ``source`` from HBM once while the zero slab
+  stays in L2.  Coordinates follow the reference: those of both inputs.
+  """
+
+  def __init__(self, source: xl.DataArray, other: xl.DataArray):
+    from weatherbenchx_b200 import engine  # pylint: disable=g-import-not-at-top
+    if not set(other.dims) <= set(source.dims):
+      raise ValueError('passthrough: the other input has extra dims')
+    inner = source.dims[-2:]
+    zeros = engine.zero_slab(
+        inner, tuple(source.sizes[d] for d in inner),
+        source.data.device if source.is_device else None)
+    super().__init__('Error', source, zeros)
+    xl._check_index_coords(source, other)  # pylint: disable=protected-access
+    self._coords = xl._merge_coords(source, other, self.dims)  # pylint: disable=protected-access
+
+
+class LazySumStatistic(LazyStatistic):
+  """Sum of lazy statistics on a common grid (WindVectorSquaredError =
+  SquaredError(u) + SquaredError(v), deterministic.py:206-219).
+
+  The Aggregator evaluates the parts in their own fused launches -- shared with
+  any other statistic of the same operands, e.g. the per-component RMSE -- and
+  adds the states; ``.values`` gives the summed field.
+  """
+
+  def __init__(self, kind: str, parts: Sequence[LazyStatistic], name=None):
+    first = parts[0]
+    for p in parts[1:]:
+      if p.dims != first.dims or p.sizes != first.sizes:
+        raise ValueError(
+            f'cannot add statistics on different grids: {first.sizes} vs '
+            f'{p.sizes}')
+    self.kind = kind
+    self.parts = tuple(parts)
+    self.predictions = first.predictions
+    self.targets = first.targets
+    self.climatology = None
+    self.dims = first.dims
+    self._sizes = dict(first.sizes)
+    self.name = name
+    self.attrs = {}
+    self._coords = dict(first.coords)
+    self._materialized = None
+
+  def group_key(self):
+    return ('sum',) + tuple(p.group_key() for p in self.parts)
+
+
 class LazyEnsembleStatistic(LazyStatistic):
   """CRPSSkill / CRPSSpread of an ensemble prediction (deferred).
 

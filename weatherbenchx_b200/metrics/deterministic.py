@@ -5,17 +5,22 @@ Mirrors the hot-path subset of
 AbsoluteError :103-112, SquaredError :115-123, SquaredPredictionAnomaly
 :222-232, SquaredTargetAnomaly :235-245, AnomalyCovariance :248-259, the
 aliases Bias / MAE / MSE :305-307, RMSE :312-324, ACC :374-400 and
-PredictionActivity :403-425.  unique_name of every statistic is the class name,
-as in the reference.
+PredictionActivity :403-425, plus PredictionPassthrough / TargetPassthrough
+:126-171 (aliases PredictionAverage / TargetAverage :308-309),
+WindVectorSquaredError :174-219 and WindVectorRMSE :327-371.  unique_name of
+every statistic follows the reference.
 """
 
 from __future__ import annotations
 
-from typing import Mapping
+from typing import Hashable, Mapping, Sequence, Union
 
 import numpy as np
 
+from weatherbenchx_b200 import xarray_lite as xl
+from weatherbenchx_b200.lazy import LazyPassthrough
 from weatherbenchx_b200.lazy import LazyStatistic
+from weatherbenchx_b200.lazy import LazySumStatistic
 from weatherbenchx_b200.metrics import base
 
 
@@ -36,6 +41,63 @@ class AbsoluteError(_FusedStatistic):
 
 class SquaredError(_FusedStatistic):
   """(predictions - targets) ** 2."""
+
+
+def _passthrough(source: xl.DataArray, other: xl.DataArray, copy_nans: bool):
+  from weatherbenchx_b200 import engine  # pylint: disable=g-import-not-at-top
+  if copy_nans or not set(other.dims) <= set(source.dims) or len(source.dims) < 1:
+    return engine.passthrough(source, other, copy_nans=copy_nans)
+  return LazyPassthrough(source, other)
+
+
+class PredictionPassthrough(base.PerVariableStatistic):
+  """Simply returns predictions (its mean is the PredictionAverage metric)."""
+
+  def __init__(self, copy_nans_from_targets: bool = False):
+    self._copy_nans_from_targets = copy_nans_from_targets
+
+  def _compute_per_variable(self, predictions, targets):
+    return _passthrough(predictions, targets, self._copy_nans_from_targets)
+
+
+class TargetPassthrough(base.PerVariableStatistic):
+  """Simply returns targets (its mean is the TargetAverage metric)."""
+
+  def __init__(self, copy_nans_from_predictions: bool = False):
+    self._copy_nans_from_predictions = copy_nans_from_predictions
+
+  def _compute_per_variable(self, predictions, targets):
+    return _passthrough(targets, predictions, self._copy_nans_from_predictions)
+
+
+class WindVectorSquaredError(base.Statistic):
+  """(u_pred - u_target)**2 + (v_pred - v_target)**2 per wind vector."""
+
+  def __init__(self, u_name: Sequence[str], v_name: Sequence[str],
+               vector_name: Sequence[str]):
+    self._u_name = u_name
+    self._v_name = v_name
+    self._vector_name = vector_name
+    if not len(self._u_name) == len(self._v_name) == len(self._vector_name):
+      raise ValueError(
+          'u_name, v_name, and vector_name must have the same length')
+
+  @property
+  def unique_name(self) -> str:
+    return 'WindVectorSquaredError_' + '_'.join(self._vector_name)
+
+  def compute(self, predictions, targets):
+    predictions = base._as_mapping(predictions)  # pylint: disable=protected-access
+    targets = base._as_mapping(targets)  # pylint: disable=protected-access
+    out = {}
+    for u, v, vector in zip(self._u_name, self._v_name, self._vector_name):
+      parts = [LazyStatistic('SquaredError', predictions[c], targets[c])
+               for c in (u, v)]
+      for part, component in zip(parts, (u, v)):
+        part.var = component  # lets the Aggregator share the per-component pass
+      out[vector] = LazySumStatistic('WindVectorSquaredError', parts,
+                                     name=vector)
+    return out
 
 
 class _FusedClimatologyStatistic(base.PerVariableStatisticWithClimatology):
@@ -61,6 +123,8 @@ class AnomalyCovariance(_FusedClimatologyStatistic):
 Bias = Error
 MAE = AbsoluteError
 MSE = SquaredError
+PredictionAverage = PredictionPassthrough
+TargetAverage = TargetPassthrough
 
 
 class RMSE(base.PerVariableMetric):
@@ -72,6 +136,30 @@ class RMSE(base.PerVariableMetric):
 
   def _values_from_mean_statistics_per_variable(self, statistic_values):
     return np.sqrt(statistic_values['SquaredError'])
+
+
+class WindVectorRMSE(base.Metric):
+  """Vector RMSE of two wind components; arguments may be names or lists."""
+
+  def __init__(self, u_name: Union[str, list], v_name: Union[str, list],
+               vector_name: Union[str, list]):
+    self._u_name = [u_name] if isinstance(u_name, str) else u_name
+    self._v_name = [v_name] if isinstance(v_name, str) else v_name
+    self._vector_name = (
+        [vector_name] if isinstance(vector_name, str) else vector_name)
+    if not len(self._u_name) == len(self._v_name) == len(self._vector_name):
+      raise ValueError(
+          'u_name, v_name, and vector_name must have the same length')
+
+  @property
+  def statistics(self) -> Mapping[str, base.Statistic]:
+    return {'WindVectorSquaredError': WindVectorSquaredError(
+        self._u_name, self._v_name, self._vector_name)}
+
+  def values_from_mean_statistics(
+      self, statistic_values: Mapping[str, Mapping[Hashable, xl.DataArray]]):
+    return {k: np.sqrt(v)
+            for k, v in statistic_values['WindVectorSquaredError'].items()}
 
 
 class ACC(base.PerVariableMetric):
