@@ -20,6 +20,8 @@ import collections
 import dataclasses
 from typing import Any, Callable, Collection, Hashable, Iterable, Mapping, Sequence
 
+import numpy as np
+
 from weatherbenchx_b200 import engine
 from weatherbenchx_b200 import xarray_lite as xl
 from weatherbenchx_b200 import xarray_tree
@@ -29,14 +31,70 @@ from weatherbenchx_b200.metrics import base as metrics_base
 
 
 def combining_sum(data_arrays: Sequence[xl.DataArray]) -> xl.DataArray:
-  """Sum with a zero-filled outer join on non-aligned coordinates."""
-  if not data_arrays:
+  """Sum with a zero-filled outer join on non-aligned coordinates.
+
+  aggregation.py:54-63 / beam_utils.CombiningSum in the reference.  Any number
+  of arrays is combined in ONE pass: the union of every index coordinate is
+  formed once and each array is added in place at its positions, so summing N
+  per-chunk blocks that tile a kept time axis costs O(result), not O(N*result).
+  """
+  arrays = [xl.as_data_array(a) for a in data_arrays]
+  if not arrays:
     return sum([])  # type: ignore
-  total = data_arrays[0]
-  for da in data_arrays[1:]:
-    a, b = xl.align(total, da, join='outer', fill_value=0)
-    total = a + b
-  return total
+  first = arrays[0]
+  if len(arrays) == 1:
+    return first
+  same_grid = all(
+      a.dims == first.dims and a.shape == first.shape and all(
+          d not in a.coords or d not in first.coords or np.array_equal(
+              a.coords[d].to_numpy(), first.coords[d].to_numpy())
+          for d in first.dims) for a in arrays[1:])
+  if same_grid:
+    total = first
+    for a in arrays[1:]:
+      total = total + a
+    return total
+  dims = first.dims
+  for a in arrays[1:]:
+    if set(a.dims) != set(dims):
+      # different dims: fall back to pairwise broadcasting semantics
+      total = first
+      for b in arrays[1:]:
+        x, y = xl.align(total, b, join='outer', fill_value=0)
+        total = x + y
+      return total
+  arrays = [a if a.dims == dims else a.transpose(*dims) for a in arrays]
+  union = {}
+  for d in dims:
+    labels = [a.coords[d].to_numpy() for a in arrays if d in a.coords]
+    if not labels:
+      continue
+    u = labels[0]
+    for lab in labels[1:]:
+      if not np.array_equal(u, lab):
+        u = np.union1d(u, lab)
+    union[d] = u
+  shape = tuple(len(union[d]) if d in union else first.sizes[d] for d in dims)
+  dtype = np.result_type(*[a.dtype for a in arrays])
+  total = np.zeros(shape, dtype=dtype)
+  for a in arrays:
+    index = []
+    for d in dims:
+      if d in union and d in a.coords:
+        index.append(np.searchsorted(union[d], a.coords[d].to_numpy()))
+      else:
+        index.append(np.arange(a.sizes[d]))
+    if dims:
+      total[np.ix_(*index)] += a.to_numpy()
+    else:
+      total = total + a.to_numpy()
+  shared = set.intersection(*[set(a.coords) for a in arrays])
+  coords = {k: v for k, v in first.coords.items()
+            if k in shared and not (set(v.dims) & set(union))}
+  for d, u in union.items():
+    coords[d] = xl.DataArray(u, (d,), name=d)
+  return xl.DataArray(total, dims, coords=coords, name=first.name,
+                      attrs=first.attrs)
 
 
 @dataclasses.dataclass

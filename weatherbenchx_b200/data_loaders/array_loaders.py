@@ -1,0 +1,128 @@
+"""Loaders over in-memory (or memory-mapped) gridded arrays.
+
+The counterpart of the reference's xarray/Zarr loaders
+(/root/reference/weatherbenchX/data_loaders/xarray_loaders.py:160-263) for the
+on-box driver: a dataset is a mapping variable -> DataArray (NumPy, np.memmap
+or CUDA payload).  Selection semantics are the reference's:
+
+* ``PredictionsFromArrays``: dims ``init_time`` and ``lead_time``;
+  ``load_chunk`` selects the exact init times and the exact lead times (or the
+  inclusive lead-time interval of a slice) -- xarray_loaders.py:191-206.
+* ``TargetsFromArrays``: dim ``valid_time``; the chunk is gathered at
+  ``valid_time = init_time + lead_time`` and gets dims (init_time, lead_time,
+  ...) with a 2-d ``valid_time`` coordinate; without lead times the init times
+  are taken as valid times -- xarray_loaders.py:242-263.
+
+Contiguous selections are returned as views (no copy), so an init-time chunk of
+a pinned or memory-mapped array goes to the GPU straight from its source.
+"""
+
+from __future__ import annotations
+
+from typing import Hashable, Iterable, Mapping, Optional, Union
+
+import numpy as np
+
+from weatherbenchx_b200 import xarray_lite as xl
+from weatherbenchx_b200.data_loaders import base
+
+
+def _positions(index: np.ndarray, labels: np.ndarray, dim: str) -> np.ndarray:
+  """Integer positions of ``labels`` in the coordinate ``index`` (exact)."""
+  if index.dtype.kind in 'mM':
+    unit = 'datetime64[ns]' if index.dtype.kind == 'M' else 'timedelta64[ns]'
+    index, labels = index.astype(unit), np.asarray(labels).astype(unit)
+  labels = np.asarray(labels)
+  order = np.argsort(index, kind='stable')
+  pos = np.searchsorted(index, labels.ravel(), sorter=order)
+  pos = np.clip(pos, 0, len(index) - 1)
+  found = order[pos]
+  if not np.array_equal(index[found], labels.ravel()):
+    missing = labels.ravel()[index[found] != labels.ravel()]
+    raise KeyError(f'not all values found in index {dim!r}: {missing[:3]}')
+  return found.reshape(labels.shape)
+
+
+def _take(da: xl.DataArray, dim: str, pos: np.ndarray) -> xl.DataArray:
+  """da.isel({dim: pos}) for 1-d positions; a view when they are a range."""
+  if len(pos) and np.array_equal(pos, np.arange(pos[0], pos[0] + len(pos))):
+    return da.isel({dim: slice(int(pos[0]), int(pos[0]) + len(pos))})
+  return da.isel({dim: pos})
+
+
+class _ArrayLoader(base.DataLoader):
+
+  def __init__(self, ds: Mapping[Hashable, xl.DataArray],
+               variables: Optional[Iterable[str]] = None,
+               sel_kwargs: Optional[Mapping] = None,
+               rename_variables: Optional[Mapping[str, str]] = None, **kwargs):
+    super().__init__(**kwargs)
+    ds = {k: xl.as_data_array(v) for k, v in dict(ds).items()}
+    if rename_variables:
+      ds = {rename_variables.get(k, k): v.rename(rename_variables.get(k, k))
+            for k, v in ds.items()}
+    if variables is not None:
+      ds = {k: ds[k] for k in variables}
+    if sel_kwargs:
+      ds = {k: v.sel({d: s for d, s in sel_kwargs.items() if d in v.dims})
+            for k, v in ds.items()}
+    self._ds = ds
+
+
+class PredictionsFromArrays(_ArrayLoader):
+  """Forecasts with dims (init_time, lead_time, ...)."""
+
+  def _load_chunk_from_source(self, init_times, lead_times=None):
+    out = {}
+    for var, da in self._ds.items():
+      chunk = _take(da, 'init_time', _positions(
+          da.coords['init_time'].to_numpy(), init_times, 'init_time'))
+      if isinstance(lead_times, slice):
+        lead = da.coords['lead_time'].to_numpy()
+        keep = np.nonzero((lead >= lead_times.start) &
+                          (lead <= lead_times.stop))[0]
+        chunk = _take(chunk, 'lead_time', keep)
+      elif lead_times is not None:
+        chunk = _take(chunk, 'lead_time', _positions(
+            da.coords['lead_time'].to_numpy(), lead_times, 'lead_time'))
+      out[var] = chunk
+    return out
+
+
+class TargetsFromArrays(_ArrayLoader):
+  """Analyses / observations on a grid with dim valid_time."""
+
+  def _load_chunk_from_source(self, init_times, lead_times=None):
+    if isinstance(lead_times, slice):
+      raise ValueError('Lead time slice not supported for target data loaders.')
+    init_times = np.asarray(init_times).astype('datetime64[ns]')
+    out = {}
+    for var, da in self._ds.items():
+      index = da.coords['valid_time'].to_numpy()
+      if lead_times is None:
+        chunk = _take(da, 'valid_time',
+                      _positions(index, init_times, 'valid_time'))
+        out[var] = chunk.rename({'valid_time': 'init_time'})
+        continue
+      lead = np.asarray(lead_times).astype('timedelta64[ns]')
+      valid = init_times[:, None] + lead[None, :]
+      pos = _positions(index, valid, 'valid_time')
+      axis = da.dims.index('valid_time')
+      if da.is_device:
+        import torch  # pylint: disable=g-import-not-at-top
+        flat = torch.as_tensor(pos.ravel(), device=da.data.device)
+        payload = da.data.index_select(axis, flat)
+      else:
+        payload = np.take(da.data, pos.ravel(), axis=axis)
+      shape = list(payload.shape)
+      shape[axis:axis + 1] = list(pos.shape)
+      payload = payload.reshape(shape)
+      dims = da.dims[:axis] + ('init_time', 'lead_time') + da.dims[axis + 1:]
+      coords = {k: v for k, v in da.coords.items()
+                if 'valid_time' not in v.dims}
+      coords['init_time'] = xl.DataArray(init_times, ('init_time',))
+      coords['lead_time'] = xl.DataArray(lead, ('lead_time',))
+      coords['valid_time'] = xl.DataArray(valid, ('init_time', 'lead_time'))
+      out[var] = xl.DataArray(payload, dims, coords=coords, name=da.name,
+                              attrs=da.attrs)
+    return out

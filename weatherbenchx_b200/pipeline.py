@@ -1,0 +1,322 @@
+"""On-box evaluation driver: time chunks -> statistics -> aggregation -> files.
+
+Replaces, for runs on one multi-GPU node, the Apache Beam pipeline of the
+reference (/root/reference/weatherbenchX/beam_pipeline.py:490-560
+``define_pipeline``) with the same arguments and the same result files:
+
+  reference stage (beam_pipeline.py)                   here
+  --------------------------------------------------   --------------------------
+  Create(times.iter_with_chunk_offsets())  :515        chunk indices, block-
+                                                       partitioned over the ranks
+  LoadPredictionsAndTargets           :62-118          loader thread, ``prefetch``
+                                                       chunks ahead of the GPU
+  ComputeStatisticsAggregateAndPrepareForCombine       Aggregator.aggregate_
+                                      :140-250         statistics (fused launches)
+  CombinePerKey(CombiningSum)         :535             per-(aggregator, statistic,
+  ConcatPerStatisticPerVariable       :253-322         variable) outer-join sum:
+                                                       blocks of a kept init_time /
+                                                       lead_time axis land at their
+                                                       coordinates, reduced ones add
+  (shuffle between workers)                            ONE collective at the end:
+                                                       packed float64 all-reduce,
+                                                       or gather + outer-join sum
+                                                       when ranks hold different
+                                                       coordinates
+  ReconstructAggregationState         :325-365         AggregationState per
+                                                       aggregator
+  ComputeMetrics / WriteMetrics /     :368-448         metric_values + NetCDF-3
+  WriteAggregationState                                files (atomic rename)
+
+One process per GPU; under ``torchrun`` every rank runs ``run_pipeline`` with
+the same arguments.  With ``checkpoint_path`` each rank periodically saves its
+partial sums and the chunk indices they cover; a restarted run skips them.
+"""
+
+from __future__ import annotations
+
+import os
+import pickle
+import queue
+import tempfile
+import threading
+import time
+from typing import Any, Callable, Mapping, Optional
+
+from weatherbenchx_b200 import aggregation
+from weatherbenchx_b200 import distributed
+from weatherbenchx_b200 import io_netcdf
+from weatherbenchx_b200 import time_chunks as time_chunks_lib
+from weatherbenchx_b200 import xarray_lite as xl
+from weatherbenchx_b200.metrics import base as metrics_base
+
+
+def _resolve_out_path(out_path, agg_name):
+  """beam_pipeline.py:391-402."""
+  if isinstance(out_path, str):
+    if agg_name is None:
+      return out_path
+    base, ext = os.path.splitext(out_path)
+    return f'{base}_{agg_name}{ext}'
+  return out_path[agg_name]
+
+
+class _Prefetcher:
+  """Loads chunks on a background thread, ``depth`` ahead of the consumer."""
+
+  def __init__(self, times, indices, predictions_loader, targets_loader,
+               depth: int, setup_fn=None):
+    self._times = times
+    self._indices = list(indices)
+    self._loaders = (predictions_loader, targets_loader)
+    self._setup_fn = setup_fn
+    self._queue: queue.Queue = queue.Queue(maxsize=max(depth, 1))
+    self._thread = None
+    self.load_seconds = 0.0
+    if depth > 0:
+      self._thread = threading.Thread(target=self._work, daemon=True)
+      self._thread.start()
+
+  def _load(self, index):
+    start = time.perf_counter()
+    init_times, lead_times = self._times[index]
+    predictions_loader, targets_loader = self._loaders
+    # targets first: they may serve as the reference of the predictions
+    # loader (beam_pipeline.py:93-105)
+    targets = targets_loader.load_chunk(init_times, lead_times)
+    predictions = predictions_loader.load_chunk(init_times, lead_times, targets)
+    self.load_seconds += time.perf_counter() - start
+    return index, predictions, targets
+
+  def _work(self):
+    try:
+      if self._setup_fn is not None:
+        self._setup_fn()
+      for index in self._indices:
+        self._queue.put(self._load(index))
+      self._queue.put(None)
+    except BaseException as e:  # pylint: disable=broad-except
+      self._queue.put(e)
+
+  def __iter__(self):
+    if self._thread is None:
+      if self._setup_fn is not None:
+        self._setup_fn()
+      for index in self._indices:
+        yield self._load(index)
+      return
+    while True:
+      item = self._queue.get()
+      if item is None:
+        return
+      if isinstance(item, BaseException):
+        raise item
+      yield item
+
+
+def _flatten(state: aggregation.AggregationState) -> dict:
+  """{(type, statistic, variable): DataArray} of one AggregationState."""
+  out = {}
+  if state.sum_weighted_statistics is None:
+    return out
+  for kind, tree in (('sum_weighted_statistics', state.sum_weighted_statistics),
+                     ('sum_weights', state.sum_weights)):
+    for stat_name, per_var in tree.items():
+      for var, da in per_var.items():
+        out[(kind, stat_name, var)] = da
+  return out
+
+
+def reconstruct_aggregation_state(pairs) -> aggregation.AggregationState:
+  """AggregationState from ((type, statistic, variable), DataArray) pairs
+  (beam_pipeline.py:325-352)."""
+  trees = {'sum_weighted_statistics': {}, 'sum_weights': {}}
+  for (kind, stat_name, var), da in pairs:
+    trees[kind].setdefault(stat_name, {})[var] = da
+  if not trees['sum_weighted_statistics']:
+    return aggregation.AggregationState.zero()
+  return aggregation.AggregationState(trees['sum_weighted_statistics'],
+                                      trees['sum_weights'])
+
+
+class _Accumulator:
+  """Outer-join running sum per (aggregator, type, statistic, variable).
+
+  Blocks are buffered and folded ``flush_every`` at a time in one pass
+  (aggregation.combining_sum), so a kept init_time axis assembled from
+  thousands of chunks is not re-copied per chunk.
+  """
+
+  def __init__(self, flush_every: int = 64):
+    self._total: dict = {}
+    self._pending: dict = {}
+    self._flush_every = flush_every
+
+  def add(self, agg_name, state: aggregation.AggregationState):
+    for key, da in _flatten(state).items():
+      blocks = self._pending.setdefault((agg_name,) + key, [])
+      blocks.append(da)
+      if len(blocks) >= self._flush_every:
+        self._fold((agg_name,) + key)
+
+  def _fold(self, key):
+    blocks = self._pending.pop(key, [])
+    if key in self._total:
+      blocks = [self._total[key]] + blocks
+    if blocks:
+      self._total[key] = aggregation.combining_sum(blocks)
+
+  def totals(self) -> dict:
+    for key in list(self._pending):
+      self._fold(key)
+    return self._total
+
+  def states(self, agg_names) -> dict:
+    totals = self.totals()
+    return {name: reconstruct_aggregation_state(
+        (key[1:], da) for key, da in totals.items() if key[0] == name)
+            for name in agg_names}
+
+  # -- checkpoint ------------------------------------------------------------
+
+  def dump(self) -> dict:
+    return {key: _plain(da) for key, da in self.totals().items()}
+
+  def load(self, plain: Mapping):
+    for key, item in plain.items():
+      self._total[key] = _unplain(item)
+
+
+def _plain(da: xl.DataArray) -> tuple:
+  return (da.to_numpy(), tuple(da.dims),
+          {k: (v.dims, v.to_numpy()) for k, v in da.coords.items()}, da.name)
+
+
+def _unplain(item: tuple) -> xl.DataArray:
+  data, dims, coords, name = item
+  return xl.DataArray(data, dims, coords={
+      k: xl.DataArray(v, d) for k, (d, v) in coords.items()}, name=name)
+
+
+def _atomic_pickle(path: str, payload) -> None:
+  directory = os.path.dirname(os.path.abspath(path)) or '.'
+  os.makedirs(directory, exist_ok=True)
+  fd, tmp = tempfile.mkstemp(dir=directory, suffix='.tmp')
+  with os.fdopen(fd, 'wb') as f:
+    pickle.dump(payload, f, protocol=pickle.HIGHEST_PROTOCOL)
+  os.replace(tmp, path)
+
+
+def run_pipeline(
+    times: time_chunks_lib.TimeChunks,
+    predictions_loader,
+    targets_loader,
+    metrics: Mapping[str, metrics_base.Metric],
+    aggregator: aggregation.Aggregator | Mapping[str, aggregation.Aggregator],
+    out_path: str | Mapping[str, str] | None = None,
+    aggregation_state_out_path: str | Mapping[str, str] | None = None,
+    setup_fn: Optional[Callable[[], None]] = None,
+    *,
+    checkpoint_path: str | None = None,
+    checkpoint_every: int = 0,
+    prefetch: int = 2,
+    group=None,
+    progress: Optional[Callable[[int, int], None]] = None,
+    require_output: bool = True,
+) -> dict:
+  """Evaluates ``metrics`` over every chunk of ``times``.
+
+  The first nine arguments are those of the reference's ``define_pipeline``
+  (without the Beam ``root``).  Returns, on every rank,
+  ``{aggregator_name: (AggregationState, metric values Dataset)}`` with
+  ``None`` as the name of a single unnamed Aggregator; rank 0 writes the files.
+
+  Args:
+    times: TimeChunks to evaluate.
+    predictions_loader / targets_loader: objects with
+      ``load_chunk(init_times, lead_times, reference)``.
+    metrics: name -> Metric.
+    aggregator: one Aggregator or a mapping name -> Aggregator.
+    out_path: NetCDF path of the metric values (or mapping per aggregator; a
+      single path gets ``_<aggregator name>`` appended per named aggregator).
+    aggregation_state_out_path: same, for the final AggregationState
+      (``AggregationState.to_dataset`` form).
+    setup_fn: called once in the loading thread before the first chunk.
+    checkpoint_path: prefix of per-rank checkpoint files.
+    checkpoint_every: save after this many chunks (0 = only never).
+    prefetch: chunks loaded ahead of the GPU (0 = load synchronously).
+    group: torch.distributed process group (default: the world).
+    progress: optional callback (chunks done on this rank, chunks of this rank).
+    require_output: the reference insists on at least one output path
+      (beam_pipeline.py:541-545); pass False to only get the return value.
+  """
+  if isinstance(aggregator, Mapping):
+    aggregators = dict(aggregator)
+    for paths, what in ((out_path, 'out_path'),
+                        (aggregation_state_out_path,
+                         'aggregation_state_out_path')):
+      if isinstance(paths, Mapping) and paths.keys() != aggregators.keys():
+        raise ValueError(f"Keys of {what} don't match aggregator names.")
+  else:
+    aggregators = {None: aggregator}
+  if require_output and out_path is None and aggregation_state_out_path is None:
+    raise ValueError(
+        'At least one of (metrics) out_path or aggregation_state_out_path must '
+        'be specified.')
+
+  rank, world_size = distributed.world()
+  mine = distributed.shard_units(list(range(len(times))), rank, world_size)
+  acc = _Accumulator()
+  done: list = []
+  ckpt_file = None
+  if checkpoint_path is not None:
+    ckpt_file = f'{checkpoint_path}.rank{rank}of{world_size}.pkl'
+    if os.path.exists(ckpt_file):
+      with open(ckpt_file, 'rb') as f:
+        saved = pickle.load(f)
+      if saved.get('n_chunks') == len(times) and set(
+          saved['done']) <= set(mine):
+        acc.load(saved['acc'])
+        done = list(saved['done'])
+  todo = [i for i in mine if i not in set(done)]
+
+  loader = _Prefetcher(times, todo, predictions_loader, targets_loader,
+                       prefetch, setup_fn)
+  since_ckpt = 0
+  for index, predictions, targets in loader:
+    statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+        metrics, predictions, targets)
+    for name, agg in aggregators.items():
+      acc.add(name, agg.aggregate_statistics(statistics))
+    done.append(index)
+    since_ckpt += 1
+    if progress is not None:
+      progress(len(done), len(mine))
+    if ckpt_file and checkpoint_every and since_ckpt >= checkpoint_every:
+      _atomic_pickle(ckpt_file, {'n_chunks': len(times), 'done': done,
+                                 'acc': acc.dump()})
+      since_ckpt = 0
+  if ckpt_file and since_ckpt:
+    _atomic_pickle(ckpt_file, {'n_chunks': len(times), 'done': done,
+                               'acc': acc.dump()})
+
+  results = {}
+  local = acc.states(aggregators)
+  for name in aggregators:
+    state = distributed.all_reduce_state(local[name], group=group)
+    values = (state.metric_values(metrics)
+              if state.sum_weighted_statistics is not None else xl.Dataset())
+    results[name] = (state, values)
+    if rank != 0:
+      continue
+    if out_path is not None:
+      io_netcdf.to_netcdf(values, _resolve_out_path(out_path, name))
+    if aggregation_state_out_path is not None:
+      io_netcdf.to_netcdf(
+          state.to_dataset(),
+          _resolve_out_path(aggregation_state_out_path, name))
+  return results
+
+
+def load_aggregation_state(path: str) -> aggregation.AggregationState:
+  """Reads a file written through ``aggregation_state_out_path``."""
+  return aggregation.AggregationState.from_dataset(io_netcdf.open_dataset(path))
