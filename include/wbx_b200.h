@@ -257,6 +257,15 @@ int wbx_crps_plan_destroy(wbx_ctx* ctx, wbx_crps_plan* plan);
 int wbx_crps_plan_run(wbx_ctx* ctx, wbx_crps_plan* plan, double* sum_ws,
                       double* sum_w, int32_t out_space, int32_t accumulate);
 
+/* As wbx_crps_plan_run (no accumulate), and additionally stores the per-point
+ * value of slot s to fields[s] (float32 device memory, [n_jobs][ny*nx] in the
+ * plan's job order; NULL entries are skipped): the fields a caller bins by
+ * region afterwards (binning.py:92-201 applied to CRPS, as the public
+ * benchmark does) come out of the same pass that reads the ensemble. */
+int wbx_crps_plan_run_fields(wbx_ctx* ctx, wbx_crps_plan* plan, double* sum_ws,
+                             double* sum_w, int32_t out_space,
+                             float* const* fields);
+
 /* Per-gridpoint CRPSSkill / CRPSSpread values for arbitrary strided layouts
  * (device pointers).  Points are the row-major flattening of `ndim` dims; the
  * target may broadcast (stride 0).  skill / spread: float32 [n_points], either

@@ -475,3 +475,119 @@ def test_identical_members_have_zero_spread():
   assert res['CRPSSpread'][0].values == 0.0
   np.testing.assert_allclose(res['CRPSSkill'][0].values, 1.5 * 64 * 128,
                              rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------
+# ensemble statistics under bin_by (the public benchmark's probabilistic suite
+# with Regions): fields from the CRPS launch + the fused class-map reduction
+# ---------------------------------------------------------------------------
+
+BIN_REGIONS = {
+    'global': ((-90, 90), (0, 360)),
+    'tropics': ((-20, 20), (0, 360)),
+    'northern-hemisphere': ((20, 90), (0, 360)),
+    'europe': ((35, 75), (-12.5, 42.5)),
+}
+
+
+@pytest.mark.parametrize('space', ['host', 'device'])
+@pytest.mark.parametrize('masked', [False, True])
+@pytest.mark.parametrize('use_sort', [False, True])
+def test_binned_ensemble_metrics_match_oracle(space, masked, use_sort,
+                                              monkeypatch):
+  from weatherbenchx_b200 import binning
+  from weatherbenchx_b200 import generic
+  rng = np.random.default_rng(17)
+  members, n_init, nlat, nlon = 10, 3, 24, 48
+  coords = {'init_time': np.arange(n_init), 'number': np.arange(members),
+            'latitude': np.linspace(-90, 90, nlat),
+            'longitude': np.linspace(0, 360, nlon, endpoint=False)}
+  dims = ('init_time', 'latitude', 'longitude')
+  y = rng.normal(280, 3, size=(n_init, nlat, nlon)).astype(np.float32)
+  x = (y[:, None] + rng.normal(0, 2, size=(n_init, members, nlat, nlon))
+       ).astype(np.float32)
+  land = xl.DataArray(rng.random((nlat, nlon)) > 0.6, dims[1:],
+                      coords={d: coords[d] for d in dims[1:]})
+  mask_np = rng.random(y.shape) > 0.2
+  X = xl.DataArray(x, ('init_time', 'number', 'latitude', 'longitude'),
+                   coords=coords, name='t')
+  Y = xl.DataArray(y, dims, coords={d: coords[d] for d in dims}, name='t')
+  if space == 'device':
+    X, Y = engine.to_device(X), engine.to_device(Y)
+  if masked:
+    m = xl.DataArray(mask_np, dims)
+    Y = Y.assign_coords(mask=engine.to_device(m) if space == 'device' else m)
+  metrics = {'crps': probabilistic.CRPSEnsemble(use_sort=use_sort),
+             'ssr': probabilistic.UnbiasedSpreadSkillRatio()}
+  bin_by = [binning.Regions(BIN_REGIONS, land_sea_mask=land)]
+  # must be served by the CRPS launch + the fused class-map kernel
+  monkeypatch.setattr(generic, 'aggregate', lambda *a, **k: (_ for _ in ()).throw(
+      AssertionError('generic path used')))
+  rd = ['init_time', 'latitude', 'longitude']
+  statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+      metrics, {'t': X}, {'t': Y})
+  state = aggregation.Aggregator(
+      reduce_dims=rd, weigh_by=[weighting.GridAreaWeighting()], bin_by=bin_by,
+      masked=masked).aggregate_statistics(statistics)
+  values = state.metric_values(metrics)
+  probe = xl.DataArray(y, dims, coords={d: coords[d] for d in dims})
+  m1 = bin_by[0].create_bin_mask(probe).values
+  w = oracle.grid_area_weights(coords['latitude'])
+  fields = {
+      'skill': oracle.crps_skill(x, y, 1),
+      'spread': oracle.crps_spread(x, 1, fair=True),
+      'var': oracle.ensemble_variance(x, 1),
+      'umse': oracle.unbiased_ensemble_mean_squared_error(x, y, 1),
+  }
+  mean = {}
+  for k, f in fields.items():
+    ws, sw, odims = oracle.aggregate(
+        f, dims, rd, weights=[(w, ('latitude',))],
+        bin_masks=[(m1, ('region', 'latitude', 'longitude'))],
+        mask=mask_np, mask_dims=dims, masked=masked)
+    assert odims == ('region',)
+    mean[k] = ws / sw
+  assert values['crps.t'].dims == ('region',)
+  assert (values['crps.t'].coords['region'].values.tolist() ==
+          list(BIN_REGIONS) + [f'{r}_land' for r in BIN_REGIONS])
+  np.testing.assert_allclose(values['crps.t'].values,
+                             mean['skill'] - 0.5 * mean['spread'], rtol=RTOL)
+  np.testing.assert_allclose(values['ssr.t'].values,
+                             np.sqrt(mean['var'] / mean['umse']), rtol=RTOL)
+
+
+def test_fields_from_the_reduce_kernels_equal_the_pointwise_ones():
+  """wbx_crps_plan_run_fields (pair, TMA-pair and sort kernels) against the
+  generic pointwise kernel and the sums of the same launch."""
+  import torch
+  rng = np.random.default_rng(23)
+  members, n_init, ny, nx = 50, 2, 16, 64
+  x = rng.normal(size=(n_init, members, ny, nx)).astype(np.float32)
+  y = rng.normal(size=(n_init, ny, nx)).astype(np.float32)
+  xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+  ctx = _cabi.get_context()
+  ref = [oracle.crps_skill(x, y, 1), oracle.crps_spread(x, 1, fair=True),
+         oracle.ensemble_variance(x, 1),
+         oracle.unbiased_ensemble_mean_squared_error(x, y, 1)]
+  for extra in (0, _cabi.FLAG_FORCE_LDG, _cabi.CRPS_USE_SORT):
+    plan = _cabi.CrpsPlan(
+        ctx, space=_cabi.SPACE_DEVICE, flags=_cabi.CRPS_FAIR | extra, ny=ny,
+        nx=nx, n_members=members, member_stride=ny * nx, point_stride=1,
+        ens=np.array([xd.data_ptr() + i * members * ny * nx * 4
+                      for i in range(n_init)], np.uint64),
+        target=np.array([yd.data_ptr() + i * ny * nx * 4
+                         for i in range(n_init)], np.uint64),
+        cell=np.zeros(n_init, np.int32), n_cells=1)
+    fields = [torch.full((n_init, ny, nx), -1.0, device='cuda')
+              for _ in range(4)]
+    ctx.use_torch_stream()
+    ws, w = plan.run_fields([f.data_ptr() for f in fields])
+    for k in range(4):
+      got = fields[k].cpu().numpy()
+      np.testing.assert_allclose(got, ref[k], rtol=2e-5, atol=2e-6)
+      np.testing.assert_allclose(ws[0, k], got.astype(np.float64).sum(),
+                                 rtol=1e-12)
+    # a NULL entry is skipped
+    only = torch.full((n_init, ny, nx), -1.0, device='cuda')
+    plan.run_fields([None, only.data_ptr(), None, None])
+    np.testing.assert_array_equal(only.cpu().numpy(), fields[1].cpu().numpy())

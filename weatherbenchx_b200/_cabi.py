@@ -160,6 +160,9 @@ SIGNATURES = {
     'wbx_crps_plan_destroy': (c_int, [c_void_p, c_void_p]),
     'wbx_crps_plan_run': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int32, c_int32]),
+    'wbx_crps_plan_run_fields': (c_int, [c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_int32,
+                                         POINTER(c_void_p)]),
     'wbx_crps_pointwise': (c_int, [c_void_p, POINTER(CrpsPointDesc), c_void_p,
                                    c_void_p]),
     'wbx_ensemble_mean': (c_int, [c_void_p, POINTER(CrpsPointDesc), c_void_p]),
@@ -434,6 +437,17 @@ class CrpsPlan:
     check(self.ctx.lib.wbx_crps_plan_run(
         self.ctx.handle, self.handle, ws.ctypes.data, w.ctypes.data,
         SPACE_HOST, 0))
+    return ws, w
+
+  def run_fields(self, field_ptrs):
+    """As run_to_host, also storing the per-point value of slot s to the device
+    buffer field_ptrs[s] ([n_jobs, ny*nx] float32; None = skip)."""
+    ws = np.empty((self.n_cells, 4), np.float64)
+    w = np.empty((self.n_cells, 4), np.float64)
+    ptrs = (c_void_p * 4)(*[c_void_p(p or 0) for p in field_ptrs])
+    check(self.ctx.lib.wbx_crps_plan_run_fields(
+        self.ctx.handle, self.handle, ws.ctypes.data, w.ctypes.data,
+        SPACE_HOST, ptrs))
     return ws, w
 
   def run_to_device(self, ws_ptr: int, w_ptr: int, accumulate: bool = False):

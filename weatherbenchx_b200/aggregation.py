@@ -25,6 +25,7 @@ import numpy as np
 from weatherbenchx_b200 import engine
 from weatherbenchx_b200 import xarray_lite as xl
 from weatherbenchx_b200 import xarray_tree
+from weatherbenchx_b200.lazy import LazyPassthrough
 from weatherbenchx_b200.lazy import LazyStatistic
 from weatherbenchx_b200.lazy import LazySumStatistic
 from weatherbenchx_b200.metrics import base as metrics_base
@@ -275,9 +276,9 @@ class Aggregator:
       return {s.kind: None for s in stats}
     weights = [w.weights(first) for w in self.weigh_by or []]
     masked = self.masked and 'mask' in first.coords
-    if first.kind in engine.CRPS_SLOT:
-      if self.bin_by:
-        raise engine.FastPathUnavailable('binned CRPS')
+    if first.kind in engine.CRPS_SLOT and self.bin_by:
+      res = self._binned_ensemble_group(stats)
+    elif first.kind in engine.CRPS_SLOT:
       res = engine.aggregate_crps(stats, self.reduce_dims, weights,
                                   masked=masked, skipna=self.skipna)
     else:
@@ -291,6 +292,33 @@ class Aggregator:
     if res is None:
       return {s.kind: None for s in stats}
     return {k: AggregationState(v[0], v[1]) for k, v in res.items()}
+
+  def _binned_ensemble_group(self, stats: Sequence[LazyStatistic]):
+    """Ensemble statistics under bin_by (the public benchmark's probabilistic
+    suite with Regions, run_benchmark_evaluation.py:341-369): the CRPS launch
+    stores the per-point values next to reading the ensemble, and the fields
+    are binned by the fused class-map kernel (4 B/point each against the
+    4*(M+1) B/point of the ensemble pass)."""
+    fields = engine.crps_fields(stats, self.reduce_dims)
+    if fields is None:
+      return None
+    pairs = []
+    for s in stats:
+      field = fields[s.kind]
+      lazy = LazyPassthrough(field, field)
+      bins = self._bin_masks(lazy)
+      if bins is None:
+        return None
+      spec = engine.build_fused_spec(
+          [lazy], self.reduce_dims,
+          [w.weights(lazy) for w in self.weigh_by or []],
+          masked=self.masked and 'mask' in lazy.coords, skipna=self.skipna,
+          bin_masks=bins[0], bin_dim_names=bins[1])
+      if spec is None:
+        return None
+      pairs.append((spec, [lazy]))
+    outs = engine.run_fused_specs(pairs)
+    return {s.kind: out['Error'] for s, out in zip(stats, outs)}
 
   def _aggregate_generic(self, stat: xl.DataArray) -> AggregationState | None:
     from weatherbenchx_b200 import generic  # pylint: disable=g-import-not-at-top

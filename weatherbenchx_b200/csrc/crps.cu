@@ -49,6 +49,7 @@ struct CrpsParams {
   int fair;
   int skipna_stat;          // Aggregator(skipna=True)
   double* records;
+  float* fields[4];         // optional per-point outputs [n_jobs][slab] or NULL
 };
 
 // skill / spread of one grid point whose members sit in a shared-memory column
@@ -166,6 +167,17 @@ __device__ __forceinline__ void crps_accumulate(const float (&v)[kCrpsStats],
   }
 }
 
+// Per-point values of the requested statistics, for callers that bin or
+// otherwise post-process the field (wbx_crps_plan_run_fields).
+__device__ __forceinline__ void crps_store_fields(const CrpsParams& P,
+                                                  const long long job,
+                                                  const unsigned e,
+                                                  const float (&v)[kCrpsStats]) {
+#pragma unroll
+  for (int k = 0; k < kCrpsStats; ++k)
+    if (P.fields[k]) __stcs(P.fields[k] + job * P.slab + e, v[k]);
+}
+
 template <bool ENS_SKIPNA, bool MASK, int WHAT>
 __global__ void __launch_bounds__(kCrpsThreads)
     crps_reduce_kernel(const CrpsParams P) {
@@ -241,6 +253,7 @@ __global__ void __launch_bounds__(kCrpsThreads)
         ensemble_moments<ENS_SKIPNA>(xs + tid, kCrpsPitch, M, ys[tid], &v[2],
                                      &v[3]);
       const unsigned e = static_cast<unsigned>(e0 + tid);
+      crps_store_fields(P, job, e, v);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
       double w = wo;
@@ -282,7 +295,7 @@ struct CrpsStageMeta {
   int cell;
   int len;
   int e0;
-  int pad;
+  int job;
   double wo;
 };
 
@@ -329,7 +342,7 @@ __global__ void __launch_bounds__(kCrpsTmaThreads)
         mt.cell = __ldg(P.cell + job);
         mt.len = len;
         mt.e0 = e0;
-        mt.pad = 0;
+        mt.job = static_cast<int>(job);
         mt.wo = P.w_outer ? __ldg(P.w_outer + job) : 1.0;
         meta[s] = mt;
         unsigned char* st = crps_smem + s * stage_stride;
@@ -394,6 +407,7 @@ __global__ void __launch_bounds__(kCrpsTmaThreads)
         ensemble_moments<ENS_SKIPNA>(xs + tid, kCrpsThreads, M, yv, &v[2],
                                      &v[3]);
       const unsigned e = static_cast<unsigned>(mt.e0 + tid);
+      crps_store_fields(P, mt.job, e, v);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
       double w = mt.wo;
@@ -579,6 +593,7 @@ __global__ void __launch_bounds__(kCrpsThreads)
       }
       v[0] = skill;
       v[1] = spread;
+      crps_store_fields(P, job, e, v);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
       double w = wo;
@@ -783,6 +798,7 @@ struct wbx_crps_plan {
   size_t smem_bytes = 0;
   bool use_sort = false;  // register sorting network (n_members <= 64)
   int what = 3;           // kWantCrps | kWantMoments
+  float* fields[4] = {nullptr, nullptr, nullptr, nullptr};  // run_fields only
   bool tma_ok = false;    // TMA-staged pair kernel allowed (alignment, size)
   size_t smem_plain = 0;  // shared memory of the non-TMA pair kernel
   wbx::DevBuf tables, weights;
@@ -1146,6 +1162,7 @@ static int crps_run_device(wbx_ctx* ctx, wbx_crps_plan* plan, double* d_ws,
   if (rc != WBX_OK) return rc;
   wbx::CrpsParams P = plan->params;
   P.records = ctx->records.as<double>();
+  for (int k = 0; k < wbx::kCrpsStats; ++k) P.fields[k] = plan->fields[k];
   rc = wbx::crps_launch(ctx, plan, P, plan->grid);
   if (rc != WBX_OK) return rc;
   return wbx::crps_finalize(ctx, plan, P.records, plan->d_cell_first_job,
@@ -1218,6 +1235,10 @@ static int crps_run_host(wbx_ctx* ctx, wbx_crps_plan* plan, double* d_ws,
     if (rc != WBX_OK) return rc;
     P.member_stride = member_major ? static_cast<long long>(slab) : 1;
     P.point_stride = member_major ? 1 : static_cast<long long>(M);
+    for (int k = 0; k < wbx::kCrpsStats; ++k)
+      P.fields[k] = plan->fields[k]
+                        ? plan->fields[k] + static_cast<size_t>(j0) * slab
+                        : nullptr;
     WBX_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
     const int grid = wbx::crps_grid(ctx, plan, P.total_tiles);
     rc = ctx->records.reserve((static_cast<size_t>(grid) + n_cells) *
@@ -1272,6 +1293,16 @@ int wbx_crps_plan_run(wbx_ctx* ctx, wbx_crps_plan* plan, double* sum_ws,
     WBX_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return WBX_OK;
+}
+
+int wbx_crps_plan_run_fields(wbx_ctx* ctx, wbx_crps_plan* plan, double* sum_ws,
+                             double* sum_w, int32_t out_space,
+                             float* const* fields) {
+  WBX_REQUIRE(ctx && plan && fields, "wbx_crps_plan_run_fields: NULL argument");
+  for (int k = 0; k < wbx::kCrpsStats; ++k) plan->fields[k] = fields[k];
+  const int rc = wbx_crps_plan_run(ctx, plan, sum_ws, sum_w, out_space, 0);
+  for (int k = 0; k < wbx::kCrpsStats; ++k) plan->fields[k] = nullptr;
+  return rc;
 }
 
 int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* d,

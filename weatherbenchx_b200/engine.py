@@ -870,6 +870,8 @@ class CrpsSpec:
   space: int
   flags: int
   stat_mask: int
+  field_dims: tuple       # job dims + slab dims: layout of per-point outputs
+  field_shape: tuple
   ny: int
   nx: int
   n_members: int
@@ -1037,8 +1039,10 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
       tuple((str(d), v.tobytes()) for d, v in sorted(
           per_dim.items(), key=lambda kv: str(kv[0]))))
   return CrpsSpec(
-      space=space, flags=flags, stat_mask=stat_mask, ny=ny, nx=nx,
-      n_members=first.n_members,
+      space=space, flags=flags, stat_mask=stat_mask,
+      field_dims=tuple(job_dims) + tuple(inner),
+      field_shape=tuple(sizes[d] for d in tuple(job_dims) + tuple(inner)),
+      ny=ny, nx=nx, n_members=first.n_members,
       member_stride=int(member_stride), point_stride=int(point_stride),
       n_cells=n_cells, ens=addresses(op_e), target=addresses(op_t),
       mask=addresses(op_m) if op_m is not None else None,
@@ -1055,6 +1059,54 @@ def aggregate_crps(stats, reduce_dims, weights=(), masked=False, skipna=False,
   spec = build_crps_spec(stats, reduce_dims, weights, masked, skipna, device)
   if spec is None:
     return None
+  ctx, plan = _crps_plan(spec, device)
+  if spec.space == _cabi.SPACE_DEVICE:
+    ctx.use_torch_stream()
+  ws, w = plan.run_to_host()
+  out = {}
+  for s in stats:
+    slot = CRPS_SLOT[s.kind]
+    out[s.kind] = (
+        xl.DataArray((ws[:, slot] * spec.scalar).reshape(spec.kept_shape),
+                     spec.kept, coords=spec.coords, name=s.name),
+        xl.DataArray((w[:, slot] * spec.scalar).reshape(spec.kept_shape),
+                     spec.kept, coords=spec.coords, name=s.name))
+  return out
+
+
+def crps_fields(stats, reduce_dims, device=None) -> dict | None:
+  """{kind: per-point field} of the ensemble statistics, from the tuned reduce
+  kernels (wbx_crps_plan_run_fields) rather than the generic pointwise one.
+
+  The fields are CUDA DataArrays laid out (outer dims..., slab dims) with the
+  statistic's coordinates; the Aggregator bins them by region with the fused
+  class-map kernel.  One pass over the ensemble serves every requested kind.
+  """
+  torch = _torch()
+  spec = build_crps_spec(stats, reduce_dims, (), False, False, device)
+  if spec is None:
+    return None
+  ctx, plan = _crps_plan(spec, device)
+  dev = torch.device('cuda', ctx.device)
+  if spec.space == _cabi.SPACE_DEVICE:
+    ctx.use_torch_stream()
+  else:  # the host-space plan runs on the context's own streams
+    torch.cuda.current_stream(dev).synchronize()
+  out, ptrs = {}, [None] * 4
+  first = stats[0]
+  coords = {k: v for k, v in first.coords.items()
+            if set(v.dims) <= set(spec.field_dims)}
+  for s in stats:
+    if s.kind in out:
+      continue
+    t = torch.empty(spec.field_shape, dtype=torch.float32, device=dev)
+    ptrs[CRPS_SLOT[s.kind]] = t.data_ptr()
+    out[s.kind] = xl.DataArray(t, spec.field_dims, coords=coords, name=s.name)
+  plan.run_fields(ptrs)
+  return out
+
+
+def _crps_plan(spec: CrpsSpec, device=None):
   ctx = _cabi.get_context(device)
   plan = _PLAN_CACHE.get(spec.cache_key)
   if plan is not None and plan.ctx is not ctx:
@@ -1074,18 +1126,7 @@ def aggregate_crps(stats, reduce_dims, weights=(), masked=False, skipna=False,
   else:
     _PLAN_CACHE.move_to_end(spec.cache_key)
   plan.keepalive = spec.keepalive
-  if spec.space == _cabi.SPACE_DEVICE:
-    ctx.use_torch_stream()
-  ws, w = plan.run_to_host()
-  out = {}
-  for s in stats:
-    slot = CRPS_SLOT[s.kind]
-    out[s.kind] = (
-        xl.DataArray((ws[:, slot] * spec.scalar).reshape(spec.kept_shape),
-                     spec.kept, coords=spec.coords, name=s.name),
-        xl.DataArray((w[:, slot] * spec.scalar).reshape(spec.kept_shape),
-                     spec.kept, coords=spec.coords, name=s.name))
-  return out
+  return ctx, plan
 
 
 def materialize_crps(stat, device=None):
