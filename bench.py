@@ -648,6 +648,7 @@ def run_b200(args):
   peak, peak_src = measured_peaks()
   per_launch_ms = kernel_ms / max(kernel_n, 1)
   achieved = POINTS_PER_STEP * ALG_BYTES_PER_POINT / (per_launch_ms * 1e-3) / 1e9
+  traffic, traffic_src = headline_traffic()
   line = {
       'metric': METRIC, 'value': value, 'unit': 'grid-points/s',
       'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -676,8 +677,8 @@ def run_b200(args):
       'roofline': {
           'bound': 'hbm', 'kernel': 'det_reduce_tma_kernel<0,0,0,0>',
           'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-          'frac': achieved / peak, 'traffic': None,
-          'peak_source': peak_src,
+          'frac': achieved / peak, 'traffic': traffic,
+          'traffic_source': traffic_src, 'peak_source': peak_src,
           'kernel_ms_per_launch': per_launch_ms, 'launches_timed': int(kernel_n),
           'algorithmic_bytes_per_launch': POINTS_PER_STEP * ALG_BYTES_PER_POINT},
       'clocks': clocks,
@@ -691,6 +692,20 @@ def run_b200(args):
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
+
+
+def headline_traffic():
+  """DRAM bytes per launch of the headline kernel (dram__bytes_read.sum +
+  dram__bytes_write.sum of one `ncu --set full` capture of this workload),
+  recorded in profiles/traffic.json next to the capture it was read from."""
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles',
+                      'traffic.json')
+  try:
+    with open(path) as f:
+      rec = json.load(f)['det_reduce_tma_kernel<0,0,0,0>']
+    return rec['dram_bytes_read'] + rec['dram_bytes_write'], rec['source']
+  except (OSError, KeyError, ValueError):
+    return None, None
 
 
 def main():

@@ -462,3 +462,49 @@ def test_fold_bin_masks_reproduces_every_mask():
   outer = xl.DataArray(np.ones((2, 3, 24), bool), ('b', 'lead_time', 'latitude'))
   with pytest.raises(engine.FastPathUnavailable):
     engine.fold_bin_masks([outer], ['b'], ['latitude', 'longitude'], sizes)
+
+
+# ---------------------------------------------------------------------------
+# plan memoisation (engine.build_fused_spec)
+# ---------------------------------------------------------------------------
+
+
+def test_spec_cache_recognises_repeats_and_retains_nothing():
+  import gc
+  import weakref
+  from weatherbenchx_b200 import weighting
+  from weatherbenchx_b200.lazy import LazyStatistic
+  rng = np.random.default_rng(0)
+  coords = {'init_time': np.arange(3), 'latitude': np.linspace(-80, 80, 8),
+            'longitude': np.arange(16) * 22.5}
+  dims = ('init_time', 'latitude', 'longitude')
+  P = xl.DataArray(rng.normal(size=(3, 8, 16)).astype(np.float32), dims,
+                   coords=coords, name='t')
+  T = xl.DataArray(rng.normal(size=(3, 8, 16)).astype(np.float32), dims,
+                   coords=coords, name='t')
+  weigher = weighting.GridAreaWeighting()
+
+  def plan(p, t, scale=1.0):
+    stat = LazyStatistic('SquaredError', p, t)
+    w = weigher.weights(stat)
+    if scale != 1.0:
+      w = w * scale
+    return engine.build_fused_spec([stat], ['latitude', 'longitude'], [w])
+
+  a, b = plan(P, T), plan(P, T)
+  assert a is b                       # same arrays, same weights -> same plan
+  assert weigher.weights(LazyStatistic('Error', P, T)) is weigher.weights(
+      LazyStatistic('Error', P, T))
+  c = plan(P, T, scale=2.0)           # other weight values -> other plan
+  assert c is not a and c.w_y[0] == 2 * a.w_y[0]
+  assert plan(P, T.isel(init_time=slice(0, 3))) is not a   # other operand
+  # a float64 operand is converted while planning: such a plan owns the copy
+  # and is rebuilt every time (its content may have changed)
+  P64 = xl.DataArray(P.values.astype(np.float64), dims, coords=coords, name='t')
+  d, e = plan(P64, T), plan(P64, T)
+  assert d is not e and len(d.keepalive) == 1 and not a.keepalive
+  # the cache holds no strong reference to the operands
+  ref = weakref.ref(P.data)
+  del P, a, b, c, d, e
+  gc.collect()
+  assert ref() is None

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import collections
 import dataclasses
+import weakref
 from typing import Hashable, Mapping, Sequence
 
 import numpy as np
@@ -361,6 +362,10 @@ class FusedSpec:
   cache_key: tuple
 
 
+_SPEC_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
+_SPEC_CACHE_SIZE = 128
+
+
 def build_fused_spec(stats: Sequence[LazyStatistic],
                      reduce_dims: Sequence[Hashable],
                      weights: Sequence[xl.DataArray] = (),
@@ -375,10 +380,48 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
   Returns None when the aggregation does not apply (reduce dims missing,
   aggregation.py:305-309); raises FastPathUnavailable when the slab kernel
   cannot express the request.
+
+  A plan is a pure function of the operand *addresses and layouts* and of the
+  *values* of the small arrays (weights, coordinates, climatology positions,
+  bin masks).  Repeated evaluation over the same arrays -- the steady state of
+  a benchmark loop or of a pipeline over device-resident data -- is recognised
+  by the identity of every payload involved (held weakly, so the cache never
+  keeps data alive) and returns the previous plan without rebuilding its job
+  tables.  Plans that own converted copies of an operand are not memoised.
   """
+  stats = sorted(stats, key=lambda s: s.climatology is None)
+  first = stats[0]
+  clim = first.climatology
+  guards = [first.predictions.data, first.targets.data]
+  if clim is not None:
+    guards += [clim, clim.climatology.data]
+  guards += [w.data for w in weights] + [m.data for m in bin_masks]
+  guards += [cv.data for cv in first.coords.values()]
+  key = (tuple(s.kind for s in stats), tuple(reduce_dims), bool(masked),
+         bool(skipna), flags_extra, device, tuple(bin_dim_names),
+         first.dims, first.predictions.dims, first.targets.dims,
+         tuple(first.coords), tuple(w.dims for w in weights),
+         tuple(id(g) for g in guards))
+  hit = _SPEC_CACHE.get(key)
+  if hit is not None and all(r() is g for r, g in zip(hit[1], guards)):
+    _SPEC_CACHE.move_to_end(key)
+    return hit[0]
+  spec = _build_fused_spec(stats, reduce_dims, weights, masked, skipna,
+                           flags_extra, device, bin_masks, bin_dim_names)
+  if spec is not None and not spec.keepalive:
+    try:
+      _SPEC_CACHE[key] = (spec, tuple(weakref.ref(g) for g in guards))
+      while len(_SPEC_CACHE) > _SPEC_CACHE_SIZE:
+        _SPEC_CACHE.popitem(last=False)
+    except TypeError:  # a payload type without weak references
+      pass
+  return spec
+
+
+def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
+                      device, bin_masks, bin_dim_names) -> FusedSpec | None:
   # The statistic that carries the climatology (if any) defines the launch;
   # climatology-free statistics of the same operands ride along for free.
-  stats = sorted(stats, key=lambda s: s.climatology is None)
   first = stats[0]
   dims = first.dims
   sizes = first.sizes
@@ -548,8 +591,34 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
       w_outer=_weight_vector(job_dims, sizes, per_dim),
       w_y=_weight_vector(y_dims, sizes, per_dim), w_x=per_dim.get(x_dim),
       scalar=scalar, stat_mask=stat_mask, kept=kept, kept_shape=[sizes[d] for d in kept],
-      coords=coords, keepalive=(pred, tgt, clim_da, mask_da),
+      coords=coords,
+      keepalive=_derived_payloads(
+          (pred, tgt, clim_da, mask_da),
+          (first.predictions, first.targets,
+           clim.climatology if clim is not None else None,
+           first.coords.get('mask'))),
       cache_key=cache_key)
+
+
+def _derived_payloads(used, originals) -> tuple:
+  """Payloads the plan addresses that are copies made while planning (dtype
+  conversion, contiguity, host->device) rather than views of the caller's
+  arrays; the plan has to keep those alive itself."""
+  def root(payload):
+    if xl._is_device(payload):  # pylint: disable=protected-access
+      return payload.untyped_storage().data_ptr()
+    while getattr(payload, 'base', None) is not None and isinstance(
+        payload.base, np.ndarray):
+      payload = payload.base
+    return payload.__array_interface__['data'][0]
+
+  out = []
+  for u, o in zip(used, originals):
+    if u is None:
+      continue
+    if o is None or root(u.data) != root(o.data):
+      out.append(u.data)
+  return tuple(out)
 
 
 def _merge_key(spec: FusedSpec):
@@ -628,7 +697,8 @@ def run_fused_specs(items, device: int | None = None):
             class_map=None if f.classes is None else f.classes.class_map,
             n_classes=0 if f.classes is None else f.classes.n_classes)
     plan = _cached_plan(ctx, key, factory)
-    # Keep the operands alive for as long as the plan may be run.
+    # Converted copies the plan addresses live as long as the plan is cached;
+    # the caller's own arrays are not retained.
     plan.keepalive = tuple(sp.keepalive for sp in specs)
     if first.space == _cabi.SPACE_DEVICE:
       ctx.use_torch_stream()
@@ -1050,7 +1120,11 @@ def build_crps_spec(stats, reduce_dims, weights=(), masked=False, skipna=False,
       w_outer=_weight_vector(job_dims, sizes, per_dim),
       w_y=_weight_vector(y_dims, sizes, per_dim), w_x=per_dim.get(x_dim),
       scalar=scalar, kept=kept, kept_shape=[sizes[d] for d in kept],
-      coords=coords, keepalive=(pred, tgt, mask_da), cache_key=cache_key)
+      coords=coords,
+      keepalive=_derived_payloads(
+          (pred, tgt, mask_da),
+          (first.predictions, first.targets, first.coords.get('mask'))),
+      cache_key=cache_key)
 
 
 def aggregate_crps(stats, reduce_dims, weights=(), masked=False, skipna=False,

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import abc
 import dataclasses
+import weakref
 
 import numpy as np
 
@@ -45,6 +46,9 @@ def cell_area_from_latitude(points: np.ndarray) -> np.ndarray:
   return np.sin(edges[1:]) - np.sin(edges[:-1])
 
 
+_WEIGHT_CACHE: dict = {}
+
+
 @dataclasses.dataclass
 class GridAreaWeighting(Weighting):
   """Weights proportional to the area of rectangular lat/lon grid boxes."""
@@ -56,6 +60,23 @@ class GridAreaWeighting(Weighting):
     if self.latitude_name not in statistic.dims:
       return xl.DataArray(1)
     lat = statistic.coords[self.latitude_name].to_numpy()
+    # memoised on the identity of the latitude payload: every statistic of a
+    # chunk asks for the same vector, and a stable result object lets the
+    # engine recognise a repeated aggregation plan.
+    key = (id(lat), self.latitude_name, self.return_normalized)
+    hit = _WEIGHT_CACHE.get(key)
+    if hit is not None and hit[0]() is lat:
+      return hit[1]
+    out = self._weights(lat)
+    try:
+      _WEIGHT_CACHE[key] = (weakref.ref(lat), out)
+      while len(_WEIGHT_CACHE) > 16:
+        _WEIGHT_CACHE.pop(next(iter(_WEIGHT_CACHE)))
+    except TypeError:
+      pass
+    return out
+
+  def _weights(self, lat: np.ndarray) -> xl.DataArray:
     steps = np.diff(lat)
     assert np.all(steps > 0) or np.all(steps < 0), (
         f'Points must be strictly monotonic: {lat}')

@@ -346,6 +346,14 @@ class DataArray:
     self._require_host('arithmetic')
     if isinstance(other, DataArray):
       other._require_host('arithmetic')
+      if (self.dims == other.dims and self._data.shape == other._data.shape
+          and _same_coords(self._coords, other._coords)):
+        # same grid, same coordinate payloads (e.g. the two halves of an
+        # AggregationState): no alignment work to do
+        res = (op(other._data, self._data) if reflexive
+               else op(self._data, other._data))
+        return self._replace(
+            data=res, name=self.name if self.name == other.name else None)
       dims, a, b = _broadcast_pair(self, other)
       coords = _merge_coords(self, other, dims)
       res = op(b, a) if reflexive else op(a, b)
@@ -507,15 +515,33 @@ def _expand(arr: np.ndarray, arr_dims: Sequence, dims: Sequence) -> np.ndarray:
   return arr.reshape(shape)
 
 
+def _same_coords(a: dict, b: dict) -> bool:
+  """True if both coordinate dicts hold the very same payload objects."""
+  if a is b:
+    return True
+  if len(a) != len(b):
+    return False
+  for k, va in a.items():
+    vb = b.get(k)
+    if vb is None or va._data is not vb._data or va.dims != vb.dims:  # pylint: disable=protected-access
+      return False
+  return True
+
+
 def _check_index_coords(a: DataArray, b: DataArray):
+  sa, sb = a.sizes, b.sizes
+  ca, cb = a._coords, b._coords  # pylint: disable=protected-access
   for d in a.dims:
-    if d in b.dims:
-      if a.sizes[d] != b.sizes[d]:
+    if d in sb:
+      if sa[d] != sb[d]:
         raise ValueError(
-            f'size mismatch along {d!r}: {a.sizes[d]} vs {b.sizes[d]} '
+            f'size mismatch along {d!r}: {sa[d]} vs {sb[d]} '
             '(xarray_lite only supports exact alignment)')
-      if d in a.coords and d in b.coords:
-        ia, ib = a.coords[d].to_numpy(), b.coords[d].to_numpy()
+      if d in ca and d in cb:
+        ia, ib = ca[d]._data, cb[d]._data  # pylint: disable=protected-access
+        if ia is ib:
+          continue
+        ia, ib = ca[d].to_numpy(), cb[d].to_numpy()
         if ia is not ib and not np.array_equal(ia, ib):
           raise ValueError(
               f'index coordinate {d!r} differs between operands; xarray_lite '
