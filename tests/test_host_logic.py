@@ -508,3 +508,37 @@ def test_spec_cache_recognises_repeats_and_retains_nothing():
   del P, a, b, c, d, e
   gc.collect()
   assert ref() is None
+
+
+def test_combining_sum_blocks_with_unsorted_labels_and_kept_time():
+  """Per-chunk blocks of a state that keeps init_time and carries an unsorted
+  string-labelled bin dim (region names): blocks land at their init_time
+  coordinates, the region axis is left as it is."""
+  regions = np.array(['global', 'tropics', 'nh', 'sh'])
+  rng = np.random.default_rng(0)
+  full = rng.normal(size=(6, 4))
+  blocks = [
+      xl.DataArray(full[i:i + 2], ('init_time', 'region'),
+                   coords={'init_time': np.arange(i, i + 2), 'region': regions})
+      for i in (4, 0, 2)]
+  total = aggregation.combining_sum(blocks)
+  assert total.dims == ('init_time', 'region')
+  np.testing.assert_array_equal(total.coords['init_time'].values, np.arange(6))
+  np.testing.assert_array_equal(total.coords['region'].values, regions)
+  np.testing.assert_array_equal(total.values, full)
+  # overlapping blocks add; transposed blocks are aligned by name
+  again = aggregation.combining_sum([total, blocks[1].transpose(
+      'region', 'init_time')])
+  expect = full.copy()
+  expect[0:2] *= 2
+  np.testing.assert_array_equal(again.values, expect)
+  # different label sets on the string axis: sorted union, zero fill
+  other = xl.DataArray(np.ones((2, 2)), ('init_time', 'region'),
+                       coords={'init_time': np.arange(2),
+                               'region': np.array(['europe', 'nh'])})
+  mixed = aggregation.combining_sum([blocks[1], other])
+  labels = mixed.coords['region'].values.tolist()
+  assert labels == sorted(set(regions.tolist()) | {'europe'})
+  np.testing.assert_array_equal(
+      mixed.sel(region='nh').values, full[0:2, 2] + 1)
+  np.testing.assert_array_equal(mixed.sel(region='europe').values, [1, 1])

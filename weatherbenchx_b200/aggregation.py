@@ -82,7 +82,12 @@ def combining_sum(data_arrays: Sequence[xl.DataArray]) -> xl.DataArray:
     index = []
     for d in dims:
       if d in union and d in a.coords:
-        index.append(np.searchsorted(union[d], a.coords[d].to_numpy()))
+        labels = a.coords[d].to_numpy()
+        if np.array_equal(labels, union[d]):
+          # also the case of a shared unsorted index (e.g. region names)
+          index.append(np.arange(len(labels)))
+        else:  # union[d] is a sorted union here
+          index.append(np.searchsorted(union[d], labels))
       else:
         index.append(np.arange(a.sizes[d]))
     if dims:
