@@ -50,7 +50,11 @@ enum {
   WBX_FLAG_SKIPNA = 1, /* Aggregator(skipna=True): NaN statistic == masked   */
   WBX_FLAG_MASKED = 2, /* Aggregator(masked=True) with a 'mask' coordinate   */
   WBX_FLAG_FORCE_LDG = 16, /* tuning/debug: bypass the TMA ring              */
-  WBX_FLAG_FORCE_TMA = 32  /* tuning/debug: fail instead of falling back     */
+  WBX_FLAG_FORCE_TMA = 32, /* tuning/debug: fail instead of falling back     */
+  WBX_FLAG_CLIM_DEVICE = 64 /* WBX_SPACE_HOST plans only: the clim addresses
+                               are device pointers (a climatology kept on the
+                               GPU across the chunks of an evaluation); only
+                               pred / target / mask are streamed             */
 };
 
 /* Slots of the fused deterministic statistics (unique_name in comments). */

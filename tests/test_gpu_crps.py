@@ -144,7 +144,10 @@ def test_golden_crps_through_cabi(m, fair):
 @pytest.mark.parametrize('members', [2, 8, 13, 50, 64, 70])
 @pytest.mark.parametrize('layout', ['member_last', 'member_major'])
 @pytest.mark.parametrize('space', ['host', 'device'])
-def test_fused_crps_matches_oracle(members, layout, space, use_sort):
+def test_fused_crps_matches_oracle(members, layout, space, use_sort,
+                                   monkeypatch):
+  # use_sort picks the kernel here (the default 'auto' policy is tested below)
+  monkeypatch.setattr(engine, 'CRPS_KERNEL', 'as_requested')
   rng = np.random.default_rng(members)
   n_init, nlat, nlon = 3, 12, 20
   coords = {'init_time': np.arange(n_init),
@@ -591,3 +594,39 @@ def test_fields_from_the_reduce_kernels_equal_the_pointwise_ones():
     only = torch.full((n_init, ny, nx), -1.0, device='cuda')
     plan.run_fields([None, only.data_ptr(), None, None])
     np.testing.assert_array_equal(only.cpu().numpy(), fields[1].cpu().numpy())
+
+
+@pytest.mark.parametrize('members,layout,expect_sort', [
+    (50, 'member_major', True), (70, 'member_major', False),
+    (50, 'member_last', False)])
+def test_auto_kernel_policy(members, layout, expect_sort, monkeypatch):
+  """CRPSEnsemble() (use_sort=False) is served by the sorting network for
+  member-major ensembles of up to 64 members, by the pair kernel otherwise;
+  both agree with the oracle."""
+  rng = np.random.default_rng(3)
+  nlat, nlon = 8, 32
+  y = rng.normal(size=(nlat, nlon)).astype(np.float32)
+  if layout == 'member_major':
+    x = rng.normal(size=(members, nlat, nlon)).astype(np.float32)
+    dims, axis = ('number', 'latitude', 'longitude'), 0
+  else:
+    x = rng.normal(size=(nlat, nlon, members)).astype(np.float32)
+    dims, axis = ('latitude', 'longitude', 'number'), 2
+  X = engine.to_device(xl.DataArray(x, dims, name='t'))
+  Y = engine.to_device(xl.DataArray(y, ('latitude', 'longitude'), name='t'))
+  flags = []
+  real = _cabi.CrpsPlan.__init__
+
+  def spy(self, ctx, **kw):
+    flags.append(kw['flags'])
+    real(self, ctx, **kw)
+
+  monkeypatch.setattr(_cabi.CrpsPlan, '__init__', spy)
+  engine.clear_plan_cache()
+  values = compute_all_metrics({'crps': probabilistic.CRPSEnsemble()},
+                               {'t': X}, {'t': Y}, ['latitude', 'longitude'])
+  assert len(flags) == 1
+  assert bool(flags[0] & _cabi.CRPS_USE_SORT) == expect_sort
+  expect = (oracle.crps_skill(x, y, axis).mean() -
+            0.5 * oracle.crps_spread(x, axis, fair=True).mean())
+  np.testing.assert_allclose(values['crps.t'].values, expect, rtol=RTOL)

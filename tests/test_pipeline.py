@@ -137,6 +137,13 @@ def test_loaders_select_like_the_reference():
                                 INIT[2:4, None] + LEAD[None, 1:3])
   k = int(np.nonzero(VALID == INIT[3] + LEAD[2])[0][0])
   np.testing.assert_array_equal(t.values[1, 1], tgts['t'].values[k])
+  # regular init / lead spacing: the (init, lead) gather is a strided window
+  # over the analysis, not a copy; an irregular one is gathered
+  assert np.shares_memory(t.data, tgts['t'].data)
+  t_irregular = tl.load_chunk(INIT[[0, 1, 3]], LEAD[1:3])['t']
+  assert not np.shares_memory(t_irregular.data, tgts['t'].data)
+  k = int(np.nonzero(VALID == INIT[3] + LEAD[1])[0][0])
+  np.testing.assert_array_equal(t_irregular.values[2, 0], tgts['t'].values[k])
   assert t.coords['mask'].values.all()
   # lead-time interval (inclusive) for predictions, refused for targets
   window = slice(LEAD[1], LEAD[2])

@@ -23,6 +23,7 @@ from weatherbenchx_b200 import _build
 WBX_OK = 0
 SPACE_DEVICE, SPACE_HOST = 0, 1
 FLAG_SKIPNA, FLAG_MASKED, FLAG_FORCE_LDG, FLAG_FORCE_TMA = 1, 2, 16, 32
+FLAG_CLIM_DEVICE = 64
 NUM_DET_STATS = 6
 NUM_DET_WCLASSES = 4
 STAT_SLOT = {

@@ -587,8 +587,12 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
   const size_t slab = static_cast<size_t>(plan->ny * plan->nx);
   const size_t fbytes = slab * 4;
   const size_t mbytes = round_up(slab, 16);
+  // WBX_FLAG_CLIM_DEVICE: the climatology rows are already in device memory
+  // (it is reused by every chunk of an evaluation); only the fields stream.
+  const bool stage_clim =
+      plan->has_clim && !(plan->flags & WBX_FLAG_CLIM_DEVICE);
   const size_t job_bytes =
-      fbytes * (plan->has_clim ? 3 : 2) + (plan->has_mask ? mbytes : 0);
+      fbytes * (stage_clim ? 3 : 2) + (plan->has_mask ? mbytes : 0);
   int64_t per_chunk = static_cast<int64_t>((ctx->staging_bytes / 2) / job_bytes);
   per_chunk = std::max<int64_t>(1, std::min<int64_t>(per_chunk, plan->n_jobs));
   for (int b = 0; b < 2; ++b) {
@@ -612,7 +616,7 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     unsigned char* s_pred = sbase;
     unsigned char* s_tgt = s_pred + nj * fbytes;
     unsigned char* s_clim = s_tgt + nj * fbytes;
-    unsigned char* s_mask = s_clim + (plan->has_clim ? nj * fbytes : 0);
+    unsigned char* s_mask = s_clim + (stage_clim ? nj * fbytes : 0);
     // Before overwriting this staging buffer, wait for the kernel that last
     // read it.
     WBX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute[buf], 0));
@@ -639,7 +643,7 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     if (rc != WBX_OK) return rc;
     rc = copy_operand(plan->target, s_tgt, fbytes, fbytes);
     if (rc != WBX_OK) return rc;
-    if (plan->has_clim) {
+    if (stage_clim) {
       rc = copy_operand(plan->clim, s_clim, fbytes, fbytes);
       if (rc != WBX_OK) return rc;
     }
@@ -674,7 +678,9 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
       h_pred[j] = reinterpret_cast<uint64_t>(s_pred + j * fbytes);
       h_tgt[j] = reinterpret_cast<uint64_t>(s_tgt + j * fbytes);
       if (plan->has_clim)
-        h_clim[j] = reinterpret_cast<uint64_t>(s_clim + j * fbytes);
+        h_clim[j] = stage_clim
+                        ? reinterpret_cast<uint64_t>(s_clim + j * fbytes)
+                        : plan->clim[j0 + j];
       if (plan->has_mask)
         h_mask[j] = reinterpret_cast<uint64_t>(s_mask + j * mbytes);
     }

@@ -50,6 +50,40 @@ def _take(da: xl.DataArray, dim: str, pos: np.ndarray) -> xl.DataArray:
   return da.isel({dim: pos})
 
 
+def _window_view(payload, axis: int, pos: np.ndarray):
+  """Zero-copy (init_time, lead_time) view of ``payload`` along ``axis`` when
+  the valid-time positions form a regular lattice pos[i, j] = a + i*di + j*dj
+  (regularly spaced init and lead times on a regularly spaced analysis): the
+  rows of neighbouring init times overlap in memory, which a strided view
+  expresses and the job tables of the kernels consume as is.  None otherwise.
+  """
+  n_i, n_j = pos.shape
+  a = int(pos[0, 0])
+  di = int(pos[1, 0]) - a if n_i > 1 else 0
+  dj = int(pos[0, 1]) - a if n_j > 1 else 0
+  lattice = a + di * np.arange(n_i)[:, None] + dj * np.arange(n_j)[None, :]
+  if di < 0 or dj < 0 or not np.array_equal(lattice, pos):
+    return None
+  if xl._is_device(payload):  # pylint: disable=protected-access
+    import torch  # pylint: disable=g-import-not-at-top
+    stride = list(payload.stride())
+    size = list(payload.shape)
+    offset = payload.storage_offset() + a * stride[axis]
+    return torch.as_strided(
+        payload, size[:axis] + [n_i, n_j] + size[axis + 1:],
+        stride[:axis] + [di * stride[axis], dj * stride[axis]] +
+        stride[axis + 1:], offset)
+  strides = list(payload.strides)
+  shape = list(payload.shape)
+  start = [slice(None)] * payload.ndim
+  start[axis] = slice(a, None)
+  return np.lib.stride_tricks.as_strided(
+      payload[tuple(start)],
+      shape[:axis] + [n_i, n_j] + shape[axis + 1:],
+      strides[:axis] + [di * strides[axis], dj * strides[axis]] +
+      strides[axis + 1:], writeable=False)
+
+
 class _ArrayLoader(base.DataLoader):
 
   def __init__(self, ds: Mapping[Hashable, xl.DataArray],
@@ -108,15 +142,17 @@ class TargetsFromArrays(_ArrayLoader):
       valid = init_times[:, None] + lead[None, :]
       pos = _positions(index, valid, 'valid_time')
       axis = da.dims.index('valid_time')
-      if da.is_device:
-        import torch  # pylint: disable=g-import-not-at-top
-        flat = torch.as_tensor(pos.ravel(), device=da.data.device)
-        payload = da.data.index_select(axis, flat)
-      else:
-        payload = np.take(da.data, pos.ravel(), axis=axis)
-      shape = list(payload.shape)
-      shape[axis:axis + 1] = list(pos.shape)
-      payload = payload.reshape(shape)
+      payload = _window_view(da.data, axis, pos)
+      if payload is None:
+        if da.is_device:
+          import torch  # pylint: disable=g-import-not-at-top
+          flat = torch.as_tensor(pos.ravel(), device=da.data.device)
+          payload = da.data.index_select(axis, flat)
+        else:
+          payload = np.take(da.data, pos.ravel(), axis=axis)
+        shape = list(payload.shape)
+        shape[axis:axis + 1] = list(pos.shape)
+        payload = payload.reshape(shape)
       dims = da.dims[:axis] + ('init_time', 'lead_time') + da.dims[axis + 1:]
       coords = {k: v for k, v in da.coords.items()
                 if 'valid_time' not in v.dims}
