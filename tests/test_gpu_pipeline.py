@@ -44,8 +44,9 @@ def _oracle_values(reduce_dims):
 
 @pytest.mark.parametrize('reduce_dims', [
     ['init_time', 'latitude', 'longitude'], ['latitude', 'longitude']])
-@pytest.mark.parametrize('chunks', [(1, 2), (4, None), (None, None)])
-def test_pipeline_on_gpu_matches_oracle(reduce_dims, chunks, tmp_path):
+@pytest.mark.parametrize('chunks,lanes', [((1, 2), 1), ((1, 2), 3),
+                                          ((4, None), 2), ((None, None), 1)])
+def test_pipeline_on_gpu_matches_oracle(reduce_dims, chunks, lanes, tmp_path):
   preds, tgts = _datasets()
   times = time_chunks.TimeChunks(INIT, LEAD, init_time_chunk_size=chunks[0],
                                  lead_time_chunk_size=chunks[1])
@@ -55,7 +56,7 @@ def test_pipeline_on_gpu_matches_oracle(reduce_dims, chunks, tmp_path):
   out = pipeline.run_pipeline(
       times, array_loaders.PredictionsFromArrays(preds),
       array_loaders.TargetsFromArrays(tgts, add_nan_mask=True), METRICS, agg,
-      out_path=path)
+      out_path=path, lanes=lanes)
   values = out[None][1]
   expected = _oracle_values(reduce_dims)
   assert set(values) == set(expected)
@@ -66,3 +67,39 @@ def test_pipeline_on_gpu_matches_oracle(reduce_dims, chunks, tmp_path):
   if 'init_time' not in reduce_dims:
     np.testing.assert_array_equal(values['rmse.t'].coords['init_time'].values,
                                   INIT)
+
+
+def test_per_init_time_state_sums_to_the_reduced_one():
+  """Keeping init_time (the state statistical_inference consumes) and summing
+  it afterwards (AggregationState.sum_along_dims, aggregation.py:150-175)
+  equals reducing init_time on the GPU; host fields against a climatology
+  that stays on the device."""
+  import torch
+  from weatherbenchx_b200 import engine
+  from weatherbenchx_b200 import xarray_lite as xl
+  preds, tgts = _datasets(('t',))
+  rng = np.random.default_rng(1)
+  grid = {k: preds['t'].coords[k].values for k in ('latitude', 'longitude')}
+  clim = {'t': engine.to_device(xl.DataArray(
+      rng.normal(size=(366, 4, len(LAT), 12)).astype(np.float32),
+      ('dayofyear', 'hour', 'latitude', 'longitude'),
+      coords=dict(grid, dayofyear=np.arange(1, 367),
+                  hour=np.arange(0, 24, 6)), name='t'))}
+  metrics = {'acc': deterministic.ACC(clim), 'rmse': deterministic.RMSE()}
+  times = time_chunks.TimeChunks(INIT, LEAD, init_time_chunk_size=2)
+  out = {}
+  for name, rd in (('kept', ['latitude', 'longitude']),
+                   ('reduced', ['init_time', 'latitude', 'longitude'])):
+    out[name] = pipeline.run_pipeline(
+        times, array_loaders.PredictionsFromArrays(preds),
+        array_loaders.TargetsFromArrays(tgts), metrics,
+        aggregation.Aggregator(reduce_dims=rd,
+                               weigh_by=[weighting.GridAreaWeighting()]),
+        require_output=False)[None][0]
+  assert torch.cuda.is_available()
+  summed = out['kept'].sum_along_dims(['init_time']).metric_values(metrics)
+  direct = out['reduced'].metric_values(metrics)
+  assert out['kept'].sum_weights['SquaredError']['t'].dims == (
+      'init_time', 'lead_time')
+  for k in direct:
+    np.testing.assert_allclose(summed[k].values, direct[k].values, rtol=1e-9)

@@ -219,9 +219,11 @@ def _run(reduce_dims, init_chunk, lead_chunk, **kw):
     ['lead_time', 'latitude', 'longitude'],
 ])
 @pytest.mark.parametrize('chunks', [(1, 1), (2, 3), (4, None), (None, 2)])
-@pytest.mark.parametrize('prefetch', [0, 2])
-def test_chunked_pipeline_equals_monolithic(reduce_dims, chunks, prefetch):
-  out, agg = _run(reduce_dims, *chunks, prefetch=prefetch, require_output=False)
+@pytest.mark.parametrize('prefetch,lanes', [(0, 1), (2, 1), (2, 3)])
+def test_chunked_pipeline_equals_monolithic(reduce_dims, chunks, prefetch,
+                                            lanes):
+  out, agg = _run(reduce_dims, *chunks, prefetch=prefetch, lanes=lanes,
+                  require_output=False)
   state, values = out[None]
   mono = _monolithic(reduce_dims)
   assert set(values) == set(mono) == {'rmse.t', 'rmse.z', 'bias.t', 'bias.z'}
@@ -299,6 +301,31 @@ def test_pipeline_resumes_from_checkpoint(tmp_path):
   _, agg = _run(reduce_dims, 1, None, require_output=False,
                 checkpoint_path=ckpt, checkpoint_every=2, prefetch=0)
   assert agg.calls == 0
+
+
+def test_lanes_fold_in_chunk_order_and_surface_errors():
+  """Concurrent lanes: results are bit-identical to the sequential run (folded
+  in chunk order), and an exception in a lane reaches the caller."""
+  rd = ['init_time', 'latitude', 'longitude']
+  seq, _ = _run(rd, 1, 1, require_output=False, lanes=1)
+  par, agg = _run(rd, 1, 1, require_output=False, lanes=4)
+  assert agg.calls == len(INIT) * len(LEAD)
+  for k, v in seq[None][1].items():
+    assert par[None][1][k].values.tobytes() == v.values.tobytes()
+
+  class Exploding(OracleAggregator):
+    def aggregate_statistics(self, statistics):
+      if self.calls == 3:
+        raise RuntimeError('lane on fire')
+      return super().aggregate_statistics(statistics)
+
+  preds, tgts = _datasets()
+  times = time_chunks.TimeChunks(INIT, LEAD, init_time_chunk_size=1)
+  with pytest.raises(RuntimeError, match='lane on fire'):
+    pipeline.run_pipeline(
+        times, array_loaders.PredictionsFromArrays(preds),
+        array_loaders.TargetsFromArrays(tgts), METRICS, Exploding(rd),
+        require_output=False, lanes=2)
 
 
 def test_loader_errors_surface_from_the_prefetch_thread():

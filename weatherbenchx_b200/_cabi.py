@@ -266,8 +266,19 @@ class Context:
     check(self.lib.wbx_ctx_set_staging_bytes(self.handle, nbytes))
 
 
+_lane = threading.local()
+
+
+def set_thread_lane(index: int) -> None:
+  """Gives the calling thread its own context (streams, staging buffers,
+  scratch) per device: lane 0 is the default context every thread shares;
+  worker threads that evaluate chunks concurrently take lanes 1, 2, ...  A
+  wbx_ctx is not re-entrant, distinct contexts are (include/wbx_b200.h)."""
+  _lane.index = int(index)
+
+
 def get_context(device: int | None = None) -> Context:
-  """Per-(process, device) cached context."""
+  """Per-(process, device, thread lane) cached context."""
   if device is None:
     device = int(os.environ.get('LOCAL_RANK', '0')) if os.environ.get(
         'WBX_B200_DEVICE_FROM_LOCAL_RANK') else 0
@@ -278,7 +289,7 @@ def get_context(device: int | None = None) -> Context:
     except ImportError:
       pass
   load_library()
-  key = (os.getpid(), device)
+  key = (os.getpid(), device, getattr(_lane, 'index', 0))
   with _lock:
     ctx = _contexts.get(key)
   if ctx is None:

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import collections
 import dataclasses
+import threading
 import weakref
 from typing import Hashable, Mapping, Sequence
 
@@ -161,15 +162,17 @@ def align_climatology(predictions: xl.DataArray,
                 if k in predictions.coords)
   key = (tuple(id(predictions.coords[k].data) for k in tkeys),
          id(climatology), id(climatology.data))
-  hit = _ALIGN_CACHE.get(key)
+  with _CACHE_LOCK:
+    hit = _ALIGN_CACHE.get(key)
   if hit is not None and hit[1] is climatology and all(
       a is predictions.coords[k].data for a, k in zip(hit[2], tkeys)):
     return hit[0]
   out = _align_climatology(predictions, climatology)
-  _ALIGN_CACHE[key] = (out, climatology,
-                       tuple(predictions.coords[k].data for k in tkeys))
-  while len(_ALIGN_CACHE) > 64:
-    _ALIGN_CACHE.popitem(last=False)
+  with _CACHE_LOCK:
+    _ALIGN_CACHE[key] = (out, climatology,
+                         tuple(predictions.coords[k].data for k in tkeys))
+    while len(_ALIGN_CACHE) > 64:
+      _ALIGN_CACHE.popitem(last=False)
   return out
 
 
@@ -208,12 +211,34 @@ def _align_climatology(predictions: xl.DataArray,
 
 _PLAN_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
 _PLAN_CACHE_SIZE = 32
+# Guards every memo of this module: pipeline lanes plan chunks concurrently.
+_CACHE_LOCK = threading.RLock()
 
 
 def clear_plan_cache():
-  for plan in _PLAN_CACHE.values():
+  with _CACHE_LOCK:
+    plans = list(_PLAN_CACHE.values())
+    _PLAN_CACHE.clear()
+  for plan in plans:
     plan.close()
-  _PLAN_CACHE.clear()
+
+
+def _plan_cache_lookup(ctx, key):
+  with _CACHE_LOCK:
+    plan = _PLAN_CACHE.get((key, id(ctx)))
+    if plan is not None:
+      _PLAN_CACHE.move_to_end((key, id(ctx)))
+    return plan
+
+
+def _plan_cache_insert(ctx, key, plan):
+  with _CACHE_LOCK:
+    _PLAN_CACHE[(key, id(ctx))] = plan
+    evicted = []
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+      evicted.append(_PLAN_CACHE.popitem(last=False)[1])
+  for old in evicted:
+    old.close()
 
 
 def _job_offsets(job_dims, job_sizes, strides: Mapping) -> np.ndarray:
@@ -280,13 +305,15 @@ def fold_bin_masks(bin_masks: Sequence[xl.DataArray], bin_dim_names,
   # grid) map to the same classes without re-hashing tens of megabytes.
   ident = (tuple(id(m.data) for m in bin_masks), tuple(bin_dim_names),
            tuple(inner), tuple(sizes[d] for d in inner))
-  hit = _CLASS_IDENT_CACHE.get(ident)
+  with _CACHE_LOCK:
+    hit = _CLASS_IDENT_CACHE.get(ident)
   if hit is not None and all(a is m.data for a, m in zip(hit[0], bin_masks)):
     return hit[1]
   out = _fold_bin_masks(bin_masks, bin_dim_names, inner, sizes)
-  _CLASS_IDENT_CACHE[ident] = (tuple(m.data for m in bin_masks), out)
-  while len(_CLASS_IDENT_CACHE) > 8:
-    _CLASS_IDENT_CACHE.popitem(last=False)
+  with _CACHE_LOCK:
+    _CLASS_IDENT_CACHE[ident] = (tuple(m.data for m in bin_masks), out)
+    while len(_CLASS_IDENT_CACHE) > 8:
+      _CLASS_IDENT_CACHE.popitem(last=False)
   return out
 
 
@@ -313,10 +340,11 @@ def _fold_bin_masks(bin_masks, bin_dim_names, inner, sizes) -> BinClasses:
     labels[bdim] = (mask.coords[bdim].to_numpy() if bdim in mask.coords
                     else np.arange(arr.shape[0]))
   key = digest.hexdigest()
-  hit = _CLASS_CACHE.get(key)
-  if hit is not None:
-    _CLASS_CACHE.move_to_end(key)
-    return hit
+  with _CACHE_LOCK:
+    hit = _CLASS_CACHE.get(key)
+    if hit is not None:
+      _CLASS_CACHE.move_to_end(key)
+      return hit
   stacked = np.concatenate(expanded, axis=0)              # [n_bins_total, slab]
   packed = np.ascontiguousarray(np.packbits(stacked, axis=0).T)  # [slab, nbytes]
   void = packed.view(np.dtype((np.void, packed.shape[1]))).reshape(-1)
@@ -330,9 +358,10 @@ def _fold_bin_masks(bin_masks, bin_dim_names, inner, sizes) -> BinClasses:
       class_map=inverse.reshape(-1).astype(np.uint8), n_classes=n_classes,
       bin_dims=list(bin_dim_names), bin_coords=labels, membership=membership,
       digest=key)
-  _CLASS_CACHE[key] = out
-  while len(_CLASS_CACHE) > 8:
-    _CLASS_CACHE.popitem(last=False)
+  with _CACHE_LOCK:
+    _CLASS_CACHE[key] = out
+    while len(_CLASS_CACHE) > 8:
+      _CLASS_CACHE.popitem(last=False)
   return out
 
 
@@ -402,19 +431,22 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
          first.dims, first.predictions.dims, first.targets.dims,
          tuple(first.coords), tuple(w.dims for w in weights),
          tuple(id(g) for g in guards))
-  hit = _SPEC_CACHE.get(key)
-  if hit is not None and all(r() is g for r, g in zip(hit[1], guards)):
-    _SPEC_CACHE.move_to_end(key)
-    return hit[0]
+  with _CACHE_LOCK:
+    hit = _SPEC_CACHE.get(key)
+    if hit is not None and all(r() is g for r, g in zip(hit[1], guards)):
+      _SPEC_CACHE.move_to_end(key)
+      return hit[0]
   spec = _build_fused_spec(stats, reduce_dims, weights, masked, skipna,
                            flags_extra, device, bin_masks, bin_dim_names)
   if spec is not None and not spec.keepalive:
     try:
-      _SPEC_CACHE[key] = (spec, tuple(weakref.ref(g) for g in guards))
+      refs = tuple(weakref.ref(g) for g in guards)
+    except TypeError:  # a payload type without weak references
+      return spec
+    with _CACHE_LOCK:
+      _SPEC_CACHE[key] = (spec, refs)
       while len(_SPEC_CACHE) > _SPEC_CACHE_SIZE:
         _SPEC_CACHE.popitem(last=False)
-    except TypeError:  # a payload type without weak references
-      pass
   return spec
 
 
@@ -641,17 +673,10 @@ def _merge_key(spec: FusedSpec):
 
 
 def _cached_plan(ctx, key, factory):
-  plan = _PLAN_CACHE.get(key)
-  if plan is not None and plan.ctx is not ctx:
-    plan = None
+  plan = _plan_cache_lookup(ctx, key)
   if plan is None:
     plan = factory()
-    _PLAN_CACHE[key] = plan
-    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-      _, old = _PLAN_CACHE.popitem(last=False)
-      old.close()
-  else:
-    _PLAN_CACHE.move_to_end(key)
+    _plan_cache_insert(ctx, key, plan)
   return plan
 
 
@@ -900,10 +925,11 @@ def ensemble_mean(da: xl.DataArray, ensemble_dim, skipna: bool = False,
   torch = _torch()
   da = xl.as_data_array(da)
   key = (id(da), id(da.data), ensemble_dim, bool(skipna))
-  hit = _ENS_MEAN_CACHE.get(key)
-  if hit is not None and hit[1] is da and hit[2] is da.data:
-    _ENS_MEAN_CACHE.move_to_end(key)
-    return hit[0]
+  with _CACHE_LOCK:
+    hit = _ENS_MEAN_CACHE.get(key)
+    if hit is not None and hit[1]() is da and hit[2]() is da.data:
+      _ENS_MEAN_CACHE.move_to_end(key)
+      return hit[0]
   if ensemble_dim not in da.dims:
     raise ValueError(f'Dimension {ensemble_dim!r} not found in {da.dims}')
   dims = tuple(d for d in da.dims if d != ensemble_dim)
@@ -930,9 +956,13 @@ def ensemble_mean(da: xl.DataArray, ensemble_dim, skipna: bool = False,
   coords = {k: v for k, v in da.coords.items() if ensemble_dim not in v.dims}
   result = xl.DataArray(out, dims, coords=coords, name=da.name,
                         attrs=da.attrs)
-  _ENS_MEAN_CACHE[key] = (result, da, da.data)
-  while len(_ENS_MEAN_CACHE) > 16:
-    _ENS_MEAN_CACHE.popitem(last=False)
+  # the inputs are held weakly: the memo must not keep an ensemble alive
+  with _CACHE_LOCK:
+    _ENS_MEAN_CACHE[key] = (result, weakref.ref(da), weakref.ref(da.data))
+    for k in [k for k, v in _ENS_MEAN_CACHE.items() if v[1]() is None]:
+      del _ENS_MEAN_CACHE[k]
+    while len(_ENS_MEAN_CACHE) > 16:
+      _ENS_MEAN_CACHE.popitem(last=False)
   return result
 
 
@@ -1201,9 +1231,7 @@ def crps_fields(stats, reduce_dims, device=None) -> dict | None:
 
 def _crps_plan(spec: CrpsSpec, device=None):
   ctx = _cabi.get_context(device)
-  plan = _PLAN_CACHE.get(spec.cache_key)
-  if plan is not None and plan.ctx is not ctx:
-    plan = None
+  plan = _plan_cache_lookup(ctx, spec.cache_key)
   if plan is None:
     plan = _cabi.CrpsPlan(
         ctx, space=spec.space, flags=spec.flags, ny=spec.ny, nx=spec.nx,
@@ -1212,12 +1240,7 @@ def _crps_plan(spec: CrpsSpec, device=None):
         mask=spec.mask, cell=spec.cell, n_cells=spec.n_cells,
         w_outer=spec.w_outer, w_y=spec.w_y, w_x=spec.w_x,
         stat_mask=spec.stat_mask)
-    _PLAN_CACHE[spec.cache_key] = plan
-    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-      _, old = _PLAN_CACHE.popitem(last=False)
-      old.close()
-  else:
-    _PLAN_CACHE.move_to_end(spec.cache_key)
+    _plan_cache_insert(ctx, spec.cache_key, plan)
   plan.keepalive = spec.keepalive
   return ctx, plan
 

@@ -113,6 +113,76 @@ class _Prefetcher:
       yield item
 
 
+def _evaluate_in_lanes(items, evaluate, lanes: int):
+  """Yields evaluate(item) for every item, in item order; with lanes > 1 the
+  calls run on ``lanes`` worker threads (engine lane i + 1 each)."""
+  if lanes <= 1:
+    for item in items:
+      yield evaluate(item)
+    return
+  from weatherbenchx_b200 import _cabi  # pylint: disable=g-import-not-at-top
+  inbox: queue.Queue = queue.Queue(maxsize=lanes)
+  outbox: queue.Queue = queue.Queue()
+  stop = threading.Event()
+
+  def put(q, value):
+    while not stop.is_set():
+      try:
+        q.put(value, timeout=0.05)
+        return True
+      except queue.Full:
+        continue
+    return False
+
+  def worker(lane):
+    _cabi.set_thread_lane(lane)
+    while not stop.is_set():
+      try:
+        job = inbox.get(timeout=0.05)
+      except queue.Empty:
+        continue
+      seq, item = job
+      try:
+        outbox.put((seq, evaluate(item), None))
+      except BaseException as e:  # pylint: disable=broad-except
+        outbox.put((seq, None, e))
+
+  def feeder():
+    seq = 0
+    try:
+      for item in items:
+        if not put(inbox, (seq, item)):
+          return
+        seq += 1
+      outbox.put(('end', seq, None))
+    except BaseException as e:  # pylint: disable=broad-except
+      outbox.put(('end', seq, e))
+
+  threads = [threading.Thread(target=worker, args=(i + 1,), daemon=True)
+             for i in range(lanes)]
+  threads.append(threading.Thread(target=feeder, daemon=True))
+  for t in threads:
+    t.start()
+  ready: dict = {}
+  next_seq, total = 0, None
+  try:
+    while total is None or next_seq < total:
+      seq, result, error = outbox.get()
+      if error is not None:
+        raise error
+      if seq == 'end':
+        total = result
+        continue
+      ready[seq] = result
+      while next_seq in ready:
+        yield ready.pop(next_seq)
+        next_seq += 1
+  finally:
+    stop.set()
+    for t in threads:
+      t.join()
+
+
 def _flatten(state: aggregation.AggregationState) -> dict:
   """{(type, statistic, variable): DataArray} of one AggregationState."""
   out = {}
@@ -219,6 +289,7 @@ def run_pipeline(
     checkpoint_path: str | None = None,
     checkpoint_every: int = 0,
     prefetch: int = 2,
+    lanes: int = 1,
     group=None,
     progress: Optional[Callable[[int, int], None]] = None,
     require_output: bool = True,
@@ -244,6 +315,11 @@ def run_pipeline(
     checkpoint_path: prefix of per-rank checkpoint files.
     checkpoint_every: save after this many chunks (0 = only never).
     prefetch: chunks loaded ahead of the GPU (0 = load synchronously).
+    lanes: chunks evaluated concurrently, each on its own thread and engine
+      context.  While one lane waits inside the library for its host->device
+      copies and kernels (the GIL is released there), another plans the next
+      chunk, which hides the per-chunk Python work behind the PCIe transfer.
+      Results are folded in chunk order, so the output does not depend on it.
     group: torch.distributed process group (default: the world).
     progress: optional callback (chunks done on this rank, chunks of this rank).
     require_output: the reference insists on at least one output path
@@ -280,13 +356,19 @@ def run_pipeline(
   todo = [i for i in mine if i not in set(done)]
 
   loader = _Prefetcher(times, todo, predictions_loader, targets_loader,
-                       prefetch, setup_fn)
-  since_ckpt = 0
-  for index, predictions, targets in loader:
+                       max(prefetch, lanes if lanes > 1 else 0), setup_fn)
+
+  def evaluate(item):
+    index, predictions, targets = item
     statistics = metrics_base.compute_unique_statistics_for_all_metrics(
         metrics, predictions, targets)
-    for name, agg in aggregators.items():
-      acc.add(name, agg.aggregate_statistics(statistics))
+    return index, [(name, agg.aggregate_statistics(statistics))
+                   for name, agg in aggregators.items()]
+
+  since_ckpt = 0
+  for index, states in _evaluate_in_lanes(loader, evaluate, lanes):
+    for name, state in states:
+      acc.add(name, state)
     done.append(index)
     since_ckpt += 1
     if progress is not None:

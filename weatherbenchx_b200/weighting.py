@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import abc
 import dataclasses
+import threading
 import weakref
 
 import numpy as np
@@ -47,6 +48,7 @@ def cell_area_from_latitude(points: np.ndarray) -> np.ndarray:
 
 
 _WEIGHT_CACHE: dict = {}
+_WEIGHT_LOCK = threading.Lock()
 
 
 @dataclasses.dataclass
@@ -69,11 +71,13 @@ class GridAreaWeighting(Weighting):
       return hit[1]
     out = self._weights(lat)
     try:
-      _WEIGHT_CACHE[key] = (weakref.ref(lat), out)
+      ref = weakref.ref(lat)
+    except TypeError:
+      return out
+    with _WEIGHT_LOCK:
+      _WEIGHT_CACHE[key] = (ref, out)
       while len(_WEIGHT_CACHE) > 16:
         _WEIGHT_CACHE.pop(next(iter(_WEIGHT_CACHE)))
-    except TypeError:
-      pass
     return out
 
   def _weights(self, lat: np.ndarray) -> xl.DataArray:
