@@ -38,7 +38,8 @@ struct DevBuf {
   void* ptr = nullptr;
   size_t cap = 0;
   int reserve(size_t bytes);
-  void release();
+  void release();       // cudaFree (implicit device synchronisation)
+  void release_idle();  // caller guarantees no work uses it: may be recycled
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(ptr); }
 };

@@ -4,6 +4,9 @@
 
 #include "common.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace wbx {
 
 static thread_local char g_error[1024] = "";
@@ -24,14 +27,44 @@ int cuda_fail(cudaError_t err, const char* what, const char* file, int line) {
   return WBX_ERR_CUDA;
 }
 
+// Small device blocks (job tables, weight vectors of a plan) are recycled
+// through a process-wide free list instead of cudaMalloc / cudaFree: a
+// streamed evaluation creates and retires one plan per chunk, and cudaFree
+// synchronises the whole device -- including the copies and kernels other
+// contexts (pipeline lanes) have in flight.  Only release_idle() feeds the
+// list: its caller has synchronised every stream that touched the buffer
+// (plan destruction), so a recycled block is never still in use.
+namespace {
+struct PooledBlock {
+  void* ptr;
+  size_t cap;
+  int device;
+};
+constexpr size_t kPoolMaxBlockBytes = 4u << 20;
+constexpr size_t kPoolMaxBlocks = 256;
+std::mutex g_pool_mutex;
+std::vector<PooledBlock> g_pool;
+}  // namespace
+
 int DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return WBX_OK;
-  if (ptr) {
-    cudaFree(ptr);
-    ptr = nullptr;
-    cap = 0;
+  release();
+  const size_t want = bytes + bytes / 4 + 256;
+  if (want <= kPoolMaxBlockBytes) {
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (size_t i = 0; i < g_pool.size(); ++i) {
+      if (g_pool[i].device == device && g_pool[i].cap >= want &&
+          g_pool[i].cap <= 4 * want) {
+        ptr = g_pool[i].ptr;
+        cap = g_pool[i].cap;
+        g_pool[i] = g_pool.back();
+        g_pool.pop_back();
+        return WBX_OK;
+      }
+    }
   }
-  size_t want = bytes + bytes / 4 + 256;
   cudaError_t err = cudaMalloc(&ptr, want);
   if (err != cudaSuccess) {
     ptr = nullptr;
@@ -42,7 +75,25 @@ int DevBuf::reserve(size_t bytes) {
 }
 
 void DevBuf::release() {
-  if (ptr) cudaFree(ptr);
+  if (ptr) cudaFree(ptr);  // synchronises the device: nothing can still use it
+  ptr = nullptr;
+  cap = 0;
+}
+
+void DevBuf::release_idle() {
+  if (ptr) {
+    bool pooled = false;
+    if (cap <= kPoolMaxBlockBytes) {
+      int device = 0;
+      cudaGetDevice(&device);
+      std::lock_guard<std::mutex> lock(g_pool_mutex);
+      if (g_pool.size() < kPoolMaxBlocks) {
+        g_pool.push_back({ptr, cap, device});
+        pooled = true;
+      }
+    }
+    if (!pooled) cudaFree(ptr);
+  }
   ptr = nullptr;
   cap = 0;
 }

@@ -1148,8 +1148,8 @@ int wbx_crps_plan_destroy(wbx_ctx* ctx, wbx_crps_plan* plan) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
   }
-  plan->tables.release();
-  plan->weights.release();
+  plan->tables.release_idle();
+  plan->weights.release_idle();
   delete plan;
   return WBX_OK;
 }

@@ -557,9 +557,9 @@ int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
   }
-  plan->tables.release();
-  plan->weights.release();
-  plan->class_map.release();
+  plan->tables.release_idle();
+  plan->weights.release_idle();
+  plan->class_map.release_idle();
   delete plan;
   return WBX_OK;
 }

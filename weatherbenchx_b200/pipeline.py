@@ -141,6 +141,8 @@ def _evaluate_in_lanes(items, evaluate, lanes: int):
         job = inbox.get(timeout=0.05)
       except queue.Empty:
         continue
+      if job is None:  # no more work: leave without waiting for `stop`
+        return
       seq, item = job
       try:
         outbox.put((seq, evaluate(item), None))
@@ -157,6 +159,8 @@ def _evaluate_in_lanes(items, evaluate, lanes: int):
       outbox.put(('end', seq, None))
     except BaseException as e:  # pylint: disable=broad-except
       outbox.put(('end', seq, e))
+    for _ in range(lanes):
+      put(inbox, None)
 
   threads = [threading.Thread(target=worker, args=(i + 1,), daemon=True)
              for i in range(lanes)]
