@@ -625,7 +625,45 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   const unsigned unx = static_cast<unsigned>(P.nx);
   int s = 0;
   uint32_t ph = 0;
+  // Lane-private pending sums of the class the lane saw last.  Region boxes
+  // and coastlines make the class of a lane's four points change rarely, so
+  // the common case is one f64 FMA per statistic and point group; the keyed
+  // warp reduction into the warp's shared accumulators runs only when some
+  // lane meets a new class, at a cell change and at the end (fixed order:
+  // bit-stable).
+  int pend = -1;
+  double pacc[NS];
+  double pok = 0.0;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) pacc[k] = 0.0;
+  auto flush_pending = [&]() {
+    unsigned um = __ballot_sync(0xffffffffu, pend >= 0);
+    while (um) {
+      const int leader = __ffs(um) - 1;
+      const int lcls = __shfl_sync(0xffffffffu, pend, leader);
+      const bool mine = pend == lcls;
+      double* slot = wacc + lcls * B.n_sel;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        if (P.stat_mask & (1 << k)) {  // warp-uniform
+          const double tot = warp_sum(mine ? pacc[k] : 0.0);
+          if (lane == 0) slot[__popc(P.stat_mask & ((1 << k) - 1))] += tot;
+        }
+      }
+      if constexpr (MASK) {
+        const double tot = warp_sum(mine ? pok : 0.0);
+        if (lane == 0) slot[B.n_sel - 1] += tot;
+      }
+      um &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    pend = -1;
+    pok = 0.0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) pacc[k] = 0.0;
+    __syncwarp();
+  };
   auto flush = [&](int cell) {
+    flush_pending();
     double* rec = P.records +
                   ((static_cast<size_t>(blockIdx.x) + (cell - P.cell_base)) *
                        kConsumerWarps + warp) * nacc;
@@ -650,6 +688,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     const uchar4* sm = reinterpret_cast<const uchar4*>(st + off_m);
     const uchar4* sk = reinterpret_cast<const uchar4*>(st + off_k);
     const int nvec = mt.len >> 2;
+    // (row, column) of the lane's first point group; advanced without division
+    unsigned y, x;
+    {
+      const unsigned e = static_cast<unsigned>(mt.e0 + 4 * (warp * 32 + lane));
+      y = e / unx;
+      x = e - y * unx;
+    }
     for (int jb = warp * 32; jb < nvec; jb += kConsumerThreads) {
       const int j = jb + lane;
       const bool active = j < nvec;
@@ -657,7 +702,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       float ok[4] = {1.f, 1.f, 1.f, 1.f};
       unsigned char cls[4] = {0, 0, 0, 0};
       double wrow = 0.0;
-      unsigned y = 0;
       if (active) {
         const float4 pv = sp[j];
         const float4 tv = stt[j];
@@ -679,60 +723,56 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           for (int k = 0; k < NS; ++k) val[i][k] = q.s[k];
           if constexpr (MASK) ok[i] = q.valid[0];
         }
-        const unsigned e = static_cast<unsigned>(mt.e0 + 4 * j);
-        y = e / unx;
         wrow = mt.wo * (P.w_y ? __ldg(P.w_y + y) : 1.0);
+      }
+      x += 4u * kConsumerThreads;
+      while (x >= unx) {
+        x -= unx;
+        ++y;
       }
       const bool uniform = active && cls[0] == cls[1] && cls[1] == cls[2] &&
                            cls[2] == cls[3];
-      const int key = static_cast<int>((y << 8) | cls[0]);
-      // ---- uniform lanes: one warp reduction per distinct (row, class) -----
-      unsigned um = __ballot_sync(0xffffffffu, uniform);
-      while (um) {
-        const int leader = __ffs(um) - 1;
-        const int lkey = __shfl_sync(0xffffffffu, key, leader);
-        const double lw = __shfl_sync(0xffffffffu, wrow, leader);
-        const bool mine = uniform && key == lkey;
-        double* slot = wacc + (lkey & 0xff) * B.n_sel;
+      const int c0 = cls[0];
+      // a lane that meets a new class forces the (rare) warp-wide fold
+      if (__any_sync(0xffffffffu, uniform && pend >= 0 && pend != c0))
+        flush_pending();
+      if (uniform) {
+        pend = c0;
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
           if (P.stat_mask & (1 << k)) {  // warp-uniform
-            const float v =
-                mine ? (val[0][k] + val[1][k]) + (val[2][k] + val[3][k]) : 0.f;
-            const float tot = warp_sum_f32(v);
-            if (lane == 0)
-              slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
-                  static_cast<double>(tot) * lw;
+            const float v4 = (val[0][k] + val[1][k]) + (val[2][k] + val[3][k]);
+            pacc[k] = fma(static_cast<double>(v4), wrow, pacc[k]);
           }
         }
         if constexpr (MASK) {
-          const float v = mine ? (ok[0] + ok[1]) + (ok[2] + ok[3]) : 0.f;
-          const float tot = warp_sum_f32(v);
-          if (lane == 0) slot[B.n_sel - 1] += static_cast<double>(tot) * lw;
+          const float v4 = (ok[0] + ok[1]) + (ok[2] + ok[3]);
+          pok = fma(static_cast<double>(v4), wrow, pok);
         }
-        um &= ~__ballot_sync(0xffffffffu, mine);
       }
       // ---- mixed lanes (a class boundary inside their four points): each
       // owner folds its own points, one lane after the other (fixed order).
       unsigned mm_ = __ballot_sync(0xffffffffu, active && !uniform);
-      __syncwarp();
-      while (mm_) {
-        const int src = __ffs(mm_) - 1;
-        if (lane == src) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            double* slot = wacc + cls[i] * B.n_sel;
-#pragma unroll
-            for (int k = 0; k < NS; ++k)
-              if (P.stat_mask & (1 << k))
-                slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
-                    static_cast<double>(val[i][k]) * wrow;
-            if constexpr (MASK)
-              slot[B.n_sel - 1] += static_cast<double>(ok[i]) * wrow;
-          }
-        }
+      if (mm_) {
         __syncwarp();
-        mm_ &= mm_ - 1;
+        while (mm_) {
+          const int src = __ffs(mm_) - 1;
+          if (lane == src) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              double* slot = wacc + cls[i] * B.n_sel;
+#pragma unroll
+              for (int k = 0; k < NS; ++k)
+                if (P.stat_mask & (1 << k))
+                  slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
+                      static_cast<double>(val[i][k]) * wrow;
+              if constexpr (MASK)
+                slot[B.n_sel - 1] += static_cast<double>(ok[i]) * wrow;
+            }
+          }
+          __syncwarp();
+          mm_ &= mm_ - 1;
+        }
       }
     }
     __syncwarp();
