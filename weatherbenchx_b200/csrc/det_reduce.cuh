@@ -537,6 +537,15 @@ __device__ __forceinline__ float warp_sum_f32(float v) {
   return v;
 }
 
+// Tiles of the binned kernel are small (kBinTile points) and each one is
+// consumed by ONE warp, which walks it in consecutive 128-point groups: a
+// lane's successive points are then neighbours along a latitude row, where the
+// bin class (region box, land / sea) changes rarely, so its sums can stay in
+// registers.  Tile g of a CTA goes to warp g % 16 and to ring slot g % stages
+// (stages = 16 or 32: one or two slots per warp).
+constexpr int kBinTile = 512;
+constexpr int kBinMaxStages = 2 * kConsumerWarps;
+
 template <bool CLIM, bool MASK>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     det_reduce_bins_kernel(const DetParams P, const BinParams B,
@@ -545,9 +554,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ring = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
-  uint64_t* empty = full + kMaxStages;
-  StageMeta* meta = reinterpret_cast<StageMeta*>(empty + kMaxStages);
-  double* wacc_all = reinterpret_cast<double*>(meta + kMaxStages);
+  uint64_t* empty = full + kBinMaxStages;
+  StageMeta* meta = reinterpret_cast<StageMeta*>(empty + kBinMaxStages);
+  double* wacc_all = reinterpret_cast<double*>(meta + kBinMaxStages);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nacc = B.n_classes * B.n_sel;   // doubles per warp
@@ -558,7 +567,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kConsumerWarps);
+      mbar_init(&empty[s], 1);  // the one warp that owns the tile
     }
     fence_mbar_init();
   }
@@ -623,14 +632,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   __syncwarp();
   int cur_cell = -1;
   const unsigned unx = static_cast<unsigned>(P.nx);
-  int s = 0;
-  uint32_t ph = 0;
-  // Lane-private pending sums of the class the lane saw last.  Region boxes
-  // and coastlines make the class of a lane's four points change rarely, so
-  // the common case is one f64 FMA per statistic and point group; the keyed
-  // warp reduction into the warp's shared accumulators runs only when some
-  // lane meets a new class, at a cell change and at the end (fixed order:
-  // bit-stable).
+  // Lane-private pending sums of the class the lane saw last: one f64 FMA per
+  // statistic and point group in the common case.  The keyed warp reduction
+  // into the warp's shared accumulators runs only when some lane meets a new
+  // class, at a cell change and at the end (fixed order: bit-stable).
   int pend = -1;
   double pacc[NS];
   double pok = 0.0;
@@ -674,7 +679,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     __syncwarp();
   };
-  for (long long g = t_begin; g < t_end; ++g) {
+  // this warp's tiles: t_begin + warp, + 16, ...  (records of cells it never
+  // meets stay at the zeros the host wrote)
+  for (long long g = t_begin + warp; g < t_end; g += kConsumerWarps) {
+    const int rel = static_cast<int>(g - t_begin);
+    const int s = rel % stages;
+    const uint32_t ph = static_cast<uint32_t>(rel / stages) & 1u;
     mbar_wait(&full[s], ph);
     const StageMeta mt = meta[s];
     if (mt.cell != cur_cell) {
@@ -691,12 +701,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     // (row, column) of the lane's first point group; advanced without division
     unsigned y, x;
     {
-      const unsigned e = static_cast<unsigned>(mt.e0 + 4 * (warp * 32 + lane));
+      const unsigned e = static_cast<unsigned>(mt.e0 + 4 * lane);
       y = e / unx;
       x = e - y * unx;
     }
-    for (int jb = warp * 32; jb < nvec; jb += kConsumerThreads) {
-      const int j = jb + lane;
+    for (int j = lane; j - lane < nvec; j += 32) {
       const bool active = j < nvec;
       float val[4][NS];
       float ok[4] = {1.f, 1.f, 1.f, 1.f};
@@ -725,10 +734,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         }
         wrow = mt.wo * (P.w_y ? __ldg(P.w_y + y) : 1.0);
       }
-      x += 4u * kConsumerThreads;
-      while (x >= unx) {
-        x -= unx;
-        ++y;
+      x += 128u;
+      if (x >= unx) {  // nx >= 128 is not required: loop until inside the row
+        do {
+          x -= unx;
+          ++y;
+        } while (x >= unx);
       }
       const bool uniform = active && cls[0] == cls[1] && cls[1] == cls[2] &&
                            cls[2] == cls[3];
@@ -777,10 +788,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
-    if (++s == stages) {
-      s = 0;
-      ph ^= 1u;
-    }
   }
   if (cur_cell >= 0) flush(cur_cell);
 }
