@@ -409,31 +409,25 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
                 (!p->has_mask || (d->mask[j] % 16) == 0);
     }
   }
-  // tile: 4096 elements (16 KiB per operand) unless the slab is smaller; the
-  // binned kernel hands whole (small) tiles to single warps.
-  const bool binned = p->n_classes > 0;
-  int tile = binned ? wbx::kBinTile : 4096;
+  // tile: 4096 elements (16 KiB per operand) unless the slab is smaller.
+  int tile = 4096;
   if (slab < tile) tile = static_cast<int>(round_up(slab, 16));
   p->tile = tile;
   p->tiles_per_slab = static_cast<int>((slab + tile - 1) / tile);
   p->stage_bytes = static_cast<int>(round_up(
       static_cast<size_t>(tile) * 4 * (p->has_clim ? 3 : 2) +
-          (p->has_mask ? tile : 0) + (binned ? tile : 0),
+          (p->has_mask ? tile : 0) + (p->n_classes > 0 ? tile : 0),
       128));
-  const int max_stages = binned ? wbx::kBinMaxStages : wbx::kMaxStages;
   const size_t overhead =
-      2 * max_stages * sizeof(uint64_t) +
-      max_stages * sizeof(wbx::StageMeta) + 128 +
-      (binned
+      2 * wbx::kMaxStages * sizeof(uint64_t) +
+      wbx::kMaxStages * sizeof(wbx::StageMeta) + 128 +
+      (p->n_classes > 0
            ? static_cast<size_t>(wbx::kConsumerWarps) * p->nacc * sizeof(double)
            : 0);
   const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024) - overhead;
   int stages = static_cast<int>(budget / p->stage_bytes);
-  stages = std::min(stages, max_stages);
-  if (binned)  // one or two ring slots per consumer warp
-    stages = stages >= 2 * wbx::kConsumerWarps ? 2 * wbx::kConsumerWarps
-             : stages >= wbx::kConsumerWarps   ? wbx::kConsumerWarps
-                                               : 0;
+  stages = std::min(stages, wbx::kMaxStages);
+  // No point in more stages than tiles a CTA will ever see.
   p->stages = stages;
   p->smem_bytes = static_cast<size_t>(stages) * p->stage_bytes + overhead;
   if (d->flags & WBX_FLAG_FORCE_TMA) {
@@ -577,8 +571,6 @@ static int run_device_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
                            warps * plan->nacc * sizeof(double);
   int rc = ctx->records.reserve(rec_bytes);
   if (rc != WBX_OK) return rc;
-  if (plan->n_classes > 0)  // a warp only writes the cells whose tiles it saw
-    WBX_CUDA(cudaMemsetAsync(ctx->records.ptr, 0, rec_bytes, ctx->stream));
   wbx::DetParams P = plan->params;
   P.records = ctx->records.as<double>();
   rc = wbx::launch_main(ctx, plan, P, plan->grid);
@@ -733,8 +725,6 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     // stream order already serialises their use.
     rc = ctx->records.reserve(rec_bytes);
     if (rc != WBX_OK) return rc;
-    if (plan->n_classes > 0)
-      WBX_CUDA(cudaMemsetAsync(ctx->records.ptr, 0, rec_bytes, ctx->stream));
     P.records = ctx->records.as<double>();
     WBX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
     rc = wbx::launch_main(ctx, plan, P, grid);

@@ -537,15 +537,6 @@ __device__ __forceinline__ float warp_sum_f32(float v) {
   return v;
 }
 
-// Tiles of the binned kernel are small (kBinTile points) and each one is
-// consumed by ONE warp, which walks it in consecutive 128-point groups: a
-// lane's successive points are then neighbours along a latitude row, where the
-// bin class (region box, land / sea) changes rarely, so its sums can stay in
-// registers.  Tile g of a CTA goes to warp g % 16 and to ring slot g % stages
-// (stages = 16 or 32: one or two slots per warp).
-constexpr int kBinTile = 512;
-constexpr int kBinMaxStages = 2 * kConsumerWarps;
-
 template <bool CLIM, bool MASK>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     det_reduce_bins_kernel(const DetParams P, const BinParams B,
@@ -554,9 +545,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ring = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
-  uint64_t* empty = full + kBinMaxStages;
-  StageMeta* meta = reinterpret_cast<StageMeta*>(empty + kBinMaxStages);
-  double* wacc_all = reinterpret_cast<double*>(meta + kBinMaxStages);
+  uint64_t* empty = full + kMaxStages;
+  StageMeta* meta = reinterpret_cast<StageMeta*>(empty + kMaxStages);
+  double* wacc_all = reinterpret_cast<double*>(meta + kMaxStages);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nacc = B.n_classes * B.n_sel;   // doubles per warp
@@ -567,7 +558,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);  // the one warp that owns the tile
+      mbar_init(&empty[s], kConsumerWarps);
     }
     fence_mbar_init();
   }
@@ -632,43 +623,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   __syncwarp();
   int cur_cell = -1;
   const unsigned unx = static_cast<unsigned>(P.nx);
-  // Lane-private pending sums of the class the lane saw last: one f64 FMA per
-  // statistic and point group in the common case.  The keyed warp reduction
-  // into the warp's shared accumulators runs only when some lane meets a new
-  // class, at a cell change and at the end (fixed order: bit-stable).
-  int pend = -1;
-  double pacc[NS];
-  double pok = 0.0;
-#pragma unroll
-  for (int k = 0; k < NS; ++k) pacc[k] = 0.0;
-  auto flush_pending = [&]() {
-    unsigned um = __ballot_sync(0xffffffffu, pend >= 0);
-    while (um) {
-      const int leader = __ffs(um) - 1;
-      const int lcls = __shfl_sync(0xffffffffu, pend, leader);
-      const bool mine = pend == lcls;
-      double* slot = wacc + lcls * B.n_sel;
-#pragma unroll
-      for (int k = 0; k < NS; ++k) {
-        if (P.stat_mask & (1 << k)) {  // warp-uniform
-          const double tot = warp_sum(mine ? pacc[k] : 0.0);
-          if (lane == 0) slot[__popc(P.stat_mask & ((1 << k) - 1))] += tot;
-        }
-      }
-      if constexpr (MASK) {
-        const double tot = warp_sum(mine ? pok : 0.0);
-        if (lane == 0) slot[B.n_sel - 1] += tot;
-      }
-      um &= ~__ballot_sync(0xffffffffu, mine);
-    }
-    pend = -1;
-    pok = 0.0;
-#pragma unroll
-    for (int k = 0; k < NS; ++k) pacc[k] = 0.0;
-    __syncwarp();
-  };
+  int s = 0;
+  uint32_t ph = 0;
   auto flush = [&](int cell) {
-    flush_pending();
     double* rec = P.records +
                   ((static_cast<size_t>(blockIdx.x) + (cell - P.cell_base)) *
                        kConsumerWarps + warp) * nacc;
@@ -679,12 +636,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     __syncwarp();
   };
-  // this warp's tiles: t_begin + warp, + 16, ...  (records of cells it never
-  // meets stay at the zeros the host wrote)
-  for (long long g = t_begin + warp; g < t_end; g += kConsumerWarps) {
-    const int rel = static_cast<int>(g - t_begin);
-    const int s = rel % stages;
-    const uint32_t ph = static_cast<uint32_t>(rel / stages) & 1u;
+  for (long long g = t_begin; g < t_end; ++g) {
     mbar_wait(&full[s], ph);
     const StageMeta mt = meta[s];
     if (mt.cell != cur_cell) {
@@ -698,19 +650,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     const uchar4* sm = reinterpret_cast<const uchar4*>(st + off_m);
     const uchar4* sk = reinterpret_cast<const uchar4*>(st + off_k);
     const int nvec = mt.len >> 2;
-    // (row, column) of the lane's first point group; advanced without division
-    unsigned y, x;
-    {
-      const unsigned e = static_cast<unsigned>(mt.e0 + 4 * lane);
-      y = e / unx;
-      x = e - y * unx;
-    }
-    for (int j = lane; j - lane < nvec; j += 32) {
+    for (int jb = warp * 32; jb < nvec; jb += kConsumerThreads) {
+      const int j = jb + lane;
       const bool active = j < nvec;
       float val[4][NS];
       float ok[4] = {1.f, 1.f, 1.f, 1.f};
       unsigned char cls[4] = {0, 0, 0, 0};
       double wrow = 0.0;
+      unsigned y = 0;
       if (active) {
         const float4 pv = sp[j];
         const float4 tv = stt[j];
@@ -732,62 +679,68 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           for (int k = 0; k < NS; ++k) val[i][k] = q.s[k];
           if constexpr (MASK) ok[i] = q.valid[0];
         }
+        const unsigned e = static_cast<unsigned>(mt.e0 + 4 * j);
+        y = e / unx;
         wrow = mt.wo * (P.w_y ? __ldg(P.w_y + y) : 1.0);
-      }
-      x += 128u;
-      if (x >= unx) {  // nx >= 128 is not required: loop until inside the row
-        do {
-          x -= unx;
-          ++y;
-        } while (x >= unx);
       }
       const bool uniform = active && cls[0] == cls[1] && cls[1] == cls[2] &&
                            cls[2] == cls[3];
-      const int c0 = cls[0];
-      // a lane that meets a new class forces the (rare) warp-wide fold
-      if (__any_sync(0xffffffffu, uniform && pend >= 0 && pend != c0))
-        flush_pending();
-      if (uniform) {
-        pend = c0;
+      const int key = static_cast<int>((y << 8) | cls[0]);
+      // ---- uniform lanes: one warp reduction per distinct (row, class) -----
+      unsigned um = __ballot_sync(0xffffffffu, uniform);
+      while (um) {
+        const int leader = __ffs(um) - 1;
+        const int lkey = __shfl_sync(0xffffffffu, key, leader);
+        const double lw = __shfl_sync(0xffffffffu, wrow, leader);
+        const bool mine = uniform && key == lkey;
+        double* slot = wacc + (lkey & 0xff) * B.n_sel;
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
           if (P.stat_mask & (1 << k)) {  // warp-uniform
-            const float v4 = (val[0][k] + val[1][k]) + (val[2][k] + val[3][k]);
-            pacc[k] = fma(static_cast<double>(v4), wrow, pacc[k]);
+            const float v =
+                mine ? (val[0][k] + val[1][k]) + (val[2][k] + val[3][k]) : 0.f;
+            const float tot = warp_sum_f32(v);
+            if (lane == 0)
+              slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
+                  static_cast<double>(tot) * lw;
           }
         }
         if constexpr (MASK) {
-          const float v4 = (ok[0] + ok[1]) + (ok[2] + ok[3]);
-          pok = fma(static_cast<double>(v4), wrow, pok);
+          const float v = mine ? (ok[0] + ok[1]) + (ok[2] + ok[3]) : 0.f;
+          const float tot = warp_sum_f32(v);
+          if (lane == 0) slot[B.n_sel - 1] += static_cast<double>(tot) * lw;
         }
+        um &= ~__ballot_sync(0xffffffffu, mine);
       }
       // ---- mixed lanes (a class boundary inside their four points): each
       // owner folds its own points, one lane after the other (fixed order).
       unsigned mm_ = __ballot_sync(0xffffffffu, active && !uniform);
-      if (mm_) {
-        __syncwarp();
-        while (mm_) {
-          const int src = __ffs(mm_) - 1;
-          if (lane == src) {
+      __syncwarp();
+      while (mm_) {
+        const int src = __ffs(mm_) - 1;
+        if (lane == src) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              double* slot = wacc + cls[i] * B.n_sel;
+          for (int i = 0; i < 4; ++i) {
+            double* slot = wacc + cls[i] * B.n_sel;
 #pragma unroll
-              for (int k = 0; k < NS; ++k)
-                if (P.stat_mask & (1 << k))
-                  slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
-                      static_cast<double>(val[i][k]) * wrow;
-              if constexpr (MASK)
-                slot[B.n_sel - 1] += static_cast<double>(ok[i]) * wrow;
-            }
+            for (int k = 0; k < NS; ++k)
+              if (P.stat_mask & (1 << k))
+                slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
+                    static_cast<double>(val[i][k]) * wrow;
+            if constexpr (MASK)
+              slot[B.n_sel - 1] += static_cast<double>(ok[i]) * wrow;
           }
-          __syncwarp();
-          mm_ &= mm_ - 1;
         }
+        __syncwarp();
+        mm_ &= mm_ - 1;
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1u;
+    }
   }
   if (cur_cell >= 0) flush(cur_cell);
 }
