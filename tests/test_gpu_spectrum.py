@@ -34,7 +34,7 @@ def _field(shape, nlat, nlon, seed=0, red=True):
   return f.astype(np.float32)
 
 
-@pytest.mark.parametrize('nlon', [8, 36, 64, 90, 240, 256, 360, 1440, 2880])
+@pytest.mark.parametrize('nlon', [8, 36, 64, 90, 240, 256, 360, 720, 1440, 2880])
 def test_matches_numpy_rfft(nlon):
   nlat = 5
   lat = np.linspace(-60, 60, nlat)

@@ -361,6 +361,141 @@ __global__ void __launch_bounds__(512)
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fixed-shape variant: H and the three radices are compile-time constants, one
+// warp per row, no padding.  Every index of the Stockham passes (q = j / Ns,
+// k = j % Ns, the twiddle stride, the scatter base) folds into constants or
+// shift/multiply sequences and the butterfly loops unroll; about two thirds of
+// the generic kernel's instructions were this address arithmetic.  Serves the
+// operational grids (0.25 deg: N = 1440 = 2 * 9 * 10 * 8; 0.5 deg: N = 720).
+// ---------------------------------------------------------------------------
+template <int R, int H, int NS>
+__device__ __forceinline__ void stockham_pass_fixed(
+    const float2* __restrict__ in, float2* __restrict__ out,
+    const float2* __restrict__ tw, const int lane) {
+  constexpr int B = H / R;
+  constexpr int kTstep = H / (NS * R);
+#pragma unroll
+  for (int j0 = 0; j0 < B; j0 += 32) {
+    const int j = j0 + lane;
+    if (j0 + 32 <= B || j < B) {
+      const int q = j / NS;   // compile-time divisor
+      const int k = j - q * NS;
+      float2 v[R];
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[t] = in[j + t * B];
+      if constexpr (NS > 1) {
+        const int kt = k * kTstep;
+#pragma unroll
+        for (int t = 1; t < R; ++t) v[t] = cmul(v[t], tw[t * kt]);
+      }
+      dft<R>(v);
+      const int base = q * (NS * R) + k;
+#pragma unroll
+      for (int t = 0; t < R; ++t) out[base + t * NS] = v[t];
+    }
+  }
+}
+
+template <int H, int R0, int R1, int R2>
+__global__ void __launch_bounds__(256)
+    zonal_spectrum_fixed_kernel(const SpecParams P) {
+  static_assert(R0 * R1 * R2 == H, "radices must factor H");
+  static_assert(H % 2 == 0, "float4 row copies");
+  extern __shared__ __align__(16) unsigned char spec_smem[];
+  constexpr int Hp = H + 2;
+  constexpr int N = 2 * H;
+  float2* tw = reinterpret_cast<float2*>(spec_smem);  // exp(-2 pi i q / H)
+  float2* twn = tw + H;                               // exp(-2 pi i k / N), k <= H
+  float2* bufs = twn + (H + 2);                       // [rows][2][Hp]
+  const int group = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int q = threadIdx.x; q < H; q += blockDim.x) {
+    double sn, cs;
+    sincospi(2.0 * q / H, &sn, &cs);
+    tw[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+  }
+  for (int q = threadIdx.x; q <= H; q += blockDim.x) {
+    double sn, cs;
+    sincospi(2.0 * q / N, &sn, &cs);
+    twn[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+  }
+  __syncthreads();
+  float2* a = bufs + static_cast<size_t>(group) * 2 * Hp;
+  float2* b = a + Hp;
+  constexpr float inv_n2 = 1.0f / (static_cast<float>(N) * static_cast<float>(N));
+  const long long rows_per_iter = static_cast<long long>(gridDim.x) * P.rows;
+  constexpr int nvec = H >> 1;                 // float4 per row
+  constexpr int kPre = (nvec + 31) / 32;       // per lane
+  float4 pre[kPre];
+  bool pre_valid = false;
+  auto row_pointer = [&](long long r, int* y_out) {
+    const long long job = r / P.ny;
+    const int y = static_cast<int>(r - job * P.ny);
+    *y_out = y;
+    return reinterpret_cast<const float*>(__ldg(P.field + job)) +
+           static_cast<long long>(y) * N;
+  };
+  auto prefetch = [&](long long r) {
+    int yy;
+    const float* rp = row_pointer(r, &yy);
+    pre_valid = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
+    if (pre_valid) {
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        const int n = lane + i * 32;
+        if (n < nvec) pre[i] = ldg_stream_f4(rp + 4 * n);
+      }
+    }
+  };
+  long long row = static_cast<long long>(blockIdx.x) * P.rows + group;
+  if (row < P.n_rows) prefetch(row);
+  for (; row < P.n_rows; row += rows_per_iter) {
+    int y;
+    const float* rowp = row_pointer(row, &y);
+    __syncwarp();  // the previous row's readers are done
+    if (pre_valid) {
+      float4* a4 = reinterpret_cast<float4*>(a);
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        const int n = lane + i * 32;
+        if (n < nvec) a4[n] = pre[i];
+      }
+    } else {
+      const float2* s2 = reinterpret_cast<const float2*>(rowp);
+      for (int n = lane; n < H; n += 32) a[n] = __ldg(s2 + n);
+    }
+    if (row + rows_per_iter < P.n_rows) prefetch(row + rows_per_iter);
+    __syncwarp();
+    stockham_pass_fixed<R0, H, 1>(a, b, tw, lane);
+    __syncwarp();
+    stockham_pass_fixed<R1, H, R0>(b, a, tw, lane);
+    __syncwarp();
+    stockham_pass_fixed<R2, H, R0 * R1>(a, b, tw, lane);
+    __syncwarp();
+    const float2* in = b;  // Z[0..H-1]
+    const float scale =
+        (P.row_scale ? static_cast<float>(__ldg(P.row_scale + y)) : 1.0f) *
+        inv_n2;
+    float* dst = P.out + row * static_cast<long long>(H + 1);
+#pragma unroll 4
+    for (int k = lane; k <= H; k += 32) {
+      const int ek = (k == H) ? 0 : k;
+      const int ec = (k == 0 || k == H) ? 0 : H - k;
+      const float2 zk = in[ek];
+      const float2 zc = in[ec];
+      const float2 zr = make_float2(zc.x, -zc.y);  // conj Z[H-k]
+      const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y + zr.y));
+      const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y - zr.y));
+      const float2 wo = cmul(twn[k], o);
+      const float xr = e.x + wo.y;  // X = e - i * wo
+      const float xi = e.y - wo.x;
+      const float factor = (k == 0) ? 1.0f : 2.0f;
+      dst[k] = factor * scale * (xr * xr + xi * xi);
+    }
+  }
+}
+
 // H = 2^a 3^b 5^c -> radix list preferring few, large passes.
 static bool factorise(int H, int* radix, int* n_passes) {
   int a = 0, b = 0, c = 0, rem = H;
@@ -470,7 +605,27 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
       std::max(1ll, std::min<long long>(want, ctx->sm_count * ctas_per_sm)));
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
-  zonal_spectrum_kernel<<<grid, threads, smem, ctx->stream>>>(P);
+  const bool warp_rows = P.gsize == 32 && !P.pad && P.n_passes == 3 &&
+                         threads <= 256;
+  auto is = [&](int h, int r0, int r1, int r2) {
+    return warp_rows && H == h && P.radix[0] == r0 && P.radix[1] == r1 &&
+           P.radix[2] == r2;
+  };
+  if (is(720, 9, 10, 8)) {
+    auto kern = zonal_spectrum_fixed_kernel<720, 9, 10, 8>;
+    WBX_CUDA(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(smem)));
+    kern<<<grid, threads, smem, ctx->stream>>>(P);
+  } else if (is(360, 9, 10, 4)) {
+    auto kern = zonal_spectrum_fixed_kernel<360, 9, 10, 4>;
+    WBX_CUDA(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(smem)));
+    kern<<<grid, threads, smem, ctx->stream>>>(P);
+  } else {
+    zonal_spectrum_kernel<<<grid, threads, smem, ctx->stream>>>(P);
+  }
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   prc = ctx->prof_end();
