@@ -374,7 +374,6 @@ __device__ __forceinline__ void stockham_pass_fixed(
     const float2* __restrict__ in, float2* __restrict__ out,
     const float2* __restrict__ tw, const int lane) {
   constexpr int B = H / R;
-  constexpr int kTstep = H / (NS * R);
 #pragma unroll
   for (int j0 = 0; j0 < B; j0 += 32) {
     const int j = j0 + lane;
@@ -385,9 +384,12 @@ __device__ __forceinline__ void stockham_pass_fixed(
 #pragma unroll
       for (int t = 0; t < R; ++t) v[t] = in[j + t * B];
       if constexpr (NS > 1) {
-        const int kt = k * kTstep;
+        // pass table laid out [k][t]: a lane reads R-1 consecutive twiddles and
+        // neighbouring lanes are an odd number of float2 apart (no bank
+        // conflicts; the shared exp(-2 pi i q / H) table gave up to 5-way ones)
+        const float2* tk = tw + k * (R - 1) - 1;
 #pragma unroll
-        for (int t = 1; t < R; ++t) v[t] = cmul(v[t], tw[t * kt]);
+        for (int t = 1; t < R; ++t) v[t] = cmul(v[t], tk[t]);
       }
       dft<R>(v);
       const int base = q * (NS * R) + k;
@@ -405,15 +407,24 @@ __global__ void __launch_bounds__(256)
   extern __shared__ __align__(16) unsigned char spec_smem[];
   constexpr int Hp = H + 2;
   constexpr int N = 2 * H;
-  float2* tw = reinterpret_cast<float2*>(spec_smem);  // exp(-2 pi i q / H)
-  float2* twn = tw + H;                               // exp(-2 pi i k / N), k <= H
-  float2* bufs = twn + (H + 2);                       // [rows][2][Hp]
+  // per-pass twiddle tables [k][t-1] (R0*(R1-1) + R0*R1*(R2-1) = H - R0 entries)
+  float2* tw1 = reinterpret_cast<float2*>(spec_smem);  // exp(-2 pi i t k / (R0 R1))
+  float2* tw2 = tw1 + R0 * (R1 - 1);                   // exp(-2 pi i t k / H)
+  float2* twn = tw1 + H;                               // exp(-2 pi i k / N), k <= H
+  float2* bufs = twn + (H + 2);                        // [rows][2][Hp]
   const int group = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  for (int q = threadIdx.x; q < H; q += blockDim.x) {
+  for (int q = threadIdx.x; q < R0 * (R1 - 1); q += blockDim.x) {
+    const int k = q / (R1 - 1), t = q - k * (R1 - 1) + 1;
     double sn, cs;
-    sincospi(2.0 * q / H, &sn, &cs);
-    tw[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+    sincospi(2.0 * (t * k) / (R0 * R1), &sn, &cs);
+    tw1[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+  }
+  for (int q = threadIdx.x; q < R0 * R1 * (R2 - 1); q += blockDim.x) {
+    const int k = q / (R2 - 1), t = q - k * (R2 - 1) + 1;
+    double sn, cs;
+    sincospi(2.0 * (t * k) / H, &sn, &cs);
+    tw2[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
   }
   for (int q = threadIdx.x; q <= H; q += blockDim.x) {
     double sn, cs;
@@ -467,11 +478,11 @@ __global__ void __launch_bounds__(256)
     }
     if (row + rows_per_iter < P.n_rows) prefetch(row + rows_per_iter);
     __syncwarp();
-    stockham_pass_fixed<R0, H, 1>(a, b, tw, lane);
+    stockham_pass_fixed<R0, H, 1>(a, b, tw1, lane);
     __syncwarp();
-    stockham_pass_fixed<R1, H, R0>(b, a, tw, lane);
+    stockham_pass_fixed<R1, H, R0>(b, a, tw1, lane);
     __syncwarp();
-    stockham_pass_fixed<R2, H, R0 * R1>(a, b, tw, lane);
+    stockham_pass_fixed<R2, H, R0 * R1>(a, b, tw2, lane);
     __syncwarp();
     const float2* in = b;  // Z[0..H-1]
     const float scale =
