@@ -103,3 +103,36 @@ def test_per_init_time_state_sums_to_the_reduced_one():
       'init_time', 'lead_time')
   for k in direct:
     np.testing.assert_allclose(summed[k].values, direct[k].values, rtol=1e-9)
+
+
+def test_device_resident_archive_uses_strided_windows():
+  """Forecasts and analyses already on the GPU: the (init, lead) target window
+  is a torch.as_strided view of the analysis tensor, results equal the host
+  run."""
+  import torch
+  from weatherbenchx_b200 import engine
+  preds, tgts = _datasets(('t',))
+  dpreds = {k: engine.to_device(v) for k, v in preds.items()}
+  dtgts = {k: engine.to_device(v) for k, v in tgts.items()}
+  loader = array_loaders.TargetsFromArrays(dtgts)
+  chunk = loader.load_chunk(INIT[1:4], LEAD)['t']
+  assert chunk.is_device and chunk.shape[:2] == (3, len(LEAD))
+  assert (chunk.data.untyped_storage().data_ptr() ==
+          dtgts['t'].data.untyped_storage().data_ptr())
+  host = array_loaders.TargetsFromArrays(tgts).load_chunk(INIT[1:4], LEAD)['t']
+  np.testing.assert_array_equal(chunk.values, host.values)
+  metrics = {'rmse': deterministic.RMSE(), 'mae': deterministic.MAE()}
+  times = time_chunks.TimeChunks(INIT, LEAD, init_time_chunk_size=3)
+  agg = aggregation.Aggregator(reduce_dims=['init_time', 'latitude',
+                                            'longitude'],
+                               weigh_by=[weighting.GridAreaWeighting()])
+  out_d = pipeline.run_pipeline(
+      times, array_loaders.PredictionsFromArrays(dpreds), loader, metrics, agg,
+      require_output=False)[None][1]
+  out_h = pipeline.run_pipeline(
+      times, array_loaders.PredictionsFromArrays(preds),
+      array_loaders.TargetsFromArrays(tgts), metrics, agg,
+      require_output=False)[None][1]
+  assert torch.cuda.is_available()
+  for k in out_h:
+    np.testing.assert_allclose(out_d[k].values, out_h[k].values, rtol=1e-12)
