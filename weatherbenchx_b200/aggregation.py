@@ -430,6 +430,7 @@ class Aggregator:
       else:
         subgroups.append(plain)
     planned = []  # (members, spec, distinct statistics) of deterministic groups
+    planned_crps = []  # the same for ensemble groups
     for members in subgroups:
       lazies = [m[2] for m in members]
       distinct = {}
@@ -439,9 +440,17 @@ class Aggregator:
       first = stats[0]
       try:
         if first.kind in engine.CRPS_SLOT:
-          fused = self._fused_group(stats)
-          for stat_name, var, s in members:
-            results[stat_name][var] = fused[s.kind]
+          if self.bin_by or not set(self.reduce_dims).issubset(first.dims):
+            fused = self._fused_group(stats)
+            for stat_name, var, s in members:
+              results[stat_name][var] = fused[s.kind]
+            continue
+          spec = engine.build_crps_spec(
+              stats, self.reduce_dims,
+              [w.weights(first) for w in self.weigh_by or []],
+              masked=self.masked and 'mask' in first.coords,
+              skipna=self.skipna)
+          planned_crps.append((members, spec, stats))
           continue
         if not set(self.reduce_dims).issubset(first.dims):
           for stat_name, var, s in members:
@@ -462,6 +471,12 @@ class Aggregator:
       except engine.FastPathUnavailable:
         for stat_name, var, s in members:
           results[stat_name][var] = self._aggregate_generic(s)
+    if planned_crps:
+      outs = engine.run_crps_specs(
+          [(spec, stats) for _, spec, stats in planned_crps])
+      for (members, _, _), out in zip(planned_crps, outs):
+        for stat_name, var, s in members:
+          results[stat_name][var] = AggregationState(*out[s.kind])
     if planned:
       # variables that share grid, flags and weights go out as ONE launch
       outs = engine.run_fused_specs([(spec, stats) for _, spec, stats in planned])

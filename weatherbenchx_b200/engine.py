@@ -1182,19 +1182,80 @@ def aggregate_crps(stats, reduce_dims, weights=(), masked=False, skipna=False,
   spec = build_crps_spec(stats, reduce_dims, weights, masked, skipna, device)
   if spec is None:
     return None
-  ctx, plan = _crps_plan(spec, device)
-  if spec.space == _cabi.SPACE_DEVICE:
-    ctx.use_torch_stream()
-  ws, w = plan.run_to_host()
-  out = {}
-  for s in stats:
-    slot = CRPS_SLOT[s.kind]
-    out[s.kind] = (
-        xl.DataArray((ws[:, slot] * spec.scalar).reshape(spec.kept_shape),
-                     spec.kept, coords=spec.coords, name=s.name),
-        xl.DataArray((w[:, slot] * spec.scalar).reshape(spec.kept_shape),
-                     spec.kept, coords=spec.coords, name=s.name))
-  return out
+  return run_crps_specs([(spec, stats)], device)[0]
+
+
+def _crps_merge_key(spec: CrpsSpec):
+  return (spec.space, spec.flags, spec.stat_mask, spec.ny, spec.nx,
+          spec.n_members, spec.member_stride, spec.point_stride,
+          spec.mask is None,
+          None if spec.w_y is None else spec.w_y.tobytes(),
+          None if spec.w_x is None else spec.w_x.tobytes())
+
+
+def run_crps_specs(items, device: int | None = None):
+  """Runs planned ensemble aggregations; the variables of a chunk (same grid,
+  ensemble layout, flags and weights) share ONE launch whose job table is the
+  concatenation and whose cells are offset -- one launch, one read-back and one
+  synchronisation instead of one per variable.
+
+  ``items``: list of (spec, stats); returns [{kind: (sum_ws, sum_w)}].
+  """
+  ctx = _cabi.get_context(device)
+  buckets: dict = collections.OrderedDict()
+  for idx, (spec, _) in enumerate(items):
+    buckets.setdefault(_crps_merge_key(spec), []).append(idx)
+  raw: dict = {}
+  for members in buckets.values():
+    specs = [items[i][0] for i in members]
+    first = specs[0]
+    if len(specs) == 1:
+      _, plan = _crps_plan(first, device)
+    else:
+      key = ('merged-crps',) + tuple(sp.cache_key for sp in specs)
+      plan = _plan_cache_lookup(ctx, key)
+      if plan is None:
+        offsets = np.cumsum([0] + [sp.n_cells for sp in specs])
+        cat = lambda name: (  # noqa: E731
+            None if getattr(first, name) is None else
+            np.concatenate([getattr(sp, name) for sp in specs]))
+        w_outer = None
+        if any(sp.w_outer is not None for sp in specs):
+          w_outer = np.concatenate([
+              sp.w_outer if sp.w_outer is not None else np.ones(len(sp.ens))
+              for sp in specs])
+        plan = _cabi.CrpsPlan(
+            ctx, space=first.space, flags=first.flags, ny=first.ny,
+            nx=first.nx, n_members=first.n_members,
+            member_stride=first.member_stride,
+            point_stride=first.point_stride, ens=cat('ens'),
+            target=cat('target'), mask=cat('mask'),
+            cell=np.concatenate([sp.cell + off for sp, off in
+                                 zip(specs, offsets)]).astype(np.int32),
+            n_cells=int(offsets[-1]), w_outer=w_outer, w_y=first.w_y,
+            w_x=first.w_x, stat_mask=first.stat_mask)
+        _plan_cache_insert(ctx, key, plan)
+      plan.keepalive = tuple(sp.keepalive for sp in specs)
+    if first.space == _cabi.SPACE_DEVICE:
+      ctx.use_torch_stream()
+    ws, w = plan.run_to_host()
+    lo = 0
+    for i, sp in zip(members, specs):
+      raw[i] = (ws[lo:lo + sp.n_cells], w[lo:lo + sp.n_cells])
+      lo += sp.n_cells
+  results = []
+  for idx, (spec, stats) in enumerate(items):
+    ws, w = raw[idx]
+    out = {}
+    for s in stats:
+      slot = CRPS_SLOT[s.kind]
+      out[s.kind] = (
+          xl.DataArray((ws[:, slot] * spec.scalar).reshape(spec.kept_shape),
+                       spec.kept, coords=spec.coords, name=s.name),
+          xl.DataArray((w[:, slot] * spec.scalar).reshape(spec.kept_shape),
+                       spec.kept, coords=spec.coords, name=s.name))
+    results.append(out)
+  return results
 
 
 def crps_fields(stats, reduce_dims, device=None) -> dict | None:
