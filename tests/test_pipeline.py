@@ -378,3 +378,73 @@ def test_pipeline_two_ranks_gloo(reduce_dims):
       np.testing.assert_allclose(r[k], mono[k].values, rtol=1e-12)
   for k in mono:
     np.testing.assert_allclose(written[k].values, mono[k].values, rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# NetCDF-3 round trip (io_netcdf.py)
+# ---------------------------------------------------------------------------
+
+
+def test_netcdf_round_trip_of_every_coordinate_kind(tmp_path):
+  lead = LEAD[:3]
+  init = INIT[:2]
+  a = xl.DataArray(
+      np.random.default_rng(0).random((2, 3, 4)),
+      ('init_time', 'lead_time', 'level'),
+      coords={'init_time': init, 'lead_time': lead,
+              'level': np.array([500, 700, 850, 1000]),
+              'valid_time': xl.DataArray(init[:, None] + lead[None, :],
+                                         ('init_time', 'lead_time'))},
+      name='rmse.geopotential')
+  scalar = xl.DataArray(np.float64(3.5), ())
+  regions = xl.DataArray(np.array([1.0, np.nan]), ('region',),
+                         coords={'region': np.array(['global', 'tropics'])})
+  flags = xl.DataArray(np.array([True, False, True]), ('k',))
+  f32 = xl.DataArray(np.arange(4, dtype=np.float32), ('level',),
+                     coords={'level': np.array([500, 700, 850, 1000])})
+  ds = xl.Dataset({'rmse.geopotential': a,
+                   'SquaredError#z#sum_weights': scalar, 'by_region': regions,
+                   'flags': flags, 'f32': f32})
+  path = str(tmp_path / 'sub' / 'x.nc')
+  io_netcdf.to_netcdf(ds, path)
+  back = io_netcdf.open_dataset(path)
+  assert set(back) == set(ds)
+  for k in ds:
+    assert back[k].dims == ds[k].dims
+    np.testing.assert_array_equal(back[k].values, ds[k].values)
+    assert back[k].values.dtype == ds[k].values.dtype
+  z = back['rmse.geopotential']
+  assert z.coords['init_time'].values.dtype == np.dtype('datetime64[ns]')
+  assert z.coords['lead_time'].values.dtype == np.dtype('timedelta64[ns]')
+  np.testing.assert_array_equal(z.coords['valid_time'].values,
+                                a.coords['valid_time'].values)
+  assert back['by_region'].coords['region'].values.tolist() == [
+      'global', 'tropics']
+  assert not os.path.exists(path + '.tmp') and len(os.listdir(
+      os.path.dirname(path))) == 1            # atomic write left no temp file
+  # a dimension used with two sizes cannot be written
+  bad = xl.Dataset({'a': xl.DataArray(np.zeros(2), ('x',)),
+                    'b': xl.DataArray(np.zeros(3), ('x',))})
+  with pytest.raises(ValueError, match='has sizes'):
+    io_netcdf.to_netcdf(bad, str(tmp_path / 'bad.nc'))
+  assert not os.path.exists(str(tmp_path / 'bad.nc'))
+
+
+def test_window_view_only_for_lattices():
+  payload = np.arange(20 * 3, dtype=np.float32).reshape(20, 3)
+  lattice = 2 + 3 * np.arange(4)[:, None] + np.arange(5)[None, :]
+  view = array_loaders._window_view(payload, 0, lattice)
+  assert view.shape == (4, 5, 3) and np.shares_memory(view, payload)
+  np.testing.assert_array_equal(view, payload[lattice])
+  assert not view.flags.writeable
+  single = array_loaders._window_view(payload, 0, np.array([[7]]))
+  np.testing.assert_array_equal(single, payload[[[7]]])
+  irregular = lattice.copy()
+  irregular[2, 3] += 1
+  assert array_loaders._window_view(payload, 0, irregular) is None
+  assert array_loaders._window_view(payload, 0, lattice[::-1]) is None
+  # along a middle axis
+  cube = np.arange(2 * 12 * 3, dtype=np.float32).reshape(2, 12, 3)
+  pos = 1 + 2 * np.arange(3)[:, None] + np.arange(4)[None, :]
+  np.testing.assert_array_equal(array_loaders._window_view(cube, 1, pos),
+                                cube[:, pos])

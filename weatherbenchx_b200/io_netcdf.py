@@ -71,7 +71,9 @@ def _decode(values: np.ndarray, attrs: Mapping):
     flat = chars.reshape(-1, chars.shape[-1])
     text = np.array([b''.join(row).decode().rstrip() for row in flat])
     return text.reshape(chars.shape[:-1])
-  return np.array(values)
+  values = np.array(values)
+  # NetCDF-3 is big-endian on disk: hand back native byte order
+  return values.astype(values.dtype.newbyteorder('='))
 
 
 def to_netcdf(dataset: Mapping[str, xl.DataArray], path: str) -> None:
