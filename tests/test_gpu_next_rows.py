@@ -324,3 +324,80 @@ def test_subselect_and_select_wrappers():
                              np.sqrt(np.mean((p[:1] - t[:1]) ** 2)), rtol=RTOL)
   with pytest.raises(ValueError, match='Invalid value for `which`'):
     wrappers.EnsembleMean(which='nobody')
+
+
+# ---------------------------------------------------------------------------
+# EnsembleAveragedMetric (probabilistic.py:35-113)
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize('layout', ['member_major', 'reference_mock'])
+def test_ensemble_averaged_metric(layout):
+  """metrics_test.py:1276-1308: per-member RMSE through the wrapper == RMSE
+  with the ensemble dim among the aggregator's reduce_dims."""
+  from weatherbenchx_b200.metrics import probabilistic
+  if layout == 'reference_mock':
+    targets = utils.to_f32(utils.mock_prediction_data(
+        time_start='2020-01-01T00', time_stop='2020-01-03T00', random=True,
+        seed=0))
+    predictions = utils.to_f32(utils.mock_prediction_data(
+        time_start='2020-01-01T00', time_stop='2020-01-03T00', random=True,
+        ensemble_size=5, seed=1))
+    rd = ['latitude', 'longitude']
+  else:
+    rng = np.random.default_rng(0)
+    coords = dict(_coords(3, 12, 20), realization=np.arange(5))
+    predictions = {'t': xl.DataArray(
+        rng.normal(size=(3, 5, 12, 20)).astype(np.float32),
+        ('init_time', 'realization', 'latitude', 'longitude'), coords=coords,
+        name='t')}
+    targets = {'t': xl.DataArray(
+        rng.normal(size=(3, 12, 20)).astype(np.float32), DIMS,
+        coords={d: coords[d] for d in DIMS}, name='t')}
+    rd = ['init_time', 'latitude', 'longitude']
+  kw = dict(weigh_by=[weighting.GridAreaWeighting()])
+  explicit = {'rmse': deterministic.RMSE(), 'mae': deterministic.MAE()}
+  expected = _aggregate(explicit, predictions, targets,
+                        reduce_dims=rd + ['realization'], **kw
+                        ).metric_values(explicit)
+  wrapped = {k: probabilistic.EnsembleAveragedMetric(
+      m, ensemble_dim='realization') for k, m in explicit.items()}
+  names = {s.unique_name for m in wrapped.values()
+           for s in m.statistics.values()}
+  assert names == {'SquaredError_each_realization',
+                   'AbsoluteError_each_realization'}
+  state = _aggregate(wrapped, predictions, targets, reduce_dims=rd, **kw)
+  actual = state.metric_values(wrapped)
+  assert set(actual) == set(expected)
+  for k in expected:
+    assert actual[k].dims == expected[k].dims
+    np.testing.assert_allclose(actual[k].values, expected[k].values, rtol=RTOL)
+  if layout == 'member_major':
+    # the state is the mean-over-members one (weights of one member, not five)
+    w = oracle.grid_area_weights(predictions['t'].coords['latitude'].values)
+    np.testing.assert_allclose(
+        state.sum_weights['SquaredError_each_realization']['t'].values,
+        3 * 20 * w.sum(), rtol=1e-12)
+    p, t = predictions['t'].values, targets['t'].values
+    field = oracle.squared_error(p, t[:, None]).mean(1)
+    ws, sw, _ = oracle.aggregate(field, DIMS, rd,
+                                 weights=[(w, ('latitude',))])
+    np.testing.assert_allclose(actual['rmse.t'].values, np.sqrt(ws / sw),
+                               rtol=RTOL)
+    # NaN skipping needs the per-point member mean: generic path, same answer
+    p2 = p.copy()
+    p2[0, 2, 3, 4] = np.nan
+    pn = {'t': xl.DataArray(p2, predictions['t'].dims,
+                            coords=predictions['t'].coords, name='t')}
+    skip = {'rmse': probabilistic.EnsembleAveragedMetric(
+        deterministic.RMSE(), ensemble_dim='realization',
+        skipna_ensemble=True)}
+    got = _aggregate(skip, pn, targets, reduce_dims=rd, **kw
+                     ).metric_values(skip)
+    field = np.nanmean(oracle.squared_error(p2, t[:, None]), axis=1)
+    ws, sw, _ = oracle.aggregate(field, DIMS, rd,
+                                 weights=[(w, ('latitude',))])
+    np.testing.assert_allclose(got['rmse.t'].values, np.sqrt(ws / sw),
+                               rtol=RTOL)
+    with pytest.raises(ValueError, match='Failed to compute'):
+      _aggregate(wrapped, targets, targets, reduce_dims=rd)

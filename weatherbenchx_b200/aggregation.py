@@ -25,6 +25,7 @@ import numpy as np
 from weatherbenchx_b200 import engine
 from weatherbenchx_b200 import xarray_lite as xl
 from weatherbenchx_b200 import xarray_tree
+from weatherbenchx_b200.lazy import LazyEnsembleAveraged
 from weatherbenchx_b200.lazy import LazyPassthrough
 from weatherbenchx_b200.lazy import LazyStatistic
 from weatherbenchx_b200.lazy import LazySumStatistic
@@ -345,6 +346,17 @@ class Aggregator:
     if (isinstance(stat, LazySumStatistic) and stat.is_lazy and
         not self.skipna):
       return _add_states([self.aggregate_stat_var(p) for p in stat.parts])
+    if isinstance(stat, LazyEnsembleAveraged) and stat.is_lazy:
+      if self.skipna or stat.skipna_ensemble:
+        return self._aggregate_generic(stat)
+      nested = dataclasses.replace(
+          self, reduce_dims=list(self.reduce_dims) + [stat.ensemble_dim])
+      state = nested.aggregate_stat_var(stat.inner)
+      if state is None:
+        return None
+      scale = 1.0 / stat.n_members
+      return AggregationState(state.sum_weighted_statistics * scale,
+                              state.sum_weights * scale)
     if (isinstance(stat, LazyStatistic) and stat.is_lazy and
         not isinstance(stat, LazySumStatistic)):
       try:
@@ -374,12 +386,20 @@ class Aggregator:
     results: dict = {name: {} for name in statistics}
     groups: dict = collections.defaultdict(list)
     sums = []  # (stat_name, var, n_parts) of LazySumStatistic members
+    averaged: dict = {}  # ensemble dim -> members averaged over it
     for stat_name, per_var in statistics.items():
       for var, stat in per_var.items():
         if stat is None:
           continue
         stat = xl.as_data_array(stat)
-        if isinstance(stat, LazySumStatistic) and stat.is_lazy:
+        if isinstance(stat, LazyEnsembleAveraged) and stat.is_lazy:
+          if self.skipna or stat.skipna_ensemble:
+            # NaN skipping happens per point after / inside the member mean
+            results[stat_name][var] = self._aggregate_generic(stat)
+          else:
+            averaged.setdefault(stat.ensemble_dim, []).append(
+                (stat_name, var, stat))
+        elif isinstance(stat, LazySumStatistic) and stat.is_lazy:
           if self.skipna:
             # NaN of the SUM decides what is skipped: needs the summed field
             results[stat_name][var] = self._aggregate_generic(stat)
@@ -483,6 +503,23 @@ class Aggregator:
       for (members, _, _), out in zip(planned, outs):
         for stat_name, var, s in members:
           results[stat_name][var] = AggregationState(*out[s.kind])
+    for dim, members in averaged.items():
+      # mean over members then weighted sums == the fused reduction over
+      # reduce_dims + [ensemble dim], divided by the member count
+      nested = dataclasses.replace(
+          self, reduce_dims=list(self.reduce_dims) + [dim])
+      inner: dict = {}
+      for stat_name, var, stat in members:
+        inner.setdefault(stat_name, {})[var] = stat.inner
+      state = nested.aggregate_statistics(inner)
+      for stat_name, var, stat in members:
+        sws = state.sum_weighted_statistics[stat_name].get(var)
+        if sws is None:
+          results[stat_name][var] = None
+          continue
+        scale = 1.0 / stat.n_members
+        results[stat_name][var] = AggregationState(
+            sws * scale, state.sum_weights[stat_name][var] * scale)
     for stat_name, var, n_parts in sums:
       results[stat_name][var] = _add_states(
           [results[('__part__', stat_name, var, i)].get(var)

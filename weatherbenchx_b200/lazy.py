@@ -157,6 +157,56 @@ class LazyPassthrough(LazyStatistic):
     self._coords = xl._merge_coords(source, other, self.dims)  # pylint: disable=protected-access
 
 
+class LazyEnsembleAveraged(LazyStatistic):
+  """Mean of a lazy statistic over the ensemble dimension
+  (EnsembleAveragedStatistic.compute, probabilistic.py:56-69).
+
+  Without NaN skipping the mean over members followed by the weighted spatial
+  sums equals the fused reduction of the inner statistic over
+  ``reduce_dims + [ensemble_dim]`` divided by the member count; that is how the
+  Aggregator evaluates it.  ``.values`` gives the per-point mean field.
+  """
+
+  def __init__(self, inner: LazyStatistic, ensemble_dim, skipna_ensemble: bool):
+    if ensemble_dim not in inner.dims:
+      raise ValueError(f'Dimension {ensemble_dim} not found in {inner.dims}')
+    self.kind = inner.kind
+    self.inner = inner
+    self.ensemble_dim = ensemble_dim
+    self.skipna_ensemble = bool(skipna_ensemble)
+    self.predictions = inner.predictions
+    self.targets = inner.targets
+    self.climatology = inner.climatology
+    self.dims = tuple(d for d in inner.dims if d != ensemble_dim)
+    self._sizes = {d: inner.sizes[d] for d in self.dims}
+    self.name = inner.name
+    self.attrs = {}
+    self._coords = {k: v for k, v in inner.coords.items()
+                    if ensemble_dim not in v.dims}
+    self._materialized = None
+
+  @property
+  def n_members(self) -> int:
+    return self.inner.sizes[self.ensemble_dim]
+
+  def group_key(self):
+    return ('ensemble-mean', self.ensemble_dim) + tuple(self.inner.group_key())
+
+  @property
+  def _data(self):
+    if self._materialized is None:
+      from weatherbenchx_b200 import engine  # pylint: disable=g-import-not-at-top
+      field = xl.DataArray(self.inner.data, self.inner.dims,
+                           coords=self.inner.coords, name=self.name)
+      self._materialized = engine.ensemble_mean(
+          field, self.ensemble_dim, skipna=self.skipna_ensemble).data
+    return self._materialized
+
+  @_data.setter
+  def _data(self, value):
+    self._materialized = value
+
+
 class LazySumStatistic(LazyStatistic):
   """Sum of lazy statistics on a common grid (WindVectorSquaredError =
   SquaredError(u) + SquaredError(v), deterministic.py:206-219).

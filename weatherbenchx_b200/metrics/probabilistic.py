@@ -26,6 +26,68 @@ from weatherbenchx_b200.metrics import base
 ENSEMBLE_DIM = 'number'
 
 
+class EnsembleAveragedStatistic(base.Statistic):
+  """A statistic averaged over the ensemble dimension (per-member scores).
+
+  Reference: probabilistic.py:35-69.  Lazy statistics stay lazy: the
+  Aggregator folds the ensemble average into the fused reduction.
+  """
+
+  def __init__(self, wrapped_statistic: base.Statistic, *, ensemble_dim: str,
+               skipna_ensemble: bool):
+    self._wrapped_statistic = wrapped_statistic
+    self._ensemble_dim = ensemble_dim
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def unique_name(self) -> str:
+    return self._wrapped_statistic.unique_name + '_each_' + self._ensemble_dim
+
+  def compute(self, predictions, targets):
+    from weatherbenchx_b200 import engine  # pylint: disable=g-import-not-at-top
+    from weatherbenchx_b200 import xarray_lite as xl  # pylint: disable=g-import-not-at-top
+    from weatherbenchx_b200.lazy import LazyEnsembleAveraged  # pylint: disable=g-import-not-at-top
+    from weatherbenchx_b200.lazy import LazyStatistic  # pylint: disable=g-import-not-at-top
+    statistics = self._wrapped_statistic.compute(predictions, targets)
+    out = {}
+    for var, da in statistics.items():
+      da = xl.as_data_array(da)
+      if self._ensemble_dim not in da.dims:
+        raise ValueError(
+            f'Dimension {self._ensemble_dim} not found in {da.dims}')
+      if (isinstance(da, LazyStatistic) and da.is_lazy and
+          type(da) is LazyStatistic):
+        out[var] = LazyEnsembleAveraged(da, self._ensemble_dim,
+                                        self._skipna_ensemble)
+      else:
+        out[var] = engine.ensemble_mean(da, self._ensemble_dim,
+                                        skipna=self._skipna_ensemble)
+    return out
+
+
+class EnsembleAveragedMetric(base.Metric):
+  """Wraps a metric so that its statistics are averaged over the ensemble
+  dimension, i.e. deterministic scores of the individual members
+  (probabilistic.py:72-113)."""
+
+  def __init__(self, wrapped_metric: base.Metric, *,
+               ensemble_dim: str = ENSEMBLE_DIM, skipna_ensemble: bool = False):
+    self._wrapped_metric = wrapped_metric
+    self._ensemble_dim = ensemble_dim
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def statistics(self) -> Mapping[str, base.Statistic]:
+    return {
+        name: EnsembleAveragedStatistic(
+            wrapped_statistic=stat, ensemble_dim=self._ensemble_dim,
+            skipna_ensemble=self._skipna_ensemble)
+        for name, stat in self._wrapped_metric.statistics.items()}
+
+  def values_from_mean_statistics(self, statistic_values):
+    return self._wrapped_metric.values_from_mean_statistics(statistic_values)
+
+
 class CRPSSkill(base.PerVariableStatistic):
   """The skill term of CRPS, E|X - Y|."""
 
