@@ -102,8 +102,10 @@ def aggregate(stat: xl.DataArray, factors: Sequence[xl.DataArray],
     desc.reduced[i] = 1 if d in reduce_set else 0
 
   if (isinstance(stat, LazyStatistic) and stat.is_lazy and
-      stat.kind not in _cabi.STAT_SLOT):
-    stat = stat._replace()  # materialise (e.g. CRPS fields)  pylint: disable=protected-access
+      (stat.kind not in _cabi.STAT_SLOT or not stat.elementwise_of_operands)):
+    # CRPS fields, sums of statistics, member means: not an elementwise
+    # function of (predictions, targets[, climatology]) -- materialise
+    stat = stat._replace()  # pylint: disable=protected-access
   if isinstance(stat, LazyStatistic) and stat.is_lazy:
     desc.op = _cabi.STAT_SLOT[stat.kind]
     ta, da_ = _device_tensor(stat.predictions, 'field', device)

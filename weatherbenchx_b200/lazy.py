@@ -56,6 +56,10 @@ class AlignedClimatology:
 class LazyStatistic(xl.DataArray):
   """A per-gridpoint statistic that is evaluated on demand."""
 
+  # True when the field is `kind` applied elementwise to (predictions, targets
+  # [, climatology]); composite handles (sums, member means) say False.
+  elementwise_of_operands = True
+
   def __init__(self, kind: str, predictions: xl.DataArray,
                targets: xl.DataArray,
                climatology: AlignedClimatology | None = None):
@@ -167,6 +171,8 @@ class LazyEnsembleAveraged(LazyStatistic):
   Aggregator evaluates it.  ``.values`` gives the per-point mean field.
   """
 
+  elementwise_of_operands = False
+
   def __init__(self, inner: LazyStatistic, ensemble_dim, skipna_ensemble: bool):
     if ensemble_dim not in inner.dims:
       raise ValueError(f'Dimension {ensemble_dim} not found in {inner.dims}')
@@ -215,6 +221,8 @@ class LazySumStatistic(LazyStatistic):
   any other statistic of the same operands, e.g. the per-component RMSE -- and
   adds the states; ``.values`` gives the summed field.
   """
+
+  elementwise_of_operands = False
 
   def __init__(self, kind: str, parts: Sequence[LazyStatistic], name=None):
     first = parts[0]
