@@ -19,7 +19,7 @@ a pinned or memory-mapped array goes to the GPU straight from its source.
 
 from __future__ import annotations
 
-from typing import Hashable, Iterable, Mapping, Optional, Union
+from typing import Hashable, Iterable, Mapping, Optional
 
 import numpy as np
 

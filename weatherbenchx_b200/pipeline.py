@@ -40,7 +40,7 @@ import queue
 import tempfile
 import threading
 import time
-from typing import Any, Callable, Mapping, Optional
+from typing import Callable, Mapping, Optional
 
 from weatherbenchx_b200 import aggregation
 from weatherbenchx_b200 import distributed
