@@ -630,3 +630,45 @@ def test_auto_kernel_policy(members, layout, expect_sort, monkeypatch):
   expect = (oracle.crps_skill(x, y, axis).mean() -
             0.5 * oracle.crps_spread(x, axis, fair=True).mean())
   np.testing.assert_allclose(values['crps.t'].values, expect, rtol=RTOL)
+
+
+@pytest.mark.parametrize('space', ['host', 'device'])
+def test_variables_of_a_chunk_share_one_ensemble_launch(space):
+  """Two variables on the same grid: one merged launch (job tables
+  concatenated, cells offset), results identical to evaluating them alone."""
+  rng = np.random.default_rng(31)
+  members, n_init, nlat, nlon = 9, 2, 8, 16
+  coords = {'init_time': np.arange(n_init), 'number': np.arange(members),
+            'latitude': np.linspace(-70, 70, nlat),
+            'longitude': np.arange(nlon) * 22.5}
+  dims = ('init_time', 'latitude', 'longitude')
+  P, T = {}, {}
+  for v in ('a', 'b'):
+    x = rng.normal(size=(n_init, members, nlat, nlon)).astype(np.float32)
+    y = rng.normal(size=(n_init, nlat, nlon)).astype(np.float32)
+    X = xl.DataArray(x, ('init_time', 'number', 'latitude', 'longitude'),
+                     coords=coords, name=v)
+    Y = xl.DataArray(y, dims, coords={d: coords[d] for d in dims}, name=v)
+    if space == 'device':
+      X, Y = engine.to_device(X), engine.to_device(Y)
+    P[v], T[v] = X, Y
+  metrics = {'crps': probabilistic.CRPSEnsemble(),
+             'ssr': probabilistic.UnbiasedSpreadSkillRatio()}
+  kw = dict(weigh_by=[weighting.GridAreaWeighting()])
+  rd = ['latitude', 'longitude']
+  ctx = _cabi.get_context()
+  both = compute_all_metrics(metrics, P, T, rd, **kw)      # warms the plans
+  n0 = ctx.kernel_launches()
+  both = compute_all_metrics(metrics, P, T, rd, **kw)
+  merged_launches = ctx.kernel_launches() - n0
+  n0 = ctx.kernel_launches()
+  alone = {}
+  for v in ('a', 'b'):
+    alone.update(compute_all_metrics(metrics, {v: P[v]}, {v: T[v]}, rd, **kw))
+  separate_launches = ctx.kernel_launches() - n0
+  if space == 'device':
+    assert merged_launches * 2 == separate_launches
+  assert set(both) == set(alone) == {'crps.a', 'crps.b', 'ssr.a', 'ssr.b'}
+  for k in alone:
+    assert both[k].dims == ('init_time',)
+    np.testing.assert_array_equal(both[k].values, alone[k].values)

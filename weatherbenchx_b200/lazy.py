@@ -63,7 +63,11 @@ class LazyStatistic(xl.DataArray):
   def __init__(self, kind: str, predictions: xl.DataArray,
                targets: xl.DataArray,
                climatology: AlignedClimatology | None = None):
-    xl._check_index_coords(predictions, targets)  # pylint: disable=protected-access
+    same_grid = (predictions.dims == targets.dims and
+                 predictions.shape == targets.shape and
+                 xl._same_coords(predictions._coords, targets._coords))  # pylint: disable=protected-access
+    if not same_grid:
+      xl._check_index_coords(predictions, targets)  # pylint: disable=protected-access
     dims = predictions.dims + tuple(
         d for d in targets.dims if d not in predictions.dims)
     sizes = dict(targets.sizes, **predictions.sizes)
@@ -83,7 +87,8 @@ class LazyStatistic(xl.DataArray):
     self._sizes = {d: sizes[d] for d in dims}
     self.name = predictions.name
     self.attrs = {}
-    self._coords = xl._merge_coords(predictions, targets, dims)  # pylint: disable=protected-access
+    self._coords = (dict(predictions._coords) if same_grid else  # pylint: disable=protected-access
+                    xl._merge_coords(predictions, targets, dims))  # pylint: disable=protected-access
     self._materialized = None
 
   # -- metadata without materialising ---------------------------------------
