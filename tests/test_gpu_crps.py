@@ -671,4 +671,5 @@ def test_variables_of_a_chunk_share_one_ensemble_launch(space):
   assert set(both) == set(alone) == {'crps.a', 'crps.b', 'ssr.a', 'ssr.b'}
   for k in alone:
     assert both[k].dims == ('init_time',)
-    np.testing.assert_array_equal(both[k].values, alone[k].values)
+    # another tile partition over the CTAs: same sums up to f64 rounding
+    np.testing.assert_allclose(both[k].values, alone[k].values, rtol=1e-12)
