@@ -681,3 +681,74 @@ def test_fused_bins_full_size_public_benchmark_regions(quarter_degree):
   again = agg.aggregate_statistics(stats)
   assert (again.sum_weighted_statistics['SquaredError']['t2m'].values.tobytes()
           == got.values.tobytes())
+
+
+# ---------------------------------------------------------------------------
+# longitude-major storage (latitude fastest): the latitude weight is w_x
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize('space', ['host', 'device'])
+@pytest.mark.parametrize('nlat', [24, 19, 721])
+@pytest.mark.parametrize('mode', ['propagate', 'masked', 'skipna'])
+def test_lon_major_layout_matches_oracle(space, nlat, mode):
+  """[init, longitude, latitude] arrays as in the 1440x721 archives: rows of
+  the slab are meridians, so the area weight varies along the row.  nlat = 24
+  takes the vectorised w_x path, 19 / 721 (odd: groups straddle rows) the
+  per-element one."""
+  rng = np.random.default_rng(nlat)
+  n_init, n_lead, nlon = 3, 2, 16 if nlat < 100 else 8
+  dims = ('init_time', 'lead_time', 'longitude', 'latitude')
+  coords = {'init_time': np.arange(n_init),
+            'lead_time': (np.arange(n_lead) * np.timedelta64(6, 'h')
+                          ).astype('timedelta64[ns]'),
+            'longitude': np.linspace(0, 360, nlon, endpoint=False),
+            'latitude': np.linspace(-90, 90, nlat)}
+  shape = (n_init, n_lead, nlon, nlat)
+  p = rng.normal(280, 5, shape).astype(np.float32)
+  t = (p + rng.normal(0, 2, shape)).astype(np.float32)
+  c = rng.normal(280, 3, (366, 4, nlon, nlat)).astype(np.float32)
+  if mode != 'propagate':
+    t[rng.random(shape) < 0.05] = np.nan
+  coords['init_time'] = (np.datetime64('2020-02-27T00', 'ns') +
+                         np.arange(n_init) * np.timedelta64(12, 'h'))
+  P = xl.DataArray(p, dims, coords=coords, name='z')
+  T = xl.DataArray(t, dims, coords=coords, name='z')
+  C = xl.DataArray(c, ('dayofyear', 'hour', 'longitude', 'latitude'),
+                   coords={'dayofyear': np.arange(1, 367),
+                           'hour': np.arange(0, 24, 6),
+                           'longitude': coords['longitude'],
+                           'latitude': coords['latitude']}, name='z')
+  mask_np = ~np.isnan(t)
+  if mode == 'masked':
+    T = T.assign_coords(mask=xl.DataArray(mask_np, dims))
+  if space == 'device':
+    P, C = engine.to_device(P), engine.to_device(C)
+    Td = engine.to_device(T)
+    if mode == 'masked':
+      Td = Td.assign_coords(mask=engine.to_device(xl.DataArray(mask_np, dims)))
+    T = Td
+  rd = ['init_time', 'lead_time', 'longitude', 'latitude']
+  metrics = {'rmse': deterministic.RMSE(), 'mae': deterministic.MAE(),
+             'acc': deterministic.ACC({'z': C})}
+  state = _aggregate(metrics, {'z': P}, {'z': T}, reduce_dims=rd,
+                     weigh_by=[weighting.GridAreaWeighting()],
+                     masked=mode == 'masked', skipna=mode == 'skipna')
+  w = oracle.grid_area_weights(coords['latitude'])
+  aligned, adims = oracle.align_climatology(
+      c, ('dayofyear', 'hour', 'longitude', 'latitude'),
+      {'dayofyear': np.arange(1, 367), 'hour': np.arange(0, 24, 6)},
+      coords['init_time'], coords['lead_time'])
+  aligned = np.transpose(aligned, [adims.index(d) for d in dims])
+  fields = {'SquaredError': oracle.squared_error(p, t),
+            'AbsoluteError': oracle.absolute_error(p, t)}
+  fields.update({n: f(p, t, aligned)
+                 for n, f in oracle.CLIMATOLOGY_STATISTICS.items()})
+  for name, field in fields.items():
+    sws, sw, _ = oracle.aggregate(
+        field, dims, rd, weights=[(w, ('latitude',))], mask=mask_np,
+        mask_dims=dims, masked=mode == 'masked', skipna=mode == 'skipna')
+    got_ws = state.sum_weighted_statistics[name]['z'].values
+    got_w = state.sum_weights[name]['z'].values
+    np.testing.assert_allclose(got_ws, sws, rtol=RTOL, equal_nan=True)
+    np.testing.assert_allclose(got_w, sw, rtol=1e-10)

@@ -464,8 +464,10 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
   }
   // weights (shared by both spaces)
   {
-    const size_t bytes = (p->wy.size() + p->wx.size()) * sizeof(double);
-    if (bytes) {
+    // w_x starts on a 16-byte boundary (it is read with double2 loads)
+    const size_t wx_off = (p->wy.size() + 1) / 2 * 2;
+    const size_t bytes = (wx_off + p->wx.size()) * sizeof(double);
+    if (p->wy.size() + p->wx.size()) {
       int rc = p->weights.reserve(bytes);
       if (rc != WBX_OK) { delete p; return rc; }
       double* base = p->weights.as<double>();
@@ -476,10 +478,10 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
         p->d_wy = base;
       }
       if (p->has_wx) {
-        WBX_CUDA(cudaMemcpyAsync(base + p->wy.size(), p->wx.data(),
+        WBX_CUDA(cudaMemcpyAsync(base + wx_off, p->wx.data(),
                                  p->wx.size() * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->stream));
-        p->d_wx = base + p->wy.size();
+        p->d_wx = base + wx_off;
       }
     }
   }

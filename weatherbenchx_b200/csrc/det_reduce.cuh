@@ -155,6 +155,45 @@ __device__ __forceinline__ void accum_row4(const float4 p, const float4 t,
   }
 }
 
+// Four consecutive points of one row whose weight varies along the row
+// (w_x: the latitude axis is the fastest one, as in the lon-major WeatherBench
+// archives): the four column weights come in as two 16-byte loads, the
+// weighted 4-sum is taken in f64 and folded with the row weight by one FMA.
+template <bool CLIM, bool MASK, bool SKIPNA>
+__device__ __forceinline__ void accum_row4_wx(const float4 p, const float4 t,
+                                              const float4 c, const uchar4 m,
+                                              const double wrow,
+                                              const double* __restrict__ wx4,
+                                              const int stat_mask,
+                                              double* acc) {
+  using L = AccLayout<CLIM, MASK, SKIPNA>;
+  PointStats<CLIM, MASK, SKIPNA> q0, q1, q2, q3;
+  q0.eval(p.x, t.x, c.x, m.x);
+  q1.eval(p.y, t.y, c.y, m.y);
+  q2.eval(p.z, t.z, c.z, m.z);
+  q3.eval(p.w, t.w, c.w, m.w);
+  const double2 wa = __ldg(reinterpret_cast<const double2*>(wx4));
+  const double2 wb = __ldg(reinterpret_cast<const double2*>(wx4) + 1);
+#pragma unroll
+  for (int k = 0; k < L::kStats; ++k) {
+    if (stat_mask & (1 << k)) {  // warp-uniform
+      double s4 = static_cast<double>(q3.s[k]) * wb.y;
+      s4 = fma(static_cast<double>(q2.s[k]), wb.x, s4);
+      s4 = fma(static_cast<double>(q1.s[k]), wa.y, s4);
+      s4 = fma(static_cast<double>(q0.s[k]), wa.x, s4);
+      acc[k] = fma(s4, wrow, acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < L::kWeights; ++k) {
+    double n4 = static_cast<double>(q3.valid[k]) * wb.y;
+    n4 = fma(static_cast<double>(q2.valid[k]), wb.x, n4);
+    n4 = fma(static_cast<double>(q1.valid[k]), wa.y, n4);
+    n4 = fma(static_cast<double>(q0.valid[k]), wa.x, n4);
+    acc[L::kStats + k] = fma(n4, wrow, acc[L::kStats + k]);
+  }
+}
+
 template <bool CLIM, bool MASK, bool SKIPNA>
 __device__ __forceinline__ void accum_point(float p, float t, float c,
                                             unsigned char m, const double w,
@@ -175,6 +214,7 @@ struct WeightCursor {
   const double* wy;
   const double* wx;
   int nx;
+  bool wx4_ok;  // w_x present, nx % 4 == 0, table 16-byte aligned
   __device__ __forceinline__ double row(unsigned y, double wo) const {
     return wy ? wo * __ldg(wy + y) : wo;
   }
@@ -194,6 +234,10 @@ __device__ __forceinline__ void accum_group4(const float4 p, const float4 t,
                                              double* acc) {
   if constexpr (!PER_ELEM) {
     accum_row4<CLIM, MASK, SKIPNA>(p, t, c, m, wc.row(y, wo), stat_mask, acc);
+  } else if (wc.wx4_ok) {
+    // rows are a multiple of four long: the group stays in its row
+    accum_row4_wx<CLIM, MASK, SKIPNA>(p, t, c, m, wc.row(y, wo), wc.wx + x,
+                                      stat_mask, acc);
   } else {
     const float pp[4] = {p.x, p.y, p.z, p.w};
     const float tt[4] = {t.x, t.y, t.z, t.w};
@@ -326,7 +370,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   double acc[L::kAcc];
 #pragma unroll
   for (int a = 0; a < L::kAcc; ++a) acc[a] = 0.0;
-  const WeightCursor wc{P.w_y, P.w_x, P.nx};
+  const WeightCursor wc{
+      P.w_y, P.w_x, P.nx,
+      P.w_x != nullptr && (P.nx & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(P.w_x) & 15) == 0};
   int cur_cell = -1;
   const int ctid = threadIdx.x;  // 0 .. kConsumerThreads-1
   const unsigned unx = static_cast<unsigned>(P.nx);
@@ -421,7 +468,10 @@ __global__ void __launch_bounds__(kLdgThreads)
   double acc[L::kAcc];
 #pragma unroll
   for (int a = 0; a < L::kAcc; ++a) acc[a] = 0.0;
-  const WeightCursor wc{P.w_y, P.w_x, P.nx};
+  const WeightCursor wc{
+      P.w_y, P.w_x, P.nx,
+      P.w_x != nullptr && (P.nx & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(P.w_x) & 15) == 0};
   int cur_cell = -1;
   long long job = t_begin / P.tiles_per_slab;
   int k = static_cast<int>(t_begin - job * P.tiles_per_slab);
