@@ -159,7 +159,7 @@ __device__ __forceinline__ void accum_row4(const float4 p, const float4 t,
 // (w_x: the latitude axis is the fastest one, as in the lon-major WeatherBench
 // archives): the four column weights come in as two 16-byte loads, the
 // weighted 4-sum is taken in f64 and folded with the row weight by one FMA.
-template <bool CLIM, bool MASK, bool SKIPNA>
+template <bool CLIM, bool MASK, bool SKIPNA, bool ALIGNED>
 __device__ __forceinline__ void accum_row4_wx(const float4 p, const float4 t,
                                               const float4 c, const uchar4 m,
                                               const double wrow,
@@ -172,8 +172,14 @@ __device__ __forceinline__ void accum_row4_wx(const float4 p, const float4 t,
   q1.eval(p.y, t.y, c.y, m.y);
   q2.eval(p.z, t.z, c.z, m.z);
   q3.eval(p.w, t.w, c.w, m.w);
-  const double2 wa = __ldg(reinterpret_cast<const double2*>(wx4));
-  const double2 wb = __ldg(reinterpret_cast<const double2*>(wx4) + 1);
+  double2 wa, wb;
+  if constexpr (ALIGNED) {
+    wa = __ldg(reinterpret_cast<const double2*>(wx4));
+    wb = __ldg(reinterpret_cast<const double2*>(wx4) + 1);
+  } else {  // odd row lengths: the group starts at any column
+    wa = make_double2(__ldg(wx4), __ldg(wx4 + 1));
+    wb = make_double2(__ldg(wx4 + 2), __ldg(wx4 + 3));
+  }
 #pragma unroll
   for (int k = 0; k < L::kStats; ++k) {
     if (stat_mask & (1 << k)) {  // warp-uniform
@@ -236,8 +242,13 @@ __device__ __forceinline__ void accum_group4(const float4 p, const float4 t,
     accum_row4<CLIM, MASK, SKIPNA>(p, t, c, m, wc.row(y, wo), stat_mask, acc);
   } else if (wc.wx4_ok) {
     // rows are a multiple of four long: the group stays in its row
-    accum_row4_wx<CLIM, MASK, SKIPNA>(p, t, c, m, wc.row(y, wo), wc.wx + x,
-                                      stat_mask, acc);
+    accum_row4_wx<CLIM, MASK, SKIPNA, true>(p, t, c, m, wc.row(y, wo),
+                                            wc.wx + x, stat_mask, acc);
+  } else if (wc.wx != nullptr && x + 3u < static_cast<unsigned>(wc.nx)) {
+    // odd row length (e.g. 721 latitudes): all but the groups that straddle
+    // a row end still share one row weight
+    accum_row4_wx<CLIM, MASK, SKIPNA, false>(p, t, c, m, wc.row(y, wo),
+                                             wc.wx + x, stat_mask, acc);
   } else {
     const float pp[4] = {p.x, p.y, p.z, p.w};
     const float tt[4] = {t.x, t.y, t.z, t.w};
