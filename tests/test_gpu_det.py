@@ -752,3 +752,57 @@ def test_lon_major_layout_matches_oracle(space, nlat, mode):
     got_w = state.sum_weights[name]['z'].values
     np.testing.assert_allclose(got_ws, sws, rtol=RTOL, equal_nan=True)
     np.testing.assert_allclose(got_w, sw, rtol=1e-10)
+
+
+@pytest.mark.parametrize('space', ['host', 'device'])
+@pytest.mark.parametrize('masked', [False, True])
+@pytest.mark.parametrize('nlat', [24, 19])
+def test_fused_bins_lon_major(space, masked, nlat, monkeypatch):
+  """Region / land-sea bins on [.., longitude, latitude] arrays: the binned
+  kernel weighs every element (w_x; odd row lengths too) instead of falling
+  back to the generic reduction."""
+  P, T, C, land = _bin_case(11, shape=(3, 2, nlat, 48))
+  order = ('init_time', 'lead_time', 'longitude', 'latitude')
+  mask_np = np.random.default_rng(5).random(P.shape) > 0.2
+  mask = xl.DataArray(mask_np, P.dims)
+  P, T = P.transpose(*order), T.transpose(*order)
+  P = xl.DataArray(np.ascontiguousarray(P.values), order, coords=P.coords,
+                   name='z')
+  T = xl.DataArray(np.ascontiguousarray(T.values), order, coords=T.coords,
+                   name='z')
+  if masked:
+    T = T.assign_coords(mask=xl.DataArray(
+        np.ascontiguousarray(mask.transpose(*order).values), order))
+  if space == 'device':
+    P, T = engine.to_device(P), engine.to_device(T)
+    if masked:
+      T = T.assign_coords(mask=engine.to_device(xl.DataArray(
+          np.ascontiguousarray(mask.transpose(*order).values), order)))
+  bin_by = [binning.Regions(REGIONS, land_sea_mask=land)]
+  from weatherbenchx_b200 import generic
+  monkeypatch.setattr(generic, 'aggregate', lambda *a, **k: (_ for _ in ()).throw(
+      AssertionError('generic path used')))
+  rd = ['init_time', 'latitude', 'longitude']
+  metrics = {'rmse': deterministic.RMSE(), 'bias': deterministic.Bias()}
+  state = _aggregate(metrics, {'z': P}, {'z': T}, reduce_dims=rd,
+                     weigh_by=[weighting.GridAreaWeighting()], bin_by=bin_by,
+                     masked=masked)
+  Ph, Th = P.to_host(), T.to_host()
+  m1 = bin_by[0].create_bin_mask(Ph).values    # (region, lat, lon) order below
+  m1 = np.asarray(bin_by[0].create_bin_mask(
+      Ph.transpose('init_time', 'lead_time', 'latitude', 'longitude')).values)
+  w = oracle.grid_area_weights(Ph.coords['latitude'].values)
+  pv = Ph.transpose('init_time', 'lead_time', 'latitude', 'longitude').values
+  tv = Th.transpose('init_time', 'lead_time', 'latitude', 'longitude').values
+  dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+  for name, field in (('SquaredError', oracle.squared_error(pv, tv)),
+                      ('Error', oracle.error(pv, tv))):
+    sws, sw, odims = oracle.aggregate(
+        field, dims, rd, weights=[(w, ('latitude',))],
+        bin_masks=[(m1, ('region', 'latitude', 'longitude'))],
+        mask=mask_np, mask_dims=dims, masked=masked)
+    got_ws = state.sum_weighted_statistics[name]['z'].transpose(*odims).values
+    got_w = state.sum_weights[name]['z'].transpose(*odims).values
+    np.testing.assert_allclose(got_ws, sws, rtol=RTOL,
+                               atol=1e-6 * np.abs(sws).max())
+    np.testing.assert_allclose(got_w, sw, rtol=1e-10)

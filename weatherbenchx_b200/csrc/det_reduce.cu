@@ -92,20 +92,26 @@ static int launch_bins(wbx_ctx* ctx, const wbx_det_plan* plan,
                        const DetParams& P, int grid) {
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
-#define WBX_BINS_LAUNCH(A, B)                                                  \
+#define WBX_BINS_LAUNCH2(A, B, W)                                              \
   do {                                                                         \
-    auto kern = det_reduce_bins_kernel<A, B>;                                  \
+    auto kern = det_reduce_bins_kernel<A, B, W>;                               \
     WBX_CUDA(cudaFuncSetAttribute(kern,                                        \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   static_cast<int>(plan->smem_bytes)));        \
     kern<<<grid, kTmaThreads, plan->smem_bytes, ctx->stream>>>(                \
         P, plan->bins, plan->stages, plan->stage_bytes);                       \
   } while (0)
+#define WBX_BINS_LAUNCH(A, B)                                                  \
+  do {                                                                         \
+    if (plan->has_wx || (plan->nx % 4) != 0) WBX_BINS_LAUNCH2(A, B, true);     \
+    else WBX_BINS_LAUNCH2(A, B, false);                                        \
+  } while (0)
   if (plan->has_clim && plan->has_mask) WBX_BINS_LAUNCH(true, true);
   else if (plan->has_clim) WBX_BINS_LAUNCH(true, false);
   else if (plan->has_mask) WBX_BINS_LAUNCH(false, true);
   else WBX_BINS_LAUNCH(false, false);
 #undef WBX_BINS_LAUNCH
+#undef WBX_BINS_LAUNCH2
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   return ctx->prof_end();
@@ -379,13 +385,11 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     p->bins.n_classes = d->n_classes;
     p->nacc = d->n_classes * nsel;
     const int64_t slab_ = d->ny * d->nx;
-    const bool ok = !p->skipna && !p->has_wx && (d->nx % 4) == 0 &&
-                    (slab_ % 16) == 0 && p->nacc <= 448;
+    const bool ok = !p->skipna && (slab_ % 16) == 0 && p->nacc <= 448;
     if (!ok) {
       delete p;
       wbx::set_error("det: this binned request needs the generic path "
-                     "(skipna, w_x, nx %% 4, slab %% 16 or too many "
-                     "classes x statistics)");
+                     "(skipna, slab %% 16 or too many classes x statistics)");
       return WBX_ERR_UNSUPPORTED;
     }
     p->class_w.assign(d->n_classes, 0.0);
@@ -396,7 +400,8 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
         wbx::set_error("det: class_map value %d >= n_classes", c);
         return WBX_ERR_INVALID;
       }
-      p->class_w[c] += p->has_wy ? d->w_y[e / d->nx] : 1.0;
+      p->class_w[c] += (p->has_wy ? d->w_y[e / d->nx] : 1.0) *
+                       (p->has_wx ? d->w_x[e % d->nx] : 1.0);
     }
   }
 

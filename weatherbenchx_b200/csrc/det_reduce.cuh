@@ -598,7 +598,11 @@ __device__ __forceinline__ float warp_sum_f32(float v) {
   return v;
 }
 
-template <bool CLIM, bool MASK>
+// WX: the weight varies along the rows of the slab (w_x; longitude-major
+// storage) and / or rows are not a multiple of four long: every element gets
+// its own f64 weight w_outer * w_y[y] * w_x[x], lanes are keyed by class alone
+// and reduced in f64.
+template <bool CLIM, bool MASK, bool WX>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     det_reduce_bins_kernel(const DetParams P, const BinParams B,
                            const int stages, const int stage_bytes) {
@@ -718,6 +722,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       float ok[4] = {1.f, 1.f, 1.f, 1.f};
       unsigned char cls[4] = {0, 0, 0, 0};
       double wrow = 0.0;
+      double wel[4] = {0.0, 0.0, 0.0, 0.0};  // WX: weight of every element
       unsigned y = 0;
       if (active) {
         const float4 pv = sp[j];
@@ -743,10 +748,24 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         const unsigned e = static_cast<unsigned>(mt.e0 + 4 * j);
         y = e / unx;
         wrow = mt.wo * (P.w_y ? __ldg(P.w_y + y) : 1.0);
+        if constexpr (WX) {
+          unsigned xi = e - y * unx, yi = y;
+          double wr = wrow;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            wel[i] = P.w_x ? wr * __ldg(P.w_x + xi) : wr;
+            if (++xi == unx) {
+              xi = 0;
+              ++yi;
+              wr = mt.wo * (P.w_y ? __ldg(P.w_y + yi) : 1.0);
+            }
+          }
+        }
       }
       const bool uniform = active && cls[0] == cls[1] && cls[1] == cls[2] &&
                            cls[2] == cls[3];
-      const int key = static_cast<int>((y << 8) | cls[0]);
+      const int key = WX ? static_cast<int>(cls[0])
+                         : static_cast<int>((y << 8) | cls[0]);
       // ---- uniform lanes: one warp reduction per distinct (row, class) -----
       unsigned um = __ballot_sync(0xffffffffu, uniform);
       while (um) {
@@ -758,18 +777,44 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
           if (P.stat_mask & (1 << k)) {  // warp-uniform
-            const float v =
-                mine ? (val[0][k] + val[1][k]) + (val[2][k] + val[3][k]) : 0.f;
-            const float tot = warp_sum_f32(v);
-            if (lane == 0)
-              slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
-                  static_cast<double>(tot) * lw;
+            if constexpr (WX) {
+              double v = 0.0;
+              if (mine) {
+                v = static_cast<double>(val[3][k]) * wel[3];
+                v = fma(static_cast<double>(val[2][k]), wel[2], v);
+                v = fma(static_cast<double>(val[1][k]), wel[1], v);
+                v = fma(static_cast<double>(val[0][k]), wel[0], v);
+              }
+              const double tot = warp_sum(v);
+              if (lane == 0)
+                slot[__popc(P.stat_mask & ((1 << k) - 1))] += tot;
+            } else {
+              const float v = mine ? (val[0][k] + val[1][k]) +
+                                         (val[2][k] + val[3][k])
+                                   : 0.f;
+              const float tot = warp_sum_f32(v);
+              if (lane == 0)
+                slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
+                    static_cast<double>(tot) * lw;
+            }
           }
         }
         if constexpr (MASK) {
-          const float v = mine ? (ok[0] + ok[1]) + (ok[2] + ok[3]) : 0.f;
-          const float tot = warp_sum_f32(v);
-          if (lane == 0) slot[B.n_sel - 1] += static_cast<double>(tot) * lw;
+          if constexpr (WX) {
+            double v = 0.0;
+            if (mine) {
+              v = static_cast<double>(ok[3]) * wel[3];
+              v = fma(static_cast<double>(ok[2]), wel[2], v);
+              v = fma(static_cast<double>(ok[1]), wel[1], v);
+              v = fma(static_cast<double>(ok[0]), wel[0], v);
+            }
+            const double tot = warp_sum(v);
+            if (lane == 0) slot[B.n_sel - 1] += tot;
+          } else {
+            const float v = mine ? (ok[0] + ok[1]) + (ok[2] + ok[3]) : 0.f;
+            const float tot = warp_sum_f32(v);
+            if (lane == 0) slot[B.n_sel - 1] += static_cast<double>(tot) * lw;
+          }
         }
         um &= ~__ballot_sync(0xffffffffu, mine);
       }
@@ -783,13 +828,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             double* slot = wacc + cls[i] * B.n_sel;
+            const double wi = WX ? wel[i] : wrow;
 #pragma unroll
             for (int k = 0; k < NS; ++k)
               if (P.stat_mask & (1 << k))
                 slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
-                    static_cast<double>(val[i][k]) * wrow;
+                    static_cast<double>(val[i][k]) * wi;
             if constexpr (MASK)
-              slot[B.n_sel - 1] += static_cast<double>(ok[i]) * wrow;
+              slot[B.n_sel - 1] += static_cast<double>(ok[i]) * wi;
           }
         }
         __syncwarp();

@@ -617,7 +617,7 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
       coords[name] = cv
   classes = None
   if bin_masks:
-    if skipna or per_dim.get(x_dim) is not None or nx % 4 or (ny * nx) % 16:
+    if skipna or (ny * nx) % 16:
       raise FastPathUnavailable('binned slab kernel: unsupported combination')
     classes = fold_bin_masks(bin_masks, bin_dim_names, inner, sizes)
     n_sel = bin(stat_mask).count('1') + (1 if op_m is not None else 0)
