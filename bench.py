@@ -390,6 +390,18 @@ def run_suite(ctx, dev, peak):
                    'peak': peak, 'unit': 'GB/s',
                    'frac': pts * 8 / (kms * 1e-3) / 1e9 / peak,
                    'algorithmic_bytes_per_point': 8}}
+  step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
+      metrics, bin_agg, lm_preds, lm_tgts)
+  ms, kms, kn = timed(step, 10)
+  out['rmse_bins16_lon_major'] = {
+      'workload': 'rmse_bins16 on the longitude-major arrays of '
+                  'rmse_lon_major (binned kernel with per-element weights)',
+      'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+      'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+      'roofline': {'bound': 'hbm', 'achieved': pts * 9 / (kms * 1e-3) / 1e9,
+                   'peak': peak, 'unit': 'GB/s',
+                   'frac': pts * 9 / (kms * 1e-3) / 1e9 / peak,
+                   'algorithmic_bytes_per_point': 9}}
   del lm_preds, lm_tgts, metrics, step
   torch.cuda.empty_cache()
 
