@@ -806,3 +806,46 @@ def test_fused_bins_lon_major(space, masked, nlat, monkeypatch):
     np.testing.assert_allclose(got_ws, sws, rtol=RTOL,
                                atol=1e-6 * np.abs(sws).max())
     np.testing.assert_allclose(got_w, sw, rtol=1e-10)
+
+
+def test_latitude_and_longitude_band_bins(monkeypatch):
+  """LatitudeBins x LongitudeBins (binning.py:204-298): 1-d band masks are
+  broadcast over the slab and served by the fused class-map kernel."""
+  P, T, C, _ = _bin_case(21)
+  del C
+  P, T = engine.to_device(P), engine.to_device(T)
+  bin_by = [binning.LatitudeBins(degrees=30),
+            binning.LongitudeBins(degrees=90, lon_range=(270, 90))]
+  from weatherbenchx_b200 import generic
+  monkeypatch.setattr(generic, 'aggregate', lambda *a, **k: (_ for _ in ()).throw(
+      AssertionError('generic path used')))
+  rd = ['init_time', 'latitude', 'longitude']
+  metrics = {'rmse': deterministic.RMSE()}
+  state = _aggregate(metrics, {'z': P}, {'z': T}, reduce_dims=rd,
+                     weigh_by=[weighting.GridAreaWeighting()], bin_by=bin_by)
+  Ph, Th = P.to_host(), T.to_host()
+  lat, lon = Ph.coords['latitude'].values, Ph.coords['longitude'].values
+  m_lat = np.stack([(lat >= s) & (lat <= s + 30) for s in range(-90, 90, 30)])
+  lon_bands = [(270, 360), (360, 450)]
+  m_lon = np.stack([
+      ((np.mod(lon, 360) >= np.mod(a, 360)) | (np.mod(lon, 360) <= np.mod(b, 360)))
+      if np.mod(b, 360) <= np.mod(a, 360) else
+      ((np.mod(lon, 360) >= np.mod(a, 360)) & (np.mod(lon, 360) <= np.mod(b, 360)))
+      for a, b in lon_bands])
+  w = oracle.grid_area_weights(lat)
+  sws, sw, odims = oracle.aggregate(
+      oracle.squared_error(Ph.values, Th.values), Ph.dims, rd,
+      weights=[(w, ('latitude',))],
+      bin_masks=[(m_lat, ('latitude_bins', 'latitude')),
+                 (m_lon, ('longitude_bins', 'longitude'))])
+  got = state.sum_weighted_statistics['SquaredError']['z']
+  assert set(got.dims) == set(odims) == {'lead_time', 'latitude_bins',
+                                         'longitude_bins'}
+  np.testing.assert_allclose(got.transpose(*odims).values, sws, rtol=RTOL,
+                             atol=1e-6 * np.abs(sws).max())
+  np.testing.assert_allclose(
+      state.sum_weights['SquaredError']['z'].transpose(*odims).values, sw,
+      rtol=1e-10)
+  np.testing.assert_array_equal(got.coords['latitude_bins'].values,
+                                np.arange(-90, 90, 30))
+  np.testing.assert_array_equal(got.coords['longitude_bins'].values, [270, 0])

@@ -2,7 +2,8 @@
 
 Mirrors the part of /root/reference/weatherbenchX/binning.py used by the
 evaluation scripts on the gridded path: Binning :22-49, the lat/lon rectangle
-helpers :52-89, Regions :147-201 and LandSea :92-144.  Masks are small boolean
+helpers :52-89, Regions :147-201, LandSea :92-144, LatitudeBins :204-243 and
+LongitudeBins :246-298.  Masks are small boolean
 host arrays ([bins, latitude, longitude]); the kernels read them as uint8.
 """
 
@@ -95,6 +96,76 @@ class Regions(Binning):
         masks, (self.bin_dim_name, 'latitude', 'longitude'),
         coords={self.bin_dim_name: np.array(names), 'latitude': lat,
                 'longitude': lon})
+
+
+class _BandBins(Binning):
+  """Bins that depend on one grid coordinate; the mask is [bins, coordinate]
+  (it broadcasts against the statistic like the reference's full-shape one)."""
+
+  _coord = ''
+
+  def _band_mask(self, values: np.ndarray, start: float) -> np.ndarray:
+    raise NotImplementedError
+
+  def create_bin_mask(self, statistic: xl.DataArray) -> xl.DataArray:
+    values = statistic.coords[self._coord].to_numpy()
+    cached = getattr(self, '_cache', None)
+    if cached is not None and cached[0] is values:
+      return cached[1]
+    starts = self._starts
+    masks = np.stack([self._band_mask(values, s) for s in starts])
+    out = xl.DataArray(
+        masks, (self.bin_dim_name, self._coord),
+        coords={self.bin_dim_name: self._labels(starts), self._coord: values})
+    self._cache = (values, out)
+    return out
+
+  def _labels(self, starts: np.ndarray) -> np.ndarray:
+    return np.asarray(starts)
+
+  def __getstate__(self):
+    state = dict(self.__dict__)
+    state.pop('_cache', None)
+    return state
+
+
+class LatitudeBins(_BandBins):
+  """Latitude bands of ``degrees`` width (binning.py:204-243); both band
+  edges are inclusive, as in the reference."""
+
+  _coord = 'latitude'
+
+  def __init__(self, degrees: float, lat_range: Tuple[int, int] = (-90, 90),
+               bin_dim_name: str = 'latitude_bins'):
+    super().__init__(bin_dim_name)
+    self._degrees = degrees
+    self._starts = np.arange(lat_range[0], lat_range[1] + degrees,
+                             degrees)[:-1]
+
+  def _band_mask(self, values, start):
+    return _lat_mask(values, (start, start + self._degrees))
+
+
+class LongitudeBins(_BandBins):
+  """Longitude bands of ``degrees`` width (binning.py:246-298), wrapping at
+  360 degrees; labelled by the band start modulo 360."""
+
+  _coord = 'longitude'
+
+  def __init__(self, degrees: float, lon_range: Tuple[int, int] = (0, 360),
+               bin_dim_name: str = 'longitude_bins'):
+    super().__init__(bin_dim_name)
+    self._degrees = degrees
+    lon_end = lon_range[1]
+    if lon_range[0] >= lon_range[1]:
+      lon_end += 360
+    self._starts = np.arange(lon_range[0], lon_end + degrees, degrees)[:-1]
+
+  def _band_mask(self, values, start):
+    return _lon_mask(values, (start, start + self._degrees))
+
+  def _labels(self, starts):
+    return np.mod(starts, 360)
 
 
 class LandSea(Binning):
