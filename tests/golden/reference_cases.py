@@ -1,0 +1,331 @@
+"""Evaluation cases shared by the golden generator and its consumers.
+
+TEST INFRASTRUCTURE.  ``build_cases(ns, inputs)`` is written once against a
+namespace of modules with the reference's names (``aggregation``, ``binning``,
+``weighting``, ``deterministic``, ``probabilistic``, ``wrappers``, ``xr``):
+
+* ``make_reference_golden.py`` passes the reference's own modules
+  (/root/reference/weatherbenchX, build container only) and stores what they
+  return;
+* ``tests/test_reference_golden.py`` passes ``weatherbenchx_b200``'s modules
+  (CUDA path, ``-m gpu``) and compares with the stored results -- the same
+  user code runs on both sides, which is the drop-in claim;
+* the CPU oracle test uses the ``spec`` of each case (plain data).
+
+Inputs are seeded NumPy arrays produced by ``make_inputs`` and stored in the
+fixture, so consumers never regenerate them.
+"""
+
+from __future__ import annotations
+
+import types
+
+import numpy as np
+
+NLAT, NLON = 19, 32  # 608 points: a multiple of 16, so the fused class-map kernel applies
+LAT = np.linspace(-90, 90, NLAT)
+LON = np.linspace(0, 360, NLON, endpoint=False)
+# Valid times cross 29 February of a leap year (dayofyear 58..62).
+INIT = np.datetime64('2020-02-27T00', 'ns') + np.arange(4) * np.timedelta64(
+    12, 'h')
+LEAD = (np.arange(3) * np.timedelta64(6, 'h')).astype('timedelta64[ns]')
+LEVEL = np.array([500, 850])
+MEMBERS = np.arange(7)
+ENS = 'realization'
+D2 = ('init_time', 'lead_time', 'latitude', 'longitude')
+D3 = ('init_time', 'lead_time', 'level', 'latitude', 'longitude')
+D_ENS_T = ('init_time', 'latitude', 'longitude')
+D_ENS_LAST = D_ENS_T + (ENS,)
+D_ENS_MAJOR = ('init_time', ENS, 'latitude', 'longitude')
+RD = ['init_time', 'latitude', 'longitude']
+COORDS = {'init_time': INIT, 'lead_time': LEAD, 'level': LEVEL,
+          'latitude': LAT, 'longitude': LON, ENS: MEMBERS}
+REGIONS = {
+    'global': ((-90, 90), (0, 360)),
+    'tropics': ((-20, 20), (0, 360)),
+    'nh': ((20, 90), (0, 360)),
+    'europe': ((35, 75), (-12.5, 42.5)),   # wraps across 0 degrees
+    'box': ((-45, 10), (100, 250)),
+}
+ENS_REGIONS = {'global': ((-90, 90), (0, 360)), 'sh': ((-90, -20), (0, 360)),
+               'box': ((-10, 60), (300, 60))}
+DOY_USED = np.arange(58, 63)
+HOURS = np.arange(0, 24, 6)
+
+
+def _shape(dims):
+  return tuple(len(COORDS[d]) for d in dims)
+
+
+def make_inputs() -> dict:
+  """Seeded float32 fields (and boolean hole / land patterns)."""
+  rng = np.random.default_rng(20240229)
+  f32 = np.float32
+  out = {}
+  out['t2'] = rng.normal(280, 10, _shape(D2)).astype(f32)
+  out['p2'] = (out['t2'] + rng.normal(0.5, 2, _shape(D2))).astype(f32)
+  out['t3'] = rng.normal(5000, 300, _shape(D3)).astype(f32)
+  out['p3'] = (out['t3'] + rng.normal(-3, 40, _shape(D3))).astype(f32)
+  out['holes2'] = rng.random(_shape(D2)) < 0.07
+  out['holes3'] = rng.random(_shape(D3)) < 0.05
+  out['land'] = rng.random((NLAT, NLON)) < 0.4
+  out['c2_rows'] = rng.normal(
+      280, 5, (len(DOY_USED), 4, NLAT, NLON)).astype(f32)
+  out['c3_rows'] = rng.normal(
+      5000, 100, (len(DOY_USED), 4, len(LEVEL), NLAT, NLON)).astype(f32)
+  out['u_t'] = rng.normal(3, 8, _shape(D3)).astype(f32)
+  out['v_t'] = rng.normal(-1, 6, _shape(D3)).astype(f32)
+  out['u_p'] = (out['u_t'] + rng.normal(0, 2, _shape(D3))).astype(f32)
+  out['v_p'] = (out['v_t'] + rng.normal(0, 2, _shape(D3))).astype(f32)
+  out['y'] = rng.normal(280, 10, _shape(D_ENS_T)).astype(f32)
+  out['x_last'] = (out['y'][..., None] + rng.normal(
+      0.3, 3, _shape(D_ENS_LAST))).astype(f32)
+  holes = rng.random(_shape(D_ENS_LAST)) < 0.15
+  holes[..., :2] = False  # at least two members at every point
+  out['member_holes'] = holes
+  out['ens_land'] = rng.random((NLAT, NLON)) < 0.4
+  out['y_holes'] = rng.random(_shape(D_ENS_T)) < 0.06
+  return out
+
+
+def full_climatology(rows: np.ndarray) -> np.ndarray:
+  """[366, 4, ...] climatology that is NaN outside the stored day-of-year rows
+  (a wrong gather index then shows up as NaN instead of passing silently)."""
+  full = np.full((366,) + rows.shape[1:], np.nan, np.float32)
+  full[DOY_USED - 1] = rows
+  return full
+
+
+def with_nan(values: np.ndarray, holes: np.ndarray) -> np.ndarray:
+  out = values.copy()
+  out[holes] = np.nan
+  return out
+
+
+def build_cases(ns, inputs):
+  """Yields (name, spec, metrics, aggregator, predictions, targets).
+
+  ``spec`` is plain data for consumers that do not go through the class
+  surface: {'family', 'reduce_dims', 'weighted', 'masked', 'skipna', 'bins',
+  'nan_targets', ...}.
+  """
+  xr = ns.xr
+  agg, binning, weighting = ns.aggregation, ns.binning, ns.weighting
+  det, prob, wrappers = ns.deterministic, ns.probabilistic, ns.wrappers
+
+  def da(values, dims, **extra_coords):
+    coords = {d: COORDS[d] for d in dims}
+    coords.update(extra_coords)
+    return xr.DataArray(values, dims, coords=coords)
+
+  def area():
+    return [weighting.GridAreaWeighting()]
+
+  # -- deterministic ---------------------------------------------------------
+  predictions = {'2m_temperature': da(inputs['p2'], D2),
+                 'geopotential': da(inputs['p3'], D3)}
+  targets = {'2m_temperature': da(inputs['t2'], D2),
+             'geopotential': da(inputs['t3'], D3)}
+  targets_nan = {
+      '2m_temperature': da(with_nan(inputs['t2'], inputs['holes2']), D2,
+                           mask=(D2, ~inputs['holes2'])),
+      'geopotential': da(with_nan(inputs['t3'], inputs['holes3']), D3,
+                         mask=(D3, ~inputs['holes3'])),
+  }
+  metrics = {'rmse': det.RMSE(), 'mse': det.MSE(), 'mae': det.MAE(),
+             'bias': det.Bias()}
+
+  def det_case(name, reduce_dims=None, weighted=True, nan_targets=False,
+               bins=None, use_metrics=None, **flags):
+    reduce_dims = reduce_dims or RD
+    spec = dict(family='det', reduce_dims=reduce_dims, weighted=weighted,
+                masked=flags.get('masked', False),
+                skipna=flags.get('skipna', False), bins=bins or [],
+                nan_targets=nan_targets)
+    aggregator = agg.Aggregator(
+        reduce_dims=reduce_dims, weigh_by=area() if weighted else None,
+        bin_by=_make_bins(ns, bins, inputs['land']) if bins else None,
+        **flags)
+    return (name, spec, use_metrics or metrics, aggregator, predictions,
+            targets_nan if nan_targets else targets)
+
+  yield det_case('det/weighted')
+  yield det_case('det/unweighted', weighted=False)
+  yield det_case('det/keep_init', reduce_dims=['latitude', 'longitude'])
+  yield det_case('det/reduce_all_but_level', reduce_dims=[
+      'init_time', 'lead_time', 'latitude', 'longitude'])
+  yield det_case('det/nan_default', nan_targets=True)
+  yield det_case('det/nan_masked', nan_targets=True, masked=True)
+  yield det_case('det/nan_skipna', nan_targets=True, skipna=True)
+  yield det_case('det/nan_masked_skipna', nan_targets=True, masked=True,
+                 skipna=True)
+  yield det_case('det/regions', bins=['regions_land'])
+  yield det_case('det/regions_x_landsea', bins=['regions', 'landsea_global'])
+  yield det_case('det/regions_nan_masked', bins=['regions_land'],
+                 nan_targets=True, masked=True)
+  yield det_case('det/regions_nan_default', bins=['regions_land'],
+                 nan_targets=True)
+  yield det_case('det/lat_lon_bands', bins=['lat30', 'lon90'],
+                 use_metrics={'mse': det.MSE()})
+
+  # -- ACC with a (dayofyear, hour) climatology ------------------------------
+  clim_coords = {'dayofyear': np.arange(1, 367), 'hour': HOURS}
+  c2 = xr.DataArray(
+      full_climatology(inputs['c2_rows']),
+      ('dayofyear', 'hour', 'latitude', 'longitude'),
+      coords=dict(clim_coords, latitude=LAT, longitude=LON))
+  c3 = xr.DataArray(
+      full_climatology(inputs['c3_rows']),
+      ('dayofyear', 'hour', 'level', 'latitude', 'longitude'),
+      coords=dict(clim_coords, level=LEVEL, latitude=LAT, longitude=LON))
+  climatology = xr.Dataset({'2m_temperature': c2, 'geopotential': c3})
+  acc_metrics = {'acc': det.ACC(climatology), 'rmse': det.RMSE()}
+  for name, nan_targets, flags in (
+      ('acc/weighted', False, {}),
+      ('acc/nan_skipna', True, {'skipna': True}),
+      ('acc/nan_masked', True, {'masked': True})):
+    case = det_case(name, nan_targets=nan_targets, use_metrics=acc_metrics,
+                    **flags)
+    case[1]['family'] = 'acc'
+    yield case
+
+  # -- wind vector -----------------------------------------------------------
+  wind_metrics = {'wind_rmse': det.WindVectorRMSE(
+      u_name='u_component_of_wind', v_name='v_component_of_wind',
+      vector_name='wind_vector')}
+  yield ('wind/weighted',
+         dict(family='wind', reduce_dims=RD, weighted=True, masked=False,
+              skipna=False, bins=[], nan_targets=False),
+         wind_metrics, agg.Aggregator(reduce_dims=RD, weigh_by=area()),
+         {'u_component_of_wind': da(inputs['u_p'], D3),
+          'v_component_of_wind': da(inputs['v_p'], D3)},
+         {'u_component_of_wind': da(inputs['u_t'], D3),
+          'v_component_of_wind': da(inputs['v_t'], D3)})
+
+  # -- ensembles -------------------------------------------------------------
+  y = da(inputs['y'], D_ENS_T)
+  x_last = da(inputs['x_last'], D_ENS_LAST)
+  x_major_values = np.ascontiguousarray(
+      np.moveaxis(inputs['x_last'], -1, 1))
+  x_major = da(x_major_values, D_ENS_MAJOR)
+  x_nan = da(np.ascontiguousarray(np.moveaxis(
+      with_nan(inputs['x_last'], inputs['member_holes']), -1, 1)),
+             D_ENS_MAJOR)
+  ens_metrics = {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True),
+      'crps_unfair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=False),
+      'ens_var': prob.EnsembleRootMeanVariance(ensemble_dim=ENS),
+      'unbiased_rmse': prob.UnbiasedEnsembleMeanRMSE(ensemble_dim=ENS),
+      'unbiased_ssr': prob.UnbiasedSpreadSkillRatio(ensemble_dim=ENS),
+  }
+
+  y_nan = da(with_nan(inputs['y'], inputs['y_holes']), D_ENS_T,
+             mask=(D_ENS_T, ~inputs['y_holes']))
+
+  def ens_case(name, x, use_metrics, reduce_dims=None, weighted=True,
+               bins=None, layout='member_major', member_nan=False,
+               family='ens', nan_targets=False, **flags):
+    reduce_dims = reduce_dims or RD
+    spec = dict(family=family, reduce_dims=reduce_dims, weighted=weighted,
+                masked=flags.get('masked', False),
+                skipna=flags.get('skipna', False), bins=bins or [],
+                layout=layout, member_nan=member_nan, nan_targets=nan_targets)
+    aggregator = agg.Aggregator(
+        reduce_dims=reduce_dims, weigh_by=area() if weighted else None,
+        bin_by=_make_bins(ns, bins, inputs['ens_land']) if bins else None,
+        **flags)
+    return (name, spec, use_metrics, aggregator, {'t2m': x},
+            {'t2m': y_nan if nan_targets else y})
+
+  yield ens_case('ens/member_last', x_last, ens_metrics, layout='member_last')
+  yield ens_case('ens/member_major', x_major, ens_metrics)
+  yield ens_case('ens/use_sort', x_major, {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True,
+                                     use_sort=True),
+      'crps_unfair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=False,
+                                       use_sort=True)})
+  yield ens_case('ens/unweighted_keep_init', x_major, ens_metrics,
+                 reduce_dims=['latitude', 'longitude'], weighted=False)
+  yield ens_case('ens/skipna_ensemble', x_nan, {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True,
+                                     skipna_ensemble=True),
+      'ens_var': prob.EnsembleRootMeanVariance(ensemble_dim=ENS,
+                                               skipna_ensemble=True),
+      'unbiased_rmse': prob.UnbiasedEnsembleMeanRMSE(
+          ensemble_dim=ENS, skipna_ensemble=True)}, member_nan=True)
+  yield ens_case('ens/nan_members_propagate', x_nan, {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True)},
+                 reduce_dims=['latitude', 'longitude'], member_nan=True)
+  yield ens_case('ens/regions', x_major, {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True),
+      'unbiased_ssr': prob.UnbiasedSpreadSkillRatio(ensemble_dim=ENS)},
+                 bins=['ens_regions_land'])
+  # NaN targets with a mask coordinate: only the statistics whose expression
+  # touches the targets carry the mask (CRPSSkill, UnbiasedEnsembleMeanSquared
+  # Error); CRPSSpread and EnsembleVariance are functions of the predictions.
+  yield ens_case('ens/nan_targets_default', x_major, ens_metrics,
+                 nan_targets=True)
+  yield ens_case('ens/nan_targets_masked', x_major, ens_metrics,
+                 nan_targets=True, masked=True)
+  yield ens_case('ens/nan_targets_skipna', x_major, ens_metrics,
+                 nan_targets=True, skipna=True)
+  yield ens_case('ens/regions_nan_targets_masked', x_major, {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True),
+      'unbiased_ssr': prob.UnbiasedSpreadSkillRatio(ensemble_dim=ENS)},
+                 bins=['ens_regions_land'], nan_targets=True, masked=True)
+  yield ens_case('ens/ensemble_averaged_rmse', x_major, {
+      'rmse_members': prob.EnsembleAveragedMetric(det.RMSE(),
+                                                  ensemble_dim=ENS)},
+                 family='ens_averaged')
+  yield ens_case('ens/ensemble_mean_rmse', x_major, {
+      'rmse_mean': wrappers.WrappedMetric(
+          det.RMSE(), [wrappers.EnsembleMean('predictions',
+                                             ensemble_dim=ENS)])},
+                 family='ens_mean')
+
+
+def _make_bins(ns, names, land_values):
+  xr, binning = ns.xr, ns.binning
+  land = xr.DataArray(land_values, ('latitude', 'longitude'),
+                      coords={'latitude': LAT, 'longitude': LON})
+  out = []
+  for name in names:
+    if name == 'regions':
+      out.append(binning.Regions(REGIONS))
+    elif name == 'regions_land':
+      out.append(binning.Regions(REGIONS, land_sea_mask=land))
+    elif name == 'ens_regions_land':
+      out.append(binning.Regions(ENS_REGIONS, land_sea_mask=land))
+    elif name == 'landsea_global':
+      out.append(binning.LandSea(land.astype(np.float32),
+                                 include_global_mask=True))
+    elif name == 'lat30':
+      out.append(binning.LatitudeBins(30))
+    elif name == 'lon90':
+      out.append(binning.LongitudeBins(90))
+    else:
+      raise KeyError(name)
+  return out
+
+
+def chunked_case(ns, inputs):
+  """The det/weighted case evaluated one init_time at a time and combined
+  with AggregationState.__add__ (aggregation.py:84-110; the identity
+  beam_pipeline_test.py:82-170 checks).  Returns (metrics, state)."""
+  base = ns.base
+  for name, _, metrics, aggregator, predictions, targets in build_cases(
+      ns, inputs):
+    if name == 'det/weighted':
+      break
+  total = ns.aggregation.AggregationState.zero()
+  for i in range(len(INIT)):
+    chunk_p = {k: v.isel(init_time=[i]) for k, v in predictions.items()}
+    chunk_t = {k: v.isel(init_time=[i]) for k, v in targets.items()}
+    statistics = base.compute_unique_statistics_for_all_metrics(
+        metrics, chunk_p, chunk_t)
+    total = total + aggregator.aggregate_statistics(statistics)
+  return metrics, total
+
+
+def namespace(**modules):
+  return types.SimpleNamespace(**modules)

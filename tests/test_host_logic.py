@@ -301,7 +301,9 @@ def _case(order, seed=0, shape=(3, 2, 2, 6, 8)):
         d for d in order if d in ('level', 'latitude', 'longitude'))
     c = c.transpose(*corder)
     c = c.copy(data=np.ascontiguousarray(c.values))
-  return p, t.assign_coords(mask=mask), c
+  # the same mask on both inputs: all six statistics carry it (a mask on the
+  # targets alone would leave SquaredPredictionAnomaly unmasked)
+  return p.assign_coords(mask=mask), t.assign_coords(mask=mask), c
 
 
 @pytest.mark.parametrize('order', [
@@ -542,3 +544,131 @@ def test_combining_sum_blocks_with_unsorted_labels_and_kept_time():
   np.testing.assert_array_equal(
       mixed.sel(region='nh').values, full[0:2, 2] + 1)
   np.testing.assert_array_equal(mixed.sel(region='europe').values, [1, 1])
+
+
+# ---------------------------------------------------------------------------
+# 'mask' coordinate per statistic (what the reference's expressions carry)
+# ---------------------------------------------------------------------------
+
+
+def _masked_inputs():
+  rng = np.random.default_rng(3)
+  dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+  coords = {'init_time': np.datetime64('2020-01-01', 'ns') +
+                         np.arange(2) * np.timedelta64(1, 'D'),
+            'lead_time': (np.arange(2) * np.timedelta64(6, 'h')
+                          ).astype('timedelta64[ns]'),
+            'latitude': np.linspace(-90, 90, 5),
+            'longitude': np.linspace(0, 360, 8, endpoint=False)}
+  shape = (2, 2, 5, 8)
+  p = xl.DataArray(rng.normal(size=shape).astype(np.float32), dims,
+                   coords=coords)
+  holes = rng.random(shape) < 0.2
+  t_values = rng.normal(size=shape).astype(np.float32)
+  t_values[holes] = np.nan
+  t = xl.DataArray(t_values, dims, coords=dict(coords, mask=(dims, ~holes)))
+  clim = xl.DataArray(
+      rng.normal(size=(366, 4, 5, 8)).astype(np.float32),
+      ('dayofyear', 'hour', 'latitude', 'longitude'),
+      coords={'dayofyear': np.arange(1, 367), 'hour': np.arange(0, 24, 6),
+              'latitude': coords['latitude'],
+              'longitude': coords['longitude']})
+  return p, t, clim
+
+
+def test_mask_coordinate_follows_the_operands_of_each_statistic():
+  """deterministic.py:225-259: (p - c)**2 has no targets' mask; the other
+  statistics inherit it (aggregation.py:339 tests hasattr(stat, 'mask'))."""
+  from weatherbenchx_b200.metrics import deterministic, probabilistic
+  p, t, clim = _masked_inputs()
+  stats = metrics_base.compute_unique_statistics_for_all_metrics(
+      {'acc': deterministic.ACC({'x': clim}), 'rmse': deterministic.RMSE()},
+      {'x': p}, {'x': t})
+  has_mask = {name: 'mask' in per_var['x'].coords
+              for name, per_var in stats.items()}
+  assert has_mask == {'SquaredPredictionAnomaly': False,
+                      'SquaredTargetAnomaly': True, 'AnomalyCovariance': True,
+                      'SquaredError': True}
+  # a mask on the predictions instead: the mirror image
+  p2 = p.assign_coords(mask=t.coords['mask'])
+  t2 = t.drop_vars('mask')
+  stats = metrics_base.compute_unique_statistics_for_all_metrics(
+      {'acc': deterministic.ACC({'x': clim})}, {'x': p2}, {'x': t2})
+  assert {n: 'mask' in v['x'].coords for n, v in stats.items()} == {
+      'SquaredPredictionAnomaly': True, 'SquaredTargetAnomaly': False,
+      'AnomalyCovariance': True}
+  # conflicting masks are dropped by the coordinate merge
+  flipped = xl.DataArray(~t.coords['mask'].values, t.dims)
+  stats = metrics_base.compute_unique_statistics_for_all_metrics(
+      {'rmse': deterministic.RMSE()}, {'x': p.assign_coords(mask=flipped)},
+      {'x': t})
+  assert 'mask' not in stats['SquaredError']['x'].coords
+  # ensembles: spread and variance are functions of the predictions alone
+  ens = xl.DataArray(
+      np.zeros((2, 2, 5, 8, 3), np.float32), p.dims + ('realization',),
+      coords={d: p.coords[d].values for d in p.dims})
+  stats = metrics_base.compute_unique_statistics_for_all_metrics(
+      {'crps': probabilistic.CRPSEnsemble(ensemble_dim='realization'),
+       'ssr': probabilistic.UnbiasedSpreadSkillRatio(
+           ensemble_dim='realization')}, {'x': ens}, {'x': t})
+  has_mask = {name.split('_')[0]: 'mask' in per_var['x'].coords
+              for name, per_var in stats.items()}
+  assert has_mask == {'CRPSSkill': True, 'CRPSSpread': False,
+                      'EnsembleVariance': False,
+                      'UnbiasedEnsembleMeanSquaredError': True}
+
+
+def test_masked_aggregation_launches_unmasked_statistics_separately(
+    monkeypatch):
+  """Aggregator(masked=True): one launch per distinct mask, and statistics
+  without a mask coordinate are not masked (engine stubbed: no GPU here)."""
+  from weatherbenchx_b200.metrics import deterministic
+  p, t, clim = _masked_inputs()
+  metrics = {'acc': deterministic.ACC({'x': clim}),
+             'rmse': deterministic.RMSE()}
+  stats = metrics_base.compute_unique_statistics_for_all_metrics(
+      metrics, {'x': p}, {'x': t})
+  launches = []
+
+  def build(stat_list, reduce_dims, weights, masked=False, skipna=False,
+            **kwargs):
+    launches.append((sorted(s.kind for s in stat_list), masked))
+    return ('spec', [s.kind for s in stat_list])
+
+  def run(pairs):
+    return [{kind: (xl.DataArray(1.0), xl.DataArray(1.0))
+             for kind in spec[1]} for spec, _ in pairs]
+
+  monkeypatch.setattr(engine, 'build_fused_spec', build)
+  monkeypatch.setattr(engine, 'run_fused_specs', run)
+  rd = ['init_time', 'latitude', 'longitude']
+  aggregation.Aggregator(reduce_dims=rd, masked=True).aggregate_statistics(
+      stats)
+  assert sorted(launches) == [
+      (['AnomalyCovariance', 'SquaredError', 'SquaredTargetAnomaly'], True),
+      (['SquaredPredictionAnomaly'], False)]
+  launches.clear()
+  aggregation.Aggregator(reduce_dims=rd).aggregate_statistics(stats)
+  assert launches == [(['AnomalyCovariance', 'SquaredError',
+                        'SquaredPredictionAnomaly', 'SquaredTargetAnomaly'],
+                       False)]
+
+
+def test_coordinate_views_and_assignment():
+  """binning.py:135,181,190-199 rely on ``stat.latitude.latitude`` and on
+  ``masks.coords[name] = labels``."""
+  da = xl.DataArray(np.zeros((2, 3)), ('region', 'latitude'),
+                    coords={'latitude': [10., 20., 30.]})
+  lat = da.latitude
+  assert lat.dims == ('latitude',)
+  np.testing.assert_array_equal(lat.latitude.values, [10., 20., 30.])
+  np.testing.assert_array_equal(da.coords['latitude'].coords['latitude'].values,
+                                [10., 20., 30.])
+  da.coords['region'] = np.array(['a', 'b'])
+  assert list(da.coords) == ['latitude', 'region']
+  assert da.coords['region'].dims == ('region',)
+  assert list(da.sel(region='b').coords['region'].values.ravel()) == ['b']
+  with pytest.raises(ValueError):
+    da.coords['region'] = np.array(['a', 'b', 'c'])
+  assert 'region' in da.coords and len(da.coords) == 2
+  assert dict(da.coords).keys() == {'latitude', 'region'}

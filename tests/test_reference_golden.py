@@ -1,0 +1,488 @@
+"""Parity against vectors produced by the reference's own code.
+
+``tests/golden/reference_golden.npz`` holds, for 30 evaluation cases, the
+AggregationState (sum_weighted_statistics / sum_weights per statistic and
+variable) and the metric values that the UNMODIFIED modules of
+/root/reference/weatherbenchX returned in the build container
+(``tests/golden/make_reference_golden.py``; xarray / jax are not installable
+there, the reference ran on the stand-in modules of
+``tests/golden/reference_runtime.py`` -- read its docstring for the exact
+split between reference code and stand-in).
+
+* not gpu: the NumPy oracle reproduces every stored array -- this is what pins
+  ``oracle/wbx_oracle.py`` to the reference;
+* gpu: the very same case definitions (``tests/golden/reference_cases.py``)
+  are run with this package's modules in place of the reference's, i.e. the
+  user code is identical and only the import changes; state and values must
+  agree with the stored ones.
+
+Tolerance: 1e-5 relative (north_star; the reference's assert_allclose default)
+plus an absolute term for sums that cancel (Error / AnomalyCovariance sums of
+mixed sign); weight sums that are counts are compared exactly.
+"""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import wbx_oracle as oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+import reference_cases as cases  # noqa: E402  pylint: disable=g-import-not-at-top
+
+GOLDEN = os.path.join(HERE, 'golden', 'reference_golden.npz')
+RTOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def golden():
+  with np.load(GOLDEN) as data:
+    return {k: data[k] for k in data.files}
+
+
+@pytest.fixture(scope='module')
+def inputs(golden):
+  return {k[3:]: v for k, v in golden.items() if k.startswith('in/')}
+
+
+def _case_keys(golden, case, part):
+  prefix = f'{case}/{part}/'
+  return [k for k in golden if k.startswith(prefix) and '@' not in k]
+
+
+def _abs_tolerance(expected):
+  """Sums of mixed sign cancel: allow RTOL of the typical magnitude."""
+  finite = np.abs(expected[np.isfinite(expected)])
+  return RTOL * float(finite.max()) if finite.size else 0.0
+
+
+def _assert_close(actual, expected, what, exact=False):
+  actual = np.asarray(actual)
+  expected = np.asarray(expected)
+  assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
+  np.testing.assert_array_equal(np.isnan(actual), np.isnan(expected),
+                                err_msg=f'{what}: NaN pattern')
+  if exact:
+    np.testing.assert_array_equal(actual, expected, err_msg=what)
+  else:
+    np.testing.assert_allclose(actual, expected, rtol=RTOL,
+                               atol=_abs_tolerance(expected), err_msg=what)
+
+
+def _transpose_to(values, dims, want_dims):
+  dims, want_dims = list(dims), list(want_dims)
+  assert sorted(dims) == sorted(want_dims), (dims, want_dims)
+  return np.transpose(values, [dims.index(d) for d in want_dims])
+
+
+# ---------------------------------------------------------------------------
+# the oracle, case by case
+# ---------------------------------------------------------------------------
+
+
+def _oracle_bins(spec, inputs):
+  """Stacked boolean masks [(mask, dims), ...] and their labels."""
+  out = []
+  for name in spec['bins']:
+    land = inputs['ens_land' if name.startswith('ens_') else 'land']
+    if name in ('regions', 'regions_land', 'ens_regions_land'):
+      regions = cases.ENS_REGIONS if name.startswith('ens_') else cases.REGIONS
+      masks, labels = oracle.regions_masks(
+          cases.LAT, cases.LON, regions,
+          land_sea_mask=None if name == 'regions' else land)
+      out.append(((masks, ('region', 'latitude', 'longitude')), labels))
+    elif name == 'landsea_global':
+      # binning.py:92-144: land = fraction >= 0.5, sea = 1 - land, global.
+      land_mask = land.astype(np.float32) >= 0.5
+      masks = np.stack([land_mask, ~land_mask, np.ones_like(land_mask)])
+      out.append(((masks, ('land_sea', 'latitude', 'longitude')),
+                  ['land', 'sea', 'global']))
+    elif name == 'lat30':
+      # binning.py:204-243: closed bands [start, start + degrees].
+      starts = np.arange(-90, 90 + 30, 30)[:-1]
+      masks = np.stack([(cases.LAT >= s) & (cases.LAT <= s + 30)
+                        for s in starts])
+      out.append(((masks, ('latitude_bins', 'latitude')), list(starts)))
+    elif name == 'lon90':
+      # binning.py:246-298 with the wrap-around rule of :63-76.
+      starts = np.arange(0, 360 + 90, 90)[:-1]
+      masks = []
+      for s in starts:
+        west, east = np.mod(s, 360), np.mod(s + 90, 360)
+        lon = np.mod(cases.LON, 360)
+        masks.append((lon >= west) & (lon <= east) if east > west
+                     else (lon <= east) | (lon >= west))
+      out.append(((np.stack(masks), ('longitude_bins', 'longitude')),
+                  list(starts)))
+    else:
+      raise KeyError(name)
+  return out
+
+
+def _oracle_fields(spec, inputs):
+  """{(statistic unique_name, variable): (values, dims, mask or None)}."""
+  family = spec['family']
+  out = {}
+  if family in ('det', 'acc'):
+    for var, p, t, holes, dims, rows in (
+        ('2m_temperature', inputs['p2'], inputs['t2'], inputs['holes2'],
+         cases.D2, inputs['c2_rows']),
+        ('geopotential', inputs['p3'], inputs['t3'], inputs['holes3'],
+         cases.D3, inputs['c3_rows'])):
+      mask = None
+      if spec['nan_targets']:
+        t = cases.with_nan(t, holes)
+        mask = ~holes
+      out[('Error', var)] = (oracle.error(p, t), dims, mask)
+      out[('AbsoluteError', var)] = (oracle.absolute_error(p, t), dims, mask)
+      out[('SquaredError', var)] = (oracle.squared_error(p, t), dims, mask)
+      if family == 'acc':
+        clim = cases.full_climatology(rows)
+        clim_dims = ('dayofyear', 'hour') + tuple(dims[2:])
+        aligned, adims = oracle.align_climatology(
+            clim, clim_dims,
+            {'dayofyear': np.arange(1, 367), 'hour': cases.HOURS},
+            cases.INIT, cases.LEAD)
+        assert tuple(adims) == tuple(dims)
+        assert not np.isnan(aligned).any()
+        for name, fn in oracle.CLIMATOLOGY_STATISTICS.items():
+          # (p - c)**2 never touches the targets, so it does not inherit
+          # their 'mask' coordinate (deterministic.py:225-232).
+          out[(name, var)] = (
+              fn(p, t, aligned), dims,
+              None if name == 'SquaredPredictionAnomaly' else mask)
+  elif family == 'wind':
+    se = oracle.wind_vector_squared_error(
+        inputs['u_p'], inputs['u_t'], inputs['v_p'], inputs['v_t'])
+    out[('WindVectorSquaredError_wind_vector', 'wind_vector')] = (
+        se, cases.D3, None)
+  else:
+    x = inputs['x_last']
+    if spec.get('member_nan'):
+      x = cases.with_nan(x, inputs['member_holes'])
+    y, mask = inputs['y'], None
+    if spec.get('nan_targets'):
+      y = cases.with_nan(y, inputs['y_holes'])
+      mask = ~inputs['y_holes']
+    if spec.get('layout', 'member_major') == 'member_major':
+      x = np.ascontiguousarray(np.moveaxis(x, -1, 1))
+      axis = 1
+    else:
+      axis = x.ndim - 1
+    dims = cases.D_ENS_T
+    if family == 'ens_averaged':
+      se = oracle.squared_error(x, np.expand_dims(y, axis))
+      out[('SquaredError_each_realization', 't2m')] = (
+          se.mean(axis=axis), dims, None)
+    elif family == 'ens_mean':
+      name = ("SquaredError_predictions_ensemble_mean_self._ensemble_dim="
+              "'realization'_self._skipna=False")
+      out[(name, 't2m')] = (
+          oracle.squared_error(oracle.ensemble_mean(x, axis), y), dims, None)
+    else:
+      for skip in (False, True):
+        if skip and not spec.get('member_nan'):
+          continue
+        # functions of the predictions alone carry no target mask
+        out[(f'EnsembleVariance_realization_skipna_ensemble_{skip}', 't2m')] = (
+            oracle.ensemble_variance(x, axis, skip), dims, None)
+        out[('UnbiasedEnsembleMeanSquaredError_realization_skipna_ensemble_'
+             f'{skip}', 't2m')] = (
+                 oracle.unbiased_ensemble_mean_squared_error(x, y, axis, skip),
+                 dims, mask)
+      out['skill'] = lambda skip: (oracle.crps_skill(x, y, axis, skip), dims,
+                                   mask)
+      out['spread'] = lambda fair, sort, skip: (
+          oracle.crps_spread(x, axis, fair=fair, use_sort=sort,
+                             skipna_ensemble=skip), dims, None)
+  return out
+
+
+def _oracle_state(case, spec, fields, stat, var, inputs):
+  if stat == 'CRPSSkill_realization':
+    values, dims, mask = fields['skill'](case == 'ens/skipna_ensemble')
+  elif stat.startswith('CRPSSpread_realization_'):
+    values, dims, mask = fields['spread'](
+        '_fair_' in stat, case == 'ens/use_sort',
+        case == 'ens/skipna_ensemble')
+  else:
+    values, dims, mask = fields[(stat, var)]
+  weights = []
+  if spec['weighted']:
+    weights.append((oracle.grid_area_weights(cases.LAT), ('latitude',)))
+  bins = _oracle_bins(spec, inputs)
+  result = oracle.aggregate(
+      values, dims, spec['reduce_dims'], weights=weights,
+      bin_masks=[b for b, _ in bins], mask=mask,
+      mask_dims=dims if mask is not None else None, masked=spec['masked'],
+      skipna=spec['skipna'])
+  assert result is not None
+  return result
+
+
+def test_fixture_is_complete(golden):
+  names = [str(n) for n in golden['cases']]
+  assert len(names) == 30 and len(set(names)) == 30
+  for case in names:
+    assert _case_keys(golden, case, 'sws'), case
+    assert _case_keys(golden, case, 'value'), case
+
+
+def test_inputs_are_reproducible(inputs):
+  """The stored inputs are exactly what make_inputs() produces (seeded)."""
+  fresh = cases.make_inputs()
+  assert set(fresh) == set(inputs)
+  for name, values in fresh.items():
+    np.testing.assert_array_equal(values, inputs[name], err_msg=name)
+
+
+def _case_table(inputs_dict):
+  ns = cases.namespace(
+      xr=_PlainNamespace(), aggregation=_PlainNamespace(),
+      binning=_PlainNamespace(), weighting=_PlainNamespace(),
+      base=_PlainNamespace(), deterministic=_PlainNamespace(),
+      probabilistic=_PlainNamespace(), wrappers=_PlainNamespace())
+  return {name: spec for name, spec, *_ in cases.build_cases(ns, inputs_dict)}
+
+
+class _PlainNamespace:
+  """Accepts any attribute access or call: only the ``spec`` of each case is
+  used by the oracle tests."""
+
+  def __getattr__(self, name):
+    return self
+
+  def __call__(self, *args, **kwargs):
+    return self
+
+
+def test_oracle_reproduces_reference_states(golden, inputs):
+  """Every sum_weighted_statistics / sum_weights array of every case."""
+  table = _case_table(inputs)
+  checked = 0
+  for case, spec in table.items():
+    fields = _oracle_fields(spec, inputs)
+    for key in _case_keys(golden, case, 'sws'):
+      _, stat, var = key[len(case) + 1:].split('/', 2)
+      sws, sw, out_dims = _oracle_state(case, spec, fields, stat, var, inputs)
+      want_dims = [str(d) for d in golden[key + '@dims']]
+      _assert_close(_transpose_to(sws, out_dims, want_dims), golden[key], key)
+      sw_key = f'{case}/sw/{stat}/{var}'
+      _assert_close(_transpose_to(sw, out_dims, want_dims), golden[sw_key],
+                    sw_key, exact=not spec['weighted'])
+      checked += 1
+  assert checked == len([k for k in golden if '/sws/' in k and '@' not in k])
+
+
+def test_oracle_reproduces_reference_values(golden, inputs):
+  """RMSE / ACC / CRPS ... values from the oracle's means."""
+  table = _case_table(inputs)
+
+  def mean(case, spec, fields, stat, var):
+    sws, sw, dims = _oracle_state(case, spec, fields, stat, var, inputs)
+    return oracle.mean_statistic(sws, sw), dims
+
+  for case, spec in table.items():
+    fields = _oracle_fields(spec, inputs)
+    for key in _case_keys(golden, case, 'value'):
+      metric, var = key[len(case) + len('/value/'):].split('.', 1)
+      want_dims = [str(d) for d in golden[key + '@dims']]
+      skip = case == 'ens/skipna_ensemble'
+      if metric in ('rmse', 'mse', 'rmse_members', 'rmse_mean', 'wind_rmse'):
+        stat = {
+            'rmse_members': 'SquaredError_each_realization',
+            'rmse_mean': ("SquaredError_predictions_ensemble_mean_self."
+                          "_ensemble_dim='realization'_self._skipna=False"),
+            'wind_rmse': 'WindVectorSquaredError_wind_vector',
+        }.get(metric, 'SquaredError')
+        value, dims = mean(case, spec, fields, stat, var)
+        value = value if metric == 'mse' else oracle.rmse_from_mean(value)
+      elif metric == 'mae':
+        value, dims = mean(case, spec, fields, 'AbsoluteError', var)
+      elif metric == 'bias':
+        value, dims = mean(case, spec, fields, 'Error', var)
+      elif metric == 'acc':
+        cov, dims = mean(case, spec, fields, 'AnomalyCovariance', var)
+        spa, _ = mean(case, spec, fields, 'SquaredPredictionAnomaly', var)
+        sta, _ = mean(case, spec, fields, 'SquaredTargetAnomaly', var)
+        value = oracle.acc_from_means(cov, spa, sta)
+      elif metric in ('crps_fair', 'crps_unfair'):
+        fair = metric.split('_')[1]
+        skill, dims = mean(case, spec, fields, 'CRPSSkill_realization', var)
+        spread, _ = mean(case, spec, fields,
+                         f'CRPSSpread_realization_{fair}_predictions', var)
+        value = oracle.crps_from_means(skill, spread)
+      else:
+        var_stat = f'EnsembleVariance_realization_skipna_ensemble_{skip}'
+        mse_stat = ('UnbiasedEnsembleMeanSquaredError_realization_'
+                    f'skipna_ensemble_{skip}')
+        if metric == 'ens_var':          # probabilistic.py EnsembleRootMeanVariance
+          value, dims = mean(case, spec, fields, var_stat, var)
+          value = np.sqrt(value)
+        elif metric == 'unbiased_rmse':  # UnbiasedEnsembleMeanRMSE
+          value, dims = mean(case, spec, fields, mse_stat, var)
+          value = np.sqrt(value)
+        elif metric == 'unbiased_ssr':   # UnbiasedSpreadSkillRatio
+          spread, dims = mean(case, spec, fields, var_stat, var)
+          skill, _ = mean(case, spec, fields, mse_stat, var)
+          value = np.sqrt(spread / skill)
+        else:
+          raise KeyError(metric)
+      _assert_close(_transpose_to(value, dims, want_dims), golden[key], key)
+
+
+def test_oracle_weights_match_reference(golden):
+  """GridAreaWeighting.weights on five latitude grids (weighting.py:45-130)."""
+  for name in ('poles_ascending', 'poles_descending', 'no_poles',
+               'quarter_degree', 'float32_coord'):
+    lat = golden[f'weights/{name}/latitude']
+    np.testing.assert_allclose(oracle.grid_area_weights(lat),
+                               golden[f'weights/{name}/weights'], rtol=1e-12,
+                               atol=1e-15, err_msg=name)
+  assert golden['weights/no_latitude_dim'] == 1
+
+
+def test_chunk_combine_equals_monolithic_in_the_reference(golden):
+  """AggregationState.__add__ over init_time chunks (aggregation.py:84-110):
+  the reference's chunked values equal its monolithic ones."""
+  for key in _case_keys(golden, 'det/chunked', 'value'):
+    whole = key.replace('det/chunked', 'det/weighted')
+    np.testing.assert_allclose(golden[key], golden[whole], rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# the CUDA path: same case code, this package's modules
+# ---------------------------------------------------------------------------
+
+
+def _product_namespace():
+  from weatherbenchx_b200 import aggregation, binning, weighting
+  from weatherbenchx_b200 import xarray_lite as xl
+  from weatherbenchx_b200.metrics import base, deterministic
+  from weatherbenchx_b200.metrics import probabilistic, wrappers
+  return cases.namespace(
+      xr=xl, aggregation=aggregation, binning=binning, weighting=weighting,
+      base=base, deterministic=deterministic, probabilistic=probabilistic,
+      wrappers=wrappers)
+
+
+def _labels_match(golden, key, da):
+  for d in da.dims:
+    stored = golden.get(f'{key}@labels/{d}')
+    if stored is not None:
+      assert [str(v) for v in da.coords[d].values] == [str(v) for v in stored]
+
+
+CASE_NAMES = [
+    'det/weighted', 'det/unweighted', 'det/keep_init',
+    'det/reduce_all_but_level', 'det/nan_default', 'det/nan_masked',
+    'det/nan_skipna', 'det/nan_masked_skipna', 'det/regions',
+    'det/regions_x_landsea', 'det/regions_nan_masked',
+    'det/regions_nan_default', 'det/lat_lon_bands', 'acc/weighted',
+    'acc/nan_skipna', 'acc/nan_masked', 'wind/weighted', 'ens/member_last',
+    'ens/member_major', 'ens/use_sort', 'ens/unweighted_keep_init',
+    'ens/skipna_ensemble', 'ens/nan_members_propagate', 'ens/regions',
+    'ens/nan_targets_default', 'ens/nan_targets_masked',
+    'ens/nan_targets_skipna', 'ens/regions_nan_targets_masked',
+    'ens/ensemble_averaged_rmse', 'ens/ensemble_mean_rmse']
+
+
+def test_case_names_cover_the_fixture(golden):
+  assert CASE_NAMES == [str(n) for n in golden['cases']]
+
+
+def _run_product_case(golden, inputs, case, space):
+  from weatherbenchx_b200 import engine
+  ns = _product_namespace()
+  for name, spec, metrics, aggregator, predictions, targets in (
+      cases.build_cases(ns, inputs)):
+    if name == case:
+      break
+  else:
+    raise KeyError(case)
+  if space == 'device':
+    predictions = {k: engine.to_device(v) for k, v in predictions.items()}
+    targets = {k: engine.to_device(v) for k, v in targets.items()}
+  statistics = ns.base.compute_unique_statistics_for_all_metrics(
+      metrics, predictions, targets)
+  state = aggregator.aggregate_statistics(statistics)
+  sws_keys = _case_keys(golden, case, 'sws')
+  stored = {tuple(k[len(case) + 5:].split('/', 1)) for k in sws_keys}
+  produced = {(s, v) for s, per_var in state.sum_weighted_statistics.items()
+              for v in per_var}
+  assert produced == stored  # same statistic unique_names, same variables
+  for stat, var in sorted(stored):
+    for part, tree in (('sws', state.sum_weighted_statistics),
+                       ('sw', state.sum_weights)):
+      key = f'{case}/{part}/{stat}/{var}'
+      da = tree[stat][var]
+      want_dims = [str(d) for d in golden[key + '@dims']]
+      _labels_match(golden, key, da)
+      _assert_close(_transpose_to(da.values, da.dims, want_dims), golden[key],
+                    key, exact=part == 'sw' and not spec['weighted'])
+  values = state.metric_values(metrics)
+  value_keys = _case_keys(golden, case, 'value')
+  assert {k[len(case) + len('/value/'):] for k in value_keys} == set(values)
+  for key in value_keys:
+    da = values[key[len(case) + len('/value/'):]]
+    want_dims = [str(d) for d in golden[key + '@dims']]
+    _assert_close(_transpose_to(da.values, da.dims, want_dims), golden[key],
+                  key)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('space', ['host', 'device'])
+@pytest.mark.parametrize('case', CASE_NAMES)
+def test_cuda_path_reproduces_reference(golden, inputs, case, space):
+  """State and values of the reference, from the CUDA path, for every case."""
+  _run_product_case(golden, inputs, case, space)
+
+
+# Cases whose host-space path needs device memory even before a kernel runs
+# (per-point fields of the CRPS launch, the EnsembleMean transform).
+NEEDS_DEVICE = {'ens/regions', 'ens/regions_nan_targets_masked',
+                'ens/ensemble_mean_rmse'}
+
+
+@pytest.mark.parametrize('case',
+                         [c for c in CASE_NAMES if c not in NEEDS_DEVICE])
+def test_host_side_with_interpreted_plans_reproduces_reference(
+    golden, inputs, case, monkeypatch):
+  """Everything above the C ABI (statistic classes, launch grouping, planner
+  tables, result unpacking) on the GPU-less box: the plans are executed by the
+  NumPy interpreter of tests/wbx_emulator.py instead of the CUDA library."""
+  import wbx_emulator
+  wbx_emulator.installed(monkeypatch)
+  _run_product_case(golden, inputs, case, 'host')
+
+
+@pytest.mark.gpu
+def test_cuda_path_chunk_combine(golden, inputs):
+  """Chunked evaluation + AggregationState.__add__ == the reference's."""
+  ns = _product_namespace()
+  metrics, total = cases.chunked_case(ns, inputs)
+  values = total.metric_values(metrics)
+  for key in _case_keys(golden, 'det/chunked', 'value'):
+    da = values[key[len('det/chunked/value/'):]]
+    want_dims = [str(d) for d in golden[key + '@dims']]
+    _assert_close(_transpose_to(da.values, da.dims, want_dims), golden[key],
+                  key)
+
+
+def test_host_weights_match_reference(golden):
+  """GridAreaWeighting of this package (host float64, uploaded as w_y)."""
+  from weatherbenchx_b200 import weighting
+  from weatherbenchx_b200 import xarray_lite as xl
+  for name in ('poles_ascending', 'poles_descending', 'no_poles',
+               'quarter_degree', 'float32_coord'):
+    lat = golden[f'weights/{name}/latitude']
+    stat = xl.DataArray(np.zeros((len(lat), 4), np.float32),
+                        ('latitude', 'longitude'),
+                        coords={'latitude': lat,
+                                'longitude': np.arange(4) * 90.0})
+    w = weighting.GridAreaWeighting().weights(stat)
+    np.testing.assert_allclose(w.values, golden[f'weights/{name}/weights'],
+                               rtol=1e-12, atol=1e-15, err_msg=name)

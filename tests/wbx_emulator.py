@@ -1,0 +1,169 @@
+"""NumPy interpreter of the C ABI's plan contract (TEST INFRASTRUCTURE).
+
+``installed(monkeypatch)`` replaces ``_cabi.get_context``, ``_cabi.DetPlan``
+and ``_cabi.CrpsPlan`` -- the three names through which the host side reaches
+the CUDA library -- by stand-ins that execute the job tables the planner built
+(``include/wbx_b200.h``: wbx_det_desc / wbx_crps_desc) with NumPy on HOST
+addresses.  Everything above the C ABI runs unmodified: statistic classes, the
+Aggregator's grouping of statistics into launches, the planner (slab layout,
+job / cell tables, weights, class maps), merged launches, the unpacking of the
+flat result buffers into labelled AggregationStates.
+
+Purpose: host-side logic can be checked on the GPU-less build box against the
+reference's golden vectors.  It is never used by the product, by ``-m gpu``
+tests, ``smoke()`` or ``bench.py``; the kernels themselves are only ever
+validated on a B200.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import warnings
+
+import numpy as np
+
+from weatherbenchx_b200 import _cabi
+
+
+def _read(addr, n, dtype):
+  nbytes = n * np.dtype(dtype).itemsize
+  buf = (ctypes.c_char * nbytes).from_address(int(addr))
+  return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+class _Context:
+  device = 0
+  handle = None
+
+  def use_torch_stream(self):
+    pass
+
+  def synchronize(self):
+    pass
+
+
+class DetPlan:
+  """wbx_det_plan_create + wbx_det_plan_run(space=HOST) on host addresses."""
+
+  def __init__(self, ctx, **desc):
+    if desc['space'] != _cabi.SPACE_HOST:
+      raise RuntimeError('the emulator only reads host memory')
+    self.desc = desc
+    self.n_cells = int(desc['n_cells'])
+    self.n_classes = int(desc.get('n_classes') or 0)
+    self.keepalive = None
+
+  def run_to_host(self):
+    d = self.desc
+    ny, nx = d['ny'], d['nx']
+    slab = ny * nx
+    ncls = max(self.n_classes, 1)
+    rows = self.n_cells * ncls
+    ws = np.zeros((rows, _cabi.NUM_DET_STATS))
+    w = np.zeros((rows, _cabi.NUM_DET_WCLASSES))
+    wy = d['w_y'] if d.get('w_y') is not None else np.ones(ny)
+    wx = d['w_x'] if d.get('w_x') is not None else np.ones(nx)
+    wgt = (np.asarray(wy)[:, None] * np.asarray(wx)[None, :]).reshape(-1)
+    skipna = bool(d['flags'] & _cabi.FLAG_SKIPNA)
+    stat_mask = d.get('stat_mask') or 63
+    classes = (np.asarray(d['class_map']).reshape(-1).astype(np.int64)
+               if self.n_classes else np.zeros(slab, np.int64))
+    for j in range(len(d['pred'])):
+      p = _read(d['pred'][j], slab, np.float32)
+      t = _read(d['target'][j], slab, np.float32)
+      c = (_read(d['clim'][j], slab, np.float32)
+           if d.get('clim') is not None else np.zeros(slab, np.float32))
+      m = (_read(d['mask'][j], slab, np.uint8) != 0
+           if d.get('mask') is not None else np.ones(slab, bool))
+      wo = d['w_outer'][j] if d.get('w_outer') is not None else 1.0
+      with np.errstate(invalid='ignore'):
+        vals = [p - t, np.abs(p - t), (p - t) ** 2, (p - c) ** 2,
+                (t - c) ** 2, (p - c) * (t - c)]
+      base = int(d['cell'][j]) * ncls
+      done_w = set()
+      for s, v in enumerate(vals):
+        if not stat_mask >> s & 1:
+          continue
+        valid = m & ~np.isnan(v) if skipna else m
+        v64 = np.where(valid, v, 0).astype(np.float64) * wgt
+        ws[base:base + ncls, s] += wo * np.bincount(
+            classes, weights=v64, minlength=ncls)
+        k = _cabi.STAT_WCLASS[s]
+        if k not in done_w:
+          done_w.add(k)
+          w[base:base + ncls, k] += wo * np.bincount(
+              classes, weights=valid * wgt, minlength=ncls)
+    return ws, w
+
+  def close(self):
+    pass
+
+
+class CrpsPlan:
+  """wbx_crps_plan_create + wbx_crps_plan_run(space=HOST) on host addresses."""
+
+  def __init__(self, ctx, **desc):
+    if desc['space'] != _cabi.SPACE_HOST:
+      raise RuntimeError('the emulator only reads host memory')
+    if not (desc['flags'] & _cabi.CRPS_SKIPNA_ENSEMBLE) and (
+        desc['n_members'] < 2 and (desc.get('stat_mask') or 15) & 2):
+      raise ValueError('Cannot estimate CRPS spread with n_ensemble < 2.')
+    self.desc = desc
+    self.n_cells = int(desc['n_cells'])
+    self.keepalive = None
+
+  def run_to_host(self):
+    d = self.desc
+    ny, nx, n_mem = d['ny'], d['nx'], d['n_members']
+    slab = ny * nx
+    ms, ps = int(d['member_stride']), int(d['point_stride'])
+    ws = np.zeros((self.n_cells, 4))
+    w = np.zeros((self.n_cells, 4))
+    wy = d['w_y'] if d.get('w_y') is not None else np.ones(ny)
+    wx = d['w_x'] if d.get('w_x') is not None else np.ones(nx)
+    wgt = (np.asarray(wy)[:, None] * np.asarray(wx)[None, :]).reshape(-1)
+    skipna_stat = bool(d['flags'] & _cabi.FLAG_SKIPNA)
+    ens_skipna = bool(d['flags'] & _cabi.CRPS_SKIPNA_ENSEMBLE)
+    fair = bool(d['flags'] & _cabi.CRPS_FAIR)
+    stat_mask = d.get('stat_mask') or 15
+    extent = (n_mem - 1) * ms + (slab - 1) * ps + 1
+    for j in range(len(d['ens'])):
+      flat = _read(d['ens'][j], extent, np.float32)
+      x = np.lib.stride_tricks.as_strided(
+          flat, (n_mem, slab), (ms * 4, ps * 4)).astype(np.float32)
+      y = _read(d['target'][j], slab, np.float32)
+      m = (_read(d['mask'][j], slab, np.uint8) != 0
+           if d.get('mask') is not None else np.ones(slab, bool))
+      wo = d['w_outer'][j] if d.get('w_outer') is not None else 1.0
+      with np.errstate(all='ignore'), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        n = (~np.isnan(x)).sum(0) if ens_skipna else np.full(slab, n_mem)
+        mean_fn = np.nanmean if ens_skipna else np.mean
+        sum_fn = np.nansum if ens_skipna else np.sum
+        var_fn = np.nanvar if ens_skipna else np.var
+        skill = mean_fn(np.abs(x - y[None]), axis=0)
+        pair = sum_fn(np.abs(x[:, None, :] - x[None, :, :]), axis=(0, 1))
+        spread = pair / (n * (n - (1 if fair else 0)))
+        var = var_fn(x, axis=0, ddof=1)
+        umse = (mean_fn(x, axis=0) - y) ** 2 - var / n
+      cell = int(d['cell'][j])
+      for s, v in enumerate((skill, spread, var, umse)):
+        if not stat_mask >> s & 1:
+          continue
+        valid = m & ~np.isnan(v) if skipna_stat else m
+        ws[cell, s] += wo * (np.where(valid, v, 0).astype(np.float64)
+                             * wgt).sum()
+        w[cell, s] += wo * (valid * wgt).sum()
+    return ws, w
+
+  def close(self):
+    pass
+
+
+def installed(monkeypatch):
+  """Routes the host side's three entry points to the interpreter."""
+  ctx = _Context()
+  monkeypatch.setattr(_cabi, 'get_context', lambda device=None: ctx)
+  monkeypatch.setattr(_cabi, 'DetPlan', DetPlan)
+  monkeypatch.setattr(_cabi, 'CrpsPlan', CrpsPlan)
+  return ctx

@@ -29,6 +29,7 @@ from weatherbenchx_b200.lazy import LazyEnsembleAveraged
 from weatherbenchx_b200.lazy import LazyPassthrough
 from weatherbenchx_b200.lazy import LazyStatistic
 from weatherbenchx_b200.lazy import LazySumStatistic
+from weatherbenchx_b200.lazy import mask_identity
 from weatherbenchx_b200.metrics import base as metrics_base
 
 
@@ -449,6 +450,19 @@ class Aggregator:
         subgroups.extend(by_clim.values())
       else:
         subgroups.append(plain)
+    if self.masked:
+      # The kernels apply one mask to every statistic of a launch, but only
+      # statistics whose expression touches the masked input carry the 'mask'
+      # coordinate in the reference (SquaredPredictionAnomaly, CRPSSpread and
+      # EnsembleVariance of unmasked predictions do not, and stay unmasked:
+      # aggregation.py:339).  Statistics with different masks get own launches.
+      split = []
+      for members in subgroups:
+        by_mask: dict = collections.defaultdict(list)
+        for m in members:
+          by_mask[mask_identity(m[2])].append(m)
+        split.extend(by_mask.values())
+      subgroups = split
     planned = []  # (members, spec, distinct statistics) of deterministic groups
     planned_crps = []  # the same for ensemble groups
     for members in subgroups:

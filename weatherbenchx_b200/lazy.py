@@ -53,6 +53,61 @@ class AlignedClimatology:
     return out
 
 
+# Statistics whose defining expression touches only one of the two inputs.  In
+# the reference the result of e.g. ``(predictions - climatology) ** 2`` carries
+# the coordinates of the predictions and the climatology only -- in particular
+# NOT the 'mask' coordinate that ``add_nan_mask_to_data`` puts on the targets
+# (deterministic.py:225-232, probabilistic.py:241-247,266-273), so
+# ``Aggregator(masked=True)`` leaves such a statistic unmasked
+# (aggregation.py:339: ``hasattr(stat, 'mask')``).
+_KIND_OPERANDS = {
+    'SquaredPredictionAnomaly': ('predictions',),
+    'SquaredTargetAnomaly': ('targets',),
+    'CRPSSpread': ('predictions',),
+    'EnsembleVariance': ('predictions',),
+}
+
+
+def _reference_mask(kind: str, predictions: xl.DataArray,
+                    targets: xl.DataArray, dims, drop_dim=None):
+  """The 'mask' coordinate the reference's result would carry, or None.
+
+  The mask of the operand(s) the expression touches; when both carry one they
+  must agree, otherwise xarray's coordinate merge drops it.
+  """
+  operands = {'predictions': predictions, 'targets': targets}
+  found = []
+  for which in _KIND_OPERANDS.get(kind, ('predictions', 'targets')):
+    mask = operands[which]._coords.get('mask')  # pylint: disable=protected-access
+    if mask is None or not set(mask.dims) <= set(dims):
+      continue
+    if drop_dim is not None and drop_dim in mask.dims:
+      continue
+    found.append(mask)
+  if not found:
+    return None
+  if len(found) == 2:
+    a, b = found
+    if a is not b and a._data is not b._data and (  # pylint: disable=protected-access
+        a.dims != b.dims or not np.array_equal(a.to_numpy(), b.to_numpy())):
+      return None
+  return found[0]
+
+
+def _with_reference_mask(coords: dict, mask) -> dict:
+  coords = dict(coords)
+  coords.pop('mask', None)
+  if mask is not None:
+    coords['mask'] = mask
+  return coords
+
+
+def mask_identity(stat) -> int | None:
+  """Groups statistics that can share a masked launch (same mask payload)."""
+  mask = stat._coords.get('mask')  # pylint: disable=protected-access
+  return None if mask is None else id(mask._data)  # pylint: disable=protected-access
+
+
 class LazyStatistic(xl.DataArray):
   """A per-gridpoint statistic that is evaluated on demand."""
 
@@ -87,8 +142,12 @@ class LazyStatistic(xl.DataArray):
     self._sizes = {d: sizes[d] for d in dims}
     self.name = predictions.name
     self.attrs = {}
-    self._coords = (dict(predictions._coords) if same_grid else  # pylint: disable=protected-access
-                    xl._merge_coords(predictions, targets, dims))  # pylint: disable=protected-access
+    coords = (dict(predictions._coords) if same_grid else  # pylint: disable=protected-access
+              xl._merge_coords(predictions, targets, dims))  # pylint: disable=protected-access
+    if 'mask' in predictions._coords or 'mask' in targets._coords:  # pylint: disable=protected-access
+      coords = _with_reference_mask(
+          coords, _reference_mask(kind, predictions, targets, dims))
+    self._coords = coords
     self._materialized = None
 
   # -- metadata without materialising ---------------------------------------
@@ -285,7 +344,11 @@ class LazyEnsembleStatistic(LazyStatistic):
     self.name = predictions.name
     self.attrs = {}
     coords = xl._merge_coords(predictions, targets, dims)  # pylint: disable=protected-access
-    self._coords = {k: v for k, v in coords.items() if ensemble_dim not in v.dims}
+    coords = {k: v for k, v in coords.items() if ensemble_dim not in v.dims}
+    if 'mask' in predictions._coords or 'mask' in targets._coords:  # pylint: disable=protected-access
+      coords = _with_reference_mask(coords, _reference_mask(
+          kind, predictions, targets, dims, drop_dim=ensemble_dim))
+    self._coords = coords
     self._materialized = None
 
   @property

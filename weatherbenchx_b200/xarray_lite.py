@@ -23,6 +23,7 @@ boundary without copying the payload.
 
 from __future__ import annotations
 
+import collections.abc
 import numbers
 from typing import Any, Hashable, Iterable, Mapping, Sequence
 
@@ -37,6 +38,37 @@ def _as_payload(data):
   if _is_device(data):
     return data
   return np.asarray(data)
+
+
+class _Coords(collections.abc.MutableMapping):
+  """``da.coords``: a live view; assignment validates like the constructor.
+
+  The reference assigns label arrays this way (``masks.coords[bin_dim] =
+  np.array(labels)``, binning.py:135,181,199).
+  """
+
+  __slots__ = ('_owner',)
+
+  def __init__(self, owner: 'DataArray'):
+    self._owner = owner
+
+  def __getitem__(self, key):
+    return self._owner._coord_view(key)  # pylint: disable=protected-access
+
+  def __setitem__(self, key, value):
+    self._owner._set_coord(key, value)  # pylint: disable=protected-access
+
+  def __delitem__(self, key):
+    del self._owner._coords[key]  # pylint: disable=protected-access
+
+  def __iter__(self):
+    return iter(self._owner._coords)  # pylint: disable=protected-access
+
+  def __len__(self):
+    return len(self._owner._coords)  # pylint: disable=protected-access
+
+  def __repr__(self):
+    return f'Coords({list(self)})'
 
 
 class DataArray:
@@ -97,6 +129,16 @@ class DataArray:
             f'coordinate {key!r} size {n} != array size {sizes[d]} on {d!r}')
     self._coords[key] = cv
 
+  def _coord_view(self, key) -> 'DataArray':
+    """A coordinate as an array that carries the coordinates on its own dims
+    (``stat.latitude.latitude`` works, as binning.py:190-196 expects)."""
+    cv = self._coords[key]
+    if not cv.dims:
+      return cv
+    own = set(cv.dims)
+    return cv._replace(coords={k: v for k, v in self._coords.items()
+                               if v.dims and set(v.dims) <= own})
+
   def _replace(self, data=None, dims=None, coords=None, name='__keep__'):
     out = DataArray.__new__(DataArray)
     out._data = self._data if data is None else _as_payload(data)
@@ -146,8 +188,8 @@ class DataArray:
     return dict(zip(self.dims, self.shape))
 
   @property
-  def coords(self) -> dict:
-    return self._coords
+  def coords(self) -> '_Coords':
+    return _Coords(self)
 
   def __len__(self):
     return self.shape[0]
@@ -156,7 +198,7 @@ class DataArray:
     if isinstance(key, Mapping):
       return self.isel(key)
     if key in self._coords:
-      return self._coords[key]
+      return self._coord_view(key)
     raise KeyError(key)
 
   def __getattr__(self, item):
@@ -166,7 +208,7 @@ class DataArray:
       raise AttributeError(item)
     coords = self.__dict__.get('_coords', {})
     if item in coords:
-      return coords[item]
+      return self._coord_view(item)
     raise AttributeError(item)
 
   def __repr__(self):
