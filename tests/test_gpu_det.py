@@ -238,10 +238,13 @@ def _oracle_states(P, T, C, reduce_dims, weights=(), mask=None, masked=False,
     out[name] = fn(P.values, T.values)
   for name, fn in oracle.CLIMATOLOGY_STATISTICS.items():
     out[name] = fn(P.values, T.values, aligned)
+  # The mask sits on the targets: (p - c)**2 does not inherit it and stays
+  # unmasked (deterministic.py:225-232, aggregation.py:339).
   return {
-      name: oracle.aggregate(stat, P.dims, reduce_dims, weights=weights,
-                             mask=mask, mask_dims=P.dims, masked=masked,
-                             skipna=skipna)
+      name: oracle.aggregate(
+          stat, P.dims, reduce_dims, weights=weights,
+          mask=None if name == 'SquaredPredictionAnomaly' else mask,
+          mask_dims=P.dims, masked=masked, skipna=skipna)
       for name, stat in out.items()
   }
 
@@ -635,7 +638,8 @@ def _oracle_states_bins(P, T, C, rd, w, m1, m2, mask_np, masked):
           v, P.dims, rd, weights=[(w, ('latitude',))],
           bin_masks=[(m1, ('region', 'latitude', 'longitude')),
                      (m2, ('ls', 'latitude', 'longitude'))],
-          mask=mask_np, mask_dims=P.dims, masked=masked)
+          mask=None if n == 'SquaredPredictionAnomaly' else mask_np,
+          mask_dims=P.dims, masked=masked)
       for n, v in vals.items()}
 
 
@@ -746,7 +750,8 @@ def test_lon_major_layout_matches_oracle(space, nlat, mode):
                  for n, f in oracle.CLIMATOLOGY_STATISTICS.items()})
   for name, field in fields.items():
     sws, sw, _ = oracle.aggregate(
-        field, dims, rd, weights=[(w, ('latitude',))], mask=mask_np,
+        field, dims, rd, weights=[(w, ('latitude',))],
+        mask=None if name == 'SquaredPredictionAnomaly' else mask_np,
         mask_dims=dims, masked=mode == 'masked', skipna=mode == 'skipna')
     got_ws = state.sum_weighted_statistics[name]['z'].values
     got_w = state.sum_weights[name]['z'].values

@@ -67,6 +67,25 @@ class _Coords(collections.abc.MutableMapping):
   def __len__(self):
     return len(self._owner._coords)  # pylint: disable=protected-access
 
+  def __contains__(self, key):
+    return key in self._owner._coords  # pylint: disable=protected-access
+
+  # Bulk iteration hands out the stored coordinate variables themselves (no
+  # per-item view): the planner walks these on every aggregation.
+  def values(self):
+    return self._owner._coords.values()  # pylint: disable=protected-access
+
+  def items(self):
+    return self._owner._coords.items()  # pylint: disable=protected-access
+
+  def keys(self):
+    return self._owner._coords.keys()  # pylint: disable=protected-access
+
+  def get(self, key, default=None):
+    if key in self._owner._coords:  # pylint: disable=protected-access
+      return self[key]
+    return default
+
   def __repr__(self):
     return f'Coords({list(self)})'
 
