@@ -11,15 +11,29 @@ follows (paths relative to /root/reference/weatherbenchX).
 
 Pinning status
 --------------
-* The reference itself cannot be imported here (xarray, jax, apache_beam are
-  absent and there is no network), so no reference-generated golden vectors
-  exist.  The oracle is pinned instead against every inline known-answer test
-  the reference holds for this path (aggregation_test.py:69-246,
-  weighting_test.py:24-46, metrics/metrics_test.py:44-98,603-660,983-1006,
-  1199-1308), re-expressed without xarray in ``tests/test_oracle_pins.py``,
-  and against ``tests/golden/*.npz`` (vectors produced by
-  ``tests/golden/make_golden.py`` which evaluates the reference's formulas in
-  float64 by brute force, independently of the vectorised code here).
+* PINNED TO OUTPUTS OF THE REFERENCE'S OWN CODE, generated in the build
+  container: ``tests/golden/make_reference_golden.py`` imports the unmodified
+  modules of /root/reference/weatherbenchX (aggregation, weighting, binning,
+  metrics/{base,deterministic,probabilistic,wrappers}) and stores the
+  AggregationState and metric values of 30 cases (all NaN modes, ACC with a
+  day-of-year climatology across 29 February, regions / land-sea / band bins,
+  both ensemble layouts, pairwise and sorted CRPS, skipna_ensemble, ensemble
+  moments, ensemble-averaged and ensemble-mean metrics, chunk combine, five
+  latitude grids) in ``tests/golden/reference_golden.npz``.
+  ``tests/test_reference_golden.py`` checks that this oracle reproduces every
+  stored array.  Caveat, stated wherever the vectors are used: xarray, jax and
+  absl are not installable in the container, so the reference ran on the
+  stand-in modules of ``tests/golden/reference_runtime.py`` (this repo's
+  labelled-array container under the name ``xarray``; NumPy under ``jax.numpy``)
+  -- control flow and arithmetic are the reference's, label alignment /
+  broadcasting / ``xr.dot`` (= ``np.einsum``) are the stand-in's.
+* Also pinned against every inline known-answer test the reference holds for
+  this path (aggregation_test.py:69-246, weighting_test.py:24-46,
+  metrics/metrics_test.py:44-98,603-660,983-1006,1199-1308), re-expressed
+  without xarray in ``tests/test_oracle_pins.py``, and against
+  ``tests/golden/hotpath_golden.npz`` (``tests/golden/make_golden.py``
+  evaluates the reference's formulas in float64 by brute force, independently
+  of the vectorised code here).
 * ``zonal_energy_spectrum``: PARITY UNPINNED.  /root/reference contains no
   implementation, call site or test of an energy spectrum (SURVEY.md finding
   2); the definition restated here is WeatherBench 2's

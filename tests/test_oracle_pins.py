@@ -1,9 +1,10 @@
 """Pins the CPU oracle (oracle/wbx_oracle.py) to the reference's own tests.
 
 Every test names the reference test it re-expresses (paths relative to
-/root/reference/weatherbenchX).  The reference cannot be imported here (no
-xarray), so its inline known answers -- not its outputs -- are the anchor;
-tests/golden/hotpath_golden.npz adds loop-by-loop float64 vectors.
+/root/reference/weatherbenchX).  This file anchors the oracle on the inline
+known answers of the reference's tests; tests/golden/hotpath_golden.npz adds
+loop-by-loop float64 vectors, and tests/test_reference_golden.py pins the
+oracle to outputs of the reference's own code (run on stand-in xarray).
 """
 
 import itertools
