@@ -141,7 +141,7 @@ def test_golden_crps_through_cabi(m, fair):
 
 
 @pytest.mark.parametrize('use_sort', [False, True])
-@pytest.mark.parametrize('members', [2, 8, 13, 50, 64, 70])
+@pytest.mark.parametrize('members', [2, 8, 13, 50, 51, 64, 70])
 @pytest.mark.parametrize('layout', ['member_last', 'member_major'])
 @pytest.mark.parametrize('space', ['host', 'device'])
 def test_fused_crps_matches_oracle(members, layout, space, use_sort,
@@ -185,7 +185,7 @@ def test_fused_crps_matches_oracle(members, layout, space, use_sort,
                                s_ws / s_w - 0.5 * p_ws / p_w, rtol=RTOL)
 
 
-@pytest.mark.parametrize('members', [5, 12, 50])
+@pytest.mark.parametrize('members', [5, 12, 50, 51])
 def test_sort_and_pair_kernels_agree_with_nans(members):
   """C ABI level: the sorting-network estimator == the pair sum, including
   skipna_ensemble (which the class surface only offers with use_sort=False,

@@ -494,6 +494,45 @@ __device__ __forceinline__ void sort_network(float (&x)[MAXM]) {
   OddEvenSort<MAXM, 0, MAXM>::run(x);
 }
 
+// Fixed-size networks for the operational ensemble sizes (sort_networks.inc,
+// generated by gen_sort_networks.py): odd-even merge sort on runs of arbitrary
+// length, 395 (n = 50) / 408 (n = 51) compare-exchanges against the 421 / 433
+// ptxas leaves of the 64-wire network with +inf pads.  The sorted order sits
+// in a fixed permutation of the wires (WBX_SORT<n>_RANKS).
+#include "sort_networks.inc"
+
+template <int MFIX>
+struct FixedSort {
+  static constexpr bool kAvailable = false;
+};
+
+#define WBX_CE(a, b) cmp_exchange<MAXM>(x, a, b);
+#define WBX_RANK_TERM(q, i) \
+  if ((q) > 0 && (q) < n) sp += static_cast<float>(2 * (q) + 1 - n) * (x[i] - c);
+#define WBX_FIXED_SORT(N)                                                      \
+  template <>                                                                  \
+  struct FixedSort<N> {                                                        \
+    static constexpr bool kAvailable = true;                                   \
+    template <int MAXM>                                                        \
+    static __device__ __forceinline__ void sort(float (&x)[MAXM]) {            \
+      WBX_SORT##N(WBX_CE)                                                      \
+    }                                                                          \
+    /* sum_q (2q + 1 - n) (x_(q) - x_(0)) over the first n ranks */            \
+    template <int MAXM>                                                        \
+    static __device__ __forceinline__ float moment(const float (&x)[MAXM],     \
+                                                   const int n) {              \
+      const float c = x[0]; /* rank 0 is wire 0 in both networks */            \
+      float sp = 0.f;                                                          \
+      WBX_SORT##N##_RANKS(WBX_RANK_TERM)                                       \
+      return sp;                                                               \
+    }                                                                          \
+  };
+WBX_FIXED_SORT(50)
+WBX_FIXED_SORT(51)
+#undef WBX_FIXED_SORT
+#undef WBX_RANK_TERM
+#undef WBX_CE
+
 // MFIX > 0 fixes the member count at compile time: the +inf padding lanes
 // become constants, ptxas folds every compare-exchange that touches them and
 // the network shrinks to the size of the real ensemble (M = 50: 64 -> 50 wires).
@@ -545,19 +584,33 @@ __global__ void __launch_bounds__(kCrpsThreads)
       // skill, moments + NaN bookkeeping (order-independent sums)
       float sk = 0.f, msum = 0.f;
       int n_nan = 0;
+      // The fixed-size networks without skipna_ensemble need no per-member NaN
+      // test (three min/max-pipe instructions per member, the pipe that bounds
+      // this kernel): sum_m |x_m| is NaN iff some member is (no cancellation:
+      // every term is >= 0, and +-inf members stay inf), and a NaN member only
+      // has to turn skill and spread into NaN at the end.
+      constexpr bool kCheapNan = !ENS_SKIPNA && FixedSort<MFIX>::kAvailable;
+      float sabs = 0.f;
 #pragma unroll
       for (int m = 0; m < MAXM; ++m) {
         if (m < M) {
-          const bool isn = !(x[m] == x[m]);
-          n_nan += isn ? 1 : 0;
-          const float d = fabsf(x[m] - y);
-          sk += (ENS_SKIPNA && isn) ? 0.f : d;
-          if constexpr (MOMENTS) msum += (ENS_SKIPNA && isn) ? 0.f : x[m];
-          if constexpr (!MOMENTS) {
-            if (isn) x[m] = inf;
+          if constexpr (kCheapNan) {
+            sk += fabsf(x[m] - y);
+            sabs += fabsf(x[m]);
+            if constexpr (MOMENTS) msum += x[m];
+          } else {
+            const bool isn = !(x[m] == x[m]);
+            n_nan += isn ? 1 : 0;
+            const float d = fabsf(x[m] - y);
+            sk += (ENS_SKIPNA && isn) ? 0.f : d;
+            if constexpr (MOMENTS) msum += (ENS_SKIPNA && isn) ? 0.f : x[m];
+            if constexpr (!MOMENTS) {
+              if (isn) x[m] = inf;
+            }
           }
         }
       }
+      if constexpr (kCheapNan) n_nan = (sabs == sabs) ? 0 : 1;
       float v[kCrpsStats] = {0.f, 0.f, 0.f, 0.f};
       if constexpr (MOMENTS) {
         const float fnm = static_cast<float>(ENS_SKIPNA ? (M - n_nan) : M);
@@ -566,22 +619,31 @@ __global__ void __launch_bounds__(kCrpsThreads)
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
           if (m < M) {
-            const bool isn = !(x[m] == x[m]);
             const float d = x[m] - mean;
-            ss = __fadd_rn(ss, (ENS_SKIPNA && isn) ? 0.f : __fmul_rn(d, d));
-            if (isn) x[m] = inf;
+            if constexpr (kCheapNan) {
+              ss = __fadd_rn(ss, __fmul_rn(d, d));  // NaN members propagate
+            } else {
+              const bool isn = !(x[m] == x[m]);
+              ss = __fadd_rn(ss, (ENS_SKIPNA && isn) ? 0.f : __fmul_rn(d, d));
+              if (isn) x[m] = inf;
+            }
           }
         }
         v[2] = __fdiv_rn(ss, fnm - 1.f);
         v[3] = __fsub_rn(__fmul_rn(mean - y, mean - y), __fdiv_rn(v[2], fnm));
       }
-      sort_network<MAXM>(x);
       const int n = ENS_SKIPNA ? (M - n_nan) : M;
-      const float c = x[0];
       float sp = 0.f;
+      if constexpr (FixedSort<MFIX>::kAvailable) {
+        FixedSort<MFIX>::template sort<MAXM>(x);
+        sp = FixedSort<MFIX>::template moment<MAXM>(x, n);
+      } else {
+        sort_network<MAXM>(x);
+        const float c = x[0];
 #pragma unroll
-      for (int q = 1; q < MAXM; ++q) {
-        if (q < n) sp += static_cast<float>(2 * q + 1 - n) * (x[q] - c);
+        for (int q = 1; q < MAXM; ++q) {
+          if (q < n) sp += static_cast<float>(2 * q + 1 - n) * (x[q] - c);
+        }
       }
       const float fn = static_cast<float>(n);
       float skill = __fdiv_rn(sk, fn);
