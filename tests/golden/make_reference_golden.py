@@ -113,6 +113,20 @@ def main():
   for name, da in total.metric_values(metrics).items():
     put_labelled(f'det/chunked/value/{name}', da)
   weighting_cases()
+  # bin masks of the coordinate-value binnings (binning.py:301-704)
+  mask_names = []
+  for name, instance, stat in reference_cases.mask_cases(NS):
+    mask = instance.create_bin_mask(stat)
+    bdim = instance.bin_dim_name
+    order = [bdim] + [d for d in mask.dims if d != bdim]
+    put(f'masks/{name}/mask', mask.transpose(*order).values)
+    put(f'masks/{name}/dims', np.array(order, dtype='U32'))
+    put(f'masks/{name}/labels',
+        np.array([str(v) for v in mask.coords[bdim].values], dtype='U32'))
+    put(f'masks/{name}/label_kind', np.array(
+        mask.coords[bdim].values.dtype.kind))
+    mask_names.append(name)
+  put('mask_cases', np.array(mask_names, dtype='U64'))
   put('cases', np.array(names, dtype='U64'))
   np.savez_compressed(OUT, **STORE)
   size = os.path.getsize(OUT)

@@ -49,6 +49,8 @@ REGIONS = {
 }
 ENS_REGIONS = {'global': ((-90, 90), (0, 360)), 'sh': ((-90, -20), (0, 360)),
                'box': ((-10, 60), (300, 60))}
+LEAD_SETS = {'analysis': 0, 'short': [0, 6], 'late': [6, 12]}   # overlapping
+LEVEL_SETS = {'low': [850], 'both': [500, 850]}
 DOY_USED = np.arange(58, 63)
 HOURS = np.arange(0, 24, 6)
 
@@ -115,6 +117,9 @@ def build_cases(ns, inputs):
 
   def da(values, dims, **extra_coords):
     coords = {d: COORDS[d] for d in dims}
+    if 'init_time' in dims and 'lead_time' in dims:
+      coords['valid_time'] = (('init_time', 'lead_time'),
+                              INIT[:, None] + LEAD[None, :])
     coords.update(extra_coords)
     return xr.DataArray(values, dims, coords=coords)
 
@@ -136,7 +141,7 @@ def build_cases(ns, inputs):
              'bias': det.Bias()}
 
   def det_case(name, reduce_dims=None, weighted=True, nan_targets=False,
-               bins=None, use_metrics=None, **flags):
+               bins=None, use_metrics=None, only=None, **flags):
     reduce_dims = reduce_dims or RD
     spec = dict(family='det', reduce_dims=reduce_dims, weighted=weighted,
                 masked=flags.get('masked', False),
@@ -146,8 +151,13 @@ def build_cases(ns, inputs):
         reduce_dims=reduce_dims, weigh_by=area() if weighted else None,
         bin_by=_make_bins(ns, bins, inputs['land']) if bins else None,
         **flags)
-    return (name, spec, use_metrics or metrics, aggregator, predictions,
-            targets_nan if nan_targets else targets)
+    use_targets = targets_nan if nan_targets else targets
+    use_predictions = predictions
+    if only:  # a coordinate-value binning needs the coordinate on every variable
+      use_predictions = {k: predictions[k] for k in only}
+      use_targets = {k: use_targets[k] for k in only}
+    return (name, spec, use_metrics or metrics, aggregator, use_predictions,
+            use_targets)
 
   yield det_case('det/weighted')
   yield det_case('det/unweighted', weighted=False)
@@ -167,6 +177,23 @@ def build_cases(ns, inputs):
                  nan_targets=True)
   yield det_case('det/lat_lon_bands', bins=['lat30', 'lon90'],
                  use_metrics={'mse': det.MSE()})
+
+  # -- bins over outer dims: time units, value sets (binning.py:394-515,640-704)
+  rd_all = ['init_time', 'lead_time', 'latitude', 'longitude']
+  yield det_case('det/by_init_hour', bins=['init_hour'])
+  yield det_case('det/by_valid_month', bins=['valid_month'], reduce_dims=rd_all)
+  yield det_case('det/lead_sets_x_regions', bins=['lead_sets', 'regions_land'],
+                 reduce_dims=rd_all)
+  yield det_case('det/regions_x_init_hour_global',
+                 bins=['regions', 'init_hour_global'])
+  yield det_case('det/by_level_sets', bins=['level_sets'],
+                 only=['geopotential'])
+  yield det_case('det/by_init_hour_nan_default', bins=['init_hour'],
+                 nan_targets=True)
+  yield det_case('det/by_init_hour_nan_masked', bins=['init_hour_global'],
+                 nan_targets=True, masked=True)
+  yield det_case('det/by_valid_month_skipna', bins=['valid_month'],
+                 reduce_dims=rd_all, nan_targets=True, skipna=True)
 
   # -- ACC with a (dayofyear, hour) climatology ------------------------------
   clim_coords = {'dayofyear': np.arange(1, 367), 'hour': HOURS}
@@ -299,6 +326,18 @@ def _make_bins(ns, names, land_values):
     elif name == 'landsea_global':
       out.append(binning.LandSea(land.astype(np.float32),
                                  include_global_mask=True))
+    elif name == 'init_hour':
+      out.append(binning.ByTimeUnit('hour', 'init_time'))
+    elif name == 'init_hour_global':
+      out.append(binning.ByTimeUnit('hour', 'init_time', add_global_bin=True))
+    elif name == 'valid_month':
+      out.append(binning.ByTimeUnit('month', 'valid_time'))
+    elif name == 'lead_sets':
+      out.append(binning.ByTimeUnitSets(LEAD_SETS, 'hour', 'lead_time',
+                                        add_global_bin=True))
+    elif name == 'level_sets':
+      out.append(binning.BySets(LEVEL_SETS, 'level', bin_dim_name='level_set',
+                                add_set_complements=True))
     elif name == 'lat30':
       out.append(binning.LatitudeBins(30))
     elif name == 'lon90':
@@ -329,3 +368,48 @@ def chunked_case(ns, inputs):
 
 def namespace(**modules):
   return types.SimpleNamespace(**modules)
+
+
+def mask_cases(ns):
+  """(name, binning instance, statistic) for the coordinate-value binnings on
+  a sparse-style statistic: one 'index' dim with non-dimension coordinates."""
+  xr, binning = ns.xr, ns.binning
+  n = 12
+  lead = (np.array([0, 6, 6, 12, 24, 24, 30, 0, 12, 6, 48, 24]) *
+          np.timedelta64(1, 'h')).astype('timedelta64[ns]')
+  valid = np.datetime64('2020-12-30T00', 'ns') + np.arange(n) * np.timedelta64(
+      7, 'h')
+  stat = xr.DataArray(
+      np.arange(n, dtype=np.float32), ('index',),
+      coords={'index': np.arange(n),
+              'lead_time': ('index', lead),
+              'valid_time': ('index', valid),
+              'seconds': ('index', np.arange(n) * 1800 + 10),
+              'elevation': ('index', np.linspace(-5.0, 2500.0, n)),
+              'station': ('index', np.array(list('abcabcabcabd')))})
+  return [
+      ('exact_lead', binning.ByExactCoord('lead_time'), stat),
+      ('exact_lead_global',
+       binning.ByExactCoord('lead_time', add_global_bin=True), stat),
+      ('exact_station_global',
+       binning.ByExactCoord('station', add_global_bin=True), stat),
+      ('lead_day', binning.ByTimeUnit('day', 'lead_time'), stat),
+      ('valid_hour_global',
+       binning.ByTimeUnit('hour', 'valid_time', add_global_bin=True), stat),
+      ('valid_dayofyear', binning.ByTimeUnit('dayofyear', 'valid_time'), stat),
+      ('valid_year', binning.ByTimeUnit('year', 'valid_time'), stat),
+      ('hour_sets', binning.ByTimeUnitSets(
+          {'night': [0, 1, 2, 3, 4, 5, 21, 22, 23], 'noon': 12, 'empty': [9]},
+          'hour', 'valid_time', add_global_bin=True), stat),
+      ('seconds_minute', binning.ByTimeUnitFromSeconds(
+          'minute', 'seconds', bins=[0, 30, 90, 300]), stat),
+      ('seconds_hour', binning.ByTimeUnitFromSeconds('hour', 'seconds'), stat),
+      ('elevation_bins', binning.ByCoordBins(
+          'elevation', np.array([0.0, 500.0, 1000.0, 3000.0])), stat),
+      ('elevation_bins_global', binning.ByCoordBins(
+          'elevation', np.array([0.0, 500.0, 1000.0, 3000.0]),
+          add_global_bin=True), stat),
+      ('station_sets', binning.BySets(
+          {'ab': ['a', 'b'], 'd': 'd'}, 'station', bin_dim_name='station_set',
+          add_set_complements=True, add_global_bin=True), stat),
+  ]

@@ -14,8 +14,8 @@ stand-ins under those module names *in this process only*:
   ``xr.dot`` = ``np.einsum`` exactly as xarray falls back to without
   opt_einsum, ``where`` / ``mean`` / ``var`` / ``sum`` = the NumPy functions
   xarray dispatches to), plus the few extra calls the reference's hot path
-  makes (``.dt.dayofyear/.hour``, vectorised ``.sel`` with labelled indexers,
-  ``.compute()``, ``xr.set_options``, list indexing of a Dataset);
+  makes (vectorised ``.sel`` with labelled indexers, ``.compute()``,
+  ``xr.set_options``, list indexing of a Dataset, ``xr.core.accessor_dt``);
 * ``jax`` / ``jax.numpy``: NumPy (only referenced by RMSE/ACC value functions
   for the autodiff tracing hook, metrics/deterministic.py:18-20);
 * ``absl.logging``: the stdlib logger.
@@ -47,30 +47,6 @@ _REPO = os.path.dirname(os.path.dirname(os.path.dirname(
 
 def available() -> bool:
   return os.path.isdir(os.path.join(REFERENCE_ROOT, 'weatherbenchX'))
-
-
-class _DatetimeFields:
-  """``DataArray.dt`` for datetime64 payloads (base.py:398-401)."""
-
-  def __init__(self, arr):
-    self._arr = arr
-
-  def _field(self, values):
-    return self._arr._replace(data=values)  # pylint: disable=protected-access
-
-  @property
-  def dayofyear(self):
-    t = self._arr.to_numpy().astype('datetime64[ns]')
-    days = (t.astype('datetime64[D]') -
-            t.astype('datetime64[Y]').astype('datetime64[D]'))
-    return self._field(days.astype(np.int64) + 1)
-
-  @property
-  def hour(self):
-    t = self._arr.to_numpy().astype('datetime64[ns]')
-    hours = (t.astype('datetime64[h]') -
-             t.astype('datetime64[D]').astype('datetime64[h]'))
-    return self._field(hours.astype(np.int64))
 
 
 def _patch_data_array(xl):
@@ -128,7 +104,6 @@ def _patch_data_array(xl):
   data_array.sel = sel
   data_array.compute = lambda self: self
   data_array.load = lambda self: self
-  data_array.dt = property(_DatetimeFields)
 
 
 def install():
@@ -165,6 +140,10 @@ def install():
 
   xr.Dataset = Dataset
   xr.DataTree = DataTree
+  # binning.py:376-391 dispatches on the accessor type
+  xr.core = types.SimpleNamespace(accessor_dt=types.SimpleNamespace(
+      TimedeltaAccessor=xl.TimedeltaAccessor,
+      DatetimeAccessor=xl.DatetimeAccessor))
   xr.set_options = set_options
   xu = types.ModuleType('xarray.ufuncs')
   for name in ('sqrt', 'isnan', 'log', 'minimum', 'maximum', 'logical_and',

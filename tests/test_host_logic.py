@@ -672,3 +672,40 @@ def test_coordinate_views_and_assignment():
     da.coords['region'] = np.array(['a', 'b', 'c'])
   assert 'region' in da.coords and len(da.coords) == 2
   assert dict(da.coords).keys() == {'latitude', 'region'}
+
+
+def test_outer_bin_masks_fold_into_the_cell_table():
+  """Bin masks over outer dims (time units, level sets) need no per-point
+  operand: the planner sorts the jobs into (kept cell, outer class) launch
+  cells and maps the class sums to bins on the host."""
+  p, t, c = _case(('init_time', 'lead_time', 'level', 'latitude', 'longitude'))
+  p, t = p.drop_vars('mask'), t.drop_vars('mask')
+  stat = LazyStatistic('SquaredError', p, t)
+  sets = binning.ByTimeUnitSets({'a': [0], 'b': [0, 12]}, 'hour', 'lead_time')
+  levels = binning.BySets({'low': [850]}, 'level', bin_dim_name='level_set',
+                          add_set_complements=True)
+  masks = [sets.create_bin_mask(stat), levels.create_bin_mask(stat)]
+  names = [sets.bin_dim_name, levels.bin_dim_name]
+  rd = ('init_time', 'lead_time', 'latitude', 'longitude')
+  spec = engine.build_fused_spec([stat], rd, [], bin_masks=masks,
+                                 bin_dim_names=names)
+  assert spec.classes is None and spec.outer is not None
+  assert spec.outer.bin_dims == names and spec.bin_order == tuple(names)
+  # jobs: level (kept) x init x lead; lead hours {0, 12} -> 1 outer class for
+  # lead (both in 'a' and 'b' differ: hour 0 in a+b, hour 12 in b only) x 2
+  # level classes, all combined with the kept level cell
+  assert np.all(np.diff(spec.cell) >= 0)
+  assert spec.cell[-1] == spec.n_cells - 1 == len(spec.outer.dense_index) - 1
+  ws, wsum = _interpret(spec)
+  slot = _cabi.STAT_SLOT['SquaredError']
+  got = spec.outer.to_bins(ws[:, slot].reshape(spec.n_cells))
+  got_w = spec.outer.to_bins(
+      wsum[:, _cabi.STAT_WCLASS[slot]].reshape(spec.n_cells))
+  val = oracle.squared_error(p.values, t.values)
+  sws, sw, out_dims = oracle.aggregate(
+      val, p.dims, rd,
+      bin_masks=[(masks[0].values, masks[0].dims),
+                 (masks[1].values, masks[1].dims)])
+  assert out_dims == ('level',) + tuple(names)
+  np.testing.assert_allclose(got, sws, rtol=1e-6, equal_nan=True)
+  np.testing.assert_allclose(got_w, sw, rtol=1e-12)

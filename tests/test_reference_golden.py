@@ -1,6 +1,6 @@
 """Parity against vectors produced by the reference's own code.
 
-``tests/golden/reference_golden.npz`` holds, for 30 evaluation cases, the
+``tests/golden/reference_golden.npz`` holds, for 38 evaluation cases, the
 AggregationState (sum_weighted_statistics / sum_weights per statistic and
 variable) and the metric values that the UNMODIFIED modules of
 /root/reference/weatherbenchX returned in the build container
@@ -100,6 +100,42 @@ def _oracle_bins(spec, inputs):
       masks = np.stack([land_mask, ~land_mask, np.ones_like(land_mask)])
       out.append(((masks, ('land_sea', 'latitude', 'longitude')),
                   ['land', 'sea', 'global']))
+    elif name in ('init_hour', 'init_hour_global'):
+      # binning.py:394-442 + 301-332: one bin per unique hour of init_time;
+      # the optional 'global' bin comes first and turns the labels into str.
+      hours = (cases.INIT.astype('datetime64[h]') -
+               cases.INIT.astype('datetime64[D]').astype('datetime64[h]')
+               ).astype(np.int64)
+      unique = np.unique(hours)
+      masks = hours[None, :] == unique[:, None]
+      labels = list(unique)
+      if name.endswith('global'):
+        masks = np.concatenate([np.ones((1, len(hours)), bool), masks])
+        labels = ['global'] + [str(u) for u in unique]
+      out.append(((masks, ('init_time_hour', 'init_time')), labels))
+    elif name == 'valid_month':
+      valid = cases.INIT[:, None] + cases.LEAD[None, :]
+      month = valid.astype('datetime64[M]').astype(np.int64) % 12 + 1
+      unique = np.unique(month)
+      masks = month[None] == unique[:, None, None]
+      out.append(((masks, ('valid_time_month', 'init_time', 'lead_time')),
+                  list(unique)))
+    elif name == 'lead_sets':
+      # binning.py:445-515: named, possibly overlapping sets; 'global' last.
+      hours = cases.LEAD.astype('timedelta64[s]').astype(np.int64) // 3600
+      masks = [np.isin(hours, np.atleast_1d(v))
+               for v in cases.LEAD_SETS.values()]
+      masks.append(np.ones(len(hours), bool))
+      out.append(((np.stack(masks), ('lead_time_hour_sets', 'lead_time')),
+                  list(cases.LEAD_SETS) + ['global']))
+    elif name == 'level_sets':
+      # binning.py:640-704 with add_set_complements.
+      masks, labels = [], []
+      for key, values in cases.LEVEL_SETS.items():
+        m = np.isin(cases.LEVEL, values)
+        masks += [m, ~m]
+        labels += [key, f'not_in_{key}']
+      out.append(((np.stack(masks), ('level_set', 'level')), labels))
     elif name == 'lat30':
       # binning.py:204-243: closed bands [start, start + degrees].
       starts = np.arange(-90, 90 + 30, 30)[:-1]
@@ -225,7 +261,7 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
 
 def test_fixture_is_complete(golden):
   names = [str(n) for n in golden['cases']]
-  assert len(names) == 30 and len(set(names)) == 30
+  assert len(names) == 38 and len(set(names)) == 38
   for case in names:
     assert _case_keys(golden, case, 'sws'), case
     assert _case_keys(golden, case, 'value'), case
@@ -345,6 +381,30 @@ def test_oracle_weights_match_reference(golden):
   assert golden['weights/no_latitude_dim'] == 1
 
 
+def test_binning_masks_match_reference(golden):
+  """create_bin_mask of the coordinate-value binnings (ByExactCoord,
+  ByTimeUnit, ByTimeUnitSets, ByTimeUnitFromSeconds, ByCoordBins, BySets):
+  mask, bin labels and label dtype kind equal the reference's
+  (binning.py:301-704), on a sparse-style statistic."""
+  ns = _product_namespace()
+  built = {name: (instance, stat)
+           for name, instance, stat in cases.mask_cases(ns)}
+  assert list(built) == [str(n) for n in golden['mask_cases']]
+  for name, (instance, stat) in built.items():
+    mask = instance.create_bin_mask(stat)
+    bdim = instance.bin_dim_name
+    want_dims = [str(d) for d in golden[f'masks/{name}/dims']]
+    assert want_dims[0] == bdim and set(mask.dims) == set(want_dims), name
+    got = mask.transpose(*want_dims)
+    assert got.dtype == bool, name
+    np.testing.assert_array_equal(got.values, golden[f'masks/{name}/mask'],
+                                  err_msg=name)
+    labels = mask.coords[bdim].values
+    assert [str(v) for v in labels] == [
+        str(v) for v in golden[f'masks/{name}/labels']], name
+    assert labels.dtype.kind == str(golden[f'masks/{name}/label_kind']), name
+
+
 def test_chunk_combine_equals_monolithic_in_the_reference(golden):
   """AggregationState.__add__ over init_time chunks (aggregation.py:84-110):
   the reference's chunked values equal its monolithic ones."""
@@ -381,7 +441,11 @@ CASE_NAMES = [
     'det/reduce_all_but_level', 'det/nan_default', 'det/nan_masked',
     'det/nan_skipna', 'det/nan_masked_skipna', 'det/regions',
     'det/regions_x_landsea', 'det/regions_nan_masked',
-    'det/regions_nan_default', 'det/lat_lon_bands', 'acc/weighted',
+    'det/regions_nan_default', 'det/lat_lon_bands', 'det/by_init_hour',
+    'det/by_valid_month', 'det/lead_sets_x_regions',
+    'det/regions_x_init_hour_global', 'det/by_level_sets',
+    'det/by_init_hour_nan_default', 'det/by_init_hour_nan_masked',
+    'det/by_valid_month_skipna', 'acc/weighted',
     'acc/nan_skipna', 'acc/nan_masked', 'wind/weighted', 'ens/member_last',
     'ens/member_major', 'ens/use_sort', 'ens/unweighted_keep_init',
     'ens/skipna_ensemble', 'ens/nan_members_propagate', 'ens/regions',

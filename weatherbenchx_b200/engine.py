@@ -366,6 +366,80 @@ def _fold_bin_masks(bin_masks, bin_dim_names, inner, sizes) -> BinClasses:
 
 
 @dataclasses.dataclass
+class OuterClasses:
+  """Bin masks over OUTER (job) dims folded into the job -> cell table.
+
+  A mask [bins, init_time] (ByTimeUnit, ByTimeUnitSets, BySets on a level
+  coordinate, ...) does not vary inside a slab, so it needs no per-point
+  operand: jobs with the same membership pattern across all such masks form an
+  *outer class*, the launch sums every (kept cell, outer class) pair into its
+  own output cell (jobs re-ordered so that cells stay contiguous), and the
+  class sums are mapped to bins on the host exactly like the slab classes of
+  ``BinClasses``: out[cell, b1, b2] = sum_c acc[cell, c] M_1[b1, c] M_2[b2, c].
+  """
+  n_classes: int
+  bin_dims: list                 # one output dim per outer binning
+  bin_coords: dict               # bin dim -> labels
+  membership: list               # per binning: float64 [n_bins, n_classes]
+  dense_index: np.ndarray        # launch cell -> base_cell * n_classes + class
+  n_base_cells: int
+  job_order: np.ndarray          # permutation applied to the job tables
+  launch_cell: np.ndarray        # int32 cell of every job, in launch order
+  digest: str
+
+  def to_bins(self, per_cell: np.ndarray) -> np.ndarray:
+    """[n_launch_cells, ...] -> [n_base_cells, bins_1, ..., ...].
+
+    (cell, class) pairs without a job are zero; 0 * NaN keeps the reference's
+    behaviour that a NaN in any job of a cell poisons all its bins."""
+    rest = per_cell.shape[1:]
+    dense = np.zeros((self.n_base_cells * self.n_classes,) + rest)
+    dense[self.dense_index] = per_cell
+    dense = dense.reshape((self.n_base_cells, self.n_classes) + rest)
+    letters = 'bdefghij'
+    k = len(self.membership)
+    expr = 'ac...,' + ','.join(f'{letters[i]}c' for i in range(k))
+    expr += '->a' + letters[:k] + '...'
+    with np.errstate(invalid='ignore'):
+      return np.einsum(expr, dense, *self.membership)
+
+
+def _fold_outer_masks(masks, bin_dim_names, job_dims, job_sizes, base_cell
+                      ) -> OuterClasses:
+  """Outer classes of the jobs (row-major over ``job_dims``)."""
+  import hashlib  # pylint: disable=g-import-not-at-top
+  n_jobs = int(np.prod(job_sizes, dtype=np.int64)) if job_dims else 1
+  sizes = dict(zip(job_dims, job_sizes))
+  expanded, labels, digest = [], {}, hashlib.blake2b(digest_size=16)
+  for mask, bdim in zip(masks, bin_dim_names):
+    other = [d for d in mask.dims if d != bdim]
+    arr = mask.transpose(bdim, *[d for d in job_dims if d in other]).to_numpy()
+    arr = arr.astype(bool, copy=False)
+    view = [arr.shape[0]] + [sizes[d] if d in other else 1 for d in job_dims]
+    arr = np.broadcast_to(arr.reshape(view), [arr.shape[0]] + list(job_sizes))
+    arr = np.ascontiguousarray(arr).reshape(arr.shape[0], n_jobs)
+    expanded.append(arr)
+    digest.update(str(bdim).encode())
+    digest.update(arr.tobytes())
+    labels[bdim] = (mask.coords[bdim].to_numpy() if bdim in mask.coords
+                    else np.arange(arr.shape[0]))
+  stacked = np.concatenate(expanded, axis=0)               # [bins_total, jobs]
+  packed = np.ascontiguousarray(np.packbits(stacked, axis=0).T)
+  void = packed.view(np.dtype((np.void, packed.shape[1]))).reshape(-1)
+  _, first_pos, klass = np.unique(void, return_index=True, return_inverse=True)
+  n_classes = len(first_pos)
+  dense = base_cell.astype(np.int64) * n_classes + klass.reshape(-1)
+  order = np.argsort(dense, kind='stable')
+  dense_index, launch_cell = np.unique(dense[order], return_inverse=True)
+  return OuterClasses(
+      n_classes=n_classes, bin_dims=list(bin_dim_names), bin_coords=labels,
+      membership=[arr[:, first_pos].astype(np.float64) for arr in expanded],
+      dense_index=dense_index, n_base_cells=int(base_cell.max()) + 1,
+      job_order=order, launch_cell=launch_cell.reshape(-1).astype(np.int32),
+      digest=digest.hexdigest())
+
+
+@dataclasses.dataclass
 class FusedSpec:
   """Everything wbx_det_plan_create needs, plus how to label the results."""
   space: int
@@ -389,6 +463,8 @@ class FusedSpec:
   coords: dict
   keepalive: tuple
   cache_key: tuple
+  outer: 'OuterClasses | None' = None
+  bin_order: tuple = ()          # bin dims in the order of Aggregator.bin_by
 
 
 _SPEC_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
@@ -502,9 +578,17 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
 
   # ---- slab = trailing run of reduced dims present in every operand.
   operands = [pred, tgt] + ([mask_da] if mask_da is not None else [])
+  # Dims of bin masks that do not touch the grid (time units, level sets, ...)
+  # stay outside the slab even when they are reduced: such a mask is then folded
+  # into the job -> cell table instead of needing a per-point class map.
+  grid_dims = set(dims[-2:])
+  mask_dims = [set(m.dims) - {b} for m, b in zip(bin_masks, bin_dim_names)]
+  slab_bound = set().union(*[md for md in mask_dims if md & grid_dims])
+  keep_outer = set().union(*[md for md in mask_dims if not md & grid_dims]
+                           ) - slab_bound
   inner: list = []
   for d in reversed(dims):
-    if d not in reduce_set:
+    if d not in reduce_set or d in keep_outer:
       break
     trial = [d] + inner
     ok = all(tuple(o.dims[-len(trial):]) == tuple(trial) for o in operands)
@@ -615,22 +699,50 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
   for name, cv in first.coords.items():
     if name not in coords and name != 'mask' and set(cv.dims) <= set(kept):
       coords[name] = cv
+  # Bin masks over the slab dims become the class map of the binned kernel,
+  # bin masks over outer dims become extra output cells of the launch.
+  slab_bins, outer_bins = [], []
+  for bmask, bdim in zip(bin_masks, bin_dim_names):
+    other = set(bmask.dims) - {bdim}
+    if other <= set(inner):
+      slab_bins.append((bmask, bdim))
+    elif other <= set(job_dims):
+      outer_bins.append((bmask, bdim))
+    else:
+      raise FastPathUnavailable('bin mask spans slab and outer dims')
   classes = None
-  if bin_masks:
+  if slab_bins:
     if skipna or (ny * nx) % 16:
       raise FastPathUnavailable('binned slab kernel: unsupported combination')
-    classes = fold_bin_masks(bin_masks, bin_dim_names, inner, sizes)
+    classes = fold_bin_masks([m for m, _ in slab_bins],
+                             [d for _, d in slab_bins], inner, sizes)
     n_sel = bin(stat_mask).count('1') + (1 if op_m is not None else 0)
     if classes.n_classes * n_sel > 448:
       raise FastPathUnavailable('too many classes x statistics')
     cache_key = cache_key + ('bins', classes.digest)
-  return FusedSpec(
-      classes=classes,
-      space=space, flags=flags, ny=ny, nx=nx, n_cells=n_cells,
+  cell = np.repeat(np.arange(n_cells, dtype=np.int32), per_cell)
+  job_tables = dict(
       pred=addresses(op_p), target=addresses(op_t), clim=clim_addr,
       mask=addresses(op_m) if op_m is not None else None,
-      cell=np.repeat(np.arange(n_cells, dtype=np.int32), per_cell),
-      w_outer=_weight_vector(job_dims, sizes, per_dim),
+      w_outer=_weight_vector(job_dims, sizes, per_dim))
+  outer_classes = None
+  if outer_bins:
+    outer_classes = _fold_outer_masks(
+        [m for m, _ in outer_bins], [d for _, d in outer_bins], job_dims,
+        job_sizes, cell)
+    order = outer_classes.job_order
+    job_tables = {k: (None if v is None else np.ascontiguousarray(v[order]))
+                  for k, v in job_tables.items()}
+    # launch cells: the (kept cell, outer class) pairs that occur, in order
+    cell = outer_classes.launch_cell
+    n_cells = len(outer_classes.dense_index)
+    cache_key = cache_key + ('outer', outer_classes.digest)
+  return FusedSpec(
+      classes=classes, outer=outer_classes, bin_order=tuple(bin_dim_names),
+      space=space, flags=flags, ny=ny, nx=nx, n_cells=n_cells,
+      pred=job_tables['pred'], target=job_tables['target'],
+      clim=job_tables['clim'], mask=job_tables['mask'], cell=cell,
+      w_outer=job_tables['w_outer'],
       w_y=_weight_vector(y_dims, sizes, per_dim), w_x=per_dim.get(x_dim),
       scalar=scalar, stat_mask=stat_mask, kept=kept, kept_shape=[sizes[d] for d in kept],
       coords=coords,
@@ -747,28 +859,34 @@ def run_fused_specs(items, device: int | None = None):
   for idx, (spec, stats) in enumerate(items):
     ws, w = raw[idx]
     out = {}
-    cls = spec.classes
-    out_dims, out_shape, out_coords = spec.kept, spec.kept_shape, spec.coords
-    if cls is not None:
-      out_dims = list(spec.kept) + list(cls.bin_dims)
-      out_shape = list(spec.kept_shape) + [m.shape[0] for m in cls.membership]
-      out_coords = dict(spec.coords)
-      for bdim in cls.bin_dims:
-        out_coords[bdim] = cls.bin_coords[bdim]
+    cls, outer = spec.classes, spec.outer
+    out_dims, out_shape = list(spec.kept), list(spec.kept_shape)
+    out_coords = dict(spec.coords)
+    for folded in (outer, cls):    # layout: kept, outer bins, slab bins
+      if folded is not None:
+        out_dims += list(folded.bin_dims)
+        out_shape += [m.shape[0] for m in folded.membership]
+        for bdim in folded.bin_dims:
+          out_coords[bdim] = folded.bin_coords[bdim]
+    # the reference's result has the bin dims in the order of bin_by
+    final_dims = list(spec.kept) + [d for d in spec.bin_order
+                                    if d in out_dims]
     for s in stats:
       slot = _cabi.STAT_SLOT[s.kind]
-      col_ws = ws[:, slot] * spec.scalar
-      col_w = w[:, _cabi.STAT_WCLASS[slot]] * spec.scalar
-      if cls is not None:
-        with np.errstate(invalid='ignore'):
-          col_ws = cls.to_bins(col_ws.reshape(spec.n_cells, cls.n_classes))
-          col_w = cls.to_bins(col_w.reshape(spec.n_cells, cls.n_classes))
-      out[s.kind] = (
-          xl.DataArray(col_ws.reshape(out_shape), out_dims, coords=out_coords,
-                       name=s.name),
-          xl.DataArray(col_w.reshape(out_shape), out_dims, coords=out_coords,
-                       name=s.name),
-      )
+      pair = []
+      for col in (ws[:, slot] * spec.scalar,
+                  w[:, _cabi.STAT_WCLASS[slot]] * spec.scalar):
+        if cls is not None:
+          with np.errstate(invalid='ignore'):
+            col = cls.to_bins(col.reshape(spec.n_cells, cls.n_classes))
+        if outer is not None:
+          col = outer.to_bins(col.reshape((spec.n_cells,) + col.shape[1:]))
+        da = xl.DataArray(col.reshape(out_shape), out_dims, coords=out_coords,
+                          name=s.name)
+        if final_dims != out_dims:
+          da = da.transpose(*final_dims)
+        pair.append(da)
+      out[s.kind] = tuple(pair)
     results.append(out)
   return results
 

@@ -127,9 +127,11 @@ class DataArray:
   def _set_coord(self, key, value):
     if isinstance(value, DataArray):
       cv = DataArray(value._data, value.dims, name=key, attrs=value.attrs)
-    elif isinstance(value, tuple) and len(value) == 2 and not np.isscalar(
-        value[0]) and isinstance(value[0], (tuple, list, str)):
-      cdims, cdata = value
+    elif isinstance(value, tuple) and len(value) == 2 and (
+        isinstance(value[0], str) or (
+            isinstance(value[0], (tuple, list)) and
+            all(isinstance(d, str) for d in value[0]))):
+      cdims, cdata = value                    # (dims, data), dims a name or names
       cv = DataArray(cdata, cdims, name=key)
     else:
       arr = np.asarray(value)
@@ -366,6 +368,22 @@ class DataArray:
 
   drop = drop_vars
 
+  def isin(self, test_elements) -> 'DataArray':
+    self._require_host('isin')
+    return self._replace(data=np.isin(self._data, np.asarray(test_elements)))
+
+  @property
+  def dt(self):
+    """Datetime / timedelta field access (``valid_time.dt.dayofyear``,
+    base.py:398-401; ``lead_time.dt.total_seconds()``, binning.py:376-389)."""
+    kind = self.dtype.kind
+    if kind == 'M':
+      return DatetimeAccessor(self)
+    if kind == 'm':
+      return TimedeltaAccessor(self)
+    raise AttributeError(
+        f"'.dt' needs datetime64 or timedelta64 values, got {self.dtype}")
+
   def assign_coords(self, coords: Mapping | None = None, **kwargs):
     out = self._replace()
     for k, v in dict(coords or {}, **kwargs).items():
@@ -434,6 +452,8 @@ class DataArray:
   def __truediv__(self, o): return self._binary(o, _divide)
   def __rtruediv__(self, o): return self._binary(o, _divide, True)
   def __pow__(self, o): return self._binary(o, np.power)
+  def __floordiv__(self, o): return self._binary(o, np.floor_divide)
+  def __mod__(self, o): return self._binary(o, np.mod)
   def __and__(self, o): return self._binary(o, np.logical_and)
   def __or__(self, o): return self._binary(o, np.logical_or)
   def __lt__(self, o): return self._binary(o, np.less)
@@ -737,6 +757,65 @@ def concat(arrays: Sequence[DataArray], dim: str) -> DataArray:
   if labels is not None:
     out._coords[dim] = DataArray(labels, (dim,), name=dim)
   return out
+
+
+class DatetimeAccessor:
+  """The numeric calendar fields of a datetime64 array."""
+
+  FIELDS = ('year', 'month', 'day', 'hour', 'minute', 'second', 'dayofyear',
+            'dayofweek', 'weekday', 'quarter')
+
+  def __init__(self, arr: DataArray):
+    self._arr = arr
+
+  def __getattr__(self, unit):
+    if unit.startswith('_') or unit not in self.FIELDS:
+      raise AttributeError(unit)
+    t = self._arr.to_numpy().astype('datetime64[ns]')
+    years = t.astype('datetime64[Y]')
+    months = t.astype('datetime64[M]')
+    days = t.astype('datetime64[D]')
+
+    def since(coarse, fine_unit):
+      fine = t.astype(f'datetime64[{fine_unit}]')
+      return (fine - coarse.astype(f'datetime64[{fine_unit}]')).astype(np.int64)
+
+    month = months.astype(np.int64) % 12 + 1
+    values = {
+        'year': lambda: years.astype(np.int64) + 1970,
+        'month': lambda: month,
+        'day': lambda: since(months, 'D') + 1,
+        'hour': lambda: since(days, 'h'),
+        'minute': lambda: since(t.astype('datetime64[h]'), 'm'),
+        'second': lambda: since(t.astype('datetime64[m]'), 's'),
+        'dayofyear': lambda: since(years, 'D') + 1,
+        'dayofweek': lambda: (days.astype(np.int64) + 3) % 7,  # Monday = 0
+        'weekday': lambda: (days.astype(np.int64) + 3) % 7,
+        'quarter': lambda: (month - 1) // 3 + 1,
+    }[unit]()
+    return self._arr._replace(data=values)  # pylint: disable=protected-access
+
+
+class TimedeltaAccessor:
+  """total_seconds / days / seconds of a timedelta64 array."""
+
+  def __init__(self, arr: DataArray):
+    self._arr = arr
+
+  def _ns(self):
+    return self._arr.to_numpy().astype('timedelta64[ns]').astype(np.int64)
+
+  def total_seconds(self) -> DataArray:
+    return self._arr._replace(data=self._ns() / 1e9)  # pylint: disable=protected-access
+
+  @property
+  def days(self) -> DataArray:
+    return self._arr._replace(data=self._ns() // (86400 * 10**9))  # pylint: disable=protected-access
+
+  @property
+  def seconds(self) -> DataArray:
+    return self._arr._replace(  # pylint: disable=protected-access
+        data=(self._ns() // 10**9) % 86400)
 
 
 class Dataset(dict):
