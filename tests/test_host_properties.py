@@ -1,0 +1,199 @@
+"""Property tests of the host side against the oracle (no GPU).
+
+Random evaluation requests -- dim orders, reduce dims, weights, NaN modes, a
+mask on either input, grid bins, outer-dim bins, several variables -- go through
+the real class surface (statistics, Aggregator, planner, merged launches,
+result unpacking); the plans are executed by the NumPy interpreter of the plan
+contract (tests/wbx_emulator.py) instead of the CUDA library, and every
+AggregationState entry is compared with ``oracle.aggregate`` on the same
+arrays.  Requests the fused kernels cannot express fall back to the generic
+CUDA kernel, which needs a GPU: those draws are rejected here
+(``hypothesis.assume``) and are covered by the ``-m gpu`` tests.
+"""
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, assume, given, settings
+from hypothesis import strategies as st
+
+import wbx_emulator
+import wbx_oracle as oracle
+from weatherbenchx_b200 import aggregation
+from weatherbenchx_b200 import binning
+from weatherbenchx_b200 import generic
+from weatherbenchx_b200 import weighting
+from weatherbenchx_b200 import xarray_lite as xl
+from weatherbenchx_b200.metrics import base as metrics_base
+from weatherbenchx_b200.metrics import deterministic
+
+RTOL = 1e-5
+OUTER = ('init_time', 'lead_time', 'level')
+GRID = ('latitude', 'longitude')
+SIZES = {'init_time': 3, 'lead_time': 2, 'level': 2, 'latitude': 6,
+         'longitude': 8}
+COORDS = {
+    'init_time': np.datetime64('2020-02-28T00', 'ns') +
+                 np.arange(3) * np.timedelta64(12, 'h'),
+    'lead_time': (np.arange(2) * np.timedelta64(6, 'h')
+                  ).astype('timedelta64[ns]'),
+    'level': np.array([500, 850]),
+    'latitude': np.linspace(-75, 75, 6),
+    'longitude': np.arange(8) * 45.0,
+}
+REGIONS = {'all': ((-90, 90), (0, 360)), 'north': ((0, 90), (0, 360)),
+           'box': ((-50, 20), (300, 100))}
+
+
+class _GenericNeedsGpu(Exception):
+  pass
+
+
+@st.composite
+def requests(draw):
+  outer = list(draw(st.permutations(OUTER)))
+  outer = outer[:draw(st.integers(1, 3))]
+  grid = list(draw(st.permutations(GRID)))
+  dims = tuple(outer + grid)
+  reduce_outer = [d for d in outer if draw(st.booleans())]
+  reduce_dims = reduce_outer + list(GRID)
+  mode = draw(st.sampled_from(['propagate', 'masked', 'skipna',
+                               'masked_skipna']))
+  mask_on = draw(st.sampled_from(['targets', 'predictions', 'both']))
+  weighted = draw(st.booleans())
+  bins = draw(st.lists(st.sampled_from(
+      ['regions', 'regions_land', 'lat_bands', 'init_hour', 'lead_sets',
+       'level_sets']), max_size=2, unique=True))
+  n_vars = draw(st.integers(1, 2))
+  seed = draw(st.integers(0, 2**16))
+  with_acc = draw(st.booleans()) and {'init_time', 'lead_time'} <= set(dims)
+  return dict(dims=dims, reduce_dims=reduce_dims, mode=mode, mask_on=mask_on,
+              weighted=weighted, bins=bins, n_vars=n_vars, seed=seed,
+              with_acc=with_acc)
+
+
+def _make_bins(names, land):
+  out = []
+  for name in names:
+    if name == 'regions':
+      out.append(binning.Regions(REGIONS))
+    elif name == 'regions_land':
+      out.append(binning.Regions(REGIONS, bin_dim_name='region_l',
+                                 land_sea_mask=land))
+    elif name == 'lat_bands':
+      out.append(binning.LatitudeBins(60))
+    elif name == 'init_hour':
+      out.append(binning.ByTimeUnit('hour', 'init_time', add_global_bin=True))
+    elif name == 'lead_sets':
+      out.append(binning.ByTimeUnitSets({'zero': 0, 'any': [0, 6]}, 'hour',
+                                        'lead_time'))
+    elif name == 'level_sets':
+      out.append(binning.BySets({'low': [850]}, 'level',
+                                bin_dim_name='level_set',
+                                add_set_complements=True))
+  return out
+
+
+@settings(max_examples=300, deadline=None, derandomize=True,
+          suppress_health_check=[HealthCheck.filter_too_much,
+                                 HealthCheck.too_slow,
+                                 HealthCheck.function_scoped_fixture])
+@given(req=requests())
+def test_random_requests_match_the_oracle(req, monkeypatch):
+  wbx_emulator.installed(monkeypatch)
+
+  def no_generic(*args, **kwargs):
+    raise _GenericNeedsGpu()
+  monkeypatch.setattr(generic, 'aggregate', no_generic)
+
+  dims, rng = req['dims'], np.random.default_rng(req['seed'])
+  shape = tuple(SIZES[d] for d in dims)
+  coords = {d: COORDS[d] for d in dims}
+  for needed, bin_name in (('init_time', 'init_hour'),
+                           ('lead_time', 'lead_sets'),
+                           ('level', 'level_sets')):
+    assume(needed in dims or bin_name not in req['bins'])
+  masked, skipna = 'masked' in req['mode'], 'skipna' in req['mode']
+  land = xl.DataArray(rng.random((6, 8)) < 0.5, GRID,
+                      coords={d: COORDS[d] for d in GRID})
+  predictions, targets, arrays, climatology, clims = {}, {}, {}, {}, {}
+  clim_dims = ('dayofyear', 'hour') + tuple(
+      d for d in dims if d not in ('init_time', 'lead_time'))
+  for v in range(req['n_vars']):
+    if req['with_acc']:
+      c = rng.normal(size=(366, 4) + tuple(SIZES[d] for d in clim_dims[2:])
+                     ).astype(np.float32)
+      climatology[f'v{v}'] = xl.DataArray(
+          c, clim_dims, coords=dict(
+              {'dayofyear': np.arange(1, 367), 'hour': np.arange(0, 24, 6)},
+              **{d: COORDS[d] for d in clim_dims[2:]}), name=f'v{v}')
+      clims[f'v{v}'] = c
+    p = rng.normal(size=shape).astype(np.float32)
+    t = rng.normal(size=shape).astype(np.float32)
+    if req['mode'] != 'propagate':
+      t[rng.random(shape) < 0.1] = np.nan
+    mask = rng.random(shape) > 0.3
+    P = xl.DataArray(p, dims, coords=coords, name=f'v{v}')
+    T = xl.DataArray(t, dims, coords=coords, name=f'v{v}')
+    if masked and req['mask_on'] in ('predictions', 'both'):
+      P = P.assign_coords(mask=xl.DataArray(mask, dims))
+    if masked and req['mask_on'] in ('targets', 'both'):
+      T = T.assign_coords(mask=xl.DataArray(mask, dims))
+    predictions[f'v{v}'], targets[f'v{v}'] = P, T
+    arrays[f'v{v}'] = (p, t, mask)
+  metrics = {'rmse': deterministic.RMSE(), 'mae': deterministic.MAE(),
+             'bias': deterministic.Bias()}
+  if req['with_acc']:
+    metrics['acc'] = deterministic.ACC(climatology)
+  bin_by = _make_bins(req['bins'], land)
+  aggregator = aggregation.Aggregator(
+      reduce_dims=req['reduce_dims'],
+      weigh_by=[weighting.GridAreaWeighting()] if req['weighted'] else None,
+      bin_by=bin_by or None, masked=masked, skipna=skipna)
+  statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+      metrics, predictions, targets)
+  try:
+    state = aggregator.aggregate_statistics(statistics)
+  except _GenericNeedsGpu:
+    assume(False)
+
+  weights = []
+  if req['weighted']:
+    weights.append((oracle.grid_area_weights(COORDS['latitude']),
+                    ('latitude',)))
+  probe = predictions['v0']
+  bin_masks = []
+  for b in bin_by:
+    m = b.create_bin_mask(probe)
+    bin_masks.append((m.values, m.dims))
+  fields = {'SquaredError': oracle.squared_error,
+            'AbsoluteError': oracle.absolute_error, 'Error': oracle.error}
+  # which inputs a statistic's expression touches decides whether it carries
+  # the mask coordinate (deterministic.py:225-259, aggregation.py:339)
+  touches = {'SquaredPredictionAnomaly': {'predictions'},
+             'SquaredTargetAnomaly': {'targets'}}
+  for var, (p, t, mask) in arrays.items():
+    values = {name: fn(p, t) for name, fn in fields.items()}
+    if req['with_acc']:
+      aligned, adims = oracle.align_climatology(
+          clims[var], clim_dims,
+          {'dayofyear': np.arange(1, 367), 'hour': np.arange(0, 24, 6)},
+          COORDS['init_time'], COORDS['lead_time'])
+      aligned = np.transpose(aligned, [adims.index(d) for d in dims])
+      for name, fn in oracle.CLIMATOLOGY_STATISTICS.items():
+        values[name] = fn(p, t, aligned)
+    for name, value in values.items():
+      carries = masked and (
+          req['mask_on'] == 'both' or
+          req['mask_on'] in touches.get(name, {'predictions', 'targets'}))
+      sws, sw, out_dims = oracle.aggregate(
+          value, dims, req['reduce_dims'], weights=weights,
+          bin_masks=bin_masks, mask=mask if carries else None,
+          mask_dims=dims if carries else None, masked=carries, skipna=skipna)
+      got_ws = state.sum_weighted_statistics[name][var]
+      got_w = state.sum_weights[name][var]
+      assert tuple(got_ws.dims) == tuple(out_dims), (got_ws.dims, out_dims)
+      np.testing.assert_array_equal(np.isnan(got_ws.values), np.isnan(sws))
+      scale = np.abs(sws[np.isfinite(sws)]).max() if np.isfinite(sws).any() else 0
+      np.testing.assert_allclose(got_ws.values, sws, rtol=RTOL,
+                                 atol=RTOL * scale, equal_nan=True)
+      np.testing.assert_allclose(got_w.values, sw, rtol=1e-12, atol=1e-12)
