@@ -197,3 +197,132 @@ def test_random_requests_match_the_oracle(req, monkeypatch):
       np.testing.assert_allclose(got_ws.values, sws, rtol=RTOL,
                                  atol=RTOL * scale, equal_nan=True)
       np.testing.assert_allclose(got_w.values, sw, rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# ensemble statistics
+# ---------------------------------------------------------------------------
+
+
+@st.composite
+def ensemble_requests(draw):
+  outer = list(draw(st.permutations(('init_time', 'lead_time'))))
+  outer = outer[:draw(st.integers(1, 2))]
+  layout = draw(st.sampled_from(['member_last', 'member_major',
+                                 'member_first']))
+  reduce_outer = [d for d in outer if draw(st.booleans())]
+  return dict(
+      outer=outer, layout=layout, reduce_dims=reduce_outer + list(GRID),
+      members=draw(st.sampled_from([2, 3, 7, 10])),
+      mode=draw(st.sampled_from(['propagate', 'masked', 'skipna'])),
+      skipna_ensemble=draw(st.booleans()),
+      use_sort=draw(st.booleans()), fair=draw(st.booleans()),
+      weighted=draw(st.booleans()), n_vars=draw(st.integers(1, 2)),
+      seed=draw(st.integers(0, 2**16)))
+
+
+@settings(max_examples=200, deadline=None, derandomize=True,
+          suppress_health_check=[HealthCheck.filter_too_much,
+                                 HealthCheck.too_slow,
+                                 HealthCheck.function_scoped_fixture])
+@given(req=ensemble_requests())
+def test_random_ensemble_requests_match_the_oracle(req, monkeypatch):
+  from weatherbenchx_b200.metrics import probabilistic
+  wbx_emulator.installed(monkeypatch)
+
+  def no_generic(*args, **kwargs):
+    raise _GenericNeedsGpu()
+  monkeypatch.setattr(generic, 'aggregate', no_generic)
+  # the sort estimator rejects skipna_ensemble (probabilistic.py:215-216)
+  assume(not (req['use_sort'] and req['skipna_ensemble']))
+
+  rng = np.random.default_rng(req['seed'])
+  tdims = tuple(req['outer']) + GRID
+  m = req['members']
+  edims = {'member_last': tdims + ('realization',),
+           'member_major': tuple(req['outer']) + ('realization',) + GRID,
+           'member_first': ('realization',) + tdims}[req['layout']]
+  sizes = dict(SIZES, realization=m)
+  coords = dict(COORDS, realization=np.arange(m))
+  masked, skipna = req['mode'] == 'masked', req['mode'] == 'skipna'
+  predictions, targets, arrays = {}, {}, {}
+  for v in range(req['n_vars']):
+    y = rng.normal(size=tuple(sizes[d] for d in tdims)).astype(np.float32)
+    x = rng.normal(size=tuple(sizes[d] for d in edims)).astype(np.float32)
+    if req['skipna_ensemble']:
+      holes = rng.random(x.shape) < 0.2
+      axis = edims.index('realization')
+      keep = [slice(None)] * x.ndim
+      keep[axis] = slice(0, 2)        # at least two members everywhere
+      holes[tuple(keep)] = False
+      x[holes] = np.nan
+    if req['mode'] != 'propagate':
+      y[rng.random(y.shape) < 0.1] = np.nan
+    mask = rng.random(y.shape) > 0.3
+    X = xl.DataArray(x, edims, coords={d: coords[d] for d in edims},
+                     name=f'v{v}')
+    Y = xl.DataArray(y, tdims, coords={d: coords[d] for d in tdims},
+                     name=f'v{v}')
+    if masked:
+      Y = Y.assign_coords(mask=xl.DataArray(mask, tdims))
+    predictions[f'v{v}'], targets[f'v{v}'] = X, Y
+    arrays[f'v{v}'] = (x, y, mask)
+  kw = dict(ensemble_dim='realization', skipna_ensemble=req['skipna_ensemble'])
+  metrics = {
+      'crps': probabilistic.CRPSEnsemble(
+          use_sort=req['use_sort'], fair=req['fair'], **kw),
+      'ssr': probabilistic.UnbiasedSpreadSkillRatio(**kw)}
+  aggregator = aggregation.Aggregator(
+      reduce_dims=req['reduce_dims'],
+      weigh_by=[weighting.GridAreaWeighting()] if req['weighted'] else None,
+      masked=masked, skipna=skipna)
+  statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+      metrics, predictions, targets)
+  try:
+    state = aggregator.aggregate_statistics(statistics)
+  except _GenericNeedsGpu:
+    assume(False)
+
+  weights = []
+  if req['weighted']:
+    weights.append((oracle.grid_area_weights(COORDS['latitude']),
+                    ('latitude',)))
+  axis = edims.index('realization')
+  skip = req['skipna_ensemble']
+  fair = 'fair' if req['fair'] else 'unfair'
+  for var, (x, y, mask) in arrays.items():
+    # per-point fields in the statistic's dim order (ensemble dim dropped)
+    sdims = tuple(d for d in edims if d != 'realization')
+    y_s = np.transpose(y, [tdims.index(d) for d in sdims])
+    mask_s = np.transpose(mask, [tdims.index(d) for d in sdims])
+    expected = {
+        'CRPSSkill_realization': (oracle.crps_skill(x, y_s, axis, skip), True),
+        f'CRPSSpread_realization_{fair}_predictions': (
+            oracle.crps_spread(x, axis, fair=req['fair'],
+                               use_sort=req['use_sort'],
+                               skipna_ensemble=skip), False),
+        f'EnsembleVariance_realization_skipna_ensemble_{skip}': (
+            oracle.ensemble_variance(x, axis, skip), False),
+        f'UnbiasedEnsembleMeanSquaredError_realization_skipna_ensemble_{skip}':
+            (oracle.unbiased_ensemble_mean_squared_error(x, y_s, axis, skip),
+             True),
+    }
+    assert set(expected) == set(state.sum_weighted_statistics)
+    for name, (field, touches_targets) in expected.items():
+      carries = masked and touches_targets
+      sws, sw, out_dims = oracle.aggregate(
+          field, sdims, req['reduce_dims'], weights=weights,
+          mask=mask_s if carries else None,
+          mask_dims=sdims if carries else None, masked=carries, skipna=skipna)
+      got_ws = state.sum_weighted_statistics[name][var]
+      got_w = state.sum_weights[name][var]
+      assert set(got_ws.dims) == set(out_dims)
+      got_ws = got_ws.transpose(*out_dims).values
+      got_w = got_w.transpose(*out_dims).values
+      np.testing.assert_array_equal(np.isnan(got_ws), np.isnan(sws),
+                                    err_msg=name)
+      finite = np.abs(sws[np.isfinite(sws)])
+      np.testing.assert_allclose(
+          got_ws, sws, rtol=1e-4, equal_nan=True, err_msg=name,
+          atol=1e-4 * (finite.max() if finite.size else 0))
+      np.testing.assert_allclose(got_w, sw, rtol=1e-12, atol=1e-12)
