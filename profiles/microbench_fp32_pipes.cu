@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(1024, 1) bench(float* out, float a, float b,
     for (int c = 0; c < CHAINS; ++c) {
       if (OP == 0) x[c] = fmaf(x[c], a, b);                       // FFMA 3-reg
       if (OP == 1) x[c] = x[c] + a;                               // FADD
-      if (OP == 2) x[c] = fmaxf(x[c], a);                         // FMNMX
+      if (OP == 2) x[c] = fmaxf(x[c], x[(c + 1) % CHAINS]);       // FMNMX
       if (OP == 3) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;"    // FFMA2
                                 : "+l"(X[c]) : "l"(A), "l"(B));
       if (OP == 4) asm volatile("add.rn.f32x2 %0, %0, %1;"        // FADD2
