@@ -497,9 +497,8 @@ __device__ __forceinline__ void sort_network(float (&x)[MAXM]) {
 // Fixed-size networks for the operational ensemble sizes (sort_networks.inc,
 // generated by gen_sort_networks.py): odd-even merge sort on runs of arbitrary
 // length, 395 (n = 50) / 408 (n = 51) compare-exchanges against the 421 / 433
-// ptxas leaves of the 64-wire network with +inf pads; 367 for the 48 wires of
-// the hybrid estimator.  The sorted order sits in a fixed permutation of the
-// wires (WBX_SORT<n>_RANKS).
+// ptxas leaves of the 64-wire network with +inf pads.  The sorted order sits
+// in a fixed permutation of the wires (WBX_SORT<n>_RANKS).
 #include "sort_networks.inc"
 
 template <int MFIX>
@@ -528,7 +527,6 @@ struct FixedSort {
       return sp;                                                               \
     }                                                                          \
   };
-WBX_FIXED_SORT(48)
 WBX_FIXED_SORT(50)
 WBX_FIXED_SORT(51)
 #undef WBX_FIXED_SORT
@@ -636,20 +634,7 @@ __global__ void __launch_bounds__(kCrpsThreads)
       }
       const int n = ENS_SKIPNA ? (M - n_nan) : M;
       float sp = 0.f;
-      if constexpr (kCheapNan) {
-        // Hybrid estimator: the min/max pipe bounds this kernel while the FMA
-        // pipe idles, so only 48 members are sorted (367 exchanges instead of
-        // 395 / 408) and the remaining 2 / 3 enter through their pair sums
-        // sum_k |x_k - x_e| on the FMA pipe (97 / 147 pairs).
-        constexpr int kSorted = 48;
-        FixedSort<kSorted>::template sort<MAXM>(x);
-        sp = FixedSort<kSorted>::template moment<MAXM>(x, kSorted);
-#pragma unroll
-        for (int e = kSorted; e < MFIX; ++e) {
-#pragma unroll
-          for (int k = 0; k < e; ++k) sp += fabsf(x[k] - x[e]);
-        }
-      } else if constexpr (FixedSort<MFIX>::kAvailable) {
+      if constexpr (FixedSort<MFIX>::kAvailable) {
         FixedSort<MFIX>::template sort<MAXM>(x);
         sp = FixedSort<MFIX>::template moment<MAXM>(x, n);
       } else {
