@@ -448,3 +448,58 @@ def test_window_view_only_for_lattices():
   pos = 1 + 2 * np.arange(3)[:, None] + np.arange(4)[None, :]
   np.testing.assert_array_equal(array_loaders._window_view(cube, 1, pos),
                                 cube[:, pos])
+
+
+# ---------------------------------------------------------------------------
+# TimeChunks against the reference's own class (build container only)
+# ---------------------------------------------------------------------------
+
+_REF_TIME_CHUNKS = '/root/reference/weatherbenchX/time_chunks.py'
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_TIME_CHUNKS),
+                    reason='the reference tree is only present in the build '
+                           'container')
+@pytest.mark.parametrize('init_chunk,lead_chunk', [
+    (None, None), (1, None), (3, 2), (4, 1), (7, 5), (100, 100)])
+@pytest.mark.parametrize('lead_kind', ['exact', 'slice'])
+def test_time_chunks_equal_the_reference_class(init_chunk, lead_chunk,
+                                               lead_kind):
+  """time_chunks.py:37-202 is pure NumPy, so the reference class itself is
+  imported (from its file, not as a package) and iterated side by side."""
+  import importlib.util
+  spec = importlib.util.spec_from_file_location('_ref_time_chunks',
+                                                _REF_TIME_CHUNKS)
+  ref = importlib.util.module_from_spec(spec)
+  sys.dont_write_bytecode = True
+  spec.loader.exec_module(ref)
+  init_times = np.arange('2020-01-01T00', '2020-01-04T12',
+                         np.timedelta64(12, 'h'), dtype='datetime64[ns]')
+  if lead_kind == 'exact':
+    lead_times = np.arange(0, 30, 6, dtype='timedelta64[h]').astype(
+        'timedelta64[ns]')
+  else:
+    if lead_chunk is not None:
+      pytest.skip('a lead_time slice cannot be chunked')
+    lead_times = slice(np.timedelta64(0, 'h'), np.timedelta64(24, 'h'))
+  kwargs = dict(init_time_chunk_size=init_chunk,
+                lead_time_chunk_size=lead_chunk)
+  theirs = ref.TimeChunks(init_times, lead_times, **kwargs)
+  ours = time_chunks.TimeChunks(init_times, lead_times, **kwargs)
+  assert len(ours) == len(theirs)
+  for (i_a, l_a), (i_b, l_b) in zip(ours, theirs):
+    np.testing.assert_array_equal(i_a, i_b)
+    if isinstance(l_b, slice):
+      assert l_a == l_b
+    else:
+      np.testing.assert_array_equal(l_a, l_b)
+  for idx in range(len(theirs)):
+    a, b = ours[idx], theirs[idx]
+    np.testing.assert_array_equal(a[0], b[0])
+  if lead_kind == 'exact':
+    # (for a lead_time slice the reference's iter_with_chunk_offsets raises a
+    # TypeError of its own: None * int, time_chunks.py:200)
+    for (off_a, _), (off_b, _) in zip(ours.iter_with_chunk_offsets(),
+                                      theirs.iter_with_chunk_offsets()):
+      assert (off_a.init_time, off_a.lead_time) == (off_b.init_time,
+                                                    off_b.lead_time)
