@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define WBX_ABI_VERSION 1
+#define WBX_ABI_VERSION 2
 
 enum {
   WBX_OK = 0,
@@ -163,7 +163,51 @@ typedef struct {
                               n_classes * (#selected stats [+1 if MASKED]) <=
                               448, else WBX_ERR_UNSUPPORTED (use
                               wbx_reduce_generic).                            */
+  int32_t xform;           /* 0, or a WBX_XF_* request (see below): the slots
+                              of the launch then hold categorical statistics
+                              of the thresholded operands                     */
+  int32_t reserved;
+  const float* thr_pred;   /* [n_jobs] threshold of job j for the predictions
+                              (ERROR_EXCEEDANCE: for |pred - target|), or NULL
+                              with WBX_XF_PRED_NONZERO                        */
+  const float* thr_target; /* [n_jobs] threshold for the targets, or NULL with
+                              WBX_XF_TARGET_NONZERO / ERROR_EXCEEDANCE        */
 } wbx_det_desc;
+
+/* Categorical transform of the operands inside the fused reduction
+ * (wbx_det_desc.xform).  Replaces, without materialising any binary field:
+ *   wrappers.binarize_thresholds / ContinuousToBinary  metrics/wrappers.py:50-88,
+ *                                                      214-267
+ *   TruePositives / TrueNegatives / FalsePositives / FalseNegatives
+ *                                                      metrics/categorical.py:25-101
+ *   ErrorExceedance                                    metrics/deterministic.py:262-295
+ * WBX_XF_CONTINGENCY: bp = pred > thr_pred[j] (or pred != 0 with
+ *   WBX_XF_PRED_NONZERO: an input that is binary already, `.astype(bool)`),
+ *   bt likewise; slots 0..3 = TP, FP, FN, TN as 0/1 values, NaN where pred or
+ *   target is NaN (`.where(~isnan(predictions * targets))`).  A NaN threshold
+ *   compares false (NumPy `x > nan`).
+ * WBX_XF_ERROR_EXCEEDANCE: slot 0 = |pred - target| > thr_pred[j], NaN where
+ *   the error or the threshold is NaN.
+ * One threshold per job: a statistic with K thresholds is K jobs per slab, the
+ * threshold index being an ordinary (kept) outer dim of the job table.  All
+ * slots share one NaN pattern, so under SKIPNA sum_w[c*4 + k] is the same for
+ * every k.  Not available together with clim or class_map
+ * (WBX_ERR_UNSUPPORTED). */
+enum {
+  WBX_XF_CONTINGENCY = 1,
+  WBX_XF_ERROR_EXCEEDANCE = 2,
+  WBX_XF_PRED_NONZERO = 16,
+  WBX_XF_TARGET_NONZERO = 32
+};
+enum {
+  WBX_XF_TRUE_POSITIVES = 0,  /* 'TruePositives'   categorical.py:25-41    */
+  WBX_XF_FALSE_POSITIVES = 1, /* 'FalsePositives'  categorical.py:65-81    */
+  WBX_XF_FALSE_NEGATIVES = 2, /* 'FalseNegatives'  categorical.py:84-101   */
+  WBX_XF_TRUE_NEGATIVES = 3,  /* 'TrueNegatives'   categorical.py:45-62    */
+  WBX_XF_BINARIZED_PRED = 4,  /* wbx_xf_elementwise only: binarize_thresholds
+                                 of `pred` (wrappers.py:88)                  */
+  WBX_NUM_XF_STATS = 4
+};
 
 /* Upload the job tables once; the plan can then be run many times (the field
  * buffers it points at may be refilled between runs). */
@@ -200,6 +244,23 @@ enum {
 int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
                         const float* target, const float* clim, int64_t n,
                         float* out);
+
+/* Per-gridpoint values of a categorical statistic (the field a caller sees when
+ * it touches the result of TruePositives.compute(...) etc. directly, or the
+ * output of ContinuousToBinary.transform_fn): slot is a WBX_XF_* slot under the
+ * WBX_XF_* request `xform` with scalar thresholds; n contiguous float32 device
+ * elements; target may be NULL for WBX_XF_BINARIZED_PRED. */
+int wbx_xf_elementwise(wbx_ctx* ctx, int32_t xform, int32_t slot,
+                       float thr_pred, float thr_target, const float* pred,
+                       const float* target, int64_t n, float* out);
+
+/* sizeof / offsetof of the descriptor structs as this library was compiled:
+ * which = 0 wbx_det_desc, 1 wbx_crps_desc, 2 wbx_crps_point_desc,
+ * 3 wbx_spectrum_desc, 4 wbx_generic_desc.  Writes up to `cap` values to
+ * `out` -- out[0] = sizeof, out[1..] = offsetof every member in declaration
+ * order -- and returns the number of values (or WBX_ERR_INVALID).  Pure host
+ * code: lets a binding check its mirror of the structs without a GPU. */
+int wbx_struct_layout(int32_t which, uint64_t* out, int32_t cap);
 
 /* ---- ensemble CRPS statistics + weighted aggregation ------------------- *
  *

@@ -402,14 +402,22 @@ def test_library_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(lib, name), name
   lib.wbx_abi_version.restype = ctypes.c_int
-  assert lib.wbx_abi_version() == 1
+  assert lib.wbx_abi_version() == _cabi.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_sizes():
-  assert ctypes.sizeof(_cabi.DetDesc) == 8 + 4 * 8 + 8 * 8 + 8 + 8
-  assert ctypes.sizeof(_cabi.GenericDesc) == (
-      16 + 8 * 8 + 8 * 4 + 4 * (8 + 8 * 8) + 6 * 8 + 6 * 4 + 6 * 8 * 8 + 0
-      + (8 - (16 + 64 + 32 + 288 + 48 + 24) % 8) % 8)
+  """Every ctypes mirror has the size and member offsets the library was
+  compiled with (wbx_struct_layout: sizeof / offsetof from the C side)."""
+  mirrors = [_cabi.DetDesc, _cabi.CrpsDesc, _cabi.CrpsPointDesc,
+             _cabi.SpectrumDesc, _cabi.GenericDesc]
+  for which, mirror in enumerate(mirrors):
+    layout = _cabi.struct_layout(which)
+    assert layout[0] == ctypes.sizeof(mirror), mirror.__name__
+    offsets = [getattr(mirror, name).offset for name, _ in mirror._fields_]
+    assert layout[1:] == offsets, mirror.__name__
+  assert ctypes.sizeof(_cabi.DetDesc) == 8 + 4 * 8 + 8 * 8 + 8 + 8 + 8 + 16
+  with pytest.raises(_cabi.WbxError):
+    _cabi.struct_layout(99)
 
 
 def test_no_gpu_means_loud_failure():

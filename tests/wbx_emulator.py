@@ -31,6 +31,22 @@ def _read(addr, n, dtype):
   return np.frombuffer(buf, dtype=dtype, count=n)
 
 
+def _xf_values(xform, p, t, thr_p, thr_t):
+  """Slots of a categorical launch (wbx_b200.h, WBX_XF_*), float32 compares."""
+  nan = np.float32(np.nan)
+  if xform & 3 == _cabi.XF_CONTINGENCY:
+    bp = (p != 0) if xform & _cabi.XF_PRED_NONZERO else (p > np.float32(thr_p))
+    bt = (t != 0) if xform & _cabi.XF_TARGET_NONZERO else (t > np.float32(thr_t))
+    ok = ~(np.isnan(p) | np.isnan(t))
+    table = [bp & bt, bp & ~bt, ~bp & bt, ~bp & ~bt]
+    return [np.where(ok, v.astype(np.float32), nan) for v in table]
+  d = np.abs(p - t)
+  ok = ~np.isnan(d) & ~np.isnan(np.float32(thr_p))
+  ex = np.where(ok, (d > np.float32(thr_p)).astype(np.float32), nan)
+  zero = np.zeros_like(ex)
+  return [ex, zero, zero, zero]
+
+
 class _Context:
   device = 0
   handle = None
@@ -66,6 +82,12 @@ class DetPlan:
     wgt = (np.asarray(wy)[:, None] * np.asarray(wx)[None, :]).reshape(-1)
     skipna = bool(d['flags'] & _cabi.FLAG_SKIPNA)
     stat_mask = d.get('stat_mask') or 63
+    xform = int(d.get('xform') or 0)
+    thr_p, thr_t = d.get('thr_pred'), d.get('thr_target')
+    if xform:
+      if d.get('clim') is not None or self.n_classes:
+        raise RuntimeError('xform with clim / class_map: WBX_ERR_UNSUPPORTED')
+      stat_mask &= 15 if xform & 3 == _cabi.XF_CONTINGENCY else 1
     classes = (np.asarray(d['class_map']).reshape(-1).astype(np.int64)
                if self.n_classes else np.zeros(slab, np.int64))
     for j in range(len(d['pred'])):
@@ -79,6 +101,10 @@ class DetPlan:
       with np.errstate(invalid='ignore'):
         vals = [p - t, np.abs(p - t), (p - t) ** 2, (p - c) ** 2,
                 (t - c) ** 2, (p - c) * (t - c)]
+        if xform:
+          vals = _xf_values(xform, p, t,
+                            None if thr_p is None else thr_p[j],
+                            None if thr_t is None else thr_t[j])
       base = int(d['cell'][j]) * ncls
       done_w = set()
       for s, v in enumerate(vals):
@@ -88,11 +114,13 @@ class DetPlan:
         v64 = np.where(valid, v, 0).astype(np.float64) * wgt
         ws[base:base + ncls, s] += wo * np.bincount(
             classes, weights=v64, minlength=ncls)
-        k = _cabi.STAT_WCLASS[s]
+        k = 0 if xform else _cabi.STAT_WCLASS[s]
         if k not in done_w:
           done_w.add(k)
           w[base:base + ncls, k] += wo * np.bincount(
               classes, weights=valid * wgt, minlength=ncls)
+    if xform:  # one NaN pattern: every sum_weights class holds the same sum
+      w[:, 1:] = w[:, :1]
     return ws, w
 
   def close(self):

@@ -21,6 +21,7 @@ import numpy as np
 from weatherbenchx_b200 import _build
 
 WBX_OK = 0
+ABI_VERSION = 2
 SPACE_DEVICE, SPACE_HOST = 0, 1
 FLAG_SKIPNA, FLAG_MASKED, FLAG_FORCE_LDG, FLAG_FORCE_TMA = 1, 2, 16, 32
 FLAG_CLIM_DEVICE = 64
@@ -36,6 +37,27 @@ STAT_SLOT = {
 }
 # sum_weights class of each statistic slot (see wbx_b200.h).
 STAT_WCLASS = {0: 0, 1: 0, 2: 0, 3: 1, 4: 2, 5: 3}
+# Categorical transform of the operands (wbx_det_desc.xform, WBX_XF_*).
+XF_CONTINGENCY, XF_ERROR_EXCEEDANCE = 1, 2
+XF_PRED_NONZERO, XF_TARGET_NONZERO = 16, 32
+NUM_XF_STATS = 4
+XF_BINARIZED_PRED = 4
+# slot of each categorical statistic in an XF launch; every slot of such a
+# launch shares one NaN pattern, i.e. sum_weights class 0.
+XF_SLOT = {
+    'TruePositives': 0,
+    'FalsePositives': 1,
+    'FalseNegatives': 2,
+    'TrueNegatives': 3,
+    'ErrorExceedance': 0,
+}
+XF_REQUEST = {
+    'TruePositives': XF_CONTINGENCY,
+    'FalsePositives': XF_CONTINGENCY,
+    'FalseNegatives': XF_CONTINGENCY,
+    'TrueNegatives': XF_CONTINGENCY,
+    'ErrorExceedance': XF_ERROR_EXCEEDANCE,
+}
 
 _ERR_NAMES = {
     -1: 'WBX_ERR_INVALID', -2: 'WBX_ERR_CUDA', -3: 'WBX_ERR_NOMEM',
@@ -64,6 +86,9 @@ class DetDesc(ctypes.Structure):
       ('w_x', POINTER(c_double)),
       ('stat_mask', c_int32), ('n_classes', c_int32),
       ('class_map', POINTER(ctypes.c_uint8)),
+      ('xform', c_int32), ('reserved', c_int32),
+      ('thr_pred', POINTER(ctypes.c_float)),
+      ('thr_target', POINTER(ctypes.c_float)),
   ]
 
 
@@ -156,6 +181,10 @@ SIGNATURES = {
                                c_void_p]),
     'wbx_det_elementwise': (c_int, [c_void_p, c_int32, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_void_p]),
+    'wbx_xf_elementwise': (c_int, [c_void_p, c_int32, c_int32, ctypes.c_float,
+                                   ctypes.c_float, c_void_p, c_void_p, c_int64,
+                                   c_void_p]),
+    'wbx_struct_layout': (c_int, [c_int32, POINTER(c_uint64), c_int32]),
     'wbx_crps_plan_create': (c_int, [c_void_p, POINTER(CrpsDesc),
                                      POINTER(c_void_p)]),
     'wbx_crps_plan_destroy': (c_int, [c_void_p, c_void_p]),
@@ -200,8 +229,8 @@ def load_library():
       fn.restype = restype
       fn.argtypes = argtypes
     abi = lib.wbx_abi_version()
-    if abi != 1:
-      raise RuntimeError(f'libwbx_b200 ABI {abi} != 1')
+    if abi != ABI_VERSION:
+      raise RuntimeError(f'libwbx_b200 ABI {abi} != {ABI_VERSION}')
     _lib, _lib_pid = lib, os.getpid()
     _contexts.clear()
     return lib
@@ -315,7 +344,9 @@ class DetPlan:
                w_outer: np.ndarray | None = None,
                w_y: np.ndarray | None = None, w_x: np.ndarray | None = None,
                stat_mask: int = 0, class_map: np.ndarray | None = None,
-               n_classes: int = 0):
+               n_classes: int = 0, xform: int = 0,
+               thr_pred: np.ndarray | None = None,
+               thr_target: np.ndarray | None = None):
     self.ctx = ctx
     self.n_cells = int(n_cells)
     self.n_classes = int(n_classes)
@@ -333,11 +364,14 @@ class DetPlan:
     cell = prep(cell, np.int32)
     w_outer, w_y, w_x = (prep(w_outer, np.float64), prep(w_y, np.float64),
                          prep(w_x, np.float64))
+    thr_pred, thr_target = prep(thr_pred, np.float32), prep(thr_target,
+                                                            np.float32)
     n_jobs = len(pred)
     for name, arr, n in (('target', target, n_jobs), ('clim', clim, n_jobs),
                          ('mask', mask, n_jobs), ('cell', cell, n_jobs),
                          ('w_outer', w_outer, n_jobs), ('w_y', w_y, ny),
-                         ('w_x', w_x, nx)):
+                         ('w_x', w_x, nx), ('thr_pred', thr_pred, n_jobs),
+                         ('thr_target', thr_target, n_jobs)):
       if arr is not None and len(arr) != n:
         raise ValueError(f'{name} has {len(arr)} entries, expected {n}')
     desc = DetDesc(
@@ -348,7 +382,9 @@ class DetPlan:
         cell=_as_ptr(cell, c_int32), w_outer=_as_ptr(w_outer, c_double),
         w_y=_as_ptr(w_y, c_double), w_x=_as_ptr(w_x, c_double),
         stat_mask=stat_mask, n_classes=n_classes,
-        class_map=_as_ptr(prep(class_map, np.uint8), ctypes.c_uint8))
+        class_map=_as_ptr(prep(class_map, np.uint8), ctypes.c_uint8),
+        xform=xform, thr_pred=_as_ptr(thr_pred, ctypes.c_float),
+        thr_target=_as_ptr(thr_target, ctypes.c_float))
     handle = c_void_p()
     check(ctx.lib.wbx_det_plan_create(ctx.handle, ctypes.byref(desc),
                                       ctypes.byref(handle)))
@@ -388,6 +424,24 @@ def det_elementwise(ctx: Context, stat: int, pred_ptr: int, target_ptr: int,
   check(ctx.lib.wbx_det_elementwise(
       ctx.handle, stat, c_void_p(pred_ptr), c_void_p(target_ptr),
       c_void_p(clim_ptr or 0), n, c_void_p(out_ptr)))
+
+
+def xf_elementwise(ctx: Context, xform: int, slot: int, thr_pred: float,
+                   thr_target: float, pred_ptr: int, target_ptr: int | None,
+                   n: int, out_ptr: int):
+  check(ctx.lib.wbx_xf_elementwise(
+      ctx.handle, xform, slot, float(thr_pred), float(thr_target),
+      c_void_p(pred_ptr), c_void_p(target_ptr or 0), n, c_void_p(out_ptr)))
+
+
+def struct_layout(which: int) -> list:
+  """[sizeof, offsetof(member 0), ...] of descriptor struct `which` as the
+  loaded library was compiled (pure host code, works without a GPU)."""
+  buf = (c_uint64 * 64)()
+  n = load_library().wbx_struct_layout(which, buf, 64)
+  if n < 0:
+    check(n)
+  return [int(buf[i]) for i in range(n)]
 
 
 class CrpsPlan:

@@ -1,4 +1,5 @@
 // Context, error handling and pinned-memory helpers of libwbx_b200.
+#include <stddef.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -290,6 +291,111 @@ int wbx_host_unregister(void* ptr) {
   WBX_REQUIRE(ptr != nullptr, "wbx_host_unregister: ptr is NULL");
   WBX_CUDA(cudaHostUnregister(ptr));
   return WBX_OK;
+}
+
+// sizeof / offsetof of every descriptor struct, in declaration order.
+int wbx_struct_layout(int32_t which, uint64_t* out, int32_t cap) {
+  if (!out || cap < 1) {
+    wbx::set_error("wbx_struct_layout: NULL / empty output");
+    return WBX_ERR_INVALID;
+  }
+  int n = 0;
+#define WBX_PUT(v) do { if (n < cap) out[n] = (uint64_t)(v); ++n; } while (0)
+  switch (which) {
+    case 0:
+      WBX_PUT(sizeof(wbx_det_desc));
+      WBX_PUT(offsetof(wbx_det_desc, space));
+      WBX_PUT(offsetof(wbx_det_desc, flags));
+      WBX_PUT(offsetof(wbx_det_desc, n_jobs));
+      WBX_PUT(offsetof(wbx_det_desc, ny));
+      WBX_PUT(offsetof(wbx_det_desc, nx));
+      WBX_PUT(offsetof(wbx_det_desc, n_cells));
+      WBX_PUT(offsetof(wbx_det_desc, pred));
+      WBX_PUT(offsetof(wbx_det_desc, target));
+      WBX_PUT(offsetof(wbx_det_desc, clim));
+      WBX_PUT(offsetof(wbx_det_desc, mask));
+      WBX_PUT(offsetof(wbx_det_desc, cell));
+      WBX_PUT(offsetof(wbx_det_desc, w_outer));
+      WBX_PUT(offsetof(wbx_det_desc, w_y));
+      WBX_PUT(offsetof(wbx_det_desc, w_x));
+      WBX_PUT(offsetof(wbx_det_desc, stat_mask));
+      WBX_PUT(offsetof(wbx_det_desc, n_classes));
+      WBX_PUT(offsetof(wbx_det_desc, class_map));
+      WBX_PUT(offsetof(wbx_det_desc, xform));
+      WBX_PUT(offsetof(wbx_det_desc, reserved));
+      WBX_PUT(offsetof(wbx_det_desc, thr_pred));
+      WBX_PUT(offsetof(wbx_det_desc, thr_target));
+      break;
+    case 1:
+      WBX_PUT(sizeof(wbx_crps_desc));
+      WBX_PUT(offsetof(wbx_crps_desc, space));
+      WBX_PUT(offsetof(wbx_crps_desc, flags));
+      WBX_PUT(offsetof(wbx_crps_desc, n_jobs));
+      WBX_PUT(offsetof(wbx_crps_desc, ny));
+      WBX_PUT(offsetof(wbx_crps_desc, nx));
+      WBX_PUT(offsetof(wbx_crps_desc, n_members));
+      WBX_PUT(offsetof(wbx_crps_desc, member_stride));
+      WBX_PUT(offsetof(wbx_crps_desc, point_stride));
+      WBX_PUT(offsetof(wbx_crps_desc, n_cells));
+      WBX_PUT(offsetof(wbx_crps_desc, ens));
+      WBX_PUT(offsetof(wbx_crps_desc, target));
+      WBX_PUT(offsetof(wbx_crps_desc, mask));
+      WBX_PUT(offsetof(wbx_crps_desc, cell));
+      WBX_PUT(offsetof(wbx_crps_desc, w_outer));
+      WBX_PUT(offsetof(wbx_crps_desc, w_y));
+      WBX_PUT(offsetof(wbx_crps_desc, w_x));
+      WBX_PUT(offsetof(wbx_crps_desc, stat_mask));
+      WBX_PUT(offsetof(wbx_crps_desc, reserved));
+      break;
+    case 2:
+      WBX_PUT(sizeof(wbx_crps_point_desc));
+      WBX_PUT(offsetof(wbx_crps_point_desc, ndim));
+      WBX_PUT(offsetof(wbx_crps_point_desc, flags));
+      WBX_PUT(offsetof(wbx_crps_point_desc, n_members));
+      WBX_PUT(offsetof(wbx_crps_point_desc, member_stride));
+      WBX_PUT(offsetof(wbx_crps_point_desc, size));
+      WBX_PUT(offsetof(wbx_crps_point_desc, ens_stride));
+      WBX_PUT(offsetof(wbx_crps_point_desc, target_stride));
+      WBX_PUT(offsetof(wbx_crps_point_desc, ens));
+      WBX_PUT(offsetof(wbx_crps_point_desc, target));
+      WBX_PUT(offsetof(wbx_crps_point_desc, variance));
+      WBX_PUT(offsetof(wbx_crps_point_desc, unbiased_mse));
+      break;
+    case 3:
+      WBX_PUT(sizeof(wbx_spectrum_desc));
+      WBX_PUT(offsetof(wbx_spectrum_desc, n_jobs));
+      WBX_PUT(offsetof(wbx_spectrum_desc, ny));
+      WBX_PUT(offsetof(wbx_spectrum_desc, nx));
+      WBX_PUT(offsetof(wbx_spectrum_desc, field));
+      WBX_PUT(offsetof(wbx_spectrum_desc, row_scale));
+      WBX_PUT(offsetof(wbx_spectrum_desc, spectrum));
+      break;
+    case 4:
+      WBX_PUT(sizeof(wbx_generic_desc));
+      WBX_PUT(offsetof(wbx_generic_desc, ndim));
+      WBX_PUT(offsetof(wbx_generic_desc, op));
+      WBX_PUT(offsetof(wbx_generic_desc, flags));
+      WBX_PUT(offsetof(wbx_generic_desc, n_factors));
+      WBX_PUT(offsetof(wbx_generic_desc, size));
+      WBX_PUT(offsetof(wbx_generic_desc, reduced));
+      WBX_PUT(offsetof(wbx_generic_desc, a));
+      WBX_PUT(offsetof(wbx_generic_desc, a_stride));
+      WBX_PUT(offsetof(wbx_generic_desc, b));
+      WBX_PUT(offsetof(wbx_generic_desc, b_stride));
+      WBX_PUT(offsetof(wbx_generic_desc, c));
+      WBX_PUT(offsetof(wbx_generic_desc, c_stride));
+      WBX_PUT(offsetof(wbx_generic_desc, mask));
+      WBX_PUT(offsetof(wbx_generic_desc, mask_stride));
+      WBX_PUT(offsetof(wbx_generic_desc, factor));
+      WBX_PUT(offsetof(wbx_generic_desc, factor_dtype));
+      WBX_PUT(offsetof(wbx_generic_desc, factor_stride));
+      break;
+    default:
+      wbx::set_error("wbx_struct_layout: unknown struct %d", which);
+      return WBX_ERR_INVALID;
+  }
+#undef WBX_PUT
+  return n;
 }
 
 }  // extern "C"

@@ -39,6 +39,9 @@ struct wbx_det_plan {
   const double* d_wx = nullptr;
   std::vector<unsigned char> chunk_host[2];
   int stat_mask = 0x3f;
+  // categorical transform (wbx_det_desc.xform): per-job thresholds
+  int xform = 0;
+  std::vector<float> thr_pred, thr_target;
   // binned plans (class map over the slab)
   int n_classes = 0;
   wbx::DevBuf class_map;
@@ -49,14 +52,14 @@ struct wbx_det_plan {
 
 namespace wbx {
 
-template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM>
+template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM, bool XF = false>
 static int launch_variant(wbx_ctx* ctx, const wbx_det_plan* plan,
                           const DetParams& P, int grid) {
   cudaStream_t st = ctx->stream;
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
   if (plan->path == kPathTma) {
-    auto kern = det_reduce_tma_kernel<CLIM, MASK, SKIPNA, PER_ELEM>;
+    auto kern = det_reduce_tma_kernel<CLIM, MASK, SKIPNA, PER_ELEM, XF>;
     WBX_CUDA(cudaFuncSetAttribute(kern,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(plan->smem_bytes)));
@@ -77,10 +80,10 @@ static int launch_variant(wbx_ctx* ctx, const wbx_det_plan* plan,
     DetParams Pc = P;
     WBX_CUDA(cudaLaunchKernelEx(&cfg, kern, Pc, stages, stage_bytes));
   } else if (plan->path == kPathLdg4) {
-    det_reduce_ldg_kernel<CLIM, MASK, SKIPNA, PER_ELEM, 4>
+    det_reduce_ldg_kernel<CLIM, MASK, SKIPNA, PER_ELEM, 4, XF>
         <<<grid, kLdgThreads, 0, st>>>(P);
   } else {
-    det_reduce_ldg_kernel<CLIM, MASK, SKIPNA, true, 1>
+    det_reduce_ldg_kernel<CLIM, MASK, SKIPNA, true, 1, XF>
         <<<grid, kLdgThreads, 0, st>>>(P);
   }
   WBX_CUDA(cudaGetLastError());
@@ -120,9 +123,22 @@ static int launch_bins(wbx_ctx* ctx, const wbx_det_plan* plan,
 static int launch_main(wbx_ctx* ctx, const wbx_det_plan* plan,
                        const DetParams& P, int grid) {
   if (plan->n_classes > 0) return launch_bins(ctx, plan, P, grid);
-  const int key = (plan->has_clim ? 8 : 0) | (plan->has_mask ? 4 : 0) |
-                  (plan->skipna ? 2 : 0) | (plan->per_elem ? 1 : 0);
+  const int key = (plan->xform ? 16 : 0) | (plan->has_clim ? 8 : 0) |
+                  (plan->has_mask ? 4 : 0) | (plan->skipna ? 2 : 0) |
+                  (plan->per_elem ? 1 : 0);
   switch (key) {
+#define WBX_CASE_XF(K, B, C, D) \
+  case K:                       \
+    return launch_variant<false, B, C, D, true>(ctx, plan, P, grid);
+    WBX_CASE_XF(16, false, false, false)
+    WBX_CASE_XF(17, false, false, true)
+    WBX_CASE_XF(18, false, true, false)
+    WBX_CASE_XF(19, false, true, true)
+    WBX_CASE_XF(20, true, false, false)
+    WBX_CASE_XF(21, true, false, true)
+    WBX_CASE_XF(22, true, true, false)
+    WBX_CASE_XF(23, true, true, true)
+#undef WBX_CASE_XF
 #define WBX_CASE(K, A, B, C, D) \
   case K:                       \
     return launch_variant<A, B, C, D>(ctx, plan, P, grid);
@@ -156,6 +172,7 @@ static void fill_steps(const wbx_det_plan* plan, DetParams* P) {
   P->tile_dq = plan->tile / nx;
   P->tile_dr = plan->tile % nx;
   P->stat_mask = plan->stat_mask;
+  P->xf_kind = plan->xform;
 }
 
 static int grid_for(const wbx_ctx* ctx, const wbx_det_plan* plan,
@@ -326,12 +343,42 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     if (d->mask) WBX_REQUIRE(d->mask[j] != 0, "det: NULL mask slab address");
   }
 
+  if (d->xform != 0) {
+    const int kind = d->xform & 3;
+    WBX_REQUIRE((d->xform & ~(3 | WBX_XF_PRED_NONZERO | WBX_XF_TARGET_NONZERO)) == 0 &&
+                    (kind == WBX_XF_CONTINGENCY || kind == WBX_XF_ERROR_EXCEEDANCE),
+                "det: bad xform request %d", d->xform);
+    if (kind == WBX_XF_CONTINGENCY) {
+      WBX_REQUIRE(((d->xform & WBX_XF_PRED_NONZERO) != 0) == (d->thr_pred == nullptr),
+                  "det: xform needs thr_pred unless WBX_XF_PRED_NONZERO is set");
+      WBX_REQUIRE(((d->xform & WBX_XF_TARGET_NONZERO) != 0) ==
+                      (d->thr_target == nullptr),
+                  "det: xform needs thr_target unless WBX_XF_TARGET_NONZERO is "
+                  "set");
+    } else {
+      WBX_REQUIRE(d->xform == WBX_XF_ERROR_EXCEEDANCE && d->thr_pred != nullptr &&
+                      d->thr_target == nullptr,
+                  "det: error exceedance takes thr_pred only");
+    }
+    if (d->clim != nullptr || d->n_classes > 0) {
+      wbx::set_error("det: xform is not available with clim or class_map");
+      return WBX_ERR_UNSUPPORTED;
+    }
+  } else {
+    WBX_REQUIRE(d->thr_pred == nullptr && d->thr_target == nullptr,
+                "det: thresholds given without an xform request");
+  }
+
   wbx_det_plan* p = new (std::nothrow) wbx_det_plan();
   if (!p) {
     wbx::set_error("det: out of host memory");
     return WBX_ERR_NOMEM;
   }
   p->space = d->space;
+  p->xform = d->xform;
+  if (d->thr_pred) p->thr_pred.assign(d->thr_pred, d->thr_pred + d->n_jobs);
+  if (d->thr_target)
+    p->thr_target.assign(d->thr_target, d->thr_target + d->n_jobs);
   p->flags = d->flags;
   p->n_jobs = d->n_jobs;
   p->ny = d->ny;
@@ -365,11 +412,18 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
   }
   p->per_elem = p->has_wx || (d->nx % 4) != 0;
   p->stat_mask = d->stat_mask ? (d->stat_mask & 0x3f) : 0x3f;
-  if (!p->has_clim) p->stat_mask &= 0x7;
-  WBX_REQUIRE(p->stat_mask != 0,
-              "det: stat_mask selects only climatology statistics but clim is "
-              "NULL");
-  p->n_stats = p->has_clim ? 6 : 3;
+  if (p->xform) {
+    p->stat_mask &= (p->xform & 3) == WBX_XF_CONTINGENCY ? 0xf : 0x1;
+  } else if (!p->has_clim) {
+    p->stat_mask &= 0x7;
+  }
+  if (p->stat_mask == 0) {
+    delete p;
+    wbx::set_error("det: stat_mask selects no statistic this launch can "
+                   "evaluate (climatology statistics need clim)");
+    return WBX_ERR_INVALID;
+  }
+  p->n_stats = p->xform ? WBX_NUM_XF_STATS : (p->has_clim ? 6 : 3);
   p->n_weights = p->skipna ? (p->has_clim ? 4 : 1) : (p->has_mask ? 1 : 0);
   p->nacc = p->n_stats + p->n_weights;
   if (d->n_classes > 0) {
@@ -509,8 +563,14 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     const size_t o_cell = take(nj * 4);
     const size_t o_first = take(first.size() * 4);
     const size_t o_cw = take(cw.size() * 8);
+    const size_t o_thp = p->thr_pred.empty() ? 0 : take(nj * 4);
+    const size_t o_tht = p->thr_target.empty() ? 0 : take(nj * 4);
     std::vector<unsigned char>& host = p->chunk_host[0];
     host.assign(off, 0);
+    if (!p->thr_pred.empty())
+      memcpy(host.data() + o_thp, p->thr_pred.data(), nj * 4);
+    if (!p->thr_target.empty())
+      memcpy(host.data() + o_tht, p->thr_target.data(), nj * 4);
     memcpy(host.data() + o_pred, p->pred.data(), nj * 8);
     memcpy(host.data() + o_tgt, p->target.data(), nj * 8);
     if (p->has_clim) memcpy(host.data() + o_clim, p->clim.data(), nj * 8);
@@ -546,6 +606,12 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     P.tile = p->tile;
     P.tiles_per_slab = p->tiles_per_slab;
     P.records = nullptr;
+    P.thr_pred = p->thr_pred.empty()
+                     ? nullptr
+                     : reinterpret_cast<const float*>(base + o_thp);
+    P.thr_target = p->thr_target.empty()
+                       ? nullptr
+                       : reinterpret_cast<const float*>(base + o_tht);
     wbx::fill_steps(p, &P);
     p->d_cell_first_job = reinterpret_cast<const int32_t*>(base + o_first);
     p->d_cell_w = reinterpret_cast<const double*>(base + o_cw);
@@ -675,8 +741,14 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     const size_t o_cell = take(nj * 4);
     const size_t o_first = take(first.size() * 4);
     const size_t o_cw = take(cw.size() * 8);
+    const size_t o_thp = plan->thr_pred.empty() ? 0 : take(nj * 4);
+    const size_t o_tht = plan->thr_target.empty() ? 0 : take(nj * 4);
     std::vector<unsigned char>& host = plan->chunk_host[buf];
     host.assign(off, 0);
+    if (!plan->thr_pred.empty())
+      memcpy(host.data() + o_thp, plan->thr_pred.data() + j0, nj * 4);
+    if (!plan->thr_target.empty())
+      memcpy(host.data() + o_tht, plan->thr_target.data() + j0, nj * 4);
     uint64_t* h_pred = reinterpret_cast<uint64_t*>(host.data() + o_pred);
     uint64_t* h_tgt = reinterpret_cast<uint64_t*>(host.data() + o_tgt);
     uint64_t* h_clim = reinterpret_cast<uint64_t*>(host.data() + o_clim);
@@ -723,6 +795,12 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     P.slab = static_cast<int>(slab);
     P.tile = plan->tile;
     P.tiles_per_slab = plan->tiles_per_slab;
+    P.thr_pred = plan->thr_pred.empty()
+                     ? nullptr
+                     : reinterpret_cast<const float*>(tbase + o_thp);
+    P.thr_target = plan->thr_target.empty()
+                       ? nullptr
+                       : reinterpret_cast<const float*>(tbase + o_tht);
     wbx::fill_steps(plan, &P);
     const int grid = wbx::grid_for(ctx, plan, P.total_tiles);
     const int n_cells = static_cast<int>(first.size()) - 1;
@@ -827,6 +905,33 @@ int wbx_det_elementwise(wbx_ctx* ctx, int32_t stat, const float* pred,
       std::min<long long>(want, static_cast<long long>(ctx->sm_count) * 16));
   wbx::det_elementwise_kernel<<<grid, block, 0, ctx->stream>>>(
       stat, pred, target, clim, n, out);
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return WBX_OK;
+}
+
+int wbx_xf_elementwise(wbx_ctx* ctx, int32_t xform, int32_t slot,
+                       float thr_pred, float thr_target, const float* pred,
+                       const float* target, int64_t n, float* out) {
+  WBX_REQUIRE(ctx && pred && out, "wbx_xf_elementwise: NULL argument");
+  const int kind = xform & 3;
+  WBX_REQUIRE((xform & ~(3 | WBX_XF_PRED_NONZERO | WBX_XF_TARGET_NONZERO)) == 0 &&
+                  (kind == WBX_XF_CONTINGENCY || kind == WBX_XF_ERROR_EXCEEDANCE),
+              "wbx_xf_elementwise: bad xform request %d", xform);
+  WBX_REQUIRE(slot >= 0 && slot <= WBX_XF_BINARIZED_PRED &&
+                  (kind == WBX_XF_CONTINGENCY || slot == 0),
+              "wbx_xf_elementwise: bad slot %d", slot);
+  WBX_REQUIRE(target != nullptr || slot == WBX_XF_BINARIZED_PRED,
+              "wbx_xf_elementwise: slot %d needs the targets", slot);
+  WBX_REQUIRE(n >= 0, "wbx_xf_elementwise: negative n");
+  if (n == 0) return WBX_OK;
+  WBX_CUDA(cudaSetDevice(ctx->device));
+  const int block = 256;
+  const long long want = (n + block - 1) / block;
+  const int grid = static_cast<int>(
+      std::min<long long>(want, static_cast<long long>(ctx->sm_count) * 16));
+  wbx::xf_elementwise_kernel<<<grid, block, 0, ctx->stream>>>(
+      xform, slot, thr_pred, thr_target, pred, target, n, out);
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   return WBX_OK;

@@ -59,7 +59,25 @@ struct DetParams {
   int tile_dq, tile_dr;
   int stat_mask;       // bit s set => statistic slot s is wanted
   double* records;
+  // XF launches only (categorical transform of the operands, wbx_det_desc.xform)
+  const float* thr_pred;    // [n_jobs] or NULL
+  const float* thr_target;  // [n_jobs] or NULL
+  int xf_kind;              // WBX_XF_* request
 };
+
+// Thresholds of the job a thread is working on (XF launches).
+struct XfArgs {
+  float thr_p = 0.f, thr_t = 0.f;
+  int kind = 0;
+};
+
+__device__ __forceinline__ XfArgs xf_for_job(const DetParams& P, long long job) {
+  XfArgs xf;
+  xf.kind = P.xf_kind;
+  xf.thr_p = P.thr_pred ? __ldg(P.thr_pred + job) : 0.f;
+  xf.thr_t = P.thr_target ? __ldg(P.thr_target + job) : 0.f;
+  return xf;
+}
 
 struct StageMeta {
   int cell;
@@ -69,24 +87,70 @@ struct StageMeta {
   double wo;
 };
 
-template <bool CLIM, bool MASK, bool SKIPNA>
+template <bool CLIM, bool MASK, bool SKIPNA, bool XF = false>
 struct AccLayout {
-  static constexpr int kStats = CLIM ? 6 : 3;
+  static_assert(!(CLIM && XF), "XF launches take no climatology");
+  static constexpr int kStats = XF ? WBX_NUM_XF_STATS : (CLIM ? 6 : 3);
   static constexpr int kWeights = SKIPNA ? (CLIM ? 4 : 1) : (MASK ? 1 : 0);
   static constexpr int kAcc = kStats + kWeights;
 };
 
 // Statistic values of one grid point, f32, rounded after every operation
 // exactly like the NumPy ufunc chain of the reference.
-template <bool CLIM, bool MASK, bool SKIPNA>
+template <bool CLIM, bool MASK, bool SKIPNA, bool XF = false>
 struct PointStats {
-  float s[CLIM ? 6 : 3];
-  float valid[AccLayout<CLIM, MASK, SKIPNA>::kWeights > 0
-                  ? AccLayout<CLIM, MASK, SKIPNA>::kWeights
+  float s[AccLayout<CLIM, MASK, SKIPNA, XF>::kStats];
+  float valid[AccLayout<CLIM, MASK, SKIPNA, XF>::kWeights > 0
+                  ? AccLayout<CLIM, MASK, SKIPNA, XF>::kWeights
                   : 1];
 
+  // Categorical statistics of the thresholded operands (wbx_det_desc.xform):
+  // contingency table entries as 0/1 values (categorical.py:25-101 applied to
+  // wrappers.binarize_thresholds, wrappers.py:88) or the error exceedance
+  // indicator (deterministic.py:285-295); NaN inputs give NaN in every slot.
+  __device__ __forceinline__ void eval_xf(float p, float t, unsigned char m,
+                                          const XfArgs& xf) {
+    bool ok;
+    if ((xf.kind & 3) == WBX_XF_CONTINGENCY) {
+      const bool bp =
+          (xf.kind & WBX_XF_PRED_NONZERO) ? (p != 0.f) : (p > xf.thr_p);
+      const bool bt =
+          (xf.kind & WBX_XF_TARGET_NONZERO) ? (t != 0.f) : (t > xf.thr_t);
+      ok = (p == p) && (t == t);
+      s[WBX_XF_TRUE_POSITIVES] = (bp && bt) ? 1.f : 0.f;
+      s[WBX_XF_FALSE_POSITIVES] = (bp && !bt) ? 1.f : 0.f;
+      s[WBX_XF_FALSE_NEGATIVES] = (!bp && bt) ? 1.f : 0.f;
+      s[WBX_XF_TRUE_NEGATIVES] = (!bp && !bt) ? 1.f : 0.f;
+    } else {
+      const float d = fabsf(__fsub_rn(p, t));
+      ok = (d == d) && (xf.thr_p == xf.thr_p);
+      s[0] = (d > xf.thr_p) ? 1.f : 0.f;
+      s[1] = 0.f;
+      s[2] = 0.f;
+      s[3] = 0.f;
+    }
+    const bool base = MASK ? (m != 0) : true;
+    if constexpr (SKIPNA) {
+      const bool good = base && ok;
+#pragma unroll
+      for (int k = 0; k < WBX_NUM_XF_STATS; ++k) s[k] = good ? s[k] : 0.f;
+      valid[0] = good ? 1.f : 0.f;
+    } else {
+      const float fill = base ? __int_as_float(0x7fc00000) : 0.f;
+#pragma unroll
+      for (int k = 0; k < WBX_NUM_XF_STATS; ++k)
+        s[k] = (base && ok) ? s[k] : fill;
+      valid[0] = base ? 1.f : 0.f;
+    }
+  }
+
   __device__ __forceinline__ void eval(float p, float t, float c,
-                                       unsigned char m) {
+                                       unsigned char m,
+                                       const XfArgs& xf = XfArgs()) {
+    if constexpr (XF) {
+      eval_xf(p, t, m, xf);
+      return;
+    }
     const float d = __fsub_rn(p, t);
     s[0] = d;
     s[1] = fabsf(d);
@@ -129,17 +193,18 @@ struct PointStats {
 
 // Four consecutive points of one latitude row (weight w is row-uniform): sum
 // the four statistic values in f32, then one f64 FMA per statistic.
-template <bool CLIM, bool MASK, bool SKIPNA>
+template <bool CLIM, bool MASK, bool SKIPNA, bool XF = false>
 __device__ __forceinline__ void accum_row4(const float4 p, const float4 t,
                                            const float4 c, const uchar4 m,
                                            const double w, const int stat_mask,
-                                           double* acc) {
-  using L = AccLayout<CLIM, MASK, SKIPNA>;
-  PointStats<CLIM, MASK, SKIPNA> q0, q1, q2, q3;
-  q0.eval(p.x, t.x, c.x, m.x);
-  q1.eval(p.y, t.y, c.y, m.y);
-  q2.eval(p.z, t.z, c.z, m.z);
-  q3.eval(p.w, t.w, c.w, m.w);
+                                           double* acc,
+                                           const XfArgs& xf = XfArgs()) {
+  using L = AccLayout<CLIM, MASK, SKIPNA, XF>;
+  PointStats<CLIM, MASK, SKIPNA, XF> q0, q1, q2, q3;
+  q0.eval(p.x, t.x, c.x, m.x, xf);
+  q1.eval(p.y, t.y, c.y, m.y, xf);
+  q2.eval(p.z, t.z, c.z, m.z, xf);
+  q3.eval(p.w, t.w, c.w, m.w, xf);
 #pragma unroll
   for (int k = 0; k < L::kStats; ++k) {
     if (stat_mask & (1 << k)) {  // warp-uniform
@@ -159,19 +224,20 @@ __device__ __forceinline__ void accum_row4(const float4 p, const float4 t,
 // (w_x: the latitude axis is the fastest one, as in the lon-major WeatherBench
 // archives): the four column weights come in as two 16-byte loads, the
 // weighted 4-sum is taken in f64 and folded with the row weight by one FMA.
-template <bool CLIM, bool MASK, bool SKIPNA, bool ALIGNED>
+template <bool CLIM, bool MASK, bool SKIPNA, bool ALIGNED, bool XF = false>
 __device__ __forceinline__ void accum_row4_wx(const float4 p, const float4 t,
                                               const float4 c, const uchar4 m,
                                               const double wrow,
                                               const double* __restrict__ wx4,
                                               const int stat_mask,
-                                              double* acc) {
-  using L = AccLayout<CLIM, MASK, SKIPNA>;
-  PointStats<CLIM, MASK, SKIPNA> q0, q1, q2, q3;
-  q0.eval(p.x, t.x, c.x, m.x);
-  q1.eval(p.y, t.y, c.y, m.y);
-  q2.eval(p.z, t.z, c.z, m.z);
-  q3.eval(p.w, t.w, c.w, m.w);
+                                              double* acc,
+                                              const XfArgs& xf = XfArgs()) {
+  using L = AccLayout<CLIM, MASK, SKIPNA, XF>;
+  PointStats<CLIM, MASK, SKIPNA, XF> q0, q1, q2, q3;
+  q0.eval(p.x, t.x, c.x, m.x, xf);
+  q1.eval(p.y, t.y, c.y, m.y, xf);
+  q2.eval(p.z, t.z, c.z, m.z, xf);
+  q3.eval(p.w, t.w, c.w, m.w, xf);
   double2 wa, wb;
   if constexpr (ALIGNED) {
     wa = __ldg(reinterpret_cast<const double2*>(wx4));
@@ -200,13 +266,14 @@ __device__ __forceinline__ void accum_row4_wx(const float4 p, const float4 t,
   }
 }
 
-template <bool CLIM, bool MASK, bool SKIPNA>
+template <bool CLIM, bool MASK, bool SKIPNA, bool XF = false>
 __device__ __forceinline__ void accum_point(float p, float t, float c,
                                             unsigned char m, const double w,
-                                            const int stat_mask, double* acc) {
-  using L = AccLayout<CLIM, MASK, SKIPNA>;
-  PointStats<CLIM, MASK, SKIPNA> q;
-  q.eval(p, t, c, m);
+                                            const int stat_mask, double* acc,
+                                            const XfArgs& xf = XfArgs()) {
+  using L = AccLayout<CLIM, MASK, SKIPNA, XF>;
+  PointStats<CLIM, MASK, SKIPNA, XF> q;
+  q.eval(p, t, c, m, xf);
 #pragma unroll
   for (int k = 0; k < L::kStats; ++k)
     if (stat_mask & (1 << k)) acc[k] += static_cast<double>(q.s[k]) * w;
@@ -231,24 +298,27 @@ struct WeightCursor {
 
 // One float4 group starting at slab element e.  PER_ELEM handles w_x and rows
 // whose length is not a multiple of four (the group may straddle rows).
-template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM>
+template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM, bool XF = false>
 __device__ __forceinline__ void accum_group4(const float4 p, const float4 t,
                                              const float4 c, const uchar4 m,
                                              unsigned y, unsigned x, double wo,
                                              const WeightCursor& wc,
                                              const int stat_mask,
-                                             double* acc) {
+                                             double* acc,
+                                             const XfArgs& xf = XfArgs()) {
   if constexpr (!PER_ELEM) {
-    accum_row4<CLIM, MASK, SKIPNA>(p, t, c, m, wc.row(y, wo), stat_mask, acc);
+    accum_row4<CLIM, MASK, SKIPNA, XF>(p, t, c, m, wc.row(y, wo), stat_mask,
+                                       acc, xf);
   } else if (wc.wx4_ok) {
     // rows are a multiple of four long: the group stays in its row
-    accum_row4_wx<CLIM, MASK, SKIPNA, true>(p, t, c, m, wc.row(y, wo),
-                                            wc.wx + x, stat_mask, acc);
+    accum_row4_wx<CLIM, MASK, SKIPNA, true, XF>(p, t, c, m, wc.row(y, wo),
+                                                wc.wx + x, stat_mask, acc, xf);
   } else if (wc.wx != nullptr && x + 3u < static_cast<unsigned>(wc.nx)) {
     // odd row length (e.g. 721 latitudes): all but the groups that straddle
     // a row end still share one row weight
-    accum_row4_wx<CLIM, MASK, SKIPNA, false>(p, t, c, m, wc.row(y, wo),
-                                             wc.wx + x, stat_mask, acc);
+    accum_row4_wx<CLIM, MASK, SKIPNA, false, XF>(p, t, c, m, wc.row(y, wo),
+                                                 wc.wx + x, stat_mask, acc,
+                                                 xf);
   } else {
     const float pp[4] = {p.x, p.y, p.z, p.w};
     const float tt[4] = {t.x, t.y, t.z, t.w};
@@ -257,8 +327,9 @@ __device__ __forceinline__ void accum_group4(const float4 p, const float4 t,
     double wrow = wc.row(y, wo);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      accum_point<CLIM, MASK, SKIPNA>(pp[i], tt[i], cc[i], mm[i],
-                                      wrow * wc.col(x), stat_mask, acc);
+      accum_point<CLIM, MASK, SKIPNA, XF>(pp[i], tt[i], cc[i], mm[i],
+                                          wrow * wc.col(x), stat_mask, acc,
+                                          xf);
       if (++x == static_cast<unsigned>(wc.nx)) {
         x = 0;
         ++y;
@@ -282,11 +353,11 @@ __device__ __forceinline__ void flush_warp(double (&acc)[NACC], double* rec,
 // ---------------------------------------------------------------------------
 // TMA-ring kernel
 // ---------------------------------------------------------------------------
-template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM>
+template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM, bool XF = false>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     det_reduce_tma_kernel(const DetParams P, const int stages,
                           const int stage_bytes) {
-  using L = AccLayout<CLIM, MASK, SKIPNA>;
+  using L = AccLayout<CLIM, MASK, SKIPNA, XF>;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ring = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -350,6 +421,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         mt.len = len;
         mt.e0 = e0;
         mt.pad = 0;
+        if constexpr (XF) mt.pad = static_cast<int>(job);  // threshold lookup
         mt.wo = wo;
         meta[s] = mt;
         unsigned char* st = ring + (size_t)s * stage_bytes;
@@ -398,6 +470,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   for (long long g = t_begin; g < t_end; ++g) {
     mbar_wait(&full[s], ph);
     const StageMeta mt = meta[s];
+    XfArgs xf;
+    if constexpr (XF) xf = xf_for_job(P, mt.pad);
     if (mt.e0 == 0) {
       ty = y_first;
       tx = x_first;
@@ -438,8 +512,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       uchar4 mv = make_uchar4(1, 1, 1, 1);
       if constexpr (CLIM) cv = sc[j];
       if constexpr (MASK) mv = sm[j];
-      accum_group4<CLIM, MASK, SKIPNA, PER_ELEM>(pv, tv, cv, mv, gy, gx, mt.wo,
-                                                 wc, P.stat_mask, acc);
+      accum_group4<CLIM, MASK, SKIPNA, PER_ELEM, XF>(
+          pv, tv, cv, mv, gy, gx, mt.wo, wc, P.stat_mask, acc, xf);
       gy += P.group_dq;
       gx += P.group_dr;
       if (gx >= unx) {
@@ -466,10 +540,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 // LDG kernel: same accumulation, direct streaming loads.  VEC = 4 needs
 // 16-byte aligned slabs with slab % 4 == 0; VEC = 1 handles anything.
 // ---------------------------------------------------------------------------
-template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM, int VEC>
+template <bool CLIM, bool MASK, bool SKIPNA, bool PER_ELEM, int VEC,
+          bool XF = false>
 __global__ void __launch_bounds__(kLdgThreads)
     det_reduce_ldg_kernel(const DetParams P) {
-  using L = AccLayout<CLIM, MASK, SKIPNA>;
+  using L = AccLayout<CLIM, MASK, SKIPNA, XF>;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long t_begin =
@@ -496,6 +571,8 @@ __global__ void __launch_bounds__(kLdgThreads)
       ma = reinterpret_cast<const unsigned char*>(__ldg(P.mask + job));
     const int cell = __ldg(P.cell + job);
     const double wo = P.w_outer ? __ldg(P.w_outer + job) : 1.0;
+    XfArgs xf;
+    if constexpr (XF) xf = xf_for_job(P, job);
     if (cell != cur_cell) {
       if (cur_cell >= 0) {
         double* rec = P.records +
@@ -532,9 +609,10 @@ __global__ void __launch_bounds__(kLdgThreads)
             if constexpr (!MASK) mv[u] = make_uchar4(1, 1, 1, 1);
             const unsigned e = static_cast<unsigned>(e0 + 4 * j);
             const unsigned y = e / static_cast<unsigned>(P.nx);
-            accum_group4<CLIM, MASK, SKIPNA, PER_ELEM>(
+            accum_group4<CLIM, MASK, SKIPNA, PER_ELEM, XF>(
                 pv[u], tv[u], cv[u], mv[u], y,
-                e - y * static_cast<unsigned>(P.nx), wo, wc, P.stat_mask, acc);
+                e - y * static_cast<unsigned>(P.nx), wo, wc, P.stat_mask, acc,
+                xf);
           }
         }
       }
@@ -549,9 +627,9 @@ __global__ void __launch_bounds__(kLdgThreads)
         unsigned char mv = 1;
         if constexpr (CLIM) cv = ldg_stream_f1(ca + e);
         if constexpr (MASK) mv = __ldg(ma + e);
-        accum_point<CLIM, MASK, SKIPNA>(pv, tv, cv, mv,
-                                        wc.row(y, wo) * wc.col(x), P.stat_mask,
-                                        acc);
+        accum_point<CLIM, MASK, SKIPNA, XF>(pv, tv, cv, mv,
+                                            wc.row(y, wo) * wc.col(x),
+                                            P.stat_mask, acc, xf);
       }
     }
     if (++k == P.tiles_per_slab) {
@@ -1041,6 +1119,33 @@ __global__ void det_elementwise_kernel(const int stat_and_flags,
       }
     }
     out[i] = add ? __fadd_rn(out[i], r) : r;
+  }
+}
+
+// Per-gridpoint values of one categorical slot (scalar thresholds); the same
+// PointStats code as the fused reduction evaluates them.
+__global__ void xf_elementwise_kernel(const int xform, const int slot,
+                                      const float thr_p, const float thr_t,
+                                      const float* __restrict__ p,
+                                      const float* __restrict__ t,
+                                      const long long n, float* out) {
+  XfArgs xf;
+  xf.kind = xform;
+  xf.thr_p = thr_p;
+  xf.thr_t = thr_t;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+       i < n; i += stride) {
+    const float pv = p[i];
+    float r;
+    if (slot == WBX_XF_BINARIZED_PRED) {
+      r = (pv == pv) ? (pv > thr_p ? 1.f : 0.f) : __int_as_float(0x7fc00000);
+    } else {
+      PointStats<false, false, false, true> q;
+      q.eval(pv, t[i], 0.f, 1, xf);
+      r = q.s[slot];
+    }
+    out[i] = r;
   }
 }
 

@@ -465,6 +465,12 @@ class FusedSpec:
   cache_key: tuple
   outer: 'OuterClasses | None' = None
   bin_order: tuple = ()          # bin dims in the order of Aggregator.bin_by
+  # categorical launches (LazyCategoricalStatistic): WBX_XF_* request and the
+  # per-job thresholds; kept dims in the order the reference's result has them
+  xform: int = 0
+  thr_pred: np.ndarray | None = None
+  thr_target: np.ndarray | None = None
+  kept_order: tuple | None = None
 
 
 _SPEC_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
@@ -504,6 +510,7 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
   guards += [cv.data for cv in first.coords.values()]
   key = (tuple(s.kind for s in stats), tuple(reduce_dims), bool(masked),
          bool(skipna), flags_extra, device, tuple(bin_dim_names),
+         first.group_key()[0] if getattr(first, 'xform', 0) else None,
          first.dims, first.predictions.dims, first.targets.dims,
          tuple(first.coords), tuple(w.dims for w in weights),
          tuple(id(g) for g in guards))
@@ -531,18 +538,22 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
   # The statistic that carries the climatology (if any) defines the launch;
   # climatology-free statistics of the same operands ride along for free.
   first = stats[0]
-  dims = first.dims
+  # categorical statistics plan with the threshold dim first (an outer, kept
+  # dim of the job table); their operands are the continuous fields
+  xform = getattr(first, 'xform', 0)
+  dims = first.plan_dims if xform else first.dims
   sizes = first.sizes
   reduce_set = set(reduce_dims)
   if not reduce_set.issubset(dims):
     return None
+  slots = _cabi.XF_SLOT if xform else _cabi.STAT_SLOT
   for s in stats:
     same_ops = s.group_key()[:2] == first.group_key()[:2]
     same_clim = (s.climatology is None or
                  s.group_key()[2] == first.group_key()[2])
-    if not (same_ops and same_clim) or s.dims != dims:
+    if not (same_ops and same_clim) or s.dims != first.dims:
       raise ValueError('statistics in one fused group must share operands')
-    if s.kind not in _cabi.STAT_SLOT:
+    if s.kind not in slots or getattr(s, 'xform', 0) != xform:
       raise FastPathUnavailable(f'{s.kind} is not a fused statistic')
 
   def canonical(da, kind):
@@ -656,8 +667,9 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
 
   stat_mask = 0
   for s in stats:
-    stat_mask |= 1 << _cabi.STAT_SLOT[s.kind]
+    stat_mask |= 1 << slots[s.kind]
   cache_key = (
+      first.group_key()[0][:5] if xform else None,
       space, flags, stat_mask, tuple(dims), tuple(sizes[d] for d in dims), tuple(inner),
       tuple(sorted(reduce_set, key=str)),
       op_p.ptr, tuple(op_p.strides.items()), op_t.ptr,
@@ -712,7 +724,7 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
       raise FastPathUnavailable('bin mask spans slab and outer dims')
   classes = None
   if slab_bins:
-    if skipna or (ny * nx) % 16:
+    if skipna or (ny * nx) % 16 or xform:
       raise FastPathUnavailable('binned slab kernel: unsupported combination')
     classes = fold_bin_masks([m for m, _ in slab_bins],
                              [d for _, d in slab_bins], inner, sizes)
@@ -724,7 +736,16 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
   job_tables = dict(
       pred=addresses(op_p), target=addresses(op_t), clim=clim_addr,
       mask=addresses(op_m) if op_m is not None else None,
-      w_outer=_weight_vector(job_dims, sizes, per_dim))
+      w_outer=_weight_vector(job_dims, sizes, per_dim),
+      thr_pred=None, thr_target=None)
+  if xform and first.threshold_dim is not None:
+    # every job compares against the threshold of its index along the
+    # threshold dim (wbx_det_desc.thr_pred / thr_target)
+    k_of_job = _job_offsets(job_dims, job_sizes, {first.threshold_dim: 1})
+    for name in ('thr_pred', 'thr_target'):
+      values = getattr(first, name)
+      if values is not None:
+        job_tables[name] = np.ascontiguousarray(values[k_of_job], np.float32)
   outer_classes = None
   if outer_bins:
     outer_classes = _fold_outer_masks(
@@ -742,7 +763,10 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
       space=space, flags=flags, ny=ny, nx=nx, n_cells=n_cells,
       pred=job_tables['pred'], target=job_tables['target'],
       clim=job_tables['clim'], mask=job_tables['mask'], cell=cell,
-      w_outer=job_tables['w_outer'],
+      w_outer=job_tables['w_outer'], xform=xform,
+      thr_pred=job_tables['thr_pred'], thr_target=job_tables['thr_target'],
+      kept_order=(tuple(d for d in first.dims if d in kept) if xform
+                  else None),
       w_y=_weight_vector(y_dims, sizes, per_dim), w_x=per_dim.get(x_dim),
       scalar=scalar, stat_mask=stat_mask, kept=kept, kept_shape=[sizes[d] for d in kept],
       coords=coords,
@@ -778,10 +802,19 @@ def _derived_payloads(used, originals) -> tuple:
 def _merge_key(spec: FusedSpec):
   """Specs with the same key can share one launch (variables of equal grid)."""
   return (spec.space, spec.flags, spec.ny, spec.nx, spec.clim is None,
-          spec.mask is None,
+          spec.mask is None, spec.xform, spec.thr_pred is None,
+          spec.thr_target is None,
           None if spec.classes is None else spec.classes.digest,
           None if spec.w_y is None else spec.w_y.tobytes(),
           None if spec.w_x is None else spec.w_x.tobytes())
+
+
+def _xf_kwargs(xform, thr_pred, thr_target) -> dict:
+  """DetPlan arguments of a categorical launch (none for the usual ones, so
+  that the plan contract seen by older callers is unchanged)."""
+  if not xform:
+    return {}
+  return dict(xform=xform, thr_pred=thr_pred, thr_target=thr_target)
 
 
 def _cached_plan(ctx, key, factory):
@@ -816,7 +849,8 @@ def run_fused_specs(items, device: int | None = None):
           n_cells=f.n_cells, w_outer=f.w_outer, w_y=f.w_y, w_x=f.w_x,
           stat_mask=f.stat_mask,
           class_map=None if f.classes is None else f.classes.class_map,
-          n_classes=0 if f.classes is None else f.classes.n_classes)
+          n_classes=0 if f.classes is None else f.classes.n_classes,
+          **_xf_kwargs(f.xform, f.thr_pred, f.thr_target))
     else:
       key = ('merged',) + tuple(sp.cache_key for sp in specs)
       offsets = np.cumsum([0] + [sp.n_cells for sp in specs])
@@ -842,7 +876,8 @@ def run_fused_specs(items, device: int | None = None):
             n_cells=int(offsets[-1]), w_outer=w_outer, w_y=f.w_y, w_x=f.w_x,
             stat_mask=mask_bits,
             class_map=None if f.classes is None else f.classes.class_map,
-            n_classes=0 if f.classes is None else f.classes.n_classes)
+            n_classes=0 if f.classes is None else f.classes.n_classes,
+            **_xf_kwargs(f.xform, cat('thr_pred'), cat('thr_target')))
     plan = _cached_plan(ctx, key, factory)
     # Converted copies the plan addresses live as long as the plan is cached;
     # the caller's own arrays are not retained.
@@ -869,13 +904,16 @@ def run_fused_specs(items, device: int | None = None):
         for bdim in folded.bin_dims:
           out_coords[bdim] = folded.bin_coords[bdim]
     # the reference's result has the bin dims in the order of bin_by
-    final_dims = list(spec.kept) + [d for d in spec.bin_order
-                                    if d in out_dims]
+    final_dims = list(spec.kept_order or spec.kept) + [
+        d for d in spec.bin_order if d in out_dims]
     for s in stats:
-      slot = _cabi.STAT_SLOT[s.kind]
+      if spec.xform:
+        slot, wclass = _cabi.XF_SLOT[s.kind], 0
+      else:
+        slot = _cabi.STAT_SLOT[s.kind]
+        wclass = _cabi.STAT_WCLASS[slot]
       pair = []
-      for col in (ws[:, slot] * spec.scalar,
-                  w[:, _cabi.STAT_WCLASS[slot]] * spec.scalar):
+      for col in (ws[:, slot] * spec.scalar, w[:, wclass] * spec.scalar):
         if cls is not None:
           with np.errstate(invalid='ignore'):
             col = cls.to_bins(col.reshape(spec.n_cells, cls.n_classes))
@@ -924,10 +962,54 @@ def _broadcast_device(da: xl.DataArray, dims, sizes, device=None):
   return t.contiguous() if not t.is_contiguous() else t
 
 
+def materialize_binarized(lazy, device: int | None = None):
+  """``binarize_thresholds`` field [..., threshold] of a LazyBinarized handle
+  (wrappers.py:88), one elementwise launch per threshold."""
+  torch = _torch()
+  src = to_device(_normalise(lazy.source, 'field'), device)
+  x = src.data.contiguous()
+  n_thr = len(lazy.thresholds)
+  out = torch.empty((n_thr,) + tuple(x.shape), dtype=torch.float32,
+                    device=x.device)
+  ctx = _cabi.get_context(x.device.index)
+  ctx.use_torch_stream()
+  for k in range(n_thr):
+    _cabi.xf_elementwise(ctx, _cabi.XF_CONTINGENCY, _cabi.XF_BINARIZED_PRED,
+                         lazy.thresholds[k], 0.0, x.data_ptr(), None,
+                         x.numel(), out[k].data_ptr())
+  return out.movedim(0, -1)
+
+
+def materialize_categorical(stat, device: int | None = None):
+  """Per-point field of a LazyCategoricalStatistic in the dim order of
+  ``stat.dims`` (a view of a [threshold, ...] tensor)."""
+  torch = _torch()
+  base = [d for d in stat.dims if d != stat.threshold_dim]
+  sizes = stat.sizes
+  p = _broadcast_device(stat.predictions, base, sizes, device)
+  t = _broadcast_device(stat.targets, base, sizes, device)
+  n_thr = 1 if stat.threshold_dim is None else sizes[stat.threshold_dim]
+  out = torch.empty((n_thr,) + tuple(p.shape), dtype=torch.float32,
+                    device=p.device)
+  ctx = _cabi.get_context(p.device.index)
+  ctx.use_torch_stream()
+  for k in range(n_thr):
+    _cabi.xf_elementwise(
+        ctx, stat.xform, _cabi.XF_SLOT[stat.kind],
+        0.0 if stat.thr_pred is None else stat.thr_pred[k],
+        0.0 if stat.thr_target is None else stat.thr_target[k],
+        p.data_ptr(), t.data_ptr(), p.numel(), out[k].data_ptr())
+  if stat.threshold_dim is None:
+    return out[0]
+  return out.movedim(0, list(stat.dims).index(stat.threshold_dim))
+
+
 def materialize(stat: LazyStatistic, device: int | None = None):
   """Evaluates the statistic per grid point on the GPU; returns a CUDA tensor."""
   if stat.kind in CRPS_SLOT:
     return materialize_crps(stat, device)
+  if getattr(stat, 'xform', 0):
+    return materialize_categorical(stat, device)
   parts = getattr(stat, 'parts', None)
   if parts is not None:  # sum of statistics (WindVectorSquaredError)
     return materialize_sum(stat, device)

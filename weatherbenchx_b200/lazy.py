@@ -356,5 +356,182 @@ class LazyEnsembleStatistic(LazyStatistic):
     return self.predictions.sizes[self.ensemble_dim]
 
 
+def threshold_f32(thresholds) -> np.ndarray:
+  """float32 thresholds t' with ``x > t'`` == ``x > t`` for every float32 x.
+
+  The reference compares float32 fields with float64 thresholds (a Python list
+  turned into a DataArray, wrappers.py:85-88, deterministic.py:272-277); NumPy
+  promotes the field, so a threshold that is not a float32 number (0.1, 0.25
+  ...) must be rounded DOWN, not to nearest, for the float32 comparison in the
+  kernel to give the same answer at the boundary.  NaN stays NaN.
+  """
+  t64 = np.asarray(thresholds, dtype=np.float64)
+  with np.errstate(over='ignore', invalid='ignore'):
+    t32 = t64.astype(np.float32)
+    above = t32.astype(np.float64) > t64
+    t32 = np.where(above, np.nextafter(t32, np.float32(-np.inf)), t32)
+  return np.ascontiguousarray(t32, dtype=np.float32)
+
+
+class LazyBinarized(xl.DataArray):
+  """``binarize_thresholds(x, thresholds, threshold_dim)`` (wrappers.py:50-88)
+  as a handle: ``(x > threshold).where(~isnan(x)).astype(float32)`` with the
+  threshold dim appended.  The categorical statistics read ``source`` and the
+  thresholds and compare inside the fused reduction; nothing is written to
+  HBM unless a caller touches ``.data`` (then the elementwise kernel
+  materialises the [..., threshold] field).
+  """
+
+  def __init__(self, source: xl.DataArray, thresholds, threshold_dim):
+    source = xl.as_data_array(source)
+    labels = np.asarray(thresholds, dtype=np.float64).reshape(-1)
+    if threshold_dim in source.dims:
+      raise ValueError(
+          f'{threshold_dim!r} is already a dimension of the input')
+    self.source = source
+    self.threshold_dim = threshold_dim
+    self.threshold_labels = labels
+    self.thresholds = threshold_f32(labels)
+    self.dims = tuple(source.dims) + (threshold_dim,)
+    self._sizes = dict(source.sizes)
+    self._sizes[threshold_dim] = len(labels)
+    self.name = source.name
+    self.attrs = {}
+    coords = dict(source._coords)  # pylint: disable=protected-access
+    coords[threshold_dim] = xl.DataArray(labels, (threshold_dim,),
+                                         name=threshold_dim)
+    self._coords = coords
+    self._materialized = None
+
+  @property
+  def shape(self):
+    return tuple(self._sizes[d] for d in self.dims)
+
+  @property
+  def sizes(self):
+    return dict(self._sizes)
+
+  @property
+  def dtype(self):
+    return np.dtype(np.float32)
+
+  @property
+  def is_device(self) -> bool:
+    return True
+
+  @property
+  def is_lazy(self) -> bool:
+    return self._materialized is None
+
+  def __repr__(self):
+    return f'<LazyBinarized {self.name!r} {self.sizes}>'
+
+  @property
+  def _data(self):
+    if self._materialized is None:
+      from weatherbenchx_b200 import engine  # pylint: disable=g-import-not-at-top
+      self._materialized = engine.materialize_binarized(self)
+    return self._materialized
+
+  @_data.setter
+  def _data(self, value):
+    self._materialized = value
+
+  _replace = LazyStatistic._replace
+
+
+CONTINGENCY_KINDS = ('TruePositives', 'FalsePositives', 'FalseNegatives',
+                     'TrueNegatives')
+
+
+class LazyCategoricalStatistic(LazyStatistic):
+  """TruePositives / FalsePositives / FalseNegatives / TrueNegatives
+  (categorical.py:25-101) of inputs that are thresholded on the fly, and
+  ErrorExceedance (deterministic.py:262-295).
+
+  The operands the kernels read are the *continuous* fields: an input that came
+  through ``ContinuousToBinary`` (a LazyBinarized handle) contributes its
+  source and its thresholds, any other input is taken as binary already
+  (``.astype(bool)``: non-zero is True).  One launch evaluates the whole
+  contingency table of a variable for all thresholds; the threshold index is a
+  kept outer dim of the job table (``plan_dims`` puts it first so that the
+  grid dims stay the contiguous slab).
+  """
+
+  elementwise_of_operands = False
+
+  def __init__(self, kind: str, predictions: xl.DataArray,
+               targets: xl.DataArray, exceedance_thresholds=None,
+               exceedance_dim=None, exceedance_coord=None):
+    from weatherbenchx_b200 import _cabi  # pylint: disable=g-import-not-at-top
+    p_bin = predictions if (isinstance(predictions, LazyBinarized)
+                            and predictions.is_lazy) else None
+    t_bin = targets if (isinstance(targets, LazyBinarized)
+                        and targets.is_lazy) else None
+    p_src = p_bin.source if p_bin is not None else predictions
+    t_src = t_bin.source if t_bin is not None else targets
+    super().__init__(kind, p_src, t_src)
+    self.thr_pred = self.thr_target = None
+    thr_dim = labels = thr_coord = None
+    if kind == 'ErrorExceedance':
+      self.xform = _cabi.XF_ERROR_EXCEEDANCE
+      if p_bin is not None or t_bin is not None:
+        raise NotImplementedError('ErrorExceedance of thresholded inputs')
+      thr_dim = exceedance_dim
+      labels = np.asarray(exceedance_thresholds, dtype=np.float64).reshape(-1)
+      thr_coord = exceedance_coord
+      self.thr_pred = threshold_f32(labels)
+    else:
+      if kind not in CONTINGENCY_KINDS:
+        raise ValueError(f'unknown categorical statistic {kind!r}')
+      self.xform = _cabi.XF_CONTINGENCY
+      if p_bin is not None and t_bin is not None and (
+          p_bin.threshold_dim != t_bin.threshold_dim or
+          not np.array_equal(p_bin.threshold_labels, t_bin.threshold_labels,
+                             equal_nan=True)):
+        raise NotImplementedError(
+            'predictions and targets thresholded along different dims / '
+            'with different values')
+      for which, b in (('pred', p_bin), ('target', t_bin)):
+        if b is None:
+          self.xform |= (_cabi.XF_PRED_NONZERO if which == 'pred'
+                         else _cabi.XF_TARGET_NONZERO)
+        else:
+          thr_dim, labels = b.threshold_dim, b.threshold_labels
+          thr_coord = b._coords.get(thr_dim)  # pylint: disable=protected-access
+          setattr(self, f'thr_{which}', b.thresholds)
+    self.threshold_dim = thr_dim
+    base_dims = self.dims
+    if thr_dim is not None:
+      if thr_dim in base_dims:
+        raise ValueError(f'{thr_dim!r} is already a dimension of the inputs')
+      # dims as xarray broadcasting orders them (wrappers.py:88,
+      # categorical.py:37-41, deterministic.py:290)
+      if kind != 'ErrorExceedance' and p_bin is not None:
+        n_p = len(p_src.dims)
+        self.dims = base_dims[:n_p] + (thr_dim,) + base_dims[n_p:]
+      else:
+        self.dims = base_dims + (thr_dim,)
+      self._sizes[thr_dim] = len(labels)
+      self._sizes = {d: self._sizes[d] for d in self.dims}
+      self._coords = dict(self._coords)
+      if thr_coord is not None:
+        self._coords[thr_dim] = xl.DataArray(
+            thr_coord.to_numpy(), (thr_dim,), name=thr_dim)
+      self.plan_dims = (thr_dim,) + base_dims
+    else:
+      self.plan_dims = base_dims
+
+  def group_key(self):
+    def key(a):
+      return None if a is None else a.tobytes()
+    return (('xf', self.xform, self.threshold_dim, key(self.thr_pred),
+             key(self.thr_target), id(self.predictions)),
+            id(self.targets), None)
+
+  def __repr__(self):
+    return f'<LazyCategoricalStatistic {self.kind} {self.name!r} {self.sizes}>'
+
+
 def statistic_names(stats: Sequence[LazyStatistic]) -> list:
   return [s.kind for s in stats]

@@ -7,8 +7,8 @@ AbsoluteError :103-112, SquaredError :115-123, SquaredPredictionAnomaly
 aliases Bias / MAE / MSE :305-307, RMSE :312-324, ACC :374-400 and
 PredictionActivity :403-425, plus PredictionPassthrough / TargetPassthrough
 :126-171 (aliases PredictionAverage / TargetAverage :308-309),
-WindVectorSquaredError :174-219 and WindVectorRMSE :327-371.  unique_name of
-every statistic follows the reference.
+WindVectorSquaredError :174-219, WindVectorRMSE :327-371 and ErrorExceedance
+:262-295.  unique_name of every statistic follows the reference.
 """
 
 from __future__ import annotations
@@ -118,6 +118,41 @@ class SquaredTargetAnomaly(_FusedClimatologyStatistic):
 
 class AnomalyCovariance(_FusedClimatologyStatistic):
   """(predictions - climatology) * (targets - climatology)."""
+
+
+class ErrorExceedance(base.PerVariableStatistic):
+  """``abs(predictions - targets) > threshold`` as 0/1 for every threshold, NaN
+  where the error or the threshold is NaN (deterministic.py:262-295).
+
+  ``thresholds``: a sequence of numbers (dim ``error_exceedance_thresholds``),
+  a 1-d DataArray or a Dataset of those keyed by variable name.  The
+  comparison happens inside the fused reduction; the threshold index is an
+  outer dim of the launch.
+  """
+
+  def __init__(self, thresholds):
+    if isinstance(thresholds, (list, tuple)):
+      thresholds = xl.DataArray(
+          np.asarray(thresholds, dtype=np.float64),
+          dims='error_exceedance_thresholds',
+          coords={'error_exceedance_thresholds': thresholds})
+    self._thresholds = thresholds
+
+  def _compute_per_variable(self, predictions, targets):
+    from weatherbenchx_b200.lazy import LazyCategoricalStatistic  # pylint: disable=g-import-not-at-top
+    thresholds = self._thresholds
+    if isinstance(thresholds, xl.Dataset):
+      thresholds = thresholds[xl.as_data_array(predictions).name]
+    thresholds = xl.as_data_array(thresholds)
+    if thresholds.ndim != 1:
+      raise NotImplementedError(
+          'error exceedance thresholds must be one-dimensional on the B200 '
+          f'hot path (got dims {thresholds.dims})')
+    dim = thresholds.dims[0]
+    return LazyCategoricalStatistic(
+        'ErrorExceedance', predictions, targets,
+        exceedance_thresholds=thresholds.to_numpy(), exceedance_dim=dim,
+        exceedance_coord=thresholds.coords.get(dim))
 
 
 Bias = Error

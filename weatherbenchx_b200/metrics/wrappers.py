@@ -12,8 +12,10 @@ ensemble-mean RMSE / bias / ACC are ``WrappedMetric(metric,
 [EnsembleMean('predictions')])``.  Its mean field comes from the
 ``wbx_ensemble_mean`` kernel (one HBM pass over the ensemble) and is memoised
 per input array, so all wrapped statistics of one variable see the SAME mean
-array and the Aggregator fuses them into one launch.  The thresholding /
-binning / quantile transforms of the reference are not part of this path.
+array and the Aggregator fuses them into one launch.  ``ContinuousToBinary`` /
+``binarize_thresholds`` (:50-88, :214-267) return lazy handles that the
+categorical statistics threshold inside the fused reduction.  The binning /
+quantile transforms of the reference are not part of this path.
 """
 
 from __future__ import annotations
@@ -64,6 +66,75 @@ class EnsembleMean(InputTransform):
     if self._ensemble_dim not in da.dims and self._skip_if_ensemble_dim_missing:
       return da
     return engine.ensemble_mean(da, self._ensemble_dim, skipna=self._skipna)
+
+
+def binarize_thresholds(x: xl.DataArray, thresholds, threshold_dim: str):
+  """``(x > threshold).where(~isnan(x)).astype(float32)`` with the thresholds
+  along a new trailing dim (wrappers.py:50-88), as a lazy handle.
+
+  ``thresholds``: an iterable of numbers, a 1-d DataArray along
+  ``threshold_dim`` or a Dataset of those keyed by variable name.  Thresholds
+  that vary over other dims (per grid point / per time) are not part of the
+  fused path.
+  """
+  from weatherbenchx_b200.lazy import LazyBinarized  # pylint: disable=g-import-not-at-top
+  x = xl.as_data_array(x)
+  if isinstance(thresholds, xl.Dataset):
+    assert x.name in thresholds, (
+        f'Input DataArray name ({x.name}) not found in thresholds')
+    thresholds = thresholds[x.name]
+  if isinstance(thresholds, xl.DataArray):
+    assert threshold_dim in thresholds.dims, (
+        f'threshold_dim ({threshold_dim}) not found in thresholds'
+        f' ({thresholds.dims})')
+    if thresholds.dims != (threshold_dim,):
+      raise NotImplementedError(
+          'thresholds that vary along dims other than the threshold dim '
+          f'({thresholds.dims}) are outside the B200 hot path')
+    labels = thresholds.coords[threshold_dim].to_numpy() if (
+        threshold_dim in thresholds.coords) else None
+    out = LazyBinarized(x, thresholds.to_numpy(), threshold_dim)
+    if labels is not None:  # the dim keeps the labels of the threshold array
+      out._coords[threshold_dim] = xl.DataArray(  # pylint: disable=protected-access
+          labels, (threshold_dim,), name=threshold_dim)
+    else:
+      del out._coords[threshold_dim]  # pylint: disable=protected-access
+    return out
+  return LazyBinarized(x, list(thresholds), threshold_dim)
+
+
+class ContinuousToBinary(InputTransform):
+  """``x > threshold`` for every threshold, along a new dim ``threshold_dim``
+  (wrappers.py:214-267).  Returns a handle: the categorical statistics compare
+  inside the fused reduction, so no binary field is stored."""
+
+  def __init__(self, which: str, threshold_value, threshold_dim: str,
+               unique_name_suffix: str | None = None):
+    super().__init__(which)
+    import collections.abc  # pylint: disable=g-import-not-at-top
+    self._threshold_value = (
+        threshold_value
+        if isinstance(threshold_value, (collections.abc.Iterable,
+                                        xl.DataArray, xl.Dataset))
+        else [threshold_value])
+    self._threshold_dim = threshold_dim
+    if isinstance(self._threshold_value, (xl.DataArray, xl.Dataset)):
+      if unique_name_suffix is None:
+        raise ValueError(
+            'unique_name_suffix must be provided if threshold_value is an'
+            ' xarray.DataArray or xarray.Dataset.')
+    self._unique_name_suffix = unique_name_suffix
+
+  @property
+  def unique_name_suffix(self) -> str:
+    if self._unique_name_suffix is None:
+      suffix = ','.join([str(t) for t in self._threshold_value])
+    else:
+      suffix = self._unique_name_suffix
+    return f'{self._threshold_dim}={suffix}'
+
+  def transform_fn(self, da: xl.DataArray) -> xl.DataArray:
+    return binarize_thresholds(da, self._threshold_value, self._threshold_dim)
 
 
 class Rename(InputTransform):

@@ -476,6 +476,10 @@ class DataArray:
     self._require_host('abs')
     return self._replace(data=np.abs(self._data))
 
+  def clip(self, min=None, max=None):  # pylint: disable=redefined-builtin
+    self._require_host('clip')
+    return self._replace(data=np.clip(self._data, min, max))
+
   def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
     if method != '__call__' or kwargs.get('out') is not None:
       return NotImplemented
