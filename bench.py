@@ -516,6 +516,55 @@ def run_suite(ctx, dev, peak):
                    'algorithmic_bytes_per_point': bpp}}
   del f, field, step
   torch.cuda.empty_cache()
+
+  # ---- thresholded contingency table (CSI / ETS / ...; categorical.py,
+  # wrappers.ContinuousToBinary): 3 thresholds, 0.25 deg.  Added after the last
+  # GPU session of round 1, so a failure here must not take the line down.
+  try:
+    from weatherbenchx_b200.metrics import categorical, wrappers
+    n_var, n_init, thresholds = 2, 20, [0.1, 1.0, 5.0]
+    dims = ('init_time', 'latitude', 'longitude')
+    coords = {'init_time': np.arange(n_init), 'latitude': lat,
+              'longitude': np.linspace(0, 360, NLON, endpoint=False)}
+    preds, tgts = {}, {}
+    for v in range(n_var):
+      t = torch.empty((n_init, NLAT, NLON), device=dev)
+      t.exponential_(0.5, generator=gen)
+      p = (t + torch.empty_like(t).normal_(0.0, 1.0, generator=gen)).clamp_(0)
+      preds[f'rain{v}'] = xl.DataArray(p, dims, coords=coords, name=f'rain{v}')
+      tgts[f'rain{v}'] = xl.DataArray(t, dims, coords=coords, name=f'rain{v}')
+    both = [wrappers.ContinuousToBinary('both', thresholds, 'threshold')]
+    metrics = {'csi': wrappers.WrappedMetric(categorical.CSI(), both),
+               'ets': wrappers.WrappedMetric(categorical.ETS(), both)}
+    aggregator = aggregation.Aggregator(
+        reduce_dims=['init_time', 'latitude', 'longitude'],
+        weigh_by=[weighting.GridAreaWeighting()])
+    step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
+        metrics, aggregator, preds, tgts)
+    ms, kms, kn = timed(step, 5)
+    pts = n_var * n_init * NLAT * NLON
+    bpp = 8.0 * len(thresholds)
+    out['contingency_3thr'] = {
+        'workload': 'CSI + ETS (whole 2x2 table, thresholds applied on load), '
+                    '3 thresholds, 2 vars x 20 init x 721x1440 f32, class API, '
+                    'device inputs',
+        'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+        'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+        'roofline': {'bound': 'hbm',
+                     'achieved': pts * bpp / (kms * 1e-3) / 1e9, 'peak': peak,
+                     'unit': 'GB/s',
+                     'frac': pts * bpp / (kms * 1e-3) / 1e9 / peak,
+                     'algorithmic_bytes_per_point': bpp,
+                     'note': '8 B per point and threshold: every threshold is '
+                             'a pass over the two fields'}}
+    del preds, tgts, metrics, step
+  except Exception as e:  # pylint: disable=broad-except
+    out['contingency_3thr'] = {'error': f'{type(e).__name__}: {e}'}
+    try:
+      ctx.profile(False)
+    except Exception:  # pylint: disable=broad-except
+      pass
+  torch.cuda.empty_cache()
   out['c5_stream_sample'] = stream_sample(dev, gen, lat)
   return out
 

@@ -14,12 +14,12 @@ Pinning status
 * PINNED TO OUTPUTS OF THE REFERENCE'S OWN CODE, generated in the build
   container: ``tests/golden/make_reference_golden.py`` imports the unmodified
   modules of /root/reference/weatherbenchX (aggregation, weighting, binning,
-  metrics/{base,deterministic,probabilistic,wrappers}) and stores the
-  AggregationState and metric values of 30 cases (all NaN modes, ACC with a
+  metrics/{base,deterministic,probabilistic,wrappers,categorical}) and stores
+  the AggregationState and metric values of 50 cases (all NaN modes, ACC with a
   day-of-year climatology across 29 February, regions / land-sea / band bins,
   both ensemble layouts, pairwise and sorted CRPS, skipna_ensemble, ensemble
-  moments, ensemble-averaged and ensemble-mean metrics, chunk combine, five
-  latitude grids) in ``tests/golden/reference_golden.npz``.
+  moments, ensemble-averaged and ensemble-mean metrics, thresholded
+  contingency tables and error exceedance, chunk combine, five latitude grids) in ``tests/golden/reference_golden.npz``.
   ``tests/test_reference_golden.py`` checks that this oracle reproduces every
   stored array.  Caveat, stated wherever the vectors are used: xarray, jax and
   absl are not installable in the container, so the reference ran on the
@@ -454,6 +454,84 @@ def passthrough(source: np.ndarray, other: np.ndarray,
   if copy_nans:
     result = np.where(~np.isnan(other), result, np.nan).astype(result.dtype)
   return result
+
+
+# ---------------------------------------------------------------------------
+# Categorical statistics (thresholded contingency tables, error exceedance)
+# ---------------------------------------------------------------------------
+
+
+def binarize_thresholds(x: np.ndarray, thresholds) -> np.ndarray:
+  """metrics/wrappers.py:85-88: ``(x > threshold).where(~isnan(x))`` as
+  float32 with the thresholds along a NEW TRAILING axis.  The thresholds are
+  float64 (a Python list turned into a DataArray), so NumPy promotes the
+  float32 field for the comparison; a NaN threshold compares False."""
+  t = np.asarray(thresholds, dtype=np.float64)
+  with np.errstate(invalid='ignore'):
+    out = (x[..., None] > t).astype(np.float32)
+  out[np.isnan(x)] = np.nan
+  return out
+
+
+def contingency_table(bp: np.ndarray, bt: np.ndarray) -> dict:
+  """metrics/categorical.py:25-101 on binary (0/1/NaN) float inputs:
+  ``astype(bool)`` products, NaN where ``predictions * targets`` is NaN."""
+  with np.errstate(invalid='ignore'):
+    p, t = bp.astype(bool), bt.astype(bool)
+    bad = np.isnan(bp * bt)
+  table = {'TruePositives': p & t, 'TrueNegatives': ~p & ~t,
+           'FalsePositives': p & ~t, 'FalseNegatives': ~p & t}
+  out = {}
+  for name, v in table.items():
+    v = v.astype(np.float32)
+    v[bad] = np.nan
+    out[name] = v
+  return out
+
+
+def error_exceedance(p: np.ndarray, t: np.ndarray, thresholds) -> np.ndarray:
+  """metrics/deterministic.py:285-295: ``abs(p - t) > threshold`` as float,
+  NaN where the error or the threshold is NaN; thresholds along a new trailing
+  axis."""
+  thr = np.asarray(thresholds, dtype=np.float64)
+  with np.errstate(invalid='ignore'):
+    abs_error = np.abs(p - t)
+    out = (abs_error[..., None] > thr).astype(np.float64)
+  out[np.isnan(abs_error)] = np.nan
+  out[..., np.isnan(thr)] = np.nan
+  return out
+
+
+def categorical_metric(name: str, tp, fp, fn, tn=None):
+  """metrics/categorical.py:345-635 on the mean statistics."""
+  with np.errstate(all='ignore'):
+    if name == 'csi':
+      return tp / (tp + fp + fn)
+    if name == 'accuracy':
+      return (tp + tn) / (tp + fp + fn + tn)
+    if name == 'recall':
+      return tp / (tp + fn)
+    if name == 'far':
+      return fp / (tp + fp)
+    if name == 'precision':
+      return tp / (tp + fp)
+    if name == 'f1':
+      return 2 * tp / (2 * tp + fp + fn)
+    if name == 'frequency_bias':
+      return (tp + fp) / (tp + fn)
+    if name == 'hss':
+      return 2 * (tp * tn - fp * fn) / (
+          (tp + fn) * (fn + tn) + (tp + fp) * (fp + tn))
+    if name == 'ets':
+      tp_random = ((tp + fp) * (tp + fn)) / (tp + fp + fn + tn)
+      return (tp - tp_random) / (tp + fp + fn - tp_random)
+    if name == 'sedi':
+      h = np.clip(tp / (tp + fn), 1e-6, 1 - 1e-6)
+      f = np.clip(fp / (fp + tn), 1e-6, 1 - 1e-6)
+      num = np.log(f) - np.log(h) + np.log(1 - h) - np.log(1 - f)
+      den = np.log(h) + np.log(f) + np.log(1 - h) + np.log(1 - f)
+      return num / den
+  raise KeyError(name)
 
 
 def crps_spread_brute_force(x: np.ndarray, ens_axis: int, fair: bool):

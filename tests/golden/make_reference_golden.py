@@ -3,7 +3,8 @@
     python tests/golden/make_reference_golden.py
 
 Executes the unmodified code of /root/reference/weatherbenchX (statistics,
-metrics, Aggregator, AggregationState, weighting, binning, wrappers) on small
+metrics incl. categorical, Aggregator, AggregationState, weighting, binning,
+wrappers) on small
 seeded inputs, through the stand-in modules of ``reference_runtime.py``
 (xarray / jax / absl are not installable in this container; read that file's
 docstring for exactly what is the reference's and what is the stand-in's).
@@ -36,6 +37,7 @@ from weatherbenchX import aggregation  # noqa: E402
 from weatherbenchX import binning  # noqa: E402
 from weatherbenchX import weighting  # noqa: E402
 from weatherbenchX.metrics import base as metrics_base  # noqa: E402
+from weatherbenchX.metrics import categorical  # noqa: E402
 from weatherbenchX.metrics import deterministic  # noqa: E402
 from weatherbenchX.metrics import probabilistic  # noqa: E402
 from weatherbenchX.metrics import wrappers  # noqa: E402
@@ -46,7 +48,7 @@ STORE: dict = {}
 NS = reference_cases.namespace(
     xr=xr, aggregation=aggregation, binning=binning, weighting=weighting,
     base=metrics_base, deterministic=deterministic,
-    probabilistic=probabilistic, wrappers=wrappers)
+    probabilistic=probabilistic, wrappers=wrappers, categorical=categorical)
 
 
 def put(key, array):

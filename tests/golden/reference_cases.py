@@ -87,7 +87,24 @@ def make_inputs() -> dict:
   out['member_holes'] = holes
   out['ens_land'] = rng.random((NLAT, NLON)) < 0.4
   out['y_holes'] = rng.random(_shape(D_ENS_T)) < 0.06
+  # precipitation-like fields (mm): many exact zeros, values that hit the
+  # thresholds exactly (multiples of 0.25) and thresholds that are not float32
+  # numbers (0.1): the comparison at the boundary is part of the contract
+  wet = rng.random(_shape(D2)) < 0.55
+  out['rain_t'] = (np.round(rng.gamma(0.8, 2.0, _shape(D2)) * 4) / 4 * wet
+                   ).astype(f32)
+  out['rain_p'] = np.maximum(
+      0, out['rain_t'] + np.round(rng.normal(0, 1.0, _shape(D2)) * 4) / 4
+  ).astype(f32)
+  out['rain_p'][rng.random(_shape(D2)) < 0.05] = f32(0.1)
+  out['rain_t'][rng.random(_shape(D2)) < 0.05] = f32(0.1)
+  out['rain_holes'] = rng.random(_shape(D2)) < 0.06
+  out['rain_p_holes'] = rng.random(_shape(D2)) < 0.03
   return out
+
+
+RAIN_THRESHOLDS = [0.0, 0.1, 0.5, 2.0, 1e9]
+EXCEEDANCE_THRESHOLDS = [0.0, 0.25, 0.1, 3.0]
 
 
 def full_climatology(rows: np.ndarray) -> np.ndarray:
@@ -309,6 +326,79 @@ def build_cases(ns, inputs):
           det.RMSE(), [wrappers.EnsembleMean('predictions',
                                              ensemble_dim=ENS)])},
                  family='ens_mean')
+
+  # -- categorical: thresholded contingency tables, error exceedance ---------
+  # (categorical.py:25-101,345-635; wrappers.py:50-88,214-267;
+  #  deterministic.py:262-295)
+  cat = ns.categorical
+  both = [wrappers.ContinuousToBinary('both', RAIN_THRESHOLDS, 'threshold')]
+  table_metrics = {
+      name: wrappers.WrappedMetric(cls(), both) for name, cls in (
+          ('csi', cat.CSI), ('accuracy', cat.Accuracy), ('recall', cat.Recall),
+          ('far', cat.FalseAlarmRate), ('precision', cat.Precision),
+          ('f1', cat.F1Score), ('frequency_bias', cat.FrequencyBias),
+          ('hss', cat.HSS), ('ets', cat.ETS), ('sedi', cat.SEDI))}
+  rain_p = {'total_precipitation_6hr': da(inputs['rain_p'], D2)}
+  rain_p_nan = {'total_precipitation_6hr': da(
+      with_nan(inputs['rain_p'], inputs['rain_p_holes']), D2)}
+  rain_t = {'total_precipitation_6hr': da(inputs['rain_t'], D2)}
+  rain_t_nan = {'total_precipitation_6hr': da(
+      with_nan(inputs['rain_t'], inputs['rain_holes']), D2,
+      mask=(D2, ~inputs['rain_holes']))}
+
+  def cat_case(name, use_metrics=None, reduce_dims=None, weighted=True,
+               nan_targets=False, nan_predictions=False, bins=None,
+               kind='table', **flags):
+    reduce_dims = reduce_dims or RD
+    spec = dict(family='cat', kind=kind, reduce_dims=reduce_dims,
+                weighted=weighted, masked=flags.get('masked', False),
+                skipna=flags.get('skipna', False), bins=bins or [],
+                nan_targets=nan_targets, nan_predictions=nan_predictions)
+    aggregator = agg.Aggregator(
+        reduce_dims=reduce_dims, weigh_by=area() if weighted else None,
+        bin_by=_make_bins(ns, bins, inputs['land']) if bins else None,
+        **flags)
+    return (name, spec, use_metrics or table_metrics, aggregator,
+            rain_p_nan if nan_predictions else rain_p,
+            rain_t_nan if nan_targets else rain_t)
+
+  yield cat_case('cat/table_weighted')
+  yield cat_case('cat/table_unweighted_keep_init', weighted=False,
+                 reduce_dims=['latitude', 'longitude'])
+  yield cat_case('cat/table_nan_default', nan_targets=True,
+                 nan_predictions=True)
+  yield cat_case('cat/table_nan_masked', nan_targets=True, masked=True)
+  yield cat_case('cat/table_nan_masked_nan_predictions', nan_targets=True,
+                 nan_predictions=True, masked=True)
+  yield cat_case('cat/table_nan_skipna', nan_targets=True,
+                 nan_predictions=True, skipna=True)
+  yield cat_case('cat/table_by_init_hour', bins=['init_hour_global'],
+                 use_metrics={'csi': table_metrics['csi'],
+                              'accuracy': table_metrics['accuracy']})
+  yield cat_case('cat/table_regions', bins=['regions_land'],
+                 use_metrics={'csi': table_metrics['csi'],
+                              'accuracy': table_metrics['accuracy']})
+  # targets that are binary already: only the predictions are thresholded
+  event = {'total_precipitation_6hr': da(
+      (inputs['rain_t'] > 0.5).astype(np.float32), D2)}
+  name, spec, _, aggregator, p_, _ = cat_case(
+      'cat/predictions_thresholded_binary_targets',
+      use_metrics={'ets': wrappers.WrappedMetric(
+          cat.ETS(), [wrappers.ContinuousToBinary(
+              'predictions', [0.5, 2.0], 'threshold')])},
+      kind='pred_only')
+  yield (name, spec, {'ets': wrappers.WrappedMetric(
+      cat.ETS(), [wrappers.ContinuousToBinary(
+          'predictions', [0.5, 2.0], 'threshold')])}, aggregator, p_, event)
+  exceedance = {'exceedance': det.ErrorExceedance(EXCEEDANCE_THRESHOLDS)}
+  yield cat_case('cat/error_exceedance', use_metrics=exceedance,
+                 kind='exceedance')
+  yield cat_case('cat/error_exceedance_nan_skipna', use_metrics=exceedance,
+                 kind='exceedance', nan_targets=True, nan_predictions=True,
+                 skipna=True)
+  yield cat_case('cat/error_exceedance_nan_default_keep_init',
+                 use_metrics=exceedance, kind='exceedance', nan_targets=True,
+                 reduce_dims=['latitude', 'longitude'])
 
 
 def _make_bins(ns, names, land_values):

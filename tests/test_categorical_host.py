@@ -1,0 +1,344 @@
+"""Host side of the categorical path on the GPU-less box.
+
+The oracle's categorical functions against the reference's inline known
+answers; the float32 threshold rule; and everything above the C ABI (lazy
+handles, launch grouping, job / threshold tables, result labelling) with the
+plans executed by the NumPy interpreter of tests/wbx_emulator.py.  The kernels
+themselves are validated by tests/test_gpu_categorical.py and the ``cat/*``
+cases of tests/test_reference_golden.py on a B200.
+"""
+
+import numpy as np
+import pytest
+
+import wbx_emulator
+import wbx_oracle as oracle
+from weatherbenchx_b200 import _cabi
+from weatherbenchx_b200 import aggregation
+from weatherbenchx_b200 import engine
+from weatherbenchx_b200 import weighting
+from weatherbenchx_b200 import xarray_lite as xl
+from weatherbenchx_b200.lazy import LazyBinarized
+from weatherbenchx_b200.lazy import LazyCategoricalStatistic
+from weatherbenchx_b200.lazy import threshold_f32
+from weatherbenchx_b200.metrics import base as metrics_base
+from weatherbenchx_b200.metrics import categorical
+from weatherbenchx_b200.metrics import deterministic
+from weatherbenchx_b200.metrics import wrappers
+
+KINDS = ('TruePositives', 'FalsePositives', 'FalseNegatives', 'TrueNegatives')
+DIMS = ('init_time', 'latitude', 'longitude')
+
+
+def _da(values, name='rain'):
+  n, ny, nx = values.shape
+  return xl.DataArray(values, DIMS, name=name, coords={
+      'init_time': np.arange(n), 'latitude': np.linspace(-90, 90, ny),
+      'longitude': np.linspace(0, 360, nx, endpoint=False)})
+
+
+# ---------------------------------------------------------------------------
+# oracle pins (reference inline known answers)
+# ---------------------------------------------------------------------------
+
+
+def test_oracle_error_exceedance_known_answer():
+  """metrics/metrics_test.py:1031-1049."""
+  p = np.array([0, -1, 1, np.nan])
+  t = np.zeros(4)
+  got = oracle.error_exceedance(p, t, [0, 0.5, 1, np.nan])
+  expected = np.array([[0, 0, 0, np.nan], [1, 1, 0, np.nan],
+                       [1, 1, 0, np.nan], [np.nan] * 4])
+  np.testing.assert_array_equal(got, expected)
+
+
+def _oracle_metric(name, p, t):
+  table = oracle.contingency_table(p, t)
+  mean = {k: v.mean() for k, v in table.items()}   # skipna=False
+  return oracle.categorical_metric(
+      name, mean['TruePositives'], mean['FalsePositives'],
+      mean['FalseNegatives'], mean['TrueNegatives'])
+
+
+def test_oracle_far_and_csi_known_answers():
+  """metrics/metrics_test.py:100-170 on binary fields."""
+  zeros, ones = np.zeros((2, 4, 6), np.float32), np.ones((2, 4, 6), np.float32)
+  half = zeros.copy()
+  half[0] = 1
+  nan = ones.copy()
+  nan[0] = np.nan
+  assert np.isnan(_oracle_metric('far', zeros, zeros))
+  assert _oracle_metric('far', ones, ones) == 0
+  assert _oracle_metric('far', ones, zeros) == 1
+  assert _oracle_metric('far', ones, half) == 0.5
+  assert np.isnan(_oracle_metric('far', zeros, nan))
+  assert np.isnan(_oracle_metric('csi', zeros, zeros))
+  assert _oracle_metric('csi', ones, ones) == 1
+  assert _oracle_metric('csi', ones, zeros) == 0
+  assert _oracle_metric('csi', ones, half) == 0.5
+  assert np.isnan(_oracle_metric('csi', zeros, nan))
+
+
+# ---------------------------------------------------------------------------
+# float32 thresholds
+# ---------------------------------------------------------------------------
+
+
+def test_threshold_f32_reproduces_the_float64_comparison():
+  """x > t (float32 field, float64 threshold: NumPy promotes the field) must
+  equal x > threshold_f32(t) evaluated in float32, also AT the boundary."""
+  rng = np.random.default_rng(0)
+  thr = np.concatenate([
+      [0.0, 0.1, 0.25, 1e-45, -0.1, 1e9, 3.4e38, 1e39, -1e39, np.inf, -np.inf],
+      rng.normal(0, 3, 200), rng.random(200) * 1e-3])
+  t32 = threshold_f32(thr)
+  assert t32.dtype == np.float32
+  for t64, t in zip(thr, t32):
+    with np.errstate(over='ignore'):
+      near = np.float32(t64)
+    x = np.array([near, np.nextafter(near, np.float32(np.inf)),
+                  np.nextafter(near, np.float32(-np.inf)), 0, -0.0, 1, -1,
+                  np.inf, -np.inf], np.float32)
+    np.testing.assert_array_equal(x > t, x.astype(np.float64) > t64,
+                                  err_msg=repr(t64))
+  assert np.isnan(threshold_f32([np.nan]))[0]
+  # exact float32 numbers stay as they are
+  np.testing.assert_array_equal(threshold_f32([0.25, 2.0, -8.5]),
+                                np.array([0.25, 2.0, -8.5], np.float32))
+  assert threshold_f32([0.1])[0] < np.float32(0.1)
+
+
+# ---------------------------------------------------------------------------
+# handles
+# ---------------------------------------------------------------------------
+
+
+def test_binarized_handle_metadata_follows_the_reference():
+  x = _da(np.zeros((2, 4, 8), np.float32))
+  b = wrappers.ContinuousToBinary('both', [0.5, 1], 'thr').transform_fn(x)
+  assert isinstance(b, LazyBinarized) and b.is_lazy
+  assert b.dims == DIMS + ('thr',) and b.shape == (2, 4, 8, 2)
+  np.testing.assert_array_equal(b.coords['thr'].values, [0.5, 1.0])
+  assert b.name == 'rain' and b.dtype == np.float32
+  # a scalar threshold becomes a length-one dim (wrappers.py:248-252)
+  one = wrappers.ContinuousToBinary('predictions', 0.5, 'thr').transform_fn(x)
+  assert one.shape == (2, 4, 8, 1)
+  # unique names (wrappers.py:260-265, 984-986)
+  t = wrappers.ContinuousToBinary('both', [0.5, 1], 'thr')
+  assert t.unique_name_suffix == 'thr=0.5,1'
+  wrapped = wrappers.WrappedMetric(categorical.CSI(), [t]).statistics
+  assert wrapped['TruePositives'].unique_name == 'TruePositives_both_thr=0.5,1'
+  with pytest.raises(ValueError):
+    wrappers.ContinuousToBinary(
+        'both', xl.DataArray([0.5], dims=['thr']), 'thr')
+  named = wrappers.ContinuousToBinary(
+      'both', xl.DataArray([0.5, 2.0], dims=['thr']), 'thr',
+      unique_name_suffix='fixed')
+  assert named.unique_name_suffix == 'thr=fixed'
+  handle = named.transform_fn(x)
+  assert handle.shape == (2, 4, 8, 2) and 'thr' not in handle.coords
+  with pytest.raises(NotImplementedError):
+    wrappers.ContinuousToBinary(
+        'both', xl.DataArray(np.zeros((2, 4)), dims=['thr', 'latitude']),
+        'thr', unique_name_suffix='x').transform_fn(x)
+
+
+def test_categorical_handle_dims_and_grouping():
+  x, y = _da(np.zeros((2, 4, 8), np.float32)), _da(np.ones((2, 4, 8), np.float32))
+  t = wrappers.ContinuousToBinary('both', [0.5, 1, 2], 'thr')
+  bp, bt = t.transform_fn(x), t.transform_fn(y)
+  tp = categorical.TruePositives().compute({'v': bp}, {'v': bt})['v']
+  fn = categorical.FalseNegatives().compute({'v': bp}, {'v': bt})['v']
+  assert isinstance(tp, LazyCategoricalStatistic) and tp.is_lazy
+  assert tp.dims == DIMS + ('thr',) and tp.plan_dims == ('thr',) + DIMS
+  assert tp.xform == _cabi.XF_CONTINGENCY
+  assert tp.group_key() == fn.group_key()
+  # other thresholds, other operands or an untransformed input: other launches
+  other = wrappers.ContinuousToBinary('both', [0.5, 1, 3], 'thr')
+  tp2 = categorical.TruePositives().compute(
+      {'v': other.transform_fn(x)}, {'v': other.transform_fn(y)})['v']
+  assert tp2.group_key() != tp.group_key()
+  raw = categorical.TruePositives().compute({'v': x}, {'v': y})['v']
+  assert raw.dims == DIMS and raw.threshold_dim is None
+  assert raw.xform == (_cabi.XF_CONTINGENCY | _cabi.XF_PRED_NONZERO |
+                       _cabi.XF_TARGET_NONZERO)
+  half = categorical.TruePositives().compute({'v': bp}, {'v': y})['v']
+  assert half.xform == _cabi.XF_CONTINGENCY | _cabi.XF_TARGET_NONZERO
+  assert half.thr_target is None and half.thr_pred is not None
+  se = deterministic.SquaredError().compute({'v': x}, {'v': y})['v']
+  assert se.group_key()[:2] != raw.group_key()[:2]
+  with pytest.raises(ValueError, match='Failed to compute'):
+    metrics_base.compute_unique_statistics_for_all_metrics(
+        {'tp': categorical.TruePositives()}, {'v': bp},
+        {'v': other.transform_fn(y)})
+
+
+def test_planner_threshold_tables():
+  """Jobs enumerate (threshold, kept dims, reduced outer dims); each job
+  carries the float32 threshold of its index."""
+  rng = np.random.default_rng(1)
+  p = _da(rng.random((3, 4, 8)).astype(np.float32))
+  t = _da(rng.random((3, 4, 8)).astype(np.float32))
+  thresholds = [0.1, 0.5, 0.9]
+  tr = wrappers.ContinuousToBinary('both', thresholds, 'thr')
+  stats = [cls().compute({'v': tr.transform_fn(p)}, {'v': tr.transform_fn(t)})
+           ['v'] for cls in (categorical.TruePositives,
+                             categorical.TrueNegatives)]
+  spec = engine.build_fused_spec(stats, ['init_time', 'latitude', 'longitude'])
+  assert spec.xform == _cabi.XF_CONTINGENCY
+  assert spec.stat_mask == 0b1001 and spec.n_cells == 3
+  # init_time is reduced and contiguous with the grid: it joins the slab
+  assert (spec.ny, spec.nx) == (12, 8) and len(spec.pred) == 3
+  np.testing.assert_array_equal(spec.cell, np.arange(3))
+  np.testing.assert_array_equal(spec.thr_pred, threshold_f32(thresholds))
+  np.testing.assert_array_equal(spec.thr_pred, spec.thr_target)
+  assert spec.thr_pred.dtype == np.float32
+  # the three thresholds read the same slab
+  assert len(set(spec.pred.tolist())) == 1
+  assert spec.kept == ['thr'] and spec.kept_order == ('thr',)
+  # keeping init_time: jobs = (threshold, init_time); the result has the
+  # reference's dim order (init_time, thr)
+  spec = engine.build_fused_spec(stats, ['latitude', 'longitude'])
+  assert (spec.ny, spec.nx) == (4, 8) and len(spec.pred) == 9
+  assert spec.kept == ['thr', 'init_time'] and spec.n_cells == 9
+  assert spec.kept_order == ('init_time', 'thr')
+  np.testing.assert_array_equal(
+      spec.thr_pred, np.repeat(threshold_f32(thresholds), 3))
+  np.testing.assert_array_equal(spec.pred[:3], spec.pred[3:6])
+  # region bins need the class-map kernel, which has no categorical variant
+  land = xl.DataArray(np.ones((2, 4, 8), bool), ('region',) + DIMS[1:])
+  with pytest.raises(engine.FastPathUnavailable):
+    engine.build_fused_spec(stats, ['init_time', 'latitude', 'longitude'],
+                            bin_masks=[land], bin_dim_names=['region'])
+
+
+# ---------------------------------------------------------------------------
+# class surface with interpreted plans
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize('mode', ['propagate', 'masked', 'skipna'])
+def test_table_metrics_with_interpreted_plans(mode, monkeypatch):
+  wbx_emulator.installed(monkeypatch)
+  launches = []
+  real = _cabi.DetPlan
+
+  class Counting(real):
+
+    def __init__(self, ctx, **desc):
+      launches.append(desc)
+      super().__init__(ctx, **desc)
+
+  monkeypatch.setattr(_cabi, 'DetPlan', Counting)
+  engine.clear_plan_cache()
+  rng = np.random.default_rng(4)
+  shape = (3, 6, 8)
+  p = (rng.gamma(1.0, 1.0, shape) * (rng.random(shape) < 0.7)).astype(np.float32)
+  t = (rng.gamma(1.0, 1.0, shape) * (rng.random(shape) < 0.7)).astype(np.float32)
+  p[rng.random(shape) < 0.1] = np.float32(0.1)
+  P, T = _da(p), _da(t)
+  if mode != 'propagate':
+    holes = rng.random(shape) < 0.1
+    t = np.where(holes, np.nan, t).astype(np.float32)
+    T = _da(t).assign_coords(mask=xl.DataArray(~holes, DIMS))
+  thresholds = [0.0, 0.1, 1.0]
+  both = [wrappers.ContinuousToBinary('both', thresholds, 'threshold')]
+  names = ('csi', 'accuracy', 'recall', 'far', 'precision', 'f1',
+           'frequency_bias', 'hss', 'ets', 'sedi')
+  classes = (categorical.CSI, categorical.Accuracy, categorical.Recall,
+             categorical.FalseAlarmRate, categorical.Precision,
+             categorical.F1Score, categorical.FrequencyBias, categorical.HSS,
+             categorical.ETS, categorical.SEDI)
+  metrics = {n: wrappers.WrappedMetric(c(), both)
+             for n, c in zip(names, classes)}
+  metrics['rmse'] = deterministic.RMSE()
+  aggregator = aggregation.Aggregator(
+      reduce_dims=['latitude', 'longitude'],
+      weigh_by=[weighting.GridAreaWeighting()], masked=mode == 'masked',
+      skipna=mode == 'skipna')
+  values = aggregation.compute_metric_values_for_single_chunk(
+      metrics, aggregator, {'rain': P}, {'rain': T})
+  # the contingency table of all thresholds is ONE plan, RMSE another
+  assert len(launches) == 2
+  assert sorted(d.get('xform', 0) for d in launches) == [0, _cabi.XF_CONTINGENCY]
+  w = oracle.grid_area_weights(np.linspace(-90, 90, shape[1]))
+  table = oracle.contingency_table(oracle.binarize_thresholds(p, thresholds),
+                                   oracle.binarize_thresholds(t, thresholds))
+  means = {}
+  for kind in KINDS:
+    sws, sw, dims = oracle.aggregate(
+        table[kind], DIMS + ('threshold',), ['latitude', 'longitude'],
+        weights=[(w, ('latitude',))],
+        mask=~np.isnan(t) if mode == 'masked' else None,
+        mask_dims=DIMS if mode == 'masked' else None, masked=mode == 'masked',
+        skipna=mode == 'skipna')
+    assert tuple(dims) == ('init_time', 'threshold')
+    means[kind] = oracle.mean_statistic(sws, sw)
+  for name in names:
+    got = values[f'{name}.rain']
+    assert got.dims == ('init_time', 'threshold')
+    np.testing.assert_allclose(
+        got.values,
+        oracle.categorical_metric(
+            name, means['TruePositives'], means['FalsePositives'],
+            means['FalseNegatives'], means['TrueNegatives']),
+        rtol=1e-9, err_msg=name)
+
+
+def test_known_answers_with_interpreted_plans(monkeypatch):
+  """metrics/metrics_test.py:100-170 through the class surface (binary inputs,
+  no threshold transform: the non-zero test of `.astype(bool)`)."""
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  zeros = _da(np.zeros((2, 4, 8), np.float32))
+  ones = _da(np.ones((2, 4, 8), np.float32))
+  half_values = np.zeros((2, 4, 8), np.float32)
+  half_values[0] = 1
+  half = _da(half_values)
+  nan_values = np.ones((2, 4, 8), np.float32)
+  nan_values[0] = np.nan
+  nan = _da(nan_values)
+
+  def value(name, metric, p, t):
+    out = aggregation.compute_metric_values_for_single_chunk(
+        {name: metric}, aggregation.Aggregator(reduce_dims=list(DIMS)),
+        {'rain': p}, {'rain': t})
+    return float(out[f'{name}.rain'].values)
+
+  far, csi = categorical.FalseAlarmRate(), categorical.CSI()
+  assert np.isnan(value('far', far, zeros, zeros))
+  assert value('far', far, ones, ones) == 0
+  assert value('far', far, ones, zeros) == 1
+  assert value('far', far, ones, half) == 0.5
+  assert np.isnan(value('far', far, zeros, nan))
+  assert np.isnan(value('csi', csi, zeros, zeros))
+  assert value('csi', csi, ones, ones) == 1
+  assert value('csi', csi, ones, zeros) == 0
+  assert value('csi', csi, ones, half) == 0.5
+  assert np.isnan(value('csi', csi, zeros, nan))
+
+
+def test_error_exceedance_with_interpreted_plans(monkeypatch):
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  rng = np.random.default_rng(6)
+  p = rng.normal(0, 1, (3, 4, 8)).astype(np.float32)
+  t = rng.normal(0, 1, (3, 4, 8)).astype(np.float32)
+  t[0, 1, 2] = np.nan
+  thresholds = xl.Dataset({'rain': xl.DataArray(
+      [0.1, 1.0, np.nan], dims=['level_of_error'],
+      coords={'level_of_error': ['small', 'large', 'undefined']})})
+  stat = deterministic.ErrorExceedance(thresholds)
+  aggregator = aggregation.Aggregator(reduce_dims=['latitude', 'longitude'],
+                                      skipna=True)
+  state = aggregator.aggregate_statistics(
+      {'ErrorExceedance': stat.compute({'rain': _da(p)}, {'rain': _da(t)})})
+  got = state.mean_statistics()['ErrorExceedance']['rain']
+  assert got.dims == ('init_time', 'level_of_error')
+  assert list(got.coords['level_of_error'].values) == ['small', 'large',
+                                                       'undefined']
+  field = oracle.error_exceedance(p, t, [0.1, 1.0, np.nan])
+  with np.errstate(invalid='ignore'):
+    expected = np.nanmean(field, axis=(1, 2))
+  np.testing.assert_allclose(got.values[:, :2], expected[:, :2], rtol=1e-12)
+  assert np.isnan(got.values[:, 2]).all()   # 0 / 0: nothing valid

@@ -1,6 +1,6 @@
 """Parity against vectors produced by the reference's own code.
 
-``tests/golden/reference_golden.npz`` holds, for 38 evaluation cases, the
+``tests/golden/reference_golden.npz`` holds, for 50 evaluation cases, the
 AggregationState (sum_weighted_statistics / sum_weights per statistic and
 variable) and the metric values that the UNMODIFIED modules of
 /root/reference/weatherbenchX returned in the build container
@@ -190,6 +190,32 @@ def _oracle_fields(spec, inputs):
           out[(name, var)] = (
               fn(p, t, aligned), dims,
               None if name == 'SquaredPredictionAnomaly' else mask)
+  elif family == 'cat':
+    var = 'total_precipitation_6hr'
+    p, t, mask = inputs['rain_p'], inputs['rain_t'], None
+    if spec['nan_predictions']:
+      p = cases.with_nan(p, inputs['rain_p_holes'])
+    if spec['nan_targets']:
+      t = cases.with_nan(t, inputs['rain_holes'])
+      mask = ~inputs['rain_holes']
+    if spec['kind'] == 'exceedance':
+      dims = cases.D2 + ('error_exceedance_thresholds',)
+      field = oracle.error_exceedance(p, t, cases.EXCEEDANCE_THRESHOLDS)
+      out[('ErrorExceedance', var)] = (field, dims, mask)
+    else:
+      dims = cases.D2 + ('threshold',)
+      if spec['kind'] == 'pred_only':
+        thresholds = [0.5, 2.0]
+        bt = (inputs['rain_t'] > 0.5).astype(np.float32)[..., None]
+        suffix = 'predictions_threshold=0.5,2.0'
+      else:
+        thresholds = cases.RAIN_THRESHOLDS
+        bt = oracle.binarize_thresholds(t, thresholds)
+        suffix = 'both_threshold=' + ','.join(str(v) for v in thresholds)
+      bp = oracle.binarize_thresholds(p, thresholds)
+      bp, bt = np.broadcast_arrays(bp, bt)
+      for name, field in oracle.contingency_table(bp, bt).items():
+        out[(f'{name}_{suffix}', var)] = (field, dims, mask)
   elif family == 'wind':
     se = oracle.wind_vector_squared_error(
         inputs['u_p'], inputs['u_t'], inputs['v_p'], inputs['v_t'])
@@ -253,7 +279,8 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
   result = oracle.aggregate(
       values, dims, spec['reduce_dims'], weights=weights,
       bin_masks=[b for b, _ in bins], mask=mask,
-      mask_dims=dims if mask is not None else None, masked=spec['masked'],
+      mask_dims=(dims[:mask.ndim] if mask is not None else None),
+      masked=spec['masked'],
       skipna=spec['skipna'])
   assert result is not None
   return result
@@ -261,7 +288,7 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
 
 def test_fixture_is_complete(golden):
   names = [str(n) for n in golden['cases']]
-  assert len(names) == 38 and len(set(names)) == 38
+  assert len(names) == 50 and len(set(names)) == 50
   for case in names:
     assert _case_keys(golden, case, 'sws'), case
     assert _case_keys(golden, case, 'value'), case
@@ -280,7 +307,8 @@ def _case_table(inputs_dict):
       xr=_PlainNamespace(), aggregation=_PlainNamespace(),
       binning=_PlainNamespace(), weighting=_PlainNamespace(),
       base=_PlainNamespace(), deterministic=_PlainNamespace(),
-      probabilistic=_PlainNamespace(), wrappers=_PlainNamespace())
+      probabilistic=_PlainNamespace(), wrappers=_PlainNamespace(),
+      categorical=_PlainNamespace())
   return {name: spec for name, spec, *_ in cases.build_cases(ns, inputs_dict)}
 
 
@@ -345,6 +373,20 @@ def test_oracle_reproduces_reference_values(golden, inputs):
         spa, _ = mean(case, spec, fields, 'SquaredPredictionAnomaly', var)
         sta, _ = mean(case, spec, fields, 'SquaredTargetAnomaly', var)
         value = oracle.acc_from_means(cov, spa, sta)
+      elif spec['family'] == 'cat':
+        if metric == 'exceedance':
+          value, dims = mean(case, spec, fields, 'ErrorExceedance', var)
+        else:
+          suffix = next(k[0] for k in fields if k[0].startswith(
+              'TruePositives_'))[len('TruePositives_'):]
+          parts = {}
+          for name in ('TruePositives', 'FalsePositives', 'FalseNegatives',
+                       'TrueNegatives'):
+            parts[name], dims = mean(case, spec, fields, f'{name}_{suffix}',
+                                     var)
+          value = oracle.categorical_metric(
+              metric, parts['TruePositives'], parts['FalsePositives'],
+              parts['FalseNegatives'], parts['TrueNegatives'])
       elif metric in ('crps_fair', 'crps_unfair'):
         fair = metric.split('_')[1]
         skill, dims = mean(case, spec, fields, 'CRPSSkill_realization', var)
@@ -421,12 +463,12 @@ def test_chunk_combine_equals_monolithic_in_the_reference(golden):
 def _product_namespace():
   from weatherbenchx_b200 import aggregation, binning, weighting
   from weatherbenchx_b200 import xarray_lite as xl
-  from weatherbenchx_b200.metrics import base, deterministic
+  from weatherbenchx_b200.metrics import base, categorical, deterministic
   from weatherbenchx_b200.metrics import probabilistic, wrappers
   return cases.namespace(
       xr=xl, aggregation=aggregation, binning=binning, weighting=weighting,
       base=base, deterministic=deterministic, probabilistic=probabilistic,
-      wrappers=wrappers)
+      wrappers=wrappers, categorical=categorical)
 
 
 def _labels_match(golden, key, da):
@@ -451,7 +493,14 @@ CASE_NAMES = [
     'ens/skipna_ensemble', 'ens/nan_members_propagate', 'ens/regions',
     'ens/nan_targets_default', 'ens/nan_targets_masked',
     'ens/nan_targets_skipna', 'ens/regions_nan_targets_masked',
-    'ens/ensemble_averaged_rmse', 'ens/ensemble_mean_rmse']
+    'ens/ensemble_averaged_rmse', 'ens/ensemble_mean_rmse',
+    'cat/table_weighted', 'cat/table_unweighted_keep_init',
+    'cat/table_nan_default', 'cat/table_nan_masked',
+    'cat/table_nan_masked_nan_predictions', 'cat/table_nan_skipna',
+    'cat/table_by_init_hour', 'cat/table_regions',
+    'cat/predictions_thresholded_binary_targets', 'cat/error_exceedance',
+    'cat/error_exceedance_nan_skipna',
+    'cat/error_exceedance_nan_default_keep_init']
 
 
 def test_case_names_cover_the_fixture(golden):
@@ -508,7 +557,9 @@ def test_cuda_path_reproduces_reference(golden, inputs, case, space):
 # Cases whose host-space path needs device memory even before a kernel runs
 # (per-point fields of the CRPS launch, the EnsembleMean transform).
 NEEDS_DEVICE = {'ens/regions', 'ens/regions_nan_targets_masked',
-                'ens/ensemble_mean_rmse'}
+                'ens/ensemble_mean_rmse',
+                # region bins + thresholds: per-point fields, generic kernel
+                'cat/table_regions'}
 
 
 @pytest.mark.parametrize('case',
