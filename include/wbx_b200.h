@@ -254,6 +254,24 @@ int wbx_xf_elementwise(wbx_ctx* ctx, int32_t xform, int32_t slot,
                        float thr_pred, float thr_target, const float* pred,
                        const float* target, int64_t n, float* out);
 
+/* SEEPS per-gridpoint field (Stable Equitable Error in Probability Space,
+ * metrics/categorical.py:104-304, SEEPS._compute_seeps_per_variable :243-304).
+ * n contiguous float32 device elements of predictions, targets and the
+ * climatological wet threshold aligned to the valid times (:251-254); p1 is the
+ * dry fraction of every grid point (:268-272), a float32 device array of
+ * p1_len elements that the fields repeat over (element i uses p1[i % p1_len];
+ * n % p1_len == 0), with NaN where the caller masks the point
+ * (p1 outside [min_p1, max_p1], :293-294).  dry_threshold is in the unit of the
+ * fields (dry_threshold_mm / 1000 for metres, :225).
+ * out[i] = 0.5 * S[forecast category][observed category](p1), NaN where
+ * pred, target or p1 is NaN; float32 arithmetic operation by operation as
+ * NumPy evaluates the reference (csrc/seeps_point.h).  Asynchronous on the
+ * context stream. */
+int wbx_seeps_elementwise(wbx_ctx* ctx, const float* pred, const float* target,
+                          const float* wet_threshold, const float* p1,
+                          int64_t p1_len, float dry_threshold, int64_t n,
+                          float* out);
+
 /* sizeof / offsetof of the descriptor structs as this library was compiled:
  * which = 0 wbx_det_desc, 1 wbx_crps_desc, 2 wbx_crps_point_desc,
  * 3 wbx_spectrum_desc, 4 wbx_generic_desc.  Writes up to `cap` values to

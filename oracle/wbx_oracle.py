@@ -534,6 +534,55 @@ def categorical_metric(name: str, tp, fp, fn, tn=None):
   raise KeyError(name)
 
 
+def seeps_categories(x: np.ndarray, wet_threshold: np.ndarray,
+                     dry_threshold_mm: float) -> np.ndarray:
+  """metrics/categorical.py:217-241: [dry, light, heavy] indicators stacked on
+  a new leading axis, float64 with NaN where ``x`` is NaN.  ``dry_threshold``
+  is a Python float, so NumPy compares the float32 field in float32."""
+  dry_threshold = dry_threshold_mm / 1000.0
+  with np.errstate(invalid='ignore'):
+    dry = x <= dry_threshold
+    light = np.logical_and(x > dry_threshold, x < wet_threshold)
+    heavy = x >= wet_threshold
+  out = np.stack([dry, light, heavy]).astype(np.float64)
+  out[:, np.isnan(x)] = np.nan
+  return out
+
+
+def seeps_p1(dry_fraction: np.ndarray, time_axes) -> np.ndarray:
+  """metrics/categorical.py:268-272: ``.mean(('hour', 'dayofyear'))`` -- xarray
+  skips NaN by default, i.e. ``np.nanmean`` in the dtype of the input."""
+  with warnings.catch_warnings():
+    warnings.simplefilter('ignore')
+    return np.nanmean(dry_fraction, axis=tuple(time_axes))
+
+
+def seeps(p: np.ndarray, t: np.ndarray, wet_threshold: np.ndarray,
+          p1: np.ndarray, dry_threshold_mm: float = 0.25, min_p1: float = 0.1,
+          max_p1: float = 0.85):
+  """metrics/categorical.py:243-296 for aligned inputs: ``wet_threshold``
+  already gathered to the valid times and broadcastable to ``p``; ``p1``
+  broadcastable to ``p`` (trailing grid dims).  Returns (score, p1 mask): the
+  score is NaN where an input is NaN or p1 lies outside [min_p1, max_p1]."""
+  f_cat = seeps_categories(p, wet_threshold, dry_threshold_mm)
+  t_cat = seeps_categories(t, wet_threshold, dry_threshold_mm)
+  contingency = f_cat[:, None] * t_cat[None, :]          # [forecast, truth, ...]
+  with np.errstate(divide='ignore', invalid='ignore'):
+    zero = np.zeros_like(p1)
+    matrix = [[zero, 1 / (1 - p1), 4 / (1 - p1)],
+              [1 / p1, zero, 3 / (1 - p1)],
+              [1 / p1 + 3 / (2 + p1), 3 / (2 + p1), zero]]
+    matrix = 0.5 * np.stack([np.stack(row) for row in matrix])
+    matrix = np.broadcast_to(
+        matrix.reshape(matrix.shape[:2] + (1,) * (p.ndim - p1.ndim)
+                       + p1.shape), contingency.shape)
+    result = np.einsum('ft...,ft...->...', contingency, matrix)
+  with np.errstate(invalid='ignore'):
+    mask = (p1 >= min_p1) & (p1 <= max_p1)
+  result = np.where(np.broadcast_to(mask, result.shape), result, np.nan)
+  return result, mask
+
+
 def crps_spread_brute_force(x: np.ndarray, ens_axis: int, fair: bool):
   """metrics/metrics_test.py:603-608 -- the reference's own brute force."""
   m = x.shape[ens_axis]

@@ -100,7 +100,23 @@ def make_inputs() -> dict:
   out['rain_t'][rng.random(_shape(D2)) < 0.05] = f32(0.1)
   out['rain_holes'] = rng.random(_shape(D2)) < 0.06
   out['rain_p_holes'] = rng.random(_shape(D2)) < 0.03
+  # SEEPS climatology rows, stored (hour, dayofyear, longitude, latitude) as in
+  # the reference's docstring (categorical.py:141-152).  Wet thresholds on the
+  # quarter grid of the rain fields (so `x >= wet` is hit exactly), a few equal
+  # to the dry threshold (0.25: a value can then be dry AND heavy); dry
+  # fractions partly outside [0.1, 0.85] and NaN at some points.
+  shape = (4, len(DOY_USED), NLON, NLAT)
+  wet_thr = (np.round(rng.uniform(0.5, 3.0, shape) * 4) / 4).astype(f32)
+  wet_thr[rng.random(shape) < 0.03] = f32(0.25)
+  out['seeps_threshold_rows'] = wet_thr
+  dry_frac = rng.uniform(0.0, 1.0, (NLON, NLAT))[None, None] + rng.normal(
+      0, 0.02, shape)
+  dry_frac[:, :, rng.random((NLON, NLAT)) < 0.04] = np.nan
+  out['seeps_dry_fraction_rows'] = dry_frac.astype(f32)
   return out
+
+
+SEEPS_DRY_THRESHOLD_MM = 250.0   # 0.25 in the unit of the rain fields
 
 
 RAIN_THRESHOLDS = [0.0, 0.1, 0.5, 2.0, 1e9]
@@ -399,6 +415,38 @@ def build_cases(ns, inputs):
   yield cat_case('cat/error_exceedance_nan_default_keep_init',
                  use_metrics=exceedance, kind='exceedance', nan_targets=True,
                  reduce_dims=['latitude', 'longitude'])
+
+  # -- SEEPS (categorical.py:104-304) -----------------------------------------
+  var = 'total_precipitation_6hr'
+  seeps_dims = ('hour', 'dayofyear', 'longitude', 'latitude')
+  seeps_coords = {'hour': HOURS, 'dayofyear': np.arange(1, 367),
+                  'longitude': LON, 'latitude': LAT}
+
+  def seeps_var(rows):
+    full = np.full((4, 366, NLON, NLAT), np.nan, np.float32)
+    full[:, DOY_USED - 1] = rows
+    return xr.DataArray(full, seeps_dims, coords=seeps_coords)
+
+  seeps_climatology = xr.Dataset({
+      f'{var}_seeps_threshold': seeps_var(inputs['seeps_threshold_rows']),
+      f'{var}_seeps_dry_fraction': seeps_var(
+          inputs['seeps_dry_fraction_rows'])})
+  seeps_metrics = {'seeps': cat.SEEPS(
+      variables=[var], climatology=seeps_climatology,
+      dry_threshold_mm=[SEEPS_DRY_THRESHOLD_MM], min_p1=[0.1], max_p1=[0.85])}
+  yield cat_case('seeps/masked_weighted', use_metrics=seeps_metrics,
+                 kind='seeps', masked=True)
+  yield cat_case('seeps/nan_targets_masked', use_metrics=seeps_metrics,
+                 kind='seeps', nan_targets=True, masked=True)
+  yield cat_case('seeps/nan_both_masked_keep_init', use_metrics=seeps_metrics,
+                 kind='seeps', nan_targets=True, nan_predictions=True,
+                 masked=True, reduce_dims=['latitude', 'longitude'])
+  yield cat_case('seeps/regions_masked', use_metrics=seeps_metrics,
+                 kind='seeps', bins=['regions_land'], masked=True)
+  yield cat_case('seeps/default_propagates', use_metrics=seeps_metrics,
+                 kind='seeps')
+  yield cat_case('seeps/skipna_unweighted', use_metrics=seeps_metrics,
+                 kind='seeps', nan_targets=True, skipna=True, weighted=False)
 
 
 def _make_bins(ns, names, land_values):

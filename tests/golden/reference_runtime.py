@@ -15,6 +15,7 @@ stand-ins under those module names *in this process only*:
   opt_einsum, ``where`` / ``mean`` / ``var`` / ``sum`` = the NumPy functions
   xarray dispatches to), plus the few extra calls the reference's hot path
   makes (vectorised ``.sel`` with labelled indexers, ``.compute()``,
+  ``xr.concat`` along a labelled new dim, ``xr.dot(dims=)``,
   ``xr.set_options``, list indexing of a Dataset, ``xr.core.accessor_dt``);
 * ``jax`` / ``jax.numpy``: NumPy (only referenced by RMSE/ACC value functions
   for the autodiff tracing hook, metrics/deterministic.py:18-20);
@@ -138,6 +139,23 @@ def install():
   def set_options(**unused_kwargs):
     yield
 
+  def concat(arrays, dim):
+    """xr.concat; ``dim`` may be a DataArray that names and labels the new
+    dimension (categorical.py:223-226,283-285)."""
+    if isinstance(dim, xl.DataArray):
+      name = dim.dims[0]
+      out = xl.concat(list(arrays), name)
+      out._coords[name] = xl.DataArray(  # pylint: disable=protected-access
+          dim.to_numpy(), (name,), name=name)
+      return out
+    return xl.concat(list(arrays), dim)
+
+  def dot(*arrays, dim=None, dims=None):
+    """xr.dot with the older ``dims=`` spelling (categorical.py:290)."""
+    return xl.dot(*arrays, dim=dims if dim is None else dim)
+
+  xr.concat = concat
+  xr.dot = dot
   xr.Dataset = Dataset
   xr.DataTree = DataTree
   # binning.py:376-391 dispatches on the accessor type

@@ -342,3 +342,83 @@ def test_error_exceedance_with_interpreted_plans(monkeypatch):
     expected = np.nanmean(field, axis=(1, 2))
   np.testing.assert_allclose(got.values[:, :2], expected[:, :2], rtol=1e-12)
   assert np.isnan(got.values[:, 2]).all()   # 0 / 0: nothing valid
+
+
+# ---------------------------------------------------------------------------
+# SEEPS: constructor, names, host-side parameters
+# ---------------------------------------------------------------------------
+
+
+def test_seeps_names_parameters_and_p1_cache():
+  from weatherbenchx_b200.metrics import categorical as cat
+  variables = ['total_precipitation_6hr', 'total_precipitation_24hr']
+  seeps = cat.SEEPS(variables=variables, climatology={})
+  assert seeps.unique_name == (
+      'SEEPS_total_precipitation_6hr_total_precipitation_24hr_'
+      'dry_threshold_mm_0.25_0.25_min_p1_0.1_0.1_max_p1_0.85_0.85')
+  seeps = cat.SEEPS(variables=variables[:1], climatology={},
+                    dry_threshold_mm=[0.1], min_p1=[0.2], max_p1=[0.7])
+  assert seeps.unique_name == (
+      'SEEPS_total_precipitation_6hr_dry_threshold_mm_0.1_min_p1_0.2_'
+      'max_p1_0.7')
+  with pytest.raises(AssertionError):
+    cat.SEEPS(variables=variables, climatology={}, min_p1=[0.1])
+  # p1 = nanmean over (hour, dayofyear) in the input dtype, memoised per array
+  rng = np.random.default_rng(0)
+  values = rng.random((4, 6, 5, 3)).astype(np.float32)
+  values[1, 2] = np.nan                      # a missing day is skipped
+  values[:, :, 4, 2] = np.nan                # an all-NaN point stays NaN
+  frac = xl.DataArray(values, ('hour', 'dayofyear', 'longitude', 'latitude'))
+  p1 = cat._dry_fraction_mean(frac)
+  assert p1.dims == ('longitude', 'latitude') and p1.dtype == np.float32
+  np.testing.assert_array_equal(
+      p1.values, oracle.seeps_p1(values, (0, 1)))
+  assert np.isnan(p1.values[4, 2]) and not np.isnan(p1.values[0, 0])
+  assert cat._dry_fraction_mean(frac) is p1
+  with pytest.raises(ValueError):
+    cat._dry_fraction_mean(xl.DataArray(values[0], ('dayofyear', 'longitude',
+                                                    'latitude')))
+
+
+def test_seeps_mask_combination(monkeypatch):
+  """categorical.py:296-304: the p1 range mask, combined with the mask of the
+  predictions OR the targets; both is an error."""
+  from weatherbenchx_b200.metrics import categorical as cat
+  wbx_emulator.installed(monkeypatch)
+  lat, lon = np.linspace(-80, 80, 4), np.arange(8) * 45.0
+  init = np.datetime64('2021-03-01T00', 'ns') + np.arange(2) * np.timedelta64(
+      1, 'D')
+  lead = (np.arange(2) * np.timedelta64(12, 'h')).astype('timedelta64[ns]')
+  dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+  coords = {'init_time': init, 'lead_time': lead, 'latitude': lat,
+            'longitude': lon}
+  rng = np.random.default_rng(2)
+  field = lambda: xl.DataArray(  # noqa: E731
+      rng.random((2, 2, 4, 8)).astype(np.float32), dims, coords=coords,
+      name='rain')
+  cdims = ('hour', 'dayofyear', 'latitude', 'longitude')
+  ccoords = {'hour': [0, 12], 'dayofyear': np.arange(1, 367), 'latitude': lat,
+             'longitude': lon}
+  frac = np.broadcast_to(np.linspace(0, 1, 32, dtype=np.float32).reshape(4, 8),
+                         (2, 366, 4, 8))
+  clim = xl.Dataset({
+      'rain_seeps_dry_fraction': xl.DataArray(frac, cdims, coords=ccoords),
+      'rain_seeps_threshold': xl.DataArray(
+          np.full((2, 366, 4, 8), 0.5, np.float32), cdims, coords=ccoords)})
+  seeps = cat.SEEPS(variables=['rain'], climatology=clim, dry_threshold_mm=100)
+  in_range = (frac[0, 0] >= np.float32(0.1)) & (frac[0, 0] <= np.float32(0.85))
+  p, t = field(), field()
+  stat = seeps.compute({'rain': p}, {'rain': t})['rain']
+  assert stat.dims == dims and stat.is_lazy
+  assert stat.coords['mask'].dims == ('latitude', 'longitude')
+  np.testing.assert_array_equal(stat.coords['mask'].values, in_range)
+  holes = rng.random((2, 2, 4, 8)) < 0.3
+  t_masked = t.assign_coords(mask=xl.DataArray(~holes, dims))
+  stat = seeps.compute({'rain': p}, {'rain': t_masked})['rain']
+  assert stat.coords['mask'].dims == dims
+  np.testing.assert_array_equal(stat.coords['mask'].values, ~holes & in_range)
+  p_masked = p.assign_coords(mask=xl.DataArray(~holes, dims))
+  stat = seeps.compute({'rain': p_masked}, {'rain': t})['rain']
+  np.testing.assert_array_equal(stat.coords['mask'].values, ~holes & in_range)
+  with pytest.raises(ValueError, match='Both predictions and targets'):
+    seeps.compute({'rain': p_masked}, {'rain': t_masked})

@@ -1,6 +1,6 @@
 """Parity against vectors produced by the reference's own code.
 
-``tests/golden/reference_golden.npz`` holds, for 50 evaluation cases, the
+``tests/golden/reference_golden.npz`` holds, for 56 evaluation cases, the
 AggregationState (sum_weighted_statistics / sum_weights per statistic and
 variable) and the metric values that the UNMODIFIED modules of
 /root/reference/weatherbenchX returned in the build container
@@ -198,7 +198,26 @@ def _oracle_fields(spec, inputs):
     if spec['nan_targets']:
       t = cases.with_nan(t, inputs['rain_holes'])
       mask = ~inputs['rain_holes']
-    if spec['kind'] == 'exceedance':
+    if spec['kind'] == 'seeps':
+      # climatology rows are stored (hour, dayofyear, longitude, latitude);
+      # gather the wet threshold of every valid time, p1 = nanmean over time
+      doy, hour = oracle.dayofyear_and_hour(
+          cases.INIT[:, None] + cases.LEAD[None, :])
+      rows = inputs['seeps_threshold_rows']
+      doy_pos = np.searchsorted(cases.DOY_USED, doy)
+      assert np.array_equal(cases.DOY_USED[doy_pos], doy)
+      wet = rows[np.searchsorted(cases.HOURS, hour), doy_pos]  # [i, l, lon, lat]
+      wet = np.swapaxes(wet, -1, -2)
+      p1 = oracle.seeps_p1(inputs['seeps_dry_fraction_rows'], (0, 1)).T
+      field, p1_mask = oracle.seeps(
+          p, t, wet, p1, dry_threshold_mm=cases.SEEPS_DRY_THRESHOLD_MM)
+      full_mask = np.broadcast_to(p1_mask, field.shape)
+      if mask is not None:   # categorical.py:296-302
+        full_mask = full_mask & mask
+      name = ('SEEPS_total_precipitation_6hr_dry_threshold_mm_'
+              f'{cases.SEEPS_DRY_THRESHOLD_MM}_min_p1_0.1_max_p1_0.85')
+      out[(name, var)] = (field, cases.D2, full_mask)
+    elif spec['kind'] == 'exceedance':
       dims = cases.D2 + ('error_exceedance_thresholds',)
       field = oracle.error_exceedance(p, t, cases.EXCEEDANCE_THRESHOLDS)
       out[('ErrorExceedance', var)] = (field, dims, mask)
@@ -288,7 +307,7 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
 
 def test_fixture_is_complete(golden):
   names = [str(n) for n in golden['cases']]
-  assert len(names) == 50 and len(set(names)) == 50
+  assert len(names) == 56 and len(set(names)) == 56
   for case in names:
     assert _case_keys(golden, case, 'sws'), case
     assert _case_keys(golden, case, 'value'), case
@@ -376,6 +395,9 @@ def test_oracle_reproduces_reference_values(golden, inputs):
       elif spec['family'] == 'cat':
         if metric == 'exceedance':
           value, dims = mean(case, spec, fields, 'ErrorExceedance', var)
+        elif metric == 'seeps':
+          stat = next(k[0] for k in fields if k[0].startswith('SEEPS_'))
+          value, dims = mean(case, spec, fields, stat, var)
         else:
           suffix = next(k[0] for k in fields if k[0].startswith(
               'TruePositives_'))[len('TruePositives_'):]
@@ -500,7 +522,10 @@ CASE_NAMES = [
     'cat/table_by_init_hour', 'cat/table_regions',
     'cat/predictions_thresholded_binary_targets', 'cat/error_exceedance',
     'cat/error_exceedance_nan_skipna',
-    'cat/error_exceedance_nan_default_keep_init']
+    'cat/error_exceedance_nan_default_keep_init',
+    'seeps/masked_weighted', 'seeps/nan_targets_masked',
+    'seeps/nan_both_masked_keep_init', 'seeps/regions_masked',
+    'seeps/default_propagates', 'seeps/skipna_unweighted']
 
 
 def test_case_names_cover_the_fixture(golden):
@@ -546,9 +571,16 @@ def _run_product_case(golden, inputs, case, space):
                   key)
 
 
+# The SEEPS cases run from tests/test_zz_gpu_seeps.py (last file of the
+# session): their elementwise kernel was written after the final GPU session of
+# round 1 and has not run on hardware yet.
+SEEPS_CASES = [c for c in CASE_NAMES if c.startswith('seeps/')]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('space', ['host', 'device'])
-@pytest.mark.parametrize('case', CASE_NAMES)
+@pytest.mark.parametrize('case',
+                         [c for c in CASE_NAMES if c not in SEEPS_CASES])
 def test_cuda_path_reproduces_reference(golden, inputs, case, space):
   """State and values of the reference, from the CUDA path, for every case."""
   _run_product_case(golden, inputs, case, space)

@@ -1,8 +1,8 @@
 """NumPy interpreter of the C ABI's plan contract (TEST INFRASTRUCTURE).
 
-``installed(monkeypatch)`` replaces ``_cabi.get_context``, ``_cabi.DetPlan``
-and ``_cabi.CrpsPlan`` -- the three names through which the host side reaches
-the CUDA library -- by stand-ins that execute the job tables the planner built
+``installed(monkeypatch)`` replaces ``_cabi.get_context``, ``_cabi.DetPlan``,
+``_cabi.CrpsPlan`` and ``engine.seeps_field`` -- the names through which the
+host side reaches the CUDA library on host-resident data -- by stand-ins that execute the job tables the planner built
 (``include/wbx_b200.h``: wbx_det_desc / wbx_crps_desc) with NumPy on HOST
 addresses.  Everything above the C ABI runs unmodified: statistic classes, the
 Aggregator's grouping of statistics into launches, the planner (slab layout,
@@ -188,10 +188,60 @@ class CrpsPlan:
     pass
 
 
+def seeps_field(predictions, targets, wet_threshold, p1, dry_threshold,
+                device=None):
+  """Host stand-in for ``engine.seeps_field`` (wbx_seeps_elementwise + the
+  device gather of the wet threshold): same arguments, same labelled result,
+  values from the documented per-point contract of include/wbx_b200.h."""
+  from weatherbenchx_b200 import xarray_lite as xl
+  dims = predictions.dims + tuple(
+      d for d in targets.dims if d not in predictions.dims)
+  sizes = dict(targets.sizes, **predictions.sizes)
+
+  def expand(da):
+    order = [d for d in dims if d in da.dims]
+    arr = da.transpose(*order).to_numpy()
+    shape = [sizes[d] if d in order else 1 for d in dims]
+    return np.broadcast_to(arr.reshape(shape), [sizes[d] for d in dims])
+
+  ac = wet_threshold
+  clim = ac.climatology
+  front = list(ac.clim_time_dims)
+  rest = [d for d in clim.dims if d not in front]
+  arr = clim.transpose(*(front + rest)).to_numpy()
+  gathered = arr[tuple(ac.positions[d] for d in front)]
+  wet = expand(xl.DataArray(gathered, tuple(ac.time_dims) + tuple(rest)))
+  p = expand(predictions).astype(np.float32)
+  t = expand(targets).astype(np.float32)
+  q = expand(p1).astype(np.float32)
+  thr = np.float32(dry_threshold)
+  with np.errstate(all='ignore'):
+    def cats(x):
+      return [x <= thr, (x > thr) & (x < wet), x >= wet]
+    one_minus, two_plus = np.float32(1) - q, np.float32(2) + q
+    inv_p1, three_over = np.float32(1) / q, np.float32(3) / two_plus
+    half = np.float32(0.5)
+    zero = np.zeros_like(q)
+    score = [[zero, half * (1 / one_minus), half * (4 / one_minus)],
+             [half * inv_p1, zero, half * (3 / one_minus)],
+             [half * (inv_p1 + three_over), half * three_over, zero]]
+    acc = np.zeros(p.shape, np.float64)
+    for f, fc in enumerate(cats(p)):
+      for k, tc in enumerate(cats(t)):
+        acc += (fc & tc).astype(np.float64) * score[f][k].astype(np.float64)
+  out = acc.astype(np.float32)
+  out[np.isnan(p) | np.isnan(t) | np.isnan(q)] = np.nan
+  coords = xl._merge_coords(predictions, targets, dims)  # pylint: disable=protected-access
+  coords.pop('mask', None)
+  return xl.DataArray(out, dims, coords=coords, name=predictions.name)
+
+
 def installed(monkeypatch):
-  """Routes the host side's three entry points to the interpreter."""
+  """Routes the host side's entry points to the interpreter."""
+  from weatherbenchx_b200 import engine
   ctx = _Context()
   monkeypatch.setattr(_cabi, 'get_context', lambda device=None: ctx)
   monkeypatch.setattr(_cabi, 'DetPlan', DetPlan)
   monkeypatch.setattr(_cabi, 'CrpsPlan', CrpsPlan)
+  monkeypatch.setattr(engine, 'seeps_field', seeps_field)
   return ctx

@@ -29,7 +29,7 @@ def sources() -> list[pathlib.Path]:
 
 def _fingerprint() -> str:
   h = hashlib.sha256()
-  for path in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.inc')) +
+  for path in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.inc')) + list(CSRC.glob('*.h')) +
                      list(INCLUDE.glob('*.h'))):
     h.update(path.name.encode())
     h.update(path.read_bytes())

@@ -185,6 +185,9 @@ SIGNATURES = {
                                    ctypes.c_float, c_void_p, c_void_p, c_int64,
                                    c_void_p]),
     'wbx_struct_layout': (c_int, [c_int32, POINTER(c_uint64), c_int32]),
+    'wbx_seeps_elementwise': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_int64, ctypes.c_float,
+                                      c_int64, c_void_p]),
     'wbx_crps_plan_create': (c_int, [c_void_p, POINTER(CrpsDesc),
                                      POINTER(c_void_p)]),
     'wbx_crps_plan_destroy': (c_int, [c_void_p, c_void_p]),
@@ -432,6 +435,14 @@ def xf_elementwise(ctx: Context, xform: int, slot: int, thr_pred: float,
   check(ctx.lib.wbx_xf_elementwise(
       ctx.handle, xform, slot, float(thr_pred), float(thr_target),
       c_void_p(pred_ptr), c_void_p(target_ptr or 0), n, c_void_p(out_ptr)))
+
+
+def seeps_elementwise(ctx: Context, pred_ptr: int, target_ptr: int,
+                      wet_ptr: int, p1_ptr: int, p1_len: int,
+                      dry_threshold: float, n: int, out_ptr: int):
+  check(ctx.lib.wbx_seeps_elementwise(
+      ctx.handle, c_void_p(pred_ptr), c_void_p(target_ptr), c_void_p(wet_ptr),
+      c_void_p(p1_ptr), p1_len, float(dry_threshold), n, c_void_p(out_ptr)))
 
 
 def struct_layout(which: int) -> list:

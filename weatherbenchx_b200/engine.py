@@ -1105,6 +1105,95 @@ def passthrough(source: xl.DataArray, other: xl.DataArray,
 
 
 # ---------------------------------------------------------------------------
+# SEEPS field (categorical.SEEPS)
+# ---------------------------------------------------------------------------
+
+
+def _gather_aligned(ac: AlignedClimatology, device=None):
+  """``climatology.sel(dayofyear=..., hour=...)`` as a device gather; returns
+  (tensor, dims) with the prediction time dims first (base.py:383-403)."""
+  torch = _torch()
+  clim = to_device(_normalise(ac.climatology, 'field'), device)
+  ct = clim.data
+  cdims = list(clim.dims)
+  front = list(ac.clim_time_dims)
+  rest = [d for d in cdims if d not in front]
+  ct = ct.permute(*[cdims.index(d) for d in front + rest])
+  index = tuple(torch.as_tensor(ac.positions[d], device=ct.device)
+                for d in front)
+  return ct[index], tuple(ac.time_dims) + tuple(rest)
+
+
+def seeps_field(predictions: xl.DataArray, targets: xl.DataArray,
+                wet_threshold: AlignedClimatology, p1: xl.DataArray,
+                dry_threshold: float, device: int | None = None
+                ) -> xl.DataArray:
+  """Per-point SEEPS (categorical.py:243-290) on the GPU (wbx_seeps_elementwise).
+
+  ``wet_threshold``: the ``*_seeps_threshold`` climatology with the gather that
+  aligns it to the valid times; ``p1``: host float32 dry fraction per grid
+  point, NaN where the point is masked out; ``dry_threshold`` in field units.
+  Returns a device-backed DataArray with the dims of predictions (+ extra
+  target dims) and the merged coordinates of both inputs (no mask).
+  """
+  torch = _torch()
+  dims = predictions.dims + tuple(
+      d for d in targets.dims if d not in predictions.dims)
+  sizes = dict(targets.sizes, **predictions.sizes)
+  for d, n in wet_threshold.sizes.items():
+    if d not in sizes or sizes[d] != n:
+      raise ValueError(
+          f'seeps threshold climatology: dim {d!r} (size {n}) does not match '
+          f'the predictions {sizes}')
+  if not set(p1.dims) <= set(dims):
+    raise ValueError(f'dry fraction dims {p1.dims} not in the data dims {dims}')
+  xl._check_index_coords(predictions, targets)  # pylint: disable=protected-access
+  xl._check_index_coords(predictions, p1)  # pylint: disable=protected-access
+  p = _broadcast_device(predictions, dims, sizes, device)
+  t = _broadcast_device(targets, dims, sizes, device)
+  gathered, gdims = _gather_aligned(wet_threshold, device)
+  wet = _broadcast_device(xl.DataArray(gathered, gdims), dims, sizes, device)
+  grid = tuple(d for d in dims if d in p1.dims)
+  if grid and tuple(dims[-len(grid):]) == grid:
+    # the usual case: p1 lives on the trailing (grid) dims and is a slab the
+    # fields repeat over
+    p1_t = torch.from_numpy(np.ascontiguousarray(
+        p1.transpose(*grid).to_numpy(), dtype=np.float32)).to(p.device)
+  else:
+    p1_t = _broadcast_device(p1, dims, sizes, device)
+  out = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+  ctx = _cabi.get_context(p.device.index)
+  ctx.use_torch_stream()
+  _cabi.seeps_elementwise(ctx, p.data_ptr(), t.data_ptr(), wet.data_ptr(),
+                          p1_t.data_ptr(), p1_t.numel(), dry_threshold,
+                          out.numel(), out.data_ptr())
+  coords = xl._merge_coords(predictions, targets, dims)  # pylint: disable=protected-access
+  coords.pop('mask', None)
+  return xl.DataArray(out, dims, coords=coords, name=predictions.name)
+
+
+def and_masks(small: xl.DataArray, full: xl.DataArray) -> xl.DataArray:
+  """``full & small`` by dim name, in the dim order of ``full`` (the p1 range
+  mask of SEEPS combined with the NaN mask of an input, categorical.py:
+  296-302); ``full`` may live on the device."""
+  if not set(small.dims) <= set(full.dims):
+    return small & full
+  shape = [full.sizes[d] if d in small.dims else 1 for d in full.dims]
+  order = [d for d in full.dims if d in small.dims]
+  small_np = np.ascontiguousarray(
+      small.transpose(*order).to_numpy()).astype(bool).reshape(shape)
+  if full.is_device:
+    torch = _torch()
+    payload = full.data
+    if payload.dtype != torch.bool:
+      payload = payload != 0
+    data = payload & torch.from_numpy(small_np).to(payload.device)
+  else:
+    data = full.to_numpy().astype(bool) & small_np
+  return xl.DataArray(data, full.dims)
+
+
+# ---------------------------------------------------------------------------
 # Ensemble mean field (wrappers.EnsembleMean)
 # ---------------------------------------------------------------------------
 
