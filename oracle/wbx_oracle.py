@@ -15,11 +15,11 @@ Pinning status
   container: ``tests/golden/make_reference_golden.py`` imports the unmodified
   modules of /root/reference/weatherbenchX (aggregation, weighting, binning,
   metrics/{base,deterministic,probabilistic,wrappers,categorical}) and stores
-  the AggregationState and metric values of 50 cases (all NaN modes, ACC with a
+  the AggregationState and metric values of 56 cases (all NaN modes, ACC with a
   day-of-year climatology across 29 February, regions / land-sea / band bins,
   both ensemble layouts, pairwise and sorted CRPS, skipna_ensemble, ensemble
   moments, ensemble-averaged and ensemble-mean metrics, thresholded
-  contingency tables and error exceedance, chunk combine, five latitude grids) in ``tests/golden/reference_golden.npz``.
+  contingency tables, error exceedance and SEEPS, chunk combine, five latitude grids) in ``tests/golden/reference_golden.npz``.
   ``tests/test_reference_golden.py`` checks that this oracle reproduces every
   stored array.  Caveat, stated wherever the vectors are used: xarray, jax and
   absl are not installable in the container, so the reference ran on the
