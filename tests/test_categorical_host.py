@@ -422,3 +422,84 @@ def test_seeps_mask_combination(monkeypatch):
   np.testing.assert_array_equal(stat.coords['mask'].values, ~holes & in_range)
   with pytest.raises(ValueError, match='Both predictions and targets'):
     seeps.compute({'rain': p_masked}, {'rain': t_masked})
+
+
+# ---------------------------------------------------------------------------
+# chunk driver: categorical metrics + SEEPS through run_pipeline
+# ---------------------------------------------------------------------------
+
+
+def test_pipeline_with_categorical_metrics_and_seeps(tmp_path, monkeypatch):
+  """Chunked evaluation (states combined by the zero-filled outer join along
+  init / lead / threshold) == one monolithic call; the files round-trip the
+  threshold dimension.  Real Aggregator, plans interpreted by the emulator."""
+  import test_pipeline as tp
+  from weatherbenchx_b200 import io_netcdf, pipeline, time_chunks
+  from weatherbenchx_b200.data_loaders import array_loaders
+  from weatherbenchx_b200.metrics import categorical as cat
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  preds, tgts = tp._datasets(('rain',))
+  cdims = ('dayofyear', 'hour', 'latitude', 'longitude')
+  ccoords = {'dayofyear': np.arange(1, 367), 'hour': np.array([0, 12]),
+             'latitude': tp.LAT, 'longitude': tp.LON}
+  rng = np.random.default_rng(9)
+  clim = xl.Dataset({
+      'rain_seeps_threshold': xl.DataArray(
+          rng.uniform(0.3, 1.5, (366, 2, tp.NLAT, tp.NLON)).astype(np.float32),
+          cdims, coords=ccoords),
+      'rain_seeps_dry_fraction': xl.DataArray(
+          np.broadcast_to(rng.uniform(0.05, 0.95, (tp.NLAT, tp.NLON)),
+                          (366, 2, tp.NLAT, tp.NLON)).astype(np.float32),
+          cdims, coords=ccoords)})
+  both = [wrappers.ContinuousToBinary('both', [-0.5, 0.0, 0.75], 'threshold')]
+  metrics = {
+      'csi': wrappers.WrappedMetric(categorical.CSI(), both),
+      'ets': wrappers.WrappedMetric(categorical.ETS(), both),
+      'exceed': deterministic.ErrorExceedance([0.1, 0.3]),
+      'seeps': cat.SEEPS(['rain'], clim, dry_threshold_mm=-200.0),
+      'rmse': deterministic.RMSE()}
+  aggregators = {
+      'time_mean': aggregation.Aggregator(
+          reduce_dims=['init_time', 'latitude', 'longitude'],
+          weigh_by=[weighting.GridAreaWeighting()], masked=True),
+      'per_init': aggregation.Aggregator(
+          reduce_dims=['latitude', 'longitude'], masked=True)}
+  out_path = str(tmp_path / 'metrics.nc')
+  state_path = str(tmp_path / 'state.nc')
+
+  def run(init_chunk, lead_chunk, **kw):
+    times = time_chunks.TimeChunks(tp.INIT, tp.LEAD,
+                                   init_time_chunk_size=init_chunk,
+                                   lead_time_chunk_size=lead_chunk)
+    return pipeline.run_pipeline(
+        times, array_loaders.PredictionsFromArrays(preds),
+        array_loaders.TargetsFromArrays(tgts), metrics, aggregators,
+        prefetch=0, **kw)
+
+  mono = run(None, None, require_output=False)
+  chunked = run(2, 3, out_path=out_path, aggregation_state_out_path=state_path)
+  names = {'csi.rain', 'ets.rain', 'exceed.rain', 'seeps.rain', 'rmse.rain'}
+  for agg_name in aggregators:
+    values, expected = chunked[agg_name][1], mono[agg_name][1]
+    assert set(values) == set(expected) == names
+    for k in names:
+      assert values[k].dims == expected[k].dims, k
+      np.testing.assert_allclose(values[k].values, expected[k].values,
+                                 rtol=1e-12, equal_nan=True, err_msg=k)
+    assert values['csi.rain'].dims[-1] == 'threshold'
+    assert values['exceed.rain'].dims[-1] == 'error_exceedance_thresholds'
+    assert np.isfinite(values['seeps.rain'].values).all()
+    stored = io_netcdf.open_dataset(str(tmp_path / f'metrics_{agg_name}.nc'))
+    for k in names:
+      np.testing.assert_array_equal(stored[k].values, values[k].values)
+    np.testing.assert_array_equal(
+        stored['csi.rain'].coords['threshold'].values, [-0.5, 0.0, 0.75])
+    state = pipeline.load_aggregation_state(
+        str(tmp_path / f'state_{agg_name}.nc'))
+    again = state.metric_values(metrics)
+    for k in names:
+      np.testing.assert_allclose(again[k].values, values[k].values,
+                                 rtol=1e-15, equal_nan=True)
+  assert chunked['per_init'][1]['csi.rain'].dims == (
+      'init_time', 'lead_time', 'threshold')
