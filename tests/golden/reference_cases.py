@@ -416,6 +416,14 @@ def build_cases(ns, inputs):
                  use_metrics=exceedance, kind='exceedance', nan_targets=True,
                  reduce_dims=['latitude', 'longitude'])
 
+  # error exceedance averaged over ensemble members (probabilistic.py:836-861)
+  ens_exceedance = {'ens_exceedance': prob.EnsembleErrorExceedance(
+      [1.0, 2.5, 6.0], ensemble_dim=ENS)}
+  yield ens_case('cat/ensemble_error_exceedance', x_major, ens_exceedance,
+                 family='ens_exceedance')
+  yield ens_case('cat/ensemble_error_exceedance_nan_members', x_nan,
+                 ens_exceedance, family='ens_exceedance', member_nan=True)
+
   # -- SEEPS (categorical.py:104-304) -----------------------------------------
   var = 'total_precipitation_6hr'
   seeps_dims = ('hour', 'dayofyear', 'longitude', 'latitude')

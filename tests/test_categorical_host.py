@@ -503,3 +503,50 @@ def test_pipeline_with_categorical_metrics_and_seeps(tmp_path, monkeypatch):
                                  rtol=1e-15, equal_nan=True)
   assert chunked['per_init'][1]['csi.rain'].dims == (
       'init_time', 'lead_time', 'threshold')
+
+
+def test_ensemble_error_exceedance_with_interpreted_plans(monkeypatch):
+  """probabilistic.py:836-861 without NaN members: ONE fused launch over
+  reduce_dims + [ensemble dim], divided by the member count."""
+  from weatherbenchx_b200.metrics import probabilistic
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  launches = []
+  real = _cabi.DetPlan
+
+  class Counting(real):
+
+    def __init__(self, ctx, **desc):
+      launches.append(desc)
+      super().__init__(ctx, **desc)
+
+  monkeypatch.setattr(_cabi, 'DetPlan', Counting)
+  rng = np.random.default_rng(12)
+  y = rng.normal(0, 1, (3, 6, 8)).astype(np.float32)
+  x = (y[:, None] + rng.normal(0, 1, (3, 5, 6, 8))).astype(np.float32)
+  dims = ('init_time', 'number', 'latitude', 'longitude')
+  coords = {'init_time': np.arange(3), 'number': np.arange(5),
+            'latitude': np.linspace(-75, 75, 6), 'longitude': np.arange(8) * 45.0}
+  X = xl.DataArray(x, dims, coords=coords, name='t')
+  Y = xl.DataArray(y, ('init_time', 'latitude', 'longitude'),
+                   coords={k: v for k, v in coords.items() if k != 'number'},
+                   name='t')
+  thresholds = [0.5, 1.5]
+  metric = probabilistic.EnsembleErrorExceedance(thresholds)
+  assert metric.unique_name == 'EnsembleErrorExceedance'
+  stat = metric.compute({'t': X}, {'t': Y})['t']
+  assert stat.dims == ('init_time', 'latitude', 'longitude',
+                       'error_exceedance_thresholds')
+  aggregator = aggregation.Aggregator(
+      reduce_dims=['latitude', 'longitude'],
+      weigh_by=[weighting.GridAreaWeighting()])
+  values = aggregation.compute_metric_values_for_single_chunk(
+      {'ee': metric}, aggregator, {'t': X}, {'t': Y})['ee.t']
+  assert len(launches) == 1 and launches[0]['xform'] == _cabi.XF_ERROR_EXCEEDANCE
+  field = oracle.error_exceedance(x, y[:, None], thresholds).mean(axis=1)
+  w = oracle.grid_area_weights(coords['latitude'])
+  sws, sw, out_dims = oracle.aggregate(
+      field, stat.dims, ['latitude', 'longitude'],
+      weights=[(w, ('latitude',))])
+  assert values.dims == tuple(out_dims)
+  np.testing.assert_allclose(values.values, sws / sw, rtol=1e-12)

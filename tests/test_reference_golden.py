@@ -1,6 +1,6 @@
 """Parity against vectors produced by the reference's own code.
 
-``tests/golden/reference_golden.npz`` holds, for 56 evaluation cases, the
+``tests/golden/reference_golden.npz`` holds, for 58 evaluation cases, the
 AggregationState (sum_weighted_statistics / sum_weights per statistic and
 variable) and the metric values that the UNMODIFIED modules of
 /root/reference/weatherbenchX returned in the build container
@@ -23,6 +23,7 @@ mixed sign); weight sums that are counts are compared exactly.
 
 import os
 import sys
+import warnings
 
 import numpy as np
 import pytest
@@ -258,6 +259,16 @@ def _oracle_fields(spec, inputs):
       se = oracle.squared_error(x, np.expand_dims(y, axis))
       out[('SquaredError_each_realization', 't2m')] = (
           se.mean(axis=axis), dims, None)
+    elif family == 'ens_exceedance':
+      # probabilistic.py:855-861: exceedance of every member, then xarray's
+      # NaN-skipping mean over the members
+      field = oracle.error_exceedance(x, np.expand_dims(y, axis),
+                                      [1.0, 2.5, 6.0])
+      with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out[('EnsembleErrorExceedance', 't2m')] = (
+            np.nanmean(field, axis=axis),
+            dims + ('error_exceedance_thresholds',), None)
     elif family == 'ens_mean':
       name = ("SquaredError_predictions_ensemble_mean_self._ensemble_dim="
               "'realization'_self._skipna=False")
@@ -307,7 +318,7 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
 
 def test_fixture_is_complete(golden):
   names = [str(n) for n in golden['cases']]
-  assert len(names) == 56 and len(set(names)) == 56
+  assert len(names) == 58 and len(set(names)) == 58
   for case in names:
     assert _case_keys(golden, case, 'sws'), case
     assert _case_keys(golden, case, 'value'), case
@@ -392,6 +403,8 @@ def test_oracle_reproduces_reference_values(golden, inputs):
         spa, _ = mean(case, spec, fields, 'SquaredPredictionAnomaly', var)
         sta, _ = mean(case, spec, fields, 'SquaredTargetAnomaly', var)
         value = oracle.acc_from_means(cov, spa, sta)
+      elif metric == 'ens_exceedance':
+        value, dims = mean(case, spec, fields, 'EnsembleErrorExceedance', var)
       elif spec['family'] == 'cat':
         if metric == 'exceedance':
           value, dims = mean(case, spec, fields, 'ErrorExceedance', var)
@@ -523,6 +536,8 @@ CASE_NAMES = [
     'cat/predictions_thresholded_binary_targets', 'cat/error_exceedance',
     'cat/error_exceedance_nan_skipna',
     'cat/error_exceedance_nan_default_keep_init',
+    'cat/ensemble_error_exceedance',
+    'cat/ensemble_error_exceedance_nan_members',
     'seeps/masked_weighted', 'seeps/nan_targets_masked',
     'seeps/nan_both_masked_keep_init', 'seeps/regions_masked',
     'seeps/default_propagates', 'seeps/skipna_unweighted']
@@ -571,16 +586,20 @@ def _run_product_case(golden, inputs, case, space):
                   key)
 
 
-# The SEEPS cases run from tests/test_zz_gpu_seeps.py (last file of the
-# session): their elementwise kernel was written after the final GPU session of
-# round 1 and has not run on hardware yet.
+# Cases added after the final GPU session of round 1 run from
+# tests/test_zz_gpu_seeps.py (last file of the session, marked as not yet
+# confirmed on hardware): SEEPS, whose elementwise kernel has never been
+# launched, and the ensemble error exceedance, a new composition of kernels
+# that each passed on the B200.
 SEEPS_CASES = [c for c in CASE_NAMES if c.startswith('seeps/')]
+LATE_CASES = SEEPS_CASES + ['cat/ensemble_error_exceedance',
+                            'cat/ensemble_error_exceedance_nan_members']
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('space', ['host', 'device'])
 @pytest.mark.parametrize('case',
-                         [c for c in CASE_NAMES if c not in SEEPS_CASES])
+                         [c for c in CASE_NAMES if c not in LATE_CASES])
 def test_cuda_path_reproduces_reference(golden, inputs, case, space):
   """State and values of the reference, from the CUDA path, for every case."""
   _run_product_case(golden, inputs, case, space)
@@ -591,7 +610,9 @@ def test_cuda_path_reproduces_reference(golden, inputs, case, space):
 NEEDS_DEVICE = {'ens/regions', 'ens/regions_nan_targets_masked',
                 'ens/ensemble_mean_rmse',
                 # region bins + thresholds: per-point fields, generic kernel
-                'cat/table_regions'}
+                'cat/table_regions',
+                # NaN members: the exact route through the member-mean field
+                'cat/ensemble_error_exceedance_nan_members'}
 
 
 @pytest.mark.parametrize('case',

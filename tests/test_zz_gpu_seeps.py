@@ -1,5 +1,6 @@
 """GPU tests of the SEEPS path (categorical.SEEPS -> wbx_seeps_elementwise ->
-fused masked reduction).
+fused masked reduction) and of probabilistic.EnsembleErrorExceedance (XF
+reduction over the members, per-point fallback when a member is NaN).
 
 STATUS: the elementwise kernel was written after the last GPU session of round
 1 (the GPU budget was spent), so these tests have NOT run on hardware yet.  What
@@ -39,9 +40,10 @@ def inputs(golden):
 
 
 @pytest.mark.parametrize('space', ['host', 'device'])
-@pytest.mark.parametrize('case', ref.SEEPS_CASES)
-def test_cuda_path_reproduces_reference_seeps(golden, inputs, case, space):
-  """State and values of the reference's own SEEPS, from the CUDA path."""
+@pytest.mark.parametrize('case', ref.LATE_CASES)
+def test_cuda_path_reproduces_reference_late_cases(golden, inputs, case, space):
+  """State and values of the reference's own SEEPS / EnsembleErrorExceedance,
+  from the CUDA path."""
   ref._run_product_case(golden, inputs, case, space)  # pylint: disable=protected-access
 
 

@@ -348,13 +348,15 @@ class Aggregator:
         not self.skipna):
       return _add_states([self.aggregate_stat_var(p) for p in stat.parts])
     if isinstance(stat, LazyEnsembleAveraged) and stat.is_lazy:
-      if self.skipna or stat.skipna_ensemble:
+      if self.skipna or (stat.skipna_ensemble and not stat.optimistic):
         return self._aggregate_generic(stat)
       nested = dataclasses.replace(
           self, reduce_dims=list(self.reduce_dims) + [stat.ensemble_dim])
       state = nested.aggregate_stat_var(stat.inner)
       if state is None:
         return None
+      if stat.skipna_ensemble and _has_nan(state.sum_weighted_statistics):
+        return self._aggregate_generic(stat)  # a NaN member: exact route
       scale = 1.0 / stat.n_members
       return AggregationState(state.sum_weighted_statistics * scale,
                               state.sum_weights * scale)
@@ -394,7 +396,7 @@ class Aggregator:
           continue
         stat = xl.as_data_array(stat)
         if isinstance(stat, LazyEnsembleAveraged) and stat.is_lazy:
-          if self.skipna or stat.skipna_ensemble:
+          if self.skipna or (stat.skipna_ensemble and not stat.optimistic):
             # NaN skipping happens per point after / inside the member mean
             results[stat_name][var] = self._aggregate_generic(stat)
           else:
@@ -531,6 +533,11 @@ class Aggregator:
         if sws is None:
           results[stat_name][var] = None
           continue
+        if stat.skipna_ensemble and _has_nan(sws):
+          # a NaN took part: the NaN-skipping member mean differs from the
+          # plain one, evaluate it per point
+          results[stat_name][var] = self._aggregate_generic(stat)
+          continue
         scale = 1.0 / stat.n_members
         results[stat_name][var] = AggregationState(
             sws * scale, state.sum_weights[stat_name][var] * scale)
@@ -544,6 +551,10 @@ class Aggregator:
       sws[stat_name] = {v: s.sum_weighted_statistics for v, s in ok.items()}
       sw[stat_name] = {v: s.sum_weights for v, s in ok.items()}
     return AggregationState(sws, sw)
+
+
+def _has_nan(da) -> bool:
+  return bool(np.isnan(xl.as_data_array(da).to_numpy()).any())
 
 
 def _add_states(states):

@@ -237,9 +237,15 @@ class LazyEnsembleAveraged(LazyStatistic):
 
   elementwise_of_operands = False
 
-  def __init__(self, inner: LazyStatistic, ensemble_dim, skipna_ensemble: bool):
+  def __init__(self, inner: LazyStatistic, ensemble_dim, skipna_ensemble: bool,
+               optimistic: bool = False):
     if ensemble_dim not in inner.dims:
       raise ValueError(f'Dimension {ensemble_dim} not found in {inner.dims}')
+    # optimistic: a NaN-skipping member mean (xarray's default ``.mean``) equals
+    # the plain one whenever no NaN takes part; the Aggregator then tries the
+    # fused reduction first and only falls back to the per-point mean field when
+    # the result shows that a NaN was met.
+    self.optimistic = bool(optimistic)
     self.kind = inner.kind
     self.inner = inner
     self.ensemble_dim = ensemble_dim

@@ -22,6 +22,7 @@ import numpy as np
 
 from weatherbenchx_b200.lazy import LazyEnsembleStatistic
 from weatherbenchx_b200.metrics import base
+from weatherbenchx_b200.metrics import deterministic
 
 ENSEMBLE_DIM = 'number'
 
@@ -63,6 +64,29 @@ class EnsembleAveragedStatistic(base.Statistic):
         out[var] = engine.ensemble_mean(da, self._ensemble_dim,
                                         skipna=self._skipna_ensemble)
     return out
+
+
+class EnsembleErrorExceedance(deterministic.ErrorExceedance):
+  """Error exceedance averaged over the ensemble members
+  (probabilistic.py:836-861: ``ErrorExceedance`` of every member, then
+  ``.mean(dim=ensemble_dim)`` -- xarray's NaN-skipping mean).
+
+  The member mean followed by the weighted sums equals the fused reduction over
+  ``reduce_dims + [ensemble_dim]`` divided by the member count as long as no
+  NaN takes part; the Aggregator evaluates it that way (one launch reading the
+  ensemble once per threshold) and recomputes through the per-point mean field
+  only if the result shows a NaN.
+  """
+
+  def __init__(self, thresholds, ensemble_dim: str = ENSEMBLE_DIM):
+    super().__init__(thresholds=thresholds)
+    self._ensemble_dim = ensemble_dim
+
+  def _compute_per_variable(self, predictions, targets):
+    from weatherbenchx_b200.lazy import LazyEnsembleAveraged  # pylint: disable=g-import-not-at-top
+    inner = super()._compute_per_variable(predictions, targets)
+    return LazyEnsembleAveraged(inner, self._ensemble_dim,
+                                skipna_ensemble=True, optimistic=True)
 
 
 class EnsembleAveragedMetric(base.Metric):
