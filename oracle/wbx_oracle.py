@@ -15,7 +15,7 @@ Pinning status
   container: ``tests/golden/make_reference_golden.py`` imports the unmodified
   modules of /root/reference/weatherbenchX (aggregation, weighting, binning,
   metrics/{base,deterministic,probabilistic,wrappers,categorical}) and stores
-  the AggregationState and metric values of 56 cases (all NaN modes, ACC with a
+  the AggregationState and metric values of 60 cases (all NaN modes, ACC with a
   day-of-year climatology across 29 February, regions / land-sea / band bins,
   both ensemble layouts, pairwise and sorted CRPS, skipna_ensemble, ensemble
   moments, ensemble-averaged and ensemble-mean metrics, thresholded
@@ -454,6 +454,26 @@ def passthrough(source: np.ndarray, other: np.ndarray,
   if copy_nans:
     result = np.where(~np.isnan(other), result, np.nan).astype(result.dtype)
   return result
+
+
+def relative_intensity(p: np.ndarray, t: np.ndarray, spatial_axes,
+                       mask: np.ndarray | None = None):
+  """metrics/deterministic.py:49-86.  Returns (result, result mask or None);
+  arithmetic in the input dtype, as NumPy does for the reference."""
+  axes = tuple(spatial_axes)
+  epsilon = 1e-6
+  with np.errstate(all='ignore'):
+    if mask is not None:
+      mask = mask == 1
+      count = mask.sum(axis=axes)
+      prediction_mean = np.where(mask, p, 0).sum(axis=axes) / count
+      prediction_mean = np.where(count > 0, prediction_mean, 0.0)
+      target_mean = np.where(mask, t, 0).sum(axis=axes) / count
+      target_mean = np.where(count > 0, target_mean, 0.0)
+      ratio = (prediction_mean + epsilon) / (target_mean + epsilon)
+      return np.abs(ratio - 1), (count > 0).astype(int)
+    ratio = (p.mean(axis=axes) + epsilon) / (t.mean(axis=axes) + epsilon)
+    return np.abs(ratio - 1), None
 
 
 # ---------------------------------------------------------------------------

@@ -416,6 +416,16 @@ def build_cases(ns, inputs):
                  use_metrics=exceedance, kind='exceedance', nan_targets=True,
                  reduce_dims=['latitude', 'longitude'])
 
+  # relative intensity of the spatial means (deterministic.py:28-88); the
+  # statistic has no grid dims left, the Aggregator reduces init_time
+  intensity = {'relative_intensity': det.RelativeIntensity()}
+  yield cat_case('cat/relative_intensity', use_metrics=intensity,
+                 kind='relative_intensity', reduce_dims=['init_time'],
+                 weighted=False)
+  yield cat_case('cat/relative_intensity_masked', use_metrics=intensity,
+                 kind='relative_intensity', reduce_dims=['init_time'],
+                 weighted=False, nan_targets=True, masked=True)
+
   # error exceedance averaged over ensemble members (probabilistic.py:836-861)
   ens_exceedance = {'ens_exceedance': prob.EnsembleErrorExceedance(
       [1.0, 2.5, 6.0], ensemble_dim=ENS)}

@@ -550,3 +550,49 @@ def test_ensemble_error_exceedance_with_interpreted_plans(monkeypatch):
       weights=[(w, ('latitude',))])
   assert values.dims == tuple(out_dims)
   np.testing.assert_allclose(values.values, sws / sw, rtol=1e-12)
+
+
+@pytest.mark.parametrize('masked', [False, True])
+def test_relative_intensity_with_interpreted_plans(masked, monkeypatch):
+  """deterministic.py:28-88: the spatial means are fused-kernel reductions."""
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  rng = np.random.default_rng(21)
+  shape = (3, 2, 6, 8)
+  dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+  coords = {'init_time': np.arange(3), 'lead_time': np.arange(2),
+            'latitude': np.linspace(-75, 75, 6), 'longitude': np.arange(8) * 45.0}
+  p = rng.gamma(1.0, 2.0, shape).astype(np.float32)
+  t = rng.gamma(1.0, 2.0, shape).astype(np.float32)
+  P = xl.DataArray(p, dims, coords=coords, name='rain')
+  T = xl.DataArray(t, dims, coords=coords, name='rain')
+  mask = None
+  if masked:
+    mask = rng.random(shape) < 0.7
+    mask[1, 0] = False                       # a slab with no valid point
+    t = np.where(mask, t, np.nan).astype(np.float32)
+    T = xl.DataArray(t, dims, coords=coords, name='rain').assign_coords(
+        mask=xl.DataArray(mask, dims))
+  stat = deterministic.RelativeIntensity().compute({'rain': P}, {'rain': T})
+  got = stat['rain']
+  assert got.dims == ('init_time', 'lead_time') and got.dtype == np.float32
+  want, want_mask = oracle.relative_intensity(p, t, (2, 3), mask)
+  np.testing.assert_allclose(got.values, want, rtol=1e-4, atol=2e-6)
+  if masked:
+    np.testing.assert_array_equal(got.coords['mask'].values, want_mask)
+    assert got.values[1, 0] == 0 and want_mask[1, 0] == 0
+  else:
+    assert 'mask' not in got.coords
+  # NaN propagates through the unmasked means (skipna=False)
+  p_nan = p.copy()
+  p_nan[2, 1, 3, 3] = np.nan
+  P_nan = xl.DataArray(p_nan, dims, coords=coords, name='rain')
+  got = deterministic.RelativeIntensity().compute({'rain': P_nan},
+                                                  {'rain': T})['rain']
+  want, _ = oracle.relative_intensity(p_nan, t, (2, 3), mask)
+  np.testing.assert_array_equal(np.isnan(got.values), np.isnan(want))
+  assert masked or np.isnan(got.values[2, 1])
+  with pytest.raises(ValueError, match='Failed to compute'):
+    metrics_base.compute_unique_statistics_for_all_metrics(
+        {'ri': deterministic.RelativeIntensity(('x', 'y'))}, {'rain': P},
+        {'rain': T})

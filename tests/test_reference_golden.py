@@ -1,6 +1,6 @@
 """Parity against vectors produced by the reference's own code.
 
-``tests/golden/reference_golden.npz`` holds, for 58 evaluation cases, the
+``tests/golden/reference_golden.npz`` holds, for 60 evaluation cases, the
 AggregationState (sum_weighted_statistics / sum_weights per statistic and
 variable) and the metric values that the UNMODIFIED modules of
 /root/reference/weatherbenchX returned in the build container
@@ -199,7 +199,10 @@ def _oracle_fields(spec, inputs):
     if spec['nan_targets']:
       t = cases.with_nan(t, inputs['rain_holes'])
       mask = ~inputs['rain_holes']
-    if spec['kind'] == 'seeps':
+    if spec['kind'] == 'relative_intensity':
+      field, field_mask = oracle.relative_intensity(p, t, (2, 3), mask)
+      out[('RelativeIntensity', var)] = (field, cases.D2[:2], field_mask)
+    elif spec['kind'] == 'seeps':
       # climatology rows are stored (hour, dayofyear, longitude, latitude);
       # gather the wet threshold of every valid time, p1 = nanmean over time
       doy, hour = oracle.dayofyear_and_hour(
@@ -318,7 +321,7 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
 
 def test_fixture_is_complete(golden):
   names = [str(n) for n in golden['cases']]
-  assert len(names) == 58 and len(set(names)) == 58
+  assert len(names) == 60 and len(set(names)) == 60
   for case in names:
     assert _case_keys(golden, case, 'sws'), case
     assert _case_keys(golden, case, 'value'), case
@@ -408,6 +411,8 @@ def test_oracle_reproduces_reference_values(golden, inputs):
       elif spec['family'] == 'cat':
         if metric == 'exceedance':
           value, dims = mean(case, spec, fields, 'ErrorExceedance', var)
+        elif metric == 'relative_intensity':
+          value, dims = mean(case, spec, fields, 'RelativeIntensity', var)
         elif metric == 'seeps':
           stat = next(k[0] for k in fields if k[0].startswith('SEEPS_'))
           value, dims = mean(case, spec, fields, stat, var)
@@ -536,6 +541,7 @@ CASE_NAMES = [
     'cat/predictions_thresholded_binary_targets', 'cat/error_exceedance',
     'cat/error_exceedance_nan_skipna',
     'cat/error_exceedance_nan_default_keep_init',
+    'cat/relative_intensity', 'cat/relative_intensity_masked',
     'cat/ensemble_error_exceedance',
     'cat/ensemble_error_exceedance_nan_members',
     'seeps/masked_weighted', 'seeps/nan_targets_masked',
@@ -593,7 +599,9 @@ def _run_product_case(golden, inputs, case, space):
 # that each passed on the B200.
 SEEPS_CASES = [c for c in CASE_NAMES if c.startswith('seeps/')]
 LATE_CASES = SEEPS_CASES + ['cat/ensemble_error_exceedance',
-                            'cat/ensemble_error_exceedance_nan_members']
+                            'cat/ensemble_error_exceedance_nan_members',
+                            'cat/relative_intensity',
+                            'cat/relative_intensity_masked']
 
 
 @pytest.mark.gpu
@@ -612,7 +620,9 @@ NEEDS_DEVICE = {'ens/regions', 'ens/regions_nan_targets_masked',
                 # region bins + thresholds: per-point fields, generic kernel
                 'cat/table_regions',
                 # NaN members: the exact route through the member-mean field
-                'cat/ensemble_error_exceedance_nan_members'}
+                'cat/ensemble_error_exceedance_nan_members',
+                # the statistic is a small host array: generic kernel
+                'cat/relative_intensity', 'cat/relative_intensity_masked'}
 
 
 @pytest.mark.parametrize('case',

@@ -7,8 +7,8 @@ AbsoluteError :103-112, SquaredError :115-123, SquaredPredictionAnomaly
 aliases Bias / MAE / MSE :305-307, RMSE :312-324, ACC :374-400 and
 PredictionActivity :403-425, plus PredictionPassthrough / TargetPassthrough
 :126-171 (aliases PredictionAverage / TargetAverage :308-309),
-WindVectorSquaredError :174-219, WindVectorRMSE :327-371 and ErrorExceedance
-:262-295.  unique_name of every statistic follows the reference.
+WindVectorSquaredError :174-219, WindVectorRMSE :327-371, ErrorExceedance
+:262-295 and RelativeIntensity :28-88.  unique_name of every statistic follows the reference.
 """
 
 from __future__ import annotations
@@ -22,6 +22,56 @@ from weatherbenchx_b200.lazy import LazyPassthrough
 from weatherbenchx_b200.lazy import LazyStatistic
 from weatherbenchx_b200.lazy import LazySumStatistic
 from weatherbenchx_b200.metrics import base
+
+
+class RelativeIntensity(base.PerVariableStatistic):
+  """``abs((mean(predictions) + eps) / (mean(targets) + eps) - 1)`` with the
+  means taken over ``spatial_dims`` (deterministic.py:28-88; for non-negative
+  fields such as precipitation).
+
+  The two spatial means are reductions of full fields, i.e. launches of the
+  fused kernel (unweighted sums and counts in float64); the ratio is formed on
+  the few numbers that remain.  With a ``mask`` coordinate on the targets the
+  means run over ``mask == 1`` only and the result carries ``mask = count > 0``
+  (:63-80).
+  """
+
+  def __init__(self, spatial_dims: Sequence[str] = ('latitude', 'longitude')):
+    self._spatial_dims = spatial_dims
+
+  def _compute_per_variable(self, predictions, targets):
+    from weatherbenchx_b200 import engine  # pylint: disable=g-import-not-at-top
+    predictions = xl.as_data_array(predictions)
+    targets = xl.as_data_array(targets)
+    spatial_dims = list(self._spatial_dims)
+    epsilon = 1e-6
+    masked = 'mask' in targets.coords
+
+    def sums(source):
+      # source - 0 against a shared zero slab; the coordinates (and so the
+      # mask) of the targets ride along
+      lazy = LazyPassthrough(source, targets)
+      res = engine.aggregate_fused([lazy], spatial_dims, masked=masked)
+      if res is None:
+        raise ValueError(
+            f'spatial dims {spatial_dims} not found in {source.dims}')
+      return res['Error']
+
+    prediction_sum, count = sums(predictions)
+    target_sum, _ = sums(targets)
+    if masked:
+      positive = count > 0
+      prediction_mean = (prediction_sum / count).where(positive, 0.0)
+      target_mean = (target_sum / count).where(positive, 0.0)
+    else:
+      prediction_mean = prediction_sum / count
+      target_mean = target_sum / count
+    ratio = (prediction_mean + epsilon) / (target_mean + epsilon)
+    result = abs(ratio - 1).astype(np.float32)
+    result.name = predictions.name
+    if masked:
+      result = result.assign_coords(mask=positive.astype(int))
+    return result
 
 
 class _FusedStatistic(base.PerVariableStatistic):
