@@ -326,3 +326,152 @@ def test_random_ensemble_requests_match_the_oracle(req, monkeypatch):
           got_ws, sws, rtol=1e-4, equal_nan=True, err_msg=name,
           atol=1e-4 * (finite.max() if finite.size else 0))
       np.testing.assert_allclose(got_w, sw, rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# categorical path: thresholds applied inside the reduction
+# ---------------------------------------------------------------------------
+
+
+@st.composite
+def categorical_requests(draw):
+  outer = list(draw(st.permutations(OUTER)))
+  outer = outer[:draw(st.integers(1, 3))]
+  grid = list(draw(st.permutations(GRID)))
+  dims = tuple(outer + grid)
+  reduce_dims = [d for d in outer if draw(st.booleans())] + list(GRID)
+  return dict(
+      dims=dims, reduce_dims=reduce_dims,
+      mode=draw(st.sampled_from(['propagate', 'masked', 'skipna',
+                                 'masked_skipna'])),
+      mask_on=draw(st.sampled_from(['targets', 'predictions'])),
+      weighted=draw(st.booleans()),
+      which=draw(st.sampled_from(['both', 'predictions', 'targets', 'none'])),
+      thresholds=draw(st.lists(st.sampled_from(
+          [-0.5, 0.0, 0.1, 0.25, 1.0, 7.0]), min_size=1, max_size=3,
+          unique=True)),
+      bins=draw(st.lists(st.sampled_from(['init_hour', 'lead_sets',
+                                          'level_sets', 'regions']),
+                         max_size=1)),
+      exceedance=draw(st.booleans()),
+      n_vars=draw(st.integers(1, 2)), seed=draw(st.integers(0, 2**16)))
+
+
+@settings(max_examples=200, deadline=None, derandomize=True,
+          suppress_health_check=[HealthCheck.filter_too_much,
+                                 HealthCheck.too_slow,
+                                 HealthCheck.function_scoped_fixture])
+@given(req=categorical_requests())
+def test_random_categorical_requests_match_the_oracle(req, monkeypatch):
+  """Contingency tables (inputs thresholded on either side, or binary already)
+  and error exceedance through the class surface, any dim order, NaN mode and
+  outer-dim binning, against the oracle's restatement of categorical.py /
+  wrappers.binarize_thresholds / deterministic.ErrorExceedance."""
+  from weatherbenchx_b200.metrics import categorical, wrappers
+  wbx_emulator.installed(monkeypatch)
+
+  def no_generic(*args, **kwargs):
+    raise _GenericNeedsGpu()
+  monkeypatch.setattr(generic, 'aggregate', no_generic)
+
+  dims, rng = req['dims'], np.random.default_rng(req['seed'])
+  shape = tuple(SIZES[d] for d in dims)
+  coords = {d: COORDS[d] for d in dims}
+  for needed, bin_name in (('init_time', 'init_hour'),
+                           ('lead_time', 'lead_sets'),
+                           ('level', 'level_sets')):
+    assume(needed in dims or bin_name not in req['bins'])
+  masked, skipna = 'masked' in req['mode'], 'skipna' in req['mode']
+  which, thresholds = req['which'], req['thresholds']
+  land = xl.DataArray(rng.random((6, 8)) < 0.5, GRID,
+                      coords={d: COORDS[d] for d in GRID})
+
+  def rain():
+    x = (np.round(rng.gamma(0.8, 1.5, shape) * 4) / 4 *
+         (rng.random(shape) < 0.6)).astype(np.float32)
+    x[rng.random(shape) < 0.05] = np.float32(0.1)
+    return x
+
+  predictions, targets, arrays = {}, {}, {}
+  for v in range(req['n_vars']):
+    p, t = rain(), rain()
+    # inputs that skip the transform are binary events already
+    if which in ('targets', 'none'):
+      p = (p > 0.25).astype(np.float32)
+    if which in ('predictions', 'none'):
+      t = (t > 0.25).astype(np.float32)
+    if req['mode'] != 'propagate':
+      t[rng.random(shape) < 0.1] = np.nan
+      if not masked:
+        p[rng.random(shape) < 0.05] = np.nan
+    mask = ~np.isnan(t) & (rng.random(shape) > 0.2)
+    P = xl.DataArray(p, dims, coords=coords, name=f'v{v}')
+    T = xl.DataArray(t, dims, coords=coords, name=f'v{v}')
+    if masked and req['mask_on'] == 'predictions':
+      P = P.assign_coords(mask=xl.DataArray(mask, dims))
+    if masked and req['mask_on'] == 'targets':
+      T = T.assign_coords(mask=xl.DataArray(mask, dims))
+    predictions[f'v{v}'], targets[f'v{v}'] = P, T
+    arrays[f'v{v}'] = (p, t, mask)
+  table = categorical.Accuracy()          # all four entries
+  if which == 'none':
+    metrics = {'accuracy': table}
+  else:
+    metrics = {'accuracy': wrappers.WrappedMetric(table, [
+        wrappers.ContinuousToBinary(which, thresholds, 'thr')])}
+  if req['exceedance']:
+    metrics['exceedance'] = deterministic.ErrorExceedance(thresholds)
+  bin_by = _make_bins(req['bins'], land)
+  aggregator = aggregation.Aggregator(
+      reduce_dims=req['reduce_dims'],
+      weigh_by=[weighting.GridAreaWeighting()] if req['weighted'] else None,
+      bin_by=bin_by or None, masked=masked, skipna=skipna)
+  statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+      metrics, predictions, targets)
+  try:
+    state = aggregator.aggregate_statistics(statistics)
+  except _GenericNeedsGpu:
+    assume(False)   # grid bins: per-point fields + generic kernel (GPU tests)
+
+  weights = []
+  if req['weighted']:
+    weights.append((oracle.grid_area_weights(COORDS['latitude']),
+                    ('latitude',)))
+  bin_masks = []
+  for b in bin_by:
+    m = b.create_bin_mask(predictions['v0'])
+    bin_masks.append((m.values, m.dims))
+  suffix = '' if which == 'none' else (
+      f'_{which}_thr=' + ','.join(str(x) for x in thresholds))
+  for var, (p, t, mask) in arrays.items():
+    bp = (oracle.binarize_thresholds(p, thresholds)
+          if which in ('both', 'predictions') else p)
+    bt = (oracle.binarize_thresholds(t, thresholds)
+          if which in ('both', 'targets') else t)
+    if which in ('predictions', 'targets'):
+      # the untransformed input broadcasts against the threshold dim
+      bp, bt = (bp, bt[..., None]) if which == 'predictions' else (
+          bp[..., None], bt)
+    bp, bt = np.broadcast_arrays(bp, bt)
+    fields = {f'{k}{suffix}': (v, dims + (('thr',) if which != 'none' else ()))
+              for k, v in oracle.contingency_table(bp, bt).items()}
+    if req['exceedance']:
+      fields['ErrorExceedance'] = (
+          oracle.error_exceedance(p, t, thresholds),
+          dims + ('error_exceedance_thresholds',))
+    for name, (value, vdims) in fields.items():
+      sws, sw, out_dims = oracle.aggregate(
+          value, vdims, req['reduce_dims'], weights=weights,
+          bin_masks=bin_masks, mask=mask if masked else None,
+          mask_dims=dims if masked else None, masked=masked, skipna=skipna)
+      got_ws = state.sum_weighted_statistics[name][var]
+      got_w = state.sum_weights[name][var]
+      assert sorted(got_ws.dims) == sorted(out_dims), (got_ws.dims, out_dims)
+      order = [got_ws.dims.index(d) for d in out_dims]
+      np.testing.assert_array_equal(
+          np.isnan(got_ws.values.transpose(order)), np.isnan(sws), err_msg=name)
+      np.testing.assert_allclose(got_ws.values.transpose(order), sws,
+                                 rtol=1e-9, atol=1e-9, equal_nan=True,
+                                 err_msg=name)
+      np.testing.assert_allclose(got_w.values.transpose(order), sw,
+                                 rtol=1e-12, atol=1e-12, err_msg=name)
