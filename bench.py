@@ -876,7 +876,11 @@ def run_b200(args):
   if world == 1 and not args.no_suite:
     del tgt, prd, host_p, host_t, preds, tgts, plan
     torch.cuda.empty_cache()
-    line['suite'] = run_suite(ctx, dev, peak)
+    try:
+      line['suite'] = run_suite(ctx, dev, peak)
+    except Exception as e:  # pylint: disable=broad-except
+      # the secondary workloads must never take the headline line down
+      line['suite_error'] = f'{type(e).__name__}: {e}'
   emit_line(line)
   if world > 1:
     dist.destroy_process_group()
