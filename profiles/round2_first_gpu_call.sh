@@ -3,10 +3,10 @@
 #
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash profiles/round2_first_gpu_call.sh'
 #
-# Round 1 ended with the categorical path verified on hardware (391 tests) but
-# not timed, and with the SEEPS kernel written but never launched.  This script
-# collects, in order of importance and with its own timeouts:
-#   1. the SEEPS GPU tests alone (they are xfail(strict=False): look for XPASS),
+# Round 1 ended with the categorical path and SEEPS verified on hardware (391 +
+# 23 tests) but not timed.  This script collects, in order of importance and
+# with its own timeouts:
+#   1. the SEEPS / late-case GPU tests alone,
 #   2. the whole GPU suite,
 #   3. bench.py (headline line + suite incl. the new `contingency_3thr` leg),
 #   4. the ncu launch list of a short bench run and one `--set full` capture of
@@ -16,7 +16,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 
-echo "== 1. SEEPS tests (expect XPASS)" | tee gpurun_out/r2_seeps_tests.log
+echo "== 1. SEEPS and late-case tests" | tee gpurun_out/r2_seeps_tests.log
 timeout 120 python -m pytest tests/test_zz_gpu_seeps.py -m gpu -q -rxX \
     -p no:cacheprovider >> gpurun_out/r2_seeps_tests.log 2>&1
 tail -15 gpurun_out/r2_seeps_tests.log

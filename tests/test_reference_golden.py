@@ -592,11 +592,9 @@ def _run_product_case(golden, inputs, case, space):
                   key)
 
 
-# Cases added after the final GPU session of round 1 run from
-# tests/test_zz_gpu_seeps.py (last file of the session, marked as not yet
-# confirmed on hardware): SEEPS, whose elementwise kernel has never been
-# launched, and the ensemble error exceedance, a new composition of kernels
-# that each passed on the B200.
+# Cases added late in round 1 run from tests/test_zz_gpu_seeps.py (SEEPS, the
+# ensemble error exceedance, relative intensity); they passed on the B200 in
+# their own run (profiles/gpu_tests_seeps_late_cases_r1.log).
 SEEPS_CASES = [c for c in CASE_NAMES if c.startswith('seeps/')]
 LATE_CASES = SEEPS_CASES + ['cat/ensemble_error_exceedance',
                             'cat/ensemble_error_exceedance_nan_members',

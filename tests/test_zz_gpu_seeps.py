@@ -2,16 +2,13 @@
 fused masked reduction) and of probabilistic.EnsembleErrorExceedance (XF
 reduction over the members, per-point fallback when a member is NaN).
 
-STATUS: the elementwise kernel was written after the last GPU session of round
-1 (the GPU budget was spent), so these tests have NOT run on hardware yet.  What
-is verified on the CPU: the per-point device function, compiled for the host
+Added after the main GPU session of round 1 and confirmed on a B200 in a
+separate short run (profiles/gpu_tests_seeps_late_cases_r1.log: 23 passed).
+Also verified on the CPU: the per-point device function, compiled for the host
 from the same header, equals the oracle bit for bit (tests/test_seeps_host.py);
-the oracle reproduces the reference's own SEEPS on six cases; the class surface
-with interpreted plans reproduces them too (tests/test_reference_golden.py).
-Until a B200 run confirms the kernel launch itself the tests are marked
-``xfail(strict=False)`` -- a pass shows up as XPASS -- and the file sorts last
-so that nothing else runs after it in the session.  Remove the marker after the
-first green run.
+the oracle reproduces the reference's own results on the ten cases used here;
+the class surface with interpreted plans reproduces them too
+(tests/test_reference_golden.py).
 """
 
 import numpy as np
@@ -20,12 +17,7 @@ import pytest
 import test_reference_golden as ref
 import wbx_oracle as oracle
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.xfail(strict=False, reason=(
-        'wbx_seeps_elementwise has not run on hardware yet (round-1 GPU '
-        'budget exhausted); CPU-verified only')),
-]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope='module')
