@@ -70,4 +70,7 @@ timeout 300 ncu --set full --clock-control none --import-source on \
     -k regex:seeps_elementwise_kernel -c 2 -o gpurun_out/r2_prof_seeps \
     python -m pytest tests/test_zz_gpu_seeps.py -m gpu -q -k bit_for_bit \
     -p no:cacheprovider > gpurun_out/r2_prof_seeps.log 2>&1
+echo "== 5. job-order experiment for K thresholds (engine.XF_L2_BLOCK_BYTES)"
+timeout 200 python profiles/exp_xf_l2.py > gpurun_out/r2_exp_xf_l2.log 2>&1
+tail -14 gpurun_out/r2_exp_xf_l2.log
 ls -la gpurun_out | tail -20

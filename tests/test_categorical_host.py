@@ -596,3 +596,64 @@ def test_relative_intensity_with_interpreted_plans(masked, monkeypatch):
     metrics_base.compute_unique_statistics_for_all_metrics(
         {'ri': deterministic.RelativeIntensity(('x', 'y'))}, {'rain': P},
         {'rain': T})
+
+
+@pytest.mark.parametrize('reduce_dims', [
+    ['init_time', 'lead_time', 'latitude', 'longitude'],
+    ['init_time', 'latitude', 'longitude'],
+    ['latitude', 'longitude']])
+@pytest.mark.parametrize('block_bytes', [1, 6 * 8 * 8 * 2, 10 ** 9])
+def test_l2_blocked_job_order_gives_the_same_sums(reduce_dims, block_bytes,
+                                                  monkeypatch):
+  """engine.XF_L2_BLOCK_BYTES (an experiment knob, off by default): blocks of
+  slabs are swept for all thresholds; a result cell is split into one launch
+  cell per block and folded on the host.  Same numbers, cells still dense and
+  non-decreasing, same slabs."""
+  wbx_emulator.installed(monkeypatch)
+  rng = np.random.default_rng(30)
+  shape = (5, 3, 6, 8)
+  dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+  coords = {'init_time': np.arange(5), 'lead_time': np.arange(3),
+            'latitude': np.linspace(-75, 75, 6), 'longitude': np.arange(8) * 45.0}
+  p = rng.gamma(1.0, 1.0, shape).astype(np.float32)
+  t = rng.gamma(1.0, 1.0, shape).astype(np.float32)
+  t[rng.random(shape) < 0.05] = np.nan
+  # lead_time first in memory order would make init_time part of the slab; keep
+  # (init, lead) as outer dims by making the arrays non-contiguous there
+  P = xl.DataArray(p, dims, coords=coords, name='v')
+  T = xl.DataArray(t, dims, coords=coords, name='v')
+  both = [wrappers.ContinuousToBinary('both', [0.2, 0.5, 1.0, 2.0], 'thr')]
+  metrics = {'acc': wrappers.WrappedMetric(categorical.Accuracy(), both)}
+  aggregator = aggregation.Aggregator(
+      reduce_dims=reduce_dims, weigh_by=[weighting.GridAreaWeighting()],
+      skipna=True)
+
+  def run():
+    engine.clear_plan_cache()
+    statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+        metrics, {'v': P}, {'v': T})
+    return aggregator.aggregate_statistics(statistics)
+
+  base = run()
+  monkeypatch.setattr(engine, 'XF_L2_BLOCK_BYTES', block_bytes)
+  stats = [c().compute({'v': both[0].transform_fn(P)},
+                       {'v': both[0].transform_fn(T)})['v']
+           for c in (categorical.TruePositives, categorical.TrueNegatives)]
+  spec = engine.build_fused_spec(
+      stats, reduce_dims, [weighting.GridAreaWeighting().weights(stats[0])],
+      skipna=True)
+  if spec.cell_fold is not None:
+    steps = np.diff(spec.cell)
+    assert spec.cell[0] == 0 and set(steps.tolist()) <= {0, 1}
+    assert spec.cell[-1] == len(spec.cell_fold) - 1 == spec.n_cells - 1
+    assert sorted(set(spec.cell_fold.tolist())) == list(
+        range(int(np.prod(spec.kept_shape))))
+  blocked = run()
+  for name, per_var in base.sum_weighted_statistics.items():
+    for var, da in per_var.items():
+      other = blocked.sum_weighted_statistics[name][var]
+      assert other.dims == da.dims
+      np.testing.assert_allclose(other.values, da.values, rtol=1e-12)
+      np.testing.assert_allclose(blocked.sum_weights[name][var].values,
+                                 base.sum_weights[name][var].values,
+                                 rtol=1e-12)

@@ -471,10 +471,22 @@ class FusedSpec:
   thr_pred: np.ndarray | None = None
   thr_target: np.ndarray | None = None
   kept_order: tuple | None = None
+  # launch cell -> result cell when a result cell is split over several launch
+  # cells (XF_L2_BLOCK_BYTES); the partial sums are added on the host
+  cell_fold: np.ndarray | None = None
 
 
 _SPEC_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
 _SPEC_CACHE_SIZE = 128
+
+# Experiment knob (off by default, not measured yet): a categorical launch with
+# K thresholds reads every slab K times, K passes apart, i.e. from HBM.  With a
+# positive value the job table is cut into blocks of slabs of about this many
+# bytes and each block is swept for all K thresholds before the next one, so
+# that the K - 1 re-reads can hit the 126 MB L2.  The kernel contract is
+# unchanged: a result cell is merely split into one launch cell per block and
+# the partial sums are added on the host in float64 (FusedSpec.cell_fold).
+XF_L2_BLOCK_BYTES = 0
 
 
 def build_fused_spec(stats: Sequence[LazyStatistic],
@@ -510,7 +522,8 @@ def build_fused_spec(stats: Sequence[LazyStatistic],
   guards += [cv.data for cv in first.coords.values()]
   key = (tuple(s.kind for s in stats), tuple(reduce_dims), bool(masked),
          bool(skipna), flags_extra, device, tuple(bin_dim_names),
-         first.group_key()[0] if getattr(first, 'xform', 0) else None,
+         (first.group_key()[0], XF_L2_BLOCK_BYTES)
+         if getattr(first, 'xform', 0) else None,
          first.dims, first.predictions.dims, first.targets.dims,
          tuple(first.coords), tuple(w.dims for w in weights),
          tuple(id(g) for g in guards))
@@ -746,6 +759,17 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
       values = getattr(first, name)
       if values is not None:
         job_tables[name] = np.ascontiguousarray(values[k_of_job], np.float32)
+  cell_fold = None
+  n_thr = sizes[first.threshold_dim] if (
+      xform and first.threshold_dim is not None) else 1
+  if (XF_L2_BLOCK_BYTES > 0 and n_thr > 1 and not outer_bins and
+      kept and kept[0] == first.threshold_dim):
+    order, cell, cell_fold = _l2_blocked_order(
+        cell, n_thr, max(1, XF_L2_BLOCK_BYTES // (ny * nx * 8)))
+    job_tables = {k: (None if v is None else np.ascontiguousarray(v[order]))
+                  for k, v in job_tables.items()}
+    n_cells = len(cell_fold)
+    cache_key = cache_key + ('l2-blocks', XF_L2_BLOCK_BYTES)
   outer_classes = None
   if outer_bins:
     outer_classes = _fold_outer_masks(
@@ -766,7 +790,7 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
       w_outer=job_tables['w_outer'], xform=xform,
       thr_pred=job_tables['thr_pred'], thr_target=job_tables['thr_target'],
       kept_order=(tuple(d for d in first.dims if d in kept) if xform
-                  else None),
+                  else None), cell_fold=cell_fold,
       w_y=_weight_vector(y_dims, sizes, per_dim), w_x=per_dim.get(x_dim),
       scalar=scalar, stat_mask=stat_mask, kept=kept, kept_shape=[sizes[d] for d in kept],
       coords=coords,
@@ -776,6 +800,31 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
            clim.climatology if clim is not None else None,
            first.coords.get('mask'))),
       cache_key=cache_key)
+
+
+def _l2_blocked_order(cell: np.ndarray, n_thr: int, block: int):
+  """Job order (block of slabs, threshold, slab) for a threshold-major job
+  table (threshold is the slowest job dim, ``cell = k * C0 + c0``).
+
+  Returns (order, launch_cell, fold): ``order`` permutes the job table,
+  ``launch_cell`` is the dense non-decreasing cell id of every permuted job --
+  one per (block, threshold, result cell) triple that occurs -- and
+  ``fold[launch cell]`` is the result cell its partial sums belong to.
+  """
+  n_jobs = len(cell)
+  per_thr = n_jobs // n_thr
+  base_cell = cell[:per_thr].astype(np.int64)            # c0 of every slab job
+  n_base_cells = int(base_cell.max()) + 1
+  order, key = [], []
+  for start in range(0, per_thr, block):
+    stop = min(per_thr, start + block)
+    for k in range(n_thr):
+      order.append(k * per_thr + np.arange(start, stop, dtype=np.int64))
+      key.append(k * n_base_cells + base_cell[start:stop])
+  order, key = np.concatenate(order), np.concatenate(key)
+  new_cell = np.concatenate([[True], key[1:] != key[:-1]])
+  launch_cell = (np.cumsum(new_cell) - 1).astype(np.int32)
+  return order, launch_cell, key[new_cell]
 
 
 def _derived_payloads(used, originals) -> tuple:
@@ -888,7 +937,17 @@ def run_fused_specs(items, device: int | None = None):
     lo = 0
     mult = 1 if first.classes is None else first.classes.n_classes
     for i, sp in zip(members, specs):
-      raw[i] = (ws[lo:lo + sp.n_cells * mult], w[lo:lo + sp.n_cells * mult])
+      part = (ws[lo:lo + sp.n_cells * mult], w[lo:lo + sp.n_cells * mult])
+      if sp.cell_fold is not None:
+        # partial sums of the launch cells of one result cell (NaN propagates)
+        n_final = int(np.prod(sp.kept_shape, dtype=np.int64))
+        folded = []
+        for arr in part:
+          out = np.zeros((n_final, arr.shape[1]), np.float64)
+          np.add.at(out, sp.cell_fold, arr)
+          folded.append(out)
+        part = tuple(folded)
+      raw[i] = part
       lo += sp.n_cells * mult
   results = []
   for idx, (spec, stats) in enumerate(items):
