@@ -717,3 +717,21 @@ def test_outer_bin_masks_fold_into_the_cell_table():
   assert out_dims == ('level',) + tuple(names)
   np.testing.assert_allclose(got, sws, rtol=1e-6, equal_nan=True)
   np.testing.assert_allclose(got_w, sw, rtol=1e-12)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/weatherbenchX'),
+                    reason='the reference tree is only present in the build '
+                           'container')
+def test_state_algebra_equals_the_reference_class():
+  """AggregationState sum / zero / outer join / mean_statistics /
+  sum_along_dims / dot / map side by side with the reference's own class
+  (aggregation.py:63-202), in a subprocess because importing the reference
+  needs stand-in modules registered under the names xarray / jax."""
+  import subprocess
+  import sys
+  script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                        'compare_state_algebra.py')
+  proc = subprocess.run([sys.executable, script], capture_output=True,
+                        text=True, timeout=300)
+  assert proc.returncode == 0, proc.stdout + proc.stderr
+  assert 'state algebra ok' in proc.stdout
