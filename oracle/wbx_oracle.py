@@ -15,7 +15,7 @@ Pinning status
   container: ``tests/golden/make_reference_golden.py`` imports the unmodified
   modules of /root/reference/weatherbenchX (aggregation, weighting, binning,
   metrics/{base,deterministic,probabilistic,wrappers,categorical}) and stores
-  the AggregationState and metric values of 60 cases (all NaN modes, ACC with a
+  the AggregationState and metric values of 62 cases (all NaN modes, ACC with a
   day-of-year climatology across 29 February, regions / land-sea / band bins,
   both ensemble layouts, pairwise and sorted CRPS, skipna_ensemble, ensemble
   moments, ensemble-averaged and ensemble-mean metrics, thresholded

@@ -16,7 +16,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 
-echo "== 1. SEEPS and late-case tests" | tee gpurun_out/r2_seeps_tests.log
+echo "== 1. SEEPS, late-case and unconfirmed-case tests (look for XPASS)" | tee gpurun_out/r2_seeps_tests.log
 timeout 120 python -m pytest tests/test_zz_gpu_seeps.py -m gpu -q -rxX \
     -p no:cacheprovider >> gpurun_out/r2_seeps_tests.log 2>&1
 tail -15 gpurun_out/r2_seeps_tests.log

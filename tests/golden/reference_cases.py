@@ -113,10 +113,14 @@ def make_inputs() -> dict:
       0, 0.02, shape)
   dry_frac[:, :, rng.random((NLON, NLAT)) < 0.04] = np.nan
   out['seeps_dry_fraction_rows'] = dry_frac.astype(f32)
+  # an ensemble of targets (e.g. perturbed analyses), member-major
+  out['y_ens'] = (out['y'][:, None] + rng.normal(
+      0, 1.5, (len(INIT), N_TARGET_MEMBERS, NLAT, NLON))).astype(f32)
   return out
 
 
 SEEPS_DRY_THRESHOLD_MM = 250.0   # 0.25 in the unit of the rain fields
+N_TARGET_MEMBERS = 3
 
 
 RAIN_THRESHOLDS = [0.0, 0.1, 0.5, 2.0, 1e9]
@@ -433,6 +437,20 @@ def build_cases(ns, inputs):
                  family='ens_exceedance')
   yield ens_case('cat/ensemble_error_exceedance_nan_members', x_nan,
                  ens_exceedance, family='ens_exceedance', member_nan=True)
+
+  # ensemble forecast against an ensemble of targets (probabilistic.py:135-145,
+  # 199-204, 691-782); the two ensembles have different sizes
+  y_ens = xr.DataArray(
+      inputs['y_ens'], D_ENS_MAJOR,
+      coords={'init_time': INIT, ENS: np.arange(N_TARGET_MEMBERS),
+              'latitude': LAT, 'longitude': LON})
+  for name, use_sort in (('ens/distance_to_target_ensemble', False),
+                         ('ens/distance_to_target_ensemble_sorted', True)):
+    case = ens_case(name, x_major, {
+        'crps_distance': prob.CRPSEnsembleDistance(ensemble_dim=ENS,
+                                                   use_sort=use_sort)},
+                    family='ens_distance')
+    yield case[:5] + ({'t2m': y_ens},)
 
   # -- SEEPS (categorical.py:104-304) -----------------------------------------
   var = 'total_precipitation_6hr'

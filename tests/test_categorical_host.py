@@ -657,3 +657,65 @@ def test_l2_blocked_job_order_gives_the_same_sums(reduce_dims, block_bytes,
       np.testing.assert_allclose(blocked.sum_weights[name][var].values,
                                  base.sum_weights[name][var].values,
                                  rtol=1e-12)
+
+
+def test_crps_distance_to_an_ensemble_of_targets(monkeypatch):
+  """probabilistic.py:135-145,199-204,691-782 with interpreted plans: the skill
+  is the mean over target members of the usual skill (launches merged into
+  one), the target spread is the spread kernel on the targets."""
+  from weatherbenchx_b200.metrics import probabilistic
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  launches = []
+  real = _cabi.CrpsPlan
+
+  class Counting(real):
+
+    def __init__(self, ctx, **desc):
+      launches.append(desc)
+      super().__init__(ctx, **desc)
+
+  monkeypatch.setattr(_cabi, 'CrpsPlan', Counting)
+  rng = np.random.default_rng(40)
+  n_init, m_pred, m_tgt, ny, nx = 3, 6, 4, 5, 8
+  truth = rng.normal(0, 1, (n_init, 1, ny, nx))
+  x = (truth + rng.normal(0, 1, (n_init, m_pred, ny, nx))).astype(np.float32)
+  y = (truth + rng.normal(0, 0.5, (n_init, m_tgt, ny, nx))).astype(np.float32)
+  dims = ('init_time', 'number', 'latitude', 'longitude')
+  grid = {'init_time': np.arange(n_init),
+          'latitude': np.linspace(-60, 60, ny), 'longitude': np.arange(nx) * 45.0}
+  X = xl.DataArray(x, dims, coords=dict(grid, number=np.arange(m_pred)),
+                   name='t')
+  Y = xl.DataArray(y, dims, coords=dict(grid, number=np.arange(m_tgt)),
+                   name='t')
+  metrics = {'distance': probabilistic.CRPSEnsembleDistance()}
+  aggregator = aggregation.Aggregator(
+      reduce_dims=['latitude', 'longitude'],
+      weigh_by=[weighting.GridAreaWeighting()])
+  statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+      metrics, {'t': X}, {'t': Y})
+  assert set(statistics) == {'CRPSSkill_number',
+                             'CRPSSpread_number_fair_predictions',
+                             'CRPSSpread_number_fair_targets'}
+  state = aggregator.aggregate_statistics(statistics)
+  values = state.metric_values(metrics)['distance.t']
+  # skill of the 4 target members in ONE merged launch, + the two spreads
+  assert len(launches) == 3
+  assert sorted(len(d['ens']) for d in launches) == [3, 3, 12]
+  w = oracle.grid_area_weights(grid['latitude'])
+  rd = ['latitude', 'longitude']
+  out_dims = ('init_time', 'latitude', 'longitude')
+
+  def mean(field):
+    sws, sw, _ = oracle.aggregate(field, out_dims, rd,
+                                  weights=[(w, ('latitude',))])
+    return sws / sw
+
+  skill = np.abs(x[:, :, None] - y[:, None, :]).mean(axis=(1, 2))
+  expected = (mean(skill) - 0.5 * mean(oracle.crps_spread(x, 1, fair=True))
+              - 0.5 * mean(oracle.crps_spread(y, 1, fair=True)))
+  np.testing.assert_allclose(values.values, expected, rtol=1e-5)
+  with pytest.raises(ValueError, match='Failed to compute'):
+    metrics_base.compute_unique_statistics_for_all_metrics(
+        {'s': probabilistic.CRPSSkill(skipna_ensemble=True)}, {'t': X},
+        {'t': Y})

@@ -1,6 +1,6 @@
 """Parity against vectors produced by the reference's own code.
 
-``tests/golden/reference_golden.npz`` holds, for 60 evaluation cases, the
+``tests/golden/reference_golden.npz`` holds, for 62 evaluation cases, the
 AggregationState (sum_weighted_statistics / sum_weights per statistic and
 variable) and the metric values that the UNMODIFIED modules of
 /root/reference/weatherbenchX returned in the build container
@@ -262,6 +262,18 @@ def _oracle_fields(spec, inputs):
       se = oracle.squared_error(x, np.expand_dims(y, axis))
       out[('SquaredError_each_realization', 't2m')] = (
           se.mean(axis=axis), dims, None)
+    elif family == 'ens_distance':
+      # probabilistic.py:135-145: mean of |x_m - y_k| over both member dims;
+      # :199-247 for the two spreads
+      y_ens = inputs['y_ens']                              # [init, K, lat, lon]
+      diff = np.abs(x[:, :, None] - y_ens[:, None, :])     # [init, M, K, ...]
+      out[('CRPSSkill_realization', 't2m')] = (diff.mean(axis=(1, 2)), dims,
+                                               None)
+      for which, data in (('predictions', x), ('targets', y_ens)):
+        out[(f'CRPSSpread_realization_fair_{which}', 't2m')] = (
+            oracle.crps_spread(data, 1, fair=True,
+                               use_sort=spec.get('use_sort', False)), dims,
+            None)
     elif family == 'ens_exceedance':
       # probabilistic.py:855-861: exceedance of every member, then xarray's
       # NaN-skipping mean over the members
@@ -297,7 +309,9 @@ def _oracle_fields(spec, inputs):
 
 
 def _oracle_state(case, spec, fields, stat, var, inputs):
-  if stat == 'CRPSSkill_realization':
+  if (stat, var) in fields:
+    values, dims, mask = fields[(stat, var)]
+  elif stat == 'CRPSSkill_realization':
     values, dims, mask = fields['skill'](case == 'ens/skipna_ensemble')
   elif stat.startswith('CRPSSpread_realization_'):
     values, dims, mask = fields['spread'](
@@ -321,7 +335,7 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
 
 def test_fixture_is_complete(golden):
   names = [str(n) for n in golden['cases']]
-  assert len(names) == 60 and len(set(names)) == 60
+  assert len(names) == 62 and len(set(names)) == 62
   for case in names:
     assert _case_keys(golden, case, 'sws'), case
     assert _case_keys(golden, case, 'value'), case
@@ -406,6 +420,13 @@ def test_oracle_reproduces_reference_values(golden, inputs):
         spa, _ = mean(case, spec, fields, 'SquaredPredictionAnomaly', var)
         sta, _ = mean(case, spec, fields, 'SquaredTargetAnomaly', var)
         value = oracle.acc_from_means(cov, spa, sta)
+      elif metric == 'crps_distance':
+        skill, dims = mean(case, spec, fields, 'CRPSSkill_realization', var)
+        spread_p, _ = mean(case, spec, fields,
+                           'CRPSSpread_realization_fair_predictions', var)
+        spread_t, _ = mean(case, spec, fields,
+                           'CRPSSpread_realization_fair_targets', var)
+        value = skill - 0.5 * spread_p - 0.5 * spread_t
       elif metric == 'ens_exceedance':
         value, dims = mean(case, spec, fields, 'EnsembleErrorExceedance', var)
       elif spec['family'] == 'cat':
@@ -544,6 +565,8 @@ CASE_NAMES = [
     'cat/relative_intensity', 'cat/relative_intensity_masked',
     'cat/ensemble_error_exceedance',
     'cat/ensemble_error_exceedance_nan_members',
+    'ens/distance_to_target_ensemble',
+    'ens/distance_to_target_ensemble_sorted',
     'seeps/masked_weighted', 'seeps/nan_targets_masked',
     'seeps/nan_both_masked_keep_init', 'seeps/regions_masked',
     'seeps/default_propagates', 'seeps/skipna_unweighted']
@@ -596,6 +619,11 @@ def _run_product_case(golden, inputs, case, space):
 # ensemble error exceedance, relative intensity); they passed on the B200 in
 # their own run (profiles/gpu_tests_seeps_late_cases_r1.log).
 SEEPS_CASES = [c for c in CASE_NAMES if c.startswith('seeps/')]
+# Added after the GPU budget of round 1 was spent: compositions of kernels that
+# passed on the B200 (merged CRPS launches over strided target-member views),
+# CPU-verified through the interpreted plans, not yet run on hardware.
+UNCONFIRMED_CASES = ['ens/distance_to_target_ensemble',
+                     'ens/distance_to_target_ensemble_sorted']
 LATE_CASES = SEEPS_CASES + ['cat/ensemble_error_exceedance',
                             'cat/ensemble_error_exceedance_nan_members',
                             'cat/relative_intensity',
@@ -605,7 +633,8 @@ LATE_CASES = SEEPS_CASES + ['cat/ensemble_error_exceedance',
 @pytest.mark.gpu
 @pytest.mark.parametrize('space', ['host', 'device'])
 @pytest.mark.parametrize('case',
-                         [c for c in CASE_NAMES if c not in LATE_CASES])
+                         [c for c in CASE_NAMES
+                          if c not in LATE_CASES + UNCONFIRMED_CASES])
 def test_cuda_path_reproduces_reference(golden, inputs, case, space):
   """State and values of the reference, from the CUDA path, for every case."""
   _run_product_case(golden, inputs, case, space)

@@ -39,6 +39,17 @@ def test_cuda_path_reproduces_reference_late_cases(golden, inputs, case, space):
   ref._run_product_case(golden, inputs, case, space)  # pylint: disable=protected-access
 
 
+@pytest.mark.xfail(strict=False, reason=(
+    'ensemble-of-targets CRPS: a composition of B200-verified kernels added '
+    'after the round-1 GPU budget was spent; CPU-verified with interpreted '
+    'plans, not yet run on hardware'))
+@pytest.mark.parametrize('space', ['host', 'device'])
+@pytest.mark.parametrize('case', ref.UNCONFIRMED_CASES)
+def test_cuda_path_reproduces_reference_unconfirmed_cases(golden, inputs, case,
+                                                          space):
+  ref._run_product_case(golden, inputs, case, space)  # pylint: disable=protected-access
+
+
 def _random_inputs(seed, n):
   rng = np.random.default_rng(seed)
   quarter = lambda lo, hi: (np.round(rng.uniform(lo, hi, n) * 4) / 4  # noqa: E731

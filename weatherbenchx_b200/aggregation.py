@@ -346,7 +346,8 @@ class Aggregator:
     stat = xl.as_data_array(stat)
     if (isinstance(stat, LazySumStatistic) and stat.is_lazy and
         not self.skipna):
-      return _add_states([self.aggregate_stat_var(p) for p in stat.parts])
+      return _add_states([self.aggregate_stat_var(p) for p in stat.parts],
+                         stat.scale)
     if isinstance(stat, LazyEnsembleAveraged) and stat.is_lazy:
       if self.skipna or (stat.skipna_ensemble and not stat.optimistic):
         return self._aggregate_generic(stat)
@@ -414,7 +415,7 @@ class Aggregator:
             results[key] = {}
             pvar = getattr(part, 'var', var)
             groups[(pvar,) + part.group_key()[:2]].append((key, var, part))
-          sums.append((stat_name, var, len(stat.parts)))
+          sums.append((stat_name, var, len(stat.parts), stat.scale))
         elif isinstance(stat, LazyStatistic) and stat.is_lazy:
           groups[(var,) + stat.group_key()[:2]].append((stat_name, var, stat))
         else:
@@ -541,10 +542,10 @@ class Aggregator:
         scale = 1.0 / stat.n_members
         results[stat_name][var] = AggregationState(
             sws * scale, state.sum_weights[stat_name][var] * scale)
-    for stat_name, var, n_parts in sums:
+    for stat_name, var, n_parts, scale in sums:
       results[stat_name][var] = _add_states(
           [results[('__part__', stat_name, var, i)].get(var)
-           for i in range(n_parts)])
+           for i in range(n_parts)], scale)
     sws, sw = {}, {}
     for stat_name in statistics:
       ok = {v: s for v, s in results[stat_name].items() if s is not None}
@@ -557,14 +558,16 @@ def _has_nan(da) -> bool:
   return bool(np.isnan(xl.as_data_array(da).to_numpy()).any())
 
 
-def _add_states(states):
-  """State of a sum of statistics on one grid: the weighted sums add, the
-  weights are those of any part (None if a part is not defined)."""
+def _add_states(states, scale: float = 1.0):
+  """State of ``scale *`` a sum of statistics on one grid: the weighted sums
+  add, the weights are those of any part (None if a part is not defined)."""
   if any(s is None for s in states):
     return None
   total = states[0].sum_weighted_statistics
   for s in states[1:]:
     total = total + s.sum_weighted_statistics
+  if scale != 1.0:
+    total = total * scale
   return AggregationState(total, states[0].sum_weights)
 
 

@@ -1108,6 +1108,9 @@ def materialize_sum(stat, device: int | None = None):
   torch = _torch()
   dims, sizes = stat.dims, stat.sizes
   out = None
+  if getattr(stat, 'scale', 1.0) != 1.0:
+    raise NotImplementedError(
+        f'per-point field of a scaled sum of {stat.kind} statistics')
   for i, part in enumerate(stat.parts):
     if part.kind not in _cabi.STAT_SLOT or part.climatology is not None:
       raise NotImplementedError(f'sum of {part.kind} statistics')

@@ -294,8 +294,12 @@ class LazySumStatistic(LazyStatistic):
 
   elementwise_of_operands = False
 
-  def __init__(self, kind: str, parts: Sequence[LazyStatistic], name=None):
+  def __init__(self, kind: str, parts: Sequence[LazyStatistic], name=None,
+               scale: float = 1.0):
     first = parts[0]
+    # the field is scale * (part0 + part1 + ...): 1 for sums, 1 / n for the
+    # mean over an ensemble of targets (CRPSSkill, probabilistic.py:135-145)
+    self.scale = float(scale)
     for p in parts[1:]:
       if p.dims != first.dims or p.sizes != first.sizes:
         raise ValueError(
@@ -330,9 +334,10 @@ class LazyEnsembleStatistic(LazyStatistic):
       raise ValueError(
           f'Dimension {ensemble_dim} not found in {predictions.dims}')
     if ensemble_dim in targets.dims:
+      # CRPSSkill / CRPSSpread split an ensemble of targets into member views
+      # before they get here (metrics/probabilistic.py)
       raise NotImplementedError(
-          'ensemble targets (CRPSSkill with a pseudo-ensemble of targets, '
-          'probabilistic.py:135-142) are outside the B200 hot path')
+          f'{kind} with an ensemble of targets is outside the B200 hot path')
     xl._check_index_coords(predictions, targets)  # pylint: disable=protected-access
     pdims = tuple(d for d in predictions.dims if d != ensemble_dim)
     dims = pdims + tuple(d for d in targets.dims if d not in pdims)

@@ -125,6 +125,28 @@ class CRPSSkill(base.PerVariableStatistic):
     return f'CRPSSkill_{self._ensemble_dim}'
 
   def _compute_per_variable(self, predictions, targets):
+    from weatherbenchx_b200 import xarray_lite as xl  # pylint: disable=g-import-not-at-top
+    targets = xl.as_data_array(targets)
+    if self._ensemble_dim in targets.dims:
+      # An ensemble of targets (probabilistic.py:135-145): the mean of
+      # |x_m - y_k| over both member dims is the mean over the target members
+      # of the usual skill.  Every target member is a strided view of the
+      # target array; the launches of the members are merged into one.
+      if self._skipna_ensemble:
+        raise NotImplementedError(
+            'skipna_ensemble with an ensemble of targets: the NaN-skipping '
+            'mean over member pairs is not a mean of per-member means')
+      from weatherbenchx_b200.lazy import LazySumStatistic  # pylint: disable=g-import-not-at-top
+      n_target = targets.sizes[self._ensemble_dim]
+      parts = [
+          LazyEnsembleStatistic(
+              'CRPSSkill', predictions,
+              targets.isel({self._ensemble_dim: k}), self._ensemble_dim,
+              fair=True, skipna_ensemble=False)
+          for k in range(n_target)]
+      return LazySumStatistic('CRPSSkill', parts,
+                              name=xl.as_data_array(predictions).name,
+                              scale=1.0 / n_target)
     return LazyEnsembleStatistic(
         'CRPSSkill', predictions, targets, self._ensemble_dim, fair=True,
         skipna_ensemble=self._skipna_ensemble)
@@ -148,11 +170,22 @@ class CRPSSpread(base.PerVariableStatistic):
     return f'CRPSSpread_{self._ensemble_dim}_{fair_str}_{self._which}'
 
   def _compute_per_variable(self, predictions, targets):
-    if self._which != 'predictions':
-      if self._which == 'targets':
-        raise NotImplementedError(
-            "CRPSSpread(which='targets') is outside the B200 hot path")
+    from weatherbenchx_b200 import xarray_lite as xl  # pylint: disable=g-import-not-at-top
+    predictions = xl.as_data_array(predictions)
+    targets = xl.as_data_array(targets)
+    if self._which not in ('predictions', 'targets'):
       raise ValueError(f'Unhandled {self._which=}')
+    ens = self._ensemble_dim
+
+    def one_member(da):
+      # the spread is a function of one input alone (probabilistic.py:
+      # 199-204); the kernel still wants a member-free companion slab
+      return da.isel({ens: 0}) if ens in da.dims else da
+
+    if self._which == 'targets':
+      predictions, targets = targets, one_member(predictions)
+    else:
+      targets = one_member(targets)
     if self._use_sort and self._skipna_ensemble:
       raise ValueError('skipna_ensemble is not supported with use_sort=True.')
     if (not self._skipna_ensemble and
@@ -238,6 +271,36 @@ class CRPSEnsemble(base.PerVariableMetric):
 
   def _values_from_mean_statistics_per_variable(self, statistic_values):
     return statistic_values['CRPSSkill'] - 0.5 * statistic_values['CRPSSpread']
+
+
+class CRPSEnsembleDistance(base.PerVariableMetric):
+  """Unbiased CRPS distance between an ensemble forecast and an ensemble of
+  targets: E|X - Y| - 0.5 E|X - X'| - 0.5 E|Y - Y'| (probabilistic.py:691-782).
+  Both inputs carry ``ensemble_dim`` (sizes may differ)."""
+
+  def __init__(self, ensemble_dim: str = ENSEMBLE_DIM, use_sort: bool = False,
+               fair: bool = True, skipna_ensemble: bool = False):
+    self._ensemble_dim = ensemble_dim
+    self._use_sort = use_sort
+    self._fair = fair
+    self._skipna_ensemble = skipna_ensemble
+
+  @property
+  def statistics(self) -> Mapping[str, base.Statistic]:
+    return {
+        'CRPSSkill': CRPSSkill(ensemble_dim=self._ensemble_dim),
+        'CRPSSpread': CRPSSpread(
+            ensemble_dim=self._ensemble_dim, use_sort=self._use_sort,
+            fair=self._fair, skipna_ensemble=self._skipna_ensemble),
+        'CRPSTargetSpread': CRPSSpread(
+            ensemble_dim=self._ensemble_dim, use_sort=self._use_sort,
+            fair=self._fair, which='targets'),
+    }
+
+  def _values_from_mean_statistics_per_variable(self, statistic_values):
+    return (statistic_values['CRPSSkill']
+            - 0.5 * statistic_values['CRPSSpread']
+            - 0.5 * statistic_values['CRPSTargetSpread'])
 
 
 class UnbiasedEnsembleMeanRMSE(base.PerVariableMetric):
