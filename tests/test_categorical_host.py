@@ -719,3 +719,126 @@ def test_crps_distance_to_an_ensemble_of_targets(monkeypatch):
     metrics_base.compute_unique_statistics_for_all_metrics(
         {'s': probabilistic.CRPSSkill(skipna_ensemble=True)}, {'t': X},
         {'t': Y})
+
+
+@pytest.mark.parametrize('ensemble_size,use_sort,fair', [
+    (4, False, True), (5, True, True), (4, True, False), (5, False, False)])
+def test_crps_ensemble_distance_reference_identities(ensemble_size, use_sort,
+                                                     fair, monkeypatch):
+  """metrics/metrics_test.py:662-752 with interpreted plans: predictions and
+  targets from the same distribution give a distance near zero (fair), and
+  targets whose members are all equal give the standard CRPS."""
+  import wbx_test_utils as utils
+  from weatherbenchx_b200.metrics import probabilistic
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  # (the 3-d variable of the reference's fixture stores `level` behind the grid
+  # dims: that layout goes through the generic kernel and is a GPU test)
+  kw = dict(time_start='2020-01-01T00', time_stop='2020-01-03T00', random=True,
+            variables_3d=())
+  targets = utils.to_f32(utils.mock_prediction_data(
+      ensemble_size=ensemble_size + 1, seed=0, lead_stop=2, **kw))
+  predictions = utils.to_f32(utils.mock_prediction_data(
+      ensemble_size=ensemble_size, seed=1, lead_stop=2, **kw))
+  # C-contiguous member-last arrays (the fixture's lead dim is a broadcast
+  # view): the layouts the host-space CRPS plan streams without staging
+  contiguous = lambda d: {k: v._replace(data=np.ascontiguousarray(v.values))  # noqa: E731
+                          for k, v in d.items()}
+  targets, predictions = contiguous(targets), contiguous(predictions)
+  n_target = ensemble_size + 1
+  no_spread = {}
+  for k, v in targets.items():
+    first = v.isel(realization=0, drop=True)
+    stacked = np.ascontiguousarray(np.broadcast_to(
+        first.values[..., None], first.shape + (n_target,)))
+    no_spread[k] = xl.DataArray(
+        stacked, first.dims + ('realization',),
+        coords=dict({d: first.coords[d] for d in first.dims},
+                    realization=np.arange(n_target)), name=k)
+  distance = {'crps': probabilistic.CRPSEnsembleDistance(
+      ensemble_dim='realization', use_sort=use_sort, fair=fair)}
+  standard = {'crps': probabilistic.CRPSEnsemble(
+      ensemble_dim='realization', use_sort=use_sort, fair=fair)}
+  reduce_dims = ['latitude', 'longitude', 'time']
+  aggregator = aggregation.Aggregator(reduce_dims=reduce_dims)
+
+  def compute(metrics, p, t):
+    return aggregation.compute_metric_values_for_single_chunk(
+        metrics, aggregator, p, t)
+
+  vs_targets = compute(distance, predictions, targets)
+  vs_no_spread = compute(distance, predictions, no_spread)
+  vs_no_ensemble = compute(standard, predictions, no_spread)
+  sizes = predictions['2m_temperature'].sizes
+  stderr = 1 / np.sqrt(np.prod([ensemble_size * sizes[d]
+                                for d in reduce_dims]))
+  for v in ('2m_temperature',):
+    if fair:
+      np.testing.assert_allclose(vs_targets[f'crps.{v}'].values, 0,
+                                 atol=5 * stderr)
+    a, b = vs_no_spread[f'crps.{v}'], vs_no_ensemble[f'crps.{v}']
+    np.testing.assert_allclose(a.values, b.transpose(*a.dims).values,
+                               rtol=1e-5, atol=5 * stderr)
+    # all target members equal: their spread is exactly zero
+    assert a.shape == b.shape
+
+
+def _relative_intensity(predictions, targets, mask=None, dims=('latitude',
+                                                               'longitude')):
+  """The statistic through the class surface (fused reductions interpreted)
+  and through the oracle, for the reference's inline cases."""
+  coords = {d: np.arange(n) for d, n in zip(dims, np.shape(predictions))}
+  P = xl.DataArray(np.asarray(predictions, np.float32), dims, coords=coords,
+                   name='var')
+  T = xl.DataArray(np.asarray(targets, np.float32), dims, coords=coords,
+                   name='var')
+  if mask is not None:
+    T = T.assign_coords(mask=xl.DataArray(np.asarray(mask), dims))
+  stat = deterministic.RelativeIntensity(
+      spatial_dims=['latitude', 'longitude']).compute({'var': P}, {'var': T})
+  want, want_mask = oracle.relative_intensity(
+      np.asarray(predictions, np.float32), np.asarray(targets, np.float32),
+      (len(dims) - 2, len(dims) - 1),
+      None if mask is None else np.asarray(mask))
+  got = stat['var']
+  np.testing.assert_allclose(got.values, want, atol=1e-5, equal_nan=True)
+  if mask is not None:
+    np.testing.assert_array_equal(got.coords['mask'].values, want_mask)
+  return got
+
+
+def test_relative_intensity_reference_known_answers(monkeypatch):
+  """metrics/deterministic_test.py:27-218 (integer 0/1 masks as there)."""
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  nan = np.nan
+  # regular: mean 25 against 10 -> |2.5 - 1|
+  got = _relative_intensity([[10, 20], [30, 40]], [[10, 10], [10, 10]])
+  np.testing.assert_allclose(got.values, 1.5, atol=1e-5)
+  assert 'mask' not in got.coords
+  # NaNs that are masked out
+  got = _relative_intensity([[10, nan], [30, 40]], [[10, nan], [10, 10]],
+                            [[1, 0], [1, 1]])
+  np.testing.assert_allclose(got.values, abs((80 / 3) / 10 - 1), atol=1e-5)
+  assert got.coords['mask'].item() == 1
+  # a kept time dim; the second time is masked out completely
+  got = _relative_intensity(
+      [[[10, 20], [30, 40]], [[100, 200], [300, 400]]],
+      [[[10, 10], [10, 10]], [[10, 10], [10, 10]]],
+      [[[1, 1], [1, 1]], [[0, 0], [0, 0]]],
+      dims=('time', 'latitude', 'longitude'))
+  np.testing.assert_allclose(got.values, [1.5, 0.0], atol=1e-5)
+  np.testing.assert_array_equal(got.coords['mask'].values, [1, 0])
+  # everything NaN and masked
+  got = _relative_intensity([[nan, nan], [nan, nan]], [[nan, nan], [nan, nan]],
+                            [[0, 0], [0, 0]])
+  np.testing.assert_allclose(got.values, 0)
+  assert got.coords['mask'].item() == 0
+  # a NaN inside the valid region propagates (skipna=False)
+  got = _relative_intensity([[10, nan], [30, 40]], [[10, 10], [10, 10]],
+                            [[1, 1], [1, 1]])
+  assert np.isnan(got.values) and got.coords['mask'].item() == 1
+  # only mask == 1 counts as valid
+  got = _relative_intensity([[10, 20], [30, 40]], [[10, 10], [10, 10]],
+                            [[1, 2], [1, 1]])
+  np.testing.assert_allclose(got.values, abs((80 / 3) / 10 - 1), atol=1e-5)

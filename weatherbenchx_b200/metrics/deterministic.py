@@ -46,6 +46,12 @@ class RelativeIntensity(base.PerVariableStatistic):
     spatial_dims = list(self._spatial_dims)
     epsilon = 1e-6
     masked = 'mask' in targets.coords
+    if masked:
+      mask = targets.coords['mask']
+      if not mask.is_device and mask.dtype != np.bool_:
+        # `targets.mask == 1` (deterministic.py:68): only the value 1 is valid
+        targets = targets.assign_coords(mask=mask._replace(  # pylint: disable=protected-access
+            data=mask.to_numpy() == 1))
 
     def sums(source):
       # source - 0 against a shared zero slab; the coordinates (and so the
