@@ -842,3 +842,54 @@ def test_relative_intensity_reference_known_answers(monkeypatch):
   got = _relative_intensity([[10, 20], [30, 40]], [[10, 10], [10, 10]],
                             [[1, 2], [1, 1]])
   np.testing.assert_allclose(got.values, abs((80 / 3) / 10 - 1), atol=1e-5)
+
+
+def test_repeated_categorical_requests_reuse_their_plan(monkeypatch):
+  """The steady state of an evaluation loop: same arrays, same transform ->
+  the planner returns the previous spec (payload identities, incl. the
+  threshold coordinate) and the library plan is reused."""
+  wbx_emulator.installed(monkeypatch)
+  engine.clear_plan_cache()
+  built = []
+  real_build = engine._build_fused_spec
+
+  def counting(*args, **kwargs):
+    built.append(1)
+    return real_build(*args, **kwargs)
+
+  monkeypatch.setattr(engine, '_build_fused_spec', counting)
+  plans = []
+  real_plan = _cabi.DetPlan
+
+  class Counting(real_plan):
+
+    def __init__(self, ctx, **desc):
+      plans.append(1)
+      super().__init__(ctx, **desc)
+
+  monkeypatch.setattr(_cabi, 'DetPlan', Counting)
+  rng = np.random.default_rng(50)
+  P = _da(rng.random((3, 6, 8)).astype(np.float32))
+  T = _da(rng.random((3, 6, 8)).astype(np.float32))
+  both = [wrappers.ContinuousToBinary('both', [0.25, 0.5], 'threshold')]
+  metrics = {'csi': wrappers.WrappedMetric(categorical.CSI(), both),
+             'exceed': deterministic.ErrorExceedance([0.1, 0.2])}
+  aggregator = aggregation.Aggregator(
+      reduce_dims=['latitude', 'longitude'],
+      weigh_by=[weighting.GridAreaWeighting()])
+  first = aggregation.compute_metric_values_for_single_chunk(
+      metrics, aggregator, {'rain': P}, {'rain': T})
+  n_built, n_plans = len(built), len(plans)
+  assert n_built == 2 and n_plans == 2      # contingency table + exceedance
+  for _ in range(3):
+    again = aggregation.compute_metric_values_for_single_chunk(
+        metrics, aggregator, {'rain': P}, {'rain': T})
+  assert len(built) == n_built and len(plans) == n_plans
+  for k in first:
+    np.testing.assert_array_equal(again[k].values, first[k].values)
+  # other thresholds on the same arrays are another plan
+  other = {'csi': wrappers.WrappedMetric(categorical.CSI(), [
+      wrappers.ContinuousToBinary('both', [0.25, 0.75], 'threshold')])}
+  aggregation.compute_metric_values_for_single_chunk(
+      other, aggregator, {'rain': P}, {'rain': T})
+  assert len(built) == n_built + 1 and len(plans) == n_plans + 1

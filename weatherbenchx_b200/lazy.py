@@ -395,7 +395,12 @@ class LazyBinarized(xl.DataArray):
 
   def __init__(self, source: xl.DataArray, thresholds, threshold_dim):
     source = xl.as_data_array(source)
-    labels = np.asarray(thresholds, dtype=np.float64).reshape(-1)
+    # a float64 vector is kept as the object it is: the planner recognises a
+    # repeated request by the identity of every payload involved, and the
+    # threshold labels become a coordinate of the statistic
+    labels = np.asarray(thresholds, dtype=np.float64)
+    if labels.ndim != 1:
+      labels = labels.reshape(-1)
     if threshold_dim in source.dims:
       raise ValueError(
           f'{threshold_dim!r} is already a dimension of the input')

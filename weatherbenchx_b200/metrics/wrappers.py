@@ -23,6 +23,8 @@ from __future__ import annotations
 import abc
 from typing import Any, Hashable, Mapping, Sequence
 
+import numpy as np
+
 from weatherbenchx_b200 import xarray_lite as xl
 from weatherbenchx_b200 import xarray_tree
 from weatherbenchx_b200.metrics import base
@@ -124,6 +126,12 @@ class ContinuousToBinary(InputTransform):
             'unique_name_suffix must be provided if threshold_value is an'
             ' xarray.DataArray or xarray.Dataset.')
     self._unique_name_suffix = unique_name_suffix
+    # one label vector per transform: every call hands the planner the same
+    # coordinate payload, so repeated evaluations reuse their plan
+    self._labels = None
+    if not isinstance(self._threshold_value, (xl.DataArray, xl.Dataset)):
+      self._threshold_value = list(self._threshold_value)
+      self._labels = np.asarray(self._threshold_value, dtype=np.float64)
 
   @property
   def unique_name_suffix(self) -> str:
@@ -134,6 +142,10 @@ class ContinuousToBinary(InputTransform):
     return f'{self._threshold_dim}={suffix}'
 
   def transform_fn(self, da: xl.DataArray) -> xl.DataArray:
+    if self._labels is not None:
+      from weatherbenchx_b200.lazy import LazyBinarized  # pylint: disable=g-import-not-at-top
+      return LazyBinarized(xl.as_data_array(da), self._labels,
+                           self._threshold_dim)
     return binarize_thresholds(da, self._threshold_value, self._threshold_dim)
 
 
