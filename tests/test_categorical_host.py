@@ -893,3 +893,32 @@ def test_repeated_categorical_requests_reuse_their_plan(monkeypatch):
   aggregation.compute_metric_values_for_single_chunk(
       other, aggregator, {'rain': P}, {'rain': T})
   assert len(built) == n_built + 1 and len(plans) == n_plans + 1
+
+
+def test_host_climatology_gather_touches_only_the_needed_rows():
+  """engine.gather_aligned_host == the oracle's alignment, for a climatology
+  stored (hour, dayofyear, longitude, latitude) and valid times across 29 Feb."""
+  init = np.datetime64('2020-02-28T00', 'ns') + np.arange(3) * np.timedelta64(
+      12, 'h')
+  lead = (np.arange(4) * np.timedelta64(6, 'h')).astype('timedelta64[ns]')
+  rng = np.random.default_rng(60)
+  clim = rng.normal(size=(4, 366, 5, 3)).astype(np.float32)
+  C = xl.DataArray(clim, ('hour', 'dayofyear', 'longitude', 'latitude'),
+                   coords={'hour': np.arange(0, 24, 6),
+                           'dayofyear': np.arange(1, 367),
+                           'longitude': np.arange(5) * 72.0,
+                           'latitude': np.linspace(-60, 60, 3)})
+  P = xl.DataArray(np.zeros((3, 4, 3, 5), np.float32),
+                   ('init_time', 'lead_time', 'latitude', 'longitude'),
+                   coords={'init_time': init, 'lead_time': lead,
+                           'latitude': np.linspace(-60, 60, 3),
+                           'longitude': np.arange(5) * 72.0})
+  aligned = engine.align_climatology(P, C)
+  got, dims = engine.gather_aligned_host(aligned)
+  assert dims == ('init_time', 'lead_time', 'longitude', 'latitude')
+  want, wdims = oracle.align_climatology(
+      clim, ('hour', 'dayofyear', 'longitude', 'latitude'),
+      {'hour': np.arange(0, 24, 6), 'dayofyear': np.arange(1, 367)}, init, lead)
+  want = np.transpose(want, [list(wdims).index(d) for d in dims])
+  np.testing.assert_array_equal(got, want)
+  assert got.shape == (3, 4, 5, 3)

@@ -1171,11 +1171,29 @@ def passthrough(source: xl.DataArray, other: xl.DataArray,
 # ---------------------------------------------------------------------------
 
 
+def gather_aligned_host(ac: AlignedClimatology):
+  """``climatology.sel(dayofyear=..., hour=...)`` of a HOST climatology with
+  NumPy: only the rows of the requested valid times are touched (a 0.25 degree
+  climatology is gigabytes, a chunk needs a few rows of it).  Returns
+  (ndarray, dims) with the prediction time dims first (base.py:383-403)."""
+  clim = ac.climatology
+  front = list(ac.clim_time_dims)
+  rest = [d for d in clim.dims if d not in front]
+  arr = clim.transpose(*(front + rest)).to_numpy()   # a view
+  gathered = arr[tuple(np.asarray(ac.positions[d]) for d in front)]
+  return gathered, tuple(ac.time_dims) + tuple(rest)
+
+
 def _gather_aligned(ac: AlignedClimatology, device=None):
-  """``climatology.sel(dayofyear=..., hour=...)`` as a device gather; returns
-  (tensor, dims) with the prediction time dims first (base.py:383-403)."""
+  """The aligned climatology rows as a device tensor; returns (tensor, dims)
+  with the prediction time dims first.  A host climatology is gathered on the
+  host and only the gathered rows are uploaded."""
   torch = _torch()
-  clim = to_device(_normalise(ac.climatology, 'field'), device)
+  if not ac.climatology.is_device:
+    gathered, gdims = gather_aligned_host(ac)
+    da = to_device(_normalise(xl.DataArray(gathered, gdims), 'field'), device)
+    return da.data, gdims
+  clim = _normalise(ac.climatology, 'field')
   ct = clim.data
   cdims = list(clim.dims)
   front = list(ac.clim_time_dims)
