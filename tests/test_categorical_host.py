@@ -922,3 +922,29 @@ def test_host_climatology_gather_touches_only_the_needed_rows():
   want = np.transpose(want, [list(wdims).index(d) for d in dims])
   np.testing.assert_array_equal(got, want)
   assert got.shape == (3, 4, 5, 3)
+
+
+def test_new_metric_classes_pickle():
+  """Beam pickles Metric objects to its workers (beam_pipeline.py:150-159):
+  nothing on the instances may hold a library handle or a lazy field."""
+  import pickle
+  from weatherbenchx_b200.metrics import categorical as cat
+  from weatherbenchx_b200.metrics import probabilistic
+  clim = xl.Dataset({'rain_seeps_threshold': xl.DataArray(
+      np.ones((2, 366, 3, 4), np.float32),
+      ('hour', 'dayofyear', 'latitude', 'longitude'))})
+  metrics = {
+      'csi': wrappers.WrappedMetric(cat.CSI(), [
+          wrappers.ContinuousToBinary('both', [0.1, 1.0], 'threshold')]),
+      'sedi': cat.SEDI(), 'seeps': cat.SEEPS(['rain'], clim),
+      'exceed': deterministic.ErrorExceedance([0.5]),
+      'ens_exceed': probabilistic.EnsembleErrorExceedance([0.5]),
+      'intensity': deterministic.RelativeIntensity(),
+      'distance': probabilistic.CRPSEnsembleDistance()}
+  clone = pickle.loads(pickle.dumps(metrics))
+  assert set(clone) == set(metrics)
+  for name, metric in metrics.items():
+    assert (sorted(s.unique_name for s in clone[name].statistics.values()) ==
+            sorted(s.unique_name for s in metric.statistics.values())), name
+  transform = clone['csi'].transforms[0]
+  np.testing.assert_array_equal(transform._labels, [0.1, 1.0])
