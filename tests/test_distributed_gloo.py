@@ -157,6 +157,82 @@ def _sharded(reduce_dims):
   return {k: v.values for k, v in values.items()}
 
 
+class _Patch:
+  """monkeypatch stand-in for the spawned workers."""
+
+  def setattr(self, obj, name, value):
+    setattr(obj, name, value)
+
+
+def _categorical_setup():
+  """Thresholded contingency metrics, error exceedance and SEEPS on rain-like
+  fields; the REAL Aggregator, its plans interpreted by tests/wbx_emulator.py
+  (host side only -- the kernels are GPU-tested)."""
+  import wbx_emulator
+  from weatherbenchx_b200 import weighting
+  from weatherbenchx_b200.metrics import categorical, wrappers
+  wbx_emulator.installed(_Patch())
+  init = np.datetime64('2020-02-27T00', 'ns') + np.arange(
+      N_INIT) * np.timedelta64(12, 'h')
+  lead = (np.arange(2) * np.timedelta64(12, 'h')).astype('timedelta64[ns]')
+  dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+  coords = {'init_time': init, 'lead_time': lead, 'latitude': LAT,
+            'longitude': np.arange(NLON) * 30.0}
+  rng = np.random.default_rng(77)
+  shape = (N_INIT, 2, NLAT, NLON)
+  rain = lambda: (np.round(rng.gamma(0.8, 2.0, shape) * 4) / 4 *  # noqa: E731
+                  (rng.random(shape) < 0.6)).astype(np.float32)
+  preds = {'rain': xl.DataArray(rain(), dims, coords=coords, name='rain')}
+  tgts = {'rain': xl.DataArray(rain(), dims, coords=coords, name='rain')}
+  cdims = ('hour', 'dayofyear', 'latitude', 'longitude')
+  ccoords = {'hour': np.array([0, 12]), 'dayofyear': np.arange(1, 367),
+             'latitude': LAT, 'longitude': coords['longitude']}
+  clim = xl.Dataset({
+      'rain_seeps_threshold': xl.DataArray(
+          (np.round(rng.uniform(0.5, 3, (2, 366, NLAT, NLON)) * 4) / 4
+           ).astype(np.float32), cdims, coords=ccoords),
+      'rain_seeps_dry_fraction': xl.DataArray(
+          np.broadcast_to(rng.uniform(0.0, 1.0, (NLAT, NLON)),
+                          (2, 366, NLAT, NLON)).astype(np.float32),
+          cdims, coords=ccoords)})
+  both = [wrappers.ContinuousToBinary('both', [0.0, 0.5, 2.0], 'threshold')]
+  metrics = {
+      'csi': wrappers.WrappedMetric(categorical.CSI(), both),
+      'ets': wrappers.WrappedMetric(categorical.ETS(), both),
+      'exceed': deterministic.ErrorExceedance([0.25, 1.0]),
+      'seeps': categorical.SEEPS(['rain'], clim, dry_threshold_mm=250.0)}
+  make_aggregator = lambda rd: aggregation.Aggregator(  # noqa: E731
+      reduce_dims=rd, weigh_by=[weighting.GridAreaWeighting()], masked=True)
+  return metrics, make_aggregator, preds, tgts
+
+
+def _categorical_sharded(reduce_dims):
+  metrics, make_aggregator, preds, tgts = _categorical_setup()
+  units = list(range(3))                                  # 2 init_times each
+
+  def load_unit(chunk):
+    sl = {'init_time': slice(2 * chunk, 2 * chunk + 2)}
+    return ({'rain': preds['rain'].isel(sl)}, {'rain': tgts['rain'].isel(sl)})
+
+  values = distributed.evaluate_sharded(
+      metrics, make_aggregator(reduce_dims), units, load_unit)
+  return {k: v.values for k, v in values.items()}
+
+
+def _w_categorical_reduced(rank, world_size):
+  return _categorical_sharded(['init_time', 'latitude', 'longitude'])
+
+
+def _w_categorical_kept_init(rank, world_size):
+  return _categorical_sharded(['latitude', 'longitude'])
+
+
+def _categorical_monolithic(reduce_dims):
+  metrics, make_aggregator, preds, tgts = _categorical_setup()
+  return aggregation.compute_metric_values_for_single_chunk(
+      metrics, make_aggregator(reduce_dims), preds, tgts)
+
+
 # --------------------------------------------------------------------------
 # tests
 # --------------------------------------------------------------------------
@@ -234,3 +310,24 @@ def test_sharded_evaluation_kept_init_time_gloo():
     for k in mono:
       assert r[k].shape == (N_INIT,)
       np.testing.assert_allclose(r[k], mono[k].values, rtol=1e-12)
+
+
+@pytest.mark.parametrize('worker,reduce_dims', [
+    ('_w_categorical_reduced', ['init_time', 'latitude', 'longitude']),
+    ('_w_categorical_kept_init', ['latitude', 'longitude'])])
+def test_sharded_categorical_evaluation_equals_monolithic_gloo(worker,
+                                                               reduce_dims):
+  """The thresholded contingency metrics, error exceedance and SEEPS through
+  the real Aggregator on two ranks (init_time chunks sharded, one combine of
+  the states) == one evaluation of everything."""
+  res = _run(globals()[worker])
+  mono = _categorical_monolithic(reduce_dims)
+  assert set(mono) == {'csi.rain', 'ets.rain', 'exceed.rain', 'seeps.rain'}
+  for r in res:
+    assert set(r.files) == set(mono)
+    for k in mono:
+      assert r[k].shape == mono[k].values.shape, k
+      np.testing.assert_allclose(r[k], mono[k].values, rtol=1e-12,
+                                 equal_nan=True, err_msg=k)
+  if 'init_time' not in reduce_dims:
+    assert res[0]['csi.rain'].shape == (N_INIT, 2, 3)
