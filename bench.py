@@ -565,6 +565,68 @@ def run_suite(ctx, dev, peak):
     except Exception:  # pylint: disable=broad-except
       pass
   torch.cuda.empty_cache()
+
+  # ---- SEEPS (categorical.SEEPS: elementwise kernel + fused masked reduction),
+  # 0.25 deg.  Also added late in round 1: guarded like the leg above.
+  try:
+    from weatherbenchx_b200.metrics import categorical
+    n_init = 20
+    dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+    lon = np.linspace(0, 360, NLON, endpoint=False)
+    coords = {
+        'init_time': np.datetime64('2020-01-01T00', 'ns') +
+                     np.arange(n_init) * np.timedelta64(6, 'h'),
+        'lead_time': np.zeros(1, 'timedelta64[ns]'),
+        'latitude': lat, 'longitude': lon}
+    t = torch.empty((n_init, 1, NLAT, NLON), device=dev)
+    t.exponential_(500.0, generator=gen)            # metres, mean 2 mm
+    p = (t + torch.empty_like(t).normal_(0.0, 2e-3, generator=gen)).clamp_(0)
+    preds = {'rain': xl.DataArray(p, dims, coords=coords, name='rain')}
+    tgts = {'rain': xl.DataArray(t, dims, coords=coords, name='rain')}
+    cdims = ('dayofyear', 'hour', 'latitude', 'longitude')
+    ccoords = {'dayofyear': np.arange(1, 9), 'hour': np.arange(0, 24, 6),
+               'latitude': lat, 'longitude': lon}
+    wet = torch.empty((8, 4, NLAT, NLON), device=dev)
+    wet.uniform_(1e-3, 8e-3, generator=gen)
+    rng = np.random.default_rng(11)
+    dry = np.broadcast_to(
+        rng.uniform(0.0, 1.0, (NLAT, NLON)).astype(np.float32),
+        (8, 4, NLAT, NLON))
+    clim = xl.Dataset({
+        'rain_seeps_threshold': xl.DataArray(wet, cdims, coords=ccoords),
+        'rain_seeps_dry_fraction': xl.DataArray(dry, cdims, coords=ccoords)})
+    metrics = {'seeps': categorical.SEEPS(['rain'], clim)}
+    aggregator = aggregation.Aggregator(
+        reduce_dims=['init_time', 'latitude', 'longitude'],
+        weigh_by=[weighting.GridAreaWeighting()], masked=True)
+    step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
+        metrics, aggregator, preds, tgts)
+    ms, kms, kn = timed(step, 5)
+    pts = n_init * NLAT * NLON
+    bpp = 21.0
+    out['seeps'] = {
+        'workload': 'SEEPS, 1 var x 20 init x 721x1440 f32, climatology on '
+                    'the device, masked lat-weighted mean, class API, device '
+                    'inputs',
+        'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+        'reduction_kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+        'roofline': {'bound': 'hbm',
+                     'achieved': pts * bpp / (ms * 1e-3) / 1e9, 'peak': peak,
+                     'unit': 'GB/s', 'frac': pts * bpp / (ms * 1e-3) / 1e9 / peak,
+                     'algorithmic_bytes_per_point': bpp,
+                     'note': 'WHOLE STEP (threshold gather, elementwise SEEPS '
+                             'kernel 12 B read + 4 B written, masked reduction '
+                             '4 B + 1 B, host planning), CUDA events around '
+                             'the class-API call; the elementwise kernel is '
+                             'not timed on its own yet'}}
+    del preds, tgts, clim, metrics, step, wet, p, t
+  except Exception as e:  # pylint: disable=broad-except
+    out['seeps'] = {'error': f'{type(e).__name__}: {e}'}
+    try:
+      ctx.profile(False)
+    except Exception:  # pylint: disable=broad-except
+      pass
+  torch.cuda.empty_cache()
   out['c5_stream_sample'] = stream_sample(dev, gen, lat)
   return out
 
