@@ -170,46 +170,58 @@ class AggregationState:
     return self.map_multi(func, self)
 
   # -- serialisation ---------------------------------------------------------
-  # The reference offers DataTree and '#'-separated Dataset forms
-  # (aggregation.py:203-265).  Without xarray the Dataset form is the
-  # checkpoint format here: a flat {path#leaf: DataArray} mapping.
+  # DataTree and '#'-separated Dataset forms, as in the reference
+  # (aggregation.py:203-265); the Dataset form is what the chunk driver writes
+  # to NetCDF as its checkpoint / final state.
+
+  def to_data_tree(self) -> xl.DataTree:
+    """DataTree representation (aggregation.py:203-216): one node per mapping
+    level, the two sums in the Dataset of each leaf node."""
+    if isinstance(self.sum_weighted_statistics, xl.DataArray):
+      return xl.DataTree(dataset=xl.Dataset({
+          'sum_weighted_statistics': self.sum_weighted_statistics,
+          'sum_weights': self.sum_weights}))
+    if isinstance(self.sum_weighted_statistics, Mapping):
+      return xl.DataTree(children={
+          str(k): AggregationState(self.sum_weighted_statistics[k],
+                                   self.sum_weights[k]).to_data_tree()
+          for k in self.sum_weighted_statistics})
+    raise TypeError('Bad type for AggregationState.sum_weighted_statistics.')
+
+  @classmethod
+  def from_data_tree(cls, data_tree: xl.DataTree) -> 'AggregationState':
+    """AggregationState from its DataTree form (aggregation.py:218-232)."""
+    if data_tree.dataset:
+      return cls(
+          data_tree.dataset['sum_weighted_statistics'].rename(data_tree.name),
+          data_tree.dataset['sum_weights'].rename(data_tree.name))
+    children = {k: cls.from_data_tree(v)
+                for k, v in data_tree.children.items()}
+    return cls(
+        sum_weighted_statistics={
+            k: v.sum_weighted_statistics for k, v in children.items()},
+        sum_weights={k: v.sum_weights for k, v in children.items()})
 
   def to_dataset(self, separator: str = '#') -> xl.Dataset:
+    """Flat ``{path#leaf: DataArray}`` form (aggregation.py:234-255).  Does not
+    round-trip if a statistic or variable name contains ``separator``."""
     out = xl.Dataset()
-
-    def walk(prefix, sws, sw):
-      if isinstance(sws, Mapping):
-        for k in sws:
-          walk(prefix + [str(k)], sws[k], sw[k])
-      else:
-        path = separator.join(prefix)
-        out[f'{path}{separator}sum_weighted_statistics'] = sws
-        out[f'{path}{separator}sum_weights'] = sw
-
-    walk([], self.sum_weighted_statistics, self.sum_weights)
+    for path, dataset in self.to_data_tree().to_dict().items():
+      path = str(path).lstrip('/').replace('/', separator)
+      for var_name, data_array in dataset.items():
+        out[f'{path}{separator}{var_name}'] = data_array
     return out
 
   @classmethod
   def from_dataset(cls, dataset: Mapping[str, xl.DataArray],
                    separator: str = '#') -> 'AggregationState':
-    def tree():
-      return collections.defaultdict(tree)
-
-    sws, sw = tree(), tree()
-    for path, da in dataset.items():
-      *parts, leaf = str(path).split(separator)
-      target = sws if leaf == 'sum_weighted_statistics' else sw
-      node = target
-      for p in parts[:-1]:
-        node = node[p]
-      node[parts[-1]] = da.rename(parts[-1])
-
-    def freeze(node):
-      if isinstance(node, collections.defaultdict):
-        return {k: freeze(v) for k, v in node.items()}
-      return node
-
-    return cls(freeze(sws), freeze(sw))
+    """Inverse of to_dataset (aggregation.py:257-265); a state whose sums are
+    bare DataArrays comes back as bare DataArrays."""
+    nodes: dict = collections.defaultdict(xl.Dataset)
+    for path, data_array in dataset.items():
+      path, var_name = str(path).rsplit(separator, 1)
+      nodes['/' + path.replace(separator, '/')][var_name] = data_array
+    return cls.from_data_tree(xl.DataTree.from_dict(nodes))
 
 
 @dataclasses.dataclass
@@ -247,7 +259,9 @@ class Aggregator:
       mask = xl.as_data_array(binning.create_bin_mask(stat))
       if not (set(mask.dims) - {binning.bin_dim_name}).issubset(stat.dims):
         return None
-      factors.append(mask)
+      # xr.dot aligns the mask with the statistic by label (aggregation.py:
+      # 334-335); e.g. LandSea returns it on the coordinates of its own input
+      factors.append(xl.reorder_like(mask, stat, 'bin mask'))
     return factors, names
 
   def _bin_masks(self, stat: xl.DataArray):
@@ -260,7 +274,7 @@ class Aggregator:
       mask = xl.as_data_array(binning.create_bin_mask(stat))
       if not (set(mask.dims) - {binning.bin_dim_name}).issubset(stat.dims):
         return None
-      masks.append(mask)
+      masks.append(xl.reorder_like(mask, stat, 'bin mask'))
     return masks, names
 
   def aggregation_fn(self, stat: xl.DataArray) -> xl.DataArray | None:
@@ -351,8 +365,11 @@ class Aggregator:
     if isinstance(stat, LazyEnsembleAveraged) and stat.is_lazy:
       if self.skipna or (stat.skipna_ensemble and not stat.optimistic):
         return self._aggregate_generic(stat)
+      # the member mean drops a 'mask' coordinate that carries the ensemble
+      # dim (probabilistic.py:56-69): the averaged statistic is then unmasked
       nested = dataclasses.replace(
-          self, reduce_dims=list(self.reduce_dims) + [stat.ensemble_dim])
+          self, reduce_dims=list(self.reduce_dims) + [stat.ensemble_dim],
+          masked=self.masked and 'mask' in stat.coords)
       state = nested.aggregate_stat_var(stat.inner)
       if state is None:
         return None
@@ -520,11 +537,19 @@ class Aggregator:
       for (members, _, _), out in zip(planned, outs):
         for stat_name, var, s in members:
           results[stat_name][var] = AggregationState(*out[s.kind])
+    by_dim_and_mask: dict = {}
     for dim, members in averaged.items():
+      for m in members:
+        # a 'mask' coordinate that carries the ensemble dim does not survive
+        # the member mean (probabilistic.py:56-69): such a statistic is
+        # aggregated unmasked, NaN members propagate
+        by_dim_and_mask.setdefault(
+            (dim, self.masked and 'mask' in m[2].coords), []).append(m)
+    for (dim, masked), members in by_dim_and_mask.items():
       # mean over members then weighted sums == the fused reduction over
       # reduce_dims + [ensemble dim], divided by the member count
       nested = dataclasses.replace(
-          self, reduce_dims=list(self.reduce_dims) + [dim])
+          self, reduce_dims=list(self.reduce_dims) + [dim], masked=masked)
       inner: dict = {}
       for stat_name, var, stat in members:
         inner.setdefault(stat_name, {})[var] = stat.inner

@@ -156,23 +156,64 @@ def align_climatology(predictions: xl.DataArray,
   """Index form of metrics/base.py:383-403 (valid_time -> dayofyear/hour).
 
   The three ACC statistics of every variable ask for the same alignment; it is
-  memoised on the identity of the time coordinates and of the climatology.
+  memoised on the identity of the time and grid coordinates and of the
+  climatology.  The non-time index coordinates of the climatology (level,
+  latitude, longitude ...) are matched to the predictions by LABEL, as
+  ``predictions - climatology.sel(...)`` does in the reference: the same labels
+  in another order give a re-ordered copy (made once per climatology),
+  different labels raise.
   """
   tkeys = tuple(k for k in ('valid_time', 'init_time', 'lead_time')
                 if k in predictions.coords)
-  key = (tuple(id(predictions.coords[k].data) for k in tkeys),
-         id(climatology), id(climatology.data))
+  gkeys = tuple(d for d in climatology.dims
+                if d in predictions.dims and d in predictions.coords
+                and d in climatology.coords)
+  guards = tuple(predictions.coords[k].data for k in tkeys + gkeys)
+  key = (tuple(id(g) for g in guards), id(climatology), id(climatology.data))
   with _CACHE_LOCK:
     hit = _ALIGN_CACHE.get(key)
   if hit is not None and hit[1] is climatology and all(
-      a is predictions.coords[k].data for a, k in zip(hit[2], tkeys)):
+      a is b for a, b in zip(hit[2], guards)):
     return hit[0]
-  out = _align_climatology(predictions, climatology)
+  out = _align_climatology(predictions,
+                           _label_ordered_climatology(predictions, climatology))
   with _CACHE_LOCK:
-    _ALIGN_CACHE[key] = (out, climatology,
-                         tuple(predictions.coords[k].data for k in tkeys))
+    _ALIGN_CACHE[key] = (out, climatology, guards)
     while len(_ALIGN_CACHE) > 64:
       _ALIGN_CACHE.popitem(last=False)
+  return out
+
+
+_REORDER_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
+
+
+def _label_ordered_climatology(predictions: xl.DataArray,
+                               climatology: xl.DataArray) -> xl.DataArray:
+  """The climatology with its grid coordinates in the label order of the
+  predictions (xl.reorder_like).  A re-ordered copy is made once per
+  (climatology, label order) and keeps its identity across chunks, so the
+  statistics of later chunks still share launches and plans."""
+  differing = []
+  for d in climatology.dims:
+    if d in predictions.dims and d in predictions.coords and (
+        d in climatology.coords):
+      a, b = climatology.coords[d], predictions.coords[d]
+      if a.data is not b.data and not np.array_equal(a.to_numpy(),
+                                                     b.to_numpy()):
+        differing.append((d, np.ascontiguousarray(b.to_numpy()).tobytes()))
+  if not differing:
+    return climatology
+  key = (id(climatology), id(climatology.data), tuple(differing))
+  with _CACHE_LOCK:
+    hit = _REORDER_CACHE.get(key)
+    if hit is not None and hit[1]() is climatology:
+      _REORDER_CACHE.move_to_end(key)
+      return hit[0]
+  out = xl.reorder_like(climatology, predictions, 'climatology')
+  with _CACHE_LOCK:
+    _REORDER_CACHE[key] = (out, weakref.ref(climatology))
+    while len(_REORDER_CACHE) > 8:
+      _REORDER_CACHE.popitem(last=False)
   return out
 
 

@@ -97,12 +97,33 @@ def to_netcdf(dataset: Mapping[str, xl.DataArray], path: str) -> None:
         f.createDimension(name, size)
       return name
 
-    written = set()
+    written: dict = {}   # legal NetCDF name -> (original name, host values)
 
-    def write_var(name, dims, values, extra):
+    def write_var(name, dims, values, extra, is_coord=False):
+      """Writes one variable and returns its NetCDF name.  A coordinate that
+      several variables share is written once -- but only if it IS the same
+      coordinate: equal name and different values raise instead of silently
+      keeping the first.  Data variables whose names collide after replacing
+      the characters NetCDF-3 forbids get a numeric suffix (the original name
+      is kept in the `wbx_name` attribute and restored on reading)."""
       nc_name = _legal(name)
+      raw_values = np.asarray(values)
       if nc_name in written:
-        return
+        prev_name, prev_values = written[nc_name]
+        if is_coord and prev_name == str(name):
+          same = (prev_values.shape == raw_values.shape and (
+              np.array_equal(prev_values, raw_values) or (
+                  prev_values.dtype.kind == 'f' and raw_values.dtype.kind == 'f'
+                  and np.array_equal(prev_values, raw_values, equal_nan=True))))
+          if same:
+            return nc_name
+          raise ValueError(
+              f'coordinate {name!r} has different values on two variables of '
+              'one file; rename one of them before writing')
+        k = 2
+        while f'{nc_name}_{k}' in written:
+          k += 1
+        nc_name = f'{nc_name}_{k}'
       values, attrs = _encode(values)
       nc_dims = [need_dim(d, n) for d, n in zip(dims, values.shape)]
       if values.ndim > len(dims):  # char arrays
@@ -118,7 +139,8 @@ def to_netcdf(dataset: Mapping[str, xl.DataArray], path: str) -> None:
         setattr(var, k, v)
       if nc_name != str(name):
         var.wbx_name = str(name)
-      written.add(nc_name)
+      written[nc_name] = (str(name), raw_values)
+      return nc_name
 
     for name, da in dataset.items():
       da = xl.as_data_array(da)
@@ -126,9 +148,9 @@ def to_netcdf(dataset: Mapping[str, xl.DataArray], path: str) -> None:
       for cname, cv in da.coords.items():
         if cname == 'mask':
           continue
-        write_var(cname, cv.dims, cv.to_numpy(), {})
+        nc_cname = write_var(cname, cv.dims, cv.to_numpy(), {}, is_coord=True)
         if cv.dims != (cname,):
-          coord_names.append(_legal(cname))
+          coord_names.append(nc_cname)
       extra = {'coordinates': ' '.join(coord_names)} if coord_names else {}
       write_var(name, da.dims, da.to_numpy(), extra)
     f.close()

@@ -42,6 +42,8 @@ import threading
 import time
 from typing import Callable, Mapping, Optional
 
+import numpy as np
+
 from weatherbenchx_b200 import aggregation
 from weatherbenchx_b200 import distributed
 from weatherbenchx_b200 import io_netcdf
@@ -271,6 +273,42 @@ def _unplain(item: tuple) -> xl.DataArray:
       k: xl.DataArray(v, d) for k, (d, v) in coords.items()}, name=name)
 
 
+def _fingerprint(times, metrics, aggregators) -> str:
+  """Identifies an evaluation for checkpoint resume: the unique names of the
+  statistics behind every metric, the aggregator settings and the init / lead
+  times with their chunking.  A checkpoint with another fingerprint holds
+  partial sums of a different computation and must not be merged."""
+  import hashlib  # pylint: disable=g-import-not-at-top
+  h = hashlib.sha256()
+  for name in sorted(metrics, key=str):
+    metric = metrics[name]
+    stats = sorted(s.unique_name for s in metric.statistics.values())
+    h.update(repr((str(name), type(metric).__name__, stats)).encode())
+  for name in sorted(aggregators, key=str):
+    agg = aggregators[name]
+    h.update(repr((
+        str(name), type(agg).__name__,
+        sorted(map(str, getattr(agg, 'reduce_dims', ()))),
+        [(type(b).__name__, getattr(b, 'bin_dim_name', None))
+         for b in getattr(agg, 'bin_by', None) or []],
+        [type(w).__name__ for w in getattr(agg, 'weigh_by', None) or []],
+        bool(getattr(agg, 'masked', False)),
+        bool(getattr(agg, 'skipna', False)))).encode())
+  for attr in ('init_times', 'lead_times'):
+    values = getattr(times, attr, None)
+    if values is not None and not isinstance(values, slice):
+      h.update(attr.lstrip('_').encode())
+      h.update(np.ascontiguousarray(np.asarray(values)).tobytes())
+    elif isinstance(values, slice):
+      h.update(repr(values).encode())
+  h.update(repr((len(times),
+                 getattr(times, 'init_time_chunk_size', None) or
+                 getattr(times, '_init_time_chunk_size', None),
+                 getattr(times, 'lead_time_chunk_size', None) or
+                 getattr(times, '_lead_time_chunk_size', None))).encode())
+  return h.hexdigest()
+
+
 def _atomic_pickle(path: str, payload) -> None:
   directory = os.path.dirname(os.path.abspath(path)) or '.'
   os.makedirs(directory, exist_ok=True)
@@ -297,6 +335,7 @@ def run_pipeline(
     group=None,
     progress: Optional[Callable[[int, int], None]] = None,
     require_output: bool = True,
+    shard: bool = True,
 ) -> dict:
   """Evaluates ``metrics`` over every chunk of ``times``.
 
@@ -328,6 +367,9 @@ def run_pipeline(
     progress: optional callback (chunks done on this rank, chunks of this rank).
     require_output: the reference insists on at least one output path
       (beam_pipeline.py:541-545); pass False to only get the return value.
+    shard: False makes this process evaluate EVERY chunk on its own, with no
+      collective, even inside an initialised process group (the monolithic
+      run a sharded result is compared with).
   """
   if isinstance(aggregator, Mapping):
     aggregators = dict(aggregator)
@@ -343,16 +385,23 @@ def run_pipeline(
         'At least one of (metrics) out_path or aggregation_state_out_path must '
         'be specified.')
 
-  rank, world_size = distributed.world()
+  rank, world_size = distributed.world() if shard else (0, 1)
   mine = distributed.shard_units(list(range(len(times))), rank, world_size)
   acc = _Accumulator()
   done: list = []
   ckpt_file = None
+  fingerprint = _fingerprint(times, metrics, aggregators)
   if checkpoint_path is not None:
     ckpt_file = f'{checkpoint_path}.rank{rank}of{world_size}.pkl'
     if os.path.exists(ckpt_file):
       with open(ckpt_file, 'rb') as f:
         saved = pickle.load(f)
+      if saved.get('fingerprint') != fingerprint:
+        raise ValueError(
+            f'{ckpt_file} was written by a different evaluation (other '
+            'metrics, aggregators, init / lead times or chunking); partial '
+            'sums of different runs must not be merged -- remove it or use '
+            'another checkpoint_path')
       if saved.get('n_chunks') == len(times) and set(
           saved['done']) <= set(mine):
         acc.load(saved['acc'])
@@ -379,20 +428,22 @@ def run_pipeline(
       progress(len(done), len(mine))
     if ckpt_file and checkpoint_every and since_ckpt >= checkpoint_every:
       _atomic_pickle(ckpt_file, {'n_chunks': len(times), 'done': done,
-                                 'acc': acc.dump()})
+                                 'acc': acc.dump(),
+                                 'fingerprint': fingerprint})
       since_ckpt = 0
   if ckpt_file and since_ckpt:
     _atomic_pickle(ckpt_file, {'n_chunks': len(times), 'done': done,
-                               'acc': acc.dump()})
+                               'acc': acc.dump(), 'fingerprint': fingerprint})
 
   results = {}
   local = acc.states(aggregators)
   for name in aggregators:
-    state = distributed.all_reduce_state(local[name], group=group)
+    state = (distributed.all_reduce_state(local[name], group=group)
+             if shard else local[name])
     values = (state.metric_values(metrics)
               if state.sum_weighted_statistics is not None else xl.Dataset())
     results[name] = (state, values)
-    if rank != 0:
+    if rank != 0 or not (shard or distributed.world()[0] == 0):
       continue
     if out_path is not None:
       io_netcdf.to_netcdf(values, _resolve_out_path(out_path, name))

@@ -295,6 +295,16 @@ class DataArray:
                   for k in key)
       new_dims = tuple(d for d, k in zip(arr.dims, key)
                        if not isinstance(k, numbers.Integral))
+      if _is_device(arr._data) and any(isinstance(k, np.ndarray) for k in key):
+        import torch  # pylint: disable=g-import-not-at-top
+        payload = arr._data
+        for axis, k in enumerate(key):   # one index_select per array indexer
+          if isinstance(k, np.ndarray):
+            payload = payload.index_select(
+                axis, torch.as_tensor(k.astype(np.int64), device=payload.device))
+        rest = tuple(slice(None) if isinstance(k, np.ndarray) else k
+                     for k in key)
+        return payload[rest], new_dims
       return arr._data[key], new_dims
 
     payload, new_dims = apply(self)
@@ -633,6 +643,44 @@ def _check_index_coords(a: DataArray, b: DataArray):
               'only supports exact alignment')
 
 
+def reorder_like(da: DataArray, ref: DataArray, what: str = 'operand'
+                 ) -> DataArray:
+  """``da`` with its index coordinates in the label order of ``ref``.
+
+  xarray aligns the operands of arithmetic and of ``xr.dot`` by coordinate
+  LABEL, never by position.  Equal labels: ``da`` is returned as is; the same
+  labels in another order (e.g. a climatology or a land-sea mask stored with
+  descending latitude): a re-ordered copy; different label sets: ValueError
+  (only exact alignment is provided).
+  """
+  indexers = {}
+  for d in da.dims:
+    if d not in ref.dims:
+      continue
+    a, b = da._coords.get(d), ref._coords.get(d)  # pylint: disable=protected-access
+    if a is None or b is None or a._data is b._data:  # pylint: disable=protected-access
+      continue
+    la, lb = a.to_numpy(), b.to_numpy()
+    if la.shape != lb.shape:
+      raise ValueError(
+          f'{what}: size mismatch along {d!r}: {la.shape[0]} vs {lb.shape[0]} '
+          '(only exact alignment is supported)')
+    if np.array_equal(la, lb):
+      continue
+    order = np.argsort(la, kind='stable')
+    pos = np.clip(np.searchsorted(la[order], lb), 0, len(la) - 1)
+    found = order[pos]
+    if (not np.array_equal(la[found], lb) or
+        len(np.unique(found)) != len(found)):
+      raise ValueError(
+          f'{what}: index coordinate {d!r} holds different labels than the '
+          'data (only exact alignment is supported)')
+    indexers[d] = found
+  if not indexers:
+    return da
+  return da.isel(indexers)
+
+
 def _broadcast_pair(a: DataArray, b: DataArray):
   _check_index_coords(a, b)
   dims = a.dims + tuple(d for d in b.dims if d not in a.dims)
@@ -850,6 +898,66 @@ class Dataset(dict):
 
   def map(self, fn):
     return Dataset({k: fn(v) for k, v in self.items()})
+
+
+class DataTree:
+  """The subset of ``xr.DataTree`` that AggregationState serialisation uses
+  (aggregation.py:203-265 of the reference): a node holds a Dataset and named
+  children; ``to_dict`` / ``from_dict`` map between a tree and
+  ``{'/path/to/node': Dataset}``."""
+
+  def __init__(self, dataset=None, children: Mapping | None = None,
+               name: str | None = None):
+    self.dataset = Dataset(dataset or {})
+    self.name = name
+    self.children: dict = {}
+    for key, child in (children or {}).items():
+      if not isinstance(child, DataTree):
+        raise TypeError(f'child {key!r} is not a DataTree')
+      if '/' in str(key):
+        raise ValueError(f"node names cannot contain '/': {key!r}")
+      child.name = str(key)
+      self.children[str(key)] = child
+
+  def __getitem__(self, path: str):
+    node = self
+    for part in [p for p in str(path).split('/') if p]:
+      if part in node.children:
+        node = node.children[part]
+      elif part in node.dataset:
+        return node.dataset[part]
+      else:
+        raise KeyError(path)
+    return node
+
+  @property
+  def subtree(self):
+    """(path, node) pairs, depth first, the root ('/') first."""
+    stack = [('/', self)]
+    while stack:
+      path, node = stack.pop(0)
+      yield path, node
+      base = path.rstrip('/')
+      stack = [(f'{base}/{k}', c) for k, c in node.children.items()] + stack
+
+  def to_dict(self) -> dict:
+    return {path: Dataset(node.dataset) for path, node in self.subtree}
+
+  @classmethod
+  def from_dict(cls, d: Mapping, name: str | None = None) -> 'DataTree':
+    root = cls(name=name)
+    for path, dataset in d.items():
+      node = root
+      for part in [p for p in str(path).split('/') if p]:
+        if part not in node.children:
+          node.children[part] = cls(name=part)
+        node = node.children[part]
+      node.dataset = Dataset(dataset or {})
+    return root
+
+  def __repr__(self):
+    return (f'<wbx DataTree {self.name!r} vars={list(self.dataset)} '
+            f'children={list(self.children)}>')
 
 
 # ---------------------------------------------------------------------------
