@@ -51,10 +51,20 @@ enum {
   WBX_FLAG_MASKED = 2, /* Aggregator(masked=True) with a 'mask' coordinate   */
   WBX_FLAG_FORCE_LDG = 16, /* tuning/debug: bypass the TMA ring              */
   WBX_FLAG_FORCE_TMA = 32, /* tuning/debug: fail instead of falling back     */
-  WBX_FLAG_CLIM_DEVICE = 64 /* WBX_SPACE_HOST plans only: the clim addresses
+  WBX_FLAG_CLIM_DEVICE = 64, /* WBX_SPACE_HOST plans only: the clim addresses
                                are device pointers (a climatology kept on the
                                GPU across the chunks of an evaluation); only
                                pred / target / mask are streamed             */
+  WBX_FLAG_TARGET_DEVICE = 128, /* WBX_SPACE_HOST plans only: the target
+                               addresses are device pointers -- analysis rows
+                               that consecutive (init, lead) chunks share
+                               (valid_time = init_time + lead_time,
+                               data_loaders/xarray_loaders.py:242-263) are
+                               uploaded once and kept on the GPU; only the
+                               predictions (and a host mask) are streamed    */
+  WBX_FLAG_MASK_DEVICE = 256 /* WBX_SPACE_HOST plans only: the mask addresses
+                               are device pointers (the mask coordinate of
+                               device-resident targets)                      */
 };
 
 /* Slots of the fused deterministic statistics (unique_name in comments). */

@@ -643,7 +643,7 @@ def test_masked_aggregation_launches_unmasked_statistics_separately(
     launches.append((sorted(s.kind for s in stat_list), masked))
     return ('spec', [s.kind for s in stat_list])
 
-  def run(pairs):
+  def run(pairs, leaves=None):
     return [{kind: (xl.DataArray(1.0), xl.DataArray(1.0))
              for kind in spec[1]} for spec, _ in pairs]
 

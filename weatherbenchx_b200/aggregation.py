@@ -23,6 +23,7 @@ from typing import Any, Callable, Collection, Hashable, Iterable, Mapping, Seque
 import numpy as np
 
 from weatherbenchx_b200 import engine
+from weatherbenchx_b200 import fastpath
 from weatherbenchx_b200 import xarray_lite as xl
 from weatherbenchx_b200 import xarray_tree
 from weatherbenchx_b200.lazy import LazyEnsembleAveraged
@@ -414,6 +415,7 @@ class Aggregator:
           continue
         stat = xl.as_data_array(stat)
         if isinstance(stat, LazyEnsembleAveraged) and stat.is_lazy:
+          fastpath.not_recordable()
           if self.skipna or (stat.skipna_ensemble and not stat.optimistic):
             # NaN skipping happens per point after / inside the member mean
             results[stat_name][var] = self._aggregate_generic(stat)
@@ -421,6 +423,7 @@ class Aggregator:
             averaged.setdefault(stat.ensemble_dim, []).append(
                 (stat_name, var, stat))
         elif isinstance(stat, LazySumStatistic) and stat.is_lazy:
+          fastpath.not_recordable()
           if self.skipna:
             # NaN of the SUM decides what is skipped: needs the summed field
             results[stat_name][var] = self._aggregate_generic(stat)
@@ -436,6 +439,7 @@ class Aggregator:
         elif isinstance(stat, LazyStatistic) and stat.is_lazy:
           groups[(var,) + stat.group_key()[:2]].append((stat_name, var, stat))
         else:
+          fastpath.not_recordable()
           results[stat_name][var] = self._aggregate_generic(stat)
     # Statistics of the same (predictions, targets) share one launch; those
     # that need a climatology define it (one sub-group per climatology).
@@ -495,6 +499,7 @@ class Aggregator:
       try:
         if first.kind in engine.CRPS_SLOT:
           if self.bin_by or not set(self.reduce_dims).issubset(first.dims):
+            fastpath.not_recordable()
             fused = self._fused_group(stats)
             for stat_name, var, s in members:
               results[stat_name][var] = fused[s.kind]
@@ -523,17 +528,23 @@ class Aggregator:
             skipna=self.skipna, bin_masks=bins[0], bin_dim_names=bins[1])
         planned.append((members, spec, stats))
       except engine.FastPathUnavailable:
+        fastpath.not_recordable()
         for stat_name, var, s in members:
           results[stat_name][var] = self._aggregate_generic(s)
     if planned_crps:
       outs = engine.run_crps_specs(
-          [(spec, stats) for _, spec, stats in planned_crps])
+          [(spec, stats) for _, spec, stats in planned_crps],
+          leaves=[[(n, v, s.kind, s.name) for n, v, s in members]
+                  for members, _, _ in planned_crps])
       for (members, _, _), out in zip(planned_crps, outs):
         for stat_name, var, s in members:
           results[stat_name][var] = AggregationState(*out[s.kind])
     if planned:
       # variables that share grid, flags and weights go out as ONE launch
-      outs = engine.run_fused_specs([(spec, stats) for _, spec, stats in planned])
+      outs = engine.run_fused_specs(
+          [(spec, stats) for _, spec, stats in planned],
+          leaves=[[(n, v, s.kind, s.name) for n, v, s in members]
+                  for members, _, _ in planned])
       for (members, _, _), out in zip(planned, outs):
         for stat_name, var, s in members:
           results[stat_name][var] = AggregationState(*out[s.kind])
@@ -599,8 +610,24 @@ def _add_states(states, scale: float = 1.0):
 def compute_metric_values_for_single_chunk(
     metrics: Mapping[str, metrics_base.Metric], aggregator: Aggregator,
     predictions, targets) -> xl.Dataset:
-  """Metric values for one predictions/targets pair (no accumulation)."""
-  statistics = metrics_base.compute_unique_statistics_for_all_metrics(
-      metrics, predictions, targets)
-  return aggregator.aggregate_statistics(statistics).metric_values(metrics)
+  """Metric values for one predictions/targets pair (no accumulation).
 
+  aggregation.py:411-435 of the reference.  A call is planned once: when the
+  same metrics and aggregator meet the same device-resident arrays again (the
+  steady state of a loop over chunks that are refilled in place), the launches
+  recorded the first time are replayed without any labelled-array work and
+  the values come back as a Dataset that is decoded when it is first read
+  (fastpath.py), so the host work of chunk i overlaps the kernels of chunk
+  i + 1.
+  """
+  key = fastpath.chunk_key(metrics, aggregator, predictions, targets)
+  compiled = fastpath.lookup(key)
+  if compiled is not None:
+    return compiled.run()
+  with fastpath.recording() as recorder:
+    statistics = metrics_base.compute_unique_statistics_for_all_metrics(
+        metrics, predictions, targets)
+    state = aggregator.aggregate_statistics(statistics)
+  values = state.metric_values(metrics)
+  fastpath.compile_chunk(key, recorder, metrics, values)
+  return values

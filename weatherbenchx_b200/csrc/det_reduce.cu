@@ -327,6 +327,10 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
   const bool masked = (d->flags & WBX_FLAG_MASKED) != 0;
   WBX_REQUIRE(masked == (d->mask != nullptr),
               "det: WBX_FLAG_MASKED and a mask table must be given together");
+  WBX_REQUIRE(d->space == WBX_SPACE_HOST ||
+                  !(d->flags & (WBX_FLAG_CLIM_DEVICE | WBX_FLAG_TARGET_DEVICE |
+                                WBX_FLAG_MASK_DEVICE)),
+              "det: WBX_FLAG_*_DEVICE only apply to WBX_SPACE_HOST plans");
   WBX_REQUIRE(d->cell[0] == 0, "det: cell[0] must be 0");
   for (int64_t j = 1; j < d->n_jobs; ++j) {
     const int step = d->cell[j] - d->cell[j - 1];
@@ -461,11 +465,19 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
 
   const int64_t slab = d->ny * d->nx;
   bool aligned = (slab % 4) == 0 && (!p->has_mask || (slab % 16) == 0);
-  if (aligned && d->space == WBX_SPACE_DEVICE) {
+  {
+    // operands the kernel reads in place (device space, or the *_DEVICE
+    // operands of a host-space plan) must be 16-byte aligned for the TMA path;
+    // staged operands land in aligned staging buffers.
+    const bool dev = d->space == WBX_SPACE_DEVICE;
+    const bool chk_t = dev || (d->flags & WBX_FLAG_TARGET_DEVICE);
+    const bool chk_c = p->has_clim && (dev || (d->flags & WBX_FLAG_CLIM_DEVICE));
+    const bool chk_m = p->has_mask && (dev || (d->flags & WBX_FLAG_MASK_DEVICE));
     for (int64_t j = 0; j < d->n_jobs && aligned; ++j) {
-      aligned = (d->pred[j] % 16) == 0 && (d->target[j] % 16) == 0 &&
-                (!p->has_clim || (d->clim[j] % 16) == 0) &&
-                (!p->has_mask || (d->mask[j] % 16) == 0);
+      aligned = (!dev || (d->pred[j] % 16) == 0) &&
+                (!chk_t || (d->target[j] % 16) == 0) &&
+                (!chk_c || (d->clim[j] % 16) == 0) &&
+                (!chk_m || (d->mask[j] % 16) == 0);
     }
   }
   // tile: 4096 elements (16 KiB per operand) unless the slab is smaller.
@@ -664,8 +676,15 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
   // (it is reused by every chunk of an evaluation); only the fields stream.
   const bool stage_clim =
       plan->has_clim && !(plan->flags & WBX_FLAG_CLIM_DEVICE);
-  const size_t job_bytes =
-      fbytes * (stage_clim ? 3 : 2) + (plan->has_mask ? mbytes : 0);
+  // WBX_FLAG_TARGET_DEVICE / MASK_DEVICE: targets (and their mask) are kept on
+  // the GPU by the caller (rows shared by consecutive chunks); only the
+  // predictions cross PCIe.
+  const bool stage_tgt = !(plan->flags & WBX_FLAG_TARGET_DEVICE);
+  const bool stage_mask =
+      plan->has_mask && !(plan->flags & WBX_FLAG_MASK_DEVICE);
+  const size_t job_bytes = fbytes * (1 + (stage_tgt ? 1 : 0) +
+                                     (stage_clim ? 1 : 0)) +
+                           (stage_mask ? mbytes : 0);
   int64_t per_chunk = static_cast<int64_t>((ctx->staging_bytes / 2) / job_bytes);
   per_chunk = std::max<int64_t>(1, std::min<int64_t>(per_chunk, plan->n_jobs));
   for (int b = 0; b < 2; ++b) {
@@ -688,7 +707,7 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     unsigned char* sbase = ctx->staging[buf].as<unsigned char>();
     unsigned char* s_pred = sbase;
     unsigned char* s_tgt = s_pred + nj * fbytes;
-    unsigned char* s_clim = s_tgt + nj * fbytes;
+    unsigned char* s_clim = s_tgt + (stage_tgt ? nj * fbytes : 0);
     unsigned char* s_mask = s_clim + (stage_clim ? nj * fbytes : 0);
     // Before overwriting this staging buffer, wait for the kernel that last
     // read it.
@@ -714,13 +733,15 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     };
     int rc = copy_operand(plan->pred, s_pred, fbytes, fbytes);
     if (rc != WBX_OK) return rc;
-    rc = copy_operand(plan->target, s_tgt, fbytes, fbytes);
-    if (rc != WBX_OK) return rc;
+    if (stage_tgt) {
+      rc = copy_operand(plan->target, s_tgt, fbytes, fbytes);
+      if (rc != WBX_OK) return rc;
+    }
     if (stage_clim) {
       rc = copy_operand(plan->clim, s_clim, fbytes, fbytes);
       if (rc != WBX_OK) return rc;
     }
-    if (plan->has_mask) {
+    if (stage_mask) {
       rc = copy_operand(plan->mask, s_mask, slab, mbytes);
       if (rc != WBX_OK) return rc;
     }
@@ -755,13 +776,16 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     uint64_t* h_mask = reinterpret_cast<uint64_t*>(host.data() + o_mask);
     for (size_t j = 0; j < nj; ++j) {
       h_pred[j] = reinterpret_cast<uint64_t>(s_pred + j * fbytes);
-      h_tgt[j] = reinterpret_cast<uint64_t>(s_tgt + j * fbytes);
+      h_tgt[j] = stage_tgt ? reinterpret_cast<uint64_t>(s_tgt + j * fbytes)
+                           : plan->target[j0 + j];
       if (plan->has_clim)
         h_clim[j] = stage_clim
                         ? reinterpret_cast<uint64_t>(s_clim + j * fbytes)
                         : plan->clim[j0 + j];
       if (plan->has_mask)
-        h_mask[j] = reinterpret_cast<uint64_t>(s_mask + j * mbytes);
+        h_mask[j] = stage_mask
+                        ? reinterpret_cast<uint64_t>(s_mask + j * mbytes)
+                        : plan->mask[j0 + j];
     }
     if (plan->has_wo)
       memcpy(host.data() + o_wo, plan->wo.data() + j0, nj * 8);

@@ -19,6 +19,7 @@ a pinned or memory-mapped array goes to the GPU straight from its source.
 
 from __future__ import annotations
 
+import threading
 from typing import Hashable, Iterable, Mapping, Optional
 
 import numpy as np
@@ -123,8 +124,117 @@ class PredictionsFromArrays(_ArrayLoader):
     return out
 
 
+class _DeviceRows:
+  """Rows of one analysis array along ``valid_time`` kept on the GPU.
+
+  Consecutive (init, lead) chunks of an evaluation share most of their target
+  rows (valid_time = init_time + lead_time: with 12-hourly init times and
+  6-hourly lead times 10 of the 12 rows of an (init=1, lead=12) chunk were
+  already needed by the chunk before).  The reference re-reads them from its
+  Zarr store for every chunk (xarray_loaders.py:242-263); a B200 has 180 GB of
+  HBM, so each row is uploaded ONCE, the first time a chunk needs it, and
+  stays.  The device array is allocated in full (address space only; pages
+  are touched row by row) and rows are filled lazily.
+  """
+
+  def __init__(self, da: xl.DataArray, device):
+    import torch  # pylint: disable=g-import-not-at-top
+    self._host = da.data
+    self._lock = threading.Lock()
+    self._present = np.zeros(da.shape[0], bool)
+    self.device = torch.device('cuda', device)
+    self.rows = torch.empty(tuple(da.shape), dtype=torch.float32,
+                            device=self.device)
+    self._stream = torch.cuda.Stream(self.device)
+    self.uploaded_bytes = 0
+
+  def ensure(self, positions: np.ndarray):
+    """Uploads the rows at ``positions`` that are not on the device yet and
+    returns after they have arrived (called from the loader thread, which
+    runs ahead of the GPU)."""
+    import torch  # pylint: disable=g-import-not-at-top
+    with self._lock:
+      need = np.unique(positions)
+      need = need[~self._present[need]]
+      if not len(need):
+        return
+      runs = np.split(need, np.nonzero(np.diff(need) != 1)[0] + 1)
+      with torch.cuda.stream(self._stream):
+        for run in runs:
+          lo, hi = int(run[0]), int(run[-1]) + 1
+          src = self._host[lo:hi]
+          if src.dtype != np.float32:
+            src = src.astype(np.float32)
+          self.rows[lo:hi].copy_(torch.from_numpy(np.ascontiguousarray(src)),
+                                 non_blocking=True)
+          self.uploaded_bytes += (hi - lo) * self.rows[0].numel() * 4
+      self._stream.synchronize()
+      self._present[need] = True
+
+
 class TargetsFromArrays(_ArrayLoader):
-  """Analyses / observations on a grid with dim valid_time."""
+  """Analyses / observations on a grid with dim valid_time.
+
+  ``device_cache=True`` keeps every target row a chunk has needed on the GPU
+  (see ``_DeviceRows``): chunks then come back as device arrays -- strided
+  views of the resident rows -- and only the predictions of a chunk cross
+  PCIe.  ``device_cache_bytes`` bounds the HBM one loader may claim (default:
+  half of what is free at first use); variables that do not fit, whose
+  ``valid_time`` is not the leading dim, or that already live on the device
+  are served from where they are.
+  """
+
+  def __init__(self, ds, *args, device_cache: bool = False,
+               device_cache_bytes: Optional[int] = None,
+               device: Optional[int] = None, **kwargs):
+    super().__init__(ds, *args, **kwargs)
+    self._device_cache = bool(device_cache)
+    self._device_cache_bytes = device_cache_bytes
+    self._device = device
+    self._resident: dict = {}
+    self._claimed = 0
+    self._resident_lock = threading.Lock()
+
+  def __getstate__(self):
+    state = dict(self.__dict__)
+    state['_resident'] = {}      # device memory is per process
+    state['_claimed'] = 0
+    state.pop('_resident_lock', None)
+    return state
+
+  def __setstate__(self, state):
+    self.__dict__.update(state)
+    self._resident_lock = threading.Lock()
+
+  @property
+  def uploaded_bytes(self) -> int:
+    """Bytes sent to the device by the cache so far (each row once)."""
+    return sum(r.uploaded_bytes for r in self._resident.values()
+               if r is not None)
+
+  def _device_rows(self, var, da):
+    """The resident rows of ``var``, or None when it is not cached."""
+    if not self._device_cache or da.is_device or not da.dims or (
+        da.dims[0] != 'valid_time'):
+      return None
+    with self._resident_lock:
+      if var in self._resident:
+        return self._resident[var]
+      import torch  # pylint: disable=g-import-not-at-top
+      if not torch.cuda.is_available():
+        raise RuntimeError('device_cache=True needs a CUDA device')
+      device = (torch.cuda.current_device() if self._device is None
+                else self._device)
+      if self._device_cache_bytes is None:
+        free, _ = torch.cuda.mem_get_info(device)
+        self._device_cache_bytes = free // 2
+      nbytes = int(np.prod(da.shape, dtype=np.int64)) * 4
+      rows = None
+      if self._claimed + nbytes <= self._device_cache_bytes:
+        rows = _DeviceRows(da, device)
+        self._claimed += nbytes
+      self._resident[var] = rows
+      return rows
 
   def _load_chunk_from_source(self, init_times, lead_times=None):
     if isinstance(lead_times, slice):
@@ -142,14 +252,19 @@ class TargetsFromArrays(_ArrayLoader):
       valid = init_times[:, None] + lead[None, :]
       pos = _positions(index, valid, 'valid_time')
       axis = da.dims.index('valid_time')
-      payload = _window_view(da.data, axis, pos)
+      source = da.data
+      resident = self._device_rows(var, da)
+      if resident is not None:
+        resident.ensure(pos.ravel())
+        source = resident.rows
+      payload = _window_view(source, axis, pos)
       if payload is None:
-        if da.is_device:
+        if xl._is_device(source):  # pylint: disable=protected-access
           import torch  # pylint: disable=g-import-not-at-top
-          flat = torch.as_tensor(pos.ravel(), device=da.data.device)
-          payload = da.data.index_select(axis, flat)
+          flat = torch.as_tensor(pos.ravel(), device=source.device)
+          payload = source.index_select(axis, flat)
         else:
-          payload = np.take(da.data, pos.ravel(), axis=axis)
+          payload = np.take(source, pos.ravel(), axis=axis)
         shape = list(payload.shape)
         shape[axis:axis + 1] = list(pos.shape)
         payload = payload.reshape(shape)

@@ -26,7 +26,10 @@ def add_nan_mask_to_data(data: Mapping[Hashable, xl.DataArray],
   for var, da in data.items():
     da = xl.as_data_array(da)
     if variable_subset is None or var in variable_subset:
-      mask = xl.DataArray(~np.isnan(da.to_numpy()), da.dims)
+      if da.is_device:  # device-resident rows: the mask is made there too
+        mask = xl.DataArray(~da.data.isnan(), da.dims)
+      else:
+        mask = xl.DataArray(~np.isnan(da.to_numpy()), da.dims)
       da = da.assign_coords(mask=mask)
     out[var] = da
   return out

@@ -130,9 +130,31 @@ def unpack_state(flat: np.ndarray, layout: list) -> aggregation.AggregationState
 # ---------------------------------------------------------------------------
 
 
+def _same_layout_everywhere(digest: str, n_values: int, group, backend,
+                           device) -> bool:
+  """True if every rank of the group holds the same state layout: ONE small
+  fixed-size all-reduce(MAX) over [h, -h, n, -n] words of the layout digest
+  (max(x) == -max(-x) for every word iff all ranks agree) -- no pickling, no
+  object gather."""
+  import torch  # pylint: disable=g-import-not-at-top
+  dist = _dist()
+  words = [int(digest[i:i + 12], 16) for i in range(0, 48, 12)] + [n_values]
+  probe = torch.tensor(words + [-w for w in words], dtype=torch.int64)
+  if backend == 'nccl':
+    probe = probe.to(device)
+  dist.all_reduce(probe, op=dist.ReduceOp.MAX, group=group)
+  probe = probe.cpu().tolist()
+  k = len(words)
+  return all(probe[i] == -probe[k + i] for i in range(k))
+
+
 def all_reduce_state(state: aggregation.AggregationState, group=None,
                      device=None) -> aggregation.AggregationState:
-  """Sum of the AggregationStates of all ranks (every rank gets the result)."""
+  """Sum of the AggregationStates of all ranks (every rank gets the result).
+
+  Two collectives when every rank holds the same structure (the usual case:
+  reduced init_time): a 10-word agreement probe and the packed float64
+  all-reduce of [sum_weighted_statistics || sum_weights]."""
   import torch  # pylint: disable=g-import-not-at-top
   dist = _dist()
   rank, size = world()
@@ -141,15 +163,17 @@ def all_reduce_state(state: aggregation.AggregationState, group=None,
   del rank
   layout = state_layout(state)
   digest = layout_digest(layout)
-  digests = [None] * size
-  dist.all_gather_object(digests, digest, group=group)
   backend = dist.get_backend(group)
-  if all(d == digests[0] for d in digests) and layout:
+  dev = None
+  if backend == 'nccl':
+    dev = torch.device('cuda', torch.cuda.current_device()
+                       if device is None else device)
+  n_values = 2 * sum(int(np.prod(shape, dtype=np.int64)) if shape else 1
+                     for _, _, shape, _ in layout)
+  if _same_layout_everywhere(digest, n_values, group, backend, dev) and layout:
     # fast path: one packed float64 all-reduce.
     flat = pack_state(state, layout)
     if backend == 'nccl':
-      dev = torch.device('cuda', torch.cuda.current_device()
-                         if device is None else device)
       buf = torch.from_numpy(flat).to(dev)
     else:
       buf = torch.from_numpy(flat.copy())

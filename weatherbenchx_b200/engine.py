@@ -20,7 +20,7 @@ import collections
 import dataclasses
 import threading
 import weakref
-from typing import Hashable, Mapping, Sequence
+from typing import Any, Hashable, Mapping, Sequence
 
 import numpy as np
 
@@ -257,6 +257,8 @@ _CACHE_LOCK = threading.RLock()
 
 
 def clear_plan_cache():
+  from weatherbenchx_b200 import fastpath  # pylint: disable=g-import-not-at-top
+  fastpath.clear()
   with _CACHE_LOCK:
     plans = list(_PLAN_CACHE.values())
     _PLAN_CACHE.clear()
@@ -273,13 +275,12 @@ def _plan_cache_lookup(ctx, key):
 
 
 def _plan_cache_insert(ctx, key, plan):
+  # An evicted plan is only dropped here: it is destroyed when its last user
+  # lets go of it (a compiled chunk of fastpath.py may still launch it).
   with _CACHE_LOCK:
     _PLAN_CACHE[(key, id(ctx))] = plan
-    evicted = []
     while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-      evicted.append(_PLAN_CACHE.popitem(last=False)[1])
-  for old in evicted:
-    old.close()
+      _PLAN_CACHE.popitem(last=False)
 
 
 def _job_offsets(job_dims, job_sizes, strides: Mapping) -> np.ndarray:
@@ -679,18 +680,18 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
   if mask_da is not None:
     mask_da = contiguous_operand(mask_da)
 
-  # ---- memory space: all host -> streamed by the library; else all device.
-  fields = [pred, tgt] + [x for x in (clim_da, mask_da) if x is not None]
-  streamed = [pred, tgt] + ([mask_da] if mask_da is not None else [])
-  clim_on_device = False
-  if (clim_da is not None and clim_da.is_device and
-      not any(f.is_device for f in streamed)):
-    # host fields against a climatology kept on the GPU: stream the fields,
-    # address the climatology rows where they are
-    clim_on_device = True
-  elif (any(f.is_device for f in fields) and
-        not all(f.is_device for f in fields)):
-    pred, tgt = to_device(pred, device), to_device(tgt, device)
+  # ---- memory space.  Predictions in host memory: a host-space plan, the
+  # library streams them; targets / mask / climatology that already live on
+  # the GPU (rows kept there across the chunks of an evaluation) are addressed
+  # where they are (WBX_FLAG_*_DEVICE).  Predictions on the GPU: everything
+  # else is brought to the device.
+  clim_on_device = target_on_device = mask_on_device = False
+  if not pred.is_device:
+    clim_on_device = clim_da is not None and clim_da.is_device
+    target_on_device = tgt.is_device
+    mask_on_device = mask_da is not None and mask_da.is_device
+  else:
+    tgt = to_device(tgt, device)
     clim_da = to_device(clim_da, device) if clim_da is not None else None
     mask_da = to_device(mask_da, device) if mask_da is not None else None
   space = _cabi.SPACE_DEVICE if pred.is_device else _cabi.SPACE_HOST
@@ -718,6 +719,10 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
     flags |= _cabi.FLAG_MASKED
   if clim_on_device:
     flags |= _cabi.FLAG_CLIM_DEVICE
+  if target_on_device:
+    flags |= _cabi.FLAG_TARGET_DEVICE
+  if mask_on_device:
+    flags |= _cabi.FLAG_MASK_DEVICE
 
   stat_mask = 0
   for s in stats:
@@ -915,19 +920,26 @@ def _cached_plan(ctx, key, factory):
   return plan
 
 
-def run_fused_specs(items, device: int | None = None):
-  """Runs planned fused aggregations; compatible ones (same grid, flags and
-  weights -- typically the variables of one chunk) are merged into ONE launch
-  whose job table is the concatenation and whose cells are offset.
+@dataclasses.dataclass
+class FusedLaunch:
+  """One wbx_det_plan serving one or more planned aggregations (items)."""
+  plan: Any
+  members: list            # indices into the item list
+  specs: list
+  space: int
+  mult: int                # result rows per cell (bin classes, or 1)
+  n_rows: int              # rows of the launch's [*, 6] / [*, 4] results
 
-  ``items``: list of (spec, stats).  Returns a list of
-  {kind: (sum_weighted_statistics, sum_weights)} in the same order.
-  """
-  ctx = _cabi.get_context(device)
+
+def plan_fused_launches(items, ctx) -> list:
+  """Groups planned fused aggregations into launches: compatible ones (same
+  grid, flags and weights -- typically the variables of one chunk) are merged
+  into ONE plan whose job table is the concatenation and whose cells are
+  offset.  Plans are cached per context."""
   buckets: dict = collections.OrderedDict()
   for idx, (spec, _) in enumerate(items):
     buckets.setdefault(_merge_key(spec), []).append(idx)
-  raw: dict = {}
+  launches = []
   for members in buckets.values():
     specs = [items[i][0] for i in members]
     first = specs[0]
@@ -972,61 +984,94 @@ def run_fused_specs(items, device: int | None = None):
     # Converted copies the plan addresses live as long as the plan is cached;
     # the caller's own arrays are not retained.
     plan.keepalive = tuple(sp.keepalive for sp in specs)
-    if first.space == _cabi.SPACE_DEVICE:
-      ctx.use_torch_stream()
-    ws, w = plan.run_to_host()
-    lo = 0
     mult = 1 if first.classes is None else first.classes.n_classes
-    for i, sp in zip(members, specs):
-      part = (ws[lo:lo + sp.n_cells * mult], w[lo:lo + sp.n_cells * mult])
-      if sp.cell_fold is not None:
-        # partial sums of the launch cells of one result cell (NaN propagates)
-        n_final = int(np.prod(sp.kept_shape, dtype=np.int64))
-        folded = []
-        for arr in part:
-          out = np.zeros((n_final, arr.shape[1]), np.float64)
-          np.add.at(out, sp.cell_fold, arr)
-          folded.append(out)
-        part = tuple(folded)
-      raw[i] = part
-      lo += sp.n_cells * mult
-  results = []
-  for idx, (spec, stats) in enumerate(items):
-    ws, w = raw[idx]
-    out = {}
-    cls, outer = spec.classes, spec.outer
-    out_dims, out_shape = list(spec.kept), list(spec.kept_shape)
-    out_coords = dict(spec.coords)
-    for folded in (outer, cls):    # layout: kept, outer bins, slab bins
-      if folded is not None:
-        out_dims += list(folded.bin_dims)
-        out_shape += [m.shape[0] for m in folded.membership]
-        for bdim in folded.bin_dims:
-          out_coords[bdim] = folded.bin_coords[bdim]
-    # the reference's result has the bin dims in the order of bin_by
-    final_dims = list(spec.kept_order or spec.kept) + [
-        d for d in spec.bin_order if d in out_dims]
-    for s in stats:
-      if spec.xform:
-        slot, wclass = _cabi.XF_SLOT[s.kind], 0
-      else:
-        slot = _cabi.STAT_SLOT[s.kind]
-        wclass = _cabi.STAT_WCLASS[slot]
-      pair = []
-      for col in (ws[:, slot] * spec.scalar, w[:, wclass] * spec.scalar):
-        if cls is not None:
-          with np.errstate(invalid='ignore'):
-            col = cls.to_bins(col.reshape(spec.n_cells, cls.n_classes))
-        if outer is not None:
-          col = outer.to_bins(col.reshape((spec.n_cells,) + col.shape[1:]))
-        da = xl.DataArray(col.reshape(out_shape), out_dims, coords=out_coords,
-                          name=s.name)
-        if final_dims != out_dims:
-          da = da.transpose(*final_dims)
-        pair.append(da)
-      out[s.kind] = tuple(pair)
-    results.append(out)
-  return results
+    launches.append(FusedLaunch(
+        plan=plan, members=list(members), specs=specs, space=first.space,
+        mult=mult, n_rows=sum(sp.n_cells for sp in specs) * mult))
+  return launches
+
+
+def split_fused_results(launch: FusedLaunch, ws: np.ndarray, w: np.ndarray
+                        ) -> dict:
+  """{item index: (ws rows, w rows)} of one launch's flat results."""
+  raw, lo = {}, 0
+  for i, sp in zip(launch.members, launch.specs):
+    n = sp.n_cells * launch.mult
+    part = (ws[lo:lo + n], w[lo:lo + n])
+    if sp.cell_fold is not None:
+      # partial sums of the launch cells of one result cell (NaN propagates)
+      n_final = int(np.prod(sp.kept_shape, dtype=np.int64))
+      folded = []
+      for arr in part:
+        out = np.zeros((n_final, arr.shape[1]), np.float64)
+        np.add.at(out, sp.cell_fold, arr)
+        folded.append(out)
+      part = tuple(folded)
+    raw[i] = part
+    lo += n
+  return raw
+
+
+def label_fused_results(spec: FusedSpec, stats, ws: np.ndarray, w: np.ndarray
+                        ) -> dict:
+  """{kind: (sum_weighted_statistics, sum_weights)} as labelled host arrays
+  from the result rows of one planned aggregation (bin classes mapped to
+  bins, kept dims in the reference's order)."""
+  out = {}
+  cls, outer = spec.classes, spec.outer
+  out_dims, out_shape = list(spec.kept), list(spec.kept_shape)
+  out_coords = dict(spec.coords)
+  for folded in (outer, cls):    # layout: kept, outer bins, slab bins
+    if folded is not None:
+      out_dims += list(folded.bin_dims)
+      out_shape += [m.shape[0] for m in folded.membership]
+      for bdim in folded.bin_dims:
+        out_coords[bdim] = folded.bin_coords[bdim]
+  # the reference's result has the bin dims in the order of bin_by
+  final_dims = list(spec.kept_order or spec.kept) + [
+      d for d in spec.bin_order if d in out_dims]
+  for s in stats:
+    if spec.xform:
+      slot, wclass = _cabi.XF_SLOT[s.kind], 0
+    else:
+      slot = _cabi.STAT_SLOT[s.kind]
+      wclass = _cabi.STAT_WCLASS[slot]
+    pair = []
+    for col in (ws[:, slot] * spec.scalar, w[:, wclass] * spec.scalar):
+      if cls is not None:
+        with np.errstate(invalid='ignore'):
+          col = cls.to_bins(col.reshape(spec.n_cells, cls.n_classes))
+      if outer is not None:
+        col = outer.to_bins(col.reshape((spec.n_cells,) + col.shape[1:]))
+      da = xl.DataArray(col.reshape(out_shape), out_dims, coords=out_coords,
+                        name=s.name)
+      if final_dims != out_dims:
+        da = da.transpose(*final_dims)
+      pair.append(da)
+    out[s.kind] = tuple(pair)
+  return out
+
+
+def run_fused_specs(items, device: int | None = None, leaves=None):
+  """Runs planned fused aggregations (see plan_fused_launches).
+
+  ``items``: list of (spec, stats).  Returns a list of
+  {kind: (sum_weighted_statistics, sum_weights)} in the same order.
+  ``leaves`` (optional, one list per item of (statistic name, variable, kind))
+  tells an active fastpath recorder which result goes where.
+  """
+  ctx = _cabi.get_context(device)
+  launches = plan_fused_launches(items, ctx)
+  raw: dict = {}
+  for launch in launches:
+    if launch.space == _cabi.SPACE_DEVICE:
+      ctx.use_torch_stream()
+    ws, w = launch.plan.run_to_host()
+    raw.update(split_fused_results(launch, ws, w))
+  from weatherbenchx_b200 import fastpath  # pylint: disable=g-import-not-at-top
+  fastpath.record('det', ctx, launches, items, leaves)
+  return [label_fused_results(spec, stats, *raw[idx])
+          for idx, (spec, stats) in enumerate(items)]
 
 
 def aggregate_fused(stats: Sequence[LazyStatistic],
@@ -1603,19 +1648,25 @@ def _crps_merge_key(spec: CrpsSpec):
           None if spec.w_x is None else spec.w_x.tobytes())
 
 
-def run_crps_specs(items, device: int | None = None):
-  """Runs planned ensemble aggregations; the variables of a chunk (same grid,
-  ensemble layout, flags and weights) share ONE launch whose job table is the
-  concatenation and whose cells are offset -- one launch, one read-back and one
-  synchronisation instead of one per variable.
+@dataclasses.dataclass
+class CrpsLaunch:
+  """One wbx_crps_plan serving one or more planned ensemble aggregations."""
+  plan: Any
+  members: list
+  specs: list
+  space: int
+  n_rows: int
 
-  ``items``: list of (spec, stats); returns [{kind: (sum_ws, sum_w)}].
-  """
-  ctx = _cabi.get_context(device)
+
+def plan_crps_launches(items, ctx, device=None) -> list:
+  """The variables of a chunk (same grid, ensemble layout, flags and weights)
+  share ONE launch whose job table is the concatenation and whose cells are
+  offset -- one launch, one read-back and one synchronisation instead of one
+  per variable."""
   buckets: dict = collections.OrderedDict()
   for idx, (spec, _) in enumerate(items):
     buckets.setdefault(_crps_merge_key(spec), []).append(idx)
-  raw: dict = {}
+  launches = []
   for members in buckets.values():
     specs = [items[i][0] for i in members]
     first = specs[0]
@@ -1646,26 +1697,51 @@ def run_crps_specs(items, device: int | None = None):
             w_x=first.w_x, stat_mask=first.stat_mask)
         _plan_cache_insert(ctx, key, plan)
       plan.keepalive = tuple(sp.keepalive for sp in specs)
-    if first.space == _cabi.SPACE_DEVICE:
+    launches.append(CrpsLaunch(
+        plan=plan, members=list(members), specs=specs, space=first.space,
+        n_rows=sum(sp.n_cells for sp in specs)))
+  return launches
+
+
+def split_crps_results(launch: CrpsLaunch, ws: np.ndarray, w: np.ndarray
+                       ) -> dict:
+  raw, lo = {}, 0
+  for i, sp in zip(launch.members, launch.specs):
+    raw[i] = (ws[lo:lo + sp.n_cells], w[lo:lo + sp.n_cells])
+    lo += sp.n_cells
+  return raw
+
+
+def label_crps_results(spec: 'CrpsSpec', stats, ws: np.ndarray, w: np.ndarray
+                       ) -> dict:
+  out = {}
+  for s in stats:
+    slot = CRPS_SLOT[s.kind]
+    out[s.kind] = (
+        xl.DataArray((ws[:, slot] * spec.scalar).reshape(spec.kept_shape),
+                     spec.kept, coords=spec.coords, name=s.name),
+        xl.DataArray((w[:, slot] * spec.scalar).reshape(spec.kept_shape),
+                     spec.kept, coords=spec.coords, name=s.name))
+  return out
+
+
+def run_crps_specs(items, device: int | None = None, leaves=None):
+  """Runs planned ensemble aggregations (see plan_crps_launches).
+
+  ``items``: list of (spec, stats); returns [{kind: (sum_ws, sum_w)}].
+  """
+  ctx = _cabi.get_context(device)
+  launches = plan_crps_launches(items, ctx, device)
+  raw: dict = {}
+  for launch in launches:
+    if launch.space == _cabi.SPACE_DEVICE:
       ctx.use_torch_stream()
-    ws, w = plan.run_to_host()
-    lo = 0
-    for i, sp in zip(members, specs):
-      raw[i] = (ws[lo:lo + sp.n_cells], w[lo:lo + sp.n_cells])
-      lo += sp.n_cells
-  results = []
-  for idx, (spec, stats) in enumerate(items):
-    ws, w = raw[idx]
-    out = {}
-    for s in stats:
-      slot = CRPS_SLOT[s.kind]
-      out[s.kind] = (
-          xl.DataArray((ws[:, slot] * spec.scalar).reshape(spec.kept_shape),
-                       spec.kept, coords=spec.coords, name=s.name),
-          xl.DataArray((w[:, slot] * spec.scalar).reshape(spec.kept_shape),
-                       spec.kept, coords=spec.coords, name=s.name))
-    results.append(out)
-  return results
+    ws, w = launch.plan.run_to_host()
+    raw.update(split_crps_results(launch, ws, w))
+  from weatherbenchx_b200 import fastpath  # pylint: disable=g-import-not-at-top
+  fastpath.record('crps', ctx, launches, items, leaves)
+  return [label_crps_results(spec, stats, *raw[idx])
+          for idx, (spec, stats) in enumerate(items)]
 
 
 def crps_fields(stats, reduce_dims, device=None) -> dict | None:

@@ -60,6 +60,7 @@ class _Coords(collections.abc.MutableMapping):
 
   def __delitem__(self, key):
     del self._owner._coords[key]  # pylint: disable=protected-access
+    self._owner._version = getattr(self._owner, '_version', 0) + 1  # pylint: disable=protected-access
 
   def __iter__(self):
     return iter(self._owner._coords)  # pylint: disable=protected-access
@@ -149,6 +150,21 @@ class DataArray:
         raise ValueError(
             f'coordinate {key!r} size {n} != array size {sizes[d]} on {d!r}')
     self._coords[key] = cv
+    # mutation stamp: lets identity-keyed memos (fastpath.py) notice that the
+    # coordinates of a live array were edited in place
+    self._version = getattr(self, '_version', 0) + 1
+
+  @classmethod
+  def _fast(cls, payload, dims: tuple, coords: dict, name=None) -> 'DataArray':
+    """Unchecked construction from parts that are known to be consistent
+    (``coords`` maps names to coordinate DataArrays and is taken as is)."""
+    out = cls.__new__(cls)
+    out._data = payload
+    out.dims = dims
+    out.name = name
+    out.attrs = {}
+    out._coords = coords
+    return out
 
   def _coord_view(self, key) -> 'DataArray':
     """A coordinate as an array that carries the coordinates on its own dims
