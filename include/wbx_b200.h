@@ -398,7 +398,8 @@ int wbx_crps_pointwise(wbx_ctx* ctx, const wbx_crps_point_desc* desc,
  * S[0] = C |F_0|^2, S[k>0] = 2 C |F_k|^2, C = row_scale[y] (2 pi R cos(lat)).
  * Job j is one contiguous float32 slab [ny, nx] at field[j] (device address);
  * spectrum receives float32 [n_jobs, ny, nx/2 + 1] (device).  nx must be even
- * with nx/2 = 2^a 3^b 5^c <= 2048.  Synchronous on the context stream.
+ * with nx/2 = 2^a 3^b 5^c <= 2048.  Asynchronous on the context stream (the
+ * host tables are consumed before the call returns).
  */
 typedef struct {
   int64_t n_jobs;

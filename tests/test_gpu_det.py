@@ -854,3 +854,112 @@ def test_latitude_and_longitude_band_bins(monkeypatch):
   np.testing.assert_array_equal(got.coords['latitude_bins'].values,
                                 np.arange(-90, 90, 30))
   np.testing.assert_array_equal(got.coords['longitude_bins'].values, [270, 0])
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json configs[0] and configs[1] at their exact shapes
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize('space', ['host', 'device'])
+def test_config_c1_rmse_32x64_10_init(space):
+  """configs[0]: RMSE of 2m_temperature on the 5.625 degree grid (32 x 64),
+  10 init times, against the oracle; host and device inputs."""
+  from weatherbenchx_b200 import aggregation, engine, weighting
+  from weatherbenchx_b200.metrics import deterministic
+  rng = np.random.default_rng(100)
+  ny, nx, n_init = 32, 64, 10
+  lat = np.linspace(-90 + 5.625 / 2, 90 - 5.625 / 2, ny)
+  lon = np.linspace(0, 360, nx, endpoint=False)
+  dims = ('init_time', 'lead_time', 'latitude', 'longitude')
+  coords = {'init_time': np.datetime64('2020-01-01', 'ns') +
+                         np.arange(n_init) * np.timedelta64(1, 'D'),
+            'lead_time': np.array([0], 'timedelta64[ns]'),
+            'latitude': lat, 'longitude': lon}
+  t = rng.normal(280, 12, (n_init, 1, ny, nx)).astype(np.float32)
+  p = (t + rng.normal(0, 2, t.shape)).astype(np.float32)
+  P = xl.DataArray(p, dims, coords=coords, name='2m_temperature')
+  T = xl.DataArray(t, dims, coords=coords, name='2m_temperature')
+  if space == 'device':
+    P, T = engine.to_device(P), engine.to_device(T)
+  w = oracle.grid_area_weights(lat)
+  for rd in (['init_time', 'latitude', 'longitude'],
+             ['init_time', 'lead_time', 'latitude', 'longitude'],
+             ['latitude', 'longitude']):
+    agg = aggregation.Aggregator(reduce_dims=rd,
+                                 weigh_by=[weighting.GridAreaWeighting()])
+    got = aggregation.compute_metric_values_for_single_chunk(
+        {'rmse': deterministic.RMSE()}, agg, {'2m_temperature': P},
+        {'2m_temperature': T})['rmse.2m_temperature']
+    sws, sw, out_dims = oracle.aggregate(oracle.squared_error(p, t), dims, rd,
+                                         weights=[(w, ('latitude',))])
+    np.testing.assert_allclose(
+        got.transpose(*out_dims).values if out_dims else got.values,
+        np.sqrt(sws / sw), rtol=1e-6)
+
+
+def test_config_c2_rmse_acc_128x256_13_levels():
+  """configs[1]: RMSE + ACC of 6 pressure-level variables on the 1.4 degree
+  grid (128 x 256), 13 levels, 10 lead times, a 4-init slice of the 40 init
+  times, climatology [366, 4, 13, 128, 256], GridAreaWeighting, reducing
+  init_time / latitude / longitude -- every value against the oracle."""
+  from weatherbenchx_b200 import aggregation, engine, weighting
+  from weatherbenchx_b200.metrics import deterministic
+  rng = np.random.default_rng(200)
+  n_var, n_init, n_lead, n_lev, ny, nx = 6, 4, 10, 13, 128, 256
+  lat = np.linspace(-90, 90, ny)
+  lon = np.linspace(0, 360, nx, endpoint=False)
+  init = (np.datetime64('2020-02-27T00', 'ns') +
+          np.arange(n_init) * np.timedelta64(12, 'h'))
+  lead = (np.arange(n_lead) * np.timedelta64(6, 'h')).astype('timedelta64[ns]')
+  dims = ('init_time', 'lead_time', 'level', 'latitude', 'longitude')
+  coords = {'init_time': init, 'lead_time': lead,
+            'level': np.array([50, 100, 150, 200, 250, 300, 400, 500, 600,
+                               700, 850, 925, 1000]),
+            'latitude': lat, 'longitude': lon}
+  cdims = ('dayofyear', 'hour', 'level', 'latitude', 'longitude')
+  ccoords = {'dayofyear': np.arange(1, 367), 'hour': np.arange(0, 24, 6),
+             'level': coords['level'], 'latitude': lat, 'longitude': lon}
+  names = ['geopotential', 'temperature', 'u_component_of_wind',
+           'v_component_of_wind', 'specific_humidity', 'vertical_velocity']
+  host, P, T, C = {}, {}, {}, {}
+  # the climatology rows the slice touches (days 58..62) carry data; one shared
+  # array keeps the host copy at 1.4 GB
+  c = np.zeros((366, 4, n_lev, ny, nx), np.float32)
+  c[55:66] = rng.normal(0, 0.5, (11, 4, n_lev, ny, nx)).astype(np.float32)
+  Cdev = engine.to_device(xl.DataArray(c, cdims, coords=ccoords))
+  for k, name in enumerate(names):
+    t = rng.normal(k, 1, (n_init, n_lead, n_lev, ny, nx)).astype(np.float32)
+    p = (t + rng.normal(0, 0.3, t.shape)).astype(np.float32)
+    host[name] = (p, t)
+    P[name] = engine.to_device(xl.DataArray(p, dims, coords=coords, name=name))
+    T[name] = engine.to_device(xl.DataArray(t, dims, coords=coords, name=name))
+    C[name] = Cdev.rename(name)
+  rd = ['init_time', 'latitude', 'longitude']
+  agg = aggregation.Aggregator(reduce_dims=rd,
+                               weigh_by=[weighting.GridAreaWeighting()])
+  got = aggregation.compute_metric_values_for_single_chunk(
+      {'rmse': deterministic.RMSE(), 'acc': deterministic.ACC(C)}, agg, P, T)
+  w = oracle.grid_area_weights(lat)
+  aligned, adims = oracle.align_climatology(
+      c, cdims, {'dayofyear': ccoords['dayofyear'], 'hour': ccoords['hour']},
+      init, lead)
+  assert adims == dims
+  for name, (p, t) in host.items():
+    sws, sw, out_dims = oracle.aggregate(oracle.squared_error(p, t), dims, rd,
+                                         weights=[(w, ('latitude',))])
+    assert out_dims == ('lead_time', 'level')
+    np.testing.assert_allclose(
+        got[f'rmse.{name}'].transpose(*out_dims).values, np.sqrt(sws / sw),
+        rtol=1e-6, err_msg=name)
+    means = {}
+    for stat, fn in oracle.CLIMATOLOGY_STATISTICS.items():
+      a, b, _ = oracle.aggregate(fn(p, t, aligned), adims, rd,
+                                 weights=[(w, ('latitude',))])
+      means[stat] = a / b
+    acc = oracle.acc_from_means(means['AnomalyCovariance'],
+                                means['SquaredPredictionAnomaly'],
+                                means['SquaredTargetAnomaly'])
+    np.testing.assert_allclose(
+        got[f'acc.{name}'].transpose(*out_dims).values, acc, rtol=1e-5,
+        err_msg=name)

@@ -136,3 +136,54 @@ def test_device_resident_archive_uses_strided_windows():
   assert torch.cuda.is_available()
   for k in out_h:
     np.testing.assert_allclose(out_d[k].values, out_h[k].values, rtol=1e-12)
+
+
+@pytest.mark.parametrize('masked', [False, True])
+@pytest.mark.parametrize('lanes', [1, 2])
+def test_target_rows_cached_on_the_device(masked, lanes):
+  """TargetsFromArrays(device_cache=True): every analysis row is uploaded once
+  and stays on the GPU; host forecasts are streamed against device targets
+  (WBX_FLAG_TARGET_DEVICE / MASK_DEVICE host-space plans).  Same numbers as
+  the all-host run, with and without a NaN mask, ACC climatology on the
+  device."""
+  from weatherbenchx_b200 import engine
+  from weatherbenchx_b200 import xarray_lite as xl
+  preds, tgts = _datasets(('t', 'z'))
+  if masked:
+    tgts = {k: v.copy() for k, v in tgts.items()}
+    tgts['t'].data[3, 2:5, 1:7] = np.nan
+  rng = np.random.default_rng(4)
+  grid = {k: preds['t'].coords[k].values for k in ('latitude', 'longitude')}
+  clim = {v: engine.to_device(xl.DataArray(
+      rng.normal(size=(366, 4, len(LAT), 12)).astype(np.float32),
+      ('dayofyear', 'hour', 'latitude', 'longitude'),
+      coords=dict(grid, dayofyear=np.arange(1, 367),
+                  hour=np.arange(0, 24, 6)), name=v)) for v in ('t', 'z')}
+  metrics = {'rmse': deterministic.RMSE(), 'mae': deterministic.MAE(),
+             'acc': deterministic.ACC(clim)}
+  times = time_chunks.TimeChunks(INIT, LEAD, init_time_chunk_size=1)
+  agg = aggregation.Aggregator(
+      reduce_dims=['init_time', 'latitude', 'longitude'],
+      weigh_by=[weighting.GridAreaWeighting()], masked=masked)
+  cached = array_loaders.TargetsFromArrays(tgts, device_cache=True,
+                                           add_nan_mask=masked)
+  chunk = cached.load_chunk(INIT[1:3], LEAD)['t']
+  assert chunk.is_device
+  host_chunk = array_loaders.TargetsFromArrays(tgts).load_chunk(
+      INIT[1:3], LEAD)['t']
+  np.testing.assert_array_equal(chunk.values, host_chunk.values)
+  out_c = pipeline.run_pipeline(
+      times, array_loaders.PredictionsFromArrays(preds), cached, metrics, agg,
+      require_output=False, lanes=lanes)[None][1]
+  out_h = pipeline.run_pipeline(
+      times, array_loaders.PredictionsFromArrays(preds),
+      array_loaders.TargetsFromArrays(tgts, add_nan_mask=masked), metrics, agg,
+      require_output=False)[None][1]
+  assert set(out_c) == set(out_h)
+  for k in out_h:
+    np.testing.assert_allclose(out_c[k].values, out_h[k].values, rtol=1e-12,
+                               err_msg=k)
+  # each row went up exactly once
+  n_rows = len(np.unique((INIT[:, None] + LEAD[None, :]).ravel()))
+  row_bytes = len(LAT) * 12 * 4
+  assert cached.uploaded_bytes == 2 * n_rows * row_bytes

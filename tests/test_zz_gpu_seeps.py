@@ -39,14 +39,12 @@ def test_cuda_path_reproduces_reference_late_cases(golden, inputs, case, space):
   ref._run_product_case(golden, inputs, case, space)  # pylint: disable=protected-access
 
 
-@pytest.mark.xfail(strict=False, reason=(
-    'ensemble-of-targets CRPS: a composition of B200-verified kernels added '
-    'after the round-1 GPU budget was spent; CPU-verified with interpreted '
-    'plans, not yet run on hardware'))
 @pytest.mark.parametrize('space', ['host', 'device'])
 @pytest.mark.parametrize('case', ref.UNCONFIRMED_CASES)
-def test_cuda_path_reproduces_reference_unconfirmed_cases(golden, inputs, case,
-                                                          space):
+def test_cuda_path_reproduces_reference_ensemble_of_targets(golden, inputs,
+                                                            case, space):
+  """Ensemble-of-targets CRPS (a composition of the CRPS launches); passing
+  on the B200 since the round-1 driver run."""
   ref._run_product_case(golden, inputs, case, space)  # pylint: disable=protected-access
 
 

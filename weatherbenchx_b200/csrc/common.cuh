@@ -64,6 +64,12 @@ struct wbx_ctx {
   wbx::DevBuf stage_tables[2];
   void* pinned_out = nullptr;
   size_t pinned_out_cap = 0;
+  // job-table ring of the asynchronous one-shot calls (wbx_zonal_spectrum):
+  // a slot is reused only after the kernel that read it has finished
+  static constexpr int kTableRing = 8;
+  wbx::DevBuf ring_tables[kTableRing];
+  cudaEvent_t ring_ev[kTableRing] = {};
+  int ring_next = 0;
   // optional per-kernel timing (wbx_ctx_profile)
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;

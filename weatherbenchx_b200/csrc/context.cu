@@ -208,6 +208,8 @@ int wbx_ctx_create(int device, wbx_ctx** out) {
     WBX_CUDA(
         cudaEventCreateWithFlags(&ctx->ev_compute[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < wbx_ctx::kTableRing; ++i)
+    WBX_CUDA(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
   ctx->stream = ctx->own_stream;
   *out = ctx;
   return WBX_OK;
@@ -226,6 +228,10 @@ int wbx_ctx_destroy(wbx_ctx* ctx) {
     ctx->stage_tables[i].release();
     if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     if (ctx->ev_compute[i]) cudaEventDestroy(ctx->ev_compute[i]);
+  }
+  for (int i = 0; i < wbx_ctx::kTableRing; ++i) {
+    ctx->ring_tables[i].release();
+    if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
   }
   for (auto& pr : ctx->prof_events) {
     cudaEventDestroy(pr.first);

@@ -590,9 +590,15 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
   // upload the job table and the row scale
   const size_t tbytes = static_cast<size_t>(d->n_jobs) * 8;
   const size_t sbytes = d->row_scale ? static_cast<size_t>(d->ny) * 8 : 0;
-  int rc = ctx->stage_tables[0].reserve(tbytes + sbytes + 16);
+  // The tables go into the next slot of a small ring; a slot is rewritten only
+  // after the kernel that last read it has finished (normally long ago), so
+  // the call itself never waits for the GPU.
+  const int slot = ctx->ring_next;
+  ctx->ring_next = (slot + 1) % wbx_ctx::kTableRing;
+  WBX_CUDA(cudaEventSynchronize(ctx->ring_ev[slot]));
+  int rc = ctx->ring_tables[slot].reserve(tbytes + sbytes + 16);
   if (rc != WBX_OK) return rc;
-  unsigned char* base = ctx->stage_tables[0].as<unsigned char>();
+  unsigned char* base = ctx->ring_tables[slot].as<unsigned char>();
   WBX_CUDA(cudaMemcpyAsync(base, d->field, tbytes, cudaMemcpyHostToDevice,
                            ctx->stream));
   if (sbytes)
@@ -641,8 +647,6 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
   ctx->launches++;
   prc = ctx->prof_end();
   if (prc != WBX_OK) return prc;
-  // the tables live in context scratch: do not let a later call overwrite them
-  // while this kernel may still be reading.
-  WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  WBX_CUDA(cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
   return WBX_OK;
 }

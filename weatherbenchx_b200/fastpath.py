@@ -386,15 +386,8 @@ class LazyDataset(xl.Dataset):
   def is_pending(self) -> bool:
     return self.__dict__.get('_pending') is not None
 
-  def __del__(self):
-    pending = self.__dict__.get('_pending')
-    if pending is not None:
-      compiled, slot, event = pending
-      try:
-        event.synchronize()   # the copy into the slot must not be in flight
-        compiled._give_slot(slot)  # pylint: disable=protected-access
-      except Exception:  # pylint: disable=broad-except
-        pass
+  # A Dataset that is dropped unread simply lets go of its pinned slot: torch's
+  # host allocator keeps the block until the copy into it has completed.
 
   # every read goes through _force
   def __getitem__(self, key):

@@ -30,6 +30,35 @@ from weatherbenchx_b200.metrics import base
 EARTH_RADIUS_M = 1000.0 * (6357.0 + 6378.0) / 2.0
 
 
+_COORD_CACHE: dict = {}
+
+
+def _spectral_coords(lat: np.ndarray, lon: np.ndarray, nx: int,
+                     latitude_name: str) -> dict:
+  """zonal_wavenumber / frequency / wavelength coordinates of a spectrum;
+  they depend on the grid only and are built once per grid (the wavelength
+  table is [latitude, wavenumber])."""
+  key = (lat.tobytes(), float(lon[0]), float(lon[1]) if nx > 1 else 0.0, nx,
+         latitude_name)
+  hit = _COORD_CACHE.get(key)
+  if hit is None:
+    scale = 2 * np.pi * EARTH_RADIUS_M * np.cos(np.deg2rad(lat))
+    k = np.arange(nx // 2 + 1)
+    spacing_deg = float(lon[1] - lon[0]) if nx > 1 else 360.0
+    with np.errstate(divide='ignore'):
+      freq = k / (nx * spacing_deg)             # cycles per degree longitude
+      hit = {
+          'zonal_wavenumber': xl.DataArray(k, ('zonal_wavenumber',)),
+          'frequency': xl.DataArray(freq, ('zonal_wavenumber',)),
+          'wavelength': xl.DataArray(
+              scale[:, None] / np.where(k > 0, k, np.nan)[None, :],
+              (latitude_name, 'zonal_wavenumber'))}
+    if len(_COORD_CACHE) > 8:
+      _COORD_CACHE.clear()
+    _COORD_CACHE[key] = hit
+  return hit
+
+
 def zonal_energy_spectrum(field: xl.DataArray, latitude_name: str = 'latitude',
                           longitude_name: str = 'longitude',
                           device: int | None = None) -> xl.DataArray:
@@ -66,18 +95,9 @@ def zonal_energy_spectrum(field: xl.DataArray, latitude_name: str = 'latitude',
   dims = tuple(outer) + (latitude_name, 'zonal_wavenumber')
   coords = {k: v for k, v in canon.coords.items()
             if longitude_name not in v.dims and k != 'mask'}
-  k = np.arange(nx // 2 + 1)
   lon = canon.coords[longitude_name].to_numpy() if (
       longitude_name in canon.coords) else np.arange(nx) * 360.0 / nx
-  spacing_deg = float(lon[1] - lon[0]) if nx > 1 else 360.0
-  coords['zonal_wavenumber'] = k
-  with np.errstate(divide='ignore'):
-    freq = k / (nx * spacing_deg)             # cycles per degree longitude
-    circ = scale[:, None]
-    coords['frequency'] = xl.DataArray(freq, ('zonal_wavenumber',))
-    coords['wavelength'] = xl.DataArray(
-        circ / np.where(k > 0, k, np.nan)[None, :],
-        (latitude_name, 'zonal_wavenumber'))
+  coords.update(_spectral_coords(lat, lon, nx, latitude_name))
   return xl.DataArray(out, dims, coords=coords, name=field.name)
 
 
