@@ -788,8 +788,10 @@ def run_c5(args, dev, rank, world, peak):
   from weatherbenchx_b200.data_loaders import array_loaders
   from weatherbenchx_b200.metrics import deterministic, probabilistic
   n_lead, n_blocks = 12, 4
-  per_rank = args.c5_inits
-  n_init = per_rank * world
+  # chunks per rank: the ensemble chunks are 25x larger than the deterministic
+  # ones, so the deterministic suite gets twice as many
+  per_rank_of = {'deterministic': 2 * args.c5_inits, 'ensemble': args.c5_inits}
+  n_init = max(per_rank_of.values()) * world
   six = np.timedelta64(6, 'h')
   t0 = np.datetime64('2020-01-01T00', 'ns')
   init = t0 + np.arange(n_init) * 2 * six
@@ -837,22 +839,20 @@ def run_c5(args, dev, rank, world, peak):
   aggregator = aggregation.Aggregator(
       reduce_dims=['init_time', 'latitude', 'longitude'],
       weigh_by=[weighting.GridAreaWeighting()])
-  times = time_chunks.TimeChunks(init, lead, init_time_chunk_size=1,
-                                 lead_time_chunk_size=n_lead)
   suites = {
       'deterministic': (
           {'rmse': deterministic.RMSE(), 'mse': deterministic.MSE(),
            'mae': deterministic.MAE(), 'bias': deterministic.Bias(),
            'acc': deterministic.ACC(clim)},
-          lambda: _RecyclingForecasts(blocks, init, lead, grid),
+          lambda it: _RecyclingForecasts(blocks, it, lead, grid),
           det_vars, 4 * n_lead * len(det_vars)),
       'ensemble': (
           {'crps': probabilistic.CRPSEnsemble(
               ensemble_dim='number', use_sort=True),
            'ssr': probabilistic.UnbiasedSpreadSkillRatio(
                ensemble_dim='number')},
-          lambda: _RecyclingForecasts(ens_blocks, init, lead, grid,
-                                      extra_dims=('number',)),
+          lambda it: _RecyclingForecasts(ens_blocks, it, lead, grid,
+                                         extra_dims=('number',)),
           (ens_var,), 4 * n_lead * members),
   }
 
@@ -864,13 +864,17 @@ def run_c5(args, dev, rank, world, peak):
   out = {}
   for suite, (metrics, forecasts, variables, fc_bytes_per_pt) in suites.items():
     targets = {v: analyses[v] for v in variables}
+    per_rank = per_rank_of[suite]
+    suite_init = init[:per_rank * world]
+    times = time_chunks.TimeChunks(suite_init, lead, init_time_chunk_size=1,
+                                   lead_time_chunk_size=n_lead)
 
     def run(shard=True, cache=(suite == 'deterministic')):
       # (the ensemble launch streams 51 fields per grid point: its one target
       # field per point is not worth a second memory space)
       loader = array_loaders.TargetsFromArrays(targets, device_cache=cache)
       result = pipeline.run_pipeline(
-          times, forecasts(), loader, metrics, aggregator,
+          times, forecasts(suite_init), loader, metrics, aggregator,
           require_output=False, lanes=2, shard=shard)
       return result[None][1], loader.uploaded_bytes
 
@@ -920,7 +924,7 @@ def run_c5(args, dev, rank, world, peak):
           spread = 2.0 * (coef * srt).sum(dim=0) / (members * (members - 1))
           spread_term[j] = (spread * w_lat[0]).sum()
           del srt, spread
-      for i in range(n_init):
+      for i in range(len(suite_init)):
         tg = an[2 * i:2 * i + n_lead]
         if suite == 'deterministic':
           fc = torch.as_tensor(blocks[v0][i % n_blocks], device=dev).double()
@@ -931,7 +935,7 @@ def run_c5(args, dev, rank, world, peak):
             skill = (ens[j].double() - tg[j][None]).abs().mean(dim=0)
             num[j] += (skill * w_lat[0]).sum() - 0.5 * spread_term[j]
             del skill
-      den = n_init * float(w_lat.sum()) * NLON
+      den = len(suite_init) * float(w_lat.sum()) * NLON
       ref = (num / den).cpu().numpy()
       key = 'rmse' if suite == 'deterministic' else 'crps'
       got = np.asarray(values[f'{key}.{v0}'].values)
@@ -951,7 +955,8 @@ def run_c5(args, dev, rank, world, peak):
       'workload': (f'config[4]: deterministic suite (RMSE, MSE, MAE, Bias, ACC; '
                    f'{len(det_vars)} vars) + ensemble suite (CRPS use_sort, '
                    f'unbiased spread/skill; {members} members), 0.25 deg, '
-                   f'{per_rank} init x {n_lead} lead per rank from pinned HOST '
+                   f'{per_rank_of["deterministic"]} / {per_rank_of["ensemble"]} '
+                   f'init x {n_lead} lead per rank from pinned HOST '
                    'memory through pipeline.run_pipeline in (init=1, lead=12) '
                    'chunks, 2 evaluation lanes, analysis rows cached on the '
                    'GPU, climatology resident on the GPU, chunks sharded over '

@@ -188,8 +188,8 @@ def test_identity_rules():
   # the cache holds its inputs weakly
   ref = weakref.ref(P['a'].data)
   del P['a'], out
-  P['a'] = engine.to_device(xl.DataArray(host['a'][0], DIMS, coords=COORDS,
-                                         name='a'))
+  P['a'] = engine.to_device(xl.DataArray(
+      host['a'][0], DIMS, coords=dict(COORDS, init_time=shifted), name='a'))
   gc.collect()
   assert ref() is None
   fresh = run()
