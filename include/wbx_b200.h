@@ -62,9 +62,11 @@ enum {
                                data_loaders/xarray_loaders.py:242-263) are
                                uploaded once and kept on the GPU; only the
                                predictions (and a host mask) are streamed    */
-  WBX_FLAG_MASK_DEVICE = 256 /* WBX_SPACE_HOST plans only: the mask addresses
+  WBX_FLAG_MASK_DEVICE = 256, /* WBX_SPACE_HOST plans only: the mask addresses
                                are device pointers (the mask coordinate of
                                device-resident targets)                      */
+  WBX_FLAG_BINS_V1 = 512    /* tuning/debug: serve a class_map plan with the
+                               first-generation binned kernel                */
 };
 
 /* Slots of the fused deterministic statistics (unique_name in comments). */

@@ -26,6 +26,7 @@ SPACE_DEVICE, SPACE_HOST = 0, 1
 FLAG_SKIPNA, FLAG_MASKED, FLAG_FORCE_LDG, FLAG_FORCE_TMA = 1, 2, 16, 32
 FLAG_CLIM_DEVICE = 64
 FLAG_TARGET_DEVICE, FLAG_MASK_DEVICE = 128, 256
+FLAG_BINS_V1 = 512
 NUM_DET_STATS = 6
 NUM_DET_WCLASSES = 4
 STAT_SLOT = {

@@ -4,7 +4,10 @@
 #include <new>
 #include <string.h>
 
+#include <type_traits>
+
 #include "det_reduce.cuh"
+#include "det_bins2.cuh"
 
 namespace wbx {
 
@@ -47,8 +50,63 @@ struct wbx_det_plan {
   wbx::DevBuf class_map;
   std::vector<double> class_w;   // sum of w_y over the points of every class
   wbx::BinParams bins{};
+  // second-generation binned kernel (det_bins2.cuh): usable when no aligned
+  // block of 8 map elements holds more than two classes
+  bool bins2 = false;
   int cells_mult() const { return n_classes > 0 ? n_classes : 1; }
 };
+
+namespace wbx {
+
+// Grid geometry of the second-generation binned kernel for a launch of nj
+// jobs: S slab parts of <= 4096 elements, S_cta of them in flight (the others
+// follow in rounds), J job groups, S_cta * J <= #SMs.
+struct Bins2Geometry {
+  int S = 0, S_cta = 0, J = 0, part = 0, stage_bytes = 0, stages = 0, na = 0;
+  size_t smem = 0;
+  bool ok = false;
+};
+
+static Bins2Geometry bins2_geometry(const wbx_ctx* ctx, const wbx_det_plan* plan,
+                                    long long nj) {
+  Bins2Geometry g;
+  const long long slab = plan->ny * plan->nx;
+  const int G = ctx->sm_count;
+  const long long s_min = (slab + 4095) / 4096;
+  const long long rounds = (s_min + G - 1) / G;
+  // parts in flight: all SMs when the slab is large; for small slabs the SMs
+  // are shared out between slab parts and job groups
+  long long s_cta = G;
+  g.J = 1;
+  if (rounds == 1) {
+    g.J = static_cast<int>(std::max<long long>(
+        1, std::min<long long>(nj, G / s_min)));
+    s_cta = std::max<long long>(s_min, std::min<long long>(
+        G / g.J, (slab + 511) / 512));
+  }
+  const long long want = s_cta * rounds;
+  g.part = static_cast<int>(round_up((slab + want - 1) / want, 16));
+  if (g.part > 4096) return g;
+  g.S = static_cast<int>((slab + g.part - 1) / g.part);
+  g.S_cta = static_cast<int>(std::min<long long>(s_cta, g.S));
+  g.na = (plan->has_clim ? 6 : 3) + (plan->has_mask ? 1 : 0);
+  g.stage_bytes = static_cast<int>(round_up(
+      static_cast<size_t>(g.part) * 4 * (plan->has_clim ? 3 : 2) +
+          (plan->has_mask ? g.part : 0), 128));
+  const size_t overhead =
+      2 * kMaxStages * sizeof(uint64_t) + kMaxStages * sizeof(StageMeta) + 128 +
+      static_cast<size_t>(kConsumerWarps) * plan->n_classes * g.na *
+          sizeof(double);
+  const size_t cap = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+  if (overhead + 2 * static_cast<size_t>(g.stage_bytes) > cap) return g;
+  g.stages = static_cast<int>(
+      std::min<size_t>(kMaxStages, (cap - overhead) / g.stage_bytes));
+  g.smem = static_cast<size_t>(g.stages) * g.stage_bytes + overhead;
+  g.ok = g.stages >= 2;
+  return g;
+}
+
+}  // namespace wbx
 
 namespace wbx {
 
@@ -118,6 +176,89 @@ static int launch_bins(wbx_ctx* ctx, const wbx_det_plan* plan,
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   return ctx->prof_end();
+}
+
+static int launch_bins2(wbx_ctx* ctx, const wbx_det_plan* plan,
+                        const DetParams& P, const Bins2Geometry& g,
+                        int n_cells, double* records) {
+  int prc = ctx->prof_begin();
+  if (prc != WBX_OK) return prc;
+  Bins2Params B;
+  B.class_map = plan->class_map.as<unsigned char>();
+  B.n_classes = plan->n_classes;
+  B.S = g.S;
+  B.S_cta = g.S_cta;
+  B.J = g.J;
+  B.part = g.part;
+  B.n_cells = n_cells;
+  B.records = records;
+  const bool wx = plan->has_wx || (plan->nx % 4) != 0;
+#define WBX_BINS2_LAUNCH(A, M, W)                                              \
+  do {                                                                         \
+    auto kern = det_reduce_bins2_kernel<A, M, W>;                              \
+    WBX_CUDA(cudaFuncSetAttribute(kern,                                        \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  static_cast<int>(g.smem)));                  \
+    kern<<<g.S_cta * g.J, kTmaThreads, g.smem, ctx->stream>>>(                 \
+        P, B, g.stages, g.stage_bytes);                                        \
+  } while (0)
+  const int key = (plan->has_clim ? 4 : 0) | (plan->has_mask ? 2 : 0) |
+                  (wx ? 1 : 0);
+  switch (key) {
+    case 0: WBX_BINS2_LAUNCH(false, false, false); break;
+    case 1: WBX_BINS2_LAUNCH(false, false, true); break;
+    case 2: WBX_BINS2_LAUNCH(false, true, false); break;
+    case 3: WBX_BINS2_LAUNCH(false, true, true); break;
+    case 4: WBX_BINS2_LAUNCH(true, false, false); break;
+    case 5: WBX_BINS2_LAUNCH(true, false, true); break;
+    case 6: WBX_BINS2_LAUNCH(true, true, false); break;
+    default: WBX_BINS2_LAUNCH(true, true, true); break;
+  }
+#undef WBX_BINS2_LAUNCH
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return ctx->prof_end();
+}
+
+static int launch_bins2_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
+                                 const Bins2Geometry& g, const double* records,
+                                 const int32_t* d_first, const double* d_cell_w,
+                                 int n_cells, long long n_jobs, double* out_ws,
+                                 double* out_w, int accumulate) {
+  Bins2FinalizeParams F;
+  F.records = records;
+  F.cell_first_job = d_first;
+  F.cell_class_w = plan->has_mask ? nullptr : d_cell_w;
+  F.out_ws = out_ws;
+  F.out_w = out_w;
+  F.n_jobs = n_jobs;
+  F.n_cells = n_cells;
+  F.n_classes = plan->n_classes;
+  F.S = g.S;
+  F.J = g.J;
+  F.ns = plan->has_clim ? 6 : 3;
+  F.na = g.na;
+  F.accumulate = accumulate;
+  if (!accumulate) {
+    // statistic slots a launch without climatology does not produce stay 0
+    WBX_CUDA(cudaMemsetAsync(
+        out_ws, 0,
+        sizeof(double) * n_cells * plan->n_classes * WBX_NUM_DET_STATS,
+        ctx->stream));
+    WBX_CUDA(cudaMemsetAsync(
+        out_w, 0,
+        sizeof(double) * n_cells * plan->n_classes * WBX_NUM_DET_WCLASSES,
+        ctx->stream));
+  }
+  const long long warps =
+      static_cast<long long>(n_cells) * plan->n_classes * (g.na + 1);
+  const int block = 128;
+  const long long blocks = (warps * 32 + block - 1) / block;
+  det_bins2_finalize_kernel<<<static_cast<unsigned>(blocks), block, 0,
+                              ctx->stream>>>(F);
+  WBX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return WBX_OK;
 }
 
 static int launch_main(wbx_ctx* ctx, const wbx_det_plan* plan,
@@ -450,6 +591,19 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
                      "(skipna, slab %% 16 or too many classes x statistics)");
       return WBX_ERR_UNSUPPORTED;
     }
+    // second-generation kernel: every aligned block of 8 map elements may
+    // hold at most two classes (a thread keeps two class slots in registers)
+    p->bins2 = !(d->flags & WBX_FLAG_BINS_V1) && (slab_ % 8) == 0;
+    for (int64_t e = 0; e < slab_ && p->bins2; e += 8) {
+      const unsigned char a = d->class_map[e];
+      int other = -1;
+      for (int i = 1; i < 8; ++i) {
+        const unsigned char c = d->class_map[e + i];
+        if (c == a) continue;
+        if (other < 0) other = c;
+        else if (c != other) { p->bins2 = false; break; }
+      }
+    }
     p->class_w.assign(d->n_classes, 0.0);
     for (int64_t e = 0; e < slab_; ++e) {
       const int c = d->class_map[e];
@@ -651,6 +805,25 @@ int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan) {
 
 static int run_device_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
                             double* d_w, int accumulate) {
+  if (plan->bins2) {
+    const wbx::Bins2Geometry g = wbx::bins2_geometry(ctx, plan, plan->n_jobs);
+    if (g.ok) {
+      const size_t rec_bytes = static_cast<size_t>(g.S) *
+                               (plan->n_cells + g.J) * plan->n_classes * g.na *
+                               sizeof(double);
+      int rc = ctx->records.reserve(rec_bytes);
+      if (rc != WBX_OK) return rc;
+      wbx::DetParams P = plan->params;
+      P.records = nullptr;
+      rc = wbx::launch_bins2(ctx, plan, P, g, static_cast<int>(plan->n_cells),
+                             ctx->records.as<double>());
+      if (rc != WBX_OK) return rc;
+      return wbx::launch_bins2_finalize(
+          ctx, plan, g, ctx->records.as<double>(), plan->d_cell_first_job,
+          plan->d_cell_w, static_cast<int>(plan->n_cells), plan->n_jobs, d_ws,
+          d_w, accumulate);
+    }
+  }
   const int warps = wbx::warps_for(plan);
   const size_t rec_bytes = (static_cast<size_t>(plan->grid) + plan->n_cells) *
                            warps * plan->nacc * sizeof(double);
@@ -828,6 +1001,33 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     wbx::fill_steps(plan, &P);
     const int grid = wbx::grid_for(ctx, plan, P.total_tiles);
     const int n_cells = static_cast<int>(first.size()) - 1;
+    if (plan->bins2) {
+      const wbx::Bins2Geometry g =
+          wbx::bins2_geometry(ctx, plan, static_cast<long long>(nj));
+      if (g.ok) {
+        const size_t b2_bytes = static_cast<size_t>(g.S) * (n_cells + g.J) *
+                                plan->n_classes * g.na * sizeof(double);
+        rc = ctx->records.reserve(b2_bytes);
+        if (rc != WBX_OK) return rc;
+        WBX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+        rc = wbx::launch_bins2(ctx, plan, P, g, n_cells,
+                               ctx->records.as<double>());
+        if (rc != WBX_OK) return rc;
+        rc = wbx::launch_bins2_finalize(
+            ctx, plan, g, ctx->records.as<double>(),
+            reinterpret_cast<const int32_t*>(tbase + o_first),
+            reinterpret_cast<const double*>(tbase + o_cw), n_cells,
+            static_cast<long long>(nj),
+            d_ws + static_cast<size_t>(P.cell_base) * plan->cells_mult() *
+                       WBX_NUM_DET_STATS,
+            d_w + static_cast<size_t>(P.cell_base) * plan->cells_mult() *
+                      WBX_NUM_DET_WCLASSES,
+            1);
+        if (rc != WBX_OK) return rc;
+        WBX_CUDA(cudaEventRecord(ctx->ev_compute[buf], ctx->stream));
+        continue;
+      }
+    }
     const size_t rec_bytes = (static_cast<size_t>(grid) + n_cells) * warps *
                              plan->nacc * sizeof(double);
     // records are reused by consecutive chunks on the same compute stream, so
