@@ -233,6 +233,15 @@ int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan);
  * aggregation.py:84-110) instead of overwriting them (device out only). */
 int wbx_det_plan_run(wbx_ctx* ctx, wbx_det_plan* plan, double* sum_ws,
                      double* sum_w, int32_t out_space, int32_t accumulate);
+/* Which kernel serves the plan (introspection for tests and profiling):
+ * 0 TMA ring, 1 vectorised LDG, 2 scalar LDG, 3 binned (first generation),
+ * 4 binned (second generation: static slab parts, csrc/det_bins2.cuh). */
+enum {
+  WBX_KERNEL_TMA = 0, WBX_KERNEL_LDG4 = 1, WBX_KERNEL_LDG1 = 2,
+  WBX_KERNEL_BINS_V1 = 3, WBX_KERNEL_BINS_V2 = 4
+};
+int wbx_det_plan_kernel(wbx_ctx* ctx, const wbx_det_plan* plan,
+                        int32_t* kernel);
 /* One-shot convenience: create + run (host outputs) + destroy. */
 int wbx_det_reduce(wbx_ctx* ctx, const wbx_det_desc* desc, double* sum_ws,
                    double* sum_w);

@@ -31,6 +31,12 @@ def _class_map(rng, ny, nx, kind):
       if len(u) > 2:
         blk[~np.isin(blk, u[:2])] = u[1]
     cmap = flat.reshape(ny, nx)
+  elif kind == 'edges3':    # a region edge one column after a land edge:
+    # some aligned blocks of 8 hold THREE classes (the serial path)
+    land = np.kron(rng.random(((ny + 7) // 8, (nx + 11) // 12)) > 0.5,
+                   np.ones((8, 12), bool))[:ny, :nx]
+    region = (np.arange(nx) > 37)[None, :] & (np.arange(ny) > ny // 3)[:, None]
+    cmap = land * 2 + region
   elif kind == 'noise':     # many classes per block: first-generation kernel
     cmap = rng.integers(0, 5, (ny, nx))
   else:
@@ -80,6 +86,9 @@ CASES = [
     (240, 484, 9, 'two', 'blocks', False, False, True, 0b100),
     (144, 146, 16, 'per_job', 'columns', False, True, True, 0b111),
     (32, 64, 5, 'one', 'single', False, False, False, 0b100),
+    (721, 1440, 6, 'two', 'edges3', False, False, False, 0b101),
+    (128, 256, 9, 'per_job', 'edges3', True, True, False, 0b111111),
+    (96, 146, 5, 'one', 'edges3', False, True, True, 0b110),
 ]
 
 
@@ -132,6 +141,9 @@ def test_bins2_matches_numpy_and_v1(case, space):
         mask=tables.get('mask'), cell=cell.astype(np.int32), n_cells=n_cells,
         w_outer=w_o, w_y=w_y, w_x=w_x, stat_mask=stat_mask, class_map=cmap,
         n_classes=n_classes)
+    want_kernel = (_cabi.KERNEL_BINS_V1 if flag or kind == 'noise'
+                   else _cabi.KERNEL_BINS_V2)
+    assert plan.kernel() == want_kernel, (plan.kernel(), want_kernel)
     results[flag] = plan.run_to_host()
     again = plan.run_to_host()
     assert again[0].tobytes() == results[flag][0].tobytes()   # bit-stable
@@ -142,7 +154,7 @@ def test_bins2_matches_numpy_and_v1(case, space):
     scale = np.abs(ws_ref).max(axis=0, keepdims=True) + 1e-30
     np.testing.assert_allclose(ws / scale, ws_ref / scale, rtol=0, atol=2e-6,
                                err_msg=f'flag {flag}')
-    np.testing.assert_allclose(sw, sw_ref, rtol=1e-12, err_msg=f'flag {flag}')
+    np.testing.assert_allclose(sw, sw_ref, rtol=1e-10, err_msg=f'flag {flag}')
   np.testing.assert_allclose(results[0][0], results[_cabi.FLAG_BINS_V1][0],
                              rtol=1e-6, atol=1e-6 * np.abs(ws_ref).max())
 

@@ -27,6 +27,7 @@ FLAG_SKIPNA, FLAG_MASKED, FLAG_FORCE_LDG, FLAG_FORCE_TMA = 1, 2, 16, 32
 FLAG_CLIM_DEVICE = 64
 FLAG_TARGET_DEVICE, FLAG_MASK_DEVICE = 128, 256
 FLAG_BINS_V1 = 512
+KERNEL_TMA, KERNEL_LDG4, KERNEL_LDG1, KERNEL_BINS_V1, KERNEL_BINS_V2 = range(5)
 NUM_DET_STATS = 6
 NUM_DET_WCLASSES = 4
 STAT_SLOT = {
@@ -179,6 +180,7 @@ SIGNATURES = {
     'wbx_det_plan_destroy': (c_int, [c_void_p, c_void_p]),
     'wbx_det_plan_run': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int32, c_int32]),
+    'wbx_det_plan_kernel': (c_int, [c_void_p, c_void_p, POINTER(c_int32)]),
     'wbx_det_reduce': (c_int, [c_void_p, POINTER(DetDesc), c_void_p,
                                c_void_p]),
     'wbx_det_elementwise': (c_int, [c_void_p, c_int32, c_void_p, c_void_p,
@@ -411,6 +413,13 @@ class DetPlan:
     check(self.ctx.lib.wbx_det_plan_run(
         self.ctx.handle, self.handle, c_void_p(ws_ptr), c_void_p(w_ptr),
         SPACE_DEVICE, 1 if accumulate else 0))
+
+  def kernel(self) -> int:
+    """WBX_KERNEL_* code of the kernel that serves this plan."""
+    out = c_int32()
+    check(self.ctx.lib.wbx_det_plan_kernel(self.ctx.handle, self.handle,
+                                           ctypes.byref(out)))
+    return out.value
 
   def close(self):
     if self.handle:

@@ -22,9 +22,11 @@
 // thread owns the SAME 8 contiguous elements for all jobs of a part, so
 //   * its classes are loaded once: slot A = the class of its first element,
 //     slot B = the other class if a boundary (coastline, region edge) falls
-//     inside its 8 elements (the host checks that no aligned 8-element block
-//     of the map holds more than two classes; else the first-generation
-//     kernel serves the plan);
+//     inside its 8 elements; elements of a third class (two different
+//     boundaries inside one block of 8, a fraction of a percent of the blocks
+//     of real masks) are added to the warp's shared sums by their owners, one
+//     lane after the other (maps where that is common keep the
+//     first-generation kernel);
 //   * its weights are loaded once (row weights, or per-element weights for
 //     longitude-major arrays / odd row lengths);
 //   * the per-point work is the unbinned kernel's (f32 statistics, f32 4-sums,
@@ -57,7 +59,10 @@ struct Bins2Params {
 // Static per-thread description of its 8 elements of the current part.
 template <bool WX>
 struct Bins2Static {
-  unsigned is_b;     // bit i: element i belongs to slot B
+  unsigned sel_a;    // bit i: element i belongs to slot A
+  unsigned sel_b;    // bit i: element i belongs to slot B
+  unsigned ovf;      // bit i: element i has a third (fourth, ...) class
+  uint2 cls8;        // the classes of the 8 elements (one byte each)
   int cls_a, cls_b;
   bool active, has_b;
   double w[WX ? 8 : 2];  // per element, or per float4 group (row weight)
@@ -204,7 +209,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     const int e_lo = s_part * B.part;
     const int part_len = min(P.slab, e_lo + B.part) - e_lo;
     S.active = 8 * ctid < part_len;
-    S.is_b = 0u;
+    S.sel_a = S.sel_b = S.ovf = 0u;
+    S.cls8 = make_uint2(0u, 0u);
     S.cls_a = S.cls_b = 0;
     S.has_b = false;
 #pragma unroll
@@ -218,16 +224,21 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         cls[i] = static_cast<unsigned char>(k8.x >> (8 * i));
         cls[4 + i] = static_cast<unsigned char>(k8.y >> (8 * i));
       }
+      S.cls8 = k8;
       S.cls_a = cls[0];
       S.cls_b = cls[0];
+      S.sel_a = 1u;
 #pragma unroll
       for (int i = 1; i < 8; ++i) {
-        if (cls[i] != S.cls_a) {
+        if (cls[i] == S.cls_a) {
+          S.sel_a |= 1u << i;
+        } else {
           if (!S.has_b) {
             S.cls_b = cls[i];
             S.has_b = true;
           }
-          S.is_b |= 1u << i;
+          if (cls[i] == S.cls_b) S.sel_b |= 1u << i;
+          else S.ovf |= 1u << i;   // rare: a third class within 8 elements
         }
       }
       if constexpr (WX) {
@@ -246,6 +257,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         S.w[1] = P.w_y ? __ldg(P.w_y + (e + 4u) / unx) : 1.0;
       }
     }
+    // (static per part) does any lane of this warp hold overflow elements?
+    const bool warp_ovf = __any_sync(0xffffffffu, S.ovf != 0u);
     int cur_cell = -1;
     for (long long job = j_lo; job < j_hi; ++job) {
       mbar_wait(&full[s], ph);
@@ -254,20 +267,25 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         if (cur_cell >= 0) flush(s_part, cur_cell);
         cur_cell = mt.cell;
       }
-      if (S.active) {
+      {
         const unsigned char* stg = ring + (size_t)s * stage_bytes;
         const float4* sp = reinterpret_cast<const float4*>(stg);
         const float4* stt = reinterpret_cast<const float4*>(stg + off_t);
         const float4* sc = reinterpret_cast<const float4*>(stg + off_c);
         const uint2* sm = reinterpret_cast<const uint2*>(stg + off_m);
         uint2 m8 = make_uint2(0x01010101u, 0x01010101u);
-        if constexpr (MASK) m8 = sm[ctid];
+        if constexpr (MASK) {
+          if (S.active) m8 = sm[ctid];
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const float4 pv = sp[2 * ctid + g];
-          const float4 tv = stt[2 * ctid + g];
-          float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (CLIM) cv = sc[2 * ctid + g];
+          // inactive threads (beyond the part) compute on zeros into nothing
+          float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), tv = pv, cv = pv;
+          if (S.active) {
+            pv = sp[2 * ctid + g];
+            tv = stt[2 * ctid + g];
+            if constexpr (CLIM) cv = sc[2 * ctid + g];
+          }
           const unsigned mw = g == 0 ? m8.x : m8.y;
           const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
           const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
@@ -277,11 +295,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           for (int i = 0; i < 4; ++i)
             q[i].eval(pp[i], tt[i], cc[i],
                       static_cast<unsigned char>(mw >> (8 * i)));
-          // all-ones where the element belongs to slot A, zero for slot B
-          unsigned ma[4];
+          // all-ones where the element belongs to slot A / slot B
+          unsigned ma[4], mb[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            ma[i] = ((S.is_b >> (4 * g + i)) & 1u) - 1u;
+          for (int i = 0; i < 4; ++i) {
+            ma[i] = 0u - ((S.sel_a >> (4 * g + i)) & 1u);
+            mb[i] = 0u - ((S.sel_b >> (4 * g + i)) & 1u);
+          }
           if constexpr (!WX) {
             const double wg = S.w[g] * mt.wo;
             if (!S.has_b) {
@@ -307,7 +327,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                   for (int i = 0; i < 4; ++i) {
                     const unsigned bits = __float_as_uint(q[i].s[k]);
                     a4[i] = __uint_as_float(bits & ma[i]);
-                    b4[i] = __uint_as_float(bits & ~ma[i]);
+                    b4[i] = __uint_as_float(bits & mb[i]);
                   }
                   const float sa = __fadd_rn(__fadd_rn(a4[0], a4[1]),
                                              __fadd_rn(a4[2], a4[3]));
@@ -323,7 +343,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                 for (int i = 0; i < 4; ++i) {
                   const unsigned bits = __float_as_uint(q[i].valid[0]);
                   a4[i] = __uint_as_float(bits & ma[i]);
-                  b4[i] = __uint_as_float(bits & ~ma[i]);
+                  b4[i] = __uint_as_float(bits & mb[i]);
                 }
                 acc[0][NS] +=
                     static_cast<double>((a4[0] + a4[1]) + (a4[2] + a4[3])) * wg;
@@ -345,7 +365,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                   const unsigned bits = __float_as_uint(q[i].s[k]);
                   va = fma(static_cast<double>(__uint_as_float(bits & ma[i])),
                            we[i], va);
-                  vb = fma(static_cast<double>(__uint_as_float(bits & ~ma[i])),
+                  vb = fma(static_cast<double>(__uint_as_float(bits & mb[i])),
                            we[i], vb);
                 }
                 acc[0][k] += va;
@@ -359,11 +379,41 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                 const unsigned bits = __float_as_uint(q[i].valid[0]);
                 va = fma(static_cast<double>(__uint_as_float(bits & ma[i])),
                          we[i], va);
-                vb = fma(static_cast<double>(__uint_as_float(bits & ~ma[i])),
+                vb = fma(static_cast<double>(__uint_as_float(bits & mb[i])),
                          we[i], vb);
               }
               acc[0][NS] += va;
               acc[1][NS] += vb;
+            }
+          }
+          // elements of a third class (two different boundaries inside one
+          // block of 8: a coastline next to a region edge): their owners add
+          // them to the warp's shared sums one lane after the other
+          if (warp_ovf) {
+            const unsigned og = (S.ovf >> (4 * g)) & 0xfu;
+            unsigned om = __ballot_sync(0xffffffffu, og != 0u);
+            while (om) {
+              const int src = __ffs(om) - 1;
+              if (lane == src) {
+                const unsigned word = g == 0 ? S.cls8.x : S.cls8.y;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if (og & (1u << i)) {
+                    double wi;
+                    if constexpr (WX) wi = S.w[4 * g + i] * mt.wo;
+                    else wi = S.w[g] * mt.wo;
+                    double* slot = wacc + ((word >> (8 * i)) & 0xffu) * NA;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k)
+                      if (stat_mask & (1 << k))
+                        slot[k] += static_cast<double>(q[i].s[k]) * wi;
+                    if constexpr (MASK)
+                      slot[NS] += static_cast<double>(q[i].valid[0]) * wi;
+                  }
+                }
+              }
+              __syncwarp();
+              om &= om - 1;
             }
           }
         }

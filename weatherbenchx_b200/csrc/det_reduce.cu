@@ -591,18 +591,23 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
                      "(skipna, slab %% 16 or too many classes x statistics)");
       return WBX_ERR_UNSUPPORTED;
     }
-    // second-generation kernel: every aligned block of 8 map elements may
-    // hold at most two classes (a thread keeps two class slots in registers)
+    // second-generation kernel: a thread keeps two class slots in registers
+    // for its aligned block of 8 map elements; blocks with more classes take
+    // a serial path, which must stay rare (<= 2 % of the blocks)
     p->bins2 = !(d->flags & WBX_FLAG_BINS_V1) && (slab_ % 8) == 0;
-    for (int64_t e = 0; e < slab_ && p->bins2; e += 8) {
-      const unsigned char a = d->class_map[e];
-      int other = -1;
-      for (int i = 1; i < 8; ++i) {
-        const unsigned char c = d->class_map[e + i];
-        if (c == a) continue;
-        if (other < 0) other = c;
-        else if (c != other) { p->bins2 = false; break; }
+    if (p->bins2) {
+      int64_t overflow = 0;
+      for (int64_t e = 0; e < slab_; e += 8) {
+        const unsigned char a = d->class_map[e];
+        int other = -1;
+        for (int i = 1; i < 8; ++i) {
+          const unsigned char c = d->class_map[e + i];
+          if (c == a) continue;
+          if (other < 0) other = c;
+          else if (c != other) { ++overflow; break; }
+        }
       }
+      p->bins2 = overflow * 50 <= slab_ / 8;
     }
     p->class_w.assign(d->n_classes, 0.0);
     for (int64_t e = 0; e < slab_; ++e) {
@@ -1094,6 +1099,19 @@ int wbx_det_plan_run(wbx_ctx* ctx, wbx_det_plan* plan, double* sum_ws,
     WBX_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(sum_ws, pin, ws_bytes);
     memcpy(sum_w, pin + ws_bytes, w_bytes);
+  }
+  return WBX_OK;
+}
+
+int wbx_det_plan_kernel(wbx_ctx* ctx, const wbx_det_plan* plan,
+                        int32_t* kernel) {
+  WBX_REQUIRE(ctx && plan && kernel, "wbx_det_plan_kernel: NULL argument");
+  if (plan->n_classes > 0) {
+    const bool v2 = plan->bins2 &&
+                    wbx::bins2_geometry(ctx, plan, plan->n_jobs).ok;
+    *kernel = v2 ? WBX_KERNEL_BINS_V2 : WBX_KERNEL_BINS_V1;
+  } else {
+    *kernel = plan->path;
   }
   return WBX_OK;
 }
