@@ -656,6 +656,11 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
   for d in reversed(dims):
     if d not in reduce_set or d in keep_outer:
       break
+    if slab_bound and slab_bound <= set(inner):
+      # grid bin masks: the slab is just the dims the masks live on, so that
+      # the class map is one grid (not one per init time) and a launch has
+      # many jobs per slab part (csrc/det_bins2.cuh)
+      break
     trial = [d] + inner
     ok = all(tuple(o.dims[-len(trial):]) == tuple(trial) for o in operands)
     if clim is not None:
