@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 echo "== bins2 tests"
-timeout 600 python -m pytest tests/test_gpu_bins2.py tests/test_gpu_crps_sort_tma.py tests/test_gpu_fastpath.py -m gpu -q -x -p no:cacheprovider > gpurun_out/r2_call3_bins2.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_bins2.py tests/test_gpu_fastpath.py -m gpu -q -x -p no:cacheprovider > gpurun_out/r2_call3_bins2.log 2>&1
 tail -30 gpurun_out/r2_call3_bins2.log
 echo "== full GPU suite"
 timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r2_call3_gpu_tests.log 2>&1
@@ -28,8 +28,6 @@ timeout 300 ncu --set full --clock-control none --import-source on \
     -k regex:det_reduce_bins -s 2 -c 1 -o gpurun_out/r2_prof_bins2 \
     python profiles/bins_once.py > gpurun_out/r2_prof_bins2.log 2>&1
 tail -3 gpurun_out/r2_prof_bins2.log
-echo "== ncu of the TMA sort kernel"
-EXP_ONLY=sort timeout 300 ncu --set full --clock-control none --import-source on \
-    -k regex:crps_sort -s 2 -c 1 -o gpurun_out/r2_prof_crps_sort_tma \
-    python profiles/exp_crps.py 1 > gpurun_out/r2_prof_crps_sort_tma.log 2>&1
-tail -2 gpurun_out/r2_prof_crps_sort_tma.log
+echo "== CRPS sort kernel: 5 vs 6 resident CTAs per SM"
+EXP_ONLY=sort timeout 200 python profiles/exp_crps.py 10 2>&1 | tail -2
+WBX_EXP_SORT_MINB6=1 EXP_ONLY=sort timeout 200 python profiles/exp_crps.py 10 2>&1 | tail -2

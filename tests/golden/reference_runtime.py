@@ -57,6 +57,13 @@ def _patch_data_array(xl):
 
   def sel(self, indexers=None, drop=False, **kwargs):
     indexers = dict(indexers or {}, **kwargs)
+    # a dimension without a coordinate is indexed by position, as xarray's
+    # default RangeIndex does (metrics_test.py:983-1006 builds its climatology
+    # with expand_dims(dayofyear=366, hour=4))
+    missing = {d: np.arange(self.sizes[d]) for d in indexers
+               if d in self.dims and d not in self.coords}
+    if missing:
+      self = self.assign_coords(missing)
     labelled = {d: v for d, v in indexers.items()
                 if isinstance(v, data_array) and v.ndim > 0}
     if not labelled:
@@ -102,6 +109,14 @@ def _patch_data_array(xl):
     return data_array(payload, dims, coords=coords, name=arr.name,
                       attrs=arr.attrs)
 
+  def setitem(self, key, value):
+    """``da[{dim: index}] = value`` on a host payload (metrics_test.py:1225)."""
+    if not isinstance(key, dict):
+      raise TypeError('only dict indexers are supported')
+    index = tuple(key.get(d, slice(None)) for d in self.dims)
+    self.to_numpy()[index] = value
+
+  data_array.__setitem__ = setitem
   data_array.sel = sel
   data_array.compute = lambda self: self
   data_array.load = lambda self: self
@@ -125,15 +140,111 @@ def install():
       setattr(xr, key, getattr(xl, key))
 
   class Dataset(xl.Dataset):
-    """Mapping of DataArrays; ``ds[[names]]`` subsets (base.py:370)."""
+    """Mapping of DataArrays with the Dataset calls the reference makes:
+    ``ds[[names]]`` subsets (base.py:370) and -- for running the reference's
+    own unit tests on this stand-in (tests/test_reference_own_tests.py) --
+    construction from ``(dims, values)`` pairs with shared coordinates,
+    ``expand_dims / rename / isel / sel / where / copy / mean``, coordinate
+    access, and variable-wise arithmetic."""
+
+    def __init__(self, data_vars=None, coords=None):
+      dict.__init__(self)
+      coords = dict(coords or {})
+      for name, value in dict(data_vars or {}).items():
+        if isinstance(value, tuple) and len(value) == 2:
+          dims, values = value
+          dims = (dims,) if isinstance(dims, str) else tuple(dims)
+          value = xl.DataArray(
+              np.asarray(values), dims,
+              coords={d: np.asarray(coords[d]) for d in dims if d in coords},
+              name=name)
+        elif coords:
+          value = xl.as_data_array(value)
+          extra = {k: np.asarray(v) for k, v in coords.items()
+                   if k in value.dims and k not in value.coords}
+          if extra:
+            value = value.assign_coords(extra)
+        dict.__setitem__(self, name, value)
+
+    def _map(self, fn, only_with=None):
+      return Dataset({k: (fn(v) if only_with is None or
+                          set(only_with) & set(v.dims) else v)
+                      for k, v in dict.items(self)})
 
     def __getitem__(self, key):
       if isinstance(key, list):
         return Dataset({k: dict.__getitem__(self, k) for k in key})
+      if key not in self.keys():
+        for da in self.values():   # a coordinate shared by the variables
+          if key in da.coords:
+            return da.coords[key]
       return dict.__getitem__(self, key)
 
-  class DataTree:  # only named in annotations
-    pass
+    @property
+    def sizes(self):
+      return self.dims
+
+    @property
+    def coords(self):
+      out = {}
+      for da in self.values():
+        for k, v in da.coords.items():
+          out.setdefault(k, v)
+      return out
+
+    def copy(self, deep=True):
+      return self._map(lambda v: v.copy(deep=deep))
+
+    def rename(self, mapping=None, **kwargs):
+      mapping = dict(mapping or {}, **kwargs)
+      out = Dataset()
+      for k, v in dict.items(self):
+        out[mapping.get(k, k)] = v.rename(
+            {a: b for a, b in mapping.items() if a in v.dims or a in v.coords})
+      return out
+
+    def expand_dims(self, dim=None, **kwargs):
+      spec = dict(dim or {}, **kwargs) if not isinstance(dim, str) else {
+          dim: 1}
+      return self._map(lambda v: v.expand_dims(spec))
+
+    def isel(self, indexers=None, drop=False, **kwargs):
+      indexers = dict(indexers or {}, **kwargs)
+      return self._map(lambda v: v.isel(
+          {d: i for d, i in indexers.items() if d in v.dims}, drop=drop))
+
+    def sel(self, indexers=None, drop=False, **kwargs):
+      indexers = dict(indexers or {}, **kwargs)
+      return self._map(lambda v: v.sel(
+          {d: i for d, i in indexers.items() if d in v.dims}, drop=drop))
+
+    def where(self, cond, other=np.nan):
+      return self._map(lambda v: v.where(cond, other))
+
+    def mean(self, dim=None, skipna=None):
+      dims = (dim,) if isinstance(dim, str) else tuple(dim or ())
+      return self._map(lambda v: v.mean(
+          [d for d in dims if d in v.dims] if dims else None, skipna=skipna))
+
+    def isnull(self):
+      return self._map(lambda v: v.isnull())
+
+    def _binary(self, other, op):
+      if isinstance(other, dict):
+        return Dataset({k: op(v, other[k]) for k, v in dict.items(self)
+                        if k in other})
+      return self._map(lambda v: op(v, other))
+
+    def __sub__(self, o): return self._binary(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._binary(o, lambda a, b: b - a)
+    def __add__(self, o): return self._binary(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._binary(o, lambda a, b: b + a)
+    def __mul__(self, o): return self._binary(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._binary(o, lambda a, b: b * a)
+    def __truediv__(self, o): return self._binary(o, lambda a, b: a / b)
+    def __abs__(self): return self._map(abs)
+
+  DataTree = xl.DataTree
 
   @contextlib.contextmanager
   def set_options(**unused_kwargs):
@@ -154,6 +265,17 @@ def install():
     """xr.dot with the older ``dims=`` spelling (categorical.py:290)."""
     return xl.dot(*arrays, dim=dims if dim is None else dim)
 
+  def like(fn):
+    def wrapped(obj, dtype=None):
+      if isinstance(obj, dict):
+        return Dataset({k: fn(v, dtype) for k, v in obj.items()})
+      return fn(obj, dtype)
+    return wrapped
+
+  xr.zeros_like = like(xl.zeros_like)
+  xr.ones_like = like(xl.ones_like)
+  if not hasattr(xl.DataArray, 'drop'):
+    xl.DataArray.drop = xl.DataArray.drop_vars   # the older spelling
   xr.concat = concat
   xr.dot = dot
   xr.Dataset = Dataset
@@ -183,10 +305,14 @@ def install():
   sys.modules['jax'] = jax
   sys.modules['jax.numpy'] = jnp
 
-  absl = types.ModuleType('absl')
-  absl.logging = logging
-  sys.modules['absl'] = absl
-  sys.modules['absl.logging'] = logging
+  try:   # the real absl when the image has it (the reference's unit tests
+    # need absl.testing); a logging-only stand-in otherwise
+    import absl.logging  # noqa: F401  pylint: disable=g-import-not-at-top,unused-import
+  except ImportError:
+    absl = types.ModuleType('absl')
+    absl.logging = logging
+    sys.modules['absl'] = absl
+    sys.modules['absl.logging'] = logging
 
   sys.path.insert(0, REFERENCE_ROOT)
   import weatherbenchX  # noqa: F401  pylint: disable=g-import-not-at-top,unused-import

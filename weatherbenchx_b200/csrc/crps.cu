@@ -19,6 +19,7 @@
 // (per-(CTA, cell, warp) partials, fixed-order second pass).
 #include <algorithm>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -619,8 +620,9 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
 // MFIX > 0 fixes the member count at compile time: the +inf padding lanes
 // become constants, ptxas folds every compare-exchange that touches them and
 // the network shrinks to the size of the real ensemble (M = 50: 64 -> 50 wires).
-template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MASK, bool MOMENTS>
-__global__ void __launch_bounds__(kCrpsThreads)
+template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MASK, bool MOMENTS,
+          int MINB = 1>
+__global__ void __launch_bounds__(kCrpsThreads, MINB)
     crps_sort_kernel(const CrpsParams P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = MFIX > 0 ? MFIX : P.n_members;
@@ -697,155 +699,6 @@ __global__ void __launch_bounds__(kCrpsThreads)
   }
 }
 
-
-// ---------------------------------------------------------------------------
-// TMA-staged sorting kernel for the operational ensemble sizes (M = 50 / 51,
-// member-major, 16-byte aligned rows, no skipna_ensemble): the producer warp of
-// crps_reduce_tma_kernel streams the NEXT tile of 128 points x (M members + the
-// target) into a two-stage shared-memory ring while the four compute warps sort
-// the current one.  A thread picks its members up with M shared-memory loads at
-// immediate offsets -- no 64-bit address arithmetic and no global-load latency
-// in the warps that run the compare-exchange network, which is bound by the
-// half-rate FMNMX pipe (profiles/ncu_crps_sort50_r2_shipped.txt: 80 % ALU pipe,
-// 17 % of the stalls on the member loads, ~150 integer instructions per point).
-// ---------------------------------------------------------------------------
-template <int MFIX, bool MASK, bool MOMENTS>
-__global__ void __launch_bounds__(kCrpsTmaThreads)
-    crps_sort_tma_kernel(const CrpsParams P) {
-  constexpr int MAXM = 64;
-  constexpr int M = MFIX;
-  extern __shared__ __align__(128) unsigned char crps_smem[];
-  constexpr size_t stage_bytes =
-      (static_cast<size_t>(M) * kCrpsThreads + kCrpsThreads) * 4 + kCrpsThreads;
-  constexpr size_t stage_stride = (stage_bytes + 127) / 128 * 128;
-  uint64_t* full = reinterpret_cast<uint64_t*>(crps_smem + kCrpsStages * stage_stride);
-  uint64_t* empty = full + kCrpsStages;
-  CrpsStageMeta* meta = reinterpret_cast<CrpsStageMeta*>(empty + kCrpsStages);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long t_begin =
-      (static_cast<long long>(blockIdx.x) * P.total_tiles) / gridDim.x;
-  const long long t_end =
-      (static_cast<long long>(blockIdx.x + 1) * P.total_tiles) / gridDim.x;
-  if (tid == 0) {
-    for (int s = 0; s < kCrpsStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kCrpsWarps);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  if (warp == kCrpsWarps) {
-    if (lane == 0) {
-      const uint64_t policy = l2_evict_first_policy();
-      long long job = t_begin / P.tiles_per_slab;
-      int k = static_cast<int>(t_begin - job * P.tiles_per_slab);
-      int s = 0;
-      uint32_t ph = 0;
-      for (long long g = t_begin; g < t_end; ++g) {
-        const float* ea = reinterpret_cast<const float*>(__ldg(P.ens + job));
-        const float* ta = reinterpret_cast<const float*>(__ldg(P.target + job));
-        const int e0 = k * kCrpsThreads;
-        const int len = min(kCrpsThreads, P.slab - e0);
-        mbar_wait(&empty[s], ph ^ 1u);
-        CrpsStageMeta mt;
-        mt.cell = __ldg(P.cell + job);
-        mt.len = len;
-        mt.e0 = e0;
-        mt.job = static_cast<int>(job);
-        mt.wo = P.w_outer ? __ldg(P.w_outer + job) : 1.0;
-        meta[s] = mt;
-        unsigned char* st = crps_smem + s * stage_stride;
-        float* xs = reinterpret_cast<float*>(st);
-        const uint32_t row_bytes = static_cast<uint32_t>(len) * 4u;
-        mbar_expect_tx(&full[s], row_bytes * static_cast<uint32_t>(M + 1) +
-                                     (MASK ? static_cast<uint32_t>(len) : 0u));
-        for (int m = 0; m < M; ++m)
-          bulk_g2s(xs + m * kCrpsThreads,
-                   ea + static_cast<long long>(m) * P.member_stride + e0,
-                   row_bytes, &full[s], policy);
-        bulk_g2s(xs + M * kCrpsThreads, ta + e0, row_bytes, &full[s], policy);
-        if constexpr (MASK) {
-          const unsigned char* ma =
-              reinterpret_cast<const unsigned char*>(__ldg(P.mask + job));
-          bulk_g2s(st + (static_cast<size_t>(M) + 1) * kCrpsThreads * 4, ma + e0,
-                   static_cast<uint32_t>(len), &full[s], policy);
-        }
-        if (++k == P.tiles_per_slab) {
-          k = 0;
-          ++job;
-        }
-        if (++s == kCrpsStages) {
-          s = 0;
-          ph ^= 1u;
-        }
-      }
-    }
-    return;
-  }
-
-  double acc[kCrpsAcc] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  int cur_cell = -1;
-  int s = 0;
-  uint32_t ph = 0;
-  const float inf = __int_as_float(0x7f800000);
-  for (long long g = t_begin; g < t_end; ++g) {
-    mbar_wait(&full[s], ph);
-    const CrpsStageMeta mt = meta[s];
-    if (mt.cell != cur_cell) {
-      if (cur_cell >= 0) {
-        double* rec = P.records +
-                      ((static_cast<size_t>(blockIdx.x) + (cur_cell - P.cell_base)) *
-                           kCrpsWarps + warp) * kCrpsAcc;
-#pragma unroll
-        for (int a = 0; a < kCrpsAcc; ++a) {
-          const double v = warp_sum(acc[a]);
-          if (lane == 0) rec[a] = v;
-          acc[a] = 0.0;
-        }
-      }
-      cur_cell = mt.cell;
-    }
-    const unsigned char* st = crps_smem + s * stage_stride;
-    const float* xs = reinterpret_cast<const float*>(st);
-    if (tid < mt.len) {
-      float x[MAXM];
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        x[m] = (m < M) ? xs[m * kCrpsThreads + tid] : inf;
-      const float y = xs[M * kCrpsThreads + tid];
-      float v[kCrpsStats];
-      sort_point<MAXM, MFIX, false, MOMENTS>(x, y, M, P.fair, v);
-      const unsigned e = static_cast<unsigned>(mt.e0 + tid);
-      crps_store_fields(P, mt.job, e, v);
-      const unsigned yy = e / static_cast<unsigned>(P.nx);
-      const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
-      double w = mt.wo;
-      if (P.w_y) w *= __ldg(P.w_y + yy);
-      if (P.w_x) w *= __ldg(P.w_x + xx);
-      bool base = true;
-      if constexpr (MASK)
-        base = st[(static_cast<size_t>(M) + 1) * kCrpsThreads * 4 + tid] != 0;
-      crps_accumulate(v, base, P.skipna_stat, w, acc);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-    if (++s == kCrpsStages) {
-      s = 0;
-      ph ^= 1u;
-    }
-  }
-  if (cur_cell >= 0) {
-    double* rec = P.records +
-                  ((static_cast<size_t>(blockIdx.x) + (cur_cell - P.cell_base)) *
-                       kCrpsWarps + warp) * kCrpsAcc;
-#pragma unroll
-    for (int a = 0; a < kCrpsAcc; ++a) {
-      const double v = warp_sum(acc[a]);
-      if (lane == 0) rec[a] = v;
-    }
-  }
-}
 
 // out[c*2 + s] (statistics) and out_w[c*2 + s] (weights), one warp per output.
 struct CrpsFinalizeParams {
@@ -1023,7 +876,6 @@ struct wbx_crps_plan {
   int what = 3;           // kWantCrps | kWantMoments
   float* fields[4] = {nullptr, nullptr, nullptr, nullptr};  // run_fields only
   bool tma_ok = false;    // TMA-staged pair kernel allowed (alignment, size)
-  bool sort_tma_ok = false;  // TMA-staged sorting kernel allowed (M = 50 / 51)
   size_t smem_plain = 0;  // shared memory of the non-TMA pair kernel
   wbx::DevBuf tables, weights;
   wbx::CrpsParams params{};
@@ -1044,34 +896,6 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
   const int what = plan->what;
-  if (plan->use_sort && plan->sort_tma_ok && P.point_stride == 1 &&
-      (P.member_stride % 4) == 0) {
-#define WBX_SORT_TMA_LAUNCH(MFIX, MSK, MOM)                                    \
-  do {                                                                         \
-    auto kern = crps_sort_tma_kernel<MFIX, MSK, MOM>;                          \
-    WBX_CUDA(cudaFuncSetAttribute(                                             \
-        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
-        static_cast<int>(plan->smem_bytes)));                                  \
-    kern<<<grid, kCrpsTmaThreads, plan->smem_bytes, ctx->stream>>>(P);         \
-  } while (0)
-    const bool mom = (what & kWantMoments) != 0;
-    const int key = (plan->n_members == 51 ? 4 : 0) | (plan->has_mask ? 2 : 0) |
-                    (mom ? 1 : 0);
-    switch (key) {
-      case 0: WBX_SORT_TMA_LAUNCH(50, false, false); break;
-      case 1: WBX_SORT_TMA_LAUNCH(50, false, true); break;
-      case 2: WBX_SORT_TMA_LAUNCH(50, true, false); break;
-      case 3: WBX_SORT_TMA_LAUNCH(50, true, true); break;
-      case 4: WBX_SORT_TMA_LAUNCH(51, false, false); break;
-      case 5: WBX_SORT_TMA_LAUNCH(51, false, true); break;
-      case 6: WBX_SORT_TMA_LAUNCH(51, true, false); break;
-      default: WBX_SORT_TMA_LAUNCH(51, true, true); break;
-    }
-#undef WBX_SORT_TMA_LAUNCH
-    WBX_CUDA(cudaGetLastError());
-    ctx->launches++;
-    return ctx->prof_end();
-  }
   if (plan->use_sort) {
 #define WBX_SORT_LAUNCH2(MAXM, MFIX, MOM)                                      \
   do {                                                                         \
@@ -1094,7 +918,12 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
     else WBX_SORT_LAUNCH2(MAXM, MFIX, false);                                  \
   } while (0)
     // the common operational ensemble sizes get a pruned network
-    if (plan->n_members == 50) WBX_SORT_LAUNCH(64, 50);
+    if (plan->n_members == 50 && !ens_skipna && !plan->has_mask &&
+        !(what & kWantMoments) && getenv("WBX_EXP_SORT_MINB6")) {
+      // experiment: 6 resident CTAs per SM (80 registers, 24 spilled words)
+      crps_sort_kernel<64, 50, false, false, false, 6>
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);
+    } else if (plan->n_members == 50) WBX_SORT_LAUNCH(64, 50);
     else if (plan->n_members == 51) WBX_SORT_LAUNCH(64, 51);
     else if (plan->n_members <= 8) WBX_SORT_LAUNCH(8, 0);
     else if (plan->n_members <= 16) WBX_SORT_LAUNCH(16, 0);
@@ -1149,9 +978,7 @@ static int crps_grid(const wbx_ctx* ctx, const wbx_crps_plan* plan,
   const size_t per_sm = std::min<size_t>(ctx->smem_optin, 227 * 1024);
   long long ctas_per_sm = std::max<size_t>(1, per_sm / (plan->smem_bytes + 1024));
   ctas_per_sm = std::min<long long>(ctas_per_sm, 8);
-  // the register-resident sorting kernel is register-limited (no shared
-  // memory); its TMA-staged variant is limited by its two-stage ring
-  if (plan->use_sort && !plan->sort_tma_ok) ctas_per_sm = 8;
+  if (plan->use_sort) ctas_per_sm = 8;  // register-limited, no shared memory
   const long long g = ctx->sm_count * ctas_per_sm;
   return static_cast<int>(std::max(1ll, std::min(g, total_tiles)));
 }
@@ -1352,10 +1179,7 @@ int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* d,
       ok = ok && d->point_stride == 1;  // host chunks are re-staged member-major
     }
     p->tma_ok = ok && !p->use_sort;
-    p->sort_tma_ok = ok && p->use_sort &&
-                     (d->n_members == 50 || d->n_members == 51) &&
-                     !(d->flags & WBX_CRPS_SKIPNA_ENSEMBLE);
-    if (p->tma_ok || p->sort_tma_ok) p->smem_bytes = need;
+    if (p->tma_ok) p->smem_bytes = need;
   }
   if (!p->use_sort &&
       p->smem_bytes > std::min<size_t>(ctx->smem_optin, 227 * 1024)) {

@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nacc = B.n_classes * NA;   // doubles per warp / per record
+  // block-of-8 permutation of the current part + per-warp counts (see set-up)
+  int* order = reinterpret_cast<int*>(wacc_all + kConsumerWarps * nacc);
+  int* warp_specials = order + kConsumerThreads;
   const int s_cta = blockIdx.x % B.S_cta;
   const int grp = blockIdx.x / B.S_cta;
   const long long j_lo = (static_cast<long long>(grp) * P.n_jobs) / B.J;
@@ -205,10 +208,41 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   int s = 0;
   uint32_t ph = 0;
   for (int s_part = s_cta; s_part < B.S; s_part += B.S_cta) {
-    // ---- static set-up for this part: classes and weights of my 8 elements
+    // ---- static set-up for this part ----------------------------------------
+    // A thread owns one aligned block of 8 elements.  Blocks that hold more
+    // than one class (a coastline, a region edge) need the two-slot code;
+    // they are a few percent of the blocks but would drag nearly every warp
+    // through it.  So the blocks are permuted once per part: the mixed ones go
+    // to the first threads (one or two warps), all other warps are
+    // class-uniform and run the plain code.
     const int e_lo = s_part * B.part;
     const int part_len = min(P.slab, e_lo + B.part) - e_lo;
-    S.active = 8 * ctid < part_len;
+    const int n_blocks = part_len >> 3;
+    bool mixed = false;
+    if (ctid < n_blocks) {
+      const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(
+          B.class_map + e_lo + 8 * ctid));
+      const unsigned first = (k8.x & 0xffu) * 0x01010101u;
+      mixed = k8.x != first || k8.y != first;
+    }
+    const unsigned mixed_lanes = __ballot_sync(0xffffffffu, mixed);
+    if (lane == 0) warp_specials[warp] = __popc(mixed_lanes);
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+    int mixed_before = 0, mixed_total = 0;
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) {
+      const int c = warp_specials[w];
+      mixed_before += w < warp ? c : 0;
+      mixed_total += c;
+    }
+    mixed_before += __popc(mixed_lanes & ((1u << lane) - 1u));
+    if (ctid < n_blocks)
+      order[mixed ? mixed_before : mixed_total + (ctid - mixed_before)] = ctid;
+    else
+      order[ctid] = ctid;
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+    const int blk = order[ctid];      // the block this thread owns
+    S.active = ctid < n_blocks;
     S.sel_a = S.sel_b = S.ovf = 0u;
     S.cls8 = make_uint2(0u, 0u);
     S.cls_a = S.cls_b = 0;
@@ -216,7 +250,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 #pragma unroll
     for (int i = 0; i < (WX ? 8 : 2); ++i) S.w[i] = 0.0;
     if (S.active) {
-      const unsigned e = static_cast<unsigned>(e_lo + 8 * ctid);
+      const unsigned e = static_cast<unsigned>(e_lo + 8 * blk);
       const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(B.class_map + e));
       unsigned char cls[8];
 #pragma unroll
@@ -257,7 +291,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         S.w[1] = P.w_y ? __ldg(P.w_y + (e + 4u) / unx) : 1.0;
       }
     }
-    // (static per part) does any lane of this warp hold overflow elements?
+    // (static per part, warp-uniform) does this warp hold mixed blocks at all?
+    const bool warp_mixed = __any_sync(0xffffffffu, S.has_b);
     const bool warp_ovf = __any_sync(0xffffffffu, S.ovf != 0u);
     int cur_cell = -1;
     for (long long job = j_lo; job < j_hi; ++job) {
@@ -275,16 +310,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         const uint2* sm = reinterpret_cast<const uint2*>(stg + off_m);
         uint2 m8 = make_uint2(0x01010101u, 0x01010101u);
         if constexpr (MASK) {
-          if (S.active) m8 = sm[ctid];
+          if (S.active) m8 = sm[blk];
         }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           // inactive threads (beyond the part) compute on zeros into nothing
           float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), tv = pv, cv = pv;
           if (S.active) {
-            pv = sp[2 * ctid + g];
-            tv = stt[2 * ctid + g];
-            if constexpr (CLIM) cv = sc[2 * ctid + g];
+            pv = sp[2 * blk + g];
+            tv = stt[2 * blk + g];
+            if constexpr (CLIM) cv = sc[2 * blk + g];
           }
           const unsigned mw = g == 0 ? m8.x : m8.y;
           const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -304,7 +339,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           }
           if constexpr (!WX) {
             const double wg = S.w[g] * mt.wo;
-            if (!S.has_b) {
+            if (!warp_mixed) {   // class-uniform warp: the unbinned code
 #pragma unroll
               for (int k = 0; k < NS; ++k) {
                 if (stat_mask & (1 << k)) {  // warp-uniform
@@ -361,12 +396,19 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
               if (stat_mask & (1 << k)) {
                 double va = 0.0, vb = 0.0;
 #pragma unroll
-                for (int i = 3; i >= 0; --i) {
-                  const unsigned bits = __float_as_uint(q[i].s[k]);
-                  va = fma(static_cast<double>(__uint_as_float(bits & ma[i])),
-                           we[i], va);
-                  vb = fma(static_cast<double>(__uint_as_float(bits & mb[i])),
-                           we[i], vb);
+                if (!warp_mixed) {
+#pragma unroll
+                  for (int i = 3; i >= 0; --i)
+                    va = fma(static_cast<double>(q[i].s[k]), we[i], va);
+                } else {
+#pragma unroll
+                  for (int i = 3; i >= 0; --i) {
+                    const unsigned bits = __float_as_uint(q[i].s[k]);
+                    va = fma(static_cast<double>(__uint_as_float(bits & ma[i])),
+                             we[i], va);
+                    vb = fma(static_cast<double>(__uint_as_float(bits & mb[i])),
+                             we[i], vb);
+                  }
                 }
                 acc[0][k] += va;
                 acc[1][k] += vb;

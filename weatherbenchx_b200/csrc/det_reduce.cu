@@ -96,7 +96,8 @@ static Bins2Geometry bins2_geometry(const wbx_ctx* ctx, const wbx_det_plan* plan
   const size_t overhead =
       2 * kMaxStages * sizeof(uint64_t) + kMaxStages * sizeof(StageMeta) + 128 +
       static_cast<size_t>(kConsumerWarps) * plan->n_classes * g.na *
-          sizeof(double);
+          sizeof(double) +
+      (kConsumerThreads + kConsumerWarps) * sizeof(int);  // block permutation
   const size_t cap = std::min<size_t>(ctx->smem_optin, 227 * 1024);
   if (overhead + 2 * static_cast<size_t>(g.stage_bytes) > cap) return g;
   g.stages = static_cast<int>(

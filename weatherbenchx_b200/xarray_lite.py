@@ -1009,12 +1009,15 @@ class testing:  # pylint: disable=invalid-name
   """``xr.testing`` look-alike used by the ported reference tests."""
 
   @staticmethod
-  def assert_allclose(a, b, rtol=1e-5, atol=1e-8):
+  def assert_allclose(a, b, rtol=1e-5, atol=1e-8, check_dim_order=False):
     if isinstance(a, Mapping):
       assert set(a) == set(b), (set(a), set(b))
       for k in a:
-        testing.assert_allclose(a[k], b[k], rtol=rtol, atol=atol)
+        testing.assert_allclose(a[k], b[k], rtol=rtol, atol=atol,
+                                check_dim_order=check_dim_order)
       return
+    if check_dim_order:
+      assert a.dims == b.dims, (a.dims, b.dims)
     assert set(a.dims) == set(b.dims), (a.dims, b.dims)
     b = b.transpose(*a.dims)
     np.testing.assert_allclose(a.to_numpy(), b.to_numpy(), rtol=rtol,
