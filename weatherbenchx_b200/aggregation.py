@@ -54,6 +54,15 @@ def combining_sum(data_arrays: Sequence[xl.DataArray]) -> xl.DataArray:
               a.coords[d].to_numpy(), first.coords[d].to_numpy())
           for d in first.dims) for a in arrays[1:])
   if same_grid:
+    # same grid everywhere (the usual case: reduced time dims): add the
+    # payloads in order, no per-block labelled-array work
+    if all(not a.is_device for a in arrays):
+      total = np.array(first.to_numpy(), dtype=np.result_type(
+          *[a.dtype for a in arrays]), copy=True)
+      for a in arrays[1:]:
+        total += a.to_numpy()
+      name = first.name if all(a.name == first.name for a in arrays) else None
+      return first._replace(data=total, name=name)  # pylint: disable=protected-access
     total = first
     for a in arrays[1:]:
       total = total + a

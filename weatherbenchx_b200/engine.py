@@ -72,7 +72,7 @@ class _Operand:
       self.strides = dict(zip(da.dims, payload.stride()))
     else:
       self.is_device = False
-      self.ptr = payload.ctypes.data
+      self.ptr = payload.__array_interface__['data'][0]
       self.strides = dict(
           zip(da.dims, (s // payload.itemsize for s in payload.strides)))
     self.itemsize = itemsize
@@ -1035,6 +1035,10 @@ def label_fused_results(spec: FusedSpec, stats, ws: np.ndarray, w: np.ndarray
   # the reference's result has the bin dims in the order of bin_by
   final_dims = list(spec.kept_order or spec.kept) + [
       d for d in spec.bin_order if d in out_dims]
+  # the coordinates are validated once per spec; every result array shares them
+  template = xl.DataArray(np.empty(out_shape, np.bool_), out_dims,
+                          coords=out_coords)
+  out_dims_t = tuple(out_dims)
   for s in stats:
     if spec.xform:
       slot, wclass = _cabi.XF_SLOT[s.kind], 0
@@ -1048,8 +1052,8 @@ def label_fused_results(spec: FusedSpec, stats, ws: np.ndarray, w: np.ndarray
           col = cls.to_bins(col.reshape(spec.n_cells, cls.n_classes))
       if outer is not None:
         col = outer.to_bins(col.reshape((spec.n_cells,) + col.shape[1:]))
-      da = xl.DataArray(col.reshape(out_shape), out_dims, coords=out_coords,
-                        name=s.name)
+      da = xl.DataArray._fast(col.reshape(out_shape), out_dims_t,  # pylint: disable=protected-access
+                              dict(template._coords), s.name)  # pylint: disable=protected-access
       if final_dims != out_dims:
         da = da.transpose(*final_dims)
       pair.append(da)

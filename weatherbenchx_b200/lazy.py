@@ -13,11 +13,17 @@ GPU by the elementwise kernel.
 from __future__ import annotations
 
 import dataclasses
+import weakref
 from typing import Sequence
 
 import numpy as np
 
 from weatherbenchx_b200 import xarray_lite as xl
+
+
+# (id(pred coords), id(target coords)) -> weakrefs + mutation stamps of pairs
+# whose index coordinates were already compared
+_CHECKED_PAIRS: dict = {}
 
 
 @dataclasses.dataclass
@@ -122,7 +128,24 @@ class LazyStatistic(xl.DataArray):
                  predictions.shape == targets.shape and
                  xl._same_coords(predictions._coords, targets._coords))  # pylint: disable=protected-access
     if not same_grid:
-      xl._check_index_coords(predictions, targets)  # pylint: disable=protected-access
+      # every statistic of a variable pairs the same two arrays: the label
+      # comparison is made once per pair of coordinate sets
+      pair = (id(predictions._coords), id(targets._coords))  # pylint: disable=protected-access
+      hit = _CHECKED_PAIRS.get(pair)
+      if not (hit is not None and hit[0]() is predictions and
+              hit[1]() is targets and hit[2] == (
+                  getattr(predictions, '_version', 0),
+                  getattr(targets, '_version', 0))):
+        xl._check_index_coords(predictions, targets)  # pylint: disable=protected-access
+        try:
+          if len(_CHECKED_PAIRS) > 256:
+            _CHECKED_PAIRS.clear()
+          _CHECKED_PAIRS[pair] = (
+              weakref.ref(predictions), weakref.ref(targets),
+              (getattr(predictions, '_version', 0),
+               getattr(targets, '_version', 0)))
+        except TypeError:
+          pass
     dims = predictions.dims + tuple(
         d for d in targets.dims if d not in predictions.dims)
     sizes = dict(targets.sizes, **predictions.sizes)

@@ -120,12 +120,14 @@ class DataArray:
     self.name = name
     self.attrs = dict(attrs or {})
     self._coords: dict[Hashable, DataArray] = {}
-    for key, value in (coords or {}).items():
-      self._set_coord(key, value)
+    if coords:
+      sizes = dict(zip(dims, payload.shape))
+      for key, value in coords.items():
+        self._set_coord(key, value, sizes)
 
   # -- construction helpers -------------------------------------------------
 
-  def _set_coord(self, key, value):
+  def _set_coord(self, key, value, sizes=None):
     if isinstance(value, DataArray):
       cv = DataArray(value._data, value.dims, name=key, attrs=value.attrs)
     elif isinstance(value, tuple) and len(value) == 2 and (
@@ -142,7 +144,8 @@ class DataArray:
         cv = DataArray(arr, (key,), name=key)
       else:
         raise ValueError(f'coordinate {key!r} needs explicit dims')
-    sizes = self.sizes
+    if sizes is None:
+      sizes = self.sizes
     for d, n in zip(cv.dims, cv.shape):
       if d not in sizes:
         raise ValueError(f'coordinate {key!r} has dim {d!r} not on the array')
