@@ -7,7 +7,7 @@
 #include <type_traits>
 
 #include "det_reduce.cuh"
-#include "det_bins2.cuh"
+#include "det_bins3.cuh"
 
 namespace wbx {
 
@@ -50,54 +50,46 @@ struct wbx_det_plan {
   wbx::DevBuf class_map;
   std::vector<double> class_w;   // sum of w_y over the points of every class
   wbx::BinParams bins{};
-  // second-generation binned kernel (det_bins2.cuh): usable when no aligned
-  // block of 8 map elements holds more than two classes
-  bool bins2 = false;
+  // third-generation binned kernel (det_bins3.cuh): the reduction schedule
+  // the host compiles from the class map (slots, segments, class -> segments)
+  struct Bins3 {
+    bool ok = false, wx = false;
+    int part = 0, S = 0, total_segs = 0, n_cols = 0;
+    wbx::DevBuf tables;
+    const uint32_t* d_desc = nullptr;
+    const void* d_w = nullptr;
+    const int32_t* d_seg_base = nullptr;
+    const int32_t* d_class_ptr = nullptr;
+    const int32_t* d_class_segs = nullptr;
+  } bins3;
   int cells_mult() const { return n_classes > 0 ? n_classes : 1; }
 };
 
 namespace wbx {
 
-// Grid geometry of the second-generation binned kernel for a launch of nj
-// jobs: S slab parts of <= 4096 elements, S_cta of them in flight (the others
-// follow in rounds), J job groups, S_cta * J <= #SMs.
-struct Bins2Geometry {
-  int S = 0, S_cta = 0, J = 0, part = 0, stage_bytes = 0, stages = 0, na = 0;
+// Launch geometry of the third-generation binned kernel for nj jobs: the S
+// slab parts are fixed by the plan; small slabs share the SMs out between
+// slab parts and J job groups (S_cta * J <= #SMs).
+struct Bins3Geometry {
+  int S_cta = 0, J = 0, stage_bytes = 0, stages = 0;
   size_t smem = 0;
   bool ok = false;
 };
 
-static Bins2Geometry bins2_geometry(const wbx_ctx* ctx, const wbx_det_plan* plan,
+static Bins3Geometry bins3_geometry(const wbx_ctx* ctx, const wbx_det_plan* plan,
                                     long long nj) {
-  Bins2Geometry g;
-  const long long slab = plan->ny * plan->nx;
+  Bins3Geometry g;
+  const wbx_det_plan::Bins3& b = plan->bins3;
+  if (!b.ok) return g;
   const int G = ctx->sm_count;
-  const long long s_min = (slab + 4095) / 4096;
-  const long long rounds = (s_min + G - 1) / G;
-  // parts in flight: all SMs when the slab is large; for small slabs the SMs
-  // are shared out between slab parts and job groups
-  long long s_cta = G;
-  g.J = 1;
-  if (rounds == 1) {
-    g.J = static_cast<int>(std::max<long long>(
-        1, std::min<long long>(nj, G / s_min)));
-    s_cta = std::max<long long>(s_min, std::min<long long>(
-        G / g.J, (slab + 511) / 512));
-  }
-  const long long want = s_cta * rounds;
-  g.part = static_cast<int>(round_up((slab + want - 1) / want, 16));
-  if (g.part > 4096) return g;
-  g.S = static_cast<int>((slab + g.part - 1) / g.part);
-  g.S_cta = static_cast<int>(std::min<long long>(s_cta, g.S));
-  g.na = (plan->has_clim ? 6 : 3) + (plan->has_mask ? 1 : 0);
+  g.S_cta = std::min(b.S, G);
+  g.J = static_cast<int>(
+      std::max<long long>(1, std::min<long long>(nj, G / g.S_cta)));
   g.stage_bytes = static_cast<int>(round_up(
-      static_cast<size_t>(g.part) * 4 * (plan->has_clim ? 3 : 2) +
-          (plan->has_mask ? g.part : 0), 128));
-  const size_t overhead =
-      2 * kMaxStages * sizeof(uint64_t) + kMaxStages * sizeof(StageMeta) + 128 +
-      static_cast<size_t>(kConsumerWarps) * plan->n_classes * g.na *
-          sizeof(double) +
-      (kConsumerThreads + kConsumerWarps) * sizeof(int);  // block permutation
+      static_cast<size_t>(b.part) * 4 * (plan->has_clim ? 3 : 2) +
+          (plan->has_mask ? b.part : 0), 128));
+  const size_t overhead = 2 * kMaxStages * sizeof(uint64_t) +
+                          kMaxStages * sizeof(StageMeta) + 128;
   const size_t cap = std::min<size_t>(ctx->smem_optin, 227 * 1024);
   if (overhead + 2 * static_cast<size_t>(g.stage_bytes) > cap) return g;
   g.stages = static_cast<int>(
@@ -105,6 +97,192 @@ static Bins2Geometry bins2_geometry(const wbx_ctx* ctx, const wbx_det_plan* plan
   g.smem = static_cast<size_t>(g.stages) * g.stage_bytes + overhead;
   g.ok = g.stages >= 2;
   return g;
+}
+
+// Host tables of the reduction schedule (see det_bins3.cuh).
+struct Bins3Host {
+  int part = 0, S = 0, total_segs = 0;
+  std::vector<uint32_t> desc;
+  std::vector<double> w64;
+  std::vector<float> w32;
+  std::vector<int32_t> seg_base, class_ptr, class_segs;
+};
+
+// Slots, segments and class lists for parts of `part` elements; false when a
+// part needs more than kBins3Slots slots.
+static bool bins3_schedule(const unsigned char* cmap, int n_classes,
+                           long long slab, long long nx, const double* w_y,
+                           const double* w_x, bool wx, int part, Bins3Host* T) {
+  struct Slot { int cls, quad, sel; };
+  const int S = static_cast<int>((slab + part - 1) / part);
+  T->part = part;
+  T->S = S;
+  T->desc.assign(static_cast<size_t>(S) * kBins3Slots, 0u);
+  if (wx) T->w32.assign(static_cast<size_t>(S) * kBins3Slots * 4, 0.f);
+  else T->w64.assign(static_cast<size_t>(S) * kBins3Slots, 0.0);
+  T->seg_base.assign(S + 1, 0);
+  std::vector<std::vector<int32_t>> segs_of(n_classes);
+  std::vector<Slot> slots, sorted;
+  std::vector<int> count(n_classes + 1);
+  int n_seg_total = 0;
+  for (int s = 0; s < S; ++s) {
+    const long long e_lo = static_cast<long long>(s) * part;
+    const int len = static_cast<int>(std::min<long long>(part, slab - e_lo));
+    slots.clear();
+    for (int q = 0; q < len / 4; ++q) {
+      const unsigned char* c4 = cmap + e_lo + 4 * q;
+      int done = 0;
+      for (int i = 0; i < 4; ++i) {
+        if (done & (1 << i)) continue;
+        int sel = 0;
+        for (int k = i; k < 4; ++k)
+          if (c4[k] == c4[i]) sel |= 1 << k;
+        done |= sel;
+        slots.push_back({c4[i], q, sel});
+      }
+    }
+    const int n = static_cast<int>(slots.size());
+    if (n > kBins3Slots) return false;
+    // counting sort by class (quads stay ascending inside a class)
+    std::fill(count.begin(), count.end(), 0);
+    for (const Slot& sl : slots) ++count[sl.cls + 1];
+    for (int c = 0; c < n_classes; ++c) count[c + 1] += count[c];
+    sorted.resize(n);
+    for (const Slot& sl : slots) sorted[count[sl.cls]++] = sl;
+    // the two passes take equal shares, rounded up to whole warps
+    const int per_pass = static_cast<int>(
+        round_up((n + kBins3Passes - 1) / kBins3Passes, 32));
+    if (per_pass > kConsumerThreads) return false;
+    int seg_local = 0;
+    T->seg_base[s] = n_seg_total;
+    for (int ps = 0; ps < kBins3Passes; ++ps) {
+      for (int t0 = 0; t0 < kConsumerThreads; t0 += 32) {
+        // one warp, one pass: 32 consecutive slots, runs of equal class
+        int lane = 0;
+        while (lane < 32) {
+          const int i = ps * per_pass + t0 + lane;
+          const size_t at =
+              (static_cast<size_t>(s) * kBins3Passes + ps) * kConsumerThreads +
+              t0 + lane;
+          if (t0 + lane >= per_pass || i >= n) {   // no slot: its own segment
+            T->desc[at] = bins3_pack(0, 0, lane, 0, 0);
+            ++lane;
+            continue;
+          }
+          int end = lane;
+          while (end + 1 < 32 && t0 + end + 1 < per_pass && i + (end + 1 - lane) < n &&
+                 sorted[i + (end + 1 - lane)].cls == sorted[i].cls)
+            ++end;
+          if (seg_local >= 4096) return false;
+          for (int l = lane; l <= end; ++l) {
+            const Slot& sl = sorted[i + (l - lane)];
+            const size_t al = at + (l - lane);
+            T->desc[al] = bins3_pack(sl.quad, sl.sel, lane, l == end, seg_local);
+            const long long e = e_lo + 4ll * sl.quad;
+            if (wx) {
+              for (int k = 0; k < 4; ++k) {
+                const long long y = (e + k) / nx, x = (e + k) % nx;
+                const double w = (w_y ? w_y[y] : 1.0) * (w_x ? w_x[x] : 1.0);
+                T->w32[al * 4 + k] =
+                    (sl.sel & (1 << k)) ? static_cast<float>(w) : 0.f;
+              }
+            } else {
+              T->w64[al] = w_y ? w_y[e / nx] : 1.0;
+            }
+          }
+          segs_of[sorted[i].cls].push_back(n_seg_total + seg_local);
+          ++seg_local;
+          lane = end + 1;
+        }
+      }
+    }
+    n_seg_total += seg_local;
+  }
+  T->seg_base[S] = n_seg_total;
+  T->total_segs = n_seg_total;
+  T->class_ptr.assign(n_classes + 1, 0);
+  T->class_segs.clear();
+  for (int c = 0; c < n_classes; ++c) {
+    T->class_segs.insert(T->class_segs.end(), segs_of[c].begin(),
+                         segs_of[c].end());
+    T->class_ptr[c + 1] = static_cast<int32_t>(T->class_segs.size());
+  }
+  return true;
+}
+
+// Chooses the part size (all SMs busy in whole rounds when the slab is large,
+// at least 512 elements per part when it is small), compiles the schedule and
+// uploads it.
+static int bins3_build(wbx_ctx* ctx, wbx_det_plan* p,
+                       const unsigned char* cmap) {
+  const long long slab = p->ny * p->nx;
+  const int G = ctx->sm_count;
+  const bool wx = p->has_wx || (p->nx % 4) != 0;
+  const long long s_min = (slab + 4095) / 4096;
+  long long want;
+  if (s_min >= G) {
+    want = (s_min + G - 1) / G * G;
+  } else {
+    const long long J = std::max<long long>(
+        1, std::min<long long>(p->n_jobs, G / s_min));
+    want = std::max<long long>(
+        s_min, std::min<long long>(G / J, (slab + 511) / 512));
+  }
+  Bins3Host T;
+  bool ok = false;
+  for (int attempt = 0; attempt < 24 && !ok; ++attempt) {
+    const int part = static_cast<int>(round_up((slab + want - 1) / want, 16));
+    if (part <= 4096)
+      ok = bins3_schedule(cmap, p->n_classes, slab, p->nx,
+                          p->has_wy ? p->wy.data() : nullptr,
+                          p->has_wx ? p->wx.data() : nullptr, wx, part, &T);
+    if (!ok) {
+      // more boundary quads than spare slots: smaller parts
+      if (part <= 16) break;
+      want = want >= G ? want + G : std::max(want + 1, want * 5 / 4);
+    }
+  }
+  if (!ok) return WBX_OK;   // the first-generation kernel serves the plan
+  wbx_det_plan::Bins3& b = p->bins3;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += round_up(bytes, 16);
+    return o;
+  };
+  const size_t o_desc = take(T.desc.size() * 4);
+  const size_t o_w = wx ? take(T.w32.size() * 4) : take(T.w64.size() * 8);
+  const size_t o_sb = take(T.seg_base.size() * 4);
+  const size_t o_cp = take(T.class_ptr.size() * 4);
+  const size_t o_cs = take(std::max<size_t>(T.class_segs.size(), 1) * 4);
+  std::vector<unsigned char> host(off, 0);
+  memcpy(host.data() + o_desc, T.desc.data(), T.desc.size() * 4);
+  if (wx) memcpy(host.data() + o_w, T.w32.data(), T.w32.size() * 4);
+  else memcpy(host.data() + o_w, T.w64.data(), T.w64.size() * 8);
+  memcpy(host.data() + o_sb, T.seg_base.data(), T.seg_base.size() * 4);
+  memcpy(host.data() + o_cp, T.class_ptr.data(), T.class_ptr.size() * 4);
+  if (!T.class_segs.empty())
+    memcpy(host.data() + o_cs, T.class_segs.data(), T.class_segs.size() * 4);
+  int rc = b.tables.reserve(off);
+  if (rc != WBX_OK) return rc;
+  unsigned char* base = b.tables.as<unsigned char>();
+  WBX_CUDA(cudaMemcpyAsync(base, host.data(), off, cudaMemcpyHostToDevice,
+                           ctx->stream));
+  WBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  b.d_desc = reinterpret_cast<const uint32_t*>(base + o_desc);
+  b.d_w = base + o_w;
+  b.d_seg_base = reinterpret_cast<const int32_t*>(base + o_sb);
+  b.d_class_ptr = reinterpret_cast<const int32_t*>(base + o_cp);
+  b.d_class_segs = reinterpret_cast<const int32_t*>(base + o_cs);
+  b.part = T.part;
+  b.S = T.S;
+  b.total_segs = T.total_segs;
+  b.wx = wx;
+  b.n_cols = (p->has_mask ? 1 : 0);
+  for (int k = 0; k < (p->has_clim ? 6 : 3); ++k)
+    if (p->stat_mask & (1 << k)) ++b.n_cols;
+  b.ok = true;
+  return WBX_OK;
 }
 
 }  // namespace wbx
@@ -179,24 +357,26 @@ static int launch_bins(wbx_ctx* ctx, const wbx_det_plan* plan,
   return ctx->prof_end();
 }
 
-static int launch_bins2(wbx_ctx* ctx, const wbx_det_plan* plan,
-                        const DetParams& P, const Bins2Geometry& g,
-                        int n_cells, double* records) {
+static int launch_bins3(wbx_ctx* ctx, const wbx_det_plan* plan,
+                        const DetParams& P, const Bins3Geometry& g,
+                        double* records) {
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
-  Bins2Params B;
-  B.class_map = plan->class_map.as<unsigned char>();
-  B.n_classes = plan->n_classes;
-  B.S = g.S;
+  const wbx_det_plan::Bins3& b = plan->bins3;
+  Bins3Params B;
+  B.slot_desc = b.d_desc;
+  B.slot_w = b.d_w;
+  B.seg_base = b.d_seg_base;
+  B.S = b.S;
   B.S_cta = g.S_cta;
   B.J = g.J;
-  B.part = g.part;
-  B.n_cells = n_cells;
+  B.part = b.part;
+  B.total_segs = b.total_segs;
+  B.n_cols = b.n_cols;
   B.records = records;
-  const bool wx = plan->has_wx || (plan->nx % 4) != 0;
-#define WBX_BINS2_LAUNCH(A, M, W)                                              \
+#define WBX_BINS3_LAUNCH(A, M, W)                                              \
   do {                                                                         \
-    auto kern = det_reduce_bins2_kernel<A, M, W>;                              \
+    auto kern = det_reduce_bins3_kernel<A, M, W>;                              \
     WBX_CUDA(cudaFuncSetAttribute(kern,                                        \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   static_cast<int>(g.smem)));                  \
@@ -204,30 +384,39 @@ static int launch_bins2(wbx_ctx* ctx, const wbx_det_plan* plan,
         P, B, g.stages, g.stage_bytes);                                        \
   } while (0)
   const int key = (plan->has_clim ? 4 : 0) | (plan->has_mask ? 2 : 0) |
-                  (wx ? 1 : 0);
+                  (b.wx ? 1 : 0);
   switch (key) {
-    case 0: WBX_BINS2_LAUNCH(false, false, false); break;
-    case 1: WBX_BINS2_LAUNCH(false, false, true); break;
-    case 2: WBX_BINS2_LAUNCH(false, true, false); break;
-    case 3: WBX_BINS2_LAUNCH(false, true, true); break;
-    case 4: WBX_BINS2_LAUNCH(true, false, false); break;
-    case 5: WBX_BINS2_LAUNCH(true, false, true); break;
-    case 6: WBX_BINS2_LAUNCH(true, true, false); break;
-    default: WBX_BINS2_LAUNCH(true, true, true); break;
+    case 0: WBX_BINS3_LAUNCH(false, false, false); break;
+    case 1: WBX_BINS3_LAUNCH(false, false, true); break;
+    case 2: WBX_BINS3_LAUNCH(false, true, false); break;
+    case 3: WBX_BINS3_LAUNCH(false, true, true); break;
+    case 4: WBX_BINS3_LAUNCH(true, false, false); break;
+    case 5: WBX_BINS3_LAUNCH(true, false, true); break;
+    case 6: WBX_BINS3_LAUNCH(true, true, false); break;
+    default: WBX_BINS3_LAUNCH(true, true, true); break;
   }
-#undef WBX_BINS2_LAUNCH
+#undef WBX_BINS3_LAUNCH
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   return ctx->prof_end();
 }
 
-static int launch_bins2_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
-                                 const Bins2Geometry& g, const double* records,
+static size_t bins3_record_bytes(const wbx_det_plan* plan,
+                                 const Bins3Geometry& g, int n_cells) {
+  return static_cast<size_t>(n_cells + g.J) * plan->bins3.total_segs *
+         plan->bins3.n_cols * sizeof(double);
+}
+
+static int launch_bins3_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
+                                 const Bins3Geometry& g, const double* records,
                                  const int32_t* d_first, const double* d_cell_w,
                                  int n_cells, long long n_jobs, double* out_ws,
                                  double* out_w, int accumulate) {
-  Bins2FinalizeParams F;
+  const wbx_det_plan::Bins3& b = plan->bins3;
+  Bins3FinalizeParams F;
   F.records = records;
+  F.class_ptr = b.d_class_ptr;
+  F.class_segs = b.d_class_segs;
   F.cell_first_job = d_first;
   F.cell_class_w = plan->has_mask ? nullptr : d_cell_w;
   F.out_ws = out_ws;
@@ -235,13 +424,14 @@ static int launch_bins2_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
   F.n_jobs = n_jobs;
   F.n_cells = n_cells;
   F.n_classes = plan->n_classes;
-  F.S = g.S;
   F.J = g.J;
+  F.total_segs = b.total_segs;
+  F.n_cols = b.n_cols;
+  F.stat_mask = plan->stat_mask;
   F.ns = plan->has_clim ? 6 : 3;
-  F.na = g.na;
   F.accumulate = accumulate;
   if (!accumulate) {
-    // statistic slots a launch without climatology does not produce stay 0
+    // statistic slots the launch does not produce stay 0
     WBX_CUDA(cudaMemsetAsync(
         out_ws, 0,
         sizeof(double) * n_cells * plan->n_classes * WBX_NUM_DET_STATS,
@@ -252,10 +442,10 @@ static int launch_bins2_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
         ctx->stream));
   }
   const long long warps =
-      static_cast<long long>(n_cells) * plan->n_classes * (g.na + 1);
+      static_cast<long long>(n_cells) * plan->n_classes * (b.n_cols + 1);
   const int block = 128;
   const long long blocks = (warps * 32 + block - 1) / block;
-  det_bins2_finalize_kernel<<<static_cast<unsigned>(blocks), block, 0,
+  det_bins3_finalize_kernel<<<static_cast<unsigned>(blocks), block, 0,
                               ctx->stream>>>(F);
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -592,24 +782,6 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
                      "(skipna, slab %% 16 or too many classes x statistics)");
       return WBX_ERR_UNSUPPORTED;
     }
-    // second-generation kernel: a thread keeps two class slots in registers
-    // for its aligned block of 8 map elements; blocks with more classes take
-    // a serial path, which must stay rare (<= 2 % of the blocks)
-    p->bins2 = !(d->flags & WBX_FLAG_BINS_V1) && (slab_ % 8) == 0;
-    if (p->bins2) {
-      int64_t overflow = 0;
-      for (int64_t e = 0; e < slab_; e += 8) {
-        const unsigned char a = d->class_map[e];
-        int other = -1;
-        for (int i = 1; i < 8; ++i) {
-          const unsigned char c = d->class_map[e + i];
-          if (c == a) continue;
-          if (other < 0) other = c;
-          else if (c != other) { ++overflow; break; }
-        }
-      }
-      p->bins2 = overflow * 50 <= slab_ / 8;
-    }
     p->class_w.assign(d->n_classes, 0.0);
     for (int64_t e = 0; e < slab_; ++e) {
       const int c = d->class_map[e];
@@ -692,6 +864,10 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
                              cudaMemcpyHostToDevice, ctx->stream));
     WBX_CUDA(cudaStreamSynchronize(ctx->stream));
     p->bins.class_map = p->class_map.as<unsigned char>();
+    if (!(d->flags & WBX_FLAG_BINS_V1)) {
+      rc = wbx::bins3_build(ctx, p, d->class_map);
+      if (rc != WBX_OK) { delete p; return rc; }
+    }
   }
   // weights (shared by both spaces)
   {
@@ -805,26 +981,24 @@ int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan) {
   plan->tables.release_idle();
   plan->weights.release_idle();
   plan->class_map.release_idle();
+  plan->bins3.tables.release_idle();
   delete plan;
   return WBX_OK;
 }
 
 static int run_device_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
                             double* d_w, int accumulate) {
-  if (plan->bins2) {
-    const wbx::Bins2Geometry g = wbx::bins2_geometry(ctx, plan, plan->n_jobs);
+  if (plan->bins3.ok) {
+    const wbx::Bins3Geometry g = wbx::bins3_geometry(ctx, plan, plan->n_jobs);
     if (g.ok) {
-      const size_t rec_bytes = static_cast<size_t>(g.S) *
-                               (plan->n_cells + g.J) * plan->n_classes * g.na *
-                               sizeof(double);
-      int rc = ctx->records.reserve(rec_bytes);
+      int rc = ctx->records.reserve(wbx::bins3_record_bytes(
+          plan, g, static_cast<int>(plan->n_cells)));
       if (rc != WBX_OK) return rc;
       wbx::DetParams P = plan->params;
       P.records = nullptr;
-      rc = wbx::launch_bins2(ctx, plan, P, g, static_cast<int>(plan->n_cells),
-                             ctx->records.as<double>());
+      rc = wbx::launch_bins3(ctx, plan, P, g, ctx->records.as<double>());
       if (rc != WBX_OK) return rc;
-      return wbx::launch_bins2_finalize(
+      return wbx::launch_bins3_finalize(
           ctx, plan, g, ctx->records.as<double>(), plan->d_cell_first_job,
           plan->d_cell_w, static_cast<int>(plan->n_cells), plan->n_jobs, d_ws,
           d_w, accumulate);
@@ -1007,19 +1181,16 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     wbx::fill_steps(plan, &P);
     const int grid = wbx::grid_for(ctx, plan, P.total_tiles);
     const int n_cells = static_cast<int>(first.size()) - 1;
-    if (plan->bins2) {
-      const wbx::Bins2Geometry g =
-          wbx::bins2_geometry(ctx, plan, static_cast<long long>(nj));
+    if (plan->bins3.ok) {
+      const wbx::Bins3Geometry g =
+          wbx::bins3_geometry(ctx, plan, static_cast<long long>(nj));
       if (g.ok) {
-        const size_t b2_bytes = static_cast<size_t>(g.S) * (n_cells + g.J) *
-                                plan->n_classes * g.na * sizeof(double);
-        rc = ctx->records.reserve(b2_bytes);
+        rc = ctx->records.reserve(wbx::bins3_record_bytes(plan, g, n_cells));
         if (rc != WBX_OK) return rc;
         WBX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
-        rc = wbx::launch_bins2(ctx, plan, P, g, n_cells,
-                               ctx->records.as<double>());
+        rc = wbx::launch_bins3(ctx, plan, P, g, ctx->records.as<double>());
         if (rc != WBX_OK) return rc;
-        rc = wbx::launch_bins2_finalize(
+        rc = wbx::launch_bins3_finalize(
             ctx, plan, g, ctx->records.as<double>(),
             reinterpret_cast<const int32_t*>(tbase + o_first),
             reinterpret_cast<const double*>(tbase + o_cw), n_cells,
@@ -1108,9 +1279,8 @@ int wbx_det_plan_kernel(wbx_ctx* ctx, const wbx_det_plan* plan,
                         int32_t* kernel) {
   WBX_REQUIRE(ctx && plan && kernel, "wbx_det_plan_kernel: NULL argument");
   if (plan->n_classes > 0) {
-    const bool v2 = plan->bins2 &&
-                    wbx::bins2_geometry(ctx, plan, plan->n_jobs).ok;
-    *kernel = v2 ? WBX_KERNEL_BINS_V2 : WBX_KERNEL_BINS_V1;
+    const bool v3 = wbx::bins3_geometry(ctx, plan, plan->n_jobs).ok;
+    *kernel = v3 ? WBX_KERNEL_BINS_V3 : WBX_KERNEL_BINS_V1;
   } else {
     *kernel = plan->path;
   }

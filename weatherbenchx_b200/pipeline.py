@@ -62,6 +62,25 @@ def _resolve_out_path(out_path, agg_name):
   return out_path[agg_name]
 
 
+def _current_cuda_device():
+  """Index of the calling thread's CUDA device, or None without a GPU."""
+  try:
+    import torch  # pylint: disable=g-import-not-at-top
+    if torch.cuda.is_available():
+      return torch.cuda.current_device()
+  except ImportError:
+    pass
+  return None
+
+
+def _bind_cuda_device(device) -> None:
+  """The CUDA current device is per host thread and starts at 0: a thread that
+  works for rank r has to be put on the device of the thread that made it."""
+  if device is not None:
+    import torch  # pylint: disable=g-import-not-at-top
+    torch.cuda.set_device(device)
+
+
 class _Prefetcher:
   """Loads chunks on a background thread, ``depth`` ahead of the consumer."""
 
@@ -73,6 +92,7 @@ class _Prefetcher:
     self._setup_fn = setup_fn
     self._queue: queue.Queue = queue.Queue(maxsize=max(depth, 1))
     self._thread = None
+    self._device = _current_cuda_device()
     self.load_seconds = 0.0
     if depth > 0:
       self._thread = threading.Thread(target=self._work, daemon=True)
@@ -91,6 +111,7 @@ class _Prefetcher:
 
   def _work(self):
     try:
+      _bind_cuda_device(self._device)
       if self._setup_fn is not None:
         self._setup_fn()
       for index in self._indices:
@@ -126,6 +147,7 @@ def _evaluate_in_lanes(items, evaluate, lanes: int):
   inbox: queue.Queue = queue.Queue(maxsize=lanes)
   outbox: queue.Queue = queue.Queue()
   stop = threading.Event()
+  device = _current_cuda_device()
 
   def put(q, value):
     while not stop.is_set():
@@ -137,6 +159,7 @@ def _evaluate_in_lanes(items, evaluate, lanes: int):
     return False
 
   def worker(lane):
+    _bind_cuda_device(device)
     _cabi.set_thread_lane(lane)
     while not stop.is_set():
       try:
@@ -153,6 +176,7 @@ def _evaluate_in_lanes(items, evaluate, lanes: int):
 
   def feeder():
     seq = 0
+    _bind_cuda_device(device)
     try:
       for item in items:
         if not put(inbox, (seq, item)):
