@@ -979,6 +979,11 @@ def run_b200(args):
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
   if not torch.cuda.is_available():
     raise RuntimeError('bench.py needs a B200; there is no CPU fallback')
+  from weatherbenchx_b200 import distributed as wbx_distributed
+  # rank -> GPU: spread over the PCIe uplinks when GPUs are left over
+  device_index = wbx_distributed.device_for_local_rank(
+      local_rank, int(os.environ.get('LOCAL_WORLD_SIZE', str(world))))
+  local_rank = device_index
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
   if world > 1:
@@ -1242,7 +1247,12 @@ def run_b200(args):
                    "rank's device-resident AggregationState (accumulate=1); ONE "
                    'f64 all-reduce of the packed state after the K chunks, '
                    'inside the timed region',
-          'e2e_steps': e2e_steps},
+          'e2e_steps': e2e_steps,
+          'devices': [wbx_distributed.device_for_local_rank(r, world)
+                      for r in range(world)],
+          'placement': 'ranks spread over the visible GPUs (the GPUs 0-3 and '
+                       '4-7 of the box share one host uplink each: '
+                       'profiles/h2d_ceiling_r2_box8_n8.json)'},
       'e2e': {
           'value': e2e_value, 'unit': 'grid-points/s',
           'ms_per_step': 1e3 * e2e_s / e2e_steps,

@@ -65,8 +65,8 @@ enum {
   WBX_FLAG_MASK_DEVICE = 256, /* WBX_SPACE_HOST plans only: the mask addresses
                                are device pointers (the mask coordinate of
                                device-resident targets)                      */
-  WBX_FLAG_BINS_V1 = 512    /* tuning/debug: serve a class_map plan with the
-                               first-generation binned kernel                */
+  WBX_FLAG_BINS_V1 = 512    /* retired (was: first-generation binned kernel);
+                               accepted and ignored                          */
 };
 
 /* Slots of the fused deterministic statistics (unique_name in comments). */
@@ -234,14 +234,32 @@ int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan);
 int wbx_det_plan_run(wbx_ctx* ctx, wbx_det_plan* plan, double* sum_ws,
                      double* sum_w, int32_t out_space, int32_t accumulate);
 /* Which kernel serves the plan (introspection for tests and profiling):
- * 0 TMA ring, 1 vectorised LDG, 2 scalar LDG, 3 binned (first generation),
- * 4 binned (second generation: static slab parts, csrc/det_bins2.cuh). */
+ * 0 TMA ring, 1 vectorised LDG, 2 scalar LDG, 5 binned (host-compiled
+ * reduction schedule, csrc/det_bins3.cuh; 3 and 4 were its predecessors). */
 enum {
   WBX_KERNEL_TMA = 0, WBX_KERNEL_LDG4 = 1, WBX_KERNEL_LDG1 = 2,
-  WBX_KERNEL_BINS_V1 = 3, WBX_KERNEL_BINS_V2 = 4
+  WBX_KERNEL_BINS_V1 = 3 /* retired */, WBX_KERNEL_BINS_V2 = 4 /* retired */,
+  WBX_KERNEL_BINS_V3 = 5
 };
 int wbx_det_plan_kernel(wbx_ctx* ctx, const wbx_det_plan* plan,
                         int32_t* kernel);
+/* Host-only introspection of the binned kernel's reduction schedule (no GPU
+ * is touched; csrc/det_bins3.cuh): what wbx_det_plan_create compiles from a
+ * class map -- the reference's bin masks (binning.py:22-49) folded over the
+ * slab dims, aggregation.py:320-335 -- for slab parts of `part` elements.
+ * Caller-allocated outputs, with S = ceil(ny * nx / part):
+ *   desc [S * 512 * 2] two words per consumer thread, layout [part][thread]:
+ *        a = [9:0] first quad of the part | [19:10] second quad | [23:20]
+ *        element selection of the first | [27:24] of the second (0: unused);
+ *        b = [1:0] first 8-lane group of the thread's segment | [2] the
+ *        thread's group closes the segment | [15:3] segment of the part;
+ *   seg_base [S + 1]; class_ptr [n_classes + 1]; class_segs [<= S * 64].
+ * WBX_ERR_UNSUPPORTED when a part would need more than 1024 slots. */
+int wbx_bins_schedule_tables(const unsigned char* class_map, int32_t n_classes,
+                             int64_t ny, int64_t nx, int32_t part,
+                             uint32_t* desc, int32_t* seg_base,
+                             int32_t* class_ptr, int32_t* class_segs,
+                             int32_t* total_segs);
 /* One-shot convenience: create + run (host outputs) + destroy. */
 int wbx_det_reduce(wbx_ctx* ctx, const wbx_det_desc* desc, double* sum_ws,
                    double* sum_w);

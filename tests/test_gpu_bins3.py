@@ -1,8 +1,8 @@
-"""The second-generation binned kernel (csrc/det_bins2.cuh) through the C ABI:
-per-(cell, class) sums against NumPy float64, against the first-generation
-kernel (WBX_FLAG_BINS_V1), across grid geometries (slab parts x job groups,
-sequential rounds), job -> cell layouts, masks, climatology, per-element
-weights and class maps it must hand back to the first-generation kernel."""
+"""The binned kernel with the host-compiled reduction schedule
+(csrc/det_bins3.cuh) through the C ABI: per-(cell, class) sums against NumPy
+float64 across grid geometries (slab parts x job groups, sequential rounds), job -> cell layouts,
+masks, climatology, per-element weights and class maps with any number of
+classes inside a quad."""
 
 import numpy as np
 import pytest
@@ -37,7 +37,10 @@ def _class_map(rng, ny, nx, kind):
                    np.ones((8, 12), bool))[:ny, :nx]
     region = (np.arange(nx) > 37)[None, :] & (np.arange(ny) > ny // 3)[:, None]
     cmap = land * 2 + region
-  elif kind == 'noise':     # many classes per block: first-generation kernel
+  elif kind == 'many':      # 120 classes x 7 accumulators: no table of sums
+    cmap = (np.arange(ny)[:, None] * 10 // ny) * 12 + (
+        np.arange(nx)[None, :] * 12 // nx)
+  elif kind == 'noise':     # up to four classes per quad
     cmap = rng.integers(0, 5, (ny, nx))
   else:
     cmap = np.zeros((ny, nx), np.int64)
@@ -89,12 +92,16 @@ CASES = [
     (721, 1440, 6, 'two', 'edges3', False, False, False, 0b101),
     (128, 256, 9, 'per_job', 'edges3', True, True, False, 0b111111),
     (96, 146, 5, 'one', 'edges3', False, True, True, 0b110),
+    (721, 1440, 5, 'per_job', 'noise', False, False, False, 0b111),
+    (1440, 721, 6, 'two', 'edges3', False, False, True, 0b100),
+    (1440, 721, 4, 'per_job', 'blocks', True, True, True, 0b111111),
+    (721, 1440, 3, 'per_job', 'many', True, True, False, 0b111111),
 ]
 
 
 @pytest.mark.parametrize('space', ['device', 'host'])
 @pytest.mark.parametrize('case', CASES, ids=lambda c: '-'.join(map(str, c)))
-def test_bins2_matches_numpy_and_v1(case, space):
+def test_bins3_matches_numpy(case, space):
   ny, nx, n_jobs, cells, kind, clim, masked, wx, stat_mask = case
   assert (ny * nx) % 16 == 0, 'binned plans need slab % 16 == 0'
   rng = np.random.default_rng(100 + CASES.index(case))
@@ -132,34 +139,27 @@ def test_bins2_matches_numpy_and_v1(case, space):
       keep.append(host)
       base, step = host.ctypes.data, host[0].nbytes
     tables[name] = np.uint64(base) + np.arange(n_jobs, dtype=np.uint64) * np.uint64(step)
-  results = {}
-  for flag in (0, _cabi.FLAG_BINS_V1):
-    plan = _cabi.DetPlan(
-        ctx, space=_cabi.SPACE_DEVICE if space == 'device' else _cabi.SPACE_HOST,
-        flags=flag | (_cabi.FLAG_MASKED if masked else 0), ny=ny, nx=nx,
-        pred=tables['pred'], target=tables['target'], clim=tables.get('clim'),
-        mask=tables.get('mask'), cell=cell.astype(np.int32), n_cells=n_cells,
-        w_outer=w_o, w_y=w_y, w_x=w_x, stat_mask=stat_mask, class_map=cmap,
-        n_classes=n_classes)
-    want_kernel = (_cabi.KERNEL_BINS_V1 if flag or kind == 'noise'
-                   else _cabi.KERNEL_BINS_V2)
-    assert plan.kernel() == want_kernel, (plan.kernel(), want_kernel)
-    results[flag] = plan.run_to_host()
-    again = plan.run_to_host()
-    assert again[0].tobytes() == results[flag][0].tobytes()   # bit-stable
-    plan.close()
+  plan = _cabi.DetPlan(
+      ctx, space=_cabi.SPACE_DEVICE if space == 'device' else _cabi.SPACE_HOST,
+      flags=_cabi.FLAG_MASKED if masked else 0, ny=ny, nx=nx,
+      pred=tables['pred'], target=tables['target'], clim=tables.get('clim'),
+      mask=tables.get('mask'), cell=cell.astype(np.int32), n_cells=n_cells,
+      w_outer=w_o, w_y=w_y, w_x=w_x, stat_mask=stat_mask, class_map=cmap,
+      n_classes=n_classes)
+  assert plan.kernel() == _cabi.KERNEL_BINS_V3
+  ws, sw = plan.run_to_host()
+  again = plan.run_to_host()
+  assert again[0].tobytes() == ws.tobytes()   # bit-stable
+  assert again[1].tobytes() == sw.tobytes()
+  plan.close()
   ws_ref, sw_ref = _reference(p, t, c, mask, cell, n_cells, cmap, n_classes,
                               w_o, w_y, w_x, stat_mask & (0x3f if clim else 7))
-  for flag, (ws, sw) in results.items():
-    scale = np.abs(ws_ref).max(axis=0, keepdims=True) + 1e-30
-    np.testing.assert_allclose(ws / scale, ws_ref / scale, rtol=0, atol=2e-6,
-                               err_msg=f'flag {flag}')
-    np.testing.assert_allclose(sw, sw_ref, rtol=1e-10, err_msg=f'flag {flag}')
-  np.testing.assert_allclose(results[0][0], results[_cabi.FLAG_BINS_V1][0],
-                             rtol=1e-6, atol=1e-6 * np.abs(ws_ref).max())
+  scale = np.abs(ws_ref).max(axis=0, keepdims=True) + 1e-30
+  np.testing.assert_allclose(ws / scale, ws_ref / scale, rtol=0, atol=2e-6)
+  np.testing.assert_allclose(sw, sw_ref, rtol=1e-10)
 
 
-def test_bins2_nan_stays_in_its_class():
+def test_bins3_nan_stays_in_its_class():
   """A NaN poisons the class it belongs to and no other (the host's
   class-to-bin product then spreads it like the reference's einsum)."""
   ny, nx, n_jobs = 64, 128, 4

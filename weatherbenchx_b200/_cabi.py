@@ -28,6 +28,7 @@ FLAG_CLIM_DEVICE = 64
 FLAG_TARGET_DEVICE, FLAG_MASK_DEVICE = 128, 256
 FLAG_BINS_V1 = 512
 KERNEL_TMA, KERNEL_LDG4, KERNEL_LDG1, KERNEL_BINS_V1, KERNEL_BINS_V2 = range(5)
+KERNEL_BINS_V3 = 5
 NUM_DET_STATS = 6
 NUM_DET_WCLASSES = 4
 STAT_SLOT = {
@@ -181,6 +182,9 @@ SIGNATURES = {
     'wbx_det_plan_run': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int32, c_int32]),
     'wbx_det_plan_kernel': (c_int, [c_void_p, c_void_p, POINTER(c_int32)]),
+    'wbx_bins_schedule_tables': (c_int, [
+        c_void_p, c_int32, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+        c_void_p, c_void_p, POINTER(c_int32)]),
     'wbx_det_reduce': (c_int, [c_void_p, POINTER(DetDesc), c_void_p,
                                c_void_p]),
     'wbx_det_elementwise': (c_int, [c_void_p, c_int32, c_void_p, c_void_p,

@@ -14,24 +14,29 @@
 // every job of job group g through the TMA ring.  For every part the host
 // lists the part's SLOTS -- (quad of 4 contiguous elements, class, 4-bit
 // element selection): one slot per quad whose elements share a class, one per
-// class for the few quads a boundary runs through -- sorts them by class and
-// deals them out to the 512 consumer threads x 2 passes.  Thirty-two
-// consecutive slots (one warp, one pass) then hold a handful of class runs,
-// the SEGMENTS, whose lane ranges are static too.
+// class for the few quads a boundary runs through -- sorts them by class, pads
+// every class to a multiple of 16 slots and deals blocks of 16 out to groups
+// of 8 consumer threads: a thread owns slots u and u + 8 of its block, so
+//   * its two slots always belong to the same class (one accumulator set),
+//   * the 8 lanes of a group read 8 neighbouring quads (in the usual case of
+//     a run of whole quads: 128 contiguous bytes, no bank conflicts),
+//   * the 4 groups of a warp hold at most 4 class runs, the SEGMENTS.
 //
 // The kernel is therefore the unbinned one plus static per-thread data:
-//   * a thread reads the same quads for all jobs; weight (f64 row weight, or
-//     four f32 element weights for longitude-major arrays / odd row lengths)
-//     and selection live in registers;
-//   * per job: f32 statistics, f32 4-sums, one f64 FMA per statistic into the
-//     thread's accumulator -- no class logic, no branches that depend on data
-//     or on the map (one warp-uniform static branch picks the code with the
-//     element selection for warps that hold a boundary quad);
-//   * when the output cell changes: a segmented inclusive warp scan (5 shuffle
-//     steps, predicated on the static first lane of the segment) leaves every
-//     segment's sum in its last lane, which writes it to the segment's record.
-//     No shared-memory accumulators, no CTA barriers, every CTA does the same
-//     work whatever the map looks like.
+//   * a thread reads the same two quads for all jobs; weights (one f64 row
+//     weight per quad, or f64 element weights for longitude-major arrays /
+//     odd row lengths) and selections live in registers;
+//   * per job: f32 statistics, f32 4-sums, one f64 FMA per statistic and quad
+//     into the thread's accumulators -- no class logic, no branches that depend
+//     on data or on the map (one warp-uniform static branch picks the code with
+//     the element selection for warps that hold a boundary quad);
+//   * when the output cell changes: three butterfly steps over the 8 lanes of
+//     a group that reduce ALL accumulators at once (a lane ends up with the
+//     group sum of one of them), two more steps predicated on the static first
+//     group of the segment leave the segment's sums in its last group, whose
+//     lanes write them to the segment's record.  No shared-memory
+//     accumulators, no CTA barriers, every CTA does the same work whatever the
+//     map looks like.
 //   * the finalize kernel adds, per (cell, class), the records of the class's
 //     segments (a host-built list) in a fixed order.
 // No atomics, fixed summation orders => bit-stable results.  The class map is
@@ -42,22 +47,27 @@
 
 namespace wbx {
 
-constexpr int kBins3Passes = 2;
-constexpr int kBins3Slots = kBins3Passes * kConsumerThreads;  // per part
+constexpr int kBins3Slots = 2 * kConsumerThreads;  // per part
 
-// slot descriptor bits: [9:0] quad | [13:10] selection | [18:14] first lane of
-// the segment | [19] last lane of the segment | [31:20] segment of the part
-__host__ __device__ __forceinline__ uint32_t bins3_pack(int quad, int sel,
-                                                        int first, int last,
-                                                        int seg) {
-  return static_cast<uint32_t>(quad) | (static_cast<uint32_t>(sel) << 10) |
-         (static_cast<uint32_t>(first) << 14) |
-         (static_cast<uint32_t>(last) << 19) | (static_cast<uint32_t>(seg) << 20);
+// Slot descriptor of a consumer thread, two words.
+//   a: [9:0] first quad | [19:10] second quad | [23:20] selection of the
+//      first | [27:24] selection of the second (0: slot unused)
+//   b: [1:0] first group of the thread's segment | [2] the thread's group
+//      closes the segment | [15:3] segment of the part
+__host__ __device__ __forceinline__ uint32_t bins3_pack_a(int quad0, int quad1,
+                                                          int sel0, int sel1) {
+  return static_cast<uint32_t>(quad0) | (static_cast<uint32_t>(quad1) << 10) |
+         (static_cast<uint32_t>(sel0) << 20) |
+         (static_cast<uint32_t>(sel1) << 24);
+}
+__host__ __device__ __forceinline__ uint32_t bins3_pack_b(int first_group,
+                                                          int closes, int seg) {
+  return static_cast<uint32_t>(first_group) |
+         (static_cast<uint32_t>(closes) << 2) | (static_cast<uint32_t>(seg) << 3);
 }
 
 struct Bins3Params {
-  const uint32_t* slot_desc;  // [S][passes][512]
-  const void* slot_w;         // [S][passes][512] double, or float4 (WX)
+  const uint2* slot_desc;     // [S][512] (bins3_pack_a, bins3_pack_b)
   const int32_t* seg_base;    // [S + 1] first segment of every part
   int S;                      // slab parts
   int S_cta;                  // parts in flight; CTA (s, g) takes s, s + S_cta, ...
@@ -165,68 +175,104 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   // ------------------- consumers ---------------------------------------------
   const int ctid = threadIdx.x;
   const int stat_mask = P.stat_mask;
-  double acc[kBins3Passes][NA];
+  const int group = lane >> 3;
+  double acc[NA];
 #pragma unroll
-  for (int ps = 0; ps < kBins3Passes; ++ps)
-#pragma unroll
-    for (int a = 0; a < NA; ++a) acc[ps][a] = 0.0;
+  for (int a = 0; a < NA; ++a) acc[a] = 0.0;
 
   int s = 0;
   uint32_t ph = 0;
   for (int s_part = s_cta; s_part < B.S; s_part += B.S_cta) {
     // ---- the static schedule of this part -----------------------------------
-    int quad[kBins3Passes], seg_first[kBins3Passes], seg_rec[kBins3Passes];
-    unsigned sel[kBins3Passes];
-    bool partial[kBins3Passes], live[kBins3Passes];
-    double w64[kBins3Passes];
-    float4 w32[kBins3Passes];
+    int quad[2];
+    unsigned sel[2];
+    double wq[2][WX ? 4 : 1];   // row weight, or element weights
     const int seg0 = __ldg(B.seg_base + s_part);
+    const unsigned e_part = static_cast<unsigned>(s_part) * B.part;
+    const unsigned unx = static_cast<unsigned>(P.nx);
+    const uint2 d = __ldg(B.slot_desc +
+                          static_cast<size_t>(s_part) * kConsumerThreads + ctid);
+    quad[0] = static_cast<int>(d.x & 0x3ffu);
+    quad[1] = static_cast<int>((d.x >> 10) & 0x3ffu);
+    sel[0] = (d.x >> 20) & 0xfu;
+    sel[1] = (d.x >> 24) & 0xfu;
+    const int seg_first_group = static_cast<int>(d.y & 3u);
+    // record of the segment this lane closes (-1: it closes none)
+    const int seg_rec = (d.y & 4u) ? seg0 + static_cast<int>(d.y >> 3) : -1;
 #pragma unroll
-    for (int ps = 0; ps < kBins3Passes; ++ps) {
-      const size_t at =
-          (static_cast<size_t>(s_part) * kBins3Passes + ps) * kConsumerThreads +
-          ctid;
-      const uint32_t d = __ldg(B.slot_desc + at);
-      quad[ps] = static_cast<int>(d & 0x3ffu);
-      sel[ps] = (d >> 10) & 0xfu;
-      seg_first[ps] = static_cast<int>((d >> 14) & 31u);
-      // record of the segment this lane closes (-1: it closes none)
-      seg_rec[ps] = ((d >> 19) & 1u) ? seg0 + static_cast<int>(d >> 20) : -1;
+    for (int ps = 0; ps < 2; ++ps) {
+      const unsigned e = e_part + 4u * static_cast<unsigned>(quad[ps]);
+      unsigned y = e / unx, x = e - y * unx;
       if constexpr (WX) {
-        w32[ps] = __ldg(reinterpret_cast<const float4*>(B.slot_w) + at);
-        w64[ps] = 0.0;
-      } else {
-        w64[ps] = __ldg(reinterpret_cast<const double*>(B.slot_w) + at);
-        w32[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      partial[ps] = __any_sync(kFull, sel[ps] != 0xfu);
-      live[ps] = __any_sync(kFull, sel[ps] != 0u);
-    }
-
-    // sums of the segments of this warp -> their records, accumulators reset
-    auto flush = [&](const int cell) {
-      double* rec = B.records +
-                    static_cast<size_t>(cell - P.cell_base + grp) *
-                        B.total_segs * B.n_cols;
 #pragma unroll
-      for (int ps = 0; ps < kBins3Passes; ++ps) {
-        if (!live[ps]) continue;   // warp-uniform
-        int col = 0;
-#pragma unroll
-        for (int k = 0; k < NA; ++k) {
-          if (k >= NS || (stat_mask & (1 << k))) {   // warp-uniform
-            double v = acc[ps][k];
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-              const double up = __shfl_up_sync(kFull, v, dlt);
-              if (lane - dlt >= seg_first[ps]) v += up;
-            }
-            if (seg_rec[ps] >= 0)
-              rec[static_cast<size_t>(seg_rec[ps]) * B.n_cols + col] = v;
-            acc[ps][k] = 0.0;
-            ++col;
+        for (int i = 0; i < 4; ++i) {
+          wq[ps][i] = (P.w_y ? __ldg(P.w_y + y) : 1.0) *
+                      (P.w_x ? __ldg(P.w_x + x) : 1.0);
+          if (++x == unx) {
+            x = 0;
+            if (y + 1 < static_cast<unsigned>(P.ny)) ++y;
           }
         }
+      } else {  // rows are a multiple of four long: a quad stays in its row
+        wq[ps][0] = P.w_y ? __ldg(P.w_y + y) : 1.0;
+      }
+    }
+    // warp-uniform, static: does the warp hold slots at all / boundary quads
+    const bool live = __any_sync(kFull, (sel[0] | sel[1]) != 0u);
+    const bool partial = __any_sync(
+        kFull, (sel[0] != 0u && sel[0] != 0xfu) || (sel[1] != 0u && sel[1] != 0xfu));
+    const bool used0 = sel[0] != 0u, used1 = sel[1] != 0u;
+    const bool add8 = group - 1 >= seg_first_group;
+    const bool add16 = group - 2 >= seg_first_group;
+
+    // Sums of the segments of this warp -> their records, accumulators reset.
+    // All accumulators are reduced together: in step m of the butterfly over
+    // the 8 lanes of a group a lane keeps one half of its columns (the half
+    // bit m of its lane number names), sends the other half to its partner
+    // and adds what it receives, so after log2(NC) steps lane l holds column
+    // l % NC summed over those steps' partners -- NC - 1 shuffles instead of
+    // NC * log2(NC); the remaining steps (rest of the group, then the groups of
+    // the segment) work on that one value.  Unselected statistics ride along
+    // (their sums are never stored).
+    auto flush = [&](const int cell) {
+      if (!live) return;   // warp-uniform
+      constexpr int NC = NA <= 4 ? 4 : 8;
+      double v[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) v[k] = k < NA ? acc[k] : 0.0;
+#pragma unroll
+      for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+      int width = NC;
+#pragma unroll
+      for (int m = 1; m < 8; m <<= 1) {
+        if (width > 1) {
+          // columns 2j, 2j + 1 -> j: lanes with bit m clear keep the even one
+          const bool odd = (lane & m) != 0;
+#pragma unroll
+          for (int j = 0; j < width / 2; ++j) {
+            const double keep = odd ? v[2 * j + 1] : v[2 * j];
+            const double send = odd ? v[2 * j] : v[2 * j + 1];
+            v[j] = keep + __shfl_xor_sync(kFull, send, m);
+          }
+          width /= 2;
+        } else {
+          v[0] += __shfl_xor_sync(kFull, v[0], m);
+        }
+      }
+      // the groups of a segment: inclusive scan from its first group
+      const double up8 = __shfl_up_sync(kFull, v[0], 8);
+      if (add8) v[0] += up8;
+      const double up16 = __shfl_up_sync(kFull, v[0], 16);
+      if (add16) v[0] += up16;
+      // lane l of the closing group holds column l % NC (step m picked bit m
+      // of the column number)
+      const int k = lane & (NC - 1);
+      const bool wanted = k < NA && (k >= NS || ((stat_mask >> k) & 1));
+      if (seg_rec >= 0 && (lane & 7) < NC && wanted) {
+        const int col = __popc(stat_mask & ((1 << (k < NS ? k : NS)) - 1) &
+                               ((1 << NS) - 1));
+        B.records[(static_cast<size_t>(cell - P.cell_base + grp) *
+                       B.total_segs + seg_rec) * B.n_cols + col] = v[0];
       }
     };
 
@@ -234,80 +280,92 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     for (long long job = j_lo; job < j_hi; ++job) {
       mbar_wait(&full[s], ph);
       const StageMeta mt = meta[s];
+      // this job's operands are requested before the previous cell is flushed:
+      // the shared-memory latency hides behind the shuffles of the flush
+      float4 pv[2], tv[2], cv[2];
+      uint32_t mw[2];
+      {
+        const unsigned char* stg = ring + (size_t)s * stage_bytes;
+        const float4* sp = reinterpret_cast<const float4*>(stg);
+        const float4* stt = reinterpret_cast<const float4*>(stg + off_t);
+        const float4* sc = reinterpret_cast<const float4*>(stg + off_c);
+        const uint32_t* sm = reinterpret_cast<const uint32_t*>(stg + off_m);
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          pv[ps] = sp[quad[ps]];
+          tv[ps] = stt[quad[ps]];
+          cv[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+          mw[ps] = 0x01010101u;
+          if constexpr (CLIM) cv[ps] = sc[quad[ps]];
+          if constexpr (MASK) mw[ps] = sm[quad[ps]];
+        }
+      }
       if (mt.cell != cur_cell) {
         if (cur_cell >= 0) flush(cur_cell);
         cur_cell = mt.cell;
       }
-      const unsigned char* stg = ring + (size_t)s * stage_bytes;
-      const float4* sp = reinterpret_cast<const float4*>(stg);
-      const float4* stt = reinterpret_cast<const float4*>(stg + off_t);
-      const float4* sc = reinterpret_cast<const float4*>(stg + off_c);
-      const uint32_t* sm = reinterpret_cast<const uint32_t*>(stg + off_m);
+      if (live) {   // warp-uniform
 #pragma unroll
-      for (int ps = 0; ps < kBins3Passes; ++ps) {
-        if (!live[ps]) continue;   // warp-uniform
-        const float4 pv = sp[quad[ps]];
-        const float4 tv = stt[quad[ps]];
-        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t mw = 0x01010101u;
-        if constexpr (CLIM) cv = sc[quad[ps]];
-        if constexpr (MASK) mw = sm[quad[ps]];
-        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
-        const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
-        const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
-        PointStats<CLIM, MASK, false> q[4];
+        for (int ps = 0; ps < 2; ++ps) {
+          const float pp[4] = {pv[ps].x, pv[ps].y, pv[ps].z, pv[ps].w};
+          const float tt[4] = {tv[ps].x, tv[ps].y, tv[ps].z, tv[ps].w};
+          const float cc[4] = {cv[ps].x, cv[ps].y, cv[ps].z, cv[ps].w};
+          PointStats<CLIM, MASK, false> q[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          q[i].eval(pp[i], tt[i], cc[i],
-                    static_cast<unsigned char>(mw >> (8 * i)));
-        if (partial[ps]) {
-          // a boundary quad in this warp: elements of other classes (they
-          // belong to other slots) become exact zeros, NaN included
+          for (int i = 0; i < 4; ++i)
+            q[i].eval(pp[i], tt[i], cc[i],
+                      static_cast<unsigned char>(mw[ps] >> (8 * i)));
+          if (partial) {
+            // a boundary quad in this warp: elements of other classes (they
+            // belong to other slots) become exact zeros, NaN included
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const bool mine = (sel[ps] >> i) & 1u;
+            for (int i = 0; i < 4; ++i) {
+              const bool mine = (sel[ps] >> i) & 1u;
 #pragma unroll
-            for (int k = 0; k < NS; ++k) q[i].s[k] = mine ? q[i].s[k] : 0.f;
-            q[i].valid[0] = mine ? q[i].valid[0] : 0.f;
-          }
-        }
-        if constexpr (!WX) {
-          const double wj = w64[ps] * mt.wo;
-#pragma unroll
-          for (int k = 0; k < NS; ++k) {
-            if (stat_mask & (1 << k)) {   // warp-uniform
-              const float s4 = __fadd_rn(__fadd_rn(q[0].s[k], q[1].s[k]),
-                                         __fadd_rn(q[2].s[k], q[3].s[k]));
-              acc[ps][k] = fma(static_cast<double>(s4), wj, acc[ps][k]);
+              for (int k = 0; k < NS; ++k) q[i].s[k] = mine ? q[i].s[k] : 0.f;
+              q[i].valid[0] = mine ? q[i].valid[0] : 0.f;
             }
           }
-          if constexpr (MASK) {
-            const float n4 = (q[0].valid[0] + q[1].valid[0]) +
-                             (q[2].valid[0] + q[3].valid[0]);
-            acc[ps][NS] = fma(static_cast<double>(n4), wj, acc[ps][NS]);
-          }
-        } else {
-          // element weights (f32, rounded once on the host): weighted 4-sum in
-          // f32, accumulated in f64
-          const float wf[4] = {w32[ps].x, w32[ps].y, w32[ps].z, w32[ps].w};
+          // an unused slot (padding of a class to 16 slots) adds exact zeros
+          const bool used = ps == 0 ? used0 : used1;
+          if constexpr (!WX) {
+            const double wj = wq[ps][0] * mt.wo;
 #pragma unroll
-          for (int k = 0; k < NS; ++k) {
-            if (stat_mask & (1 << k)) {
-              const float s4 = __fadd_rn(
-                  __fadd_rn(__fmul_rn(q[0].s[k], wf[0]),
-                            __fmul_rn(q[1].s[k], wf[1])),
-                  __fadd_rn(__fmul_rn(q[2].s[k], wf[2]),
-                            __fmul_rn(q[3].s[k], wf[3])));
-              acc[ps][k] = fma(static_cast<double>(s4), mt.wo, acc[ps][k]);
+            for (int k = 0; k < NS; ++k) {
+              if (stat_mask & (1 << k)) {   // warp-uniform
+                float s4 = __fadd_rn(__fadd_rn(q[0].s[k], q[1].s[k]),
+                                     __fadd_rn(q[2].s[k], q[3].s[k]));
+                s4 = used ? s4 : 0.f;
+                acc[k] = fma(static_cast<double>(s4), wj, acc[k]);
+              }
             }
-          }
-          if constexpr (MASK) {
-            const float n4 =
-                __fadd_rn(__fadd_rn(__fmul_rn(q[0].valid[0], wf[0]),
-                                    __fmul_rn(q[1].valid[0], wf[1])),
-                          __fadd_rn(__fmul_rn(q[2].valid[0], wf[2]),
-                                    __fmul_rn(q[3].valid[0], wf[3])));
-            acc[ps][NS] = fma(static_cast<double>(n4), mt.wo, acc[ps][NS]);
+            if constexpr (MASK) {
+              float n4 = (q[0].valid[0] + q[1].valid[0]) +
+                         (q[2].valid[0] + q[3].valid[0]);
+              n4 = used ? n4 : 0.f;
+              acc[NS] = fma(static_cast<double>(n4), wj, acc[NS]);
+            }
+          } else {
+            // element weights: weighted 4-sum in f64, like the unbinned kernel
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+              if (stat_mask & (1 << k)) {
+                double s4 = static_cast<double>(q[3].s[k]) * wq[ps][3];
+                s4 = fma(static_cast<double>(q[2].s[k]), wq[ps][2], s4);
+                s4 = fma(static_cast<double>(q[1].s[k]), wq[ps][1], s4);
+                s4 = fma(static_cast<double>(q[0].s[k]), wq[ps][0], s4);
+                s4 = used ? s4 : 0.0;
+                acc[k] = fma(s4, mt.wo, acc[k]);
+              }
+            }
+            if constexpr (MASK) {
+              double n4 = static_cast<double>(q[3].valid[0]) * wq[ps][3];
+              n4 = fma(static_cast<double>(q[2].valid[0]), wq[ps][2], n4);
+              n4 = fma(static_cast<double>(q[1].valid[0]), wq[ps][1], n4);
+              n4 = fma(static_cast<double>(q[0].valid[0]), wq[ps][0], n4);
+              n4 = used ? n4 : 0.0;
+              acc[NS] = fma(n4, mt.wo, acc[NS]);
+            }
           }
         }
       }

@@ -47,17 +47,14 @@ struct wbx_det_plan {
   std::vector<float> thr_pred, thr_target;
   // binned plans (class map over the slab)
   int n_classes = 0;
-  wbx::DevBuf class_map;
   std::vector<double> class_w;   // sum of w_y over the points of every class
-  wbx::BinParams bins{};
   // third-generation binned kernel (det_bins3.cuh): the reduction schedule
   // the host compiles from the class map (slots, segments, class -> segments)
   struct Bins3 {
     bool ok = false, wx = false;
     int part = 0, S = 0, total_segs = 0, n_cols = 0;
     wbx::DevBuf tables;
-    const uint32_t* d_desc = nullptr;
-    const void* d_w = nullptr;
+    const uint2* d_desc = nullptr;
     const int32_t* d_seg_base = nullptr;
     const int32_t* d_class_ptr = nullptr;
     const int32_t* d_class_segs = nullptr;
@@ -102,27 +99,22 @@ static Bins3Geometry bins3_geometry(const wbx_ctx* ctx, const wbx_det_plan* plan
 // Host tables of the reduction schedule (see det_bins3.cuh).
 struct Bins3Host {
   int part = 0, S = 0, total_segs = 0;
-  std::vector<uint32_t> desc;
-  std::vector<double> w64;
-  std::vector<float> w32;
+  std::vector<uint32_t> desc;   // [S][512][2]
   std::vector<int32_t> seg_base, class_ptr, class_segs;
 };
 
 // Slots, segments and class lists for parts of `part` elements; false when a
-// part needs more than kBins3Slots slots.
+// part needs more than kBins3Slots slots (classes padded to 16 included).
 static bool bins3_schedule(const unsigned char* cmap, int n_classes,
-                           long long slab, long long nx, const double* w_y,
-                           const double* w_x, bool wx, int part, Bins3Host* T) {
+                           long long slab, int part, Bins3Host* T) {
   struct Slot { int cls, quad, sel; };
   const int S = static_cast<int>((slab + part - 1) / part);
   T->part = part;
   T->S = S;
-  T->desc.assign(static_cast<size_t>(S) * kBins3Slots, 0u);
-  if (wx) T->w32.assign(static_cast<size_t>(S) * kBins3Slots * 4, 0.f);
-  else T->w64.assign(static_cast<size_t>(S) * kBins3Slots, 0.0);
+  T->desc.assign(static_cast<size_t>(S) * kConsumerThreads * 2, 0u);
   T->seg_base.assign(S + 1, 0);
   std::vector<std::vector<int32_t>> segs_of(n_classes);
-  std::vector<Slot> slots, sorted;
+  std::vector<Slot> slots, padded;
   std::vector<int> count(n_classes + 1);
   int n_seg_total = 0;
   for (int s = 0; s < S; ++s) {
@@ -141,59 +133,61 @@ static bool bins3_schedule(const unsigned char* cmap, int n_classes,
         slots.push_back({c4[i], q, sel});
       }
     }
-    const int n = static_cast<int>(slots.size());
-    if (n > kBins3Slots) return false;
-    // counting sort by class (quads stay ascending inside a class)
+    // counting sort by class (quads stay ascending inside a class), every
+    // class padded with unused slots to a multiple of 16
     std::fill(count.begin(), count.end(), 0);
     for (const Slot& sl : slots) ++count[sl.cls + 1];
-    for (int c = 0; c < n_classes; ++c) count[c + 1] += count[c];
-    sorted.resize(n);
-    for (const Slot& sl : slots) sorted[count[sl.cls]++] = sl;
-    // the two passes take equal shares, rounded up to whole warps
-    const int per_pass = static_cast<int>(
-        round_up((n + kBins3Passes - 1) / kBins3Passes, 32));
-    if (per_pass > kConsumerThreads) return false;
+    size_t n_padded = 0;
+    for (int c = 0; c < n_classes; ++c) n_padded += round_up(count[c + 1], 16);
+    if (n_padded > static_cast<size_t>(kBins3Slots)) return false;
+    std::vector<int> start(n_classes + 1, 0);
+    for (int c = 0; c < n_classes; ++c)
+      start[c + 1] = start[c] + static_cast<int>(round_up(count[c + 1], 16));
+    padded.assign(n_padded, Slot{-1, 0, 0});
+    for (int c = 0; c < n_classes; ++c)
+      for (int u = start[c]; u < start[c + 1]; ++u) padded[u].cls = c;
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (const Slot& sl : slots) padded[fill[sl.cls]++] = sl;
+    // block b of 16 slots -> threads 8 b .. 8 b + 7 (slots u and u + 8)
+    const int n_blocks = static_cast<int>(n_padded / 16);
     int seg_local = 0;
     T->seg_base[s] = n_seg_total;
-    for (int ps = 0; ps < kBins3Passes; ++ps) {
-      for (int t0 = 0; t0 < kConsumerThreads; t0 += 32) {
-        // one warp, one pass: 32 consecutive slots, runs of equal class
-        int lane = 0;
-        while (lane < 32) {
-          const int i = ps * per_pass + t0 + lane;
-          const size_t at =
-              (static_cast<size_t>(s) * kBins3Passes + ps) * kConsumerThreads +
-              t0 + lane;
-          if (t0 + lane >= per_pass || i >= n) {   // no slot: its own segment
-            T->desc[at] = bins3_pack(0, 0, lane, 0, 0);
-            ++lane;
-            continue;
+    for (int t0 = 0; t0 < kConsumerThreads; t0 += 32) {
+      // one warp: four groups of 8 lanes, runs of groups of equal class
+      int g = 0;
+      while (g < 4) {
+        const int b0 = t0 / 8 + g;
+        if (b0 >= n_blocks) {   // unused group: sel 0, closes nothing
+          for (int l = 0; l < 8; ++l) {
+            const size_t at =
+                (static_cast<size_t>(s) * kConsumerThreads + t0 + 8 * g + l) * 2;
+            T->desc[at] = bins3_pack_a(0, 0, 0, 0);
+            T->desc[at + 1] = bins3_pack_b(g, 0, 0);
           }
-          int end = lane;
-          while (end + 1 < 32 && t0 + end + 1 < per_pass && i + (end + 1 - lane) < n &&
-                 sorted[i + (end + 1 - lane)].cls == sorted[i].cls)
-            ++end;
-          if (seg_local >= 4096) return false;
-          for (int l = lane; l <= end; ++l) {
-            const Slot& sl = sorted[i + (l - lane)];
-            const size_t al = at + (l - lane);
-            T->desc[al] = bins3_pack(sl.quad, sl.sel, lane, l == end, seg_local);
-            const long long e = e_lo + 4ll * sl.quad;
-            if (wx) {
-              for (int k = 0; k < 4; ++k) {
-                const long long y = (e + k) / nx, x = (e + k) % nx;
-                const double w = (w_y ? w_y[y] : 1.0) * (w_x ? w_x[x] : 1.0);
-                T->w32[al * 4 + k] =
-                    (sl.sel & (1 << k)) ? static_cast<float>(w) : 0.f;
-              }
-            } else {
-              T->w64[al] = w_y ? w_y[e / nx] : 1.0;
-            }
-          }
-          segs_of[sorted[i].cls].push_back(n_seg_total + seg_local);
-          ++seg_local;
-          lane = end + 1;
+          ++g;
+          continue;
         }
+        const int cls = padded[16 * b0].cls;
+        int g_end = g;
+        while (g_end + 1 < 4 && b0 + (g_end + 1 - g) < n_blocks &&
+               padded[16 * (b0 + (g_end + 1 - g))].cls == cls)
+          ++g_end;
+        if (seg_local >= 8192) return false;
+        for (int gg = g; gg <= g_end; ++gg) {
+          const int b = b0 + (gg - g);
+          for (int l = 0; l < 8; ++l) {
+            const Slot& s0 = padded[16 * b + l];
+            const Slot& s1 = padded[16 * b + 8 + l];
+            const size_t at =
+                (static_cast<size_t>(s) * kConsumerThreads + t0 + 8 * gg + l) * 2;
+            T->desc[at] = bins3_pack_a(s0.quad, s1.quad, s0.sel, s1.sel);
+            T->desc[at + 1] =
+                bins3_pack_b(g, gg == g_end, seg_local);
+          }
+        }
+        segs_of[cls].push_back(n_seg_total + seg_local);
+        ++seg_local;
+        g = g_end + 1;
       }
     }
     n_seg_total += seg_local;
@@ -233,9 +227,7 @@ static int bins3_build(wbx_ctx* ctx, wbx_det_plan* p,
   for (int attempt = 0; attempt < 24 && !ok; ++attempt) {
     const int part = static_cast<int>(round_up((slab + want - 1) / want, 16));
     if (part <= 4096)
-      ok = bins3_schedule(cmap, p->n_classes, slab, p->nx,
-                          p->has_wy ? p->wy.data() : nullptr,
-                          p->has_wx ? p->wx.data() : nullptr, wx, part, &T);
+      ok = bins3_schedule(cmap, p->n_classes, slab, part, &T);
     if (!ok) {
       // more boundary quads than spare slots: smaller parts
       if (part <= 16) break;
@@ -251,14 +243,11 @@ static int bins3_build(wbx_ctx* ctx, wbx_det_plan* p,
     return o;
   };
   const size_t o_desc = take(T.desc.size() * 4);
-  const size_t o_w = wx ? take(T.w32.size() * 4) : take(T.w64.size() * 8);
   const size_t o_sb = take(T.seg_base.size() * 4);
   const size_t o_cp = take(T.class_ptr.size() * 4);
   const size_t o_cs = take(std::max<size_t>(T.class_segs.size(), 1) * 4);
   std::vector<unsigned char> host(off, 0);
   memcpy(host.data() + o_desc, T.desc.data(), T.desc.size() * 4);
-  if (wx) memcpy(host.data() + o_w, T.w32.data(), T.w32.size() * 4);
-  else memcpy(host.data() + o_w, T.w64.data(), T.w64.size() * 8);
   memcpy(host.data() + o_sb, T.seg_base.data(), T.seg_base.size() * 4);
   memcpy(host.data() + o_cp, T.class_ptr.data(), T.class_ptr.size() * 4);
   if (!T.class_segs.empty())
@@ -269,8 +258,7 @@ static int bins3_build(wbx_ctx* ctx, wbx_det_plan* p,
   WBX_CUDA(cudaMemcpyAsync(base, host.data(), off, cudaMemcpyHostToDevice,
                            ctx->stream));
   WBX_CUDA(cudaStreamSynchronize(ctx->stream));
-  b.d_desc = reinterpret_cast<const uint32_t*>(base + o_desc);
-  b.d_w = base + o_w;
+  b.d_desc = reinterpret_cast<const uint2*>(base + o_desc);
   b.d_seg_base = reinterpret_cast<const int32_t*>(base + o_sb);
   b.d_class_ptr = reinterpret_cast<const int32_t*>(base + o_cp);
   b.d_class_segs = reinterpret_cast<const int32_t*>(base + o_cs);
@@ -328,35 +316,6 @@ static int launch_variant(wbx_ctx* ctx, const wbx_det_plan* plan,
   return ctx->prof_end();
 }
 
-static int launch_bins(wbx_ctx* ctx, const wbx_det_plan* plan,
-                       const DetParams& P, int grid) {
-  int prc = ctx->prof_begin();
-  if (prc != WBX_OK) return prc;
-#define WBX_BINS_LAUNCH2(A, B, W)                                              \
-  do {                                                                         \
-    auto kern = det_reduce_bins_kernel<A, B, W>;                               \
-    WBX_CUDA(cudaFuncSetAttribute(kern,                                        \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  static_cast<int>(plan->smem_bytes)));        \
-    kern<<<grid, kTmaThreads, plan->smem_bytes, ctx->stream>>>(                \
-        P, plan->bins, plan->stages, plan->stage_bytes);                       \
-  } while (0)
-#define WBX_BINS_LAUNCH(A, B)                                                  \
-  do {                                                                         \
-    if (plan->has_wx || (plan->nx % 4) != 0) WBX_BINS_LAUNCH2(A, B, true);     \
-    else WBX_BINS_LAUNCH2(A, B, false);                                        \
-  } while (0)
-  if (plan->has_clim && plan->has_mask) WBX_BINS_LAUNCH(true, true);
-  else if (plan->has_clim) WBX_BINS_LAUNCH(true, false);
-  else if (plan->has_mask) WBX_BINS_LAUNCH(false, true);
-  else WBX_BINS_LAUNCH(false, false);
-#undef WBX_BINS_LAUNCH
-#undef WBX_BINS_LAUNCH2
-  WBX_CUDA(cudaGetLastError());
-  ctx->launches++;
-  return ctx->prof_end();
-}
-
 static int launch_bins3(wbx_ctx* ctx, const wbx_det_plan* plan,
                         const DetParams& P, const Bins3Geometry& g,
                         double* records) {
@@ -365,7 +324,6 @@ static int launch_bins3(wbx_ctx* ctx, const wbx_det_plan* plan,
   const wbx_det_plan::Bins3& b = plan->bins3;
   Bins3Params B;
   B.slot_desc = b.d_desc;
-  B.slot_w = b.d_w;
   B.seg_base = b.d_seg_base;
   B.S = b.S;
   B.S_cta = g.S_cta;
@@ -454,7 +412,10 @@ static int launch_bins3_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
 
 static int launch_main(wbx_ctx* ctx, const wbx_det_plan* plan,
                        const DetParams& P, int grid) {
-  if (plan->n_classes > 0) return launch_bins(ctx, plan, P, grid);
+  if (plan->n_classes > 0) {
+    set_error("internal: binned plans have their own launch path");
+    return WBX_ERR_INVALID;
+  }
   const int key = (plan->xform ? 16 : 0) | (plan->has_clim ? 8 : 0) |
                   (plan->has_mask ? 4 : 0) | (plan->skipna ? 2 : 0) |
                   (plan->per_elem ? 1 : 0);
@@ -522,42 +483,6 @@ static int launch_finalize(wbx_ctx* ctx, const wbx_det_plan* plan,
                            const double* d_cell_w, int n_cells, int grid_main,
                            long long total_tiles, double* out_ws, double* out_w,
                            int accumulate) {
-  if (plan->n_classes > 0) {
-    BinFinalizeParams F;
-    F.records = records;
-    F.cell_first_job = d_first;
-    F.cell_class_w = plan->has_mask ? nullptr : d_cell_w;
-    F.out_ws = out_ws;
-    F.out_w = out_w;
-    F.total_tiles = total_tiles;
-    F.n_cells = n_cells;
-    F.grid_main = grid_main;
-    F.tiles_per_slab = plan->tiles_per_slab;
-    F.n_classes = plan->n_classes;
-    F.n_sel = plan->bins.n_sel;
-    F.accumulate = accumulate;
-    for (int i = 0; i < WBX_NUM_DET_STATS + 2; ++i) F.sel[i] = plan->bins.sel[i];
-    if (!accumulate) {
-      // unselected statistic slots are not written by the kernel
-      WBX_CUDA(cudaMemsetAsync(
-          out_ws, 0,
-          sizeof(double) * n_cells * plan->n_classes * WBX_NUM_DET_STATS,
-          ctx->stream));
-      WBX_CUDA(cudaMemsetAsync(
-          out_w, 0,
-          sizeof(double) * n_cells * plan->n_classes * WBX_NUM_DET_WCLASSES,
-          ctx->stream));
-    }
-    const long long warps =
-        static_cast<long long>(n_cells) * plan->n_classes * (F.n_sel + 1);
-    const int block = 128;
-    const long long blocks = (warps * 32 + block - 1) / block;
-    det_bins_finalize_kernel<<<static_cast<unsigned>(blocks), block, 0,
-                               ctx->stream>>>(F);
-    WBX_CUDA(cudaGetLastError());
-    ctx->launches++;
-    return WBX_OK;
-  }
   FinalizeParams F;
   F.records = records;
   F.cell_first_job = d_first;
@@ -766,20 +691,11 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     WBX_REQUIRE(d->class_map != nullptr, "det: n_classes > 0 needs a class_map");
     WBX_REQUIRE(d->n_classes <= 256, "det: at most 256 bin classes");
     p->n_classes = d->n_classes;
-    int nsel = 0;
-    for (int k = 0; k < WBX_NUM_DET_STATS + 2; ++k) p->bins.sel[k] = -1;
-    for (int k = 0; k < p->n_stats; ++k)
-      if (p->stat_mask & (1 << k)) p->bins.sel[nsel++] = k;
-    if (p->has_mask) p->bins.sel[nsel++] = -1;  // weight accumulator
-    p->bins.n_sel = nsel;
-    p->bins.n_classes = d->n_classes;
-    p->nacc = d->n_classes * nsel;
     const int64_t slab_ = d->ny * d->nx;
-    const bool ok = !p->skipna && (slab_ % 16) == 0 && p->nacc <= 448;
-    if (!ok) {
+    if (p->skipna || (slab_ % 16) != 0) {
       delete p;
       wbx::set_error("det: this binned request needs the generic path "
-                     "(skipna, slab %% 16 or too many classes x statistics)");
+                     "(skipna, or slab %% 16 != 0)");
       return WBX_ERR_UNSUPPORTED;
     }
     p->class_w.assign(d->n_classes, 0.0);
@@ -819,14 +735,11 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
   p->tiles_per_slab = static_cast<int>((slab + tile - 1) / tile);
   p->stage_bytes = static_cast<int>(round_up(
       static_cast<size_t>(tile) * 4 * (p->has_clim ? 3 : 2) +
-          (p->has_mask ? tile : 0) + (p->n_classes > 0 ? tile : 0),
+          (p->has_mask ? tile : 0),
       128));
   const size_t overhead =
       2 * wbx::kMaxStages * sizeof(uint64_t) +
-      wbx::kMaxStages * sizeof(wbx::StageMeta) + 128 +
-      (p->n_classes > 0
-           ? static_cast<size_t>(wbx::kConsumerWarps) * p->nacc * sizeof(double)
-           : 0);
+      wbx::kMaxStages * sizeof(wbx::StageMeta) + 128;
   const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024) - overhead;
   int stages = static_cast<int>(budget / p->stage_bytes);
   stages = std::min(stages, wbx::kMaxStages);
@@ -857,16 +770,14 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
 
   WBX_CUDA(cudaSetDevice(ctx->device));
   if (p->n_classes > 0) {
-    const size_t bytes = static_cast<size_t>(d->ny * d->nx);
-    int rc = p->class_map.reserve(bytes);
+    // the class map itself never goes to the GPU: the reduction schedule the
+    // host compiles from it does (det_bins3.cuh)
+    int rc = wbx::bins3_build(ctx, p, d->class_map);
     if (rc != WBX_OK) { delete p; return rc; }
-    WBX_CUDA(cudaMemcpyAsync(p->class_map.ptr, d->class_map, bytes,
-                             cudaMemcpyHostToDevice, ctx->stream));
-    WBX_CUDA(cudaStreamSynchronize(ctx->stream));
-    p->bins.class_map = p->class_map.as<unsigned char>();
-    if (!(d->flags & WBX_FLAG_BINS_V1)) {
-      rc = wbx::bins3_build(ctx, p, d->class_map);
-      if (rc != WBX_OK) { delete p; return rc; }
+    if (!p->bins3.ok) {
+      delete p;
+      wbx::set_error("det: no reduction schedule for this class map");
+      return WBX_ERR_UNSUPPORTED;
     }
   }
   // weights (shared by both spaces)
@@ -980,7 +891,6 @@ int wbx_det_plan_destroy(wbx_ctx* ctx, wbx_det_plan* plan) {
   }
   plan->tables.release_idle();
   plan->weights.release_idle();
-  plan->class_map.release_idle();
   plan->bins3.tables.release_idle();
   delete plan;
   return WBX_OK;
@@ -1279,11 +1189,41 @@ int wbx_det_plan_kernel(wbx_ctx* ctx, const wbx_det_plan* plan,
                         int32_t* kernel) {
   WBX_REQUIRE(ctx && plan && kernel, "wbx_det_plan_kernel: NULL argument");
   if (plan->n_classes > 0) {
-    const bool v3 = wbx::bins3_geometry(ctx, plan, plan->n_jobs).ok;
-    *kernel = v3 ? WBX_KERNEL_BINS_V3 : WBX_KERNEL_BINS_V1;
+    (void)ctx;
+    *kernel = WBX_KERNEL_BINS_V3;
   } else {
     *kernel = plan->path;
   }
+  return WBX_OK;
+}
+
+int wbx_bins_schedule_tables(const unsigned char* class_map, int32_t n_classes,
+                             int64_t ny, int64_t nx, int32_t part,
+                             uint32_t* desc, int32_t* seg_base,
+                             int32_t* class_ptr, int32_t* class_segs,
+                             int32_t* total_segs) {
+  WBX_REQUIRE(class_map && desc && seg_base && class_ptr && class_segs &&
+                  total_segs, "wbx_bins_schedule_tables: NULL argument");
+  WBX_REQUIRE(n_classes >= 1 && n_classes <= 256 && ny >= 1 && nx >= 1 &&
+                  (ny * nx) % 16 == 0 && part >= 16 && part <= 4096 &&
+                  part % 16 == 0,
+              "wbx_bins_schedule_tables: bad geometry");
+  for (int64_t e = 0; e < ny * nx; ++e)
+    WBX_REQUIRE(class_map[e] < n_classes,
+                "wbx_bins_schedule_tables: class_map value >= n_classes");
+  wbx::Bins3Host T;
+  if (!wbx::bins3_schedule(class_map, n_classes, ny * nx, part, &T)) {
+    wbx::set_error("wbx_bins_schedule_tables: a part of %d elements needs more "
+                   "than %d slots", part, wbx::kBins3Slots);
+    return WBX_ERR_UNSUPPORTED;
+  }
+  memcpy(desc, T.desc.data(), T.desc.size() * sizeof(uint32_t));
+  memcpy(seg_base, T.seg_base.data(), T.seg_base.size() * sizeof(int32_t));
+  memcpy(class_ptr, T.class_ptr.data(), T.class_ptr.size() * sizeof(int32_t));
+  if (!T.class_segs.empty())
+    memcpy(class_segs, T.class_segs.data(),
+           T.class_segs.size() * sizeof(int32_t));
+  *total_segs = T.total_segs;
   return WBX_OK;
 }
 

@@ -646,354 +646,6 @@ __global__ void __launch_bounds__(kLdgThreads)
 }
 
 // ---------------------------------------------------------------------------
-// Binned variant (aggregation.py:320-335: bin masks as extra xr.dot operands).
-//
-// All bin masks that depend only on the slab dims (Regions, LandSea, latitude /
-// longitude bands ...) are folded on the host into ONE uint8 class map over the
-// slab: two grid points are in the same class iff they belong to exactly the
-// same set of bins.  The kernel accumulates every statistic per (cell, class)
-// in a single pass over the fields -- HBM traffic stays 8/12 B per point however
-// many bins there are -- and the host turns class sums into bin sums with the
-// 0/1 membership matrix (a few hundred multiply-adds).
-//
-// Per float4 group a lane is either *uniform* (its four points share a class)
-// or *mixed* (a class boundary, e.g. a coastline, falls inside it).  Uniform
-// lanes are reduced warp-wide once per distinct (row, class) key; mixed lanes
-// are folded point by point.  Only lane 0 updates the warp-private
-// shared-memory accumulators, in a fixed order => still bit-stable.
-// ---------------------------------------------------------------------------
-struct BinParams {
-  const unsigned char* class_map;  // [slab] device
-  int n_classes;
-  int n_sel;                       // selected statistics (+1 weight if masked)
-  int sel[WBX_NUM_DET_STATS + 2];  // statistic slot of every selected index
-};
-
-__device__ __forceinline__ float warp_sum_f32(float v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1)
-    v += __shfl_xor_sync(0xffffffffu, v, off);
-  return v;
-}
-
-// WX: the weight varies along the rows of the slab (w_x; longitude-major
-// storage) and / or rows are not a multiple of four long: every element gets
-// its own f64 weight w_outer * w_y[y] * w_x[x], lanes are keyed by class alone
-// and reduced in f64.
-template <bool CLIM, bool MASK, bool WX>
-__global__ void __launch_bounds__(kTmaThreads, 1)
-    det_reduce_bins_kernel(const DetParams P, const BinParams B,
-                           const int stages, const int stage_bytes) {
-  constexpr int NS = CLIM ? 6 : 3;
-  extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* ring = smem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
-  uint64_t* empty = full + kMaxStages;
-  StageMeta* meta = reinterpret_cast<StageMeta*>(empty + kMaxStages);
-  double* wacc_all = reinterpret_cast<double*>(meta + kMaxStages);
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int nacc = B.n_classes * B.n_sel;   // doubles per warp
-  const long long t_begin =
-      (static_cast<long long>(blockIdx.x) * P.total_tiles) / gridDim.x;
-  const long long t_end =
-      (static_cast<long long>(blockIdx.x + 1) * P.total_tiles) / gridDim.x;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kConsumerWarps);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const int off_t = P.tile * 4;
-  const int off_c = P.tile * 8;
-  const int off_m = P.tile * 4 * (CLIM ? 3 : 2);
-  const int off_k = off_m + (MASK ? P.tile : 0);
-
-  if (warp == kConsumerWarps) {
-    if (lane == 0) {
-      const uint64_t policy = l2_evict_first_policy();
-      long long job = t_begin / P.tiles_per_slab;
-      int k = static_cast<int>(t_begin - job * P.tiles_per_slab);
-      int s = 0;
-      uint32_t ph = 0;
-      for (long long g = t_begin; g < t_end; ++g) {
-        const float* pa = reinterpret_cast<const float*>(__ldg(P.pred + job));
-        const float* ta = reinterpret_cast<const float*>(__ldg(P.target + job));
-        const int e0 = k * P.tile;
-        const int len = min(P.tile, P.slab - e0);
-        mbar_wait(&empty[s], ph ^ 1u);
-        StageMeta mt;
-        mt.cell = __ldg(P.cell + job);
-        mt.len = len;
-        mt.e0 = e0;
-        mt.pad = 0;
-        mt.wo = P.w_outer ? __ldg(P.w_outer + job) : 1.0;
-        meta[s] = mt;
-        unsigned char* st = ring + (size_t)s * stage_bytes;
-        const uint32_t fbytes = static_cast<uint32_t>(len) * 4u;
-        mbar_expect_tx(&full[s], fbytes * (CLIM ? 3u : 2u) +
-                                     static_cast<uint32_t>(len) * (MASK ? 2u : 1u));
-        bulk_g2s(st, pa + e0, fbytes, &full[s], policy);
-        bulk_g2s(st + off_t, ta + e0, fbytes, &full[s], policy);
-        if constexpr (CLIM)
-          bulk_g2s(st + off_c,
-                   reinterpret_cast<const float*>(__ldg(P.clim + job)) + e0,
-                   fbytes, &full[s], policy);
-        if constexpr (MASK)
-          bulk_g2s(st + off_m,
-                   reinterpret_cast<const unsigned char*>(__ldg(P.mask + job)) + e0,
-                   static_cast<uint32_t>(len), &full[s], policy);
-        bulk_g2s(st + off_k, B.class_map + e0, static_cast<uint32_t>(len),
-                 &full[s], policy);
-        if (++k == P.tiles_per_slab) {
-          k = 0;
-          ++job;
-        }
-        if (++s == stages) {
-          s = 0;
-          ph ^= 1u;
-        }
-      }
-    }
-    return;
-  }
-
-  double* wacc = wacc_all + static_cast<size_t>(warp) * nacc;
-  for (int i = lane; i < nacc; i += 32) wacc[i] = 0.0;
-  __syncwarp();
-  int cur_cell = -1;
-  const unsigned unx = static_cast<unsigned>(P.nx);
-  int s = 0;
-  uint32_t ph = 0;
-  auto flush = [&](int cell) {
-    double* rec = P.records +
-                  ((static_cast<size_t>(blockIdx.x) + (cell - P.cell_base)) *
-                       kConsumerWarps + warp) * nacc;
-    __syncwarp();
-    for (int i = lane; i < nacc; i += 32) {
-      rec[i] = wacc[i];
-      wacc[i] = 0.0;
-    }
-    __syncwarp();
-  };
-  for (long long g = t_begin; g < t_end; ++g) {
-    mbar_wait(&full[s], ph);
-    const StageMeta mt = meta[s];
-    if (mt.cell != cur_cell) {
-      if (cur_cell >= 0) flush(cur_cell);
-      cur_cell = mt.cell;
-    }
-    const unsigned char* st = ring + (size_t)s * stage_bytes;
-    const float4* sp = reinterpret_cast<const float4*>(st);
-    const float4* stt = reinterpret_cast<const float4*>(st + off_t);
-    const float4* sc = reinterpret_cast<const float4*>(st + off_c);
-    const uchar4* sm = reinterpret_cast<const uchar4*>(st + off_m);
-    const uchar4* sk = reinterpret_cast<const uchar4*>(st + off_k);
-    const int nvec = mt.len >> 2;
-    for (int jb = warp * 32; jb < nvec; jb += kConsumerThreads) {
-      const int j = jb + lane;
-      const bool active = j < nvec;
-      float val[4][NS];
-      float ok[4] = {1.f, 1.f, 1.f, 1.f};
-      unsigned char cls[4] = {0, 0, 0, 0};
-      double wrow = 0.0;
-      double wel[4] = {0.0, 0.0, 0.0, 0.0};  // WX: weight of every element
-      unsigned y = 0;
-      if (active) {
-        const float4 pv = sp[j];
-        const float4 tv = stt[j];
-        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (CLIM) cv = sc[j];
-        const uchar4 kv = sk[j];
-        cls[0] = kv.x; cls[1] = kv.y; cls[2] = kv.z; cls[3] = kv.w;
-        uchar4 mv = make_uchar4(1, 1, 1, 1);
-        if constexpr (MASK) mv = sm[j];
-        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
-        const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
-        const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
-        const unsigned char mm[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          PointStats<CLIM, MASK, false> q;
-          q.eval(pp[i], tt[i], cc[i], mm[i]);
-#pragma unroll
-          for (int k = 0; k < NS; ++k) val[i][k] = q.s[k];
-          if constexpr (MASK) ok[i] = q.valid[0];
-        }
-        const unsigned e = static_cast<unsigned>(mt.e0 + 4 * j);
-        y = e / unx;
-        wrow = mt.wo * (P.w_y ? __ldg(P.w_y + y) : 1.0);
-        if constexpr (WX) {
-          unsigned xi = e - y * unx, yi = y;
-          double wr = wrow;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            wel[i] = P.w_x ? wr * __ldg(P.w_x + xi) : wr;
-            if (++xi == unx) {
-              xi = 0;
-              ++yi;
-              wr = mt.wo * (P.w_y ? __ldg(P.w_y + yi) : 1.0);
-            }
-          }
-        }
-      }
-      const bool uniform = active && cls[0] == cls[1] && cls[1] == cls[2] &&
-                           cls[2] == cls[3];
-      const int key = WX ? static_cast<int>(cls[0])
-                         : static_cast<int>((y << 8) | cls[0]);
-      // ---- uniform lanes: one warp reduction per distinct (row, class) -----
-      unsigned um = __ballot_sync(0xffffffffu, uniform);
-      while (um) {
-        const int leader = __ffs(um) - 1;
-        const int lkey = __shfl_sync(0xffffffffu, key, leader);
-        const double lw = __shfl_sync(0xffffffffu, wrow, leader);
-        const bool mine = uniform && key == lkey;
-        double* slot = wacc + (lkey & 0xff) * B.n_sel;
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-          if (P.stat_mask & (1 << k)) {  // warp-uniform
-            if constexpr (WX) {
-              double v = 0.0;
-              if (mine) {
-                v = static_cast<double>(val[3][k]) * wel[3];
-                v = fma(static_cast<double>(val[2][k]), wel[2], v);
-                v = fma(static_cast<double>(val[1][k]), wel[1], v);
-                v = fma(static_cast<double>(val[0][k]), wel[0], v);
-              }
-              const double tot = warp_sum(v);
-              if (lane == 0)
-                slot[__popc(P.stat_mask & ((1 << k) - 1))] += tot;
-            } else {
-              const float v = mine ? (val[0][k] + val[1][k]) +
-                                         (val[2][k] + val[3][k])
-                                   : 0.f;
-              const float tot = warp_sum_f32(v);
-              if (lane == 0)
-                slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
-                    static_cast<double>(tot) * lw;
-            }
-          }
-        }
-        if constexpr (MASK) {
-          if constexpr (WX) {
-            double v = 0.0;
-            if (mine) {
-              v = static_cast<double>(ok[3]) * wel[3];
-              v = fma(static_cast<double>(ok[2]), wel[2], v);
-              v = fma(static_cast<double>(ok[1]), wel[1], v);
-              v = fma(static_cast<double>(ok[0]), wel[0], v);
-            }
-            const double tot = warp_sum(v);
-            if (lane == 0) slot[B.n_sel - 1] += tot;
-          } else {
-            const float v = mine ? (ok[0] + ok[1]) + (ok[2] + ok[3]) : 0.f;
-            const float tot = warp_sum_f32(v);
-            if (lane == 0) slot[B.n_sel - 1] += static_cast<double>(tot) * lw;
-          }
-        }
-        um &= ~__ballot_sync(0xffffffffu, mine);
-      }
-      // ---- mixed lanes (a class boundary inside their four points): each
-      // owner folds its own points, one lane after the other (fixed order).
-      unsigned mm_ = __ballot_sync(0xffffffffu, active && !uniform);
-      __syncwarp();
-      while (mm_) {
-        const int src = __ffs(mm_) - 1;
-        if (lane == src) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            double* slot = wacc + cls[i] * B.n_sel;
-            const double wi = WX ? wel[i] : wrow;
-#pragma unroll
-            for (int k = 0; k < NS; ++k)
-              if (P.stat_mask & (1 << k))
-                slot[__popc(P.stat_mask & ((1 << k) - 1))] +=
-                    static_cast<double>(val[i][k]) * wi;
-            if constexpr (MASK)
-              slot[B.n_sel - 1] += static_cast<double>(ok[i]) * wi;
-          }
-        }
-        __syncwarp();
-        mm_ &= mm_ - 1;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-    if (++s == stages) {
-      s = 0;
-      ph ^= 1u;
-    }
-  }
-  if (cur_cell >= 0) flush(cur_cell);
-}
-
-// records -> out[(cell * n_classes + c)][slot]; one warp per (cell, class, q).
-struct BinFinalizeParams {
-  const double* records;
-  const int32_t* cell_first_job;
-  const double* cell_class_w;   // [n_cells * n_classes] constant weights or NULL
-  double* out_ws;               // [n_cells * n_classes * 6]
-  double* out_w;                // [n_cells * n_classes * 4]
-  long long total_tiles;
-  int n_cells, grid_main, tiles_per_slab, n_classes, n_sel, accumulate;
-  int sel[WBX_NUM_DET_STATS + 2];
-};
-
-__global__ void __launch_bounds__(128) det_bins_finalize_kernel(
-    const BinFinalizeParams F) {
-  const long long warp_global =
-      (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long per_cell = static_cast<long long>(F.n_classes) * (F.n_sel + 1);
-  if (warp_global >= F.n_cells * per_cell) return;
-  const int c = static_cast<int>(warp_global / per_cell);
-  const int rem = static_cast<int>(warp_global - c * per_cell);
-  const int cls = rem / (F.n_sel + 1);
-  const int q = rem - cls * (F.n_sel + 1);   // q == n_sel: constant weights
-  const size_t oc = static_cast<size_t>(c) * F.n_classes + cls;
-  if (q == F.n_sel) {
-    if (F.cell_class_w && lane == 0) {
-      const double v = F.cell_class_w[oc];
-      for (int k = 0; k < WBX_NUM_DET_WCLASSES; ++k) {
-        double* dst = F.out_w + oc * WBX_NUM_DET_WCLASSES + k;
-        *dst = F.accumulate ? (*dst + v) : v;
-      }
-    }
-    return;
-  }
-  const int nacc = F.n_classes * F.n_sel;
-  const long long ft =
-      static_cast<long long>(F.cell_first_job[c]) * F.tiles_per_slab;
-  const long long lt =
-      static_cast<long long>(F.cell_first_job[c + 1]) * F.tiles_per_slab - 1;
-  const long long G = F.grid_main;
-  const int b_lo = static_cast<int>(((ft + 1) * G - 1) / F.total_tiles);
-  const int b_hi = static_cast<int>(((lt + 1) * G - 1) / F.total_tiles);
-  const int n = (b_hi - b_lo + 1) * kConsumerWarps;
-  const double* rec = F.records +
-                      (static_cast<size_t>(b_lo) + c) * kConsumerWarps * nacc +
-                      static_cast<size_t>(cls) * F.n_sel + q;
-  double sum = 0.0;
-  for (int i = lane; i < n; i += 32) sum += __ldcg(rec + static_cast<size_t>(i) * nacc);
-  sum = warp_sum(sum);
-  if (lane == 0) {
-    const int sidx = F.sel[q];
-    if (sidx >= 0) {
-      double* dst = F.out_ws + oc * WBX_NUM_DET_STATS + sidx;
-      *dst = F.accumulate ? (*dst + sum) : sum;
-    } else {
-      for (int k = 0; k < WBX_NUM_DET_WCLASSES; ++k) {
-        double* dst = F.out_w + oc * WBX_NUM_DET_WCLASSES + k;
-        *dst = F.accumulate ? (*dst + sum) : sum;
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // Deterministic second pass: sum the records of each cell in CTA/warp order.
 // ---------------------------------------------------------------------------
 struct FinalizeParams {

@@ -148,6 +148,25 @@ def _same_layout_everywhere(digest: str, n_values: int, group, backend,
   return all(probe[i] == -probe[k + i] for i in range(k))
 
 
+def device_for_local_rank(local_rank: int, local_world: int,
+                          visible: int | None = None) -> int:
+  """CUDA device index for rank `local_rank` of `local_world` ranks on a node.
+
+  With fewer ranks than visible GPUs the ranks are spread evenly over the
+  device indices (rank r -> r * (visible // local_world)).  Evaluation is fed
+  from host memory, so the placement that matters is the PCIe one, not NVLink:
+  on the 8 x B200 boxes of this pool the GPUs 0-3 and 4-7 each share one host
+  uplink (measured, profiles/h2d_ceiling_r2_box8_n8.json: four neighbouring
+  GPUs copy 115 GB/s together, GPUs 0,2,4,6 copy 213 GB/s), and spreading the
+  ranks puts as few of them as possible behind the same uplink."""
+  if visible is None:
+    import torch  # pylint: disable=g-import-not-at-top
+    visible = torch.cuda.device_count()
+  if local_world <= 0 or visible < 2 * local_world:
+    return local_rank % max(visible, 1)
+  return local_rank * (visible // local_world)
+
+
 def all_reduce_state(state: aggregation.AggregationState, group=None,
                      device=None) -> aggregation.AggregationState:
   """Sum of the AggregationStates of all ranks (every rank gets the result).
