@@ -251,10 +251,11 @@ int wbx_det_plan_kernel(wbx_ctx* ctx, const wbx_det_plan* plan,
  *   desc [S * 512 * 2] two words per consumer thread, layout [part][thread]:
  *        a = [9:0] first quad of the part | [19:10] second quad | [23:20]
  *        element selection of the first | [27:24] of the second (0: unused);
- *        b = [1:0] first 8-lane group of the thread's segment | [2] the
- *        thread's group closes the segment | [15:3] segment of the part;
+ *        b = [4:0] first lane of the thread's segment | [5] closes the
+ *        segment | [6] warp with lane-granular segments | [19:7] segment of
+ *        the part;
  *   seg_base [S + 1]; class_ptr [n_classes + 1]; class_segs [<= S * 64].
- * WBX_ERR_UNSUPPORTED when a part would need more than 1024 slots. */
+ * WBX_ERR_UNSUPPORTED when a part would need more than 512 threads. */
 int wbx_bins_schedule_tables(const unsigned char* class_map, int32_t n_classes,
                              int64_t ny, int64_t nx, int32_t part,
                              uint32_t* desc, int32_t* seg_base,

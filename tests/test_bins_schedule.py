@@ -51,7 +51,7 @@ def _replay(tab, values, weights, part, per_element):
     b = tab['desc'][s, :, 1].astype(np.int64)
     quad = np.stack([a & 0x3ff, (a >> 10) & 0x3ff], 1)  # [thread, slot]
     sel = np.stack([(a >> 20) & 0xf, (a >> 24) & 0xf], 1)
-    first_group, closes, seg = b & 3, (b >> 2) & 1, b >> 3
+    first_lane, closes, misc, seg = b & 31, (b >> 5) & 1, (b >> 6) & 1, b >> 7
     assert (quad[sel != 0] * 4 + 3 < length).all()
     # slot value: selected elements of the quad (exact zeros elsewhere)
     idx = e_lo + 4 * quad[..., None] + np.arange(4)
@@ -64,24 +64,42 @@ def _replay(tab, values, weights, part, per_element):
     else:   # the weight of the quad's first element serves the whole quad
       slot = v.sum(-1) * weights[idx[..., 0]]
     acc = slot.sum(-1).reshape(THREADS // 32, 32)       # the thread's two slots
-    # butterfly over the 8 lanes of a group, then the scan over the groups
+    first_lane = first_lane.reshape(-1, 32)
+    closes = closes.reshape(-1, 32)
+    misc = misc.reshape(-1, 32)
+    seg = seg.reshape(-1, 32)
+    assert (misc == misc[:, :1]).all()                  # warp-uniform
+    lane_id = np.arange(32)
+    # warps with lane-granular segments: segmented inclusive scan
+    scan = acc.copy()
+    delta = 1
+    while delta < 32:
+      up = np.zeros_like(scan)
+      up[:, delta:] = scan[:, :-delta]
+      scan = scan + np.where(lane_id - delta >= first_lane, up, 0.0)
+      delta *= 2
+    # other warps: butterfly over the 8 lanes of a group, scan over the groups
+    regular = misc[:, 0] == 0
+    used = (sel != 0).any(-1).reshape(-1, 32)
+    assert (first_lane[regular][used[regular]] % 8 == 0).all()
     group_sum = acc.reshape(-1, 4, 8).sum(-1)           # [warp, group]
-    head = first_group.reshape(-1, 4, 8)
-    assert (head == head[..., :1]).all()                # group-uniform
-    head = head[..., 0]
+    head = first_lane.reshape(-1, 4, 8)[..., 0] >> 3
     g = np.arange(4)
     v1 = group_sum.copy()
     v1[:, 1:] += np.where(g[1:] - 1 >= head[:, 1:], group_sum[:, :-1], 0.0)
     v2 = v1.copy()
     v2[:, 2:] += np.where(g[2:] - 2 >= head[:, 2:], v1[:, :-2], 0.0)
-    # every lane of the closing group carries the flag; the kernel lets the
-    # lanes holding a wanted column write (here: one value per group)
-    closing = closes.reshape(-1, 4, 8) == 1
-    assert (closing == closing[..., :1]).all()          # group-uniform
-    closing = closing[..., 0]
-    rec = tab['seg_base'][s] + seg.reshape(-1, 4, 8)[..., 0][closing]
+    by_group = np.repeat(v2, 8, axis=1)
+    # (a regular warp flags every lane of the closing group: each stores one
+    # accumulator; one of them stands for the segment here)
+    reg_close = closes.reshape(-1, 4, 8)
+    assert (reg_close[regular] == reg_close[regular][..., :1]).all()
+    assert not closes[~used].any()                      # unused lanes close nothing
+    lane_val = np.where(misc == 1, scan, by_group)
+    closing = (closes == 1) & ((misc == 1) | (lane_id % 8 == 7))
+    rec = tab['seg_base'][s] + seg[closing]
     assert rec.max(initial=-1) < tab['seg_base'][s + 1]
-    np.add.at(seg_sums, rec, v2[closing])
+    np.add.at(seg_sums, rec, lane_val[closing])
     np.add.at(seg_written, rec, 1)
     # the two slots of a thread, and the groups of a segment, share a class
   assert (covered == 1).all()         # every element is in exactly one slot

@@ -156,7 +156,9 @@ def test_bins3_matches_numpy(case, space):
                               w_o, w_y, w_x, stat_mask & (0x3f if clim else 7))
   scale = np.abs(ws_ref).max(axis=0, keepdims=True) + 1e-30
   np.testing.assert_allclose(ws / scale, ws_ref / scale, rtol=0, atol=2e-6)
-  np.testing.assert_allclose(sw, sw_ref, rtol=1e-10)
+  # element weights (w_x / odd rows) are rounded to float32 inside the kernel
+  per_element = wx or nx % 4 != 0
+  np.testing.assert_allclose(sw, sw_ref, rtol=1e-7 if per_element else 1e-10)
 
 
 def test_bins3_nan_stays_in_its_class():

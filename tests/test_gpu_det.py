@@ -810,7 +810,9 @@ def test_fused_bins_lon_major(space, masked, nlat, monkeypatch):
     got_w = state.sum_weights[name]['z'].transpose(*odims).values
     np.testing.assert_allclose(got_ws, sws, rtol=RTOL,
                                atol=1e-6 * np.abs(sws).max())
-    np.testing.assert_allclose(got_w, sw, rtol=1e-10)
+    # element weights are float32 inside the binned kernel: the masked sum of
+    # weights carries their rounding (~3e-8), the constant one is exact
+    np.testing.assert_allclose(got_w, sw, rtol=1e-7 if masked else 1e-10)
 
 
 def test_latitude_and_longitude_band_bins(monkeypatch):

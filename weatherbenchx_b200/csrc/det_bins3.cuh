@@ -14,18 +14,23 @@
 // every job of job group g through the TMA ring.  For every part the host
 // lists the part's SLOTS -- (quad of 4 contiguous elements, class, 4-bit
 // element selection): one slot per quad whose elements share a class, one per
-// class for the few quads a boundary runs through -- sorts them by class, pads
-// every class to a multiple of 16 slots and deals blocks of 16 out to groups
-// of 8 consumer threads: a thread owns slots u and u + 8 of its block, so
+// class for the few quads a boundary runs through -- and sorts them by class.
+// Whole blocks of 16 slots of a class go to groups of 8 consecutive consumer
+// threads: a thread owns slots u and u + 8 of its block, so
 //   * its two slots always belong to the same class (one accumulator set),
 //   * the 8 lanes of a group read 8 neighbouring quads (in the usual case of
 //     a run of whole quads: 128 contiguous bytes, no bank conflicts),
 //   * the 4 groups of a warp hold at most 4 class runs, the SEGMENTS.
+// What is left of every class (< 16 slots) follows, two slots per thread, in
+// the lanes after the last block: there a segment is any run of lanes, and
+// the warps that hold such lanes ("misc" warps, one or two per part) reduce
+// with a general segmented scan.  Nothing is padded, so a part of ~3500
+// elements fills the 512 threads whatever the number of classes in it.
 //
 // The kernel is therefore the unbinned one plus static per-thread data:
 //   * a thread reads the same two quads for all jobs; weights (one f64 row
-//     weight per quad, or f64 element weights for longitude-major arrays /
-//     odd row lengths) and selections live in registers;
+//     weight per quad, or element weights for longitude-major arrays / odd
+//     row lengths) and selections live in registers;
 //   * per job: f32 statistics, f32 4-sums, one f64 FMA per statistic and quad
 //     into the thread's accumulators -- no class logic, no branches that depend
 //     on data or on the map (one warp-uniform static branch picks the code with
@@ -52,18 +57,21 @@ constexpr int kBins3Slots = 2 * kConsumerThreads;  // per part
 // Slot descriptor of a consumer thread, two words.
 //   a: [9:0] first quad | [19:10] second quad | [23:20] selection of the
 //      first | [27:24] selection of the second (0: slot unused)
-//   b: [1:0] first group of the thread's segment | [2] the thread's group
-//      closes the segment | [15:3] segment of the part
+//   b: [4:0] first lane of the thread's segment | [5] closes the segment (in
+//      a misc warp: the last lane of the segment; elsewhere: every lane of
+//      its last group) | [6] misc warp | [19:7] segment of the part
 __host__ __device__ __forceinline__ uint32_t bins3_pack_a(int quad0, int quad1,
                                                           int sel0, int sel1) {
   return static_cast<uint32_t>(quad0) | (static_cast<uint32_t>(quad1) << 10) |
          (static_cast<uint32_t>(sel0) << 20) |
          (static_cast<uint32_t>(sel1) << 24);
 }
-__host__ __device__ __forceinline__ uint32_t bins3_pack_b(int first_group,
-                                                          int closes, int seg) {
-  return static_cast<uint32_t>(first_group) |
-         (static_cast<uint32_t>(closes) << 2) | (static_cast<uint32_t>(seg) << 3);
+__host__ __device__ __forceinline__ uint32_t bins3_pack_b(int first_lane,
+                                                          int closes, int misc,
+                                                          int seg) {
+  return static_cast<uint32_t>(first_lane) |
+         (static_cast<uint32_t>(closes) << 5) |
+         (static_cast<uint32_t>(misc) << 6) | (static_cast<uint32_t>(seg) << 7);
 }
 
 struct Bins3Params {
@@ -78,6 +86,107 @@ struct Bins3Params {
   double* records;            // [n_cells + J][total_segs][n_cols]
 };
 
+// Sums of the segments of a warp -> their records, accumulators reset.
+//
+// Warps whose segments are runs of whole 8-lane groups: all accumulators are
+// reduced together.  In step m of the butterfly over the 8 lanes of a group a
+// lane keeps one half of its columns (the half bit m of its lane number
+// names), sends the other half to its partner and adds what it receives, so
+// after log2(NC) steps lane l holds column l % NC summed over those steps'
+// partners -- NC - 1 shuffles instead of NC * log2(NC); the remaining steps
+// (rest of the group, then the groups of the segment) work on that one value.
+// Unselected statistics ride along (their sums are never stored).  `rec` is
+// the record of the segment the lane's group closes, or NULL.
+template <int NS, int NA>
+__device__ __forceinline__ void bins3_flush_groups(double (&acc)[NA],
+                                                   double* rec,
+                                                   const int stat_mask,
+                                                   const int lane,
+                                                   const int seg_first_lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int NC = NA <= 4 ? 4 : 8;
+  double v[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) v[k] = k < NA ? acc[k] : 0.0;
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+  // columns 2j, 2j + 1 -> j: lanes with bit m clear keep the even one
+  {
+    const bool odd = (lane & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < NC / 2; ++j) {
+      const double keep = odd ? v[2 * j + 1] : v[2 * j];
+      const double send = odd ? v[2 * j] : v[2 * j + 1];
+      v[j] = keep + __shfl_xor_sync(kFull, send, 1);
+    }
+  }
+  {
+    const bool odd = (lane & 2) != 0;
+#pragma unroll
+    for (int j = 0; j < NC / 4; ++j) {
+      const double keep = odd ? v[2 * j + 1] : v[2 * j];
+      const double send = odd ? v[2 * j] : v[2 * j + 1];
+      v[j] = keep + __shfl_xor_sync(kFull, send, 2);
+    }
+  }
+  if constexpr (NC == 8) {
+    const bool odd = (lane & 4) != 0;
+    const double keep = odd ? v[1] : v[0];
+    const double send = odd ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(kFull, send, 4);
+  } else {
+    v[0] += __shfl_xor_sync(kFull, v[0], 4);
+  }
+  // the groups of a segment: inclusive scan from its first group
+  const int group = lane >> 3, first_group = seg_first_lane >> 3;
+  const double up8 = __shfl_up_sync(kFull, v[0], 8);
+  if (group - 1 >= first_group) v[0] += up8;
+  const double up16 = __shfl_up_sync(kFull, v[0], 16);
+  if (group - 2 >= first_group) v[0] += up16;
+  // lane l of the closing group holds column l % NC (step m picked bit m of
+  // the column number)
+  const int k = lane & (NC - 1);
+  const bool wanted = k < NA && (k >= NS || ((stat_mask >> k) & 1));
+  if (rec != nullptr && (lane & 7) < NC && wanted) {
+    const int col = __popc(stat_mask & ((1 << (k < NS ? k : NS)) - 1));
+    rec[col] = v[0];
+  }
+}
+
+// Warps that hold the remainders of classes: segments are arbitrary runs of
+// lanes.  One segmented inclusive scan per accumulator, all issued step by
+// step; `rec` is the record of the segment the lane closes, or NULL.
+template <int NS, int NA>
+__device__ __forceinline__ void bins3_flush_lanes(double (&acc)[NA], double* rec,
+                                                  const int stat_mask,
+                                                  const int lane,
+                                                  const int seg_first_lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  double v[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) {
+    v[k] = acc[k];
+    acc[k] = 0.0;
+  }
+#pragma unroll
+  for (int dlt = 1; dlt < 32; dlt <<= 1) {
+    const bool add = lane - dlt >= seg_first_lane;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      const double up = __shfl_up_sync(kFull, v[k], dlt);
+      v[k] += add ? up : 0.0;
+    }
+  }
+  if (rec != nullptr) {
+    int col = 0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+      if (k >= NS || ((stat_mask >> k) & 1)) rec[col++] = v[k];
+  }
+}
+
+// (17 warps: one SM sub-partition holds five of them, which caps the kernel at
+// 96 registers per thread)
 template <bool CLIM, bool MASK, bool WX>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     det_reduce_bins3_kernel(const DetParams P, const Bins3Params B,
@@ -175,7 +284,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   // ------------------- consumers ---------------------------------------------
   const int ctid = threadIdx.x;
   const int stat_mask = P.stat_mask;
-  const int group = lane >> 3;
   double acc[NA];
 #pragma unroll
   for (int a = 0; a < NA; ++a) acc[a] = 0.0;
@@ -186,7 +294,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     // ---- the static schedule of this part -----------------------------------
     int quad[2];
     unsigned sel[2];
-    double wq[2][WX ? 4 : 1];   // row weight, or element weights
+    // weights: one f64 row weight per quad, or (WX) four f32 element weights
+    double wq[2];
+    float wf[2][WX ? 4 : 1];
     const int seg0 = __ldg(B.seg_base + s_part);
     const unsigned e_part = static_cast<unsigned>(s_part) * B.part;
     const unsigned unx = static_cast<unsigned>(P.nx);
@@ -196,25 +306,30 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     quad[1] = static_cast<int>((d.x >> 10) & 0x3ffu);
     sel[0] = (d.x >> 20) & 0xfu;
     sel[1] = (d.x >> 24) & 0xfu;
-    const int seg_first_group = static_cast<int>(d.y & 3u);
+    const int seg_first_lane = static_cast<int>(d.y & 31u);
     // record of the segment this lane closes (-1: it closes none)
-    const int seg_rec = (d.y & 4u) ? seg0 + static_cast<int>(d.y >> 3) : -1;
+    const int seg_rec = (d.y & 32u) ? seg0 + static_cast<int>(d.y >> 7) : -1;
+    const bool misc = (d.y & 64u) != 0u;   // warp-uniform
 #pragma unroll
     for (int ps = 0; ps < 2; ++ps) {
       const unsigned e = e_part + 4u * static_cast<unsigned>(quad[ps]);
       unsigned y = e / unx, x = e - y * unx;
       if constexpr (WX) {
 #pragma unroll
+        wq[ps] = 0.0;
+#pragma unroll
         for (int i = 0; i < 4; ++i) {
-          wq[ps][i] = (P.w_y ? __ldg(P.w_y + y) : 1.0) *
-                      (P.w_x ? __ldg(P.w_x + x) : 1.0);
+          const double w = (P.w_y ? __ldg(P.w_y + y) : 1.0) *
+                           (P.w_x ? __ldg(P.w_x + x) : 1.0);
+          wf[ps][i] = static_cast<float>(w);
           if (++x == unx) {
             x = 0;
             if (y + 1 < static_cast<unsigned>(P.ny)) ++y;
           }
         }
       } else {  // rows are a multiple of four long: a quad stays in its row
-        wq[ps][0] = P.w_y ? __ldg(P.w_y + y) : 1.0;
+        wq[ps] = P.w_y ? __ldg(P.w_y + y) : 1.0;
+        wf[ps][0] = 0.f;
       }
     }
     // warp-uniform, static: does the warp hold slots at all / boundary quads
@@ -222,58 +337,17 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     const bool partial = __any_sync(
         kFull, (sel[0] != 0u && sel[0] != 0xfu) || (sel[1] != 0u && sel[1] != 0xfu));
     const bool used0 = sel[0] != 0u, used1 = sel[1] != 0u;
-    const bool add8 = group - 1 >= seg_first_group;
-    const bool add16 = group - 2 >= seg_first_group;
 
-    // Sums of the segments of this warp -> their records, accumulators reset.
-    // All accumulators are reduced together: in step m of the butterfly over
-    // the 8 lanes of a group a lane keeps one half of its columns (the half
-    // bit m of its lane number names), sends the other half to its partner
-    // and adds what it receives, so after log2(NC) steps lane l holds column
-    // l % NC summed over those steps' partners -- NC - 1 shuffles instead of
-    // NC * log2(NC); the remaining steps (rest of the group, then the groups of
-    // the segment) work on that one value.  Unselected statistics ride along
-    // (their sums are never stored).
     auto flush = [&](const int cell) {
       if (!live) return;   // warp-uniform
-      constexpr int NC = NA <= 4 ? 4 : 8;
-      double v[NC];
-#pragma unroll
-      for (int k = 0; k < NC; ++k) v[k] = k < NA ? acc[k] : 0.0;
-#pragma unroll
-      for (int k = 0; k < NA; ++k) acc[k] = 0.0;
-      int width = NC;
-#pragma unroll
-      for (int m = 1; m < 8; m <<= 1) {
-        if (width > 1) {
-          // columns 2j, 2j + 1 -> j: lanes with bit m clear keep the even one
-          const bool odd = (lane & m) != 0;
-#pragma unroll
-          for (int j = 0; j < width / 2; ++j) {
-            const double keep = odd ? v[2 * j + 1] : v[2 * j];
-            const double send = odd ? v[2 * j] : v[2 * j + 1];
-            v[j] = keep + __shfl_xor_sync(kFull, send, m);
-          }
-          width /= 2;
-        } else {
-          v[0] += __shfl_xor_sync(kFull, v[0], m);
-        }
-      }
-      // the groups of a segment: inclusive scan from its first group
-      const double up8 = __shfl_up_sync(kFull, v[0], 8);
-      if (add8) v[0] += up8;
-      const double up16 = __shfl_up_sync(kFull, v[0], 16);
-      if (add16) v[0] += up16;
-      // lane l of the closing group holds column l % NC (step m picked bit m
-      // of the column number)
-      const int k = lane & (NC - 1);
-      const bool wanted = k < NA && (k >= NS || ((stat_mask >> k) & 1));
-      if (seg_rec >= 0 && (lane & 7) < NC && wanted) {
-        const int col = __popc(stat_mask & ((1 << (k < NS ? k : NS)) - 1) &
-                               ((1 << NS) - 1));
-        B.records[(static_cast<size_t>(cell - P.cell_base + grp) *
-                       B.total_segs + seg_rec) * B.n_cols + col] = v[0];
-      }
+      double* rec = nullptr;
+      if (seg_rec >= 0)
+        rec = B.records + (static_cast<size_t>(cell - P.cell_base + grp) *
+                               B.total_segs + seg_rec) * B.n_cols;
+      if (misc)   // warp-uniform
+        bins3_flush_lanes<NS, NA>(acc, rec, stat_mask, lane, seg_first_lane);
+      else
+        bins3_flush_groups<NS, NA>(acc, rec, stat_mask, lane, seg_first_lane);
     };
 
     int cur_cell = -1;
@@ -326,45 +400,52 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
               q[i].valid[0] = mine ? q[i].valid[0] : 0.f;
             }
           }
-          // an unused slot (padding of a class to 16 slots) adds exact zeros
+          // an unused slot (the odd one of a class remainder) adds exact zeros
           const bool used = ps == 0 ? used0 : used1;
+          const unsigned keep = used ? 0xffffffffu : 0u;
           if constexpr (!WX) {
-            const double wj = wq[ps][0] * mt.wo;
+            const double wj = wq[ps] * mt.wo;
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
               if (stat_mask & (1 << k)) {   // warp-uniform
-                float s4 = __fadd_rn(__fadd_rn(q[0].s[k], q[1].s[k]),
-                                     __fadd_rn(q[2].s[k], q[3].s[k]));
-                s4 = used ? s4 : 0.f;
-                acc[k] = fma(static_cast<double>(s4), wj, acc[k]);
+                const float s4 = __fadd_rn(__fadd_rn(q[0].s[k], q[1].s[k]),
+                                           __fadd_rn(q[2].s[k], q[3].s[k]));
+                acc[k] = fma(static_cast<double>(__uint_as_float(
+                                 __float_as_uint(s4) & keep)), wj, acc[k]);
               }
             }
             if constexpr (MASK) {
-              float n4 = (q[0].valid[0] + q[1].valid[0]) +
-                         (q[2].valid[0] + q[3].valid[0]);
-              n4 = used ? n4 : 0.f;
-              acc[NS] = fma(static_cast<double>(n4), wj, acc[NS]);
+              const float n4 = (q[0].valid[0] + q[1].valid[0]) +
+                               (q[2].valid[0] + q[3].valid[0]);
+              acc[NS] = fma(static_cast<double>(__uint_as_float(
+                                __float_as_uint(n4) & keep)), wj, acc[NS]);
             }
           } else {
-            // element weights: weighted 4-sum in f64, like the unbinned kernel
+            // element weights: the statistic values are f32 roundings, their
+            // weighted 4-sum is taken in f32 with the weights rounded to f32
+            // (one more rounding of the same size per term), then f64; the
+            // sum of weights of a masked aggregation goes the same way
+            // (relative error ~1e-8, against the 1e-5 of the parity bar)
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
               if (stat_mask & (1 << k)) {
-                double s4 = static_cast<double>(q[3].s[k]) * wq[ps][3];
-                s4 = fma(static_cast<double>(q[2].s[k]), wq[ps][2], s4);
-                s4 = fma(static_cast<double>(q[1].s[k]), wq[ps][1], s4);
-                s4 = fma(static_cast<double>(q[0].s[k]), wq[ps][0], s4);
-                s4 = used ? s4 : 0.0;
-                acc[k] = fma(s4, mt.wo, acc[k]);
+                const float s4 = __fadd_rn(
+                    __fadd_rn(__fmul_rn(q[0].s[k], wf[ps][0]),
+                              __fmul_rn(q[1].s[k], wf[ps][1])),
+                    __fadd_rn(__fmul_rn(q[2].s[k], wf[ps][2]),
+                              __fmul_rn(q[3].s[k], wf[ps][3])));
+                acc[k] = fma(static_cast<double>(__uint_as_float(
+                                 __float_as_uint(s4) & keep)), mt.wo, acc[k]);
               }
             }
             if constexpr (MASK) {
-              double n4 = static_cast<double>(q[3].valid[0]) * wq[ps][3];
-              n4 = fma(static_cast<double>(q[2].valid[0]), wq[ps][2], n4);
-              n4 = fma(static_cast<double>(q[1].valid[0]), wq[ps][1], n4);
-              n4 = fma(static_cast<double>(q[0].valid[0]), wq[ps][0], n4);
-              n4 = used ? n4 : 0.0;
-              acc[NS] = fma(n4, mt.wo, acc[NS]);
+              const float n4 = __fadd_rn(
+                  __fadd_rn(__fmul_rn(q[0].valid[0], wf[ps][0]),
+                            __fmul_rn(q[1].valid[0], wf[ps][1])),
+                  __fadd_rn(__fmul_rn(q[2].valid[0], wf[ps][2]),
+                            __fmul_rn(q[3].valid[0], wf[ps][3])));
+              acc[NS] = fma(static_cast<double>(__uint_as_float(
+                                __float_as_uint(n4) & keep)), mt.wo, acc[NS]);
             }
           }
         }

@@ -104,17 +104,21 @@ struct Bins3Host {
 };
 
 // Slots, segments and class lists for parts of `part` elements; false when a
-// part needs more than kBins3Slots slots (classes padded to 16 included).
+// part needs more than the 512 consumer threads.
+struct Bins3Slot { int cls, quad, sel; };
+struct Bins3Thread { int cls; Bins3Slot a, b; };
+
 static bool bins3_schedule(const unsigned char* cmap, int n_classes,
                            long long slab, int part, Bins3Host* T) {
-  struct Slot { int cls, quad, sel; };
+  using Slot = Bins3Slot;
+  using Thread = Bins3Thread;
   const int S = static_cast<int>((slab + part - 1) / part);
   T->part = part;
   T->S = S;
   T->desc.assign(static_cast<size_t>(S) * kConsumerThreads * 2, 0u);
   T->seg_base.assign(S + 1, 0);
   std::vector<std::vector<int32_t>> segs_of(n_classes);
-  std::vector<Slot> slots, padded;
+  std::vector<Slot> slots, sorted;
   std::vector<int> count(n_classes + 1);
   int n_seg_total = 0;
   for (int s = 0; s < S; ++s) {
@@ -133,61 +137,82 @@ static bool bins3_schedule(const unsigned char* cmap, int n_classes,
         slots.push_back({c4[i], q, sel});
       }
     }
-    // counting sort by class (quads stay ascending inside a class), every
-    // class padded with unused slots to a multiple of 16
+    // counting sort by class (quads stay ascending inside a class)
     std::fill(count.begin(), count.end(), 0);
     for (const Slot& sl : slots) ++count[sl.cls + 1];
-    size_t n_padded = 0;
-    for (int c = 0; c < n_classes; ++c) n_padded += round_up(count[c + 1], 16);
-    if (n_padded > static_cast<size_t>(kBins3Slots)) return false;
     std::vector<int> start(n_classes + 1, 0);
-    for (int c = 0; c < n_classes; ++c)
-      start[c + 1] = start[c] + static_cast<int>(round_up(count[c + 1], 16));
-    padded.assign(n_padded, Slot{-1, 0, 0});
-    for (int c = 0; c < n_classes; ++c)
-      for (int u = start[c]; u < start[c + 1]; ++u) padded[u].cls = c;
-    std::vector<int> fill(start.begin(), start.end() - 1);
-    for (const Slot& sl : slots) padded[fill[sl.cls]++] = sl;
-    // block b of 16 slots -> threads 8 b .. 8 b + 7 (slots u and u + 8)
-    const int n_blocks = static_cast<int>(n_padded / 16);
+    for (int c = 0; c < n_classes; ++c) start[c + 1] = start[c] + count[c + 1];
+    sorted.resize(slots.size());
+    {
+      std::vector<int> fill(start.begin(), start.end() - 1);
+      for (const Slot& sl : slots) sorted[fill[sl.cls]++] = sl;
+    }
+    // threads: first the whole blocks of 16 slots of every class (8 threads,
+    // slots u and u + 8), then the remainders (two consecutive slots each)
+    std::vector<Thread> threads;
+    for (int c = 0; c < n_classes; ++c) {
+      const int n = start[c + 1] - start[c];
+      for (int blk = 0; blk < n / 16; ++blk) {
+        for (int l = 0; l < 8; ++l) {
+          Thread th;
+          th.cls = c;
+          th.a = sorted[start[c] + 16 * blk + l];
+          th.b = sorted[start[c] + 16 * blk + 8 + l];
+          threads.push_back(th);
+        }
+      }
+    }
+    const int n_regular = static_cast<int>(threads.size());
+    for (int c = 0; c < n_classes; ++c) {
+      const int n = start[c + 1] - start[c];
+      for (int u = n / 16 * 16; u < n; u += 2) {
+        Thread th;
+        th.cls = c;
+        th.a = sorted[start[c] + u];
+        th.b.cls = c;
+        th.b.quad = 0;
+        th.b.sel = 0;
+        if (u + 1 < n) th.b = sorted[start[c] + u + 1];
+        threads.push_back(th);
+      }
+    }
+    const int n_threads = static_cast<int>(threads.size());
+    if (n_threads > kConsumerThreads) return false;
     int seg_local = 0;
     T->seg_base[s] = n_seg_total;
     for (int t0 = 0; t0 < kConsumerThreads; t0 += 32) {
-      // one warp: four groups of 8 lanes, runs of groups of equal class
-      int g = 0;
-      while (g < 4) {
-        const int b0 = t0 / 8 + g;
-        if (b0 >= n_blocks) {   // unused group: sel 0, closes nothing
-          for (int l = 0; l < 8; ++l) {
-            const size_t at =
-                (static_cast<size_t>(s) * kConsumerThreads + t0 + 8 * g + l) * 2;
-            T->desc[at] = bins3_pack_a(0, 0, 0, 0);
-            T->desc[at + 1] = bins3_pack_b(g, 0, 0);
-          }
-          ++g;
+      // a warp that holds remainder lanes reduces at lane granularity
+      const bool misc = t0 + 32 > n_regular && t0 < n_threads;
+      int lane = 0;
+      while (lane < 32) {
+        const size_t at =
+            (static_cast<size_t>(s) * kConsumerThreads + t0 + lane) * 2;
+        if (t0 + lane >= n_threads) {   // unused lane: selects nothing
+          T->desc[at] = bins3_pack_a(0, 0, 0, 0);
+          T->desc[at + 1] = bins3_pack_b(lane, 0, misc, 0);
+          ++lane;
           continue;
         }
-        const int cls = padded[16 * b0].cls;
-        int g_end = g;
-        while (g_end + 1 < 4 && b0 + (g_end + 1 - g) < n_blocks &&
-               padded[16 * (b0 + (g_end + 1 - g))].cls == cls)
-          ++g_end;
+        // the segment: the run of lanes of this class in this warp
+        const int cls = threads[t0 + lane].cls;
+        int end = lane;
+        while (end + 1 < 32 && t0 + end + 1 < n_threads &&
+               threads[t0 + end + 1].cls == cls)
+          ++end;
         if (seg_local >= 8192) return false;
-        for (int gg = g; gg <= g_end; ++gg) {
-          const int b = b0 + (gg - g);
-          for (int l = 0; l < 8; ++l) {
-            const Slot& s0 = padded[16 * b + l];
-            const Slot& s1 = padded[16 * b + 8 + l];
-            const size_t at =
-                (static_cast<size_t>(s) * kConsumerThreads + t0 + 8 * gg + l) * 2;
-            T->desc[at] = bins3_pack_a(s0.quad, s1.quad, s0.sel, s1.sel);
-            T->desc[at + 1] =
-                bins3_pack_b(g, gg == g_end, seg_local);
-          }
+        for (int l = lane; l <= end; ++l) {
+          const Thread& th = threads[t0 + l];
+          const size_t al =
+              (static_cast<size_t>(s) * kConsumerThreads + t0 + l) * 2;
+          T->desc[al] = bins3_pack_a(th.a.quad, th.b.quad, th.a.sel, th.b.sel);
+          // regular warps: segments are runs of whole groups and every lane
+          // of the last group stores one accumulator
+          const bool closes = misc ? l == end : l >= (end & ~7);
+          T->desc[al + 1] = bins3_pack_b(lane, closes, misc, seg_local);
         }
         segs_of[cls].push_back(n_seg_total + seg_local);
         ++seg_local;
-        g = g_end + 1;
+        lane = end + 1;
       }
     }
     n_seg_total += seg_local;

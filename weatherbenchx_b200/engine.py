@@ -323,13 +323,14 @@ class BinClasses:
   digest: str
 
   def to_bins(self, per_class: np.ndarray) -> np.ndarray:
-    """[n_cells, n_classes] class sums -> [n_cells, bins_1, bins_2, ...].
+    """[n_cells, n_classes, ...] class sums -> [n_cells, bins_1, bins_2, ..., ...].
 
     NaN class sums poison every bin (0 * NaN), like the reference's einsum over
     bin masks does for NaNs outside the bin."""
     letters = 'bdefghij'
-    expr = 'ac,' + ','.join(f'{letters[k]}c' for k in range(len(self.membership)))
-    expr += '->a' + ''.join(letters[k] for k in range(len(self.membership)))
+    k = len(self.membership)
+    expr = 'ac...,' + ','.join(f'{letters[i]}c' for i in range(k))
+    expr += '->a' + letters[:k] + '...'
     return np.einsum(expr, per_class, *self.membership)
 
 
@@ -1017,16 +1018,15 @@ def split_fused_results(launch: FusedLaunch, ws: np.ndarray, w: np.ndarray
   return raw
 
 
-def label_fused_results(spec: FusedSpec, stats, ws: np.ndarray, w: np.ndarray
-                        ) -> dict:
-  """{kind: (sum_weighted_statistics, sum_weights)} as labelled host arrays
-  from the result rows of one planned aggregation (bin classes mapped to
-  bins, kept dims in the reference's order)."""
-  out = {}
-  cls, outer = spec.classes, spec.outer
+def _label_layout(spec: FusedSpec):
+  """What labelling the result rows of ``spec`` needs, built once per spec:
+  (dims as laid out, shape, validated coordinate dict, final dim order)."""
+  cached = getattr(spec, '_label_layout', None)
+  if cached is not None:
+    return cached
   out_dims, out_shape = list(spec.kept), list(spec.kept_shape)
   out_coords = dict(spec.coords)
-  for folded in (outer, cls):    # layout: kept, outer bins, slab bins
+  for folded in (spec.outer, spec.classes):  # layout: kept, outer bins, slab bins
     if folded is not None:
       out_dims += list(folded.bin_dims)
       out_shape += [m.shape[0] for m in folded.membership]
@@ -1035,26 +1035,50 @@ def label_fused_results(spec: FusedSpec, stats, ws: np.ndarray, w: np.ndarray
   # the reference's result has the bin dims in the order of bin_by
   final_dims = list(spec.kept_order or spec.kept) + [
       d for d in spec.bin_order if d in out_dims]
-  # the coordinates are validated once per spec; every result array shares them
+  # the coordinates are validated once; every result array shares them
   template = xl.DataArray(np.empty(out_shape, np.bool_), out_dims,
                           coords=out_coords)
-  out_dims_t = tuple(out_dims)
+  cached = (tuple(out_dims), tuple(out_shape), template._coords,  # pylint: disable=protected-access
+            None if final_dims == out_dims else tuple(final_dims))
+  try:
+    spec._label_layout = cached  # pylint: disable=protected-access
+  except AttributeError:
+    pass
+  return cached
+
+
+def label_fused_results(spec: FusedSpec, stats, ws: np.ndarray, w: np.ndarray
+                        ) -> dict:
+  """{kind: (sum_weighted_statistics, sum_weights)} as labelled host arrays
+  from the result rows of one planned aggregation (bin classes mapped to
+  bins, kept dims in the reference's order).  All columns go through the
+  class -> bin products together."""
+  cls, outer = spec.classes, spec.outer
+  out_dims, out_shape, coords, final_dims = _label_layout(spec)
+  columns = []
   for s in stats:
     if spec.xform:
       slot, wclass = _cabi.XF_SLOT[s.kind], 0
     else:
       slot = _cabi.STAT_SLOT[s.kind]
       wclass = _cabi.STAT_WCLASS[slot]
+    columns += [ws[:, slot], w[:, wclass]]
+  block = np.stack(columns, axis=-1)            # [rows, 2 * statistics]
+  if spec.scalar != 1.0:
+    block = block * spec.scalar
+  if cls is not None:
+    with np.errstate(invalid='ignore'):
+      block = cls.to_bins(block.reshape(spec.n_cells, cls.n_classes, -1))
+  if outer is not None:
+    block = outer.to_bins(block.reshape((spec.n_cells,) + block.shape[1:]))
+  block = block.reshape(out_shape + (len(columns),))
+  out = {}
+  for i, s in enumerate(stats):
     pair = []
-    for col in (ws[:, slot] * spec.scalar, w[:, wclass] * spec.scalar):
-      if cls is not None:
-        with np.errstate(invalid='ignore'):
-          col = cls.to_bins(col.reshape(spec.n_cells, cls.n_classes))
-      if outer is not None:
-        col = outer.to_bins(col.reshape((spec.n_cells,) + col.shape[1:]))
-      da = xl.DataArray._fast(col.reshape(out_shape), out_dims_t,  # pylint: disable=protected-access
-                              dict(template._coords), s.name)  # pylint: disable=protected-access
-      if final_dims != out_dims:
+    for col in (block[..., 2 * i], block[..., 2 * i + 1]):
+      da = xl.DataArray._fast(col.copy(), out_dims,  # pylint: disable=protected-access
+                              dict(coords), s.name)
+      if final_dims is not None:
         da = da.transpose(*final_dims)
       pair.append(da)
     out[s.kind] = tuple(pair)
