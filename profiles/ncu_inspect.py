@@ -1,5 +1,5 @@
 """Prints key raw metrics, stall mix and opcode mix of every kernel in an
-ncu report:  python profiles/inspect.py gpurun_out/x.ncu-rep"""
+ncu report:  python profiles/ncu_inspect.py gpurun_out/x.ncu-rep"""
 import collections, csv, io, subprocess, sys
 rep = sys.argv[1]
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
@@ -14,6 +14,10 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
         'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum']

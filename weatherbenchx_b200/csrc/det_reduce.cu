@@ -25,6 +25,7 @@ struct wbx_det_plan {
   std::vector<uint64_t> pred, target, clim, mask;
   std::vector<int32_t> cell;
   std::vector<double> wo, wy, wx;
+  std::vector<float> wxf;
   double sum_wy = 1.0, sum_wx = 1.0;
   int path = 0;
   int tile = 0, tiles_per_slab = 0, stages = 0, stage_bytes = 0;
@@ -40,6 +41,7 @@ struct wbx_det_plan {
   wbx::DevBuf weights;
   const double* d_wy = nullptr;
   const double* d_wx = nullptr;
+  const float* d_wxf = nullptr;
   std::vector<unsigned char> chunk_host[2];
   int stat_mask = 0x3f;
   // categorical transform (wbx_det_desc.xform): per-job thresholds
@@ -807,9 +809,11 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
   }
   // weights (shared by both spaces)
   {
-    // w_x starts on a 16-byte boundary (it is read with double2 loads)
+    // layout: w_y | w_x (f64) | w_x rounded to f32, every table 16-byte aligned
     const size_t wx_off = (p->wy.size() + 1) / 2 * 2;
-    const size_t bytes = (wx_off + p->wx.size()) * sizeof(double);
+    const size_t wxf_off = (wx_off + p->wx.size() + 1) / 2 * 2;
+    const size_t bytes = wxf_off * sizeof(double) +
+                         round_up(p->wx.size() * sizeof(float), 16);
     if (p->wy.size() + p->wx.size()) {
       int rc = p->weights.reserve(bytes);
       if (rc != WBX_OK) { delete p; return rc; }
@@ -825,6 +829,11 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
                                  p->wx.size() * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->stream));
         p->d_wx = base + wx_off;
+        p->wxf.assign(p->wx.begin(), p->wx.end());
+        WBX_CUDA(cudaMemcpyAsync(base + wxf_off, p->wxf.data(),
+                                 p->wxf.size() * sizeof(float),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        p->d_wxf = reinterpret_cast<const float*>(base + wxf_off);
       }
     }
   }
@@ -881,6 +890,7 @@ int wbx_det_plan_create(wbx_ctx* ctx, const wbx_det_desc* d,
     P.cell = reinterpret_cast<const int32_t*>(base + o_cell);
     P.w_y = p->d_wy;
     P.w_x = p->d_wx;
+    P.w_xf = p->d_wxf;
     P.n_jobs = p->n_jobs;
     P.total_tiles = p->n_jobs * p->tiles_per_slab;
     P.cell_base = 0;
@@ -1099,6 +1109,7 @@ static int run_host_space(wbx_ctx* ctx, wbx_det_plan* plan, double* d_ws,
     P.cell = reinterpret_cast<const int32_t*>(tbase + o_cell);
     P.w_y = plan->d_wy;
     P.w_x = plan->d_wx;
+    P.w_xf = plan->d_wxf;
     P.n_jobs = static_cast<long long>(nj);
     P.total_tiles = static_cast<long long>(nj) * plan->tiles_per_slab;
     P.cell_base = plan->cell[j0];

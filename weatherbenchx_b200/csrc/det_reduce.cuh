@@ -45,6 +45,7 @@ struct DetParams {
   const double* w_outer;
   const double* w_y;
   const double* w_x;
+  const float* w_xf;   // w_x rounded to f32 (16-byte aligned), or NULL
   long long n_jobs;
   long long total_tiles;
   int cell_base;
@@ -222,13 +223,18 @@ __device__ __forceinline__ void accum_row4(const float4 p, const float4 t,
 
 // Four consecutive points of one row whose weight varies along the row
 // (w_x: the latitude axis is the fastest one, as in the lon-major WeatherBench
-// archives): the four column weights come in as two 16-byte loads, the
-// weighted 4-sum is taken in f64 and folded with the row weight by one FMA.
+// archives).  The statistic values are f32 roundings; they are multiplied by
+// the column weights rounded to f32 (one 16-byte load, one more rounding of
+// the same size per term), summed in f32 like the row-uniform case and folded
+// with the f64 row weight by one FMA: one f32 -> f64 conversion per group and
+// statistic instead of four (the conversion is the slow instruction here, 8
+// cycles per warp on the XU pipe).
 template <bool CLIM, bool MASK, bool SKIPNA, bool ALIGNED, bool XF = false>
 __device__ __forceinline__ void accum_row4_wx(const float4 p, const float4 t,
                                               const float4 c, const uchar4 m,
                                               const double wrow,
-                                              const double* __restrict__ wx4,
+                                              const float* __restrict__ wx4,
+                                              const double* __restrict__ wx4d,
                                               const int stat_mask,
                                               double* acc,
                                               const XfArgs& xf = XfArgs()) {
@@ -238,31 +244,57 @@ __device__ __forceinline__ void accum_row4_wx(const float4 p, const float4 t,
   q1.eval(p.y, t.y, c.y, m.y, xf);
   q2.eval(p.z, t.z, c.z, m.z, xf);
   q3.eval(p.w, t.w, c.w, m.w, xf);
-  double2 wa, wb;
+  float4 wv;
   if constexpr (ALIGNED) {
-    wa = __ldg(reinterpret_cast<const double2*>(wx4));
-    wb = __ldg(reinterpret_cast<const double2*>(wx4) + 1);
+    wv = __ldg(reinterpret_cast<const float4*>(wx4));
   } else {  // odd row lengths: the group starts at any column
-    wa = make_double2(__ldg(wx4), __ldg(wx4 + 1));
-    wb = make_double2(__ldg(wx4 + 2), __ldg(wx4 + 3));
+    wv = make_float4(__ldg(wx4), __ldg(wx4 + 1), __ldg(wx4 + 2), __ldg(wx4 + 3));
   }
+  if constexpr (XF) {
+    // 0/1 indicator statistics: exact f64 weights keep "the table entries
+    // add up to the sum of weights" an identity
+    const double w4[4] = {__ldg(wx4d), __ldg(wx4d + 1), __ldg(wx4d + 2),
+                          __ldg(wx4d + 3)};
 #pragma unroll
-  for (int k = 0; k < L::kStats; ++k) {
-    if (stat_mask & (1 << k)) {  // warp-uniform
-      double s4 = static_cast<double>(q3.s[k]) * wb.y;
-      s4 = fma(static_cast<double>(q2.s[k]), wb.x, s4);
-      s4 = fma(static_cast<double>(q1.s[k]), wa.y, s4);
-      s4 = fma(static_cast<double>(q0.s[k]), wa.x, s4);
-      acc[k] = fma(s4, wrow, acc[k]);
+    for (int k = 0; k < L::kStats; ++k) {
+      if (stat_mask & (1 << k)) {  // warp-uniform
+        double s4 = static_cast<double>(q3.s[k]) * w4[3];
+        s4 = fma(static_cast<double>(q2.s[k]), w4[2], s4);
+        s4 = fma(static_cast<double>(q1.s[k]), w4[1], s4);
+        s4 = fma(static_cast<double>(q0.s[k]), w4[0], s4);
+        acc[k] = fma(s4, wrow, acc[k]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < L::kStats; ++k) {
+      if (stat_mask & (1 << k)) {  // warp-uniform
+        const float s4 = __fadd_rn(
+            __fadd_rn(__fmul_rn(q0.s[k], wv.x), __fmul_rn(q1.s[k], wv.y)),
+            __fadd_rn(__fmul_rn(q2.s[k], wv.z), __fmul_rn(q3.s[k], wv.w)));
+        acc[k] = fma(static_cast<double>(s4), wrow, acc[k]);
+      }
     }
   }
+  // the sums of weights of masked / skipna aggregations stay in f64 (they are
+  // the denominators; unmasked launches have none of these)
+  if constexpr (L::kWeights > 0) {
+    double2 wa, wb;
+    if constexpr (ALIGNED) {
+      wa = __ldg(reinterpret_cast<const double2*>(wx4d));
+      wb = __ldg(reinterpret_cast<const double2*>(wx4d) + 1);
+    } else {
+      wa = make_double2(__ldg(wx4d), __ldg(wx4d + 1));
+      wb = make_double2(__ldg(wx4d + 2), __ldg(wx4d + 3));
+    }
 #pragma unroll
-  for (int k = 0; k < L::kWeights; ++k) {
-    double n4 = static_cast<double>(q3.valid[k]) * wb.y;
-    n4 = fma(static_cast<double>(q2.valid[k]), wb.x, n4);
-    n4 = fma(static_cast<double>(q1.valid[k]), wa.y, n4);
-    n4 = fma(static_cast<double>(q0.valid[k]), wa.x, n4);
-    acc[L::kStats + k] = fma(n4, wrow, acc[L::kStats + k]);
+    for (int k = 0; k < L::kWeights; ++k) {
+      double n4 = static_cast<double>(q3.valid[k]) * wb.y;
+      n4 = fma(static_cast<double>(q2.valid[k]), wb.x, n4);
+      n4 = fma(static_cast<double>(q1.valid[k]), wa.y, n4);
+      n4 = fma(static_cast<double>(q0.valid[k]), wa.x, n4);
+      acc[L::kStats + k] = fma(n4, wrow, acc[L::kStats + k]);
+    }
   }
 }
 
@@ -286,8 +318,9 @@ __device__ __forceinline__ void accum_point(float p, float t, float c,
 struct WeightCursor {
   const double* wy;
   const double* wx;
+  const float* wxf;   // w_x in f32 (16-byte aligned table)
   int nx;
-  bool wx4_ok;  // w_x present, nx % 4 == 0, table 16-byte aligned
+  bool wx4_ok;  // w_x present, nx % 4 == 0 (both tables 16-byte aligned)
   __device__ __forceinline__ double row(unsigned y, double wo) const {
     return wy ? wo * __ldg(wy + y) : wo;
   }
@@ -312,13 +345,14 @@ __device__ __forceinline__ void accum_group4(const float4 p, const float4 t,
   } else if (wc.wx4_ok) {
     // rows are a multiple of four long: the group stays in its row
     accum_row4_wx<CLIM, MASK, SKIPNA, true, XF>(p, t, c, m, wc.row(y, wo),
-                                                wc.wx + x, stat_mask, acc, xf);
+                                                wc.wxf + x, wc.wx + x,
+                                                stat_mask, acc, xf);
   } else if (wc.wx != nullptr && x + 3u < static_cast<unsigned>(wc.nx)) {
     // odd row length (e.g. 721 latitudes): all but the groups that straddle
     // a row end still share one row weight
     accum_row4_wx<CLIM, MASK, SKIPNA, false, XF>(p, t, c, m, wc.row(y, wo),
-                                                 wc.wx + x, stat_mask, acc,
-                                                 xf);
+                                                 wc.wxf + x, wc.wx + x,
+                                                 stat_mask, acc, xf);
   } else {
     const float pp[4] = {p.x, p.y, p.z, p.w};
     const float tt[4] = {t.x, t.y, t.z, t.w};
@@ -453,10 +487,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   double acc[L::kAcc];
 #pragma unroll
   for (int a = 0; a < L::kAcc; ++a) acc[a] = 0.0;
-  const WeightCursor wc{
-      P.w_y, P.w_x, P.nx,
-      P.w_x != nullptr && (P.nx & 3) == 0 &&
-          (reinterpret_cast<uintptr_t>(P.w_x) & 15) == 0};
+  const WeightCursor wc{P.w_y, P.w_x, P.w_xf, P.nx,
+                        P.w_xf != nullptr && (P.nx & 3) == 0};
   int cur_cell = -1;
   const int ctid = threadIdx.x;  // 0 .. kConsumerThreads-1
   const unsigned unx = static_cast<unsigned>(P.nx);
@@ -554,10 +586,8 @@ __global__ void __launch_bounds__(kLdgThreads)
   double acc[L::kAcc];
 #pragma unroll
   for (int a = 0; a < L::kAcc; ++a) acc[a] = 0.0;
-  const WeightCursor wc{
-      P.w_y, P.w_x, P.nx,
-      P.w_x != nullptr && (P.nx & 3) == 0 &&
-          (reinterpret_cast<uintptr_t>(P.w_x) & 15) == 0};
+  const WeightCursor wc{P.w_y, P.w_x, P.w_xf, P.nx,
+                        P.w_xf != nullptr && (P.nx & 3) == 0};
   int cur_cell = -1;
   long long job = t_begin / P.tiles_per_slab;
   int k = static_cast<int>(t_begin - job * P.tiles_per_slab);

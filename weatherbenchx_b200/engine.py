@@ -327,11 +327,16 @@ class BinClasses:
 
     NaN class sums poison every bin (0 * NaN), like the reference's einsum over
     bin masks does for NaNs outside the bin."""
-    letters = 'bdefghij'
     k = len(self.membership)
-    expr = 'ac...,' + ','.join(f'{letters[i]}c' for i in range(k))
-    expr += '->a' + letters[:k] + '...'
-    return np.einsum(expr, per_class, *self.membership)
+    with np.errstate(invalid='ignore'):
+      if k == 1 and per_class.ndim == 3:
+        # [bins, classes] @ [cells, classes, columns]: one BLAS call per cell
+        # (0 * NaN = NaN survives the product like it does in einsum)
+        return np.matmul(self.membership[0], per_class)
+      letters = 'bdefghij'
+      expr = 'ac...,' + ','.join(f'{letters[i]}c' for i in range(k))
+      expr += '->a' + letters[:k] + '...'
+      return np.einsum(expr, per_class, *self.membership)
 
 
 _CLASS_CACHE: 'collections.OrderedDict' = collections.OrderedDict()
@@ -1047,41 +1052,48 @@ def _label_layout(spec: FusedSpec):
   return cached
 
 
-def label_fused_results(spec: FusedSpec, stats, ws: np.ndarray, w: np.ndarray
-                        ) -> dict:
+def label_fused_results(spec: FusedSpec, stats, ws: np.ndarray, w: np.ndarray,
+                        means: bool = False) -> dict:
   """{kind: (sum_weighted_statistics, sum_weights)} as labelled host arrays
   from the result rows of one planned aggregation (bin classes mapped to
   bins, kept dims in the reference's order).  All columns go through the
-  class -> bin products together."""
+  class -> bin products together.  ``means=True`` returns {kind: sum_ws /
+  sum_w} instead (what AggregationState.mean_statistics would form,
+  aggregation.py:112-131)."""
   cls, outer = spec.classes, spec.outer
   out_dims, out_shape, coords, final_dims = _label_layout(spec)
-  columns = []
+  slots, wclasses = [], []
   for s in stats:
     if spec.xform:
-      slot, wclass = _cabi.XF_SLOT[s.kind], 0
+      slots.append(_cabi.XF_SLOT[s.kind])
+      wclasses.append(0)
     else:
-      slot = _cabi.STAT_SLOT[s.kind]
-      wclass = _cabi.STAT_WCLASS[slot]
-    columns += [ws[:, slot], w[:, wclass]]
-  block = np.stack(columns, axis=-1)            # [rows, 2 * statistics]
+      slots.append(_cabi.STAT_SLOT[s.kind])
+      wclasses.append(_cabi.STAT_WCLASS[slots[-1]])
+  n = len(stats)
+  block = np.concatenate([ws[:, slots], w[:, wclasses]], axis=1)  # [rows, 2n]
   if spec.scalar != 1.0:
     block = block * spec.scalar
   if cls is not None:
-    with np.errstate(invalid='ignore'):
-      block = cls.to_bins(block.reshape(spec.n_cells, cls.n_classes, -1))
+    block = cls.to_bins(block.reshape(spec.n_cells, cls.n_classes, 2 * n))
   if outer is not None:
     block = outer.to_bins(block.reshape((spec.n_cells,) + block.shape[1:]))
-  block = block.reshape(out_shape + (len(columns),))
+  block = block.reshape(out_shape + (2 * n,))
+
+  def labelled(values, name):
+    da = xl.DataArray._fast(values, out_dims, dict(coords), name)  # pylint: disable=protected-access
+    return da if final_dims is None else da.transpose(*final_dims)
+
   out = {}
+  if means:
+    with np.errstate(invalid='ignore', divide='ignore'):
+      ratio = np.true_divide(block[..., :n], block[..., n:])
+    for i, s in enumerate(stats):
+      out[s.kind] = labelled(ratio[..., i].copy(), s.name)
+    return out
   for i, s in enumerate(stats):
-    pair = []
-    for col in (block[..., 2 * i], block[..., 2 * i + 1]):
-      da = xl.DataArray._fast(col.copy(), out_dims,  # pylint: disable=protected-access
-                              dict(coords), s.name)
-      if final_dims is not None:
-        da = da.transpose(*final_dims)
-      pair.append(da)
-    out[s.kind] = tuple(pair)
+    out[s.kind] = (labelled(block[..., i].copy(), s.name),
+                   labelled(block[..., n + i].copy(), s.name))
   return out
 
 

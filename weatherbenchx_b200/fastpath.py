@@ -107,6 +107,16 @@ def _torch():
   return torch
 
 
+def _raw_stream(torch, device: int) -> int:
+  """cudaStream_t of torch's current stream on ``device`` (the private C
+  getter is ~20x cheaper than building a torch.cuda.Stream object; the
+  public API is the fallback)."""
+  getter = getattr(torch._C, '_cuda_getCurrentRawStream', None)  # pylint: disable=protected-access
+  if getter is not None:
+    return int(getter(device))
+  return torch.cuda.current_stream(device).cuda_stream
+
+
 def _array_key(var, da, guards: list):
   da = xl.as_data_array(da)
   payload = da._data if not hasattr(da, 'is_lazy') else None  # pylint: disable=protected-access
@@ -141,7 +151,7 @@ def chunk_key(metrics, aggregator, predictions, targets):
                       for v, da in predictions.items())
     tgt_part = tuple(_array_key(v, da, guards) for v, da in targets.items())
     device = torch.cuda.current_device()
-    stream = torch.cuda.current_stream(device).cuda_stream
+    stream = _raw_stream(torch, device)
     key = (tuple(metric_part), agg_part, pred_part, tgt_part, device, stream,
            getattr(_cabi._lane, 'index', 0),  # pylint: disable=protected-access
            engine.CRPS_KERNEL, engine.XF_L2_BLOCK_BYTES)
@@ -228,7 +238,7 @@ class CompiledChunk:
     base = self._dev_out.data_ptr()
     self._launch_args = [(plan, base + 8 * ows, base + 8 * ow)
                          for plan, ows, ow in self.launches]
-    self._stream = torch.cuda.current_stream(self.device).cuda_stream
+    self._stream = _raw_stream(torch, self.ctx.device)
     self._slots: list = []
     self._slot_lock = threading.Lock()
 
@@ -303,10 +313,9 @@ class CompiledChunk:
           for _, _, leaf in leaves:
             if all(leaf.kind != s.kind for s in stats):
               stats.append(leaf)
-          labelled = engine.label_fused_results(spec, stats, ws, w)
+          labelled = engine.label_fused_results(spec, stats, ws, w, means=True)
           for stat_name, var, leaf in leaves:
-            sws, sw = labelled[leaf.kind]
-            means.setdefault(stat_name, {})[var] = sws / sw
+            means.setdefault(stat_name, {})[var] = labelled[leaf.kind]
     metrics = {name: ref() for name, ref in self._metrics.items()}
     values = metrics_base.compute_metrics_from_statistics(metrics, means)
     out = {}
