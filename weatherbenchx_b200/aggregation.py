@@ -629,6 +629,9 @@ def compute_metric_values_for_single_chunk(
   (fastpath.py), so the host work of chunk i overlaps the kernels of chunk
   i + 1.
   """
+  compiled = fastpath.quick_lookup(metrics, aggregator, predictions, targets)
+  if compiled is not None:
+    return compiled.run()
   key = fastpath.chunk_key(metrics, aggregator, predictions, targets)
   compiled = fastpath.lookup(key)
   if compiled is not None:

@@ -160,6 +160,40 @@ def chunk_key(metrics, aggregator, predictions, targets):
     return None   # not replayable; never an error
 
 
+def quick_lookup(metrics, aggregator, predictions, targets):
+  """The compiled chunk of a call whose objects are the very ones of an
+  earlier call, or None.  Builds the identity part of chunk_key only: no type
+  checks (a hit means the compiled chunk's weak references to exactly these
+  objects are alive, so they are what they were) and no guard list."""
+  if not ENABLED or not _COMPILED:
+    return None
+  try:
+    torch = _torch()
+    from weatherbenchx_b200 import engine  # pylint: disable=g-import-not-at-top
+    device = torch.cuda.current_device()
+    key = (
+        tuple([(name, id(m)) for name, m in metrics.items()]),
+        (type(aggregator), tuple(aggregator.reduce_dims),
+         tuple([id(b) for b in aggregator.bin_by or ()]),
+         tuple([id(w) for w in aggregator.weigh_by or ()]),
+         bool(aggregator.masked), bool(aggregator.skipna)),
+        tuple([(v, id(da), id(da._data), da._version)  # pylint: disable=protected-access
+               for v, da in predictions.items()]),
+        tuple([(v, id(da), id(da._data), da._version)  # pylint: disable=protected-access
+               for v, da in targets.items()]),
+        device, _raw_stream(torch, device),
+        getattr(_cabi._lane, 'index', 0),  # pylint: disable=protected-access
+        engine.CRPS_KERNEL, engine.XF_L2_BLOCK_BYTES)
+  except Exception:  # pylint: disable=broad-except
+    return None      # (not DataArrays, no _version, ...): the full path decides
+  with _LOCK:
+    compiled = _COMPILED.get(key)
+    if compiled is None or not compiled.alive():
+      return None
+    _COMPILED.move_to_end(key)
+    return compiled
+
+
 def lookup(key):
   if key is None:
     return None

@@ -95,6 +95,7 @@ class DataArray:
   """N-d array with named dims and coordinate variables."""
 
   __array_priority__ = 60
+  _version = 0   # mutation stamp of the coordinates (bumped per instance)
 
   def __init__(self, data, dims: Sequence[Hashable] | str | None = None,
                coords: Mapping[Hashable, Any] | None = None,
