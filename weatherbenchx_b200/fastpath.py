@@ -316,6 +316,7 @@ class CompiledChunk:
     means: dict = {}
     for kind, glaunches, items in self.groups:
       raw: dict = {}
+      binned: dict = {}
       for launch, off_ws, off_w, ws_cols, w_cols in glaunches:
         ws = flat[off_ws:off_ws + launch.n_rows * ws_cols].reshape(
             launch.n_rows, ws_cols)
@@ -323,6 +324,9 @@ class CompiledChunk:
             launch.n_rows, w_cols)
         if kind == 'det':
           raw.update(engine.split_fused_results(launch, ws, w))
+          whole = engine.bin_launch_results(launch, ws, w)
+          if whole is not None:
+            binned.update(whole)
         else:
           raw.update(engine.split_crps_results(launch, ws, w))
       for idx, (spec, leaves) in enumerate(items):
@@ -347,7 +351,8 @@ class CompiledChunk:
           for _, _, leaf in leaves:
             if all(leaf.kind != s.kind for s in stats):
               stats.append(leaf)
-          labelled = engine.label_fused_results(spec, stats, ws, w, means=True)
+          labelled = engine.label_fused_results(
+              spec, stats, ws, w, means=True, binned=binned.get(idx))
           for stat_name, var, leaf in leaves:
             means.setdefault(stat_name, {})[var] = labelled[leaf.kind]
     metrics = {name: ref() for name, ref in self._metrics.items()}
