@@ -62,6 +62,33 @@ def _resolve_out_path(out_path, agg_name):
   return out_path[agg_name]
 
 
+# Optional event trace of a run (WBX_PIPELINE_TRACE=<path>): one JSON line per
+# phase of every chunk -- (thread, chunk, phase, start, end) in seconds -- to
+# see how loading, planning and the library calls of the lanes overlap.
+_TRACE: list = []
+_TRACE_LOCK = threading.Lock()
+
+
+def _trace(chunk, phase: str, start: float) -> None:
+  if os.environ.get('WBX_PIPELINE_TRACE'):
+    with _TRACE_LOCK:
+      _TRACE.append((threading.current_thread().name, int(chunk), phase,
+                     start, time.perf_counter()))
+
+
+def _dump_trace() -> None:
+  path = os.environ.get('WBX_PIPELINE_TRACE')
+  if not path:
+    return
+  import json  # pylint: disable=g-import-not-at-top
+  with _TRACE_LOCK:
+    rows, _TRACE[:] = list(_TRACE), []
+  with open(path, 'a') as f:
+    for thread, chunk, phase, start, end in rows:
+      f.write(json.dumps({'thread': thread, 'chunk': chunk, 'phase': phase,
+                          'start': start, 'end': end}) + '\n')
+
+
 def _current_cuda_device():
   """Index of the calling thread's CUDA device, or None without a GPU."""
   try:
@@ -107,6 +134,7 @@ class _Prefetcher:
     targets = targets_loader.load_chunk(init_times, lead_times)
     predictions = predictions_loader.load_chunk(init_times, lead_times, targets)
     self.load_seconds += time.perf_counter() - start
+    _trace(index, 'load', start)
     return index, predictions, targets
 
   def _work(self):
@@ -437,10 +465,15 @@ def run_pipeline(
 
   def evaluate(item):
     index, predictions, targets = item
+    start = time.perf_counter()
     statistics = metrics_base.compute_unique_statistics_for_all_metrics(
         metrics, predictions, targets)
-    return index, [(name, agg.aggregate_statistics(statistics))
-                   for name, agg in aggregators.items()]
+    _trace(index, 'statistics', start)
+    start = time.perf_counter()
+    states = [(name, agg.aggregate_statistics(statistics))
+              for name, agg in aggregators.items()]
+    _trace(index, 'aggregate', start)
+    return index, states
 
   since_ckpt = 0
   for index, states in _evaluate_in_lanes(loader, evaluate, lanes):
@@ -459,6 +492,7 @@ def run_pipeline(
     _atomic_pickle(ckpt_file, {'n_chunks': len(times), 'done': done,
                                'acc': acc.dump(), 'fingerprint': fingerprint})
 
+  _dump_trace()
   results = {}
   local = acc.states(aggregators)
   for name in aggregators:
