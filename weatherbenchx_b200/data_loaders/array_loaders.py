@@ -146,18 +146,25 @@ class _DeviceRows:
     self.rows = torch.empty(tuple(da.shape), dtype=torch.float32,
                             device=self.device)
     self._stream = torch.cuda.Stream(self.device)
+    self._last_event = None
     self.uploaded_bytes = 0
 
-  def ensure(self, positions: np.ndarray):
-    """Uploads the rows at ``positions`` that are not on the device yet and
-    returns after they have arrived (called from the loader thread, which
-    runs ahead of the GPU)."""
+  def ensure(self, positions: np.ndarray, wait: bool = True):
+    """Uploads the rows at ``positions`` that are not on the device yet.
+
+    ``wait=True`` returns after they have arrived.  ``wait=False`` only issues
+    the copies and returns the event that follows the last upload of this
+    cache (all uploads share one stream, so it covers every row a chunk can
+    need); whoever consumes the chunk waits for it.  The loader thread of the
+    chunk driver must not wait itself: its small copy queues behind the
+    100 MB forecast copies of the evaluation lanes on the same PCIe link, and
+    a loader that blocks for each chunk starves the lanes."""
     import torch  # pylint: disable=g-import-not-at-top
     with self._lock:
       need = np.unique(positions)
       need = need[~self._present[need]]
       if not len(need):
-        return
+        return self._last_event
       runs = np.split(need, np.nonzero(np.diff(need) != 1)[0] + 1)
       with torch.cuda.stream(self._stream):
         for run in runs:
@@ -168,8 +175,13 @@ class _DeviceRows:
           self.rows[lo:hi].copy_(torch.from_numpy(np.ascontiguousarray(src)),
                                  non_blocking=True)
           self.uploaded_bytes += (hi - lo) * self.rows[0].numel() * 4
-      self._stream.synchronize()
+        event = torch.cuda.Event()
+        event.record(self._stream)
+      self._last_event = event
       self._present[need] = True
+    if wait:
+      event.synchronize()
+    return event
 
 
 class TargetsFromArrays(_ArrayLoader):
@@ -194,11 +206,22 @@ class TargetsFromArrays(_ArrayLoader):
     self._resident: dict = {}
     self._claimed = 0
     self._resident_lock = threading.Lock()
+    # chunk driver: do not wait for the uploads inside load_chunk, hand the
+    # event to the consumer (take_ready_events)
+    self.async_uploads = False
+    self._chunk_events: list = []
+
+  def take_ready_events(self) -> list:
+    """Events the arrays of the last load_chunk call of this thread's loader
+    have to wait for before they are read (async_uploads only)."""
+    events, self._chunk_events = self._chunk_events, []
+    return events
 
   def __getstate__(self):
     state = dict(self.__dict__)
     state['_resident'] = {}      # device memory is per process
     state['_claimed'] = 0
+    state['_chunk_events'] = []
     state.pop('_resident_lock', None)
     return state
 
@@ -255,7 +278,9 @@ class TargetsFromArrays(_ArrayLoader):
       source = da.data
       resident = self._device_rows(var, da)
       if resident is not None:
-        resident.ensure(pos.ravel())
+        event = resident.ensure(pos.ravel(), wait=not self.async_uploads)
+        if self.async_uploads and event is not None:
+          self._chunk_events.append(event)
         source = resident.rows
       payload = _window_view(source, axis, pos)
       if payload is None:

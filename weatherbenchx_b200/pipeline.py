@@ -133,9 +133,16 @@ class _Prefetcher:
     # loader (beam_pipeline.py:93-105)
     targets = targets_loader.load_chunk(init_times, lead_times)
     predictions = predictions_loader.load_chunk(init_times, lead_times, targets)
+    # uploads a loader issued without waiting (TargetsFromArrays device cache):
+    # the evaluation waits for them, not this thread
+    events = []
+    for loader in (targets_loader, predictions_loader):
+      take = getattr(loader, 'take_ready_events', None)
+      if take is not None:
+        events += take()
     self.load_seconds += time.perf_counter() - start
     _trace(index, 'load', start)
-    return index, predictions, targets
+    return index, predictions, targets, events
 
   def _work(self):
     try:
@@ -460,11 +467,19 @@ def run_pipeline(
         done = list(saved['done'])
   todo = [i for i in mine if i not in set(done)]
 
+  async_loaders = [l for l in (targets_loader, predictions_loader)
+                   if getattr(l, 'async_uploads', None) is False]
+  for l in async_loaders:
+    l.async_uploads = True
   loader = _Prefetcher(times, todo, predictions_loader, targets_loader,
                        max(prefetch, lanes if lanes > 1 else 0), setup_fn)
 
   def evaluate(item):
-    index, predictions, targets = item
+    index, predictions, targets, events = item
+    start = time.perf_counter()
+    for event in events:
+      event.synchronize()
+    _trace(index, 'wait', start)
     start = time.perf_counter()
     statistics = metrics_base.compute_unique_statistics_for_all_metrics(
         metrics, predictions, targets)
@@ -475,23 +490,26 @@ def run_pipeline(
     _trace(index, 'aggregate', start)
     return index, states
 
-  since_ckpt = 0
-  for index, states in _evaluate_in_lanes(loader, evaluate, lanes):
-    for name, state in states:
-      acc.add(name, state)
-    done.append(index)
-    since_ckpt += 1
-    if progress is not None:
-      progress(len(done), len(mine))
-    if ckpt_file and checkpoint_every and since_ckpt >= checkpoint_every:
+  try:
+    since_ckpt = 0
+    for index, states in _evaluate_in_lanes(loader, evaluate, lanes):
+      for name, state in states:
+        acc.add(name, state)
+      done.append(index)
+      since_ckpt += 1
+      if progress is not None:
+        progress(len(done), len(mine))
+      if ckpt_file and checkpoint_every and since_ckpt >= checkpoint_every:
+        _atomic_pickle(ckpt_file, {'n_chunks': len(times), 'done': done,
+                                   'acc': acc.dump(),
+                                   'fingerprint': fingerprint})
+        since_ckpt = 0
+    if ckpt_file and since_ckpt:
       _atomic_pickle(ckpt_file, {'n_chunks': len(times), 'done': done,
-                                 'acc': acc.dump(),
-                                 'fingerprint': fingerprint})
-      since_ckpt = 0
-  if ckpt_file and since_ckpt:
-    _atomic_pickle(ckpt_file, {'n_chunks': len(times), 'done': done,
-                               'acc': acc.dump(), 'fingerprint': fingerprint})
-
+                                 'acc': acc.dump(), 'fingerprint': fingerprint})
+  finally:
+    for l in async_loaders:
+      l.async_uploads = False
   _dump_trace()
   results = {}
   local = acc.states(aggregators)
