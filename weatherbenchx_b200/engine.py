@@ -667,7 +667,7 @@ def _build_fused_spec(stats, reduce_dims, weights, masked, skipna, flags_extra,
     if slab_bound and slab_bound <= set(inner):
       # grid bin masks: the slab is just the dims the masks live on, so that
       # the class map is one grid (not one per init time) and a launch has
-      # many jobs per slab part (csrc/det_bins2.cuh)
+      # many jobs per slab part (csrc/det_bins3.cuh)
       break
     trial = [d] + inner
     ok = all(tuple(o.dims[-len(trial):]) == tuple(trial) for o in operands)
