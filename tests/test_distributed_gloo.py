@@ -247,6 +247,20 @@ def test_shard_units_partitions_everything_once():
     assert max(map(len, got)) - min(map(len, got)) <= 1
 
 
+def test_ranks_are_spread_over_the_visible_devices():
+  """Fewer ranks than GPUs: every other (fourth, ...) device, so that as few
+  ranks as possible share a host uplink."""
+  place = distributed.device_for_local_rank
+  assert [place(r, 1, 8) for r in range(1)] == [0]
+  assert [place(r, 2, 8) for r in range(2)] == [0, 4]
+  assert [place(r, 4, 8) for r in range(4)] == [0, 2, 4, 6]
+  assert [place(r, 8, 8) for r in range(8)] == list(range(8))
+  assert [place(r, 3, 8) for r in range(3)] == [0, 2, 4]
+  assert [place(r, 4, 4) for r in range(4)] == [0, 1, 2, 3]   # nothing spare
+  assert [place(r, 4, 6) for r in range(4)] == [0, 1, 2, 3]
+  assert place(0, 1, 1) == 0
+
+
 def test_pack_unpack_round_trip():
   state = aggregation.AggregationState(
       {'s': {'a': xl.DataArray(np.arange(6.0).reshape(2, 3), ('x', 'y'),

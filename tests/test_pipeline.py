@@ -328,6 +328,49 @@ def test_lanes_fold_in_chunk_order_and_surface_errors():
         require_output=False, lanes=2)
 
 
+def test_trace_and_ready_events(tmp_path, monkeypatch):
+  """WBX_PIPELINE_TRACE records the phases of every chunk, and the events a
+  loader hands out through take_ready_events are waited for by the evaluation
+  (the device cache of TargetsFromArrays issues its uploads without waiting
+  when the chunk driver asks it to)."""
+  import json
+  trace = tmp_path / 'trace.jsonl'
+  monkeypatch.setenv('WBX_PIPELINE_TRACE', str(trace))
+  waited = []
+
+  class Event:
+    def __init__(self, tag):
+      self.tag = tag
+
+    def synchronize(self):
+      waited.append(self.tag)
+
+  class EventfulTargets(array_loaders.TargetsFromArrays):
+    def load_chunk(self, init_times, lead_times=None, reference=None):
+      assert self.async_uploads        # set by run_pipeline, reset afterwards
+      self._chunk_events.append(Event(str(np.asarray(init_times)[0])))
+      return super().load_chunk(init_times, lead_times, reference)
+
+  preds, tgts = _datasets()
+  rd = ['init_time', 'latitude', 'longitude']
+  times = time_chunks.TimeChunks(INIT, LEAD, init_time_chunk_size=1)
+  loader = EventfulTargets(tgts)
+  out = pipeline.run_pipeline(
+      times, array_loaders.PredictionsFromArrays(preds), loader, METRICS,
+      OracleAggregator(rd), require_output=False, lanes=2)
+  assert loader.async_uploads is False
+  assert len(waited) == len(times) and len(set(waited)) == len(INIT)
+  rows = [json.loads(line) for line in trace.read_text().splitlines()]
+  phases = {r['phase'] for r in rows}
+  assert phases == {'load', 'wait', 'statistics', 'aggregate'}
+  assert {r['chunk'] for r in rows} == set(range(len(times)))
+  assert all(r['end'] >= r['start'] for r in rows)
+  mono = _monolithic(rd)
+  for k in mono:
+    np.testing.assert_allclose(out[None][1][k].values, mono[k].values,
+                               rtol=1e-12)
+
+
 def test_loader_errors_surface_from_the_prefetch_thread():
   class Broken:
     def load_chunk(self, *args):
