@@ -151,7 +151,8 @@ def test_schedule_replay_matches_direct_sums(shape, per_element):
     served = 0
     # (the 0.25 degree grid takes seconds per replay: its own part size and
     # one small one)
-    for part in ((3520, 1024) if ny * nx > 500_000 else (4096, 3520, 1024, 64)):
+    for part in ((3520, 1024, 512) if ny * nx > 500_000 else
+                 (4096, 3520, 1024, 64)):
       rc, tab = _tables(cmap, n_classes, ny, nx, part)
       if rc != 0:      # too many boundary quads for this part size
         assert name in ('noise', 'edges', 'coast') and part > 1024, (name, part)
