@@ -10,8 +10,8 @@ tail -4 gpurun_out/r2_call17_gpu_tests.log
 echo "== smoke"
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "== bench (default flags)"
-/usr/bin/time -v timeout 1500 python bench.py > gpurun_out/r2_call17_bench.json 2> gpurun_out/r2_call17_bench.err
-grep -n "Elapsed (wall clock)" gpurun_out/r2_call17_bench.err
+timeout 1500 python bench.py > gpurun_out/r2_call17_bench.json 2> gpurun_out/r2_call17_bench.err
+
 python - <<'PY'
 import json
 try:
