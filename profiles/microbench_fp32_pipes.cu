@@ -51,6 +51,23 @@ __global__ void __launch_bounds__(1024, 1) bench(float* out, float a, float b,
         x[c] = x[c] + a;
         x[c] = fmaxf(x[c], b);
       }
+      if (OP == 9) asm volatile("max.f32 %0, %0, %1, %2;"        // FMNMX3
+                                : "+f"(x[c]) : "f"(x[(c + 1) % CHAINS]), "f"(b));
+      if (OP == 10 && (c & 1) == 0) {   // compare-exchange: 2 FMNMX
+        const float lo = fminf(x[c], x[c + 1]), hi = fmaxf(x[c], x[c + 1]);
+        x[c] = lo + a;   // (+ a keeps the chain from folding: 2 FADD extra)
+        x[c + 1] = hi + a;
+      }
+      if (OP == 11 && (c & 1) == 0) {   // mixed CE: 1 FMNMX + 2 FADD
+        const float lo = fminf(x[c], x[c + 1]);
+        const float hi = __fsub_rn(__fadd_rn(x[c], x[c + 1]), lo);
+        x[c] = lo + a;
+        x[c + 1] = hi + a;
+      }
+      if (OP == 12) {                                             // VIMNMX (s32)
+        int v = max(__float_as_int(x[c]), __float_as_int(x[(c + 1) % CHAINS]));
+        x[c] = __int_as_float(v);
+      }
       if (OP == 8) {                                              // FADD2 + 2 LOP3
         asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(X[c]) : "l"(A));
         X[c] &= 0x7fffffff7fffffffull;
@@ -66,7 +83,7 @@ __global__ void __launch_bounds__(1024, 1) bench(float* out, float a, float b,
 }
 
 template <int OP>
-void run(const char* name, int instr_per_step) {
+void run(const char* name, double instr_per_step) {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   float* out;
@@ -100,5 +117,10 @@ int main() {
   run<6>("FADD + FADD|x| (pair-sum step)", 2);
   run<7>("FADD + FMNMX (two pipes)", 2);
   run<8>("FADD2 + LOP3.64 (packed abs)", 3);
+  run<9>("FMNMX3 (3-input max)", 1);
+  // per PAIR of chains: (2 FMNMX + 2 FADD) / 2 and (1 FMNMX + 4 FADD) / 2
+  run<10>("compare-exchange 2 FMNMX (+2 FADD)", 2);
+  run<11>("compare-exchange 1 FMNMX + 2 FADD (+2 FADD)", 2.5);
+  run<12>("VIMNMX s32", 1);
   return 0;
 }

@@ -228,6 +228,71 @@ def test_sort_and_pair_kernels_agree_with_nans(members):
       rtol=RTOL)
 
 
+@pytest.mark.parametrize('moments', [False, True])
+@pytest.mark.parametrize('members', [50, 51])
+def test_fixed_size_sort_kernel_edge_points(members, moments):
+  """The fixed-size networks sort x_m - y (crps.cu, kSplit) and fold their last
+  layer into the moment: per-point fields against the oracle where that shift
+  is not usable (NaN / infinite targets, a masked row of the analysis), with a
+  NaN member, one infinite member, identical members (spread exactly zero, as
+  the reference's float64 sum gives) and a field far from zero."""
+  import torch
+  rng = np.random.default_rng(members)
+  n_init, ny, nx = 2, 16, 64
+  x = (101325 + 300 * rng.normal(size=(n_init, members, ny, nx))
+       ).astype(np.float32)
+  y = (101325 + 300 * rng.normal(size=(n_init, ny, nx))).astype(np.float32)
+  x[0, 7, 3, 5] = np.nan
+  x[1, :, 2, :8] = x[1, :1, 2, :8]
+  x[1, members - 1, 9, 9] = np.inf
+  y[0, 4, 4] = np.nan
+  y[0, 5, 5] = np.inf
+  y[0, 5, 6] = -np.inf
+  y[1, 6, :] = np.nan
+  xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+  with np.errstate(invalid='ignore'):
+    want = [oracle.crps_skill(x, y, 1), oracle.crps_spread(x, 1, fair=True),
+            oracle.ensemble_variance(x, 1),
+            oracle.unbiased_ensemble_mean_squared_error(x, y, 1)]
+  ctx = _cabi.get_context()
+  ctx.use_torch_stream()
+  plan = _cabi.CrpsPlan(
+      ctx, space=_cabi.SPACE_DEVICE,
+      flags=_cabi.CRPS_FAIR | _cabi.CRPS_USE_SORT | _cabi.FLAG_SKIPNA, ny=ny,
+      nx=nx, n_members=members, member_stride=ny * nx, point_stride=1,
+      ens=np.array([xd.data_ptr() + i * members * ny * nx * 4
+                    for i in range(n_init)], np.uint64),
+      target=np.array([yd.data_ptr() + i * ny * nx * 4
+                       for i in range(n_init)], np.uint64),
+      cell=np.zeros(n_init, np.int32), n_cells=1,
+      stat_mask=15 if moments else 3)
+  n_fields = 4 if moments else 2
+  fields = [torch.full((n_init, ny, nx), -1.0, device='cuda')
+            for _ in range(n_fields)]
+  ws, w = plan.run_fields([f.data_ptr() for f in fields] +
+                          [None] * (4 - n_fields))
+  got = [f.cpu().numpy() for f in fields]
+  # the one infinite member: pair sums of inf - inf are NaN in the reference's
+  # pair form and inf in the sorted form; not compared
+  cmp = np.ones((n_init, ny, nx), bool)
+  cmp[1, 9, 9] = False
+  for k in range(n_fields):
+    np.testing.assert_array_equal(np.isnan(got[k][cmp]), np.isnan(want[k][cmp]))
+    np.testing.assert_array_equal(np.isinf(got[k][cmp]), np.isinf(want[k][cmp]))
+    ok = cmp & np.isfinite(want[k])
+    np.testing.assert_allclose(got[k][ok], want[k][ok],
+                               rtol=2e-5 if k >= 2 else 2e-6,
+                               atol=1e-2 if k == 3 else 0)
+    # the sums of the same launch (skipna statistic: NaN points dropped)
+    fin = np.isfinite(got[k])
+    if np.isfinite(got[k][~np.isnan(got[k])]).all():
+      np.testing.assert_allclose(ws[0, k], got[k][fin].astype(np.float64).sum(),
+                                 rtol=1e-12)
+  assert (got[1][1, 2, :8] == 0).all()
+  assert np.isinf(got[0][0, 5, 5]) and np.isinf(got[0][0, 5, 6])
+  assert np.isfinite(got[1][0, 5, 5]) and np.isfinite(got[1][1, 6, :]).all()
+
+
 @pytest.mark.parametrize('masked', [False, True])
 def test_tma_staged_pair_kernel_equals_plain_one(masked):
   """The TMA double-buffered pair kernel and the cooperative-load one run the

@@ -507,16 +507,58 @@ struct FixedSort {
   static constexpr bool kAvailable = false;
 };
 
+// The pipe that bounds the sorting network is the ALU pipe (FMNMX: one warp
+// instruction per two cycles per scheduler); the FMA pipe next to it is mostly
+// idle.  Two rewrites move work across (exact algebra, float rounding only):
+//  (1) the moment is formed WITHOUT the network's last layer: a pair of
+//      adjacent ranks (q, q + 1) that sits unsorted on wires (a, b) contributes
+//      (2q + 2 - n) (a + b) + |a - b| -- FMA-pipe instructions instead of
+//      two FMNMX + two FFMA.  The signed part is written with differences
+//      only (sort_networks.inc: _HEAD / _TAIL / _MOMENT), so identical
+//      members give a spread of exactly zero, as the reference's float64 sum;
+//  (2) MIXPCT per cent of the remaining compare-exchanges compute their
+//      maximum as (a + b) - min(a, b): one FMNMX + two FADD.  The members are
+//      centred on the first one beforehand, so the rounding of a + b is
+//      relative to the ensemble's range, not to the field's magnitude
+//      (measured: no change of the spread above 1e-8 relative at 100 %).
+constexpr int kSortMixPct = 45;     // measured: 30 / 35 / 40 / 45 / 50 within 1 %
+constexpr int kSortFixedCtas = 4;   // resident CTAs per SM asked of ptxas (128 reg.)
+__host__ __device__ constexpr bool sort_ce_mixed(const int index,
+                                                 const int mixpct) {
+  return (index * 61) % 100 < mixpct;
+}
+
+template <int MAXM, bool MIXED>
+__device__ __forceinline__ void cmp_exchange_v(float (&x)[MAXM], const int a,
+                                               const int b) {
+  const float lo = fminf(x[a], x[b]);
+  float hi;
+  if constexpr (MIXED) hi = __fsub_rn(__fadd_rn(x[a], x[b]), lo);
+  else hi = fmaxf(x[a], x[b]);
+  x[a] = lo;
+  x[b] = hi;
+}
+
 #define WBX_CE(a, b) cmp_exchange<MAXM>(x, a, b);
+#define WBX_CEV(i, a, b) \
+  cmp_exchange_v<MAXM, sort_ce_mixed(i, MIXPCT)>(x, a, b);
 #define WBX_RANK_TERM(q, i) \
   if ((q) > 0 && (q) < n) sp += static_cast<float>(2 * (q) + 1 - n) * (x[i] - c);
-#define WBX_FIXED_SORT(N)                                                      \
+#define WBX_TAIL_ABS(a, b) sd += fabsf(x[a] - x[b]);
+#define WBX_MOM_D2(m, a1, b1, a2, b2) \
+  sp += static_cast<float>(m) * ((x[a2] + x[b2]) - (x[a1] + x[b1]));
+#define WBX_MOM_D1(c, w1, w2) sp += static_cast<float>(c) * (x[w2] - x[w1]);
+#define WBX_MOM_A2(m, a, b, w0) \
+  sp += static_cast<float>(m) * fmaf(-2.f, x[w0], x[a] + x[b]);
+#define WBX_MOM_A1(c, w, w0) sp += static_cast<float>(c) * (x[w] - x[w0]);
+#define WBX_FIXED_SORT(NN)                                                     \
   template <>                                                                  \
-  struct FixedSort<N> {                                                        \
+  struct FixedSort<NN> {                                                       \
     static constexpr bool kAvailable = true;                                   \
+    static constexpr int N = NN;                                               \
     template <int MAXM>                                                        \
     static __device__ __forceinline__ void sort(float (&x)[MAXM]) {            \
-      WBX_SORT##N(WBX_CE)                                                      \
+      WBX_SORT##NN(WBX_CE)                                                     \
     }                                                                          \
     /* sum_q (2q + 1 - n) (x_(q) - x_(0)) over the first n ranks */            \
     template <int MAXM>                                                        \
@@ -524,19 +566,35 @@ struct FixedSort {
                                                    const int n) {              \
       const float c = x[0]; /* rank 0 is wire 0 in both networks */            \
       float sp = 0.f;                                                          \
-      WBX_SORT##N##_RANKS(WBX_RANK_TERM)                                       \
+      WBX_SORT##NN##_RANKS(WBX_RANK_TERM)                                      \
       return sp;                                                               \
+    }                                                                          \
+    /* sum_q (2q + 1 - N) x_(q) of N CENTRED members: the network up to its   \
+       last layer, then the pair form of the moment */                         \
+    template <int MAXM, int MIXPCT>                                            \
+    static __device__ __forceinline__ float sorted_moment(float (&x)[MAXM]) {  \
+      WBX_SORT##NN##_HEAD(WBX_CEV)                                             \
+      float sp = 0.f, sd = 0.f;                                                \
+      WBX_SORT##NN##_MOMENT(WBX_MOM_D2, WBX_MOM_D1, WBX_MOM_A2, WBX_MOM_A1)    \
+      WBX_SORT##NN##_TAIL(WBX_TAIL_ABS)                                        \
+      return sp + sd;                                                          \
     }                                                                          \
   };
 WBX_FIXED_SORT(50)
 WBX_FIXED_SORT(51)
 #undef WBX_FIXED_SORT
+#undef WBX_MOM_A1
+#undef WBX_MOM_A2
+#undef WBX_MOM_D1
+#undef WBX_MOM_D2
+#undef WBX_TAIL_ABS
 #undef WBX_RANK_TERM
+#undef WBX_CEV
 #undef WBX_CE
 
 // Skill, spread (sort / PWM estimator) and the optional moments of one grid
 // point whose members are in x[0 .. M) (x is sorted in place).
-template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MOMENTS>
+template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MOMENTS, int MIXPCT>
 __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
                                            const int M, const int fair,
                                            float (&v)[kCrpsStats]) {
@@ -550,11 +608,18 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
   // every term is >= 0, and +-inf members stay inf), and a NaN member only
   // has to turn skill and spread into NaN at the end.
   constexpr bool kCheapNan = !ENS_SKIPNA && FixedSort<MFIX>::kAvailable;
+  // kSplit: the differences x_m - y that the skill needs anyway are what gets
+  // sorted (the spread does not change under a shift, and the shift keeps the
+  // rounding of the FMA-pipe compare-exchanges relative to the ensemble's own
+  // scale); their absolute sum doubles as the NaN detector.
+  constexpr bool kSplit = kCheapNan && MIXPCT >= 0;
   float sabs = 0.f;
 #pragma unroll
   for (int m = 0; m < MAXM; ++m) {
     if (m < M) {
-      if constexpr (kCheapNan) {
+      if constexpr (kSplit) {
+        if constexpr (MOMENTS) msum += x[m];
+      } else if constexpr (kCheapNan) {
         sk += fabsf(x[m] - y);
         sabs += fabsf(x[m]);
         if constexpr (MOMENTS) msum += x[m];
@@ -570,7 +635,7 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
       }
     }
   }
-  if constexpr (kCheapNan) n_nan = (sabs == sabs) ? 0 : 1;
+  if constexpr (kCheapNan && !kSplit) n_nan = (sabs == sabs) ? 0 : 1;
   v[0] = v[1] = v[2] = v[3] = 0.f;
   if constexpr (MOMENTS) {
     const float fnm = static_cast<float>(ENS_SKIPNA ? (M - n_nan) : M);
@@ -594,7 +659,30 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
   }
   const int n = ENS_SKIPNA ? (M - n_nan) : M;
   float sp = 0.f;
-  if constexpr (FixedSort<MFIX>::kAvailable) {
+  if constexpr (kSplit) {
+    // n == M == MFIX here.  A target that is not finite (masked analysis
+    // cells) cannot be the shift: the skill is summed on its own there and
+    // the first member is subtracted instead.
+    float c = y, sk_raw = 0.f;
+    const bool y_finite = fabsf(y) < inf;
+    if (!y_finite) {
+#pragma unroll
+      for (int m = 0; m < MAXM; ++m) {
+        if (m < MFIX) sk_raw += fabsf(x[m] - y);
+      }
+      c = x[0];
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+      if (m < MFIX) {
+        x[m] -= c;
+        sk += fabsf(x[m]);
+      }
+    }
+    n_nan = (sk == sk) ? 0 : 1;  // NaN member (every term is >= 0)
+    if (!y_finite) sk = sk_raw;
+    sp = FixedSort<MFIX>::template sorted_moment<MAXM, MIXPCT>(x);
+  } else if constexpr (FixedSort<MFIX>::kAvailable) {
     FixedSort<MFIX>::template sort<MAXM>(x);
     sp = FixedSort<MFIX>::template moment<MAXM>(x, n);
   } else {
@@ -621,7 +709,7 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
 // become constants, ptxas folds every compare-exchange that touches them and
 // the network shrinks to the size of the real ensemble (M = 50: 64 -> 50 wires).
 template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MASK, bool MOMENTS,
-          int MINB = 1>
+          int MINB = 1, int MIXPCT = -1>
 __global__ void __launch_bounds__(kCrpsThreads, MINB)
     crps_sort_kernel(const CrpsParams P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -667,7 +755,7 @@ __global__ void __launch_bounds__(kCrpsThreads, MINB)
                        : inf;
       const float y = ldg_stream_f1(ta + e);
       float v[kCrpsStats];
-      sort_point<MAXM, MFIX, ENS_SKIPNA, MOMENTS>(x, y, M, P.fair, v);
+      sort_point<MAXM, MFIX, ENS_SKIPNA, MOMENTS, MIXPCT>(x, y, M, P.fair, v);
       crps_store_fields(P, job, e, v);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
@@ -700,7 +788,7 @@ __global__ void __launch_bounds__(kCrpsThreads, MINB)
 }
 
 
-// out[c*2 + s] (statistics) and out_w[c*2 + s] (weights), one warp per output.
+// out[c*4 + s] (statistics) and out_w[c*4 + s] (weights), one CTA per cell.
 struct CrpsFinalizeParams {
   const double* records;
   const int32_t* cell_first_job;
@@ -710,13 +798,19 @@ struct CrpsFinalizeParams {
   int n_cells, grid_main, tiles_per_slab, accumulate;
 };
 
-__global__ void __launch_bounds__(128) crps_finalize_kernel(
+// One CTA per cell: thread t adds accumulator t % 8 of the records t / 8,
+// t / 8 + 128, ... (a warp reads 256 consecutive bytes), then the 128 partial
+// sums of every accumulator are combined in a fixed order (shuffles over the
+// 4 records of a warp, the 32 warps through shared memory).
+constexpr int kCrpsFinalizeThreads = 1024;
+static_assert(kCrpsAcc == 8, "crps_finalize_kernel: lane -> accumulator map");
+
+__global__ void __launch_bounds__(kCrpsFinalizeThreads) crps_finalize_kernel(
     const CrpsFinalizeParams F) {
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp_global >= F.n_cells * kCrpsAcc) return;
-  const int c = warp_global / kCrpsAcc;
-  const int a = warp_global - c * kCrpsAcc;
+  __shared__ double part[kCrpsFinalizeThreads / 32][kCrpsAcc];
+  const int c = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int a = t & (kCrpsAcc - 1);
   const long long ft =
       static_cast<long long>(F.cell_first_job[c]) * F.tiles_per_slab;
   const long long lt =
@@ -728,13 +822,20 @@ __global__ void __launch_bounds__(128) crps_finalize_kernel(
   const double* rec =
       F.records + (static_cast<size_t>(b_lo) + c) * kCrpsWarps * kCrpsAcc + a;
   double sum = 0.0;
-  for (int i = lane; i < n; i += 32) sum += rec[static_cast<size_t>(i) * kCrpsAcc];
-  sum = warp_sum(sum);
-  if (lane == 0) {
-    double* dst = a < kCrpsStats
-                      ? F.out_ws + (size_t)c * kCrpsStats + a
-                      : F.out_w + (size_t)c * kCrpsStats + (a - kCrpsStats);
-    *dst = F.accumulate ? (*dst + sum) : sum;
+  for (int i = t >> 3; i < n; i += kCrpsFinalizeThreads / kCrpsAcc)
+    sum += rec[static_cast<size_t>(i) * kCrpsAcc];
+  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+  if (lane < kCrpsAcc) part[warp][lane] = sum;
+  __syncthreads();
+  if (t < kCrpsAcc) {
+    double total = 0.0;
+#pragma unroll 8
+    for (int w = 0; w < kCrpsFinalizeThreads / 32; ++w) total += part[w][t];
+    double* dst = t < kCrpsStats
+                      ? F.out_ws + (size_t)c * kCrpsStats + t
+                      : F.out_w + (size_t)c * kCrpsStats + (t - kCrpsStats);
+    *dst = F.accumulate ? (*dst + total) : total;
   }
 }
 
@@ -897,8 +998,12 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
   if (prc != WBX_OK) return prc;
   const int what = plan->what;
   if (plan->use_sort) {
+    // Without skipna_ensemble the fixed-size networks run with the FMA-pipe
+    // rewrites (kSortMixPct, sort_ce_mixed) at 4 resident CTAs per SM.
 #define WBX_SORT_LAUNCH2(MAXM, MFIX, MOM)                                      \
   do {                                                                         \
+    constexpr int kMinB = (MFIX) > 0 ? kSortFixedCtas : 1;                     \
+    constexpr int kMix = (MFIX) > 0 ? kSortMixPct : -1;                        \
     if (ens_skipna && plan->has_mask)                                          \
       crps_sort_kernel<MAXM, MFIX, true, true, MOM>                            \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
@@ -906,10 +1011,10 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
       crps_sort_kernel<MAXM, MFIX, true, false, MOM>                           \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
     else if (plan->has_mask)                                                   \
-      crps_sort_kernel<MAXM, MFIX, false, true, MOM>                           \
+      crps_sort_kernel<MAXM, MFIX, false, true, MOM, kMinB, kMix>              \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
     else                                                                       \
-      crps_sort_kernel<MAXM, MFIX, false, false, MOM>                          \
+      crps_sort_kernel<MAXM, MFIX, false, false, MOM, kMinB, kMix>             \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
   } while (0)
 #define WBX_SORT_LAUNCH(MAXM, MFIX)                                            \
@@ -918,12 +1023,7 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
     else WBX_SORT_LAUNCH2(MAXM, MFIX, false);                                  \
   } while (0)
     // the common operational ensemble sizes get a pruned network
-    if (plan->n_members == 50 && !ens_skipna && !plan->has_mask &&
-        !(what & kWantMoments) && getenv("WBX_EXP_SORT_MINB6")) {
-      // experiment: 6 resident CTAs per SM (80 registers, 24 spilled words)
-      crps_sort_kernel<64, 50, false, false, false, 6>
-          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);
-    } else if (plan->n_members == 50) WBX_SORT_LAUNCH(64, 50);
+    if (plan->n_members == 50) WBX_SORT_LAUNCH(64, 50);
     else if (plan->n_members == 51) WBX_SORT_LAUNCH(64, 51);
     else if (plan->n_members <= 8) WBX_SORT_LAUNCH(8, 0);
     else if (plan->n_members <= 16) WBX_SORT_LAUNCH(16, 0);
@@ -978,7 +1078,11 @@ static int crps_grid(const wbx_ctx* ctx, const wbx_crps_plan* plan,
   const size_t per_sm = std::min<size_t>(ctx->smem_optin, 227 * 1024);
   long long ctas_per_sm = std::max<size_t>(1, per_sm / (plan->smem_bytes + 1024));
   ctas_per_sm = std::min<long long>(ctas_per_sm, 8);
-  if (plan->use_sort) ctas_per_sm = 8;  // register-limited, no shared memory
+  // register-limited, no shared memory; every CTA owns an equal run of tiles,
+  // and many short runs balance better than one per resident CTA (measured at
+  // M = 50, 4 resident: 8 / 12 / 16 / 24 / 48 per SM -> 1.10 / 1.08 / 1.07 /
+  // 1.06 / 1.05 ms; profiles/exp_crps_r2_mix.log)
+  if (plan->use_sort) ctas_per_sm = 24;
   const long long g = ctx->sm_count * ctas_per_sm;
   return static_cast<int>(std::max(1ll, std::min(g, total_tiles)));
 }
@@ -1065,10 +1169,7 @@ static int crps_finalize(wbx_ctx* ctx, const wbx_crps_plan* plan,
   F.grid_main = grid_main;
   F.tiles_per_slab = plan->tiles_per_slab;
   F.accumulate = accumulate;
-  const long long threads = static_cast<long long>(n_cells) * kCrpsAcc * 32;
-  const int block = 128;
-  crps_finalize_kernel<<<static_cast<int>((threads + block - 1) / block), block,
-                         0, ctx->stream>>>(F);
+  crps_finalize_kernel<<<n_cells, kCrpsFinalizeThreads, 0, ctx->stream>>>(F);
   WBX_CUDA(cudaGetLastError());
   ctx->launches++;
   return WBX_OK;
