@@ -168,6 +168,14 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
   return r;
 }
 
+__device__ __forceinline__ float2 ldg_stream_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];"
+               : "=f"(r.x), "=f"(r.y)
+               : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ float ldg_stream_f1(const float* p) {
   float r;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));

@@ -200,6 +200,52 @@ __device__ __forceinline__ void dft<16>(float2* v) {
   dft_composite<4, 4>(v, kW16);
 }
 
+// Good-Thomas prime-factor DFT for coprime N1 * N2 (compile-time indices): with
+//   n = (N2 n1 + N1 n2) mod N,   k = (A k1 + C k2) mod N,
+//   A = N2 (N2^-1 mod N1),       C = N1 (N1^-1 mod N2)
+// the transform is N2 DFTs of length N1 followed by N1 of length N2 with NO
+// twiddles in between: 12 points cost 4 x dft<3> + 3 x dft<4>, fewer FP32
+// instructions per point and level than the radix-9 / radix-10 composites.
+template <int N1, int N2, int A, int C>
+__device__ __forceinline__ void dft_pfa(float2* v) {
+  constexpr int N = N1 * N2;
+  float2 y[N];
+#pragma unroll
+  for (int n2 = 0; n2 < N2; ++n2) {
+    float2 t[N1];
+#pragma unroll
+    for (int n1 = 0; n1 < N1; ++n1) t[n1] = v[(N2 * n1 + N1 * n2) % N];
+    dft<N1>(t);
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) y[k1 * N2 + n2] = t[k1];
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < N1; ++k1) {
+    float2 t[N2];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) t[n2] = y[k1 * N2 + n2];
+    dft<N2>(t);
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) v[(A * k1 + C * k2) % N] = t[k2];
+  }
+}
+template <>
+__device__ __forceinline__ void dft<6>(float2* v) {
+  dft_pfa<2, 3, 3, 4>(v);
+}
+template <>
+__device__ __forceinline__ void dft<12>(float2* v) {
+  dft_pfa<3, 4, 4, 9>(v);
+}
+template <>
+__device__ __forceinline__ void dft<24>(float2* v) {
+  dft_pfa<3, 8, 16, 9>(v);
+}
+template <>
+__device__ __forceinline__ void dft<30>(float2* v) {
+  dft_pfa<5, 6, 6, 25>(v);
+}
+
 // One Stockham pass of radix R over a length-H sequence held in shared memory.
 // q = j / Ns via the magic multiplier; `pm` is the padding mask (see kernel).
 template <int R>
@@ -369,7 +415,10 @@ __global__ void __launch_bounds__(512)
 // the generic kernel's instructions were this address arithmetic.  Serves the
 // operational grids (0.25 deg: N = 1440 = 2 * 9 * 10 * 8; 0.5 deg: N = 720).
 // ---------------------------------------------------------------------------
-template <int R, int H, int NS>
+// IN_T: distance between the R operands of a butterfly in `in` (H / R unless
+// the producer padded its output); OUT_Q: distance between consecutive output
+// blocks q in `out` (NS * R unless padded for the consumer).
+template <int R, int H, int NS, int IN_T = H / R, int OUT_Q = NS * R>
 __device__ __forceinline__ void stockham_pass_fixed(
     const float2* __restrict__ in, float2* __restrict__ out,
     const float2* __restrict__ tw, const int lane) {
@@ -382,7 +431,7 @@ __device__ __forceinline__ void stockham_pass_fixed(
       const int k = j - q * NS;
       float2 v[R];
 #pragma unroll
-      for (int t = 0; t < R; ++t) v[t] = in[j + t * B];
+      for (int t = 0; t < R; ++t) v[t] = in[j + t * IN_T];
       if constexpr (NS > 1) {
         // pass table laid out [k][t]: a lane reads R-1 consecutive twiddles and
         // neighbouring lanes are an odd number of float2 apart (no bank
@@ -392,7 +441,7 @@ __device__ __forceinline__ void stockham_pass_fixed(
         for (int t = 1; t < R; ++t) v[t] = cmul(v[t], tk[t]);
       }
       dft<R>(v);
-      const int base = q * (NS * R) + k;
+      const int base = q * OUT_Q + k;
 #pragma unroll
       for (int t = 0; t < R; ++t) out[base + t * NS] = v[t];
     }
@@ -504,6 +553,257 @@ __global__ void __launch_bounds__(256)
       const float factor = (k == 0) ? 1.0f : 2.0f;
       dst[k] = factor * scale * (xr * xr + xi * xi);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Second fixed-shape variant (the one the operational grids run): radices
+// (5, 12, 12) for H = 720 and (5, 6, 12) for H = 360.
+//  * the butterfly counts 144 / 60 / 60 fill 5 / 2 / 2 warp iterations to
+//    90-94 % (80 / 72 / 90 of the (9, 10, 8) split filled 3 each to 75-94 %),
+//    and the prime-factor 12- and 6-point butterflies need no inner twiddles;
+//  * the first pass takes its operands straight from global memory in the
+//    order it needs them (lane j reads z[j + t B0]: 8-byte loads, 256
+//    contiguous bytes per warp instruction), prefetched one row ahead in
+//    registers -- no staging copy of the row through shared memory;
+//  * the real-FFT split handles the bins k and H - k together: they share
+//    E = Z[k] + conj Z[H-k], O = Z[k] - conj Z[H-k] and w^(H-k) = -conj w^k,
+//        X[k]   = (E.x + P.y,  E.y - P.x) / 2,     P = w^k O
+//        X[H-k] = (E.x - P.y, -E.y - P.x) / 2
+//    (k = 0 pairs with the Nyquist bin through Z[H] = Z[0]; k = H/2 with
+//    itself), which halves the shared-memory reads and the twiddle table of
+//    that stage and removes a third of its arithmetic.
+// ---------------------------------------------------------------------------
+template <int H, int R0, int R1, int R2>
+__global__ void __launch_bounds__(256, 2)
+    zonal_spectrum_fixed2_kernel(const SpecParams P) {
+  static_assert(R0 * R1 * R2 == H, "radices must factor H");
+  static_assert(R0 % 2 == 1, "the first pass scatters with stride R0");
+  extern __shared__ __align__(16) unsigned char spec_smem[];
+  constexpr int N = 2 * H;
+  constexpr int B0 = H / R0;
+  constexpr int kIt0 = (B0 + 31) / 32;
+  float2* tw1 = reinterpret_cast<float2*>(spec_smem);  // exp(-2 pi i t k / (R0 R1))
+  float2* tw2 = tw1 + R0 * (R1 - 1);                   // exp(-2 pi i t k / H)
+  float2* twn = tw1 + H;                               // exp(-2 pi i k / N), k <= H/2
+  float2* bufs = twn + (H / 2 + 2);                    // [rows][H + kPadB]
+  // The second pass scatters blocks of R0 consecutive elements R0 R1 apart:
+  // with that distance padded to = R0 (mod 16) in 8-byte units the 32 lanes of
+  // a store hit 32 different banks (unpadded: 3.9 M two-way conflicts per C4
+  // step, 15 % of all shared-memory wavefronts).
+  constexpr int kQ1 = R0 * R1 + ((R0 - R0 * R1) % 16 + 16) % 16;
+  constexpr int kPadB = R2 * kQ1;                      // length of buffer b
+  const int group = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int q = threadIdx.x; q < R0 * (R1 - 1); q += blockDim.x) {
+    const int k = q / (R1 - 1), t = q - k * (R1 - 1) + 1;
+    double sn, cs;
+    sincospi(2.0 * (t * k) / (R0 * R1), &sn, &cs);
+    tw1[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+  }
+  for (int q = threadIdx.x; q < R0 * R1 * (R2 - 1); q += blockDim.x) {
+    const int k = q / (R2 - 1), t = q - k * (R2 - 1) + 1;
+    double sn, cs;
+    sincospi(2.0 * (t * k) / H, &sn, &cs);
+    tw2[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+  }
+  for (int q = threadIdx.x; q <= H / 2; q += blockDim.x) {
+    double sn, cs;
+    sincospi(2.0 * q / N, &sn, &cs);
+    twn[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+  }
+  __syncthreads();
+  float2* a = bufs + static_cast<size_t>(group) * (H + kPadB);
+  float2* b = a + H;
+  // |X|^2 / N^2 with X = (E -+ ...) / 2
+  constexpr float inv_4n2 =
+      0.25f / (static_cast<float>(N) * static_cast<float>(N));
+  const long long rows_per_iter = static_cast<long long>(gridDim.x) * P.rows;
+  float2 pre[kIt0 * R0];
+  auto row_pointer = [&](long long r, int* y_out) {
+    const long long job = r / P.ny;
+    const int y = static_cast<int>(r - job * P.ny);
+    *y_out = y;
+    return reinterpret_cast<const float2*>(
+               reinterpret_cast<const float*>(__ldg(P.field + job)) +
+               static_cast<long long>(y) * N);
+  };
+  auto prefetch = [&](long long r) {
+    int yy;
+    const float2* rp = row_pointer(r, &yy) + lane;
+#pragma unroll
+    for (int it = 0; it < kIt0; ++it) {
+      if (it * 32 + 32 <= B0 || it * 32 + lane < B0) {
+#pragma unroll
+        for (int t = 0; t < R0; ++t)
+          pre[it * R0 + t] = ldg_stream_f2(rp + it * 32 + t * B0);
+      }
+    }
+  };
+  long long row = static_cast<long long>(blockIdx.x) * P.rows + group;
+  if (row < P.n_rows) prefetch(row);
+  for (; row < P.n_rows; row += rows_per_iter) {
+    const int y = static_cast<int>(row % P.ny);
+    __syncwarp();  // the previous row's readers of `a` are done
+    // pass 1 (no twiddles): registers -> a[j R0 + t]
+#pragma unroll
+    for (int it = 0; it < kIt0; ++it) {
+      const int j = it * 32 + lane;
+      if (it * 32 + 32 <= B0 || j < B0) {
+        float2 v[R0];
+#pragma unroll
+        for (int t = 0; t < R0; ++t) v[t] = pre[it * R0 + t];
+        dft<R0>(v);
+#pragma unroll
+        for (int t = 0; t < R0; ++t) a[j * R0 + t] = v[t];
+      }
+    }
+    if (row + rows_per_iter < P.n_rows) prefetch(row + rows_per_iter);
+    __syncwarp();
+    stockham_pass_fixed<R1, H, R0, H / R1, kQ1>(a, b, tw1, lane);
+    __syncwarp();
+    stockham_pass_fixed<R2, H, R0 * R1, kQ1>(b, a, tw2, lane);
+    __syncwarp();
+    const float2* in = a;  // Z[0..H-1]
+    const float scale =
+        (P.row_scale ? static_cast<float>(__ldg(P.row_scale + y)) : 1.0f) *
+        inv_4n2;
+    float* dst = P.out + row * static_cast<long long>(H + 1);
+#pragma unroll 4
+    for (int k = lane; k <= H / 2; k += 32) {
+      const float2 zk = in[k];
+      const float2 zc = in[k == 0 ? 0 : H - k];
+      const float2 e = make_float2(zk.x + zc.x, zk.y - zc.y);  // Z[k] + conj Z[H-k]
+      const float2 o = make_float2(zk.x - zc.x, zk.y + zc.y);  // Z[k] - conj Z[H-k]
+      const float2 pw = cmul(twn[k], o);
+      const float ar = e.x + pw.y, ai = e.y - pw.x;            // 2 X[k]
+      const float br = e.x - pw.y, bi = e.y + pw.x;            // 2 X[H-k] (conj)
+      const float two = 2.0f * scale;
+      dst[k] = (k == 0 ? scale : two) * (ar * ar + ai * ai);
+      dst[H - k] = two * (br * br + bi * bi);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Two-pass variant for H = 720 = 24 * 30: ONE round trip through shared memory
+// per row instead of two (the three-pass kernels are bound by shared-memory
+// wavefronts: 450 per row against 383 ideal, ncu_spectrum_r2_fixed2_a.txt).
+//   pass 1  lanes 0..29: 24 operands z[j + 30 t] straight from global memory
+//           (prefetched one row ahead in registers), prime-factor DFT-24
+//           (3 x 8, no inner twiddles), stored to a[25 j + t] (odd stride);
+//   pass 2  lanes 0..23: operands a[25 t + k], twiddles exp(-2 pi i t k / H)
+//           from a [k][t] table, prime-factor DFT-30 (5 x 6); lane k then holds
+//           Z[k + 24 t] in register t;
+//   split   the partner Z[H - (k + 24 t)] of register t is register 29 - t of
+//           lane 24 - k (register (30 - t) % 30 of lane 0 for k = 0): one
+//           shuffle per component, no second trip through shared memory; the
+//           bins m = k + 24 t < H/2 and H - m are formed together as in the
+//           three-pass kernel (lane 0 also owns m = H/2).
+// ---------------------------------------------------------------------------
+template <int H, int R0, int R1>
+__global__ void __launch_bounds__(256, 2)
+    zonal_spectrum_2pass_kernel(const SpecParams P) {
+  static_assert(R0 * R1 == H, "radices must factor H");
+  static_assert(R0 <= 32 && R1 <= 32 && R0 % 2 == 0 && R1 % 2 == 0,
+                "one butterfly per lane in both passes");
+  extern __shared__ __align__(16) unsigned char spec_smem[];
+  constexpr int N = 2 * H;
+  constexpr int B0 = R1;          // butterflies (lanes) of pass 1
+  constexpr int B1 = R0;          // butterflies (lanes) of pass 2
+  constexpr int kPitch = R0 + 1;  // odd: conflict-free scatter of pass 1
+  constexpr int kHalfT = R1 / 2;  // registers t < kHalfT hold the bins < H/2
+  float2* tw = reinterpret_cast<float2*>(spec_smem);   // [B1][R1 - 1]
+  float2* twn = tw + B1 * (R1 - 1);                    // exp(-2 pi i k / N), k <= H/2
+  float2* bufs = twn + (H / 2 + 2);                    // [rows][B0 * kPitch]
+  const int group = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int q = threadIdx.x; q < B1 * (R1 - 1); q += blockDim.x) {
+    const int k = q / (R1 - 1), t = q - k * (R1 - 1) + 1;
+    double sn, cs;
+    sincospi(2.0 * (t * k) / H, &sn, &cs);
+    tw[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+  }
+  for (int q = threadIdx.x; q <= H / 2; q += blockDim.x) {
+    double sn, cs;
+    sincospi(2.0 * q / N, &sn, &cs);
+    twn[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
+  }
+  __syncthreads();
+  float2* a = bufs + static_cast<size_t>(group) * (B0 * kPitch);
+  constexpr float inv_4n2 =
+      0.25f / (static_cast<float>(N) * static_cast<float>(N));
+  const long long rows_per_iter = static_cast<long long>(gridDim.x) * P.rows;
+  float2 pre[R0];
+  auto prefetch = [&](long long r) {
+    const long long job = r / P.ny;
+    const int y = static_cast<int>(r - job * P.ny);
+    const float2* rp = reinterpret_cast<const float2*>(
+                           reinterpret_cast<const float*>(__ldg(P.field + job)) +
+                           static_cast<long long>(y) * N) + lane;
+    if (lane < B0) {
+#pragma unroll
+      for (int t = 0; t < R0; ++t) pre[t] = ldg_stream_f2(rp + t * B0);
+    }
+  };
+  const int src = (2 * B1 - lane) % B1;  // partner lane of the split
+  long long row = static_cast<long long>(blockIdx.x) * P.rows + group;
+  if (row < P.n_rows) prefetch(row);
+  for (; row < P.n_rows; row += rows_per_iter) {
+    const int y = static_cast<int>(row % P.ny);
+    __syncwarp();  // the previous row's readers of `a` are done
+    if (lane < B0) {
+      dft<R0>(pre);
+#pragma unroll
+      for (int t = 0; t < R0; ++t) a[lane * kPitch + t] = pre[t];
+    }
+    __syncwarp();
+    float2 z[R1];
+    if (lane < B1) {
+#pragma unroll
+      for (int t = 0; t < R1; ++t) z[t] = a[t * kPitch + lane];
+      const float2* tk = tw + lane * (R1 - 1) - 1;
+#pragma unroll
+      for (int t = 1; t < R1; ++t) z[t] = cmul(z[t], tk[t]);
+      dft<R1>(z);
+    } else {
+#pragma unroll
+      for (int t = 0; t < R1; ++t) z[t] = make_float2(0.f, 0.f);
+    }
+    // the next row's operands travel while this one is split and stored
+    if (row + rows_per_iter < P.n_rows) prefetch(row + rows_per_iter);
+    const float scale =
+        (P.row_scale ? static_cast<float>(__ldg(P.row_scale + y)) : 1.0f) *
+        inv_4n2;
+    const float two = 2.0f * scale;
+    float* dst = P.out + row * static_cast<long long>(H + 1);
+    // idle lanes (>= B1) run the arithmetic on lane 0's indices and store
+    // nothing: predicated stores instead of a divergent region per register
+    const bool owner = lane < B1;
+    const int lk = owner ? lane : 0;
+    auto emit = [&](const int m, const float2 zk, const float2 zc,
+                    const bool store) {
+      const float2 e = make_float2(zk.x + zc.x, zk.y - zc.y);  // Z[m] + conj Z[H-m]
+      const float2 o = make_float2(zk.x - zc.x, zk.y + zc.y);  // Z[m] - conj Z[H-m]
+      const float2 pw = cmul(twn[m], o);
+      const float ar = e.x + pw.y, ai = e.y - pw.x;            // 2 X[m]
+      const float br = e.x - pw.y, bi = e.y + pw.x;            // 2 conj X[H-m]
+      const float lo = (m == 0 ? scale : two) * (ar * ar + ai * ai);
+      const float hi = two * (br * br + bi * bi);
+      if (store) {
+        dst[m] = lo;
+        dst[H - m] = hi;
+      }
+    };
+#pragma unroll
+    for (int t = 0; t < kHalfT; ++t) {
+      const float2 give = (lane == 0) ? z[(R1 - t) % R1] : z[R1 - 1 - t];
+      float2 zc;
+      zc.x = __shfl_sync(0xffffffffu, give.x, src);
+      zc.y = __shfl_sync(0xffffffffu, give.y, src);
+      emit(lk + B1 * t, z[t], zc, owner);
+    }
+    emit(H / 2, z[kHalfT], z[kHalfT], lane == 0);  // its own partner
   }
 }
 
@@ -628,7 +928,54 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
     return warp_rows && H == h && P.radix[0] == r0 && P.radix[1] == r1 &&
            P.radix[2] == r2;
   };
-  if (is(720, 9, 10, 8)) {
+  // The operational grids: radices chosen for the warp-per-row kernel, not by
+  // factorise() (whose "few large passes" rule serves the generic kernel).
+  const bool fixed2_ok = H == 720 || H == 360;
+  const char* which = getenv("WBX_SPECTRUM_KERNEL");  // experiments only
+  const bool want_old = which && !strcmp(which, "fixed");
+  const bool want_3pass = which && !strcmp(which, "fixed2");
+  if (H == 720 && !want_old && !want_3pass) {
+    constexpr int kR0 = 24, kR1 = 30;
+    const int rows2 = 8, threads2 = rows2 * 32;
+    const size_t smem2 = (static_cast<size_t>(kR0) * (kR1 - 1) + (H / 2 + 2) +
+                          static_cast<size_t>(rows2) * kR1 * (kR0 + 1)) *
+                         sizeof(float2);
+    P.rows = rows2;
+    P.gsize = 32;
+    const long long want2 = (P.n_rows + rows2 - 1) / rows2;
+    const int grid2 = static_cast<int>(std::max(
+        1ll, std::min<long long>(want2, ctx->sm_count * 2ll)));
+    auto kern = zonal_spectrum_2pass_kernel<720, kR0, kR1>;
+    WBX_CUDA(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(smem2)));
+    kern<<<grid2, threads2, smem2, ctx->stream>>>(P);
+  } else if (fixed2_ok && !want_old) {
+    const int rows2 = 8, threads2 = rows2 * 32;
+    const int r0 = 5, r1 = H == 720 ? 12 : 6, r2 = 12;
+    const int q1 = r0 * r1 + (((r0 - r0 * r1) % 16) + 16) % 16;
+    const size_t smem2 = (static_cast<size_t>(H) + (H / 2 + 2) +
+                          static_cast<size_t>(rows2) * (H + r2 * q1)) *
+                         sizeof(float2);
+    P.rows = rows2;
+    P.gsize = 32;
+    const long long want2 = (P.n_rows + rows2 - 1) / rows2;
+    const int grid2 = static_cast<int>(std::max(
+        1ll, std::min<long long>(want2, ctx->sm_count * 2ll)));
+    if (H == 720) {
+      auto kern = zonal_spectrum_fixed2_kernel<720, 5, 12, 12>;
+      WBX_CUDA(cudaFuncSetAttribute(
+          kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          static_cast<int>(smem2)));
+      kern<<<grid2, threads2, smem2, ctx->stream>>>(P);
+    } else {
+      auto kern = zonal_spectrum_fixed2_kernel<360, 5, 6, 12>;
+      WBX_CUDA(cudaFuncSetAttribute(
+          kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          static_cast<int>(smem2)));
+      kern<<<grid2, threads2, smem2, ctx->stream>>>(P);
+    }
+  } else if (is(720, 9, 10, 8)) {
     auto kern = zonal_spectrum_fixed_kernel<720, 9, 10, 8>;
     WBX_CUDA(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
