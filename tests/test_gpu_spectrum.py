@@ -49,6 +49,31 @@ def test_matches_numpy_rfft(nlon):
   _close(s.values.astype(np.float64), oracle.zonal_energy_spectrum(f, lat))
 
 
+@pytest.mark.parametrize('kernel', ['default', 'fixed2', 'fixed'])
+@pytest.mark.parametrize('nlat,nlon', [(721, 1440), (361, 720)])
+def test_fixed_shape_kernels_on_many_rows(nlat, nlon, kernel, monkeypatch):
+  """The operational grids run compile-time-shaped kernels (spectrum.cu: the
+  two-pass 24 x 30 kernel for N = 1440, the three-pass (5, 6, 12) one for
+  N = 720; WBX_SPECTRUM_KERNEL selects the older variants).  More rows than one
+  sweep of the persistent grid (148 SMs x 2 CTAs x 8 rows), several slabs, every
+  row against numpy.fft."""
+  if kernel == 'default':
+    monkeypatch.delenv('WBX_SPECTRUM_KERNEL', raising=False)
+  else:
+    monkeypatch.setenv('WBX_SPECTRUM_KERNEL', kernel)
+  n_fields = 4 if nlat == 721 else 7
+  assert n_fields * nlat > 148 * 2 * 8
+  lat = np.linspace(-90, 90, nlat)
+  f = _field((n_fields,), nlat, nlon, seed=nlat + len(kernel))
+  da = xl.DataArray(f, ('level', 'latitude', 'longitude'),
+                    coords={'latitude': lat,
+                            'longitude': np.arange(nlon) * 360.0 / nlon},
+                    name='u')
+  s = spectral.zonal_energy_spectrum(da)
+  assert s.shape == (n_fields, nlat, nlon // 2 + 1)
+  _close(s.values.astype(np.float64), oracle.zonal_energy_spectrum(f, lat))
+
+
 def test_unsupported_lengths_raise():
   da = xl.DataArray(np.zeros((3, 14), np.float32), ('latitude', 'longitude'),
                     coords={'latitude': [-10.0, 0.0, 10.0]})
