@@ -747,6 +747,8 @@ __global__ void __launch_bounds__(kCrpsThreads, MINB)
     if (tid < len) {
       const unsigned e = static_cast<unsigned>(e0 + tid);
       const float* src = ea + static_cast<long long>(e) * P.point_stride;
+      // (one mad.wide.u32 per member address instead of nvcc's chains of
+      // 64-bit adds was measured SLOWER: 1.044 -> 1.095 ms, GPU call 31)
       float x[MAXM];
 #pragma unroll
       for (int m = 0; m < MAXM; ++m)
