@@ -566,6 +566,20 @@ def run_suite(ctx, dev, peak, oos_legs=False):
                    'fp32_tflops': pts * flops / (kms * 1e-3) / 1e12,
                    'note': 'at the FP32-issue / HBM ridge: ~2.5 kFLOP per '
                            '204 B point (SURVEY.md 8d)'}}
+  # the same call under the default kernel policy: what a user of the
+  # reference's default CRPSEnsemble() (use_sort=False) gets -- both
+  # estimators are one statistic (probabilistic.py:190-192), so member-major
+  # ensembles of up to 64 members run the sorting network either way
+  ms, kms, kn = timed(step, 3)
+  out['crps_c3_default_policy'] = {
+      'workload': 'CRPSEnsemble() exactly as crps_c3 but with the default '
+                  'engine.CRPS_KERNEL="auto" (sorting network for M <= 64)',
+      'value': pts / (ms * 1e-3), 'unit': 'grid-points/s', 'ms_per_step': ms,
+      'kernel_ms_per_step': kms, 'launches_per_step': int(kn),
+      'roofline': {'bound': 'hbm', 'achieved': pts * bpp / (kms * 1e-3) / 1e9,
+                   'peak': peak, 'unit': 'GB/s',
+                   'frac': pts * bpp / (kms * 1e-3) / 1e9 / peak,
+                   'algorithmic_bytes_per_point': bpp}}
   metrics = {'crps': probabilistic.CRPSEnsemble(use_sort=True)}
   step = lambda: aggregation.compute_metric_values_for_single_chunk(  # noqa: E731
       metrics, aggregator, preds, tgts)
