@@ -594,7 +594,8 @@ WBX_FIXED_SORT(51)
 
 // Skill, spread (sort / PWM estimator) and the optional moments of one grid
 // point whose members are in x[0 .. M) (x is sorted in place).
-template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MOMENTS, int MIXPCT>
+template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MOMENTS, int MIXPCT,
+          bool CRPS = true>
 __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
                                            const int M, const int fair,
                                            float (&v)[kCrpsStats]) {
@@ -657,6 +658,7 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
     v[2] = __fdiv_rn(ss, fnm - 1.f);
     v[3] = __fsub_rn(__fmul_rn(mean - y, mean - y), __fdiv_rn(v[2], fnm));
   }
+  if constexpr (!CRPS) return;  // moments only: nothing to sort
   const int n = ENS_SKIPNA ? (M - n_nan) : M;
   float sp = 0.f;
   if constexpr (kSplit) {
@@ -708,8 +710,11 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
 // MFIX > 0 fixes the member count at compile time: the +inf padding lanes
 // become constants, ptxas folds every compare-exchange that touches them and
 // the network shrinks to the size of the real ensemble (M = 50: 64 -> 50 wires).
+// CRPS = false: the moments alone (variance, unbiased MSE) from the same
+// register-resident members, no network -- an HBM-bound stream of 51 loads and
+// ~250 FP32 instructions per point.
 template <int MAXM, int MFIX, bool ENS_SKIPNA, bool MASK, bool MOMENTS,
-          int MINB = 1, int MIXPCT = -1>
+          int MINB = 1, int MIXPCT = -1, bool CRPS = true>
 __global__ void __launch_bounds__(kCrpsThreads, MINB)
     crps_sort_kernel(const CrpsParams P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -757,7 +762,8 @@ __global__ void __launch_bounds__(kCrpsThreads, MINB)
                        : inf;
       const float y = ldg_stream_f1(ta + e);
       float v[kCrpsStats];
-      sort_point<MAXM, MFIX, ENS_SKIPNA, MOMENTS, MIXPCT>(x, y, M, P.fair, v);
+      sort_point<MAXM, MFIX, ENS_SKIPNA, MOMENTS, MIXPCT, CRPS>(x, y, M, P.fair,
+                                                                v);
       crps_store_fields(P, job, e, v);
       const unsigned yy = e / static_cast<unsigned>(P.nx);
       const unsigned xx = e - yy * static_cast<unsigned>(P.nx);
@@ -1019,9 +1025,25 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
       crps_sort_kernel<MAXM, MFIX, false, false, MOM, kMinB, kMix>             \
           <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
   } while (0)
+#define WBX_MOMENTS_LAUNCH(MAXM, MFIX)                                         \
+  do {                                                                         \
+    if (ens_skipna && plan->has_mask)                                          \
+      crps_sort_kernel<MAXM, MFIX, true, true, true, 1, -1, false>             \
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+    else if (ens_skipna)                                                       \
+      crps_sort_kernel<MAXM, MFIX, true, false, true, 1, -1, false>            \
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+    else if (plan->has_mask)                                                   \
+      crps_sort_kernel<MAXM, MFIX, false, true, true, 1, -1, false>            \
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+    else                                                                       \
+      crps_sort_kernel<MAXM, MFIX, false, false, true, 1, -1, false>           \
+          <<<grid, kCrpsThreads, 0, ctx->stream>>>(P);                         \
+  } while (0)
 #define WBX_SORT_LAUNCH(MAXM, MFIX)                                            \
   do {                                                                         \
-    if (what & kWantMoments) WBX_SORT_LAUNCH2(MAXM, MFIX, true);               \
+    if (!(what & kWantCrps)) WBX_MOMENTS_LAUNCH(MAXM, MFIX);                   \
+    else if (what & kWantMoments) WBX_SORT_LAUNCH2(MAXM, MFIX, true);          \
     else WBX_SORT_LAUNCH2(MAXM, MFIX, false);                                  \
   } while (0)
     // the common operational ensemble sizes get a pruned network
@@ -1032,6 +1054,7 @@ static int crps_launch(wbx_ctx* ctx, const wbx_crps_plan* plan,
     else if (plan->n_members <= 32) WBX_SORT_LAUNCH(32, 0);
     else WBX_SORT_LAUNCH(64, 0);
 #undef WBX_SORT_LAUNCH
+#undef WBX_MOMENTS_LAUNCH
 #undef WBX_SORT_LAUNCH2
     WBX_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -1260,10 +1283,11 @@ int wbx_crps_plan_create(wbx_ctx* ctx, const wbx_crps_desc* d,
   p->smem_plain = p->smem_bytes;
   p->what = ((stat_mask & 3) ? wbx::kWantCrps : 0) |
             ((stat_mask & 12) ? wbx::kWantMoments : 0);
-  // moments alone need no sorted sample: the (then HBM-bound) pair-kernel
-  // skeleton serves them.
-  p->use_sort = (d->flags & WBX_CRPS_USE_SORT) != 0 && d->n_members <= 64 &&
-                (p->what & wbx::kWantCrps);
+  // register-resident members (n_members <= 64): the sorting network for the
+  // CRPS statistics, the same skeleton without the network for moments alone
+  // (0.734 ms per 20.8 M points at M = 50 = 0.88 of HBM peak; the pair-kernel
+  // skeleton that served them before: 0.828 ms, profiles/exp_crps_r2_call34.log)
+  p->use_sort = (d->flags & WBX_CRPS_USE_SORT) != 0 && d->n_members <= 64;
   {
     // TMA variant: member-major rows, everything 16-byte aligned.
     const size_t stage =
