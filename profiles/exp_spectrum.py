@@ -5,11 +5,12 @@ of rows -- PARITY UNPINNED (no spectrum exists in the reference):
 
     python profiles/exp_spectrum.py [steps]
 
-WBX_SPECTRUM_KERNEL (experiments only) selects the kernel: "fixed" = the first
-fixed-shape kernel ((9, 10, 8) / (9, 10, 4) radices, row staged through shared
-memory), "fixed2" = three passes (5, 12 | 6, 12) with the first pass from
-registers and the paired split, unset = the library's choice (N = 1440: the
-two-pass 24 x 30 kernel; N = 720: fixed2)."""
+WBX_SPECTRUM_KERNEL selects the kernel: "generic" = the runtime-shaped kernel,
+"fixed2" = three passes (5, 12 | 6, 12) with the first pass from registers and
+the paired split, unset = the library's choice (N = 1440: the two-pass 24 x 30
+kernel; N = 720: fixed2).  GPU calls 28 / 30 of round 2 also ran "fixed", the
+round-1 fixed-shape kernel ((9, 10, 8) radices, row staged through shared
+memory: 0.178 ms), which has been removed since."""
 import json
 import os
 import sys
@@ -51,7 +52,7 @@ for nlat, nlon in ((721, 1440), (361, 720)):
     x = f[i, y].double().cpu().numpy()
     F = np.fft.rfft(x) / nlon
     ref[i, y] = np.abs(F) ** 2 * np.r_[1.0, 2.0 * np.ones(nlon // 2)]
-  for which in ('fixed', 'fixed2', None) * 2:
+  for which in ('generic', 'fixed2', None) * 2:
     if which:
       os.environ['WBX_SPECTRUM_KERNEL'] = which
     else:

@@ -49,12 +49,13 @@ def test_matches_numpy_rfft(nlon):
   _close(s.values.astype(np.float64), oracle.zonal_energy_spectrum(f, lat))
 
 
-@pytest.mark.parametrize('kernel', ['default', 'fixed2', 'fixed'])
+@pytest.mark.parametrize('kernel', ['default', 'fixed2', 'generic'])
 @pytest.mark.parametrize('nlat,nlon', [(721, 1440), (361, 720)])
 def test_fixed_shape_kernels_on_many_rows(nlat, nlon, kernel, monkeypatch):
   """The operational grids run compile-time-shaped kernels (spectrum.cu: the
   two-pass 24 x 30 kernel for N = 1440, the three-pass (5, 6, 12) one for
-  N = 720; WBX_SPECTRUM_KERNEL selects the older variants).  More rows than one
+  N = 720; WBX_SPECTRUM_KERNEL selects the three-pass kernel for N = 1440 too,
+  or the runtime-shaped generic kernel).  More rows than one
   sweep of the persistent grid (148 SMs x 2 CTAs x 8 rows), several slabs, every
   row against numpy.fft."""
   if kernel == 'default':

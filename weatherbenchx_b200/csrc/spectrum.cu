@@ -408,12 +408,14 @@ __global__ void __launch_bounds__(512)
 }
 
 // ---------------------------------------------------------------------------
-// Fixed-shape variant: H and the three radices are compile-time constants, one
-// warp per row, no padding.  Every index of the Stockham passes (q = j / Ns,
+// Fixed-shape variants: H and the radices are compile-time constants, one warp
+// per row, no padding.  Every index of the Stockham passes (q = j / Ns,
 // k = j % Ns, the twiddle stride, the scatter base) folds into constants or
 // shift/multiply sequences and the butterfly loops unroll; about two thirds of
-// the generic kernel's instructions were this address arithmetic.  Serves the
-// operational grids (0.25 deg: N = 1440 = 2 * 9 * 10 * 8; 0.5 deg: N = 720).
+// the generic kernel's instructions were this address arithmetic.  They serve
+// the operational grids (0.25 deg: N = 1440, 0.5 deg: N = 720).  The first
+// such kernel (round 1: radices (9, 10, 8), row staged through shared memory,
+// 0.178 ms per C4 step) was replaced by the two below and is gone.
 // ---------------------------------------------------------------------------
 // IN_T: distance between the R operands of a butterfly in `in` (H / R unless
 // the producer padded its output); OUT_Q: distance between consecutive output
@@ -448,117 +450,10 @@ __device__ __forceinline__ void stockham_pass_fixed(
   }
 }
 
-template <int H, int R0, int R1, int R2>
-__global__ void __launch_bounds__(256)
-    zonal_spectrum_fixed_kernel(const SpecParams P) {
-  static_assert(R0 * R1 * R2 == H, "radices must factor H");
-  static_assert(H % 2 == 0, "float4 row copies");
-  extern __shared__ __align__(16) unsigned char spec_smem[];
-  constexpr int Hp = H + 2;
-  constexpr int N = 2 * H;
-  // per-pass twiddle tables [k][t-1] (R0*(R1-1) + R0*R1*(R2-1) = H - R0 entries)
-  float2* tw1 = reinterpret_cast<float2*>(spec_smem);  // exp(-2 pi i t k / (R0 R1))
-  float2* tw2 = tw1 + R0 * (R1 - 1);                   // exp(-2 pi i t k / H)
-  float2* twn = tw1 + H;                               // exp(-2 pi i k / N), k <= H
-  float2* bufs = twn + (H + 2);                        // [rows][2][Hp]
-  const int group = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  for (int q = threadIdx.x; q < R0 * (R1 - 1); q += blockDim.x) {
-    const int k = q / (R1 - 1), t = q - k * (R1 - 1) + 1;
-    double sn, cs;
-    sincospi(2.0 * (t * k) / (R0 * R1), &sn, &cs);
-    tw1[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
-  }
-  for (int q = threadIdx.x; q < R0 * R1 * (R2 - 1); q += blockDim.x) {
-    const int k = q / (R2 - 1), t = q - k * (R2 - 1) + 1;
-    double sn, cs;
-    sincospi(2.0 * (t * k) / H, &sn, &cs);
-    tw2[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
-  }
-  for (int q = threadIdx.x; q <= H; q += blockDim.x) {
-    double sn, cs;
-    sincospi(2.0 * q / N, &sn, &cs);
-    twn[q] = make_float2(static_cast<float>(cs), static_cast<float>(-sn));
-  }
-  __syncthreads();
-  float2* a = bufs + static_cast<size_t>(group) * 2 * Hp;
-  float2* b = a + Hp;
-  constexpr float inv_n2 = 1.0f / (static_cast<float>(N) * static_cast<float>(N));
-  const long long rows_per_iter = static_cast<long long>(gridDim.x) * P.rows;
-  constexpr int nvec = H >> 1;                 // float4 per row
-  constexpr int kPre = (nvec + 31) / 32;       // per lane
-  float4 pre[kPre];
-  bool pre_valid = false;
-  auto row_pointer = [&](long long r, int* y_out) {
-    const long long job = r / P.ny;
-    const int y = static_cast<int>(r - job * P.ny);
-    *y_out = y;
-    return reinterpret_cast<const float*>(__ldg(P.field + job)) +
-           static_cast<long long>(y) * N;
-  };
-  auto prefetch = [&](long long r) {
-    int yy;
-    const float* rp = row_pointer(r, &yy);
-    pre_valid = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
-    if (pre_valid) {
-#pragma unroll
-      for (int i = 0; i < kPre; ++i) {
-        const int n = lane + i * 32;
-        if (n < nvec) pre[i] = ldg_stream_f4(rp + 4 * n);
-      }
-    }
-  };
-  long long row = static_cast<long long>(blockIdx.x) * P.rows + group;
-  if (row < P.n_rows) prefetch(row);
-  for (; row < P.n_rows; row += rows_per_iter) {
-    int y;
-    const float* rowp = row_pointer(row, &y);
-    __syncwarp();  // the previous row's readers are done
-    if (pre_valid) {
-      float4* a4 = reinterpret_cast<float4*>(a);
-#pragma unroll
-      for (int i = 0; i < kPre; ++i) {
-        const int n = lane + i * 32;
-        if (n < nvec) a4[n] = pre[i];
-      }
-    } else {
-      const float2* s2 = reinterpret_cast<const float2*>(rowp);
-      for (int n = lane; n < H; n += 32) a[n] = __ldg(s2 + n);
-    }
-    if (row + rows_per_iter < P.n_rows) prefetch(row + rows_per_iter);
-    __syncwarp();
-    stockham_pass_fixed<R0, H, 1>(a, b, tw1, lane);
-    __syncwarp();
-    stockham_pass_fixed<R1, H, R0>(b, a, tw1, lane);
-    __syncwarp();
-    stockham_pass_fixed<R2, H, R0 * R1>(a, b, tw2, lane);
-    __syncwarp();
-    const float2* in = b;  // Z[0..H-1]
-    const float scale =
-        (P.row_scale ? static_cast<float>(__ldg(P.row_scale + y)) : 1.0f) *
-        inv_n2;
-    float* dst = P.out + row * static_cast<long long>(H + 1);
-#pragma unroll 4
-    for (int k = lane; k <= H; k += 32) {
-      const int ek = (k == H) ? 0 : k;
-      const int ec = (k == 0 || k == H) ? 0 : H - k;
-      const float2 zk = in[ek];
-      const float2 zc = in[ec];
-      const float2 zr = make_float2(zc.x, -zc.y);  // conj Z[H-k]
-      const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y + zr.y));
-      const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y - zr.y));
-      const float2 wo = cmul(twn[k], o);
-      const float xr = e.x + wo.y;  // X = e - i * wo
-      const float xi = e.y - wo.x;
-      const float factor = (k == 0) ? 1.0f : 2.0f;
-      dst[k] = factor * scale * (xr * xr + xi * xi);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------
-// Second fixed-shape variant (the one the operational grids run): radices
-// (5, 12, 12) for H = 720 and (5, 6, 12) for H = 360.
+// Three-pass fixed-shape kernel: radices (5, 6, 12) for H = 360 (what N = 720
+// runs) and (5, 12, 12) for H = 720 (kept selectable, WBX_SPECTRUM_KERNEL=fixed2,
+// as the cross-check of the two-pass kernel in the tests).
 //  * the butterfly counts 144 / 60 / 60 fill 5 / 2 / 2 warp iterations to
 //    90-94 % (80 / 72 / 90 of the (9, 10, 8) split filled 3 each to 75-94 %),
 //    and the prime-factor 12- and 6-point butterflies need no inner twiddles;
@@ -922,19 +817,15 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
       std::max(1ll, std::min<long long>(want, ctx->sm_count * ctas_per_sm)));
   int prc = ctx->prof_begin();
   if (prc != WBX_OK) return prc;
-  const bool warp_rows = P.gsize == 32 && !P.pad && P.n_passes == 3 &&
-                         threads <= 256;
-  auto is = [&](int h, int r0, int r1, int r2) {
-    return warp_rows && H == h && P.radix[0] == r0 && P.radix[1] == r1 &&
-           P.radix[2] == r2;
-  };
   // The operational grids: radices chosen for the warp-per-row kernel, not by
   // factorise() (whose "few large passes" rule serves the generic kernel).
   const bool fixed2_ok = H == 720 || H == 360;
-  const char* which = getenv("WBX_SPECTRUM_KERNEL");  // experiments only
-  const bool want_old = which && !strcmp(which, "fixed");
+  // WBX_SPECTRUM_KERNEL (debugging / tests): "fixed2" = the three-pass kernel
+  // for N = 1440 too, "generic" = the runtime-shaped kernel for every N
+  const char* which = getenv("WBX_SPECTRUM_KERNEL");
+  const bool want_generic = which && !strcmp(which, "generic");
   const bool want_3pass = which && !strcmp(which, "fixed2");
-  if (H == 720 && !want_old && !want_3pass) {
+  if (H == 720 && !want_generic && !want_3pass) {
     constexpr int kR0 = 24, kR1 = 30;
     const int rows2 = 8, threads2 = rows2 * 32;
     const size_t smem2 = (static_cast<size_t>(kR0) * (kR1 - 1) + (H / 2 + 2) +
@@ -950,7 +841,7 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
         static_cast<int>(smem2)));
     kern<<<grid2, threads2, smem2, ctx->stream>>>(P);
-  } else if (fixed2_ok && !want_old) {
+  } else if (fixed2_ok && !want_generic) {
     const int rows2 = 8, threads2 = rows2 * 32;
     const int r0 = 5, r1 = H == 720 ? 12 : 6, r2 = 12;
     const int q1 = r0 * r1 + (((r0 - r0 * r1) % 16) + 16) % 16;
@@ -975,18 +866,6 @@ extern "C" int wbx_zonal_spectrum(wbx_ctx* ctx, const wbx_spectrum_desc* d) {
           static_cast<int>(smem2)));
       kern<<<grid2, threads2, smem2, ctx->stream>>>(P);
     }
-  } else if (is(720, 9, 10, 8)) {
-    auto kern = zonal_spectrum_fixed_kernel<720, 9, 10, 8>;
-    WBX_CUDA(cudaFuncSetAttribute(
-        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        static_cast<int>(smem)));
-    kern<<<grid, threads, smem, ctx->stream>>>(P);
-  } else if (is(360, 9, 10, 4)) {
-    auto kern = zonal_spectrum_fixed_kernel<360, 9, 10, 4>;
-    WBX_CUDA(cudaFuncSetAttribute(
-        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        static_cast<int>(smem)));
-    kern<<<grid, threads, smem, ctx->stream>>>(P);
   } else {
     zonal_spectrum_kernel<<<grid, threads, smem, ctx->stream>>>(P);
   }
