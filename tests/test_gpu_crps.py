@@ -231,11 +231,12 @@ def test_sort_and_pair_kernels_agree_with_nans(members):
 @pytest.mark.parametrize('moments', [False, True])
 @pytest.mark.parametrize('members', [50, 51])
 def test_fixed_size_sort_kernel_edge_points(members, moments):
-  """The fixed-size networks sort x_m - y (crps.cu, kSplit) and fold their last
-  layer into the moment: per-point fields against the oracle where that shift
-  is not usable (NaN / infinite targets, a masked row of the analysis), with a
-  NaN member, one infinite member, identical members (spread exactly zero, as
-  the reference's float64 sum gives) and a field far from zero."""
+  """The fixed-size networks sort x_m - x_0 (crps.cu, kSplit), fold their last
+  layer into the moment and take the skill sum as the NaN detector: per-point
+  fields against the oracle with NaN / infinite targets, a masked row of the
+  analysis, a target 1e5 spreads away from the ensemble, a NaN member, one
+  infinite member, identical members (spread exactly zero, as the reference's
+  float64 sum gives) and a field far from zero."""
   import torch
   rng = np.random.default_rng(members)
   n_init, ny, nx = 2, 16, 64
@@ -249,6 +250,7 @@ def test_fixed_size_sort_kernel_edge_points(members, moments):
   y[0, 5, 5] = np.inf
   y[0, 5, 6] = -np.inf
   y[1, 6, :] = np.nan
+  y[1, 10, :] += np.float32(3e7)
   xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
   with np.errstate(invalid='ignore'):
     want = [oracle.crps_skill(x, y, 1), oracle.crps_spread(x, 1, fair=True),

@@ -518,9 +518,10 @@ struct FixedSort {
 //      members give a spread of exactly zero, as the reference's float64 sum;
 //  (2) MIXPCT per cent of the remaining compare-exchanges compute their
 //      maximum as (a + b) - min(a, b): one FMNMX + two FADD.  The members are
-//      centred on the first one beforehand, so the rounding of a + b is
-//      relative to the ensemble's range, not to the field's magnitude
-//      (measured: no change of the spread above 1e-8 relative at 100 %).
+//      shifted by the first one beforehand, so the rounding of a + b is
+//      relative to the ensemble's range, not to the field's magnitude or the
+//      forecast error (measured: no change of the spread above 1e-8 relative
+//      at 100 %).
 constexpr int kSortMixPct = 45;     // measured: 30 / 35 / 40 / 45 / 50 within 1 %
 constexpr int kSortFixedCtas = 4;   // resident CTAs per SM asked of ptxas (128 reg.)
 __host__ __device__ constexpr bool sort_ce_mixed(const int index,
@@ -609,10 +610,10 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
   // every term is >= 0, and +-inf members stay inf), and a NaN member only
   // has to turn skill and spread into NaN at the end.
   constexpr bool kCheapNan = !ENS_SKIPNA && FixedSort<MFIX>::kAvailable;
-  // kSplit: the differences x_m - y that the skill needs anyway are what gets
-  // sorted (the spread does not change under a shift, and the shift keeps the
+  // kSplit: the members are shifted by the first one before they are sorted
+  // (the spread does not change under a shift, and the shift keeps the
   // rounding of the FMA-pipe compare-exchanges relative to the ensemble's own
-  // scale); their absolute sum doubles as the NaN detector.
+  // range); the skill sum doubles as the NaN detector.
   constexpr bool kSplit = kCheapNan && MIXPCT >= 0;
   float sabs = 0.f;
 #pragma unroll
@@ -662,27 +663,31 @@ __device__ __forceinline__ void sort_point(float (&x)[MAXM], const float y,
   const int n = ENS_SKIPNA ? (M - n_nan) : M;
   float sp = 0.f;
   if constexpr (kSplit) {
-    // n == M == MFIX here.  A target that is not finite (masked analysis
-    // cells) cannot be the shift: the skill is summed on its own there and
-    // the first member is subtracted instead.
-    float c = y, sk_raw = 0.f;
-    const bool y_finite = fabsf(y) < inf;
-    if (!y_finite) {
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m) {
-        if (m < MFIX) sk_raw += fabsf(x[m] - y);
-      }
-      c = x[0];
-    }
+    // n == M == MFIX here.  The network runs on x_m - x_0: every operand of
+    // its FMA-pipe arithmetic is then bounded by the ensemble's own range
+    // whatever the field's magnitude or the forecast error is (any shift
+    // serves: the coefficients sum to zero).  The skill is summed from the
+    // raw members, as everywhere else; for a finite target it is NaN iff a
+    // member is (every term is >= 0), which saves a separate NaN sum.
+    const float c = x[0];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) {
       if (m < MFIX) {
+        sk += fabsf(x[m] - y);
         x[m] -= c;
-        sk += fabsf(x[m]);
       }
     }
-    n_nan = (sk == sk) ? 0 : 1;  // NaN member (every term is >= 0)
-    if (!y_finite) sk = sk_raw;
+    if (fabsf(y) < inf) {
+      n_nan = (sk == sk) ? 0 : 1;
+    } else {
+      // masked analysis cells: the skill is inf / NaN by itself
+      float s = 0.f;
+#pragma unroll
+      for (int m = 0; m < MAXM; ++m) {
+        if (m < MFIX) s += x[m];
+      }
+      n_nan = (s == s) ? 0 : 1;
+    }
     sp = FixedSort<MFIX>::template sorted_moment<MAXM, MIXPCT>(x);
   } else if constexpr (FixedSort<MFIX>::kAvailable) {
     FixedSort<MFIX>::template sort<MAXM>(x);
