@@ -13,13 +13,20 @@
 // mixed-radix Stockham autosort FFT ping-ponging between two shared-memory
 // buffers, and split into the N/2+1 real-FFT bins
 //   X[k] = (Z[k] + conj Z[H-k])/2 - i w_N^k (Z[k] - conj Z[H-k])/2 .
-// Radices 2,3,4,5 and the in-register composites 8, 9, 10, 16 keep N = 1440
-// (H = 720 = 10 * 9 * 8) at three passes.  Shared-memory indices are padded by
-// one complex per 16 (e + e/16) so that the strided Stockham scatter of the
-// early passes is bank-conflict free; (j / Ns, j % Ns) use host-computed magic
-// multipliers.  Twiddles come from shared-memory tables computed once per CTA
-// in double precision.  One group of `gsize` threads per row, several rows per
-// CTA, persistent grid; HBM traffic is 4 B/point in + 4 (N/2+1)/N B/point out.
+// Three kernels share this file:
+//  * zonal_spectrum_kernel: any N = 2 * 2^a 3^b 5^c up to 4096.  Radices 2, 3,
+//    4, 5 and the in-register composites 8, 9, 10, 16; shared-memory indices
+//    padded by one complex per 16 (e + e/16) so that the strided Stockham
+//    scatter of the early passes is bank-conflict free; (j / Ns, j % Ns) by
+//    host-computed magic multipliers; one group of `gsize` threads per row.
+//  * zonal_spectrum_fixed2_kernel<H, 5, R1, 12>: compile-time shapes, one warp
+//    per row, three passes with prime-factor 6- / 12-point butterflies, first
+//    pass straight from global memory (what N = 720 runs).
+//  * zonal_spectrum_2pass_kernel<720, 24, 30>: two passes, one round trip
+//    through shared memory, partner bins by warp shuffle (what N = 1440 runs).
+// Twiddles come from shared-memory tables computed once per CTA in double
+// precision.  Several rows per CTA, persistent grid; HBM traffic is
+// 4 B/point in + 4 (N/2+1)/N B/point out.
 #include <algorithm>
 #include <string.h>
 
