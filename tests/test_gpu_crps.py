@@ -337,6 +337,45 @@ def test_tma_staged_pair_kernel_equals_plain_one(masked):
                              rtol=1e-12)
 
 
+@pytest.mark.parametrize('stat_mask', [0b0011, 0b1111, 0b1100])
+@pytest.mark.parametrize('members', [50, 51, 20])
+def test_register_kernels_with_a_statistic_mask(members, stat_mask):
+  """The register-resident kernels (sorting network, fixed-size and generic;
+  moments alone without the network) under FLAG_MASKED, with latitude weights
+  and several slabs per cell, against the oracle."""
+  import torch
+  rng = np.random.default_rng(members + stat_mask)
+  n_init, ny, nx = 3, 48, 64
+  x = rng.normal(280, 3, size=(n_init, members, ny, nx)).astype(np.float32)
+  y = rng.normal(280, 3, size=(n_init, ny, nx)).astype(np.float32)
+  m = (rng.random((n_init, ny, nx)) > 0.2)
+  xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+  md = torch.from_numpy(m).cuda()
+  w = oracle.grid_area_weights(np.linspace(-90, 90, ny))
+  plan = _cabi.CrpsPlan(
+      _cabi.get_context(), space=_cabi.SPACE_DEVICE,
+      flags=_cabi.CRPS_FAIR | _cabi.CRPS_USE_SORT | _cabi.FLAG_MASKED,
+      ny=ny, nx=nx, n_members=members, member_stride=ny * nx, point_stride=1,
+      ens=np.array([xd.data_ptr() + i * members * ny * nx * 4
+                    for i in range(n_init)], np.uint64),
+      target=np.array([yd.data_ptr() + i * ny * nx * 4
+                       for i in range(n_init)], np.uint64),
+      mask=np.array([md.data_ptr() + i * ny * nx for i in range(n_init)],
+                    np.uint64),
+      cell=np.zeros(n_init, np.int32), n_cells=1, w_y=w, stat_mask=stat_mask)
+  ws, wsum = plan.run_to_host()
+  wm = w[None, :, None] * m
+  want = [(oracle.crps_skill(x, y, 1) * wm).sum(),
+          (oracle.crps_spread(x, 1, fair=True) * wm).sum(),
+          (oracle.ensemble_variance(x, 1) * wm).sum(),
+          (oracle.unbiased_ensemble_mean_squared_error(x, y, 1) * wm).sum()]
+  for k in range(4):
+    if stat_mask & (1 << k):
+      np.testing.assert_allclose(ws[0, k], want[k], rtol=RTOL,
+                                 atol=1e-3 if k == 3 else 0)
+      np.testing.assert_allclose(wsum[0, k], wm.sum(), rtol=1e-12)
+
+
 def test_pointwise_fields_match_oracle():
   rng = np.random.default_rng(0)
   x = rng.normal(size=(2, 5, 7, 6)).astype(np.float32)
