@@ -116,6 +116,16 @@ def make_inputs() -> dict:
   # an ensemble of targets (e.g. perturbed analyses), member-major
   out['y_ens'] = (out['y'][:, None] + rng.normal(
       0, 1.5, (len(INIT), N_TARGET_MEMBERS, NLAT, NLON))).astype(f32)
+  # operational ensemble sizes (member-major), appended LAST so that every
+  # array above keeps its values: the sizes the CRPS sort kernel has
+  # fixed-size networks for (crps.cu, MFIX = 50 / 51)
+  for m in (50, 51):
+    out[f'x{m}_major'] = (out['y'][:, None] + rng.normal(
+        0.3, 3, (len(INIT), m, NLAT, NLON))).astype(f32)
+  holes = np.zeros(out['x51_major'].shape, bool)
+  holes[:, 7] = rng.random((len(INIT), NLAT, NLON)) < 0.03   # one NaN member
+  holes[:, 50] = rng.random((len(INIT), NLAT, NLON)) < 0.02  # ... or two
+  out['member_holes51'] = holes
   return out
 
 
@@ -288,12 +298,15 @@ def build_cases(ns, inputs):
 
   def ens_case(name, x, use_metrics, reduce_dims=None, weighted=True,
                bins=None, layout='member_major', member_nan=False,
-               family='ens', nan_targets=False, **flags):
+               family='ens', nan_targets=False, x_key=None, holes_key=None,
+               **flags):
     reduce_dims = reduce_dims or RD
     spec = dict(family=family, reduce_dims=reduce_dims, weighted=weighted,
                 masked=flags.get('masked', False),
                 skipna=flags.get('skipna', False), bins=bins or [],
                 layout=layout, member_nan=member_nan, nan_targets=nan_targets)
+    if x_key:   # a member-major input other than x_last (50 / 51 members)
+      spec.update(x_key=x_key, holes_key=holes_key)
     aggregator = agg.Aggregator(
         reduce_dims=reduce_dims, weigh_by=area() if weighted else None,
         bin_by=_make_bins(ns, bins, inputs['ens_land']) if bins else None,
@@ -346,6 +359,34 @@ def build_cases(ns, inputs):
           det.RMSE(), [wrappers.EnsembleMean('predictions',
                                              ensemble_dim=ENS)])},
                  family='ens_mean')
+
+  # -- operational ensemble sizes: 50 and 51 members --------------------------
+  # (the sizes of the public benchmark's probabilistic suite,
+  #  run_benchmark_evaluation.py:341-357; in the product these run the
+  #  fixed-size sorting networks and the moments-only register kernel)
+  x50 = da(inputs['x50_major'], D_ENS_MAJOR, **{ENS: np.arange(50)})
+  x51 = da(inputs['x51_major'], D_ENS_MAJOR, **{ENS: np.arange(51)})
+  x51_nan = da(with_nan(inputs['x51_major'], inputs['member_holes51']),
+               D_ENS_MAJOR, **{ENS: np.arange(51)})
+  yield ens_case('ens50/all_metrics', x50, ens_metrics, x_key='x50_major')
+  yield ens_case('ens51/use_sort', x51, {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True,
+                                     use_sort=True)}, x_key='x51_major')
+  yield ens_case('ens50/moments_only', x50, {
+      'ens_var': prob.EnsembleRootMeanVariance(ensemble_dim=ENS),
+      'unbiased_rmse': prob.UnbiasedEnsembleMeanRMSE(ensemble_dim=ENS),
+      'unbiased_ssr': prob.UnbiasedSpreadSkillRatio(ensemble_dim=ENS)},
+                 x_key='x50_major')
+  yield ens_case('ens50/nan_targets_masked', x50, ens_metrics,
+                 nan_targets=True, masked=True, x_key='x50_major')
+  yield ens_case('ens51/nan_members_propagate', x51_nan, {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True)},
+                 reduce_dims=['latitude', 'longitude'], member_nan=True,
+                 x_key='x51_major', holes_key='member_holes51')
+  yield ens_case('ens50/regions', x50, {
+      'crps_fair': prob.CRPSEnsemble(ensemble_dim=ENS, fair=True),
+      'unbiased_ssr': prob.UnbiasedSpreadSkillRatio(ensemble_dim=ENS)},
+                 bins=['ens_regions_land'], x_key='x50_major')
 
   # -- categorical: thresholded contingency tables, error exceedance ---------
   # (categorical.py:25-101,345-635; wrappers.py:50-88,214-267;

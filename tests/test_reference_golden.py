@@ -1,6 +1,6 @@
 """Parity against vectors produced by the reference's own code.
 
-``tests/golden/reference_golden.npz`` holds, for 62 evaluation cases, the
+``tests/golden/reference_golden.npz`` holds, for 68 evaluation cases, the
 AggregationState (sum_weighted_statistics / sum_weights per statistic and
 variable) and the metric values that the UNMODIFIED modules of
 /root/reference/weatherbenchX returned in the build container
@@ -245,14 +245,17 @@ def _oracle_fields(spec, inputs):
     out[('WindVectorSquaredError_wind_vector', 'wind_vector')] = (
         se, cases.D3, None)
   else:
-    x = inputs['x_last']
+    member_major_input = bool(spec.get('x_key'))   # 50 / 51-member cases
+    x = inputs[spec.get('x_key') or 'x_last']
     if spec.get('member_nan'):
-      x = cases.with_nan(x, inputs['member_holes'])
+      x = cases.with_nan(x, inputs[spec.get('holes_key') or 'member_holes'])
     y, mask = inputs['y'], None
     if spec.get('nan_targets'):
       y = cases.with_nan(y, inputs['y_holes'])
       mask = ~inputs['y_holes']
-    if spec.get('layout', 'member_major') == 'member_major':
+    if member_major_input:
+      axis = 1
+    elif spec.get('layout', 'member_major') == 'member_major':
       x = np.ascontiguousarray(np.moveaxis(x, -1, 1))
       axis = 1
     else:
@@ -315,7 +318,7 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
     values, dims, mask = fields['skill'](case == 'ens/skipna_ensemble')
   elif stat.startswith('CRPSSpread_realization_'):
     values, dims, mask = fields['spread'](
-        '_fair_' in stat, case == 'ens/use_sort',
+        '_fair_' in stat, case.endswith('/use_sort'),
         case == 'ens/skipna_ensemble')
   else:
     values, dims, mask = fields[(stat, var)]
@@ -335,7 +338,7 @@ def _oracle_state(case, spec, fields, stat, var, inputs):
 
 def test_fixture_is_complete(golden):
   names = [str(n) for n in golden['cases']]
-  assert len(names) == 62 and len(set(names)) == 62
+  assert len(names) == 68 and len(set(names)) == 68
   for case in names:
     assert _case_keys(golden, case, 'sws'), case
     assert _case_keys(golden, case, 'value'), case
@@ -555,6 +558,9 @@ CASE_NAMES = [
     'ens/nan_targets_default', 'ens/nan_targets_masked',
     'ens/nan_targets_skipna', 'ens/regions_nan_targets_masked',
     'ens/ensemble_averaged_rmse', 'ens/ensemble_mean_rmse',
+    'ens50/all_metrics', 'ens51/use_sort', 'ens50/moments_only',
+    'ens50/nan_targets_masked', 'ens51/nan_members_propagate',
+    'ens50/regions',
     'cat/table_weighted', 'cat/table_unweighted_keep_init',
     'cat/table_nan_default', 'cat/table_nan_masked',
     'cat/table_nan_masked_nan_predictions', 'cat/table_nan_skipna',
@@ -643,7 +649,7 @@ def test_cuda_path_reproduces_reference(golden, inputs, case, space):
 # Cases whose host-space path needs device memory even before a kernel runs
 # (per-point fields of the CRPS launch, the EnsembleMean transform).
 NEEDS_DEVICE = {'ens/regions', 'ens/regions_nan_targets_masked',
-                'ens/ensemble_mean_rmse',
+                'ens50/regions', 'ens/ensemble_mean_rmse',
                 # region bins + thresholds: per-point fields, generic kernel
                 'cat/table_regions',
                 # NaN members: the exact route through the member-mean field
